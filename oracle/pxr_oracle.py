@@ -1,0 +1,371 @@
+"""CPU oracle for the full-catalogue scoring / ranking / metrics path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in ``pixelrec_multimodal_b200/`` may import
+this module; only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` do, and only as the
+checker / the CPU arm that is timed beside the GPU path.
+
+This is a plain-numpy restatement of the reference algorithm.  The arithmetic
+of the reference lives in third-party PyTorch (``torch>=2.2.1`` unpinned in the
+reference's ``setup.py:8``; CI pins 2.6.0; this container has 2.11.0), so the
+restatement is pinned by running the *reference module itself* in this
+container (stub identity backbones) and committing its outputs
+as ``tests/golden/*.npz`` (generator: ``oracle/make_golden.py``).  The
+reference's own known-answer tests for the metric formulas and the recommender
+ordering semantics are restated in ``tests/test_oracle_golden.py``.
+
+Every function cites the reference file:line it follows (paths relative to the
+reference root).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, List, Optional, Sequence, Set, Tuple
+
+import numpy as np
+
+try:  # erf for exact GELU (nn.GELU default, src/models/multimodal.py:160)
+    from scipy.special import erf as _erf
+except Exception:  # pragma: no cover - scipy is in the image
+    _erf = np.vectorize(math.erf)
+
+
+# --------------------------------------------------------------------------
+# elementary layers
+# --------------------------------------------------------------------------
+def activation(x: np.ndarray, name: str) -> np.ndarray:
+    """src/models/multimodal.py:150-167 (unknown names fall back to ReLU)."""
+    name = (name or "relu").lower()
+    if name == "gelu":
+        return 0.5 * x * (1.0 + _erf(x / math.sqrt(2.0)))
+    if name == "tanh":
+        return np.tanh(x)
+    if name == "leaky_relu":
+        return np.where(x >= 0, x, 0.01 * x)
+    if name == "silu":
+        return x / (1.0 + np.exp(-x))
+    return np.maximum(x, 0.0)
+
+
+def linear(x: np.ndarray, w: np.ndarray, b: Optional[np.ndarray]) -> np.ndarray:
+    y = x @ w.T
+    return y if b is None else y + b
+
+
+def _projection(x, sd, prefix, act, dt):
+    """src/models/multimodal.py:262-313: Linear->act->Dropout(id) or the
+    two-layer variant when ``projection_hidden_dim`` is set (keys .0 and .3)."""
+    y = activation(linear(x, sd[prefix + ".0.weight"].astype(dt), sd[prefix + ".0.bias"].astype(dt)), act)
+    if prefix + ".3.weight" in sd:
+        y = activation(linear(y, sd[prefix + ".3.weight"].astype(dt), sd[prefix + ".3.bias"].astype(dt)), act)
+    return y
+
+
+def modality_features(sd, act, user_idx, item_idx, tag_idx, vis=None, txt=None, num=None,
+                      dtype=np.float64) -> List[np.ndarray]:
+    """Feature list in the fixed order of src/models/multimodal.py:553-570."""
+    dt = dtype
+    feats = [sd["user_embedding.weight"].astype(dt)[user_idx],
+             sd["item_embedding.weight"].astype(dt)[item_idx],
+             sd["tag_embedding.weight"].astype(dt)[tag_idx]]
+    if vis is not None and "vision_projection.0.weight" in sd:
+        feats.append(_projection(vis.astype(dt), sd, "vision_projection", act, dt))
+    if txt is not None and "language_projection.0.weight" in sd:
+        feats.append(_projection(txt.astype(dt), sd, "language_projection", act, dt))
+    if num is not None and "numerical_projection.0.weight" in sd:
+        feats.append(_projection(num.astype(dt), sd, "numerical_projection", act, dt))
+    return feats
+
+
+def gated_fusion(sd, feats, dt):
+    """src/models/layers.py:195-225."""
+    cat = np.concatenate(feats, axis=1)
+    logits = linear(cat, sd["fusion_layer.gating_network.0.weight"].astype(dt),
+                    sd["fusion_layer.gating_network.0.bias"].astype(dt))
+    logits = logits - logits.max(axis=-1, keepdims=True)
+    g = np.exp(logits)
+    g /= g.sum(axis=-1, keepdims=True)
+    stack = np.stack(feats, axis=1)                    # (B, M, D)
+    return (stack * g[:, :, None]).sum(axis=1)
+
+
+def attention_fusion(sd, feats, num_heads, dt):
+    """src/models/layers.py:135-164 as documented (list -> stack dim 0 ->
+    nn.MultiheadAttention(batch_first=False) -> residual + LayerNorm(eps 1e-5)
+    -> mean over tokens).  The call at src/models/multimodal.py:513-519 hands a
+    tensor instead of a list and raises; SURVEY.md fact 3."""
+    x = np.stack(feats, axis=0)                         # (M, B, D)
+    M, B, D = x.shape
+    w_in = sd["fusion_layer.attention.in_proj_weight"].astype(dt)
+    b_in = sd["fusion_layer.attention.in_proj_bias"].astype(dt)
+    qkv = x @ w_in.T + b_in                             # (M, B, 3D)
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    dh = D // num_heads
+    q = q.reshape(M, B, num_heads, dh)
+    k = k.reshape(M, B, num_heads, dh)
+    v = v.reshape(M, B, num_heads, dh)
+    s = np.einsum("abhd,cbhd->bhac", q, k) / math.sqrt(dh)   # (B, h, M, M)
+    s = s - s.max(axis=-1, keepdims=True)
+    p = np.exp(s)
+    p /= p.sum(axis=-1, keepdims=True)
+    o = np.einsum("bhac,cbhd->abhd", p, v).reshape(M, B, D)
+    o = o @ sd["fusion_layer.attention.out_proj.weight"].astype(dt).T + \
+        sd["fusion_layer.attention.out_proj.bias"].astype(dt)
+    y = x + o
+    mu = y.mean(axis=-1, keepdims=True)
+    var = ((y - mu) ** 2).mean(axis=-1, keepdims=True)
+    z = (y - mu) / np.sqrt(var + 1e-5)
+    z = z * sd["fusion_layer.norm.weight"].astype(dt) + sd["fusion_layer.norm.bias"].astype(dt)
+    return z.mean(axis=0)
+
+
+def prediction_layout(sd, use_batch_norm: bool) -> Tuple[List[int], int]:
+    """Indices of the hidden Linears and of the output Linear inside
+    ``prediction_network`` (src/models/multimodal.py:371-386)."""
+    idxs = sorted({int(k.split(".")[1]) for k in sd if k.startswith("prediction_network.") and
+                   k.endswith(".weight") and sd[k].ndim == 2})
+    return idxs[:-1], idxs[-1]
+
+
+def prediction_network(sd, x, act, use_batch_norm, dt, return_logit=False):
+    """[Linear -> act -> BatchNorm1d(eval, eps 1e-5) -> Dropout(id)] x L ->
+    Linear(H_L, 1) (src/models/multimodal.py:366-386, 594)."""
+    hidden, last = prediction_layout(sd, use_batch_norm)
+    for i in hidden:
+        p = f"prediction_network.{i}"
+        x = activation(linear(x, sd[p + ".weight"].astype(dt), sd[p + ".bias"].astype(dt)), act)
+        if use_batch_norm:
+            bn = f"prediction_network.{i + 2}"
+            x = (x - sd[bn + ".running_mean"].astype(dt)) / np.sqrt(sd[bn + ".running_var"].astype(dt) + 1e-5)
+            x = x * sd[bn + ".weight"].astype(dt) + sd[bn + ".bias"].astype(dt)
+    p = f"prediction_network.{last}"
+    return linear(x, sd[p + ".weight"].astype(dt), sd[p + ".bias"].astype(dt))
+
+
+def final_activation(z: np.ndarray, name: str) -> np.ndarray:
+    """Sigmoid / Tanh / none (multimodal.py:381-384) then the NaN/Inf guard
+    (multimodal.py:596-597: nan->0, +inf->10, -inf->-10)."""
+    name = (name or "none").lower()
+    with np.errstate(over="ignore"):
+        if name == "sigmoid":
+            y = 1.0 / (1.0 + np.exp(-z))
+        elif name == "tanh":
+            y = np.tanh(z)
+        else:
+            y = z
+    return np.nan_to_num(y, nan=0.0, posinf=10.0, neginf=-10.0)
+
+
+def forward_pairs(sd: Dict[str, np.ndarray], cfg: dict, user_idx, item_idx, tag_idx,
+                  vis=None, txt=None, num=None, dtype=np.float64, return_logit=False) -> np.ndarray:
+    """``MultimodalRecommender.forward`` on B pairs -> (B,) scores
+    (src/models/multimodal.py:528-610).  ``cfg`` keys: fusion_type,
+    fusion_activation, use_batch_norm, final_activation, num_attention_heads."""
+    act = cfg.get("fusion_activation", "relu")
+    feats = modality_features(sd, act, np.asarray(user_idx), np.asarray(item_idx), np.asarray(tag_idx),
+                              vis, txt, num, dtype)
+    ft = cfg.get("fusion_type", "concatenate")
+    if ft == "concatenate":
+        fused = np.concatenate(feats, axis=1)
+    elif ft == "gated":
+        fused = gated_fusion(sd, feats, dtype)
+    elif ft == "attention":
+        fused = attention_fusion(sd, feats, int(cfg.get("num_attention_heads", 4)), dtype)
+    else:
+        raise ValueError(f"Unknown fusion type: '{ft}'")
+    z = prediction_network(sd, fused, act, bool(cfg.get("use_batch_norm", True)), dtype)[:, 0]
+    if return_logit:
+        return z
+    return final_activation(z, cfg.get("final_activation", "sigmoid"))
+
+
+def score_block(sd, cfg, user_indices: np.ndarray, item_lo: int, item_hi: int, feats: dict,
+                dtype=np.float64, return_logit=False, chunk_pairs: int = 1 << 18) -> np.ndarray:
+    """Dense score matrix [len(user_indices), item_hi-item_lo]: every user
+    against every item, i.e. what the loop of
+    src/inference/recommender.py:97-103 produces with ``candidates=None``."""
+    users = np.asarray(user_indices, dtype=np.int64)
+    items = np.arange(item_lo, item_hi, dtype=np.int64)
+    out = np.empty((len(users), len(items)), dtype=dtype)
+    per = max(1, chunk_pairs // max(1, len(items)))
+    for u0 in range(0, len(users), per):
+        uu = users[u0:u0 + per]
+        ui = np.repeat(uu, len(items))
+        ii = np.tile(items, len(uu))
+        s = forward_pairs(sd, cfg, ui, ii, feats["tag_idx"][ii],
+                          feats.get("vis")[ii] if feats.get("vis") is not None else None,
+                          feats.get("txt")[ii] if feats.get("txt") is not None else None,
+                          feats.get("num")[ii] if feats.get("num") is not None else None,
+                          dtype=dtype, return_logit=return_logit)
+        out[u0:u0 + len(uu)] = s.reshape(len(uu), len(items))
+    return out
+
+
+# --------------------------------------------------------------------------
+# ranking (Recommender.get_recommendations semantics)
+# --------------------------------------------------------------------------
+def topk_from_scores(scores: np.ndarray, k: int, seen: Optional[Iterable[int]] = None,
+                     item_base: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """Candidates in index order, seen items dropped, *stable* descending sort,
+    first k (src/inference/recommender.py:73-106).  Stable sort over
+    index-ordered candidates means ties go to the lower item index.  Returns
+    (global item indices int64, scores), length <= k."""
+    n = scores.shape[0]
+    cand = np.arange(n, dtype=np.int64)
+    if seen is not None:
+        seen = np.asarray(list(seen), dtype=np.int64) - item_base
+        seen = seen[(seen >= 0) & (seen < n)]
+        mask = np.ones(n, dtype=bool)
+        mask[seen] = False
+        cand = cand[mask]
+    order = np.argsort(-scores[cand], kind="stable")[:k]
+    sel = cand[order]
+    return sel + item_base, scores[sel]
+
+
+def merge_topk(lists: Sequence[Tuple[np.ndarray, np.ndarray]], k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Top-k of the union of per-shard top-k lists; ties -> lower global index
+    (shards are contiguous index ranges)."""
+    idx = np.concatenate([l[0] for l in lists])
+    sc = np.concatenate([l[1] for l in lists])
+    order = np.lexsort((idx, -sc))[:k]
+    return idx[order], sc[order]
+
+
+# --------------------------------------------------------------------------
+# metrics
+# --------------------------------------------------------------------------
+def ndcg_tasks(recommended: Sequence, relevant: Set, k: int) -> float:
+    """src/evaluation/tasks.py:718-747 (IDCG over min(len(relevant), k))."""
+    if not relevant:
+        return 0.0
+    dcg = 0.0
+    for i, item in enumerate(recommended[:k], 1):
+        if item in relevant:
+            dcg += 1.0 / np.log2(i + 1)
+    num_relevant = min(len(relevant), k)
+    idcg = sum(1.0 / np.log2(i + 2) for i in range(num_relevant))
+    return dcg / idcg if idcg > 0 else 0.0
+
+
+def retrieval_metrics(all_recs: Sequence[Sequence], all_pos: Sequence[Set], k: int) -> Dict[str, float]:
+    """Accuracy block of TopKRetrievalEvaluator.evaluate
+    (src/evaluation/tasks.py:567-635): precision denominator is len(recs),
+    users without positives contribute zeros but stay in the mean."""
+    n = len(all_recs)
+    hits = np.zeros(n)
+    pden = np.array([len(r) for r in all_recs], dtype=np.float32)
+    rden = np.array([len(p) for p in all_pos], dtype=np.float32)
+    mrr = np.zeros(n)
+    ndcg = np.zeros(n)
+    for i in range(n):
+        rec_set, pos_set = set(all_recs[i]), set(all_pos[i])
+        if not pos_set:
+            continue
+        hits[i] = len(rec_set & pos_set)
+        for j, item in enumerate(all_recs[i], 1):
+            if item in pos_set:
+                mrr[i] = 1.0 / j
+                break
+        ndcg[i] = ndcg_tasks(list(all_recs[i]), pos_set, k)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        precision = hits / pden
+        recall = hits / rden
+    precision[np.isnan(precision)] = 0.0
+    recall[np.isnan(recall)] = 0.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f1 = 2 * precision * recall / (precision + recall)
+    f1[np.isnan(f1)] = 0.0
+    hit_rate = (hits > 0).astype(float)
+    return {
+        "avg_precision_at_k": float(np.mean(precision)) if n else 0.0,
+        "avg_recall_at_k": float(np.mean(recall)) if n else 0.0,
+        "avg_f1_at_k": float(np.mean(f1)) if n else 0.0,
+        "avg_hit_rate_at_k": float(np.mean(hit_rate)) if n else 0.0,
+        "avg_ndcg_at_k": float(np.mean(ndcg)) if n else 0.0,
+        "avg_mrr": float(np.mean(mrr)) if n else 0.0,
+        "num_users_evaluated": n,
+    }
+
+
+def precision_at_k(recommended, relevant, k):
+    """src/evaluation/metrics.py:11-35 (denominator k)."""
+    if not recommended or k == 0:
+        return 0.0
+    return sum(1 for it in recommended[:k] if it in relevant) / k
+
+
+def recall_at_k(recommended, relevant, k):
+    """src/evaluation/metrics.py:37-61."""
+    if not relevant or k == 0:
+        return 0.0
+    return sum(1 for it in recommended[:k] if it in relevant) / len(relevant)
+
+
+def ndcg_metrics(recommended, relevant, k):
+    """src/evaluation/metrics.py:63-100 (IDCG over the sorted hit vector)."""
+    rel = [1 if it in relevant else 0 for it in recommended[:k]]
+    if sum(rel) == 0:
+        return 0.0
+    dcg = lambda s: sum(v / np.log2(i + 2) for i, v in enumerate(s))
+    return dcg(rel) / dcg(sorted(rel, reverse=True))
+
+
+def average_precision(recommended, relevant):
+    """src/evaluation/metrics.py:102-133."""
+    if not relevant:
+        return 0.0
+    precisions, hits = [], 0
+    for i, it in enumerate(recommended):
+        if it in relevant:
+            hits += 1
+            precisions.append(hits / (i + 1))
+    return sum(precisions) / len(relevant) if precisions else 0.0
+
+
+def mrr(recommendations, relevant_items):
+    """src/evaluation/advanced_metrics.py:15-45."""
+    rr = []
+    for recs, rel in zip(recommendations, relevant_items):
+        for i, it in enumerate(recs):
+            if it in rel:
+                rr.append(1.0 / (i + 1))
+                break
+        else:
+            rr.append(0.0)
+    return float(np.mean(rr)) if rr else 0.0
+
+
+def hit_rate(recommendations, relevant_items):
+    """src/evaluation/advanced_metrics.py:47-69."""
+    if not recommendations:
+        return 0.0
+    return sum(1 for recs, rel in zip(recommendations, relevant_items) if any(it in rel for it in recs)) / len(recommendations)
+
+
+# --------------------------------------------------------------------------
+# split / folded algebra used by the kernels, restated
+# in fp64 so tests can check the algebra independently of bf16 rounding
+# --------------------------------------------------------------------------
+def fold_batchnorm(sd, use_batch_norm: bool, dt=np.float64):
+    """BN sits after the activation, so it folds into the *next* Linear:
+    s = g/sqrt(var+eps), t = b - mean*s, W' = W diag(s), b' = b + W t."""
+    hidden, last = prediction_layout(sd, use_batch_norm)
+    ws, bs = [], []
+    scale, shift = None, None
+    for i in hidden + [last]:
+        p = f"prediction_network.{i}"
+        w = sd[p + ".weight"].astype(dt)
+        b = sd[p + ".bias"].astype(dt)
+        if scale is not None:
+            b = b + w @ shift
+            w = w * scale[None, :]
+        ws.append(w)
+        bs.append(b)
+        if use_batch_norm and i != last:
+            bn = f"prediction_network.{i + 2}"
+            scale = sd[bn + ".weight"].astype(dt) / np.sqrt(sd[bn + ".running_var"].astype(dt) + 1e-5)
+            shift = sd[bn + ".bias"].astype(dt) - sd[bn + ".running_mean"].astype(dt) * scale
+        else:
+            scale, shift = None, None
+    return ws, bs

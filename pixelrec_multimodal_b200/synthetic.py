@@ -1,0 +1,247 @@
+"""PixelRec-shaped synthetic workload generator.
+
+Two generators live here:
+
+* ``det_*``: a counter-based, version-independent generator (SplitMix64 over
+  uint64 numpy arithmetic).  Given (seed, stream name, shape) it always returns
+  the same numbers on every numpy / platform, so the golden fixtures under
+  ``tests/golden`` only need to store *outputs* of the reference, not weights.
+* ``torch_*`` helpers used by ``bench.py`` to materialise the big
+  Pixel200K/1M/8M-shaped tables directly on the GPU.
+
+Weights are "trained-like" rather than the reference's ``xavier_uniform`` on
+the embedding tables (reference ``src/models/multimodal.py:185-188``): with the
+reference init every score collapses into [0.47, 0.52] and a top-K parity test
+would be vacuous (SURVEY.md §7 "hard parts").
+"""
+from __future__ import annotations
+
+import zlib
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+SEED = 20261018
+
+_MASK = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        x = (x + np.uint64(0x9E3779B97F4A7C15)) & _MASK
+        z = x
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _MASK
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _MASK
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def _stream_base(seed: int, name: str) -> np.uint64:
+    h = zlib.crc32(name.encode("utf-8")) & 0xFFFFFFFF
+    base = np.array([(seed & 0xFFFFFFFF) << 32 | h], dtype=np.uint64)
+    return _splitmix64(base)[0]
+
+
+def det_uniform(seed: int, name: str, shape, offset: int = 0) -> np.ndarray:
+    """float64 uniforms in [0, 1), one per element, addressed by flat index."""
+    n = int(np.prod(shape)) if len(tuple(np.atleast_1d(shape))) else 1
+    idx = np.arange(offset, offset + n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        bits = _splitmix64(idx * np.uint64(0xD1342543DE82EF95) + _stream_base(seed, name))
+    u = (bits >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return u.reshape(shape)
+
+
+def det_normal(seed: int, name: str, shape) -> np.ndarray:
+    """float64 standard normals via Box-Muller on two det_uniform streams."""
+    u1 = det_uniform(seed, name + "/u1", shape)
+    u2 = det_uniform(seed, name + "/u2", shape)
+    u1 = np.maximum(u1, 1e-300)
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+
+def det_randint(seed: int, name: str, shape, high: int) -> np.ndarray:
+    return np.minimum((det_uniform(seed, name, shape) * high).astype(np.int64), high - 1)
+
+
+@dataclass
+class ModelSpec:
+    """Mirror of the reference ctor arguments that shape the weights
+    (reference ``src/models/multimodal.py:42-66``)."""
+
+    n_users: int
+    n_items: int
+    n_tags: int = 30
+    num_numerical_features: int = 7
+    embedding_dim: int = 64
+    vision_dim: int = 512          # 0 = no vision modality
+    language_dim: int = 384        # 0 = no language modality
+    fusion_type: str = "concatenate"
+    fusion_hidden_dims: List[int] = field(default_factory=lambda: [512, 256, 128])
+    fusion_activation: str = "relu"
+    use_batch_norm: bool = True
+    projection_hidden_dim: Optional[int] = None
+    final_activation: str = "sigmoid"
+    num_attention_heads: int = 4
+
+    @property
+    def num_modalities(self) -> int:
+        return 3 + (self.vision_dim > 0) + (self.language_dim > 0) + (self.num_numerical_features > 0)
+
+
+def _linear(seed, name, out_f, in_f, sd, key):
+    bound = 1.0 / np.sqrt(in_f)
+    sd[key + ".weight"] = ((det_uniform(seed, name + ".w", (out_f, in_f)) * 2 - 1) * bound).astype(np.float32)
+    sd[key + ".bias"] = ((det_uniform(seed, name + ".b", (out_f,)) * 2 - 1) * bound).astype(np.float32)
+
+
+def make_state_dict(spec: ModelSpec, seed: int = SEED, logit_scale: float = 1.0) -> Dict[str, np.ndarray]:
+    """Random "trained-like" weights under the reference state_dict key names
+    (SURVEY.md §8(a) A1)."""
+    D = spec.embedding_dim
+    sd: Dict[str, np.ndarray] = {}
+    s = 1.0 / np.sqrt(D)
+    sd["user_embedding.weight"] = (det_normal(seed, "user_embedding", (spec.n_users, D)) * s).astype(np.float32)
+    sd["item_embedding.weight"] = (det_normal(seed, "item_embedding", (spec.n_items, D)) * s).astype(np.float32)
+    sd["tag_embedding.weight"] = (det_normal(seed, "tag_embedding", (spec.n_tags, D)) * s).astype(np.float32)
+
+    def proj(prefix, in_dim):
+        if spec.projection_hidden_dim:
+            P = spec.projection_hidden_dim
+            _linear(seed, prefix + ".0", P, in_dim, sd, prefix + ".0")
+            _linear(seed, prefix + ".3", D, P, sd, prefix + ".3")
+        else:
+            _linear(seed, prefix + ".0", D, in_dim, sd, prefix + ".0")
+
+    if spec.vision_dim > 0:
+        proj("vision_projection", spec.vision_dim)
+    if spec.language_dim > 0:
+        proj("language_projection", spec.language_dim)
+    if spec.num_numerical_features > 0:
+        proj("numerical_projection", spec.num_numerical_features)
+
+    M = spec.num_modalities
+    if spec.fusion_type == "concatenate":
+        fusion_in = M * D
+    elif spec.fusion_type == "gated":
+        _linear(seed, "gate", M, M * D, sd, "fusion_layer.gating_network.0")
+        # trained gates are far from uniform: widen the logits
+        sd["fusion_layer.gating_network.0.weight"] *= np.float32(3.0)
+        fusion_in = D
+    elif spec.fusion_type == "attention":
+        b = 1.0 / np.sqrt(D)
+        sd["fusion_layer.attention.in_proj_weight"] = (
+            (det_uniform(seed, "attn.in_w", (3 * D, D)) * 2 - 1) * b * 1.5).astype(np.float32)
+        sd["fusion_layer.attention.in_proj_bias"] = (
+            (det_uniform(seed, "attn.in_b", (3 * D,)) * 2 - 1) * 0.1).astype(np.float32)
+        sd["fusion_layer.attention.out_proj.weight"] = (
+            (det_uniform(seed, "attn.out_w", (D, D)) * 2 - 1) * b).astype(np.float32)
+        sd["fusion_layer.attention.out_proj.bias"] = (
+            (det_uniform(seed, "attn.out_b", (D,)) * 2 - 1) * 0.1).astype(np.float32)
+        sd["fusion_layer.norm.weight"] = (1.0 + 0.1 * det_normal(seed, "attn.ln_w", (D,))).astype(np.float32)
+        sd["fusion_layer.norm.bias"] = (0.1 * det_normal(seed, "attn.ln_b", (D,))).astype(np.float32)
+        fusion_in = D
+    else:
+        raise ValueError(f"Unknown fusion type: '{spec.fusion_type}'")
+
+    stride = 4 if spec.use_batch_norm else 3
+    in_dim = fusion_in
+    for li, h in enumerate(spec.fusion_hidden_dims):
+        base = li * stride
+        _linear(seed, f"mlp{li}", h, in_dim, sd, f"prediction_network.{base}")
+        if spec.use_batch_norm:
+            bn = f"prediction_network.{base + 2}"
+            sd[bn + ".weight"] = (1.0 + 0.1 * det_normal(seed, bn + ".g", (h,))).astype(np.float32)
+            sd[bn + ".bias"] = (0.1 * det_normal(seed, bn + ".b", (h,))).astype(np.float32)
+            sd[bn + ".running_mean"] = (0.2 * det_normal(seed, bn + ".m", (h,))).astype(np.float32)
+            sd[bn + ".running_var"] = (0.5 + det_uniform(seed, bn + ".v", (h,))).astype(np.float32)
+            sd[bn + ".num_batches_tracked"] = np.array(100, dtype=np.int64)
+        in_dim = h
+    last = len(spec.fusion_hidden_dims) * stride
+    _linear(seed, "mlp_out", 1, in_dim, sd, f"prediction_network.{last}")
+    sd[f"prediction_network.{last}.weight"] *= np.float32(logit_scale)
+    return sd
+
+
+def final_linear_key(spec: ModelSpec) -> str:
+    stride = 4 if spec.use_batch_norm else 3
+    return f"prediction_network.{len(spec.fusion_hidden_dims) * stride}"
+
+
+def make_item_features(spec: ModelSpec, seed: int = SEED) -> Dict[str, np.ndarray]:
+    """Per-item cached features as the hoisted frozen backbones would emit them
+    (SURVEY.md §8(d)): CLIP-pooled-like vision vectors of norm 10, unit-norm
+    SBERT-like text vectors, standardised numericals, Zipf tags."""
+    NI = spec.n_items
+    out: Dict[str, np.ndarray] = {}
+    if spec.vision_dim > 0:
+        v = det_normal(seed, "feat.vis", (NI, spec.vision_dim))
+        out["vis"] = (10.0 * v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+    if spec.language_dim > 0:
+        t = det_normal(seed, "feat.txt", (NI, spec.language_dim))
+        out["txt"] = (t / np.linalg.norm(t, axis=1, keepdims=True)).astype(np.float32)
+    if spec.num_numerical_features > 0:
+        out["num"] = det_normal(seed, "feat.num", (NI, spec.num_numerical_features)).astype(np.float32)
+    ranks = np.arange(1, spec.n_tags + 1, dtype=np.float64)
+    cdf = np.cumsum(ranks ** -1.2)
+    cdf /= cdf[-1]
+    out["tag_idx"] = np.searchsorted(cdf, det_uniform(seed, "feat.tag", (NI,))).astype(np.int64)
+    return out
+
+
+def make_histories(n_users: int, n_items: int, seed: int = SEED, mean_log: float = 2.6,
+                   sigma_log: float = 0.6, lo: int = 5, hi: int = 500):
+    """Leave-one-out histories (reference ``src/data/splitting.py:282-337``):
+    per user a Zipf(1.0)-popular item set; the last item is the test positive,
+    the second-last validation, the rest the train history used by
+    ``filter_seen``.  Returns CSR (indptr int64, idx int32 sorted ascending) for
+    train, plus ``test_item`` (int32, one per user)."""
+    n = np.clip(np.exp(mean_log + sigma_log * det_normal(seed, "hist.n", (n_users,))), lo, min(hi, n_items // 2))
+    n = n.astype(np.int64)
+    indptr = np.zeros(n_users + 1, dtype=np.int64)
+    np.cumsum(n, out=indptr[1:])
+    total = int(indptr[-1])
+    ranks = np.arange(1, n_items + 1, dtype=np.float64)
+    cdf = np.cumsum(1.0 / ranks)
+    cdf /= cdf[-1]
+    draws = np.searchsorted(cdf, det_uniform(seed, "hist.items", (total,))).astype(np.int64)
+    perm = np.argsort(det_uniform(seed, "hist.perm", (n_items,)), kind="stable")
+    draws = perm[np.minimum(draws, n_items - 1)]
+    train_indptr = np.zeros(n_users + 1, dtype=np.int64)
+    train_chunks, test_item = [], np.full(n_users, -1, dtype=np.int32)
+    for u in range(n_users):
+        items = draws[indptr[u]:indptr[u + 1]]
+        _, first = np.unique(items, return_index=True)
+        seq = items[np.sort(first)]                    # de-duplicated, in "time" order
+        if len(seq) >= 3:
+            test_item[u] = seq[-1]
+            tr = np.sort(seq[:-2])
+        else:
+            tr = np.sort(seq)
+        train_chunks.append(tr.astype(np.int32))
+        train_indptr[u + 1] = train_indptr[u] + len(tr)
+    train_idx = np.concatenate(train_chunks) if train_chunks else np.zeros(0, np.int32)
+    return train_indptr, train_idx, test_item
+
+
+def user_ids(n: int) -> List[str]:
+    """Zero-padded so LabelEncoder's lexicographic order equals numeric order
+    (reference ``src/data/dataset.py:142-148``)."""
+    return [f"u{i:08d}" for i in range(n)]
+
+
+def item_ids(n: int) -> List[str]:
+    return [f"i{i:08d}" for i in range(n)]
+
+
+def apply_logit_calibration(sd: Dict[str, np.ndarray], spec: ModelSpec, mean: float, std: float,
+                            target_std: float = 2.0) -> None:
+    """Rescale the output Linear in place so that pre-activation logits measured
+    by the caller as (mean, std) become (0, target_std): a trained model spreads
+    its scores over (0, 1) instead of the random-init [0.47, 0.52] band
+    ("bf16 tolerance vs. score compression")."""
+    key = final_linear_key(spec)
+    scale = np.float32(target_std / max(std, 1e-12))
+    sd[key + ".weight"] = (sd[key + ".weight"] * scale).astype(np.float32)
+    sd[key + ".bias"] = ((sd[key + ".bias"] - np.float32(mean)) * scale).astype(np.float32)
