@@ -1,0 +1,192 @@
+/*
+ * pxr.h — C ABI of libpxr.so: the B200 (sm_100a) full-catalogue scoring /
+ * top-K ranking / ranking-metrics path of PixelRec_Multimodal.
+ *
+ * The reference has no FFI: this path sits behind duck-typed Python objects
+ * (SURVEY.md §8(b)).  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference root).  The Python host
+ * (pixelrec_multimodal_b200/) binds these with ctypes; device buffers are owned
+ * by the caller (PyTorch) and passed as raw pointers + sizes + a cudaStream_t.
+ *
+ * Conventions
+ *   - every call returns 0 on success or a negative pxr_status; nothing throws
+ *     or aborts across the boundary; pxr_last_error() gives the text.
+ *   - all device work is asynchronous on the given stream.
+ *   - a handle is not thread-safe: one handle per GPU per thread.
+ *   - the library allocates device memory only in pxr_load_weights (folded /
+ *     bf16 weight images, < 4 MB) and frees it in pxr_destroy; everything else
+ *     lives in caller-provided workspaces whose sizes the *_bytes calls report.
+ *   - matrices are row-major; indices are int64 where the reference uses
+ *     torch.long and int32 for item ids inside CSR / top-K lists.
+ */
+#ifndef PXR_H_
+#define PXR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PXR_VERSION 1
+#define PXR_MAX_HIDDEN 8
+#define PXR_MAX_KS 8
+
+typedef struct pxr_handle pxr_handle;
+typedef void* pxr_stream; /* cudaStream_t */
+
+typedef enum {
+  PXR_OK = 0,
+  PXR_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+  PXR_ERR_CUDA = -2,        /* a CUDA runtime call failed               */
+  PXR_ERR_STATE = -3,       /* call order (weights / items not loaded)  */
+  PXR_ERR_WORKSPACE = -4    /* workspace too small                      */
+} pxr_status;
+
+/* model.fusion_type, src/config.py:43; src/models/multimodal.py:583-593 */
+typedef enum { PXR_FUSION_CONCAT = 0, PXR_FUSION_GATED = 1, PXR_FUSION_ATTENTION = 2 } pxr_fusion;
+/* fusion_activation, src/models/multimodal.py:150-167 */
+typedef enum { PXR_ACT_RELU = 0, PXR_ACT_GELU = 1, PXR_ACT_TANH = 2, PXR_ACT_LEAKY_RELU = 3, PXR_ACT_SILU = 4 } pxr_act;
+/* final_activation, src/models/multimodal.py:381-384 */
+typedef enum { PXR_FINAL_NONE = 0, PXR_FINAL_SIGMOID = 1, PXR_FINAL_TANH = 2 } pxr_final;
+/* which scoring kernel pxr_score_topk uses */
+typedef enum { PXR_PATH_AUTO = 0, PXR_PATH_SIMT = 1, PXR_PATH_TCGEN05 = 2 } pxr_path;
+
+/* Mirrors the constructor arguments of MultimodalRecommender that shape the
+ * computation (src/models/multimodal.py:42-66). */
+typedef struct {
+  int32_t struct_size;          /* sizeof(pxr_config), for ABI checking            */
+  int32_t fusion;               /* pxr_fusion                                      */
+  int32_t embedding_dim;        /* D                                               */
+  int32_t vision_dim;           /* Dv of the cached vision features, 0 = absent    */
+  int32_t language_dim;         /* Dl of the cached text features, 0 = absent      */
+  int32_t num_numerical;        /* F, 0 = absent                                   */
+  int32_t projection_hidden;    /* projection_hidden_dim, 0 = single-layer         */
+  int32_t n_hidden;             /* len(fusion_hidden_dims)                         */
+  int32_t hidden[PXR_MAX_HIDDEN];
+  int32_t num_heads;            /* attention fusion only                           */
+  int32_t activation;           /* pxr_act                                         */
+  int32_t final_activation;     /* pxr_final                                       */
+  int32_t use_batch_norm;
+  int32_t n_tags;
+  int32_t path;                 /* pxr_path; PXR_PATH_AUTO picks tcgen05 when the  */
+                                /* shape is supported, else the SIMT kernels       */
+} pxr_config;
+
+/* fp32 DEVICE pointers named after the reference state_dict keys
+ * (SURVEY.md §8(a) A1); NULL where the configuration has no such tensor.
+ * The big user / item embedding tables are NOT copied: they are passed to the
+ * calls that gather from them. */
+typedef struct {
+  int32_t struct_size;
+  const float* tag_embedding;            /* tag_embedding.weight        (n_tags, D)  */
+  const float* vision_w0;  const float* vision_b0;   /* vision_projection.0   (D|P, Dv)   */
+  const float* vision_w1;  const float* vision_b1;   /* vision_projection.3   (D, P)      */
+  const float* language_w0; const float* language_b0;/* language_projection.0             */
+  const float* language_w1; const float* language_b1;/* language_projection.3             */
+  const float* numerical_w0; const float* numerical_b0;
+  const float* numerical_w1; const float* numerical_b1;
+  const float* gate_w;  const float* gate_b;         /* fusion_layer.gating_network.0 (M, M*D) */
+  const float* attn_in_w; const float* attn_in_b;    /* fusion_layer.attention.in_proj_* (3D, D) */
+  const float* attn_out_w; const float* attn_out_b;  /* fusion_layer.attention.out_proj.* (D, D) */
+  const float* attn_ln_w; const float* attn_ln_b;    /* fusion_layer.norm.*                      */
+  const float* mlp_w[PXR_MAX_HIDDEN];    /* prediction_network.{0,4,8..}.weight     */
+  const float* mlp_b[PXR_MAX_HIDDEN];
+  const float* bn_w[PXR_MAX_HIDDEN];     /* prediction_network.{2,6,10..}.weight    */
+  const float* bn_b[PXR_MAX_HIDDEN];
+  const float* bn_mean[PXR_MAX_HIDDEN];
+  const float* bn_var[PXR_MAX_HIDDEN];
+  const float* out_w;  const float* out_b;           /* last Linear (1, H_L)                     */
+  float bn_eps;                                      /* 1e-5 (nn.BatchNorm1d default)            */
+} pxr_weights;
+
+int pxr_version(void);
+const char* pxr_last_error(const pxr_handle* h);     /* h may be NULL: last create error */
+
+/* replaces MultimodalRecommender.__init__ (src/models/multimodal.py:42-148) */
+int pxr_create(const pxr_config* cfg, pxr_handle** out);
+void pxr_destroy(pxr_handle* h);
+
+/* replaces load_state_dict of the checkpoint (scripts/evaluate.py:366-375):
+ * folds eval-mode BatchNorm into the next Linear, splits the first Linear into
+ * per-user / per-item halves, builds the bf16 tcgen05 operand images. */
+int pxr_load_weights(pxr_handle* h, const pxr_weights* w, pxr_stream stream);
+
+/* K1 + K2.  Replaces the per-pair item half of forward
+ * (src/models/multimodal.py:554-570) and the per-user re-stacking of item
+ * features (src/inference/recommender.py:162-191): gathers item / tag
+ * embeddings, runs the modality projections once per item and stores the
+ * per-item partial record the scoring kernels consume.
+ *   item_embedding : (>= max(item_idx)+1, D) fp32 table
+ *   item_idx       : (n_rows,) int64 rows of the table, NULL = item_base + r
+ *   tag_idx        : (n_rows,) int64
+ *   vis/txt/num    : (n_rows, Dv|Dl|F) fp32, NULL where the modality is absent
+ *   item_base      : global index of row 0 (item-axis shard offset)
+ * The records stay in `workspace` (pxr_items_bytes(h, n_rows) bytes, 256-byte
+ * aligned), which must outlive every scoring call that uses them. */
+size_t pxr_items_bytes(const pxr_handle* h, int64_t n_rows);
+int pxr_precompute_items(pxr_handle* h, const float* item_embedding, const int64_t* item_idx,
+                         const int64_t* tag_idx, const float* vis, const float* txt, const float* num,
+                         int64_t n_rows, int64_t item_base, void* workspace, size_t workspace_bytes,
+                         pxr_stream stream);
+
+/* K3 (+ in-kernel top-K).  Replaces Recommender.get_recommendations with
+ * candidates=None for a batch of users (src/inference/recommender.py:52-110):
+ * every user of the batch against every precomputed item row, seen items
+ * dropped, stable descending order (ties -> lower item index), first K.
+ *   user_embedding : (n_users_total, D) fp32 table;  user_idx : (n_users,) int64
+ *   seen_indptr    : (n_users+1,) int64 CSR offsets for this batch, NULL = no filter
+ *   seen_idx       : int32 GLOBAL item indices, ascending inside each user
+ *   out_scores     : (n_users, K) fp32, descending, padded with -inf
+ *   out_idx        : (n_users, K) int32 GLOBAL item indices, padded with -1 */
+size_t pxr_score_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k);
+int pxr_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
+                   const int64_t* seen_indptr, const int32_t* seen_idx, int32_t k,
+                   float* out_scores, int32_t* out_idx, void* workspace, size_t workspace_bytes,
+                   pxr_stream stream);
+
+/* Scores of explicit (user, item-row) pairs against the precomputed records.
+ * Replaces MultimodalRecommender.forward (src/models/multimodal.py:528-610),
+ * Recommender._score_items_batch / get_item_score and the candidate-list mode
+ * of get_recommendations (src/inference/recommender.py:81-82,112-236).
+ *   item_row : (n,) int64 LOCAL row numbers inside the precomputed records
+ *   out      : (n,) fp32 scores after the final activation and NaN/Inf guard
+ *   out_logit: optional (n,) fp32 pre-activation logits (NULL to skip) */
+int pxr_score_pairs(pxr_handle* h, const float* user_embedding, const int64_t* user_idx,
+                    const int64_t* item_row, int64_t n, float* out, float* out_logit, pxr_stream stream);
+
+/* K4.  Merge S per-shard top-K lists per user (the step after the NCCL
+ * all-gather of SURVEY.md §8(e)); ties -> lower global item index.
+ *   scores_in / idx_in : (S, n_users, K) ;  out_* : (n_users, K) */
+int pxr_merge_topk(const float* scores_in, const int32_t* idx_in, int32_t n_shards, int64_t n_users,
+                   int32_t k, float* out_scores, int32_t* out_idx, pxr_stream stream);
+
+/* K5.  Replaces the accuracy block of TopKRetrievalEvaluator.evaluate and
+ * _calculate_ndcg (src/evaluation/tasks.py:567-635, 718-747) for several
+ * cut-offs at once (@10 is a prefix of @50).
+ *   topk_idx   : (n_users, k_stride) int32 ranked GLOBAL item ids, -1 padded
+ *   gt_indptr  : (n_users+1,) int64 ;  gt_idx : int32 relevant items (any order)
+ *   ks         : host array of n_ks cut-offs, each <= k_stride
+ *   discount   : (k_stride,) float64 DEVICE table 1/log2(i+2) (host-computed so it
+ *                is bit-identical to numpy's);  ideal : (k_stride+1,) float64
+ *                DEVICE prefix sums of it in Python's left-to-right order
+ *   out_sums   : (n_ks, 7) float64 DEVICE: sums over users of precision, recall,
+ *                f1, hit_rate, ndcg (tasks.py variant), mrr, ndcg (metrics.py
+ *                variant, src/evaluation/metrics.py:63-100)
+ *   workspace  : pxr_metrics_bytes(n_users, n_ks) bytes */
+size_t pxr_metrics_bytes(int64_t n_users, int32_t n_ks);
+int pxr_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, const int64_t* gt_indptr,
+                const int32_t* gt_idx, const int32_t* ks, int32_t n_ks, const double* discount,
+                const double* ideal, double* out_sums, void* workspace, size_t workspace_bytes,
+                pxr_stream stream);
+
+/* Introspection used by bench.py / tests. */
+int64_t pxr_launch_count(const pxr_handle* h);       /* kernels launched through this handle */
+int pxr_active_path(const pxr_handle* h);            /* pxr_path pxr_score_topk will use      */
+int pxr_set_path(pxr_handle* h, int path);           /* force SIMT / tcgen05 (tests)          */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PXR_H_ */

@@ -1,0 +1,221 @@
+// Shared declarations for libpxr.so (see include/pxr.h for the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "pxr.h"
+
+#define PXR_MAX_MODALITIES 6
+
+// ---------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------
+struct PxrLinear {            // one (BN-folded) Linear of the prediction MLP or a projection
+  int n = 0, k = 0;           // out features, in features
+  float* w = nullptr;         // [n][k] row-major fp32 (folded)
+  float* wt = nullptr;        // [k][n] transposed fp32 (folded) for linear_rows
+  float* b = nullptr;         // [n]
+};
+
+struct pxr_handle {
+  pxr_config cfg;
+  int device = 0;
+  int n_sm = 0;
+  int M = 0;                  // number of modalities (tokens), reference multimodal.py:336-342
+  int max_smem_optin = 0;
+  char err[512];
+  int64_t launches = 0;
+  int path = PXR_PATH_SIMT;   // resolved path
+  bool weights_loaded = false;
+
+  // weight arena (device)
+  void* arena = nullptr;
+  size_t arena_bytes = 0, arena_used = 0;
+  float* tag_emb = nullptr;   // copy of tag_embedding.weight
+  PxrLinear proj[3][2];       // [vision, language, numerical][layer 0 / layer 1]
+  bool has_mod[3] = {false, false, false};
+  PxrLinear gate;             // (M, M*D)
+  PxrLinear attn_in, attn_out;
+  float* ln_w = nullptr; float* ln_b = nullptr;
+  PxrLinear mlp[PXR_MAX_HIDDEN];
+  PxrLinear out;              // (1, H_L)
+
+  // fast (tcgen05) path images
+  bool fast_ok = false;
+  void* fast_w = nullptr;     // bf16 swizzled operand images + fp32 vectors (see score_tc.cu)
+
+  // precomputed item records (caller workspace)
+  float* item_feats = nullptr;   // [n_rows][M-1][D] fp32
+  void* item_fast = nullptr;     // fast-path per-item records
+  int64_t n_rows = 0;
+  int64_t item_base = 0;
+};
+
+#define PXR_FAIL(h, code, ...)                                   \
+  do {                                                           \
+    snprintf((h)->err, sizeof((h)->err), __VA_ARGS__);           \
+    return (code);                                               \
+  } while (0)
+
+#define PXR_CUDA(h, expr)                                                            \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      snprintf((h)->err, sizeof((h)->err), "%s failed: %s (%s:%d)", #expr,           \
+               cudaGetErrorString(_e), __FILE__, __LINE__);                          \
+      return PXR_ERR_CUDA;                                                           \
+    }                                                                                \
+  } while (0)
+
+static inline size_t pxr_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float pxr_apply_act(float x, int act) {
+  // reference src/models/multimodal.py:150-167
+  switch (act) {
+    case PXR_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    case PXR_ACT_TANH: return tanhf(x);
+    case PXR_ACT_LEAKY_RELU: return x >= 0.f ? x : 0.01f * x;
+    case PXR_ACT_SILU: return x / (1.0f + expf(-x));
+    default: return fmaxf(x, 0.f);
+  }
+}
+
+__device__ __forceinline__ float pxr_apply_final(float z, int fin) {
+  // final activation (multimodal.py:381-384) + NaN/Inf guard (multimodal.py:596-597)
+  float y = z;
+  if (fin == PXR_FINAL_SIGMOID) y = 1.0f / (1.0f + expf(-z));
+  else if (fin == PXR_FINAL_TANH) y = tanhf(z);
+  if (isnan(y)) y = 0.f;
+  else if (isinf(y)) y = y > 0 ? 10.f : -10.f;
+  return y;
+}
+
+// Order-preserving float -> uint32 (larger float => larger key).
+__device__ __forceinline__ uint32_t pxr_ord(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float pxr_unord(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+// Composite ranking key: higher score first, then LOWER item index
+// (stable sort over index-ordered candidates, recommender.py:76,105).
+__device__ __forceinline__ unsigned long long pxr_key(float score, uint32_t idx) {
+  return ((unsigned long long)pxr_ord(score) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ float pxr_key_score(unsigned long long k) { return pxr_unord((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t pxr_key_idx(unsigned long long k) { return 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull); }
+
+// ---------------------------------------------------------------------------
+// SIMT fp32 row-block linear layers (generic path + item precompute).
+// 256 threads; ROWS in {32,16,8,4}.
+// ---------------------------------------------------------------------------
+#define PXR_SIMT_THREADS 256
+
+// out[r][n] = act(sum_k in[r][k] * Wt[k][n] + bias[n]), n < N, N % 4 == 0,
+// in rows 16-byte aligned (ldin % 4 == 0).  act < 0: identity.
+template <int ROWS>
+__device__ __forceinline__ void linear_rows(const float* in, int ldin, int K, const float* __restrict__ Wt,
+                                            const float* __restrict__ bias, int N, float* out, int ldout,
+                                            int act) {
+  constexpr int RG = ROWS / 4;
+  constexpr int CT = PXR_SIMT_THREADS / RG;
+  constexpr int CW = CT * 4;
+  const int ct = threadIdx.x % CT, rg = threadIdx.x / CT;
+  const int K4 = K & ~3;
+  for (int nc = 0; nc < N; nc += CW) {
+    const int n0 = nc + ct * 4;
+    if (n0 >= N) continue;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    for (int k = 0; k < K4; k += 4) {
+      float4 w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(Wt + (size_t)(k + j) * N + n0);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 x = *reinterpret_cast<const float4*>(in + (size_t)(rg * 4 + r) * ldin + k);
+        acc[r][0] += x.x * w[0].x + x.y * w[1].x + x.z * w[2].x + x.w * w[3].x;
+        acc[r][1] += x.x * w[0].y + x.y * w[1].y + x.z * w[2].y + x.w * w[3].y;
+        acc[r][2] += x.x * w[0].z + x.y * w[1].z + x.z * w[2].z + x.w * w[3].z;
+        acc[r][3] += x.x * w[0].w + x.y * w[1].w + x.z * w[2].w + x.w * w[3].w;
+      }
+    }
+    for (int k = K4; k < K; ++k) {
+      const float4 w = *reinterpret_cast<const float4*>(Wt + (size_t)k * N + n0);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float x = in[(size_t)(rg * 4 + r) * ldin + k];
+        acc[r][0] += x * w.x; acc[r][1] += x * w.y; acc[r][2] += x * w.z; acc[r][3] += x * w.w;
+      }
+    }
+    const float4 b = bias ? *reinterpret_cast<const float4*>(bias + n0) : make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float4 o;
+      o.x = acc[r][0] + b.x; o.y = acc[r][1] + b.y; o.z = acc[r][2] + b.z; o.w = acc[r][3] + b.w;
+      if (act >= 0) { o.x = pxr_apply_act(o.x, act); o.y = pxr_apply_act(o.y, act); o.z = pxr_apply_act(o.z, act); o.w = pxr_apply_act(o.w, act); }
+      *reinterpret_cast<float4*>(out + (size_t)(rg * 4 + r) * ldout + n0) = o;
+    }
+  }
+}
+
+// Small / odd N: one warp per row, lanes stride over k; W row-major [N][K].
+template <int ROWS>
+__device__ __forceinline__ void linear_small(const float* in, int ldin, int K, const float* __restrict__ W,
+                                             const float* __restrict__ bias, int N, float* out, int ldout) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < ROWS; r += PXR_SIMT_THREADS / 32) {
+    for (int n = 0; n < N; ++n) {
+      float s = 0.f;
+      for (int k = lane; k < K; k += 32) s += in[(size_t)r * ldin + k] * W[(size_t)n * K + k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) out[(size_t)r * ldout + n] = s + (bias ? bias[n] : 0.f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// kernel launch entry points implemented in the other translation units
+// ---------------------------------------------------------------------------
+int pxr_simt_smem_rows(const pxr_handle* h, bool items_kernel);
+int pxr_launch_items_simt(pxr_handle* h, const float* item_embedding, const int64_t* item_idx,
+                          const int64_t* tag_idx, const float* vis, const float* txt, const float* num,
+                          int64_t n_rows, int64_t item_base, float* feats_out, cudaStream_t st);
+// dense == true: rows are (u, i) over user_idx[0..n_users) x item rows [0..n_rows); scores (masked = -inf)
+// are written to out[(u * n_rows + i)].  dense == false: explicit pairs.
+int pxr_launch_score_simt(pxr_handle* h, const float* user_embedding, const int64_t* user_idx,
+                          const int64_t* item_row, int64_t n_pairs, int64_t n_users_dense,
+                          const int64_t* seen_indptr, const int32_t* seen_idx, float* out, float* out_logit,
+                          bool dense, cudaStream_t st);
+int pxr_launch_topk_rows(pxr_handle* h, const float* scores, int64_t n_users, int64_t n_items, int64_t item_base,
+                         int32_t k, float* out_scores, int32_t* out_idx, cudaStream_t st);
+int pxr_launch_merge(const float* scores_in, const int32_t* idx_in, int32_t n_shards, int64_t n_users, int32_t k,
+                     float* out_scores, int32_t* out_idx, cudaStream_t st);
+int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, const int64_t* gt_indptr,
+                       const int32_t* gt_idx, const int32_t* ks, int32_t n_ks, const double* discount,
+                       const double* ideal, double* out_sums, void* ws, cudaStream_t st);
+
+// tcgen05 path (score_tc.cu)
+bool pxr_tc_supported(const pxr_handle* h);
+size_t pxr_tc_weight_bytes(const pxr_handle* h);
+int pxr_tc_prepare_weights(pxr_handle* h, cudaStream_t st);
+size_t pxr_tc_item_bytes(const pxr_handle* h, int64_t n_rows);
+int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t st);
+size_t pxr_tc_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k);
+int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
+                      const int64_t* seen_indptr, const int32_t* seen_idx, int32_t k, float* out_scores,
+                      int32_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t st);

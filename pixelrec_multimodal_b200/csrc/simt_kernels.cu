@@ -1,0 +1,568 @@
+// Generic fp32 SIMT kernels of libpxr.so:
+//   K1/K2  items_simt      gather + modality projections, once per item row
+//   K3g    score_simt      literal per-pair forward (all fusion types / shapes)
+//   K3t    topk_rows       exact row top-K over a dense score block (radix select)
+//   K4     merge_topk      S-way merge of per-shard top-K lists
+//   K5     metrics         Precision/Recall/F1/HitRate/NDCG/MRR@K sums
+// The tcgen05 path (score_tc.cu) replaces K3g+K3t for the supported shapes; these
+// kernels remain the path for every other configuration and for explicit pairs.
+#include "pxr_common.cuh"
+
+// ===========================================================================
+// K1/K2: item precompute (reference multimodal.py:554-570, once per item)
+// ===========================================================================
+struct ItemsParams {
+  int D, M, act;
+  const float* item_embedding; const int64_t* item_idx; const int64_t* tag_idx;
+  const float* tag_emb;
+  const float* in[3]; int in_dim[3]; int has[3]; int slot[3];
+  const float* w0t[3]; const float* b0[3]; int n0[3];
+  const float* w1t[3]; const float* b1[3];     // optional second layer (n0 -> D)
+  int64_t n_rows, item_base;
+  float* feats;                                // [n_rows_padded][M-1][D]
+  int ld_in, ld_hid;
+};
+
+template <int ROWS>
+__global__ void __launch_bounds__(PXR_SIMT_THREADS) items_simt_kernel(ItemsParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* inbuf = smem;                              // [ROWS][ld_in]
+  float* hid = inbuf + (size_t)ROWS * p.ld_in;      // [ROWS][ld_hid]
+  const int64_t row0 = (int64_t)blockIdx.x * ROWS;
+  const int FD = (p.M - 1) * p.D;
+  float* out_base = p.feats + row0 * FD;
+
+  // slots 0 (item embedding) and 1 (tag embedding): plain gathers
+  for (int idx = threadIdx.x; idx < ROWS * (p.D / 4) * 2; idx += PXR_SIMT_THREADS) {
+    const int r = idx / (p.D / 4 * 2);
+    const int rem = idx % (p.D / 4 * 2);
+    const int which = rem / (p.D / 4);
+    const int c = (rem % (p.D / 4)) * 4;
+    const int64_t row = row0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < p.n_rows) {
+      if (which == 0) {
+        const int64_t it = p.item_idx ? p.item_idx[row] : (p.item_base + row);
+        v = *reinterpret_cast<const float4*>(p.item_embedding + it * p.D + c);
+      } else {
+        v = *reinterpret_cast<const float4*>(p.tag_emb + p.tag_idx[row] * p.D + c);
+      }
+    }
+    *reinterpret_cast<float4*>(out_base + (size_t)r * FD + which * p.D + c) = v;
+  }
+
+  for (int m = 0; m < 3; ++m) {
+    if (!p.has[m]) continue;
+    const int K = p.in_dim[m];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ROWS * p.ld_in; idx += PXR_SIMT_THREADS) {
+      const int r = idx / p.ld_in, k = idx % p.ld_in;
+      const int64_t row = row0 + r;
+      inbuf[idx] = (row < p.n_rows && k < K) ? p.in[m][row * K + k] : 0.f;
+    }
+    __syncthreads();
+    float* dst = out_base + p.slot[m] * p.D;
+    if (p.w1t[m]) {
+      linear_rows<ROWS>(inbuf, p.ld_in, K, p.w0t[m], p.b0[m], p.n0[m], hid, p.ld_hid, p.act);
+      __syncthreads();
+      linear_rows<ROWS>(hid, p.ld_hid, p.n0[m], p.w1t[m], p.b1[m], p.D, dst, FD, p.act);
+    } else {
+      linear_rows<ROWS>(inbuf, p.ld_in, K, p.w0t[m], p.b0[m], p.D, dst, FD, p.act);
+    }
+  }
+}
+
+static int items_rows_for(const pxr_handle* h, int* ld_in, int* ld_hid, size_t* smem) {
+  int kmax = 4;
+  const int dims[3] = {h->cfg.vision_dim, h->cfg.language_dim, h->cfg.num_numerical};
+  for (int m = 0; m < 3; ++m) if (dims[m] > kmax) kmax = dims[m];
+  *ld_in = (kmax + 3) & ~3;
+  *ld_hid = h->cfg.projection_hidden > 0 ? ((h->cfg.projection_hidden + 3) & ~3) : 4;
+  const int cands[4] = {32, 16, 8, 4};
+  for (int i = 0; i < 4; ++i) {
+    size_t s = (size_t)cands[i] * (*ld_in + *ld_hid) * sizeof(float);
+    if (s <= (size_t)h->max_smem_optin - 1024) { *smem = s; return cands[i]; }
+  }
+  return 0;
+}
+
+template <int ROWS>
+static int launch_items(pxr_handle* h, const ItemsParams& p, size_t smem, cudaStream_t st) {
+  PXR_CUDA(h, cudaFuncSetAttribute(items_simt_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = (p.n_rows + ROWS - 1) / ROWS;
+  items_simt_kernel<ROWS><<<(unsigned)blocks, PXR_SIMT_THREADS, smem, st>>>(p);
+  h->launches++;
+  PXR_CUDA(h, cudaGetLastError());
+  return PXR_OK;
+}
+
+int pxr_launch_items_simt(pxr_handle* h, const float* item_embedding, const int64_t* item_idx,
+                          const int64_t* tag_idx, const float* vis, const float* txt, const float* num,
+                          int64_t n_rows, int64_t item_base, float* feats_out, cudaStream_t st) {
+  ItemsParams p;
+  memset(&p, 0, sizeof(p));
+  p.D = h->cfg.embedding_dim; p.M = h->M; p.act = h->cfg.activation;
+  p.item_embedding = item_embedding; p.item_idx = item_idx; p.tag_idx = tag_idx; p.tag_emb = h->tag_emb;
+  const float* ins[3] = {vis, txt, num};
+  const int dims[3] = {h->cfg.vision_dim, h->cfg.language_dim, h->cfg.num_numerical};
+  int slot = 2;
+  for (int m = 0; m < 3; ++m) {
+    p.has[m] = h->has_mod[m];
+    if (!p.has[m]) continue;
+    if (!ins[m]) PXR_FAIL(h, PXR_ERR_INVALID, "modality %d is configured but its feature pointer is NULL", m);
+    p.in[m] = ins[m]; p.in_dim[m] = dims[m]; p.slot[m] = slot++;
+    p.w0t[m] = h->proj[m][0].wt; p.b0[m] = h->proj[m][0].b; p.n0[m] = h->proj[m][0].n;
+    p.w1t[m] = h->proj[m][1].wt; p.b1[m] = h->proj[m][1].b;
+  }
+  p.n_rows = n_rows; p.item_base = item_base; p.feats = feats_out;
+  size_t smem = 0;
+  const int rows = items_rows_for(h, &p.ld_in, &p.ld_hid, &smem);
+  switch (rows) {
+    case 32: return launch_items<32>(h, p, smem, st);
+    case 16: return launch_items<16>(h, p, smem, st);
+    case 8: return launch_items<8>(h, p, smem, st);
+    case 4: return launch_items<4>(h, p, smem, st);
+  }
+  PXR_FAIL(h, PXR_ERR_INVALID, "feature dims too large for the item precompute kernel");
+}
+
+// ===========================================================================
+// K3g: literal per-pair forward (reference multimodal.py:553-597)
+// ===========================================================================
+struct ScoreParams {
+  int fusion, D, M, n_hidden, hidden[PXR_MAX_HIDDEN], heads, act, fin, maxdim;
+  const float* gate_w; const float* gate_b;
+  const float* attn_in_wt; const float* attn_in_b; const float* attn_out_wt; const float* attn_out_b;
+  const float* ln_w; const float* ln_b;
+  const float* mlp_wt[PXR_MAX_HIDDEN]; const float* mlp_b[PXR_MAX_HIDDEN];
+  const float* out_w; const float* out_b;
+  const float* user_emb; const int64_t* user_idx; const int64_t* item_row;
+  const float* item_feats; int64_t n_items; int64_t n_pairs; int dense; int64_t item_base;
+  const int64_t* seen_indptr; const int32_t* seen_idx;
+  float* out; float* out_logit;
+};
+
+template <int ROWS>
+__global__ void __launch_bounds__(PXR_SIMT_THREADS) score_simt_kernel(ScoreParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int D = p.D, M = p.M, MD = M * D, maxdim = p.maxdim;
+  float* X = smem;                                   // [ROWS][M*D]: the token stack == the concat vector
+  float* A = X + (size_t)ROWS * MD;                  // [ROWS][maxdim]
+  float* B = A + (size_t)ROWS * maxdim;              // [ROWS][maxdim]
+  float* G = B + (size_t)ROWS * maxdim;              // [ROWS][8]
+  long long* prow = reinterpret_cast<long long*>(G + ROWS * 8);   // [ROWS][2] (user row, item row)
+  const int64_t row0 = (int64_t)blockIdx.x * ROWS;
+
+  if (threadIdx.x < ROWS) {
+    const int64_t pair = row0 + threadIdx.x;
+    long long u = -1, ir = -1;
+    if (pair < p.n_pairs) {
+      if (p.dense) { u = p.user_idx[pair / p.n_items]; ir = pair % p.n_items; }
+      else { u = p.user_idx[pair]; ir = p.item_row[pair]; }
+    }
+    prow[threadIdx.x * 2] = u; prow[threadIdx.x * 2 + 1] = ir;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < ROWS * (MD / 4); idx += PXR_SIMT_THREADS) {
+    const int r = idx / (MD / 4), c = (idx % (MD / 4)) * 4;
+    const long long u = prow[r * 2], ir = prow[r * 2 + 1];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u >= 0) {
+      v = (c < D) ? *reinterpret_cast<const float4*>(p.user_emb + u * D + c)
+                  : *reinterpret_cast<const float4*>(p.item_feats + ir * (MD - D) + (c - D));
+    }
+    *reinterpret_cast<float4*>(X + (size_t)r * MD + c) = v;
+  }
+  __syncthreads();
+
+  const float* cur = X; int ldcur = MD, Kcur = MD;
+  float* nxt = A;
+  if (p.fusion == PXR_FUSION_GATED) {
+    // reference layers.py:195-225
+    linear_small<ROWS>(X, MD, MD, p.gate_w, p.gate_b, M, G, 8);
+    __syncthreads();
+    if (threadIdx.x < ROWS) {
+      float* g = G + threadIdx.x * 8;
+      float mx = g[0];
+      for (int m = 1; m < M; ++m) mx = fmaxf(mx, g[m]);
+      float s = 0.f;
+      for (int m = 0; m < M; ++m) { g[m] = expf(g[m] - mx); s += g[m]; }
+      for (int m = 0; m < M; ++m) g[m] /= s;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ROWS * D; idx += PXR_SIMT_THREADS) {
+      const int r = idx / D, d = idx % D;
+      float s = 0.f;
+      for (int m = 0; m < M; ++m) s += G[r * 8 + m] * X[(size_t)r * MD + m * D + d];
+      A[(size_t)r * maxdim + d] = s;
+    }
+    __syncthreads();
+    cur = A; ldcur = maxdim; Kcur = D; nxt = B;
+  } else if (p.fusion == PXR_FUSION_ATTENTION) {
+    // reference layers.py:135-164 (documented semantics), nn.MultiheadAttention batch_first=False
+    const int D3 = 3 * D, dh = D / p.heads;
+    for (int m = 0; m < M; ++m)
+      linear_rows<ROWS>(X + m * D, MD, D, p.attn_in_wt, p.attn_in_b, D3, A + m * D3, maxdim, -1);
+    __syncthreads();
+    const float scale = rsqrtf((float)dh);
+    for (int w = threadIdx.x; w < ROWS * p.heads * M; w += PXR_SIMT_THREADS) {
+      const int r = w / (p.heads * M), hd = (w / M) % p.heads, a = w % M;
+      float* row = A + (size_t)r * maxdim;
+      float* q = row + a * D3 + hd * dh;
+      float s[PXR_MAX_MODALITIES];
+      float mx = -INFINITY;
+      for (int b = 0; b < M; ++b) {
+        const float* kk = row + b * D3 + D + hd * dh;
+        float acc = 0.f;
+        for (int d = 0; d < dh; ++d) acc += q[d] * kk[d];
+        s[b] = acc * scale; mx = fmaxf(mx, s[b]);
+      }
+      float sum = 0.f;
+      for (int b = 0; b < M; ++b) { s[b] = expf(s[b] - mx); sum += s[b]; }
+      const float inv = 1.f / sum;
+      for (int d = 0; d < dh; ++d) {
+        float o = 0.f;
+        for (int b = 0; b < M; ++b) o += s[b] * inv * row[b * D3 + 2 * D + hd * dh + d];
+        q[d] = o;                                   // O overwrites this work item's own Q slice
+      }
+    }
+    __syncthreads();
+    for (int m = 0; m < M; ++m)
+      linear_rows<ROWS>(A + m * D3, maxdim, D, p.attn_out_wt, p.attn_out_b, D, B + m * D, maxdim, -1);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < ROWS; r += PXR_SIMT_THREADS / 32) {
+      float fused[16];                               // D <= 512
+#pragma unroll
+      for (int j = 0; j < 16; ++j) fused[j] = 0.f;
+      for (int m = 0; m < M; ++m) {
+        float y[16];
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int d = lane + j * 32;
+          y[j] = d < D ? X[(size_t)r * MD + m * D + d] + B[(size_t)r * maxdim + m * D + d] : 0.f;
+          sum += y[j];
+        }
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mu = sum / D;
+        float var = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const int d = lane + j * 32; if (d < D) var += (y[j] - mu) * (y[j] - mu); }
+        for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+        const float rstd = rsqrtf(var / D + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int d = lane + j * 32;
+          if (d < D) fused[j] += (y[j] - mu) * rstd * p.ln_w[d] + p.ln_b[d];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { const int d = lane + j * 32; if (d < D) A[(size_t)r * maxdim + d] = fused[j] / M; }
+    }
+    __syncthreads();
+    cur = A; ldcur = maxdim; Kcur = D; nxt = B;
+  }
+
+  // prediction MLP with eval-mode BatchNorm folded into the next Linear (multimodal.py:366-386)
+  for (int l = 0; l < p.n_hidden; ++l) {
+    linear_rows<ROWS>(cur, ldcur, Kcur, p.mlp_wt[l], p.mlp_b[l], p.hidden[l], nxt, maxdim, p.act);
+    __syncthreads();
+    cur = nxt; ldcur = maxdim; Kcur = p.hidden[l];
+    nxt = (cur == A) ? B : A;
+  }
+  linear_small<ROWS>(cur, ldcur, Kcur, p.out_w, p.out_b, 1, G, 8);
+  __syncthreads();
+  if (threadIdx.x < ROWS) {
+    const int64_t pair = row0 + threadIdx.x;
+    if (pair < p.n_pairs) {
+      const float z = G[threadIdx.x * 8];
+      float s = pxr_apply_final(z, p.fin);
+      if (p.dense && p.seen_indptr) {
+        const int64_t ul = pair / p.n_items;
+        const int32_t gi = (int32_t)(p.item_base + pair % p.n_items);
+        int64_t lo = p.seen_indptr[ul], hi = p.seen_indptr[ul + 1];
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (p.seen_idx[mid] < gi) lo = mid + 1; else hi = mid; }
+        if (lo < p.seen_indptr[ul + 1] && p.seen_idx[lo] == gi) s = -INFINITY;   // filtered (recommender.py:88-90)
+      }
+      p.out[pair] = s;
+      if (p.out_logit) p.out_logit[pair] = z;
+    }
+  }
+}
+
+static int score_maxdim(const pxr_handle* h) {
+  int md = h->cfg.embedding_dim;
+  for (int l = 0; l < h->cfg.n_hidden; ++l) if (h->cfg.hidden[l] > md) md = h->cfg.hidden[l];
+  if (h->cfg.fusion == PXR_FUSION_ATTENTION) { int q = h->M * 3 * h->cfg.embedding_dim; if (q > md) md = q; }
+  return (md + 3) & ~3;
+}
+
+static size_t score_smem(const pxr_handle* h, int rows) {
+  const int MD = h->M * h->cfg.embedding_dim;
+  return ((size_t)rows * MD + 2 * (size_t)rows * score_maxdim(h) + (size_t)rows * 8) * sizeof(float) +
+         (size_t)rows * 2 * sizeof(long long);
+}
+
+int pxr_simt_smem_rows(const pxr_handle* h, bool items_kernel) {
+  if (items_kernel) { int a, b; size_t s; return items_rows_for(h, &a, &b, &s); }
+  const int cands[4] = {32, 16, 8, 4};
+  for (int i = 0; i < 4; ++i) if (score_smem(h, cands[i]) <= (size_t)h->max_smem_optin - 1024) return cands[i];
+  return 0;
+}
+
+template <int ROWS>
+static int launch_score(pxr_handle* h, const ScoreParams& p, cudaStream_t st) {
+  const size_t smem = score_smem(h, ROWS);
+  PXR_CUDA(h, cudaFuncSetAttribute(score_simt_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = (p.n_pairs + ROWS - 1) / ROWS;
+  if (blocks > 0x7fffffffLL) PXR_FAIL(h, PXR_ERR_INVALID, "too many pairs for one launch");
+  score_simt_kernel<ROWS><<<(unsigned)blocks, PXR_SIMT_THREADS, smem, st>>>(p);
+  h->launches++;
+  PXR_CUDA(h, cudaGetLastError());
+  return PXR_OK;
+}
+
+int pxr_launch_score_simt(pxr_handle* h, const float* user_embedding, const int64_t* user_idx,
+                          const int64_t* item_row, int64_t n_pairs, int64_t n_users_dense,
+                          const int64_t* seen_indptr, const int32_t* seen_idx, float* out, float* out_logit,
+                          bool dense, cudaStream_t st) {
+  if (n_pairs == 0) return PXR_OK;
+  ScoreParams p;
+  memset(&p, 0, sizeof(p));
+  p.fusion = h->cfg.fusion; p.D = h->cfg.embedding_dim; p.M = h->M; p.n_hidden = h->cfg.n_hidden;
+  for (int l = 0; l < p.n_hidden; ++l) { p.hidden[l] = h->cfg.hidden[l]; p.mlp_wt[l] = h->mlp[l].wt; p.mlp_b[l] = h->mlp[l].b; }
+  p.heads = h->cfg.num_heads; p.act = h->cfg.activation; p.fin = h->cfg.final_activation; p.maxdim = score_maxdim(h);
+  p.gate_w = h->gate.w; p.gate_b = h->gate.b;
+  p.attn_in_wt = h->attn_in.wt; p.attn_in_b = h->attn_in.b; p.attn_out_wt = h->attn_out.wt; p.attn_out_b = h->attn_out.b;
+  p.ln_w = h->ln_w; p.ln_b = h->ln_b;
+  p.out_w = h->out.w; p.out_b = h->out.b;
+  p.user_emb = user_embedding; p.user_idx = user_idx; p.item_row = item_row;
+  p.item_feats = h->item_feats; p.n_items = h->n_rows; p.n_pairs = n_pairs; p.dense = dense ? 1 : 0;
+  p.item_base = h->item_base; p.seen_indptr = seen_indptr; p.seen_idx = seen_idx;
+  p.out = out; p.out_logit = out_logit;
+  (void)n_users_dense;
+  switch (pxr_simt_smem_rows(h, false)) {
+    case 32: return launch_score<32>(h, p, st);
+    case 16: return launch_score<16>(h, p, st);
+    case 8: return launch_score<8>(h, p, st);
+    case 4: return launch_score<4>(h, p, st);
+  }
+  PXR_FAIL(h, PXR_ERR_INVALID, "layer dims too large for the SIMT scoring kernel");
+}
+
+// ===========================================================================
+// K3t: exact top-K of each row of a dense score block (masked entries = -inf).
+// 64-bit keys (score, ~index) are all distinct, so an 8-pass radix select finds
+// the exact K-th key and ties resolve to the lower item index by construction.
+// ===========================================================================
+#define TOPK_THREADS 256
+#define TOPK_MAX_K 1024
+
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int n_pow2) {
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool desc = ((i & size) == 0);
+          const unsigned long long a = keys[i], b = keys[j];
+          if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[j] = a; }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS) topk_rows_kernel(const float* __restrict__ scores, int64_t n_items,
+                                                                  int64_t item_base, int k, float* out_scores,
+                                                                  int32_t* out_idx) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long sel[TOPK_MAX_K];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_remaining, s_count, s_nvalid;
+  const float* row = scores + (int64_t)blockIdx.x * n_items;
+  if (threadIdx.x == 0) { s_prefix = 0ull; s_remaining = k; s_count = 0; s_nvalid = 0; }
+  __syncthreads();
+  // number of unmasked candidates
+  int local = 0;
+  for (int64_t i = threadIdx.x; i < n_items; i += TOPK_THREADS) local += (row[i] != -INFINITY);
+  atomicAdd(&s_nvalid, local);
+  __syncthreads();
+  const int keff = min(k, s_nvalid);
+  if (threadIdx.x == 0) s_remaining = keff;
+  __syncthreads();
+  if (keff > 0) {
+    for (int pass = 7; pass >= 0; --pass) {
+      for (int i = threadIdx.x; i < 256; i += TOPK_THREADS) hist[i] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int64_t i = threadIdx.x; i < n_items; i += TOPK_THREADS) {
+        const float s = row[i];
+        if (s == -INFINITY) continue;
+        const unsigned long long key = pxr_key(s, (uint32_t)i);
+        if (pass == 7 || (key >> (8 * (pass + 1))) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255ull], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int rem = s_remaining, b = 255;
+        for (; b > 0; --b) { if ((int)hist[b] >= rem) break; rem -= hist[b]; }
+        s_remaining = rem; s_prefix = (prefix << 8) | (unsigned long long)b;
+      }
+      __syncthreads();
+    }
+    const unsigned long long kth = s_prefix;
+    for (int64_t i = threadIdx.x; i < n_items; i += TOPK_THREADS) {
+      const float s = row[i];
+      if (s == -INFINITY) continue;
+      const unsigned long long key = pxr_key(s, (uint32_t)i);
+      if (key >= kth) { const int slot = atomicAdd(&s_count, 1); if (slot < TOPK_MAX_K) sel[slot] = key; }
+    }
+  }
+  __syncthreads();
+  int n2 = 1;
+  while (n2 < keff) n2 <<= 1;
+  for (int i = keff + threadIdx.x; i < n2; i += TOPK_THREADS) sel[i] = 0ull;
+  if (keff > 1) bitonic_sort_desc(sel, n2);
+  __syncthreads();
+  for (int i = threadIdx.x; i < k; i += TOPK_THREADS) {
+    float s = -INFINITY; int32_t id = -1;
+    if (i < keff) { s = pxr_key_score(sel[i]); id = (int32_t)(pxr_key_idx(sel[i]) + item_base); }
+    out_scores[(int64_t)blockIdx.x * k + i] = s;
+    out_idx[(int64_t)blockIdx.x * k + i] = id;
+  }
+}
+
+int pxr_launch_topk_rows(pxr_handle* h, const float* scores, int64_t n_users, int64_t n_items, int64_t item_base,
+                         int32_t k, float* out_scores, int32_t* out_idx, cudaStream_t st) {
+  if (k > TOPK_MAX_K) PXR_FAIL(h, PXR_ERR_INVALID, "k=%d exceeds %d", k, TOPK_MAX_K);
+  if (n_users == 0) return PXR_OK;
+  topk_rows_kernel<<<(unsigned)n_users, TOPK_THREADS, 0, st>>>(scores, n_items, item_base, k, out_scores, out_idx);
+  h->launches++;
+  PXR_CUDA(h, cudaGetLastError());
+  return PXR_OK;
+}
+
+// ===========================================================================
+// K4: merge S per-shard top-K lists per user (rank by counting; keys distinct)
+// ===========================================================================
+#define MERGE_THREADS 128
+#define MERGE_MAX_KEYS 4096
+
+__global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const float* __restrict__ scores_in,
+                                                                    const int32_t* __restrict__ idx_in, int n_shards,
+                                                                    int64_t n_users, int k, float* out_scores,
+                                                                    int32_t* out_idx) {
+  __shared__ unsigned long long keys[MERGE_MAX_KEYS];
+  const int64_t u = blockIdx.x;
+  const int n = n_shards * k;
+  for (int i = threadIdx.x; i < n; i += MERGE_THREADS) {
+    const int s = i / k, j = i % k;
+    const int64_t off = ((int64_t)s * n_users + u) * k + j;
+    const int32_t id = idx_in[off];
+    keys[i] = id < 0 ? 0ull : pxr_key(scores_in[off], (uint32_t)id);
+  }
+  for (int i = threadIdx.x; i < k; i += MERGE_THREADS) { out_scores[u * k + i] = -INFINITY; out_idx[u * k + i] = -1; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += MERGE_THREADS) {
+    const unsigned long long me = keys[i];
+    if (me == 0ull) continue;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += (keys[j] > me);
+    if (rank < k) { out_scores[u * k + rank] = pxr_key_score(me); out_idx[u * k + rank] = (int32_t)pxr_key_idx(me); }
+  }
+}
+
+int pxr_launch_merge(const float* scores_in, const int32_t* idx_in, int32_t n_shards, int64_t n_users, int32_t k,
+                     float* out_scores, int32_t* out_idx, cudaStream_t st) {
+  if ((int64_t)n_shards * k > MERGE_MAX_KEYS) return PXR_ERR_INVALID;
+  if (n_users == 0) return PXR_OK;
+  merge_topk_kernel<<<(unsigned)n_users, MERGE_THREADS, 0, st>>>(scores_in, idx_in, n_shards, n_users, k, out_scores, out_idx);
+  return cudaGetLastError() == cudaSuccess ? PXR_OK : PXR_ERR_CUDA;
+}
+
+// ===========================================================================
+// K5: ranking metrics (reference tasks.py:567-635, 718-747; metrics.py:63-100)
+// ===========================================================================
+#define METRIC_COLS 7
+#define METRIC_THREADS 128
+
+struct MetricKs { int n; int k[PXR_MAX_KS]; };
+
+__global__ void __launch_bounds__(METRIC_THREADS) metrics_user_kernel(const int32_t* __restrict__ topk, int k_stride,
+                                                                       int64_t n_users, const int64_t* __restrict__ gt_indptr,
+                                                                       const int32_t* __restrict__ gt_idx, MetricKs ks,
+                                                                       const double* __restrict__ discount,
+                                                                       const double* __restrict__ ideal,
+                                                                       double* __restrict__ block_sums) {
+  __shared__ double red[METRIC_THREADS];
+  const int64_t u = (int64_t)blockIdx.x * METRIC_THREADS + threadIdx.x;
+  double vals[PXR_MAX_KS][METRIC_COLS];
+  for (int a = 0; a < ks.n; ++a) for (int c = 0; c < METRIC_COLS; ++c) vals[a][c] = 0.0;
+  if (u < n_users) {
+    const int64_t g0 = gt_indptr[u], g1 = gt_indptr[u + 1];
+    const int npos = (int)(g1 - g0);
+    if (npos > 0) {                                   // "if not pos_set: continue" (tasks.py:589-591)
+      const int32_t* rec = topk + u * k_stride;
+      int hits = 0, nrec = 0, first = 0, ki = 0;
+      double dcg = 0.0;
+      for (int j = 0; j < k_stride && ki < ks.n; ++j) {
+        const int32_t it = rec[j];
+        if (it >= 0) {
+          nrec++;
+          bool hit = false;
+          for (int64_t g = g0; g < g1; ++g) if (gt_idx[g] == it) { hit = true; break; }
+          if (hit) { hits++; dcg += discount[j]; if (!first) first = j + 1; }
+        }
+        while (ki < ks.n && j + 1 == ks.k[ki]) {     // cut-offs ascending
+          const int k = ks.k[ki];
+          const double prec = nrec > 0 ? (double)hits / (double)nrec : 0.0;   // denominator len(recs), tasks.py:577
+          const double rec_ = (double)hits / (double)npos;
+          const double f1 = (prec + rec_) > 0.0 ? 2.0 * prec * rec_ / (prec + rec_) : 0.0;
+          const double idcg = ideal[npos < k ? npos : k];
+          vals[ki][0] = prec; vals[ki][1] = rec_; vals[ki][2] = f1; vals[ki][3] = hits > 0 ? 1.0 : 0.0;
+          vals[ki][4] = idcg > 0.0 ? dcg / idcg : 0.0;
+          vals[ki][5] = first ? 1.0 / (double)first : 0.0;
+          vals[ki][6] = hits > 0 ? dcg / ideal[hits] : 0.0;
+          ki++;
+        }
+      }
+    }
+  }
+  for (int a = 0; a < ks.n; ++a) {
+    for (int c = 0; c < METRIC_COLS; ++c) {
+      red[threadIdx.x] = vals[a][c];
+      __syncthreads();
+      for (int s = METRIC_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) block_sums[(int64_t)blockIdx.x * (PXR_MAX_KS * METRIC_COLS) + a * METRIC_COLS + c] = red[0];
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void metrics_final_kernel(const double* __restrict__ block_sums, int64_t n_blocks, int n_ks, double* out) {
+  // one thread per (k, column); fixed summation order => deterministic
+  const int t = threadIdx.x;
+  if (t >= n_ks * METRIC_COLS) return;
+  double s = 0.0;
+  for (int64_t b = 0; b < n_blocks; ++b) s += block_sums[b * (PXR_MAX_KS * METRIC_COLS) + t];
+  out[t] = s;
+}
+
+int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, const int64_t* gt_indptr,
+                       const int32_t* gt_idx, const int32_t* ks, int32_t n_ks, const double* discount,
+                       const double* ideal, double* out_sums, void* ws, cudaStream_t st) {
+  MetricKs mk; mk.n = n_ks;
+  for (int i = 0; i < n_ks; ++i) { mk.k[i] = ks[i]; if (i && ks[i] <= ks[i - 1]) return PXR_ERR_INVALID; if (ks[i] > k_stride || ks[i] <= 0) return PXR_ERR_INVALID; }
+  const int64_t blocks = (n_users + METRIC_THREADS - 1) / METRIC_THREADS;
+  if (blocks == 0) { cudaMemsetAsync(out_sums, 0, sizeof(double) * n_ks * METRIC_COLS, st); return PXR_OK; }
+  metrics_user_kernel<<<(unsigned)blocks, METRIC_THREADS, 0, st>>>(topk_idx, k_stride, n_users, gt_indptr, gt_idx, mk,
+                                                                   discount, ideal, (double*)ws);
+  metrics_final_kernel<<<1, 64, 0, st>>>((const double*)ws, blocks, n_ks, out_sums);
+  return cudaGetLastError() == cudaSuccess ? PXR_OK : PXR_ERR_CUDA;
+}

@@ -1,0 +1,279 @@
+"""PxrEngine: torch-tensor wrapper over the libpxr C ABI (include/pxr.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every kernel that
+touches a score is in libpxr.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PxrError
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class PxrEngine:
+    """One handle = one model configuration on one GPU (not thread-safe)."""
+
+    def __init__(self, *, fusion_type: str, embedding_dim: int, vision_dim: int, language_dim: int,
+                 num_numerical: int, hidden_dims: Sequence[int], n_tags: int, num_heads: int = 4,
+                 activation: str = "relu", final_activation: str = "sigmoid", use_batch_norm: bool = True,
+                 projection_hidden_dim: Optional[int] = None, path: str = "auto",
+                 device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise PxrError("PxrEngine needs a CUDA device: the scoring path has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise PxrError(f"PxrEngine needs a CUDA device, got {self.device}")
+        if fusion_type not in _lib.FUSION:
+            raise ValueError(f"Unknown fusion type: '{fusion_type}'")
+        cfg = _lib.PxrConfig()
+        cfg.struct_size = C.sizeof(_lib.PxrConfig)
+        cfg.fusion = _lib.FUSION[fusion_type]
+        cfg.embedding_dim = embedding_dim
+        cfg.vision_dim = int(vision_dim or 0)
+        cfg.language_dim = int(language_dim or 0)
+        cfg.num_numerical = int(num_numerical or 0)
+        cfg.projection_hidden = int(projection_hidden_dim or 0)
+        if len(hidden_dims) > _lib.PXR_MAX_HIDDEN:
+            raise ValueError(f"at most {_lib.PXR_MAX_HIDDEN} hidden layers are supported")
+        cfg.n_hidden = len(hidden_dims)
+        for i, hdim in enumerate(hidden_dims):
+            cfg.hidden[i] = int(hdim)
+        cfg.num_heads = num_heads
+        # unknown activation names fall back to ReLU like the reference (multimodal.py:167)
+        cfg.activation = _lib.ACT.get((activation or "relu").lower(), 0)
+        cfg.final_activation = _lib.FINAL.get((final_activation or "none").lower(), 0)
+        cfg.use_batch_norm = int(bool(use_batch_norm))
+        cfg.n_tags = n_tags
+        cfg.path = _lib.PATH[path]
+        self.cfg = cfg
+        self.fusion_type = fusion_type
+        self.D = embedding_dim
+        self.M = 3 + (cfg.vision_dim > 0) + (cfg.language_dim > 0) + (cfg.num_numerical > 0)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.pxr_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise PxrError(f"pxr_create failed ({rc}): {self.lib.pxr_last_error(None).decode()}")
+        self._keep: Dict[str, object] = {}
+        self._items_ws: Optional[torch.Tensor] = None
+        self._score_ws: Optional[torch.Tensor] = None
+        self.n_rows = 0
+        self.item_base = 0
+
+    # ------------------------------------------------------------------ util
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.pxr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise PxrError(f"{what} failed ({rc}): {self.lib.pxr_last_error(self._h).decode()}")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.pxr_launch_count(self._h))
+
+    @property
+    def active_path(self) -> str:
+        return {1: "simt", 2: "tcgen05"}.get(self.lib.pxr_active_path(self._h), "?")
+
+    def set_path(self, path: str):
+        self._check(self.lib.pxr_set_path(self._h, _lib.PATH[path]), "pxr_set_path")
+
+    # --------------------------------------------------------------- weights
+    def load_weights(self, sd: Dict[str, torch.Tensor], use_batch_norm: bool, bn_eps: float = 1e-5):
+        """``sd`` uses the reference state_dict key names."""
+        dev = self.device
+        keep: Dict[str, torch.Tensor] = {}
+
+        def g(key):
+            if key not in sd:
+                return None
+            keep[key] = _dev_f32(sd[key], dev)
+            return keep[key]
+
+        w = _lib.PxrWeights()
+        w.struct_size = C.sizeof(_lib.PxrWeights)
+        w.bn_eps = bn_eps
+
+        def setp(field, key):
+            t = g(key)
+            setattr(w, field, t.data_ptr() if t is not None else None)
+
+        setp("tag_embedding", "tag_embedding.weight")
+        for name, pref in (("vision", "vision_projection"), ("language", "language_projection"),
+                           ("numerical", "numerical_projection")):
+            setp(f"{name}_w0", f"{pref}.0.weight")
+            setp(f"{name}_b0", f"{pref}.0.bias")
+            setp(f"{name}_w1", f"{pref}.3.weight")
+            setp(f"{name}_b1", f"{pref}.3.bias")
+        setp("gate_w", "fusion_layer.gating_network.0.weight")
+        setp("gate_b", "fusion_layer.gating_network.0.bias")
+        setp("attn_in_w", "fusion_layer.attention.in_proj_weight")
+        setp("attn_in_b", "fusion_layer.attention.in_proj_bias")
+        setp("attn_out_w", "fusion_layer.attention.out_proj.weight")
+        setp("attn_out_b", "fusion_layer.attention.out_proj.bias")
+        setp("attn_ln_w", "fusion_layer.norm.weight")
+        setp("attn_ln_b", "fusion_layer.norm.bias")
+        stride = 4 if use_batch_norm else 3
+        n_hidden = self.cfg.n_hidden
+        for l in range(n_hidden):
+            base = l * stride
+            for field, key in (("mlp_w", f"prediction_network.{base}.weight"),
+                               ("mlp_b", f"prediction_network.{base}.bias")):
+                t = g(key)
+                getattr(w, field)[l] = t.data_ptr() if t is not None else None
+            if use_batch_norm:
+                for field, suf in (("bn_w", "weight"), ("bn_b", "bias"), ("bn_mean", "running_mean"),
+                                   ("bn_var", "running_var")):
+                    t = g(f"prediction_network.{base + 2}.{suf}")
+                    getattr(w, field)[l] = t.data_ptr() if t is not None else None
+        last = n_hidden * stride
+        setp("out_w", f"prediction_network.{last}.weight")
+        setp("out_b", f"prediction_network.{last}.bias")
+        with torch.cuda.device(dev):
+            self._check(self.lib.pxr_load_weights(self._h, C.byref(w), _stream()), "pxr_load_weights")
+            torch.cuda.current_stream().synchronize()   # the fp32 sources in `keep` may now be dropped
+        self.n_rows = 0
+        self._items_ws = None
+
+    # ----------------------------------------------------------------- items
+    def precompute_items(self, item_embedding: torch.Tensor, tag_idx: torch.Tensor,
+                         vis: Optional[torch.Tensor], txt: Optional[torch.Tensor], num: Optional[torch.Tensor],
+                         item_idx: Optional[torch.Tensor] = None, item_base: int = 0,
+                         n_rows: Optional[int] = None):
+        """K1+K2 over ``n_rows`` item rows.  Row r describes global item
+        ``item_idx[r]`` (or ``item_base + r``); feature tensors are row-aligned."""
+        dev = self.device
+        n = int(n_rows if n_rows is not None else tag_idx.shape[0])
+        emb = _dev_f32(item_embedding, dev)
+        tag = tag_idx.to(device=dev, dtype=torch.int64).contiguous()
+        v = _dev_f32(vis, dev) if vis is not None and self.cfg.vision_dim else None
+        t = _dev_f32(txt, dev) if txt is not None and self.cfg.language_dim else None
+        x = _dev_f32(num, dev) if num is not None and self.cfg.num_numerical else None
+        for name, ten, dim in (("vision", v, self.cfg.vision_dim), ("language", t, self.cfg.language_dim),
+                               ("numerical", x, self.cfg.num_numerical)):
+            if dim and (ten is None or ten.shape[0] < n or ten.shape[-1] != dim):
+                raise ValueError(f"{name} features must be ({n}, {dim}), got "
+                                 f"{None if ten is None else tuple(ten.shape)}")
+        ii = item_idx.to(device=dev, dtype=torch.int64).contiguous() if item_idx is not None else None
+        nbytes = int(self.lib.pxr_items_bytes(self._h, n))
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 256
+        with torch.cuda.device(dev):
+            self._check(self.lib.pxr_precompute_items(
+                self._h, _ptr(emb), _ptr(ii), _ptr(tag), _ptr(v), _ptr(t), _ptr(x), n, int(item_base),
+                C.c_void_p(ws.data_ptr() + off), nbytes, _stream()), "pxr_precompute_items")
+        self._items_ws = ws
+        self._keep["items_in"] = (emb, tag, v, t, x, ii)   # inputs must outlive the async launch
+        self.n_rows, self.item_base = n, int(item_base)
+
+    # --------------------------------------------------------------- scoring
+    def score_topk(self, user_embedding: torch.Tensor, user_idx: torch.Tensor, k: int,
+                   seen_indptr: Optional[torch.Tensor] = None, seen_idx: Optional[torch.Tensor] = None
+                   ) -> Tuple[torch.Tensor, torch.Tensor]:
+        dev = self.device
+        n = int(user_idx.shape[0])
+        out_s = torch.empty((n, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((n, k), dtype=torch.int32, device=dev)
+        nbytes = int(self.lib.pxr_score_topk_bytes(self._h, n, k))
+        if self._score_ws is None or self._score_ws.numel() < nbytes + 256:
+            self._score_ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        ws = self._score_ws
+        off = (-ws.data_ptr()) % 256
+        with torch.cuda.device(dev):
+            self._check(self.lib.pxr_score_topk(
+                self._h, _ptr(user_embedding), _ptr(user_idx), n, _ptr(seen_indptr), _ptr(seen_idx), k,
+                _ptr(out_s), _ptr(out_i), C.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream()),
+                "pxr_score_topk")
+        return out_s, out_i
+
+    def score_pairs(self, user_embedding: torch.Tensor, user_idx: torch.Tensor, item_row: torch.Tensor,
+                    want_logit: bool = False):
+        dev = self.device
+        n = int(user_idx.shape[0])
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        logit = torch.empty(n, dtype=torch.float32, device=dev) if want_logit else None
+        with torch.cuda.device(dev):
+            self._check(self.lib.pxr_score_pairs(self._h, _ptr(user_embedding), _ptr(user_idx), _ptr(item_row), n,
+                                                 _ptr(out), _ptr(logit), _stream()), "pxr_score_pairs")
+        return (out, logit) if want_logit else out
+
+    # ---------------------------------------------------------------- merges
+    def merge_topk(self, scores: torch.Tensor, idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(S, n_users, K) per-shard lists -> (n_users, K); ties -> lower global index."""
+        return merge_topk(scores, idx)
+
+
+def merge_topk(scores: torch.Tensor, idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    S, n, k = scores.shape
+    scores = scores.contiguous()
+    idx = idx.to(torch.int32).contiguous()
+    out_s = torch.empty((n, k), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((n, k), dtype=torch.int32, device=scores.device)
+    with torch.cuda.device(scores.device):
+        rc = lib.pxr_merge_topk(_ptr(scores), _ptr(idx), S, n, k, _ptr(out_s), _ptr(out_i), _stream())
+    if rc != 0:
+        raise PxrError(f"pxr_merge_topk failed ({rc})")
+    return out_s, out_i
+
+
+_METRIC_COLS = ("precision", "recall", "f1", "hit_rate", "ndcg", "mrr", "ndcg_list_ideal")
+
+
+def ranking_metric_sums(topk_idx: torch.Tensor, gt_indptr: torch.Tensor, gt_idx: torch.Tensor,
+                        ks: Sequence[int]) -> np.ndarray:
+    """K5: per-cut-off sums over users, shape (len(ks), 7) float64 (host).  Column
+    order: precision, recall, f1, hit_rate, ndcg (tasks.py), mrr, ndcg (metrics.py)."""
+    lib = _lib.load()
+    dev = topk_idx.device
+    topk_idx = topk_idx.to(torch.int32).contiguous()
+    n, kstride = topk_idx.shape
+    ks = sorted(int(k) for k in ks)
+    # numpy-computed tables so device results are bit-identical to the reference's numpy arithmetic
+    disc = np.array([1.0 / np.log2(i + 2) for i in range(kstride)], dtype=np.float64)
+    ideal = np.zeros(kstride + 1, dtype=np.float64)
+    acc = 0
+    for i in range(kstride):
+        acc = acc + disc[i]          # Python left-to-right sum, as in tasks.py:744
+        ideal[i + 1] = acc
+    d_disc = torch.from_numpy(disc).to(dev)
+    d_ideal = torch.from_numpy(ideal).to(dev)
+    out = torch.zeros((len(ks), 7), dtype=torch.float64, device=dev)
+    nbytes = int(lib.pxr_metrics_bytes(n, len(ks)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ks_arr = (C.c_int32 * len(ks))(*ks)
+    gt_indptr = gt_indptr.to(device=dev, dtype=torch.int64).contiguous()
+    gt_idx = gt_idx.to(device=dev, dtype=torch.int32).contiguous()
+    with torch.cuda.device(dev):
+        rc = lib.pxr_metrics(_ptr(topk_idx), kstride, n, _ptr(gt_indptr), _ptr(gt_idx), ks_arr, len(ks),
+                             _ptr(d_disc), _ptr(d_ideal), _ptr(out), _ptr(ws), nbytes, _stream())
+    if rc != 0:
+        raise PxrError(f"pxr_metrics failed ({rc})")
+    return out.cpu().numpy()

@@ -1,0 +1,322 @@
+"""FastRecommender: drop-in for the reference inference ``Recommender``
+(reference ``src/inference/recommender.py:20-293``) on the full-catalogue path.
+
+Same constructor, same ``get_recommendations`` / ``get_item_score`` /
+``print_cache_stats`` / ``clear_cache`` surface and the same duck-typed
+``.dataset`` / ``.model`` attributes the evaluators read
+(``src/evaluation/tasks.py:171-175, 349-354, 816``), plus the batched
+``recommend_all`` the per-user string API can never match for throughput.
+
+What changes underneath: item features are uploaded and projected ONCE
+(``pxr_precompute_items``) instead of being re-stacked and re-uploaded for every
+user (recommender.py:162-191); string<->index mapping uses dictionaries built
+once instead of per-call ``LabelEncoder.transform`` scans (recommender.py:64,
+76, 191); user histories become one CSR; scoring + top-K run in libpxr.so.
+"""
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .engine import PxrEngine, merge_topk
+from .model import FastMultimodalRecommender
+
+
+@dataclass
+class ItemFeatureStore:
+    """Dense per-item cached features in item-encoder order (row i = item index i):
+    the post-backbone embeddings the hoisted frozen backbones emit."""
+
+    tag_idx: torch.Tensor                       # (NI,) int64
+    vis: Optional[torch.Tensor] = None          # (NI, Dv) fp32
+    txt: Optional[torch.Tensor] = None          # (NI, Dl) fp32
+    num: Optional[torch.Tensor] = None          # (NI, F)  fp32
+    missing: Optional[np.ndarray] = None        # (NI,) bool: items whose features could not be fetched
+
+    @property
+    def n_items(self) -> int:
+        return int(self.tag_idx.shape[0])
+
+    @staticmethod
+    def from_dataset(dataset, item_ids: Sequence[str], model: FastMultimodalRecommender) -> "ItemFeatureStore":
+        """Pull one feature dict per item the way the reference does
+        (recommender.py:239-269: dataset.feature_cache first, then
+        dataset._get_item_features) and stack them once.  Expected keys are those
+        of reference dataset.py:264-303 with cached features in place of raw
+        inputs: 'image' (Dv,), 'text_input_ids' (Dl,) float, 'numerical_features'
+        (F,), 'tag_idx' ()."""
+        n = len(item_ids)
+        tag = torch.zeros(n, dtype=torch.int64)
+        vis = torch.zeros(n, model.vision_dim) if model.vision_dim else None
+        txt = torch.zeros(n, model.language_dim) if model.language_dim else None
+        num = torch.zeros(n, model.num_numerical_features) if model.num_numerical_features else None
+        missing = np.zeros(n, dtype=bool)
+        cache = getattr(dataset, "feature_cache", None)
+        for i, iid in enumerate(item_ids):
+            feats = None
+            if cache is not None:
+                try:
+                    feats = cache.get(iid)
+                except Exception:
+                    feats = None
+            if not feats and hasattr(dataset, "_get_item_features"):
+                try:
+                    feats = dataset._get_item_features(iid)
+                except Exception:
+                    feats = None
+            if not feats:
+                missing[i] = True
+                continue
+            tag[i] = int(feats["tag_idx"]) if "tag_idx" in feats else 0
+            if vis is not None:
+                vis[i] = torch.as_tensor(feats["image"], dtype=torch.float32).reshape(-1)
+            if txt is not None:
+                txt[i] = torch.as_tensor(feats["text_input_ids"], dtype=torch.float32).reshape(-1)
+            if num is not None:
+                num[i] = torch.as_tensor(feats["numerical_features"], dtype=torch.float32).reshape(-1)
+        return ItemFeatureStore(tag, vis, txt, num, missing if missing.any() else None)
+
+
+def build_history_csr(user_index: Dict[str, int], item_index: Dict[str, int], interactions,
+                      n_users: int) -> Tuple[np.ndarray, np.ndarray]:
+    """One CSR of train histories (indptr int64, item idx int32 ascending per
+    user) replacing the per-call pandas mask of reference dataset.py:462-476."""
+    uu = interactions["user_id"].astype(str).map(user_index)
+    ii = interactions["item_id"].astype(str).map(item_index)
+    ok = uu.notna() & ii.notna()
+    u = uu[ok].to_numpy(dtype=np.int64)
+    i = ii[ok].to_numpy(dtype=np.int64)
+    pairs = np.unique(u * (1 << 32) + i)
+    u, i = pairs >> 32, pairs & 0xFFFFFFFF
+    indptr = np.zeros(n_users + 1, dtype=np.int64)
+    np.add.at(indptr, u + 1, 1)
+    np.cumsum(indptr, out=indptr)
+    return indptr, i.astype(np.int32)
+
+
+class FastRecommender:
+    def __init__(self, model: FastMultimodalRecommender, dataset, device: torch.device,
+                 cache_max_items: int = 1000, cache_dir: Optional[str] = None, cache_to_disk: bool = False,
+                 item_features: Optional[ItemFeatureStore] = None,
+                 history: Optional[Tuple[np.ndarray, np.ndarray]] = None,
+                 item_range: Optional[Tuple[int, int]] = None, user_block: int = 8192):
+        self.model = model
+        self.dataset = dataset
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("FastRecommender needs a CUDA device: the scoring path has no CPU fallback")
+        self.model.to(self.device)
+        self.model.eval()
+        self.cache_max_items = cache_max_items
+        self.feature_cache: Dict[str, Dict[str, torch.Tensor]] = {}
+        logging.basicConfig(level=logging.INFO)
+        self.logger = logging.getLogger(__name__)
+        self.user_block = int(user_block)
+
+        ucls = getattr(getattr(dataset, "user_encoder", None), "classes_", None)
+        icls = getattr(getattr(dataset, "item_encoder", None), "classes_", None)
+        self.user_ids: List[str] = [str(c) for c in ucls] if ucls is not None else []
+        self.item_ids: List[str] = [str(c) for c in icls] if icls is not None else []
+        self.user_index: Dict[str, int] = {u: i for i, u in enumerate(self.user_ids)}
+        self.item_index: Dict[str, int] = {it: i for i, it in enumerate(self.item_ids)}
+        self._item_ids_np = np.array(self.item_ids, dtype=object)
+
+        self.items = item_features if item_features is not None else \
+            ItemFeatureStore.from_dataset(dataset, self.item_ids, model)
+        if self.items.n_items != len(self.item_ids):
+            raise ValueError(f"item feature store has {self.items.n_items} rows, item encoder has {len(self.item_ids)}")
+        if self.items.missing is not None:
+            # reference: items without features score 0.0 (recommender.py:229-230)
+            raise NotImplementedError(
+                f"{int(self.items.missing.sum())} items have no cached features; the GPU path needs a complete "
+                "feature store (missing-feature items scoring 0.0 is not implemented yet)")
+
+        # train histories -> CSR (global item indices)
+        if history is not None:
+            self.hist_indptr, self.hist_idx = history
+        elif getattr(dataset, "interactions", None) is not None and len(self.user_ids):
+            self.hist_indptr, self.hist_idx = build_history_csr(self.user_index, self.item_index,
+                                                                dataset.interactions, len(self.user_ids))
+        else:
+            self.hist_indptr, self.hist_idx = None, None
+        self._d_hist_idx = None if self.hist_idx is None else torch.from_numpy(np.ascontiguousarray(self.hist_idx)).to(self.device)
+
+        lo, hi = item_range if item_range is not None else (0, len(self.item_ids))
+        self.item_lo, self.item_hi = int(lo), int(hi)
+        self._engine: Optional[PxrEngine] = None
+        self._engine_token = None
+
+    # -------------------------------------------------------------- catalogue
+    def engine(self) -> PxrEngine:
+        """Engine with this recommender's item range precomputed (K1+K2 run once)."""
+        eng = self.model.engine("catalogue")
+        token = (id(eng), self.model._engines["catalogue"][1], self.item_lo, self.item_hi)
+        if self._engine_token != token:
+            lo, hi = self.item_lo, self.item_hi
+            sl = slice(lo, hi)
+            eng.precompute_items(self.model.item_embedding.weight.detach(), self.items.tag_idx[sl],
+                                 None if self.items.vis is None else self.items.vis[sl],
+                                 None if self.items.txt is None else self.items.txt[sl],
+                                 None if self.items.num is None else self.items.num[sl],
+                                 item_idx=None, item_base=lo, n_rows=hi - lo)
+            self._engine, self._engine_token = eng, token
+        return eng
+
+    # ------------------------------------------------------------ batched API
+    def _seen_csr_for(self, users: np.ndarray):
+        """CSR restricted to ``users`` (device tensors), global item indices."""
+        if self.hist_indptr is None:
+            indptr = torch.zeros(len(users) + 1, dtype=torch.int64, device=self.device)
+            return indptr, torch.zeros(1, dtype=torch.int32, device=self.device)
+        starts, ends = self.hist_indptr[users], self.hist_indptr[users + 1]
+        lens = ends - starts
+        indptr = np.zeros(len(users) + 1, dtype=np.int64)
+        np.cumsum(lens, out=indptr[1:])
+        if len(users) and np.all(np.diff(users) == 1):
+            # contiguous user block: the block's CSR is a slice of the resident one
+            base = int(starts[0])
+            idx = self._d_hist_idx[base:base + int(indptr[-1])]
+            if idx.numel() == 0:
+                idx = torch.zeros(1, dtype=torch.int32, device=self.device)
+            return torch.from_numpy(indptr).to(self.device, non_blocking=True), idx
+        gather = np.concatenate([np.arange(s, e) for s, e in zip(starts, ends)]) if len(users) else np.zeros(0, np.int64)
+        idx = torch.from_numpy(np.ascontiguousarray(self.hist_idx[gather])).to(self.device) if len(gather) else \
+            torch.zeros(1, dtype=torch.int32, device=self.device)
+        return torch.from_numpy(indptr).to(self.device), idx
+
+    @torch.no_grad()
+    def recommend_all(self, user_indices, top_k: int = 10, filter_seen: bool = True
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Every user of ``user_indices`` (encoder indices) against every item of
+        this recommender's item range.  Returns device tensors
+        (scores (n, K) fp32 descending, item indices (n, K) int32, -inf / -1 padded)."""
+        eng = self.engine()
+        users = np.asarray(user_indices.cpu() if isinstance(user_indices, torch.Tensor) else user_indices,
+                           dtype=np.int64)
+        uemb = self.model.user_embedding.weight.detach()
+        outs_s, outs_i = [], []
+        for u0 in range(0, len(users), self.user_block):
+            blk = users[u0:u0 + self.user_block]
+            d_users = torch.from_numpy(np.ascontiguousarray(blk)).to(self.device, non_blocking=True)
+            if filter_seen:
+                indptr, idx = self._seen_csr_for(blk)
+                s, i = eng.score_topk(uemb, d_users, top_k, indptr, idx)
+            else:
+                s, i = eng.score_topk(uemb, d_users, top_k)
+            outs_s.append(s)
+            outs_i.append(i)
+        if not outs_s:
+            return (torch.empty((0, top_k), dtype=torch.float32, device=self.device),
+                    torch.empty((0, top_k), dtype=torch.int32, device=self.device))
+        return torch.cat(outs_s), torch.cat(outs_i)
+
+    # --------------------------------------------------------- reference API
+    def get_recommendations(self, user_id: str, top_k: int = 10, filter_seen: bool = True,
+                            candidates: Optional[List[str]] = None) -> List[Tuple[str, float]]:
+        """reference recommender.py:52-110 — same semantics: unknown user / no
+        candidates -> []; candidate order is encoder order (or the given list
+        filtered to known items); seen items dropped; STABLE descending sort, so
+        ties keep candidate order; first ``top_k``; Python floats."""
+        user_id = str(user_id)
+        if not self.user_ids or not self.item_ids:
+            self.logger.warning("User / item encoder not properly initialized.")
+            return []
+        u = self.user_index.get(user_id)
+        if u is None:
+            self.logger.warning(f"User '{user_id}' not found in the trained user encoder.")
+            return []
+        if candidates is None:
+            if filter_seen and self.hist_indptr is None:
+                seen = self._get_user_interactions(user_id)
+                return self._recommend_with_seen_set(u, top_k, seen)
+            s, i = self.recommend_all(np.array([u]), top_k=top_k, filter_seen=filter_seen)
+            s, i = s[0].cpu().numpy(), i[0].cpu().numpy()
+            return [(self.item_ids[int(ii)], float(ss)) for ss, ii in zip(s, i) if ii >= 0]
+        cand = [str(c) for c in candidates if str(c) in self.item_index]
+        if not cand:
+            self.logger.info(f"No valid candidate items found for user '{user_id}'.")
+            return []
+        if filter_seen:
+            seen = self._get_user_interactions(user_id)
+            cand = [c for c in cand if c not in seen]
+        if not cand:
+            self.logger.info(f"All candidate items for user '{user_id}' have been filtered.")
+            return []
+        scores = self._score_items_batch(u, cand)
+        pairs = list(zip(cand, scores))
+        pairs.sort(key=lambda x: x[1], reverse=True)       # stable, as recommender.py:105
+        return pairs[:top_k]
+
+    def _recommend_with_seen_set(self, u: int, top_k: int, seen: Iterable[str]):
+        idx = np.array(sorted({self.item_index[s] for s in seen if s in self.item_index}), dtype=np.int32)
+        eng = self.engine()
+        d_users = torch.tensor([u], dtype=torch.int64, device=self.device)
+        indptr = torch.tensor([0, len(idx)], dtype=torch.int64, device=self.device)
+        d_idx = torch.from_numpy(idx).to(self.device) if len(idx) else torch.zeros(1, dtype=torch.int32, device=self.device)
+        s, i = eng.score_topk(self.model.user_embedding.weight.detach(), d_users, top_k, indptr, d_idx)
+        s, i = s[0].cpu().numpy(), i[0].cpu().numpy()
+        return [(self.item_ids[int(ii)], float(ss)) for ss, ii in zip(s, i) if ii >= 0]
+
+    def get_item_score(self, user_id: str, item_id: str) -> float:
+        """reference recommender.py:112-141: 0.0 for unknown ids."""
+        u = self.user_index.get(str(user_id))
+        if u is None or str(item_id) not in self.item_index:
+            return 0.0
+        return self._score_items_batch(u, [str(item_id)])[0]
+
+    def _score_items_batch(self, u: int, item_ids_str: List[str]) -> List[float]:
+        """reference recommender.py:144-236 for one user and explicit items."""
+        if not item_ids_str:
+            return []
+        eng = self.engine()
+        gi = np.array([self.item_index[i] for i in item_ids_str], dtype=np.int64)
+        inside = (gi >= self.item_lo) & (gi < self.item_hi)
+        if not inside.all():
+            raise ValueError("candidate items outside this recommender's item range")
+        rows = torch.from_numpy(gi - self.item_lo).to(self.device)
+        users = torch.full((len(gi),), u, dtype=torch.int64, device=self.device)
+        out = eng.score_pairs(self.model.user_embedding.weight.detach(), users, rows)
+        return [float(x) for x in out.cpu().tolist()]
+
+    def _get_item_features(self, item_id_str: str):
+        """reference recommender.py:239-269 (evaluators call this, tasks.py:455)."""
+        i = self.item_index.get(str(item_id_str))
+        if i is None:
+            return None
+        feats = {"tag_idx": self.items.tag_idx[i]}
+        if self.items.vis is not None:
+            feats["image"] = self.items.vis[i]
+        if self.items.txt is not None:
+            feats["text_input_ids"] = self.items.txt[i]
+            feats["text_attention_mask"] = torch.ones(1, dtype=torch.long)
+        if self.items.num is not None:
+            feats["numerical_features"] = self.items.num[i]
+        return feats
+
+    def _get_user_interactions(self, user_id_str: str) -> set:
+        """reference recommender.py:271-281."""
+        if self.hist_indptr is not None:
+            u = self.user_index.get(str(user_id_str))
+            if u is None:
+                return set()
+            return {self.item_ids[j] for j in self.hist_idx[self.hist_indptr[u]:self.hist_indptr[u + 1]]}
+        try:
+            return set(self.dataset.get_user_history(str(user_id_str)))
+        except Exception as e:  # same swallow-and-log as the reference
+            self.logger.error(f"Error getting user interactions for user '{user_id_str}': {e}")
+            return set()
+
+    def print_cache_stats(self):
+        print(f"Feature store: {self.items.n_items} items resident on {self.device}")
+        print(f"Cache capacity: {self.cache_max_items}")
+
+    def clear_cache(self):
+        self.feature_cache.clear()
+        print("Feature cache cleared")
+
+
+__all__ = ["FastRecommender", "ItemFeatureStore", "build_history_csr", "merge_topk"]

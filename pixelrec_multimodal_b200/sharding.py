@@ -1,0 +1,53 @@
+"""Item-axis sharding across the GPUs of one box.
+
+Items [0, NI) are split into ``world`` contiguous ranges (contiguous so that
+"lower global index wins ties" survives concatenating shards in rank order).
+Each rank scores its shard for the same user block (``pxr_score_topk``), the
+per-shard top-K lists (fp32 score, int32 global index: 8*K bytes per user) are
+exchanged with ONE all-gather, and every rank merges them (``pxr_merge_topk``).
+No other communication is on the data path; metric sums need no collective
+because every rank ends up with the full lists.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous ceil(NI/world)-sized ranges; trailing ranks may be short or empty."""
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
+
+
+def allgather_topk(scores: torch.Tensor, idx: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(n, K) local lists -> (world, n, K) stacked in rank order."""
+    world = dist.get_world_size(group)
+    all_s = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
+    all_i = torch.empty((world,) + tuple(idx.shape), dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(all_s, scores.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, idx.contiguous(), group=group)
+    return all_s, all_i
+
+
+class ShardedTopK:
+    """Lock-step sharded scoring: ``local_topk(users, k, filter_seen)`` is the
+    rank's scorer over its item range (``FastRecommender.recommend_all`` in
+    production), ``merge`` the S-way merge (``pxr_merge_topk``)."""
+
+    def __init__(self, local_topk: Callable, merge: Optional[Callable] = None, group=None):
+        self.local_topk = local_topk
+        if merge is None:
+            from .engine import merge_topk as merge
+        self.merge = merge
+        self.group = group
+
+    def recommend_all(self, user_indices, top_k: int, filter_seen: bool = True):
+        s, i = self.local_topk(user_indices, top_k, filter_seen)
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return s, i
+        all_s, all_i = allgather_topk(s, i, self.group)
+        return self.merge(all_s, all_i)
