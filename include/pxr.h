@@ -181,6 +181,15 @@ int pxr_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, cons
                 const double* ideal, double* out_sums, void* workspace, size_t workspace_bytes,
                 pxr_stream stream);
 
+/* Live timing of the dominant kernel (the pair-scoring kernel of
+ * pxr_score_topk) with CUDA events recorded on the launching stream, for the
+ * roofline line of bench.py.  pxr_profile_read synchronises on the recorded
+ * events, returns the summed duration and launch count since the last read and
+ * resets both.  At most PXR_PROFILE_SLOTS launches are kept between reads. */
+#define PXR_PROFILE_SLOTS 1024
+int pxr_profile_enable(pxr_handle* h, int on);
+int pxr_profile_read(pxr_handle* h, double* total_ms, int64_t* n_launches);
+
 /* Introspection used by bench.py / tests. */
 int64_t pxr_launch_count(const pxr_handle* h);       /* kernels launched through this handle */
 int pxr_active_path(const pxr_handle* h);            /* pxr_path pxr_score_topk will use      */

@@ -41,7 +41,31 @@ extern "C" void pxr_destroy(pxr_handle* h) {
   if (!h) return;
   if (h->arena) cudaFree(h->arena);
   if (h->fast_w) cudaFree(h->fast_w);
+  if (h->prof_ev) { for (int i = 0; i < 2 * PXR_PROFILE_SLOTS; ++i) cudaEventDestroy(h->prof_ev[i]); delete[] h->prof_ev; }
   delete h;
+}
+
+extern "C" int pxr_profile_enable(pxr_handle* h, int on) {
+  if (!h) return PXR_ERR_INVALID;
+  if (on && !h->prof_ev) {
+    h->prof_ev = new cudaEvent_t[2 * PXR_PROFILE_SLOTS];
+    for (int i = 0; i < 2 * PXR_PROFILE_SLOTS; ++i) PXR_CUDA(h, cudaEventCreate(&h->prof_ev[i]));
+  }
+  h->profile = on != 0; h->prof_n = 0;
+  return PXR_OK;
+}
+
+extern "C" int pxr_profile_read(pxr_handle* h, double* total_ms, int64_t* n_launches) {
+  if (!h || !total_ms || !n_launches) return PXR_ERR_INVALID;
+  double tot = 0.0;
+  for (int i = 0; i < h->prof_n; ++i) {
+    PXR_CUDA(h, cudaEventSynchronize(h->prof_ev[2 * i + 1]));
+    float ms = 0.f;
+    PXR_CUDA(h, cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+    tot += ms;
+  }
+  *total_ms = tot; *n_launches = h->prof_n; h->prof_n = 0;
+  return PXR_OK;
 }
 
 extern "C" int64_t pxr_launch_count(const pxr_handle* h) { return h ? h->launches : 0; }

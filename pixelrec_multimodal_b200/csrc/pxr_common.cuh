@@ -49,6 +49,11 @@ struct pxr_handle {
   bool fast_ok = false;
   void* fast_w = nullptr;     // bf16 swizzled operand images + fp32 vectors (see score_tc.cu)
 
+  // live timing of the dominant kernel (pxr_profile_*)
+  bool profile = false;
+  cudaEvent_t* prof_ev = nullptr;   // 2 * PXR_PROFILE_SLOTS events, created lazily
+  int prof_n = 0;
+
   // precomputed item records (caller workspace)
   float* item_feats = nullptr;   // [n_rows][M-1][D] fp32
   void* item_fast = nullptr;     // fast-path per-item records
@@ -71,6 +76,14 @@ struct pxr_handle {
       return PXR_ERR_CUDA;                                                           \
     }                                                                                \
   } while (0)
+
+// bracket the dominant kernel launch with events when profiling is on
+static inline void pxr_prof_begin(pxr_handle* h, cudaStream_t st) {
+  if (h->profile && h->prof_n < PXR_PROFILE_SLOTS) cudaEventRecord(h->prof_ev[2 * h->prof_n], st);
+}
+static inline void pxr_prof_end(pxr_handle* h, cudaStream_t st) {
+  if (h->profile && h->prof_n < PXR_PROFILE_SLOTS) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], st); h->prof_n++; }
+}
 
 static inline size_t pxr_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -317,7 +317,9 @@ static int launch_score(pxr_handle* h, const ScoreParams& p, cudaStream_t st) {
   PXR_CUDA(h, cudaFuncSetAttribute(score_simt_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t blocks = (p.n_pairs + ROWS - 1) / ROWS;
   if (blocks > 0x7fffffffLL) PXR_FAIL(h, PXR_ERR_INVALID, "too many pairs for one launch");
+  if (p.dense) pxr_prof_begin(h, st);
   score_simt_kernel<ROWS><<<(unsigned)blocks, PXR_SIMT_THREADS, smem, st>>>(p);
+  if (p.dense) pxr_prof_end(h, st);
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
   return PXR_OK;

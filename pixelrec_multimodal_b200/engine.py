@@ -102,6 +102,16 @@ class PxrEngine:
     def active_path(self) -> str:
         return {1: "simt", 2: "tcgen05"}.get(self.lib.pxr_active_path(self._h), "?")
 
+    def profile(self, on: bool = True):
+        """Time the dominant kernel with CUDA events on the launching stream."""
+        self._check(self.lib.pxr_profile_enable(self._h, int(on)), "pxr_profile_enable")
+
+    def profile_read(self) -> Tuple[float, int]:
+        """(summed ms, launches) of the dominant kernel since the last read."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        self._check(self.lib.pxr_profile_read(self._h, C.byref(ms), C.byref(n)), "pxr_profile_read")
+        return float(ms.value), int(n.value)
+
     def set_path(self, path: str):
         self._check(self.lib.pxr_set_path(self._h, _lib.PATH[path]), "pxr_set_path")
 

@@ -77,6 +77,6 @@ class FullCatalogueEvaluator:
         res["by_k"] = by_k
         if self.keep_predictions:
             s, i = scores.cpu().numpy(), idx.cpu().numpy()
-            res["predictions"] = {r.user_ids[int(u)]: [(r.item_ids[int(b)], float(a)) for a, b in zip(s[j], i[j]) if b >= 0]
+            res["predictions"] = {str(r.user_ids[int(u)]): [(str(r.item_ids[int(b)]), float(a)) for a, b in zip(s[j], i[j]) if b >= 0]
                                   for j, u in enumerate(self.users)}
         return res

@@ -103,7 +103,8 @@ class FastRecommender:
                  cache_max_items: int = 1000, cache_dir: Optional[str] = None, cache_to_disk: bool = False,
                  item_features: Optional[ItemFeatureStore] = None,
                  history: Optional[Tuple[np.ndarray, np.ndarray]] = None,
-                 item_range: Optional[Tuple[int, int]] = None, user_block: int = 8192):
+                 item_range: Optional[Tuple[int, int]] = None, user_block: int = 8192,
+                 n_users: Optional[int] = None, n_items: Optional[int] = None):
         self.model = model
         self.dataset = dataset
         self.device = torch.device(device)
@@ -119,36 +120,67 @@ class FastRecommender:
 
         ucls = getattr(getattr(dataset, "user_encoder", None), "classes_", None)
         icls = getattr(getattr(dataset, "item_encoder", None), "classes_", None)
-        self.user_ids: List[str] = [str(c) for c in ucls] if ucls is not None else []
-        self.item_ids: List[str] = [str(c) for c in icls] if icls is not None else []
-        self.user_index: Dict[str, int] = {u: i for i, u in enumerate(self.user_ids)}
-        self.item_index: Dict[str, int] = {it: i for i, it in enumerate(self.item_ids)}
-        self._item_ids_np = np.array(self.item_ids, dtype=object)
+        # id tables are kept as given (no per-element copies: 8.9 M users at Pixel8M scale); the
+        # string -> index dictionaries are built on first use by the string API only
+        self.user_ids = ucls if ucls is not None else []
+        self.item_ids = icls if icls is not None else []
+        self.n_users = int(n_users if n_users is not None else len(self.user_ids))
+        self.n_items = int(n_items if n_items is not None else len(self.item_ids))
+        self._user_index: Optional[Dict[str, int]] = None
+        self._item_index: Optional[Dict[str, int]] = None
 
         self.items = item_features if item_features is not None else \
-            ItemFeatureStore.from_dataset(dataset, self.item_ids, model)
-        if self.items.n_items != len(self.item_ids):
-            raise ValueError(f"item feature store has {self.items.n_items} rows, item encoder has {len(self.item_ids)}")
+            ItemFeatureStore.from_dataset(dataset, [str(c) for c in self.item_ids], model)
+        if self.items.n_items != self.n_items:
+            raise ValueError(f"item feature store has {self.items.n_items} rows, item encoder has {self.n_items}")
         if self.items.missing is not None:
             # reference: items without features score 0.0 (recommender.py:229-230)
             raise NotImplementedError(
                 f"{int(self.items.missing.sum())} items have no cached features; the GPU path needs a complete "
                 "feature store (missing-feature items scoring 0.0 is not implemented yet)")
 
-        # train histories -> CSR (global item indices)
+        # train histories -> one CSR resident on the device (global item indices, ascending per user)
+        if history is None and getattr(dataset, "interactions", None) is not None and self.n_users:
+            history = build_history_csr(self.user_index, self.item_index, dataset.interactions, self.n_users)
+        self._h_hist = None                                     # host copy, made on demand
         if history is not None:
-            self.hist_indptr, self.hist_idx = history
-        elif getattr(dataset, "interactions", None) is not None and len(self.user_ids):
-            self.hist_indptr, self.hist_idx = build_history_csr(self.user_index, self.item_index,
-                                                                dataset.interactions, len(self.user_ids))
+            ip, ix = history
+            self._d_hist_indptr = torch.as_tensor(ip).to(device=self.device, dtype=torch.int64).contiguous()
+            self._d_hist_idx = torch.as_tensor(ix).to(device=self.device, dtype=torch.int32).contiguous()
+            if self._d_hist_idx.numel() == 0:
+                self._d_hist_idx = torch.zeros(1, dtype=torch.int32, device=self.device)
         else:
-            self.hist_indptr, self.hist_idx = None, None
-        self._d_hist_idx = None if self.hist_idx is None else torch.from_numpy(np.ascontiguousarray(self.hist_idx)).to(self.device)
+            self._d_hist_indptr, self._d_hist_idx = None, None
 
-        lo, hi = item_range if item_range is not None else (0, len(self.item_ids))
+        lo, hi = item_range if item_range is not None else (0, self.n_items)
         self.item_lo, self.item_hi = int(lo), int(hi)
         self._engine: Optional[PxrEngine] = None
         self._engine_token = None
+
+    @property
+    def user_index(self) -> Dict[str, int]:
+        if self._user_index is None:
+            self._user_index = {str(u): i for i, u in enumerate(self.user_ids)}
+        return self._user_index
+
+    @property
+    def item_index(self) -> Dict[str, int]:
+        if self._item_index is None:
+            self._item_index = {str(it): i for i, it in enumerate(self.item_ids)}
+        return self._item_index
+
+    @property
+    def has_history(self) -> bool:
+        return self._d_hist_indptr is not None
+
+    def device_history(self):
+        """(indptr int64, idx int32) of the resident train-history CSR, or (None, None)."""
+        return self._d_hist_indptr, self._d_hist_idx
+
+    def _host_history(self):
+        if self._h_hist is None:
+            self._h_hist = (self._d_hist_indptr.cpu().numpy(), self._d_hist_idx.cpu().numpy())
+        return self._h_hist
 
     # -------------------------------------------------------------- catalogue
     def engine(self) -> PxrEngine:
@@ -167,26 +199,25 @@ class FastRecommender:
         return eng
 
     # ------------------------------------------------------------ batched API
-    def _seen_csr_for(self, users: np.ndarray):
-        """CSR restricted to ``users`` (device tensors), global item indices."""
-        if self.hist_indptr is None:
-            indptr = torch.zeros(len(users) + 1, dtype=torch.int64, device=self.device)
+    def _seen_csr_for(self, users: np.ndarray, d_users: torch.Tensor):
+        """(seen_indptr, seen_idx) device tensors for ``pxr_score_topk``: offsets
+        of each user's ascending item list inside ``seen_idx`` (global indices)."""
+        if self._d_hist_indptr is None:
+            return torch.zeros(len(users) + 1, dtype=torch.int64, device=self.device), \
+                torch.zeros(1, dtype=torch.int32, device=self.device)
+        if len(users) and (len(users) == 1 or bool(np.all(np.diff(users) == 1))):
+            # contiguous user block: views of the resident CSR, nothing is copied
+            u0 = int(users[0])
+            return self._d_hist_indptr[u0:u0 + len(users) + 1], self._d_hist_idx
+        starts = self._d_hist_indptr[d_users]
+        lens = self._d_hist_indptr[d_users + 1] - starts
+        indptr = torch.zeros(len(users) + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(lens, 0, out=indptr[1:])
+        total = int(indptr[-1])
+        if total == 0:
             return indptr, torch.zeros(1, dtype=torch.int32, device=self.device)
-        starts, ends = self.hist_indptr[users], self.hist_indptr[users + 1]
-        lens = ends - starts
-        indptr = np.zeros(len(users) + 1, dtype=np.int64)
-        np.cumsum(lens, out=indptr[1:])
-        if len(users) and np.all(np.diff(users) == 1):
-            # contiguous user block: the block's CSR is a slice of the resident one
-            base = int(starts[0])
-            idx = self._d_hist_idx[base:base + int(indptr[-1])]
-            if idx.numel() == 0:
-                idx = torch.zeros(1, dtype=torch.int32, device=self.device)
-            return torch.from_numpy(indptr).to(self.device, non_blocking=True), idx
-        gather = np.concatenate([np.arange(s, e) for s, e in zip(starts, ends)]) if len(users) else np.zeros(0, np.int64)
-        idx = torch.from_numpy(np.ascontiguousarray(self.hist_idx[gather])).to(self.device) if len(gather) else \
-            torch.zeros(1, dtype=torch.int32, device=self.device)
-        return torch.from_numpy(indptr).to(self.device), idx
+        pos = torch.arange(total, device=self.device) + torch.repeat_interleave(starts - indptr[:-1], lens)
+        return indptr, self._d_hist_idx[pos]
 
     @torch.no_grad()
     def recommend_all(self, user_indices, top_k: int = 10, filter_seen: bool = True
@@ -203,7 +234,7 @@ class FastRecommender:
             blk = users[u0:u0 + self.user_block]
             d_users = torch.from_numpy(np.ascontiguousarray(blk)).to(self.device, non_blocking=True)
             if filter_seen:
-                indptr, idx = self._seen_csr_for(blk)
+                indptr, idx = self._seen_csr_for(blk, d_users)
                 s, i = eng.score_topk(uemb, d_users, top_k, indptr, idx)
             else:
                 s, i = eng.score_topk(uemb, d_users, top_k)
@@ -222,7 +253,7 @@ class FastRecommender:
         filtered to known items); seen items dropped; STABLE descending sort, so
         ties keep candidate order; first ``top_k``; Python floats."""
         user_id = str(user_id)
-        if not self.user_ids or not self.item_ids:
+        if not len(self.user_ids) or not len(self.item_ids):
             self.logger.warning("User / item encoder not properly initialized.")
             return []
         u = self.user_index.get(user_id)
@@ -230,12 +261,12 @@ class FastRecommender:
             self.logger.warning(f"User '{user_id}' not found in the trained user encoder.")
             return []
         if candidates is None:
-            if filter_seen and self.hist_indptr is None:
+            if filter_seen and not self.has_history:
                 seen = self._get_user_interactions(user_id)
                 return self._recommend_with_seen_set(u, top_k, seen)
             s, i = self.recommend_all(np.array([u]), top_k=top_k, filter_seen=filter_seen)
             s, i = s[0].cpu().numpy(), i[0].cpu().numpy()
-            return [(self.item_ids[int(ii)], float(ss)) for ss, ii in zip(s, i) if ii >= 0]
+            return [(str(self.item_ids[int(ii)]), float(ss)) for ss, ii in zip(s, i) if ii >= 0]
         cand = [str(c) for c in candidates if str(c) in self.item_index]
         if not cand:
             self.logger.info(f"No valid candidate items found for user '{user_id}'.")
@@ -259,7 +290,7 @@ class FastRecommender:
         d_idx = torch.from_numpy(idx).to(self.device) if len(idx) else torch.zeros(1, dtype=torch.int32, device=self.device)
         s, i = eng.score_topk(self.model.user_embedding.weight.detach(), d_users, top_k, indptr, d_idx)
         s, i = s[0].cpu().numpy(), i[0].cpu().numpy()
-        return [(self.item_ids[int(ii)], float(ss)) for ss, ii in zip(s, i) if ii >= 0]
+        return [(str(self.item_ids[int(ii)]), float(ss)) for ss, ii in zip(s, i) if ii >= 0]
 
     def get_item_score(self, user_id: str, item_id: str) -> float:
         """reference recommender.py:112-141: 0.0 for unknown ids."""
@@ -299,11 +330,12 @@ class FastRecommender:
 
     def _get_user_interactions(self, user_id_str: str) -> set:
         """reference recommender.py:271-281."""
-        if self.hist_indptr is not None:
+        if self.has_history:
             u = self.user_index.get(str(user_id_str))
             if u is None:
                 return set()
-            return {self.item_ids[j] for j in self.hist_idx[self.hist_indptr[u]:self.hist_indptr[u + 1]]}
+            ip, ix = self._host_history()
+            return {str(self.item_ids[int(j)]) for j in ix[ip[u]:ip[u + 1]]}
         try:
             return set(self.dataset.get_user_history(str(user_id_str)))
         except Exception as e:  # same swallow-and-log as the reference

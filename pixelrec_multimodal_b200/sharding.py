@@ -26,11 +26,13 @@ def shard_range(n_items: int, world: int, rank: int) -> Tuple[int, int]:
 def allgather_topk(scores: torch.Tensor, idx: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """(n, K) local lists -> (world, n, K) stacked in rank order."""
     world = dist.get_world_size(group)
-    all_s = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
-    all_i = torch.empty((world,) + tuple(idx.shape), dtype=idx.dtype, device=idx.device)
+    n, k = scores.shape
+    # the concatenated (world*n, K) form is the one both NCCL and gloo accept
+    all_s = torch.empty((world * n, k), dtype=scores.dtype, device=scores.device)
+    all_i = torch.empty((world * n, k), dtype=idx.dtype, device=idx.device)
     dist.all_gather_into_tensor(all_s, scores.contiguous(), group=group)
     dist.all_gather_into_tensor(all_i, idx.contiguous(), group=group)
-    return all_s, all_i
+    return all_s.view(world, n, k), all_i.view(world, n, k)
 
 
 class ShardedTopK:

@@ -245,3 +245,68 @@ def apply_logit_calibration(sd: Dict[str, np.ndarray], spec: ModelSpec, mean: fl
     scale = np.float32(target_std / max(std, 1e-12))
     sd[key + ".weight"] = (sd[key + ".weight"] * scale).astype(np.float32)
     sd[key + ".bias"] = ((sd[key + ".bias"] - np.float32(mean)) * scale).astype(np.float32)
+
+
+# --------------------------------------------------------------------------
+# torch generators for the big Pixel200K/1M/8M-shaped workloads (bench.py)
+# --------------------------------------------------------------------------
+def torch_workload(spec: ModelSpec, device, seed: int = SEED, with_histories: bool = True):
+    """Same distributions as the det_* generators but drawn
+    with a seeded ``torch.Generator`` on ``device`` so 1M-8M-user tables take
+    milliseconds.  Returns (state_dict of torch tensors, feature dict, history
+    dict or None).  The small dense weights still come from ``make_state_dict``
+    so they are identical to what the tests use."""
+    import dataclasses
+    import torch
+
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    D = spec.embedding_dim
+    small = dataclasses.replace(spec, n_users=1, n_items=1)
+    sd = {k: torch.from_numpy(np.asarray(v)).to(dev) for k, v in make_state_dict(small, seed=seed).items()}
+    s = 1.0 / np.sqrt(D)
+    sd["user_embedding.weight"] = torch.randn((spec.n_users, D), generator=g, device=dev) * s
+    sd["item_embedding.weight"] = torch.randn((spec.n_items, D), generator=g, device=dev) * s
+    NI = spec.n_items
+    feats = {}
+    if spec.vision_dim > 0:
+        v = torch.randn((NI, spec.vision_dim), generator=g, device=dev)
+        feats["vis"] = 10.0 * v / v.norm(dim=1, keepdim=True)
+    if spec.language_dim > 0:
+        t = torch.randn((NI, spec.language_dim), generator=g, device=dev)
+        feats["txt"] = t / t.norm(dim=1, keepdim=True)
+    if spec.num_numerical_features > 0:
+        feats["num"] = torch.randn((NI, spec.num_numerical_features), generator=g, device=dev)
+    ranks = torch.arange(1, spec.n_tags + 1, device=dev, dtype=torch.float64)
+    cdf = torch.cumsum(ranks ** -1.2, 0)
+    cdf = cdf / cdf[-1]
+    feats["tag_idx"] = torch.searchsorted(cdf, torch.rand(NI, generator=g, device=dev, dtype=torch.float64)).clamp_(max=spec.n_tags - 1)
+    hist = None
+    if with_histories:
+        hist = torch_histories(spec.n_users, NI, g, dev)
+    return sd, feats, hist
+
+
+def torch_histories(n_users: int, n_items: int, g, dev, mean_log: float = 2.6, sigma_log: float = 0.6,
+                    lo: int = 5, hi: int = 500):
+    """Vectorised leave-one-out histories: per user n_u ~ clip(LogNormal) Zipf(1.0)
+    draws, de-duplicated; one extra draw is the held-out test positive and is
+    removed from the train history.  Train CSR is ascending inside each user."""
+    import torch
+    n = torch.exp(mean_log + sigma_log * torch.randn(n_users, generator=g, device=dev)).clamp_(lo, min(hi, max(lo, n_items // 2))).long()
+    owner = torch.repeat_interleave(torch.arange(n_users, device=dev), n)
+    cdf = torch.cumsum(1.0 / torch.arange(1, n_items + 1, device=dev, dtype=torch.float64), 0)
+    cdf = cdf / cdf[-1]
+    perm = torch.randperm(n_items, generator=g, device=dev)
+    draw = lambda m: perm[torch.searchsorted(cdf, torch.rand(m, generator=g, device=dev, dtype=torch.float64)).clamp_(max=n_items - 1)]
+    items = draw(int(owner.numel()))
+    test_item = draw(n_users)
+    key = owner * n_items + items
+    key = key[key != torch.arange(n_users, device=dev)[owner] * n_items + test_item[owner]]
+    key = torch.unique(key)                                    # sorted: by user, then item
+    u, it = key // n_items, key % n_items
+    counts = torch.bincount(u, minlength=n_users)
+    indptr = torch.zeros(n_users + 1, dtype=torch.int64, device=dev)
+    indptr[1:] = torch.cumsum(counts, 0)
+    return dict(train_indptr=indptr, train_idx=it.to(torch.int32), test_item=test_item.to(torch.int32))

@@ -1,0 +1,178 @@
+"""CPU-side checks: libpxr.so loads and exports every symbol include/pxr.h
+declares (no compute calls without a GPU), the ctypes mirrors match the header,
+host-side logic (sharding ranges, history CSR, world-size-2 gloo merge), and the
+product path refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from pixelrec_multimodal_b200 import _lib, sharding
+from pixelrec_multimodal_b200.recommender import build_history_csr
+
+REPO = Path(__file__).resolve().parent.parent
+HEADER = (REPO / "include" / "pxr.h").read_text()
+
+
+def _declared_functions():
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    return sorted(set(re.findall(r"\b(pxr_[a-z0-9_]+)\s*\(", body)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pxr.h but not exported by libpxr.so"
+    assert set(names) == set(_lib.declared_symbols())
+    assert lib.pxr_version() == int(re.search(r"#define PXR_VERSION (\d+)", HEADER).group(1))
+
+
+def test_ctypes_structs_match_header(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "pxr.h"\nint main(){printf("%zu %zu\\n", sizeof(pxr_config), sizeof(pxr_weights));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", str(REPO / "include"), str(src), "-o", str(exe)], check=True)
+    a, b = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+    assert C.sizeof(_lib.PxrConfig) == a
+    assert C.sizeof(_lib.PxrWeights) == b
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C with no CUDA/torch types."""
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", str(REPO / "include" / "pxr.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    assert "torch" not in body.lower() and "Tensor" not in body
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from pixelrec_multimodal_b200 import FastMultimodalRecommender, PxrError
+    from pixelrec_multimodal_b200.engine import PxrEngine
+    with pytest.raises(PxrError):
+        PxrEngine(fusion_type="concatenate", embedding_dim=16, vision_dim=8, language_dim=8, num_numerical=2,
+                  hidden_dims=[16], n_tags=3)
+    m = FastMultimodalRecommender(n_users=4, n_items=4, n_tags=3, num_numerical_features=2, embedding_dim=16,
+                                  vision_model_name="cached8", language_model_name="cached8",
+                                  fusion_hidden_dims=[16])
+    z = torch.zeros(2, dtype=torch.long)
+    with pytest.raises(RuntimeError):
+        m(z, z, z, image=torch.zeros(2, 8), text_input_ids=torch.zeros(2, 8),
+          text_attention_mask=torch.ones(2, 1), numerical_features=torch.zeros(2, 2))
+
+
+def test_product_never_imports_oracle():
+    pkg = REPO / "pixelrec_multimodal_b200"
+    for p in pkg.rglob("*.py"):
+        txt = p.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), p
+    for p in list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
+        assert "oracle/" not in p.read_text(), p
+
+
+def test_state_dict_keys_mirror_reference():
+    """Key names / shapes of SURVEY.md A1 for the three fusion types."""
+    from pixelrec_multimodal_b200 import FastMultimodalRecommender
+    for ft, extra in (("concatenate", []),
+                      ("gated", ["fusion_layer.gating_network.0.weight", "fusion_layer.gating_network.0.bias"]),
+                      ("attention", ["fusion_layer.attention.in_proj_weight", "fusion_layer.attention.in_proj_bias",
+                                     "fusion_layer.attention.out_proj.weight", "fusion_layer.attention.out_proj.bias",
+                                     "fusion_layer.norm.weight", "fusion_layer.norm.bias"])):
+        m = FastMultimodalRecommender(n_users=5, n_items=6, n_tags=3, num_numerical_features=7, embedding_dim=64,
+                                      vision_model_name="cached512", language_model_name="cached384",
+                                      fusion_type=ft)
+        sd = m.state_dict()
+        for k in ["user_embedding.weight", "item_embedding.weight", "tag_embedding.weight",
+                  "vision_projection.0.weight", "language_projection.0.bias", "numerical_projection.0.weight",
+                  "prediction_network.0.weight", "prediction_network.2.running_var",
+                  "prediction_network.4.weight", "prediction_network.8.weight", "prediction_network.12.weight"] + extra:
+            assert k in sd, (ft, k)
+        assert tuple(sd["prediction_network.0.weight"].shape) == (512, 384 if ft == "concatenate" else 64)
+        assert tuple(sd["prediction_network.12.weight"].shape) == (1, 128)
+        assert tuple(sd["vision_projection.0.weight"].shape) == (64, 512)
+    with pytest.raises(ValueError):
+        FastMultimodalRecommender(n_users=5, n_items=6, n_tags=3, num_numerical_features=7, fusion_type="bogus")
+
+
+def test_shard_ranges_cover_and_are_contiguous():
+    for n in (0, 1, 7, 96282, 407082):
+        for w in (1, 2, 4, 8):
+            r = [sharding.shard_range(n, w, k) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            for a, b in zip(r, r[1:]):
+                assert a[1] == b[0]
+            assert all(lo <= hi for lo, hi in r)
+
+
+def test_history_csr():
+    import pandas as pd
+    ui = {"a": 0, "b": 1, "c": 2}
+    ii = {f"i{j}": j for j in range(6)}
+    df = pd.DataFrame({"user_id": ["b", "a", "b", "b", "zz", "a"], "item_id": ["i5", "i2", "i1", "i5", "i0", "nope"]})
+    indptr, idx = build_history_csr(ui, ii, df, 3)
+    assert indptr.tolist() == [0, 1, 3, 3]
+    assert idx.tolist() == [2, 1, 5]
+    assert idx.dtype == np.int32 and indptr.dtype == np.int64
+
+
+_GLOO_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["PXR_REPO"])
+from pixelrec_multimodal_b200.sharding import ShardedTopK, shard_range
+from oracle import pxr_oracle as orc
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+rng = np.random.default_rng(5)
+NU, NI, K = 9, 37, 6
+scores = np.round(rng.standard_normal((NU, NI)), 1).astype(np.float32)   # rounding creates ties
+lo, hi = shard_range(NI, world, rank)
+def local_topk(users, k, filter_seen):
+    s = np.full((len(users), k), -np.inf, np.float32); i = np.full((len(users), k), -1, np.int32)
+    for r, u in enumerate(users):
+        sel, sc = orc.topk_from_scores(scores[u, lo:hi].astype(np.float64), k, item_base=lo)
+        s[r, :len(sel)] = sc; i[r, :len(sel)] = sel
+    return torch.from_numpy(s), torch.from_numpy(i)
+def merge(all_s, all_i):
+    S, n, k = all_s.shape
+    out_s = np.full((n, k), -np.inf, np.float32); out_i = np.full((n, k), -1, np.int32)
+    for r in range(n):
+        lists = []
+        for s in range(S):
+            m = all_i[s, r].numpy() >= 0
+            lists.append((all_i[s, r].numpy()[m].astype(np.int64), all_s[s, r].numpy()[m].astype(np.float64)))
+        idx, sc = orc.merge_topk(lists, k)
+        out_s[r, :len(idx)] = sc; out_i[r, :len(idx)] = idx
+    return torch.from_numpy(out_s), torch.from_numpy(out_i)
+st = ShardedTopK(local_topk, merge)
+s, i = st.recommend_all(np.arange(NU), K, False)
+for u in range(NU):
+    sel, sc = orc.topk_from_scores(scores[u].astype(np.float64), K)
+    assert i[u].tolist() == sel.tolist(), (rank, u, i[u].tolist(), sel.tolist())
+dist.barrier(); dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_sharded_topk_world2_gloo(tmp_path):
+    """N>1 path on CPU: 2 gloo ranks, each owning a contiguous item range, one
+    all-gather of the per-shard top-K lists, merge == top-K of the full row
+    (including tie-break by lower global index across the shard boundary)."""
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, PXR_REPO=str(REPO), MASTER_ADDR="127.0.0.1", MASTER_PORT="29731", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "OK" in o

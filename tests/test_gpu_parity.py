@@ -1,0 +1,283 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes ->
+libpxr.so), against the CPU oracle and the committed reference outputs.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8(d)):
+  * SIMT fp32 path: |s - s_ref| <= 2e-5 (fp32 summation-order noise; the
+    reference's own fp32 run differs from its fp64 run by up to 7e-5).
+  * tcgen05 bf16 path: |s - s_ref| <= 2e-3 * max(|s_ref|, 1e-3) on scores is the
+    target; the test bound is stated per test next to the assertion.
+  * top-K indices: identical wherever the oracle gap between neighbours exceeds
+    the score tolerance, swaps only inside the tolerance band; ties -> lower
+    item index.  Metrics: equal to the oracle's to 1e-12 on identical lists.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pxr_oracle as orc
+from pixelrec_multimodal_b200 import synthetic as syn
+from tests import _cases as cs
+
+pytestmark = pytest.mark.gpu
+
+SIMT_TOL = 2e-5
+
+
+def _fwd(model, c, path=None):
+    spec, feats, ii = c["spec"], c["feats"], c["items"]
+    dev = "cuda"
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
+    kw = dict(user_idx=t(c["users"], torch.long), item_idx=t(ii, torch.long), tag_idx=t(feats["tag_idx"][ii], torch.long))
+    if spec.vision_dim:
+        kw["image"] = t(feats["vis"][ii], torch.float32)
+    if spec.language_dim:
+        kw["text_input_ids"] = t(feats["txt"][ii], torch.float32)
+        kw["text_attention_mask"] = torch.ones(len(ii), 1, dtype=torch.long, device=dev)
+    if spec.num_numerical_features:
+        kw["numerical_features"] = t(feats["num"][ii], torch.float32)
+    return model(**kw)
+
+
+@pytest.mark.parametrize("name", cs.FORWARD_CASES)
+def test_forward_matches_reference_golden(name):
+    """FastMultimodalRecommender.forward == the reference module's forward
+    (tests/golden, produced by the unmodified reference) on identical weights."""
+    c = cs.load_forward_case(name)
+    model = cs.torch_model_from(c["spec"], c["sd"])
+    out = _fwd(model, c)
+    assert out.shape == (len(c["users"]), 1) and out.dtype == torch.float32 and out.is_cuda
+    got = out[:, 0].double().cpu().numpy()
+    scale = max(1.0, float(np.max(np.abs(c["ref64"]))))
+    assert np.max(np.abs(got - c["ref64"])) <= 1e-4 * scale, name   # fp32 vs the reference's fp64 run
+    assert np.max(np.abs(got - c["ref32"])) <= 1e-4 * scale, name
+    assert model.engine("forward").launch_count > 0
+
+
+def _check_topk(got_s, got_i, ref_row, k, seen, tol_abs, tol_rel):
+    """ref_row: oracle scores (fp64) of every item for this user."""
+    ref_sel, ref_sc = orc.topk_from_scores(ref_row, k, seen=seen)
+    n = len(ref_sel)
+    gi, gs = got_i[:n], got_s[:n]
+    assert np.all(got_i[n:] == -1) and np.all(np.isneginf(got_s[n:]))
+    assert np.all(gi >= 0) and len(set(gi.tolist())) == n
+    if seen is not None and len(seen):
+        assert not set(gi.tolist()) & set(int(x) for x in seen)
+    band = lambda s: tol_abs + tol_rel * abs(s)
+    # scores of the returned items agree with the oracle
+    assert np.all(np.abs(gs - ref_row[gi]) <= np.array([band(s) for s in ref_row[gi]]))
+    # returned list is sorted by (score desc, index asc)
+    for a in range(n - 1):
+        assert gs[a] > gs[a + 1] or (gs[a] == gs[a + 1] and gi[a] < gi[a + 1])
+    # position-wise: identical, or a swap inside the tolerance band
+    for j in range(n):
+        if gi[j] != ref_sel[j]:
+            assert abs(ref_row[gi[j]] - ref_sc[j]) <= 2 * band(ref_sc[j]), (j, gi[j], ref_sel[j])
+    return int(np.sum(gi == ref_sel))
+
+
+def _topk_case(fusion, path, n_users=48, n_items=1500, k=50, full=True, seed_off=0):
+    kw = {} if full else dict(embedding_dim=16, vision_dim=32, language_dim=24, fusion_hidden_dims=[64, 32, 16])
+    spec = syn.ModelSpec(n_users=n_users, n_items=n_items, fusion_type=fusion, **kw)
+    sd, feats = cs.make_workload(spec, syn.SEED + 11 + seed_off)
+    indptr, idx, test_item = syn.make_histories(n_users, n_items, seed=syn.SEED + 11 + seed_off, lo=3, hi=40)
+    return spec, sd, feats, indptr, idx, test_item
+
+
+def _engine_for(spec, sd, feats, path="auto", item_lo=0, item_hi=None):
+    model = cs.torch_model_from(spec, sd, kernel_path=path)
+    eng = model.engine("catalogue")
+    hi = spec.n_items if item_hi is None else item_hi
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a[item_lo:hi])).cuda()
+    eng.precompute_items(model.item_embedding.weight.detach(), t(feats["tag_idx"]), t(feats.get("vis")),
+                         t(feats.get("txt")), t(feats.get("num")), item_base=item_lo, n_rows=hi - item_lo)
+    return model, eng
+
+
+@pytest.mark.parametrize("fusion", ["concatenate", "gated", "attention"])
+def test_score_topk_simt_matches_oracle(fusion):
+    spec, sd, feats, indptr, idx, _ = _topk_case(fusion, "simt")
+    model, eng = _engine_for(spec, sd, feats, "simt")
+    assert eng.active_path == "simt"
+    users = np.arange(spec.n_users)
+    ref = orc.score_block(sd, cs.spec_cfg(spec), users, 0, spec.n_items, feats, dtype=np.float64)
+    s, i = eng.score_topk(model.user_embedding.weight.detach(), torch.from_numpy(users).cuda(), 50,
+                          torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda())
+    s, i = s.cpu().numpy().astype(np.float64), i.cpu().numpy()
+    same = 0
+    for u in users:
+        same += _check_topk(s[u], i[u], ref[u], 50, idx[indptr[u]:indptr[u + 1]], SIMT_TOL, 0.0)
+    assert same >= 0.98 * 50 * len(users)
+    # no filter
+    s2, i2 = eng.score_topk(model.user_embedding.weight.detach(), torch.from_numpy(users).cuda(), 10)
+    for u in users:
+        _check_topk(s2[u].cpu().numpy().astype(np.float64), i2[u].cpu().numpy(), ref[u], 10, None, SIMT_TOL, 0.0)
+
+
+def test_score_pairs_logits_simt():
+    spec, sd, feats, *_ = _topk_case("gated", "simt", n_users=16, n_items=300)
+    model, eng = _engine_for(spec, sd, feats, "simt")
+    rng = np.random.default_rng(3)
+    uu, ii = rng.integers(0, spec.n_users, 1000), rng.integers(0, spec.n_items, 1000)
+    s, z = eng.score_pairs(model.user_embedding.weight.detach(), torch.from_numpy(uu).cuda(),
+                           torch.from_numpy(ii).cuda(), want_logit=True)
+    zr = orc.forward_pairs(sd, cs.spec_cfg(spec), uu, ii, feats["tag_idx"][ii], feats["vis"][ii], feats["txt"][ii],
+                           feats["num"][ii], return_logit=True)
+    assert np.max(np.abs(z.cpu().numpy() - zr)) <= 2e-4
+    assert np.max(np.abs(s.cpu().numpy() - orc.final_activation(zr, "sigmoid"))) <= SIMT_TOL
+
+
+def test_topk_edge_cases():
+    """k > catalogue, a user who has seen everything, empty user batch, empty shard."""
+    spec, sd, feats, *_ = _topk_case("concatenate", "simt", n_users=6, n_items=20, full=False)
+    model, eng = _engine_for(spec, sd, feats, "simt")
+    uemb = model.user_embedding.weight.detach()
+    users = torch.arange(3).cuda()
+    indptr = torch.tensor([0, 20, 20, 23]).cuda()
+    seen = torch.tensor(list(range(20)) + [4, 5, 19], dtype=torch.int32).cuda()
+    s, i = eng.score_topk(uemb, users, 32, indptr, seen)
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    assert np.all(i[0] == -1) and np.all(np.isneginf(s[0]))                 # everything filtered
+    assert np.sum(i[1] >= 0) == 20 and np.all(i[1][20:] == -1)              # k > n_items -> padded
+    assert np.sum(i[2] >= 0) == 17 and not {4, 5, 19} & set(i[2].tolist())
+    ref = orc.score_block(sd, cs.spec_cfg(spec), np.arange(3), 0, 20, feats)
+    _check_topk(s[1].astype(np.float64), i[1], ref[1], 32, None, SIMT_TOL, 0)
+    s0, i0 = eng.score_topk(uemb, torch.zeros(0, dtype=torch.long).cuda(), 5)
+    assert s0.shape == (0, 5) and i0.shape == (0, 5)
+    # empty item shard: all padding
+    model2, eng2 = _engine_for(spec, sd, feats, "simt", item_lo=20, item_hi=20)
+    s, i = eng2.score_topk(model2.user_embedding.weight.detach(), users, 4)
+    assert np.all(i.cpu().numpy() == -1) and np.all(np.isneginf(s.cpu().numpy()))
+
+
+def test_merge_topk_with_ties():
+    from pixelrec_multimodal_b200.engine import merge_topk
+    rng = np.random.default_rng(9)
+    S, n, k = 4, 33, 50
+    sc = np.round(rng.standard_normal((S, n, k)), 1).astype(np.float32)      # many ties
+    sc = -np.sort(-sc, axis=2)
+    ix = np.stack([np.stack([np.sort(rng.choice(1000, k, replace=False)) + 1000 * s for _ in range(n)]) for s in range(S)])
+    # ix ascending + sc descending per list => equal scores are already index-ascending inside a shard list
+    ix = ix.astype(np.int32)
+    sc[3, :, 40:] = -np.inf
+    ix[3, :, 40:] = -1                                                        # a short shard list
+    gs, gi = merge_topk(torch.from_numpy(sc).cuda(), torch.from_numpy(ix).cuda())
+    gs, gi = gs.cpu().numpy(), gi.cpu().numpy()
+    for u in range(n):
+        lists = [(ix[s, u][ix[s, u] >= 0].astype(np.int64), sc[s, u][ix[s, u] >= 0].astype(np.float64)) for s in range(S)]
+        ri, rs = orc.merge_topk(lists, k)
+        assert gi[u].tolist() == ri.tolist()
+        assert np.array_equal(gs[u].astype(np.float64), rs)
+
+
+def test_sharded_equals_unsharded_single_gpu():
+    """Item-axis sharding emulated on one GPU: per-shard top-K
+    lists merged by pxr_merge_topk == the unsharded top-K (bit-exact)."""
+    from pixelrec_multimodal_b200.engine import merge_topk
+    from pixelrec_multimodal_b200.sharding import shard_range
+    spec, sd, feats, indptr, idx, _ = _topk_case("gated", "simt", n_users=24, n_items=1003)
+    users = torch.arange(spec.n_users).cuda()
+    d_indptr, d_idx = torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda()
+    model, eng = _engine_for(spec, sd, feats, "simt")
+    fs, fi = eng.score_topk(model.user_embedding.weight.detach(), users, 50, d_indptr, d_idx)
+    parts_s, parts_i = [], []
+    for r in range(4):
+        lo, hi = shard_range(spec.n_items, 4, r)
+        m, e = _engine_for(spec, sd, feats, "simt", lo, hi)
+        s, i = e.score_topk(m.user_embedding.weight.detach(), users, 50, d_indptr, d_idx)
+        assert int(i.max()) < hi and (int(i[i >= 0].min()) >= lo if (i >= 0).any() else True)
+        parts_s.append(s)
+        parts_i.append(i)
+    ms, mi = merge_topk(torch.stack(parts_s), torch.stack(parts_i))
+    assert torch.equal(mi, fi) and torch.equal(ms, fs)
+
+
+def test_metrics_match_oracle():
+    from pixelrec_multimodal_b200 import ranking_metrics
+    rng = np.random.default_rng(1)
+    n, K, NI = 500, 50, 400
+    recs = np.stack([rng.permutation(NI)[:K] for _ in range(n)]).astype(np.int32)
+    recs[7, 30:] = -1                          # a short list (catalogue exhausted)
+    recs[8, :] = -1                            # empty list
+    npos = rng.integers(0, 6, n)               # some users have no positives
+    gt = [rng.choice(NI, c, replace=False) for c in npos]
+    indptr = np.concatenate([[0], np.cumsum(npos)]).astype(np.int64)
+    gt_idx = np.concatenate(gt).astype(np.int32) if indptr[-1] else np.zeros(0, np.int32)
+    got = ranking_metrics(torch.from_numpy(recs).cuda(), indptr, gt_idx, [10, 50])
+    for k in (10, 50):
+        all_recs = [[int(x) for x in recs[u][:k] if x >= 0] for u in range(n)]
+        all_pos = [set(int(x) for x in g) for g in gt]
+        want = orc.retrieval_metrics(all_recs, all_pos, k)
+        for key in ("avg_precision_at_k", "avg_recall_at_k", "avg_f1_at_k", "avg_hit_rate_at_k", "avg_ndcg_at_k", "avg_mrr"):
+            assert abs(got[k][key] - want[key]) <= 1e-12, (k, key, got[k][key], want[key])
+        alt = np.mean([orc.ndcg_metrics(r, p, k) if p else 0.0 for r, p in zip(all_recs, all_pos)])
+        assert abs(got[k]["avg_ndcg_list_ideal_at_k"] - alt) <= 1e-12
+        assert got[k]["num_users_evaluated"] == n
+
+
+def test_metrics_reference_known_answer():
+    """reference tests/unit/src/evaluation/test_tasks.py:84-108 through pxr_metrics."""
+    from pixelrec_multimodal_b200 import ranking_metrics
+    # items: i1..i100 -> 0..99 ; u1 recs [i2, i50, i1] positives {i1, i3}; u2 recs [i60,i70,i80] positives {i4,i5}
+    recs = torch.tensor([[1, 49, 0], [59, 69, 79]], dtype=torch.int32).cuda()
+    got = ranking_metrics(recs, np.array([0, 2, 4]), np.array([0, 2, 3, 4], dtype=np.int32), [3])[3]
+    assert got["avg_precision_at_k"] == pytest.approx((1 / 3) / 2, abs=1e-15)
+    assert got["avg_recall_at_k"] == pytest.approx((1 / 2) / 2, abs=1e-15)
+    assert got["avg_mrr"] == pytest.approx((1 / 3) / 2, abs=1e-15)
+    assert got["num_users_evaluated"] == 2
+
+
+@pytest.mark.parametrize("fusion", ["concatenate", "gated", "attention"])
+def test_recommender_matches_reference_lists(fusion):
+    """FastRecommender.get_recommendations / get_item_score vs the lists the
+    reference Recommender produced (tests/golden/recommender_lists.json)."""
+    from pixelrec_multimodal_b200 import FastRecommender
+    blob = cs.load_recommender_golden()[fusion]
+    spec = syn.ModelSpec(**blob["spec"])
+    sd, feats = cs.build_case(spec, blob["seed"], blob["cal_mean"], blob["cal_std"])
+    indptr, idx = np.array(blob["train_indptr"]), np.array(blob["train_idx"])
+    ds = cs.LightDataset(spec, feats, indptr, idx)
+    model = cs.torch_model_from(spec, sd)
+    rec = FastRecommender(model, ds, torch.device("cuda"))
+    for u in range(spec.n_users):
+        uid = ds.uids[u]
+        case = blob["cases"][uid]
+        for key, kwargs in (("top10_filter", dict(top_k=10, filter_seen=True)),
+                            ("top5_nofilter", dict(top_k=5, filter_seen=False)),
+                            ("cands", dict(top_k=4, filter_seen=False,
+                                           candidates=[ds.iids[j] for j in (40, 3, 17, 3, 29)] + ["nope"]))):
+            got = rec.get_recommendations(uid, **kwargs)
+            want = case[key]
+            assert len(got) == len(want)
+            assert all(isinstance(g[0], str) and isinstance(g[1], float) for g in got)
+            for (gi, gs), (wi, ws) in zip(got, want):
+                assert abs(gs - ws) <= 1e-4
+            if [g[0] for g in got] != [w[0] for w in want]:
+                # only swaps of near-equal scores are acceptable
+                for (gi, gs), (wi, ws) in zip(got, want):
+                    assert gi == wi or abs(gs - ws) <= 1e-5
+        assert abs(rec.get_item_score(uid, ds.iids[5]) - case["score_i5"]) <= 1e-4
+    assert rec.get_recommendations("nobody", top_k=5) == []
+    assert rec.get_item_score("nobody", ds.iids[0]) == 0.0
+    assert rec.get_item_score(ds.uids[0], "nope") == 0.0
+
+
+def test_full_catalogue_evaluator():
+    import pandas as pd
+    from pixelrec_multimodal_b200 import FastRecommender, FullCatalogueEvaluator
+    spec, sd, feats, indptr, idx, test_item = _topk_case("concatenate", "auto", n_users=40, n_items=300, full=False)
+    ds = cs.LightDataset(spec, feats, indptr, idx)
+    model = cs.torch_model_from(spec, sd)
+    rec = FastRecommender(model, ds, torch.device("cuda"))
+    ok = test_item >= 0
+    test_df = pd.DataFrame({"user_id": [ds.uids[u] for u in np.nonzero(ok)[0]],
+                            "item_id": [ds.iids[int(j)] for j in test_item[ok]]})
+    ev = FullCatalogueEvaluator(rec, test_df, top_k=50, ks=[10, 50], filter_seen=True, keep_predictions=True)
+    res = ev.evaluate()
+    recs = [[it for it, _ in res["predictions"][uid]] for uid in test_df["user_id"]]
+    pos = [{it} for it in test_df["item_id"]]
+    want = orc.retrieval_metrics(recs, pos, 50)
+    for key in ("avg_precision_at_k", "avg_recall_at_k", "avg_f1_at_k", "avg_hit_rate_at_k", "avg_ndcg_at_k", "avg_mrr"):
+        assert abs(res[key] - want[key]) <= 1e-12, key
+    assert res["num_users_evaluated"] == len(test_df) and res["evaluation_method"] == "full_evaluation"
+    want10 = orc.retrieval_metrics([r[:10] for r in recs], pos, 10)
+    assert abs(res["by_k"][10]["avg_ndcg_at_k"] - want10["avg_ndcg_at_k"]) <= 1e-12
