@@ -369,3 +369,52 @@ def fold_batchnorm(sd, use_batch_norm: bool, dt=np.float64):
         else:
             scale, shift = None, None
     return ws, bs
+
+
+# --------------------------------------------------------------------------
+# reduced-precision emulation of the tcgen05 kernel's rounding points
+# --------------------------------------------------------------------------
+def round_bf16(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even to bfloat16 (8-bit significand), returned as float64."""
+    a = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    a = (a + 0x7FFF + ((a >> 16) & 1)) & 0xFFFF0000
+    return a.astype(np.uint32).view(np.float32).astype(np.float64)
+
+
+def round_fp16(x: np.ndarray) -> np.ndarray:
+    return np.asarray(x, dtype=np.float64).astype(np.float16).astype(np.float64)
+
+
+def forward_pairs_lowp(sd, cfg, user_idx, item_idx, tag_idx, vis=None, txt=None, num=None, rnd=round_bf16,
+                       return_logit=False):
+    """The same forward with the operand roundings of the fused tcgen05 kernel
+    (csrc/score_tc.cu): BatchNorm folded into the next Linear, the fused vector
+    (gated) or layer-1 activation, every hidden activation and the hidden-layer
+    weights rounded to the 16-bit operand format, fp32/fp64 accumulation,
+    fp32 biases, last Linear in full precision.  Used to separate "the kernel
+    computes what it documents" (kernel vs this, tight) from "what 16-bit
+    operands cost" (this vs forward_pairs, reported)."""
+    dt = np.float64
+    act = cfg.get("fusion_activation", "relu")
+    feats = modality_features(sd, act, np.asarray(user_idx), np.asarray(item_idx), np.asarray(tag_idx), vis, txt, num, dt)
+    ft = cfg.get("fusion_type", "concatenate")
+    ws, bs = fold_batchnorm(sd, bool(cfg.get("use_batch_norm", True)))
+    if ft == "gated":
+        x = rnd(gated_fusion(sd, feats, dt))
+        h = x
+        start = 0
+    elif ft == "concatenate":
+        # layer 1 is split into per-user and per-item partials, summed in full precision
+        x = np.concatenate(feats, axis=1)
+        h = rnd(activation(x @ ws[0].T + bs[0], act))
+        start = 1
+    else:
+        raise ValueError("no reduced-precision kernel for fusion type " + ft)
+    for li in range(start, len(ws) - 1):
+        z = h @ rnd(ws[li]).T + bs[li]
+        a = activation(z, act)
+        h = rnd(a) if li < len(ws) - 2 else a
+    z = (h @ ws[-1].T + bs[-1])[:, 0]
+    if return_logit:
+        return z
+    return final_activation(z, cfg.get("final_activation", "sigmoid"))

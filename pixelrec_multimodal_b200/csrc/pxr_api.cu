@@ -245,8 +245,8 @@ static int64_t simt_chunk_users(const pxr_handle* h, int64_t n_users) {
 extern "C" size_t pxr_score_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k) {
   if (!h || n_users <= 0) return 256;
   size_t simt = pxr_align_up((size_t)simt_chunk_users(h, n_users) * (size_t)(h->n_rows > 0 ? h->n_rows : 1) * sizeof(float), 256);
-  size_t tc = h->fast_ok ? pxr_tc_topk_bytes(h, n_users, k) : 0;
-  return (h->path == PXR_PATH_TCGEN05 ? tc : simt) + 256;
+  if (h->path == PXR_PATH_TCGEN05 && pxr_tc_can_run(h, k)) return pxr_tc_topk_bytes(h, n_users, k) + 256;
+  return simt + 256;
 }
 
 extern "C" int pxr_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
@@ -260,7 +260,7 @@ extern "C" int pxr_score_topk(pxr_handle* h, const float* user_embedding, const 
   if (n_users == 0) return PXR_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (workspace_bytes < pxr_score_topk_bytes(h, n_users, k)) PXR_FAIL(h, PXR_ERR_WORKSPACE, "score workspace too small: %zu < %zu", workspace_bytes, pxr_score_topk_bytes(h, n_users, k));
-  if (h->path == PXR_PATH_TCGEN05)
+  if (h->path == PXR_PATH_TCGEN05 && pxr_tc_can_run(h, k))
     return pxr_tc_score_topk(h, user_embedding, user_idx, n_users, seen_indptr, seen_idx, k, out_scores, out_idx, workspace, workspace_bytes, st);
   if (h->n_rows == 0) {   // empty catalogue shard: every list is padding
     PXR_CUDA(h, cudaMemsetAsync(out_idx, 0xFF, sizeof(int32_t) * n_users * k, st));

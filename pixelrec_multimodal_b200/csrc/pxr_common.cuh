@@ -47,6 +47,7 @@ struct pxr_handle {
 
   // fast (tcgen05) path images
   bool fast_ok = false;
+  bool tc_attr_set = false;
   void* fast_w = nullptr;     // bf16 swizzled operand images + fp32 vectors (see score_tc.cu)
 
   // live timing of the dominant kernel (pxr_profile_*)
@@ -224,6 +225,7 @@ int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_user
 
 // tcgen05 path (score_tc.cu)
 bool pxr_tc_supported(const pxr_handle* h);
+bool pxr_tc_can_run(const pxr_handle* h, int32_t k);   // this call (k, shard size) fits the kernel's limits
 size_t pxr_tc_weight_bytes(const pxr_handle* h);
 int pxr_tc_prepare_weights(pxr_handle* h, cudaStream_t st);
 size_t pxr_tc_item_bytes(const pxr_handle* h, int64_t n_rows);

@@ -310,3 +310,81 @@ def torch_histories(n_users: int, n_items: int, g, dev, mean_log: float = 2.6, s
     indptr = torch.zeros(n_users + 1, dtype=torch.int64, device=dev)
     indptr[1:] = torch.cumsum(counts, 0)
     return dict(train_indptr=indptr, train_idx=it.to(torch.int32), test_item=test_item.to(torch.int32))
+
+
+# --------------------------------------------------------------------------
+# "trained-like" conditioning of a random model (workload generation only)
+# --------------------------------------------------------------------------
+def condition_like_trained(sd, spec: ModelSpec, feats, n_users: int = 64, n_items: int = 512, target_std: float = 2.0):
+    """Make a random-init model numerically resemble a trained one, in place.
+
+    Two things a trained checkpoint has and a random one lacks:
+      * BatchNorm running statistics that MATCH the activations they normalise
+        (training sets them to the batch statistics).  Random running stats leave a
+        large common offset in every layer, so the pair-dependent part of the logit
+        is a small difference of large numbers and any reduced-precision path looks
+        ~10x worse than it would on a real model.
+      * logits spread over several units (scores over (0, 1)) instead of the
+        random-init [0.47, 0.52] band.
+    ``sd`` / ``feats`` are dicts of torch tensors (any device) or numpy arrays (then
+    converted and written back as numpy).  Statistics come from a sample of
+    ``n_users x n_items`` pairs pushed through plain torch ops: this is workload
+    generation, not the scoring path."""
+    import torch
+    import torch.nn.functional as F
+
+    as_np = not isinstance(next(iter(sd.values())), torch.Tensor)
+    T = {k: torch.as_tensor(np.asarray(v) if as_np else v) for k, v in sd.items()}
+    Ft = {k: torch.as_tensor(np.asarray(v) if as_np else v) for k, v in feats.items()}
+    dev = T["user_embedding.weight"].device
+    nu, ni = min(n_users, spec.n_users), min(n_items, spec.n_items)
+    uu = torch.arange(nu, device=dev).repeat_interleave(ni)
+    ii = torch.arange(ni, device=dev).repeat(nu)
+    act = {"relu": F.relu, "gelu": F.gelu, "tanh": torch.tanh, "leaky_relu": lambda x: F.leaky_relu(x, 0.01),
+           "silu": F.silu}.get((spec.fusion_activation or "relu").lower(), F.relu)
+
+    def proj(x, prefix):
+        y = act(F.linear(x, T[prefix + ".0.weight"].double(), T[prefix + ".0.bias"].double()))
+        if prefix + ".3.weight" in T:
+            y = act(F.linear(y, T[prefix + ".3.weight"].double(), T[prefix + ".3.bias"].double()))
+        return y
+
+    toks = [T["user_embedding.weight"].double()[uu], T["item_embedding.weight"].double()[ii],
+            T["tag_embedding.weight"].double()[Ft["tag_idx"][ii].long()]]
+    for key, prefix in (("vis", "vision_projection"), ("txt", "language_projection"), ("num", "numerical_projection")):
+        if key in Ft and prefix + ".0.weight" in T:
+            toks.append(proj(Ft[key][ii].double(), prefix))
+    if spec.fusion_type == "concatenate":
+        x = torch.cat(toks, 1)
+    elif spec.fusion_type == "gated":
+        g = torch.softmax(F.linear(torch.cat(toks, 1), T["fusion_layer.gating_network.0.weight"].double(),
+                                   T["fusion_layer.gating_network.0.bias"].double()), -1)
+        x = (torch.stack(toks, 1) * g.unsqueeze(-1)).sum(1)
+    else:
+        X = torch.stack(toks, 0)
+        Dm = X.shape[-1]
+        a, _ = F.multi_head_attention_forward(
+            X, X, X, Dm, spec.num_attention_heads, T["fusion_layer.attention.in_proj_weight"].double(),
+            T["fusion_layer.attention.in_proj_bias"].double(), None, None, False, 0.0,
+            T["fusion_layer.attention.out_proj.weight"].double(), T["fusion_layer.attention.out_proj.bias"].double(),
+            training=False, need_weights=False)
+        x = F.layer_norm(X + a, (Dm,), T["fusion_layer.norm.weight"].double(), T["fusion_layer.norm.bias"].double(),
+                         1e-5).mean(0)
+    stride = 4 if spec.use_batch_norm else 3
+    for li in range(len(spec.fusion_hidden_dims)):
+        p = f"prediction_network.{li * stride}"
+        x = act(F.linear(x, T[p + ".weight"].double(), T[p + ".bias"].double()))
+        if spec.use_batch_norm:
+            bn = f"prediction_network.{li * stride + 2}"
+            mean, var = x.mean(0), x.var(0, unbiased=False) + 1e-3
+            T[bn + ".running_mean"] = mean.to(T[bn + ".running_mean"].dtype)
+            T[bn + ".running_var"] = var.to(T[bn + ".running_var"].dtype)
+            x = (x - mean) / torch.sqrt(var + 1e-5) * T[bn + ".weight"].double() + T[bn + ".bias"].double()
+    last = f"prediction_network.{len(spec.fusion_hidden_dims) * stride}"
+    z = F.linear(x, T[last + ".weight"].double(), T[last + ".bias"].double())[:, 0]
+    scale = target_std / max(float(z.std()), 1e-12)
+    T[last + ".bias"] = ((T[last + ".bias"].double() - z.mean()) * scale).to(T[last + ".bias"].dtype)
+    T[last + ".weight"] = (T[last + ".weight"].double() * scale).to(T[last + ".weight"].dtype)
+    for k in list(sd.keys()):
+        sd[k] = T[k].cpu().numpy() if as_np else T[k]
+    return sd
