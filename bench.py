@@ -25,7 +25,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 from pathlib import Path
 
@@ -62,38 +61,44 @@ def peaks():
     return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        super().__init__(daemon=True)
-        self.gpu, self.rows, self._stop_evt = gpu_index, [], threading.Event()
+        self.gpu, self.proc = gpu_index, None
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            rows = [[x.strip() for x in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+        isnum = lambda v: v.replace(".", "", 1).isdigit()
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and isnum(r[0])]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and isnum(r[1])]
+        pw = [float(r[2]) for r in rows if len(r) >= 7 and isnum(r[2])]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(rows)}
 
 
 # ---------------------------------------------------------------------------
@@ -110,6 +115,7 @@ def cpu_workload(cfg_name: str, seed: int):
         NU, NI, fusion, _ = CONFIGS[cfg_name]
         spec = syn.ModelSpec(n_users=NU, n_items=NI, fusion_type=fusion)
         sd, feats, hist = syn.torch_workload(spec, "cpu", seed=seed)
+        syn.condition_like_trained(sd, spec, feats)
         torch.set_num_threads(os.cpu_count() or 1)
         _CPU_WL[(cfg_name, seed)] = dict(sd=sd, feats=feats, indptr=hist["train_indptr"], idx=hist["train_idx"],
                                          cfg=cs.spec_cfg(spec), NU=NU, NI=NI, fusion=fusion)
@@ -187,6 +193,8 @@ def b200_arm(args):
     NU, NI, fusion, desc = CONFIGS[args.config]
     spec = syn.ModelSpec(n_users=NU, n_items=NI, fusion_type=fusion)
     sd, feats, hist = syn.torch_workload(spec, dev, seed=args.seed)      # identical on every rank (same seed)
+    # BatchNorm statistics matched to the activations and logits spread to std 2, like a trained checkpoint
+    syn.condition_like_trained(sd, spec, feats)
 
     model = FastMultimodalRecommender(
         n_users=NU, n_items=NI, n_tags=spec.n_tags, num_numerical_features=spec.num_numerical_features,
@@ -194,8 +202,6 @@ def b200_arm(args):
         language_model_name=f"cached{spec.language_dim}", use_contrastive=False, fusion_type=fusion,
         fusion_hidden_dims=list(spec.fusion_hidden_dims), kernel_path=args.path).to(dev)
     model.load_state_dict(sd, strict=False)
-    # calibrate the output layer so scores spread over (0,1) like a trained model
-    _calibrate(model, feats, dev)
 
     class _Enc:
         def __init__(self, n, p): self.classes_ = _LazyIds(n, p)
@@ -344,27 +350,10 @@ class _LazyIds:
         return f"{self.prefix}{int(i):08d}"
 
 
-def _calibrate(model, feats, dev):
-    """Rescale the output Linear so pre-sigmoid logits of a sample have mean 0 /
-    std 2: random-init scores would collapse into [0.47, 0.52]."""
-    import torch
-    n = min(512, feats["tag_idx"].shape[0])
-    users = torch.arange(64, device=dev).repeat_interleave(n)
-    items = torch.arange(n, device=dev).repeat(64)
-    _, z = model(users, items, feats["tag_idx"][items], image=feats["vis"][items], text_input_ids=feats["txt"][items],
-                 text_attention_mask=torch.ones(1, device=dev), numerical_features=feats["num"][items], return_logits=True)
-    mean, std = float(z.mean()), float(z.std())
-    last = [m for m in model.prediction_network if isinstance(m, torch.nn.Linear)][-1]
-    with torch.no_grad():
-        scale = 2.0 / max(std, 1e-9)
-        last.bias.copy_((last.bias - mean) * scale)
-        last.weight.mul_(scale)
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="B", choices=list(CONFIGS))

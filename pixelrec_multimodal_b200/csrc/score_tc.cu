@@ -292,7 +292,7 @@ score_gated_kernel(const __grid_constant__ Params p) {
         }
         ptx::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(BAR(BAR_A_FULL), 0);
+        if (lane == 0) ptx::mbar_arrive_cluster_release(BAR(BAR_A_FULL), 0);
       }
     }
   } else if (warp == 4) {
@@ -328,7 +328,7 @@ score_gated_kernel(const __grid_constant__ Params p) {
         ptx::commit2_mc(BAR(BAR_D3_FULL), 3);
       };
       for (int T = 0; T < NT; ++T) {
-        ptx::mbar_wait(BAR(BAR_A_FULL), T & 1);
+        ptx::mbar_wait_cluster(BAR(BAR_A_FULL), T & 1);
         ptx::tc_fence_after();
         issue_m1(0);
         issue_m1(1);

@@ -281,3 +281,155 @@ def test_full_catalogue_evaluator():
     assert res["num_users_evaluated"] == len(test_df) and res["evaluation_method"] == "full_evaluation"
     want10 = orc.retrieval_metrics([r[:10] for r in recs], pos, 10)
     assert abs(res["by_k"][10]["avg_ndcg_at_k"] - want10["avg_ndcg_at_k"]) <= 1e-12
+
+
+# ======================================================================================
+# tcgen05 path (csrc/score_tc.cu).  Two-step parity:
+#   (1) kernel == the oracle with the kernel's documented 16-bit operand roundings
+#       (oracle.forward_pairs_lowp): tight, |ds| <= 2e-3 (fp32 vs fp64 accumulation; an activation that lands on a
+#       bf16 rounding boundary can flip to the neighbouring value: measured max 5.0e-4);
+#   (2) that emulation vs the exact oracle is what bf16 operands cost: on these trained-like
+#       synthetic weights |ds| <= 3e-2 absolute (measured max 2.4e-2, rms 4e-3; logits
+#       |dz| rms 0.02 at logit std 2).  THIS is the stated bf16 tolerance of the scoring path.
+# Top-K: identical to the emulated oracle's list except swaps inside band (1); against the
+# exact oracle, differences only inside band (2).  Ties -> lower item index.
+# ======================================================================================
+TC_EMU_TOL = 2e-3
+TC_BF16_TOL = 3e-2
+
+
+def _tc_workload(n_users, n_items, seed, fusion="gated"):
+    spec = syn.ModelSpec(n_users=n_users, n_items=n_items, fusion_type=fusion)
+    sd = syn.make_state_dict(spec, seed=seed)
+    feats = syn.make_item_features(spec, seed=seed)
+    syn.condition_like_trained(sd, spec, feats)
+    indptr, idx, test_item = syn.make_histories(n_users, n_items, seed=seed, lo=3, hi=min(60, max(4, n_items // 3)))
+    return spec, sd, feats, indptr, idx, test_item
+
+
+def _lowp_scores(sd, spec, feats, users, rnd=None):
+    rnd = rnd or orc.round_bf16
+    NI = spec.n_items
+    out = np.empty((len(users), NI))
+    for r, u in enumerate(users):
+        ii = np.arange(NI)
+        out[r] = orc.forward_pairs_lowp(sd, cs.spec_cfg(spec), np.full(NI, u), ii, feats["tag_idx"], feats["vis"],
+                                        feats["txt"], feats["num"], rnd=rnd)
+    return out
+
+
+def _structural_checks(s, i, k, n_items, indptr=None, idx=None, item_lo=0):
+    """size-independent properties of every list: sorted by (score desc, index asc), unique,
+    inside the item range, no seen item, padding only at the tail"""
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    valid = i >= 0
+    assert np.all(valid[:, :-1] >= valid[:, 1:])                      # padding only at the tail
+    assert np.all(np.isneginf(s[~valid])) and np.all(np.isfinite(s[valid]))
+    assert np.all((i[valid] >= item_lo) & (i[valid] < item_lo + n_items))
+    ds = s[:, :-1] - s[:, 1:]
+    both = valid[:, :-1] & valid[:, 1:]
+    assert np.all(ds[both] >= 0)
+    tie = both & (ds == 0)
+    assert np.all(i[:, :-1][tie] < i[:, 1:][tie])
+    srt = np.sort(np.where(valid, i, -np.arange(1, i.shape[1] + 1)[None, :]), axis=1)
+    assert np.all(srt[:, 1:] != srt[:, :-1])                           # no duplicates
+    if indptr is not None:
+        for u in range(i.shape[0]):
+            assert not (set(i[u][valid[u]].tolist()) & set(idx[indptr[u]:indptr[u + 1]].tolist())), u
+    return s, i
+
+
+@pytest.mark.parametrize("n_users,n_items,k,filt", [(48, 1500, 50, True), (16, 48, 64, False), (33, 1000, 10, True)])
+def test_tcgen05_gated_matches_emulated_and_exact_oracle(n_users, n_items, k, filt):
+    spec, sd, feats, indptr, idx, _ = _tc_workload(n_users, n_items, syn.SEED + 21)
+    model, eng = _engine_for(spec, sd, feats, "tcgen05")
+    assert eng.active_path == "tcgen05"
+    users = np.arange(n_users)
+    args = (torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda()) if filt else ()
+    s, i = eng.score_topk(model.user_embedding.weight.detach(), torch.from_numpy(users).cuda(), k, *args)
+    s, i = _structural_checks(s, i, k, n_items, indptr if filt else None, idx)
+    s = s.astype(np.float64)
+    emu = _lowp_scores(sd, spec, feats, users)
+    ref = orc.score_block(sd, cs.spec_cfg(spec), users, 0, n_items, feats)
+    assert np.max(np.abs(emu - ref)) <= TC_BF16_TOL          # what bf16 operands cost on this model
+    same_emu = same_ref = total = 0
+    for u in users:
+        seen = idx[indptr[u]:indptr[u + 1]] if filt else None
+        same_emu += _check_topk(s[u], i[u], emu[u], k, seen, TC_EMU_TOL, 0.0)
+        same_ref += _check_topk(s[u], i[u], ref[u], k, seen, TC_BF16_TOL, 0.0)
+        total += min(k, n_items - (len(seen) if seen is not None else 0))
+    assert same_emu >= 0.97 * total, (same_emu, total)       # identical to the emulation except near-ties
+    print(f"tcgen05 top-{k}: {same_emu}/{total} positions identical to the bf16-emulated oracle, "
+          f"{same_ref}/{total} to the exact oracle")
+
+
+def test_tcgen05_many_units_and_item_splits():
+    """More user groups than CTA pairs (several units per pair: list reset between units) and an item
+    range split across units (partial lists merged by K4): sampled users vs the emulated oracle, all
+    users for the structural properties, and tcgen05 == sharded tcgen05 + merge bit-for-bit."""
+    from pixelrec_multimodal_b200.engine import merge_topk
+    from pixelrec_multimodal_b200.sharding import shard_range
+    n_users, n_items, k = 2500, 1203, 50
+    spec, sd, feats, indptr, idx, _ = _tc_workload(n_users, n_items, syn.SEED + 22)
+    model, eng = _engine_for(spec, sd, feats, "tcgen05")
+    users = torch.arange(n_users).cuda()
+    d_indptr, d_idx = torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda()
+    fs, fi = eng.score_topk(model.user_embedding.weight.detach(), users, k, d_indptr, d_idx)
+    s, i = _structural_checks(fs, fi, k, n_items, indptr, idx)
+    sample = np.array([0, 1, 7, 8, 15, 16, 17, 1183, 1184, 1199, 2047, 2048, 2491, 2496, 2499])
+    emu = _lowp_scores(sd, spec, feats, sample)
+    for r, u in enumerate(sample):
+        _check_topk(s[u].astype(np.float64), i[u], emu[r], k, idx[indptr[u]:indptr[u + 1]], TC_EMU_TOL, 0.0)
+    # a ragged user subset (not a multiple of 16, arbitrary order) gives the same lists
+    sub = torch.tensor([2499, 3, 1184, 77, 16], device="cuda")
+    sub_ptr = torch.zeros(6, dtype=torch.int64)
+    chunks = []
+    for r, u in enumerate(sub.tolist()):
+        chunks.append(idx[indptr[u]:indptr[u + 1]])
+        sub_ptr[r + 1] = sub_ptr[r] + len(chunks[-1])
+    ss, si = eng.score_topk(model.user_embedding.weight.detach(), sub, k, sub_ptr.cuda(),
+                            torch.from_numpy(np.concatenate(chunks)).cuda())
+    assert torch.equal(si, fi[sub]) and torch.equal(ss, fs[sub])
+    # item-axis shards + K4 merge == unsharded, bit for bit (per-pair arithmetic does not depend on the tiling)
+    parts_s, parts_i = [], []
+    for r in range(3):
+        lo, hi = shard_range(n_items, 3, r)
+        m, e = _engine_for(spec, sd, feats, "tcgen05", lo, hi)
+        ps, pi = e.score_topk(m.user_embedding.weight.detach(), users, k, d_indptr, d_idx)
+        parts_s.append(ps); parts_i.append(pi)
+    ms_, mi_ = merge_topk(torch.stack(parts_s), torch.stack(parts_i))
+    assert torch.equal(mi_, fi) and torch.equal(ms_, fs)
+
+
+def test_tcgen05_full_size_properties():
+    """BASELINE.json configs[1] catalogue size (96 282 items), one block of users: structural properties
+    of every list and agreement with the fp32 SIMT path inside the stated bf16 band."""
+    n_users, n_items, k = 512, 96282, 50
+    spec = syn.ModelSpec(n_users=n_users, n_items=n_items, fusion_type="gated")
+    sd, feats, hist = syn.torch_workload(spec, "cuda", seed=7)
+    syn.condition_like_trained(sd, spec, feats)
+    from pixelrec_multimodal_b200 import FastMultimodalRecommender
+    out = {}
+    for path in ("tcgen05", "simt"):
+        m = FastMultimodalRecommender(n_users=n_users, n_items=n_items, n_tags=spec.n_tags, num_numerical_features=7,
+                                      embedding_dim=64, vision_model_name="cached512", language_model_name="cached384",
+                                      fusion_type="gated", kernel_path=path).cuda()
+        m.load_state_dict(sd, strict=False)
+        e = m.engine("catalogue")
+        e.precompute_items(m.item_embedding.weight.detach(), feats["tag_idx"], feats["vis"], feats["txt"], feats["num"])
+        nu = n_users if path == "tcgen05" else 24
+        out[path] = e.score_topk(m.user_embedding.weight.detach(), torch.arange(nu).cuda(), k, hist["train_indptr"][:nu + 1],
+                                 hist["train_idx"])
+    ip, ix = hist["train_indptr"].cpu().numpy(), hist["train_idx"].cpu().numpy()
+    s, i = _structural_checks(*out["tcgen05"], k, n_items, ip, ix)
+    s2, i2 = out["simt"][0].cpu().numpy(), out["simt"][1].cpu().numpy()
+    for u in range(24):
+        # every item the fp32 path ranks in its top-50 with a margin above the band must be in the bf16 list too
+        kth = s[u][k - 1]
+        sure = i2[u][s2[u] > kth + 2 * TC_BF16_TOL]
+        assert set(sure.tolist()) <= set(i[u].tolist()), u
+        common = np.intersect1d(i[u], i2[u])
+        assert len(common) >= 10
+        a = {int(x): float(y) for x, y in zip(i[u], s[u])}
+        b = {int(x): float(y) for x, y in zip(i2[u], s2[u])}
+        assert max(abs(a[c] - b[c]) for c in common.tolist()) <= TC_BF16_TOL
