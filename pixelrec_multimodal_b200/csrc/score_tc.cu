@@ -54,12 +54,14 @@ constexpr uint32_t OFF_A1 = 196608;       // 128 rows x 128 B (K = 64 bf16), SWI
 constexpr uint32_t OFF_MISC = 212992;
 
 // tensor-memory map (columns)
-constexpr uint32_t TM_D1 = 0;             // 2 buffers x 64 cols; H1 chunk packed into the first 32 of each
-constexpr uint32_t TM_D3 = 128;           // 128 cols
+constexpr uint32_t TM_D1 = 0;             // layer-1 chunk buffers 0,1: 64 cols each; H1 chunk packed into the first 32
+constexpr uint32_t TM_D3 = 128;           // 128 cols: layer-3 accumulator at tile end, chunk buffers 2,3 in between
+__host__ __device__ constexpr uint32_t tm_buf(int b) { return b < 2 ? TM_D1 + 64u * b : TM_D3 + 64u * (b - 2); }
 constexpr uint32_t TM_D2 = 256;           // 256 cols; H2 halves packed at +0..63 and +128..191
 
 enum {
-  BAR_W = 0, BAR_A_FULL, BAR_A_EMPTY, BAR_D1_FULL0, BAR_D1_FULL1, BAR_H1_FULL0, BAR_H1_FULL1, BAR_D2_FULL,
+  BAR_W = 0, BAR_A_FULL, BAR_A_EMPTY, BAR_D1_FULL0, BAR_D1_FULL1, BAR_D1_FULL2, BAR_D1_FULL3, BAR_H1_FULL0, BAR_H1_FULL1,
+  BAR_H1_FULL2, BAR_H1_FULL3, BAR_D2_FULL,
   BAR_H2_FULL0, BAR_H2_FULL1, BAR_D3_FULL, BAR_D3_EMPTY, BAR_UNIT_DONE, BAR_UNIT_RESET, N_BARS
 };
 
@@ -155,8 +157,7 @@ score_gated_kernel(const __grid_constant__ Params p) {
     ptx::mbar_init(BAR(BAR_W), 1);
     ptx::mbar_init(BAR(BAR_A_FULL), 8);
     ptx::mbar_init(BAR(BAR_A_EMPTY), 1);
-    ptx::mbar_init(BAR(BAR_D1_FULL0), 1); ptx::mbar_init(BAR(BAR_D1_FULL1), 1);
-    ptx::mbar_init(BAR(BAR_H1_FULL0), 8); ptx::mbar_init(BAR(BAR_H1_FULL1), 8);
+    for (int b = 0; b < 4; ++b) { ptx::mbar_init(BAR(BAR_D1_FULL0 + b), 1); ptx::mbar_init(BAR(BAR_H1_FULL0 + b), 8); }
     ptx::mbar_init(BAR(BAR_D2_FULL), 1);
     ptx::mbar_init(BAR(BAR_H2_FULL0), 8); ptx::mbar_init(BAR(BAR_H2_FULL1), 8);
     ptx::mbar_init(BAR(BAR_D3_FULL), 1);
@@ -305,15 +306,22 @@ score_gated_kernel(const __grid_constant__ Params p) {
       const uint64_t dW2 = ptx::smem_desc_sw128(base + OFF_W2);
       const uint64_t dW3 = ptx::smem_desc_sw128(base + OFF_W3);
       constexpr uint32_t I1 = ptx::idesc_bf16(256, 64), I2 = ptx::idesc_bf16(256, 256), I3 = ptx::idesc_bf16(256, 128);
-      uint32_t h1ph[2] = {0, 0};
-      auto issue_m1 = [&](int c) {        // D1[c&1] = A1 . W1[chunk c]^T   (K = 64: 4 steps of 16)
+      uint32_t h1ph[4] = {0, 0, 0, 0};
+      auto issue_m1 = [&](int c) {        // D1[c % 4] = A1 . W1[chunk c]^T   (K = 64: 4 steps of 16)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          ptx::mma2_ss(tmem + TM_D1 + (c & 1) * 64, dA1 + 2 * k, dW1 + (uint64_t)(c * 4096 >> 4) + 2 * k, I1, k > 0);
-        ptx::commit2_mc(BAR(BAR_D1_FULL0 + (c & 1)), 3);
+          ptx::mma2_ss(tmem + tm_buf(c & 3), dA1 + 2 * k, dW1 + (uint64_t)(c * 4096 >> 4) + 2 * k, I1, k > 0);
+        ptx::commit2_mc(BAR(BAR_D1_FULL0 + (c & 3)), 3);
+      };
+      auto issue_m2 = [&](int c) {        // D2 += H1[c] . W2[:, 64c .. 64c+63]^T
+        const int b = c & 3;
+        ptx::mbar_wait(BAR(BAR_H1_FULL0 + b), h1ph[b]); h1ph[b] ^= 1;
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          ptx::mma2_ts(tmem + TM_D2, tmem + tm_buf(b) + 8 * k, dW2 + (uint64_t)(c * 16384 >> 4) + 2 * k, I2, (c > 0 || k > 0));
       };
       auto issue_m3 = [&](int Tprev) {    // D3 = H2 . W3^T   (K = 256 in two halves as the H2 halves arrive)
-        if (Tprev >= 1) ptx::mbar_wait(BAR(BAR_D3_EMPTY), (Tprev - 1) & 1);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           ptx::mbar_wait(BAR(BAR_H2_FULL0 + half), Tprev & 1);
@@ -327,26 +335,25 @@ score_gated_kernel(const __grid_constant__ Params p) {
         }
         ptx::commit2_mc(BAR(BAR_D3_FULL), 3);
       };
+      // Issue order per tile (the tensor pipe executes in issue order).  Chunk buffers 2,3 share the D3 columns,
+      // so layer-1 chunks 2,3 of tile T wait until the layer-3 epilogue of tile T-1 has drained D3; every other
+      // layer-1 chunk is issued as soon as its buffer's previous H1 chunk has been consumed, 2-4 chunks ahead of
+      // the layer-2 MMA that needs it: the epilogue latency is off the critical path.
       for (int T = 0; T < NT; ++T) {
         ptx::mbar_wait_cluster(BAR(BAR_A_FULL), T & 1);
         ptx::tc_fence_after();
         issue_m1(0);
         issue_m1(1);
         if (T > 0) issue_m3(T - 1);
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          const int b = c & 1;
-          ptx::mbar_wait(BAR(BAR_H1_FULL0 + b), h1ph[b]); h1ph[b] ^= 1;
-          ptx::tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 4; ++k)      // D2 += H1[c] . W2[:, 64c .. 64c+63]^T
-            ptx::mma2_ts(tmem + TM_D2, tmem + TM_D1 + b * 64 + 8 * k, dW2 + (uint64_t)(c * 16384 >> 4) + 2 * k, I2,
-                         (c > 0 || k > 0));
-          if (c + 2 < 8) {
-            issue_m1(c + 2);
-            if (c + 2 == 7) ptx::commit2_mc(BAR(BAR_A_EMPTY), 3);
-          }
-        }
+        issue_m2(0); issue_m1(4);
+        if (T > 0) { ptx::mbar_wait(BAR(BAR_D3_EMPTY), (T - 1) & 1); ptx::tc_fence_after(); }
+        issue_m1(2);
+        issue_m1(3);
+        issue_m2(1); issue_m1(5);
+        issue_m2(2); issue_m1(6);
+        issue_m2(3); issue_m1(7);
+        ptx::commit2_mc(BAR(BAR_A_EMPTY), 3);
+        issue_m2(4); issue_m2(5); issue_m2(6); issue_m2(7);
         ptx::commit2_mc(BAR(BAR_D2_FULL), 3);
       }
       if (NT > 0) issue_m3(NT - 1);
@@ -427,7 +434,7 @@ score_gated_kernel(const __grid_constant__ Params p) {
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
     const int r = q * 32 + lane;                     // row of the tile this thread owns
     const int ru = r >> 4, rj = r & 15;              // user slot / item slot of the row
-    uint32_t d1ph = 0, reset_ph = 0;
+    uint32_t d1ph[2] = {0, 0}, reset_ph = 0;
     int T = 0;
     Unit prev; prev.ntiles = 0; int prev_t = 0; int64_t prev_ubase = 0; bool have_prev = false;
 
@@ -492,13 +499,14 @@ score_gated_kernel(const __grid_constant__ Params p) {
         // layer-1 chunks of tile T handled by this group: c = grp, grp + 2, ...
         for (int ci = 0; ci < 4; ++ci) {
           const int c = 2 * ci + grp;
-          ptx::mbar_wait(BAR(BAR_D1_FULL0 + grp), d1ph); d1ph ^= 1;
+          const int b = c & 3;                       // chunk buffer: grp (ci even) or grp + 2 (ci odd)
+          ptx::mbar_wait(BAR(BAR_D1_FULL0 + b), d1ph[ci & 1]); d1ph[ci & 1] ^= 1;
           ptx::tc_fence_after();
-          epi_pack64(tl + TM_D1 + grp * 64, tl + TM_D1 + grp * 64, ms.b1 + c * 64);
+          epi_pack64(tl + tm_buf(b), tl + tm_buf(b), ms.b1 + c * 64);
           ptx::tc_wait_st();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_cluster(BAR(BAR_H1_FULL0 + grp), 0);
+          if (lane == 0) ptx::mbar_arrive_cluster(BAR(BAR_H1_FULL0 + b), 0);
           if (ci == 0 && have_prev && grp == 0) {
             const bool last = (prev_t == prev.ntiles - 1);
             if (prev_t == 0 && (T - 1) > 0) { ptx::mbar_wait(BAR(BAR_UNIT_RESET), reset_ph); reset_ph ^= 1; }
