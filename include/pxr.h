@@ -50,6 +50,9 @@ typedef enum { PXR_FUSION_CONCAT = 0, PXR_FUSION_GATED = 1, PXR_FUSION_ATTENTION
 typedef enum { PXR_ACT_RELU = 0, PXR_ACT_GELU = 1, PXR_ACT_TANH = 2, PXR_ACT_LEAKY_RELU = 3, PXR_ACT_SILU = 4 } pxr_act;
 /* final_activation, src/models/multimodal.py:381-384 */
 typedef enum { PXR_FINAL_NONE = 0, PXR_FINAL_SIGMOID = 1, PXR_FINAL_TANH = 2 } pxr_final;
+/* 16-bit operand format of the tcgen05 path (accumulation is always fp32).  bf16: any range, 8-bit significand;
+ * fp16: 11-bit significand (about 7x lower score error), conversions saturate at +-65504. */
+typedef enum { PXR_PRECISION_BF16 = 0, PXR_PRECISION_FP16 = 1 } pxr_precision;
 /* which scoring kernel pxr_score_topk uses */
 typedef enum { PXR_PATH_AUTO = 0, PXR_PATH_SIMT = 1, PXR_PATH_TCGEN05 = 2 } pxr_path;
 
@@ -72,6 +75,7 @@ typedef struct {
   int32_t n_tags;
   int32_t path;                 /* pxr_path; PXR_PATH_AUTO picks tcgen05 when the  */
                                 /* shape is supported, else the SIMT kernels       */
+  int32_t precision;            /* pxr_precision of the tcgen05 path               */
 } pxr_config;
 
 /* fp32 DEVICE pointers named after the reference state_dict keys

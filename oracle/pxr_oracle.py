@@ -404,9 +404,13 @@ def forward_pairs_lowp(sd, cfg, user_idx, item_idx, tag_idx, vis=None, txt=None,
         h = x
         start = 0
     elif ft == "concatenate":
-        # layer 1 is split into per-user and per-item partials, summed in full precision
+        # layer 1 is split into a per-user partial (fp32) and a per-item partial (+ bias, stored in 16 bit),
+        # SURVEY.md A3; their sum goes through the activation and is rounded once more as the layer-2 operand
+        D = feats[0].shape[1]
         x = np.concatenate(feats, axis=1)
-        h = rnd(activation(x @ ws[0].T + bs[0], act))
+        pu = x[:, :D] @ ws[0][:, :D].T
+        pi = rnd(x[:, D:] @ ws[0][:, D:].T + bs[0])
+        h = rnd(activation(pu + pi, act))
         start = 1
     else:
         raise ValueError("no reduced-precision kernel for fusion type " + ft)

@@ -13,6 +13,7 @@ FUSION = {"concatenate": 0, "gated": 1, "attention": 2}
 ACT = {"relu": 0, "gelu": 1, "tanh": 2, "leaky_relu": 3, "silu": 4}
 FINAL = {"none": 0, "sigmoid": 1, "tanh": 2}
 PATH = {"auto": 0, "simt": 1, "tcgen05": 2}
+PRECISION = {"bf16": 0, "fp16": 1}
 
 
 class PxrError(RuntimeError):
@@ -25,7 +26,7 @@ class PxrConfig(C.Structure):
                 ("projection_hidden", C.c_int32), ("n_hidden", C.c_int32),
                 ("hidden", C.c_int32 * PXR_MAX_HIDDEN), ("num_heads", C.c_int32), ("activation", C.c_int32),
                 ("final_activation", C.c_int32), ("use_batch_norm", C.c_int32), ("n_tags", C.c_int32),
-                ("path", C.c_int32)]
+                ("path", C.c_int32), ("precision", C.c_int32)]
 
 
 _F = C.c_void_p

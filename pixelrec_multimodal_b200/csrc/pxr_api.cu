@@ -19,6 +19,7 @@ extern "C" int pxr_create(const pxr_config* cfg, pxr_handle** out) {
   if (cfg->projection_hidden < 0 || cfg->projection_hidden % 4) CFAIL("projection_hidden_dim must be a multiple of 4");
   if (cfg->fusion == PXR_FUSION_ATTENTION && (cfg->num_heads <= 0 || cfg->embedding_dim % cfg->num_heads)) CFAIL("embed_dim must be divisible by num_heads");
   if (cfg->n_tags <= 0) CFAIL("n_tags must be positive");
+  if (cfg->precision != PXR_PRECISION_BF16 && cfg->precision != PXR_PRECISION_FP16) CFAIL("unknown precision %d", cfg->precision);
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { snprintf(g_create_err, sizeof(g_create_err), "no CUDA device: libpxr has no CPU fallback"); return PXR_ERR_CUDA; }
   cudaDeviceProp prop;

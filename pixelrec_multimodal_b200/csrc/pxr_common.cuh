@@ -47,7 +47,7 @@ struct pxr_handle {
 
   // fast (tcgen05) path images
   bool fast_ok = false;
-  bool tc_attr_set = false;
+  uint32_t tc_attr_set = 0;   // bit per kernel whose max-dynamic-smem attribute has been set
   void* fast_w = nullptr;     // bf16 swizzled operand images + fp32 vectors (see score_tc.cu)
 
   // live timing of the dominant kernel (pxr_profile_*)

@@ -33,7 +33,7 @@ class PxrEngine:
     def __init__(self, *, fusion_type: str, embedding_dim: int, vision_dim: int, language_dim: int,
                  num_numerical: int, hidden_dims: Sequence[int], n_tags: int, num_heads: int = 4,
                  activation: str = "relu", final_activation: str = "sigmoid", use_batch_norm: bool = True,
-                 projection_hidden_dim: Optional[int] = None, path: str = "auto",
+                 projection_hidden_dim: Optional[int] = None, path: str = "auto", precision: str = "bf16",
                  device: Optional[torch.device] = None):
         if not torch.cuda.is_available():
             raise PxrError("PxrEngine needs a CUDA device: the scoring path has no CPU fallback")
@@ -63,6 +63,7 @@ class PxrEngine:
         cfg.use_batch_norm = int(bool(use_batch_norm))
         cfg.n_tags = n_tags
         cfg.path = _lib.PATH[path]
+        cfg.precision = _lib.PRECISION[precision]
         self.cfg = cfg
         self.fusion_type = fusion_type
         self.D = embedding_dim

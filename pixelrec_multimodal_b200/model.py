@@ -79,7 +79,8 @@ class FastMultimodalRecommender(nn.Module):
                  use_batch_norm: bool = True, projection_hidden_dim: Optional[int] = None,
                  final_activation: str = "sigmoid", init_method: str = "xavier_uniform",
                  contrastive_temperature: float = 0.07, fusion_type: str = "concatenate",
-                 vision_dim: Optional[int] = None, language_dim: Optional[int] = None, kernel_path: str = "auto"):
+                 vision_dim: Optional[int] = None, language_dim: Optional[int] = None, kernel_path: str = "auto",
+                 operand_dtype: str = "bf16"):
         super().__init__()
         self.fusion_type = fusion_type
         self.n_users, self.n_items, self.n_tags = n_users, n_items, n_tags
@@ -95,6 +96,7 @@ class FastMultimodalRecommender(nn.Module):
         self.projection_hidden_dim = projection_hidden_dim
         self.final_activation = final_activation
         self.kernel_path = kernel_path
+        self.operand_dtype = operand_dtype      # 16-bit operand format of the fused tcgen05 kernels: "bf16" | "fp16"
         # the contrastive heads and backbones are training / feature-production concerns (out of scope)
         self.use_contrastive = False
         self.vision_model = None
@@ -190,7 +192,7 @@ class FastMultimodalRecommender(nn.Module):
                 hidden_dims=self.fusion_hidden_dims, n_tags=self.n_tags, num_heads=self.num_attention_heads,
                 activation=self.fusion_activation, final_activation=self.final_activation,
                 use_batch_norm=self.use_batch_norm, projection_hidden_dim=self.projection_hidden_dim,
-                path=self.kernel_path, device=dev)
+                path=self.kernel_path, precision=self.operand_dtype, device=dev)
             slot[1] = None
         if slot[1] != ver:
             sd = {k: v for k, v in self.state_dict().items() if not k.endswith("num_batches_tracked")}

@@ -60,7 +60,7 @@ def make_workload(spec: syn.ModelSpec, seed: int, target_std: float = 2.0, sampl
     return sd, feats
 
 
-def torch_model_from(spec: syn.ModelSpec, sd, device="cuda", kernel_path="auto"):
+def torch_model_from(spec: syn.ModelSpec, sd, device="cuda", kernel_path="auto", operand_dtype="bf16"):
     import torch
     from pixelrec_multimodal_b200 import FastMultimodalRecommender
     m = FastMultimodalRecommender(
@@ -71,7 +71,8 @@ def torch_model_from(spec: syn.ModelSpec, sd, device="cuda", kernel_path="auto")
         use_contrastive=False, num_attention_heads=spec.num_attention_heads,
         fusion_hidden_dims=list(spec.fusion_hidden_dims), fusion_activation=spec.fusion_activation,
         use_batch_norm=spec.use_batch_norm, projection_hidden_dim=spec.projection_hidden_dim,
-        final_activation=spec.final_activation, fusion_type=spec.fusion_type, kernel_path=kernel_path)
+        final_activation=spec.final_activation, fusion_type=spec.fusion_type, kernel_path=kernel_path,
+        operand_dtype=operand_dtype)
     m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
     return m.to(device).eval()
 

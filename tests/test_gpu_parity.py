@@ -83,8 +83,8 @@ def _topk_case(fusion, path, n_users=48, n_items=1500, k=50, full=True, seed_off
     return spec, sd, feats, indptr, idx, test_item
 
 
-def _engine_for(spec, sd, feats, path="auto", item_lo=0, item_hi=None):
-    model = cs.torch_model_from(spec, sd, kernel_path=path)
+def _engine_for(spec, sd, feats, path="auto", item_lo=0, item_hi=None, dtype="bf16"):
+    model = cs.torch_model_from(spec, sd, kernel_path=path, operand_dtype=dtype)
     eng = model.engine("catalogue")
     hi = spec.n_items if item_hi is None else item_hi
     t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a[item_lo:hi])).cuda()
@@ -294,8 +294,10 @@ def test_full_catalogue_evaluator():
 # Top-K: identical to the emulated oracle's list except swaps inside band (1); against the
 # exact oracle, differences only inside band (2).  Ties -> lower item index.
 # ======================================================================================
-TC_EMU_TOL = 2e-3
-TC_BF16_TOL = 3e-2
+TC_EMU_TOL = {"bf16": 2e-3, "fp16": 5e-4}      # kernel vs the oracle with the kernel's roundings
+TC_BAND = {"bf16": 3e-2, "fp16": 6e-3}         # 16-bit operands vs the exact oracle: the stated tolerance
+TC_BF16_TOL = TC_BAND["bf16"]
+_RND = {"bf16": orc.round_bf16, "fp16": orc.round_fp16}
 
 
 def _tc_workload(n_users, n_items, seed, fusion="gated"):
@@ -339,38 +341,43 @@ def _structural_checks(s, i, k, n_items, indptr=None, idx=None, item_lo=0):
     return s, i
 
 
-@pytest.mark.parametrize("n_users,n_items,k,filt", [(48, 1500, 50, True), (16, 48, 64, False), (33, 1000, 10, True)])
-def test_tcgen05_gated_matches_emulated_and_exact_oracle(n_users, n_items, k, filt):
-    spec, sd, feats, indptr, idx, _ = _tc_workload(n_users, n_items, syn.SEED + 21)
-    model, eng = _engine_for(spec, sd, feats, "tcgen05")
+@pytest.mark.parametrize("fusion,dtype,n_users,n_items,k,filt", [
+    ("gated", "bf16", 48, 1500, 50, True), ("gated", "bf16", 16, 48, 64, False), ("gated", "bf16", 33, 1000, 10, True),
+    ("gated", "fp16", 48, 1500, 50, True),
+    ("concatenate", "bf16", 48, 1500, 50, True), ("concatenate", "bf16", 16, 48, 64, False),
+    ("concatenate", "bf16", 33, 1000, 10, True), ("concatenate", "fp16", 48, 1500, 50, True)])
+def test_tcgen05_matches_emulated_and_exact_oracle(fusion, dtype, n_users, n_items, k, filt):
+    spec, sd, feats, indptr, idx, _ = _tc_workload(n_users, n_items, syn.SEED + 21, fusion)
+    model, eng = _engine_for(spec, sd, feats, "tcgen05", dtype=dtype)
     assert eng.active_path == "tcgen05"
     users = np.arange(n_users)
     args = (torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda()) if filt else ()
     s, i = eng.score_topk(model.user_embedding.weight.detach(), torch.from_numpy(users).cuda(), k, *args)
     s, i = _structural_checks(s, i, k, n_items, indptr if filt else None, idx)
     s = s.astype(np.float64)
-    emu = _lowp_scores(sd, spec, feats, users)
+    emu = _lowp_scores(sd, spec, feats, users, _RND[dtype])
     ref = orc.score_block(sd, cs.spec_cfg(spec), users, 0, n_items, feats)
-    assert np.max(np.abs(emu - ref)) <= TC_BF16_TOL          # what bf16 operands cost on this model
+    assert np.max(np.abs(emu - ref)) <= TC_BAND[dtype]       # what 16-bit operands cost on this model
     same_emu = same_ref = total = 0
     for u in users:
         seen = idx[indptr[u]:indptr[u + 1]] if filt else None
-        same_emu += _check_topk(s[u], i[u], emu[u], k, seen, TC_EMU_TOL, 0.0)
-        same_ref += _check_topk(s[u], i[u], ref[u], k, seen, TC_BF16_TOL, 0.0)
+        same_emu += _check_topk(s[u], i[u], emu[u], k, seen, TC_EMU_TOL[dtype], 0.0)
+        same_ref += _check_topk(s[u], i[u], ref[u], k, seen, TC_BAND[dtype], 0.0)
         total += min(k, n_items - (len(seen) if seen is not None else 0))
     assert same_emu >= 0.97 * total, (same_emu, total)       # identical to the emulation except near-ties
-    print(f"tcgen05 top-{k}: {same_emu}/{total} positions identical to the bf16-emulated oracle, "
-          f"{same_ref}/{total} to the exact oracle")
+    print(f"tcgen05 {fusion}/{dtype} top-{k}: {same_emu}/{total} positions identical to the emulated oracle, "
+          f"{same_ref}/{total} to the exact oracle; max|emu-exact| = {np.max(np.abs(emu - ref)):.2e}")
 
 
-def test_tcgen05_many_units_and_item_splits():
+@pytest.mark.parametrize("fusion", ["gated", "concatenate"])
+def test_tcgen05_many_units_and_item_splits(fusion):
     """More user groups than CTA pairs (several units per pair: list reset between units) and an item
     range split across units (partial lists merged by K4): sampled users vs the emulated oracle, all
     users for the structural properties, and tcgen05 == sharded tcgen05 + merge bit-for-bit."""
     from pixelrec_multimodal_b200.engine import merge_topk
     from pixelrec_multimodal_b200.sharding import shard_range
     n_users, n_items, k = 2500, 1203, 50
-    spec, sd, feats, indptr, idx, _ = _tc_workload(n_users, n_items, syn.SEED + 22)
+    spec, sd, feats, indptr, idx, _ = _tc_workload(n_users, n_items, syn.SEED + 22, fusion)
     model, eng = _engine_for(spec, sd, feats, "tcgen05")
     users = torch.arange(n_users).cuda()
     d_indptr, d_idx = torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda()
@@ -379,7 +386,7 @@ def test_tcgen05_many_units_and_item_splits():
     sample = np.array([0, 1, 7, 8, 15, 16, 17, 1183, 1184, 1199, 2047, 2048, 2491, 2496, 2499])
     emu = _lowp_scores(sd, spec, feats, sample)
     for r, u in enumerate(sample):
-        _check_topk(s[u].astype(np.float64), i[u], emu[r], k, idx[indptr[u]:indptr[u + 1]], TC_EMU_TOL, 0.0)
+        _check_topk(s[u].astype(np.float64), i[u], emu[r], k, idx[indptr[u]:indptr[u + 1]], TC_EMU_TOL["bf16"], 0.0)
     # a ragged user subset (not a multiple of 16, arbitrary order) gives the same lists
     sub = torch.tensor([2499, 3, 1184, 77, 16], device="cuda")
     sub_ptr = torch.zeros(6, dtype=torch.int64)
@@ -401,11 +408,12 @@ def test_tcgen05_many_units_and_item_splits():
     assert torch.equal(mi_, fi) and torch.equal(ms_, fs)
 
 
-def test_tcgen05_full_size_properties():
+@pytest.mark.parametrize("fusion", ["gated", "concatenate"])
+def test_tcgen05_full_size_properties(fusion):
     """BASELINE.json configs[1] catalogue size (96 282 items), one block of users: structural properties
     of every list and agreement with the fp32 SIMT path inside the stated bf16 band."""
     n_users, n_items, k = 512, 96282, 50
-    spec = syn.ModelSpec(n_users=n_users, n_items=n_items, fusion_type="gated")
+    spec = syn.ModelSpec(n_users=n_users, n_items=n_items, fusion_type=fusion)
     sd, feats, hist = syn.torch_workload(spec, "cuda", seed=7)
     syn.condition_like_trained(sd, spec, feats)
     from pixelrec_multimodal_b200 import FastMultimodalRecommender
@@ -413,7 +421,7 @@ def test_tcgen05_full_size_properties():
     for path in ("tcgen05", "simt"):
         m = FastMultimodalRecommender(n_users=n_users, n_items=n_items, n_tags=spec.n_tags, num_numerical_features=7,
                                       embedding_dim=64, vision_model_name="cached512", language_model_name="cached384",
-                                      fusion_type="gated", kernel_path=path).cuda()
+                                      fusion_type=fusion, kernel_path=path).cuda()
         m.load_state_dict(sd, strict=False)
         e = m.engine("catalogue")
         e.precompute_items(m.item_embedding.weight.detach(), feats["tag_idx"], feats["vis"], feats["txt"], feats["num"])
