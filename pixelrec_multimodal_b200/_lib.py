@@ -72,7 +72,10 @@ _lib = None
 
 
 def lib_path() -> Path:
-    return Path(__file__).resolve().parent / "libpxr.so"
+    """In-tree libpxr.so; PXR_LIB points at an alternative build (A/B experiments only)."""
+    import os
+    alt = os.environ.get("PXR_LIB")
+    return Path(alt) if alt else Path(__file__).resolve().parent / "libpxr.so"
 
 
 def load() -> C.CDLL:
@@ -84,7 +87,7 @@ def load() -> C.CDLL:
     from . import build as _build
     path = lib_path()
     try:
-        if _build.needs_build():
+        if path == Path(__file__).resolve().parent / "libpxr.so" and _build.needs_build():
             _build.build()
     except Exception as e:  # a prebuilt .so (the GPU box has one) is still fine
         if not path.exists():

@@ -49,6 +49,9 @@ constexpr int QCAP = 512;                 // candidate queue entries
 constexpr int THREADS = 512;
 constexpr uint32_t IDX_MASK = 0x0FFFFFFFu;   // 28-bit item index inside a queue / list key
 constexpr int FMT_BF16 = 0, FMT_FP16 = 1;
+#ifndef PXR_TOPK_IDLE_NS
+#define PXR_TOPK_IDLE_NS 200
+#endif
 
 enum {
   BAR_W = 0, BAR_A_FULL, BAR_A_EMPTY, BAR_D1_FULL0, BAR_D1_FULL1, BAR_D1_FULL2, BAR_D1_FULL3, BAR_H1_FULL0, BAR_H1_FULL1,
@@ -536,7 +539,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
         if (lane == 0) dn = ptx::mbar_test_wait(BAR(BAR_UNIT_DONE), done_ph) ? 1u : 0u;
         dn = __shfl_sync(0xffffffffu, dn, 0);
         if (dn) { finished = true; done_ph ^= 1; }
-        else __nanosleep(200);                 // idle: do not burn issue slots / power while the queue is empty
+        else __nanosleep(PXR_TOPK_IDLE_NS);    // idle: do not burn issue slots / power while the queue is empty
       }
       // write the K best of every user of this unit, then reset for the next unit
       for (int u = 0; u < TU; ++u) {
@@ -562,8 +565,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
     const int r = q * 32 + lane;                     // row of the tile this thread owns
     const int ru = r >> 4, rj = r & 15;              // user slot / item slot of the row
-    uint32_t d1ph[2] = {0, 0}, reset_ph = 0;
-    uint32_t h1use[2] = {0, 0};                      // concat: uses so far of chunk buffers grp and grp + 2
+    uint32_t d1ph = 0, reset_ph = 0;                 // d1ph: phase bits of chunk buffers grp (bit 0) and grp + 2 (bit 1)
+    uint32_t h1use0 = 0, h1use1 = 0;                 // concat: uses so far of chunk buffers grp and grp + 2
     int T = 0;
     Unit prev; prev.ntiles = 0; prev.row_lo = prev.row_hi = 0; prev.g = prev.s = 0;
     int prev_t = 0; int64_t prev_ubase = 0; bool have_prev = false;
@@ -630,13 +633,13 @@ score_fused_kernel(const __grid_constant__ Params p) {
       const int c = 2 * ci + grp;
       const int b = c & 3;                           // grp (ci even) or grp + 2 (ci odd)
       if (GATED) {
-        ptx::mbar_wait(BAR(BAR_D1_FULL0 + b), d1ph[ci & 1]); d1ph[ci & 1] ^= 1;
+        ptx::mbar_wait(BAR(BAR_D1_FULL0 + b), (d1ph >> (ci & 1)) & 1u); d1ph ^= 1u << (ci & 1);
         ptx::tc_fence_after();
         epi_pack64<FMT>(tl + MP::h1buf(b), tl + MP::h1buf(b), ms.b1 + c * 64);
       } else {
         const int buf = T & 1;
         if (ci == 0) ptx::mbar_wait(BAR(BAR_PI_FULL0 + buf), (T >> 1) & 1);          // this tile's item partials landed
-        const uint32_t n = h1use[ci & 1]++;
+        const uint32_t n = (ci & 1) ? h1use1++ : h1use0++;
         if (n > 0) { ptx::mbar_wait(BAR(BAR_H1_EMPTY0 + b), (n - 1) & 1); ptx::tc_fence_after(); }   // layer 2 consumed the buffer
         concat_h1_chunk<FMT>(sm + MP::OFF_PI + buf * MP::PI_BUF + rj * MP::PI_STRIDE + c * 128,
                              sm + MP::OFF_PU + ru * MP::PU_STRIDE + c * 256, tl + MP::h1buf(b));
@@ -654,17 +657,19 @@ score_fused_kernel(const __grid_constant__ Params p) {
       const Unit un = decode_unit(p, w);
       const int64_t ubase = ((int64_t)un.g * 2 + rank) * TU;
       for (int t = 0; t < un.ntiles; ++t, ++T) {
-        if (GATED) {
-          if (have_prev) do_e2(T - 1);
-          do_l1(0);
-          if (have_prev && grp == 0) prev_e3();
-          do_l1(1); do_l1(2); do_l1(3);
-        } else {
-          do_l1(0);                                  // refill a free buffer while layer 2 of the previous tile drains
-          if (have_prev) do_e2(T - 1);
-          do_l1(1);
-          if (have_prev && grp == 0) prev_e3();
-          do_l1(2); do_l1(3);
+        // One rolled loop over this group's four layer-1 chunks (the body must stay resident in the instruction
+        // cache: fully unrolling it costs ~6 % throughput).  The deferred layer-2 / layer-3 epilogues of the
+        // PREVIOUS tile are slotted in where their inputs become available:
+        //   gated : E2(T-1), L1(0), E3(T-1), L1(1), L1(2), L1(3)
+        //   concat: L1(0), E2(T-1), L1(1), E3(T-1), L1(2), L1(3)   (L1(0) refills a free buffer while layer 2 drains)
+        if (GATED && have_prev) do_e2(T - 1);
+#pragma unroll 1
+        for (int ci = 0; ci < 4; ++ci) {
+          do_l1(ci);
+          if (have_prev) {
+            if (!GATED && ci == 0) do_e2(T - 1);
+            if (grp == 0 && ci == (GATED ? 0 : 1)) prev_e3();
+          }
         }
         prev = un; prev_t = t; prev_ubase = ubase; have_prev = true;
       }

@@ -1,0 +1,10 @@
+#!/bin/bash
+# build a variant of libpxr.so with extra nvcc defines into pixelrec_multimodal_b200/variants/<name>/libpxr.so
+name=$1; shift
+cd "$(dirname "$0")/../pixelrec_multimodal_b200"
+mkdir -p variants/$name
+for f in pxr_api simt_kernels score_tc; do
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -DPXR_PRECISE_MATH -Xcompiler -fPIC -I ../include -I csrc "$@" -c csrc/$f.cu -o variants/$name/$f.o &
+done
+wait
+nvcc -shared -o variants/$name/libpxr.so variants/$name/*.o -gencode arch=compute_100a,code=sm_100a && echo built variants/$name
