@@ -37,6 +37,7 @@ CONFIGS = {
     # name: (n_users, n_items, fusion, description)
     "A": (1_000, 2_000, "concatenate", "configs[0] simple_config_example concat 1K x 2K"),
     "B": (200_000, 96_282, "gated", "configs[1] gated, CLIP-512 + SBERT-384, Pixel200K-shaped 200K x 96K, top-50"),
+    "Bc": (200_000, 96_282, "concatenate", "concat fusion at the configs[1] shape (200K x 96K), top-50 (not a BASELINE config: kernel comparison)"),
     "C": (1_001_822, 100_541, "attention", "configs[2] attention + numerical, Pixel1M-shaped 1M x 100K"),
     "D": (8_886_078, 407_082, "gated", "configs[3] Pixel8M-shaped 8.9M x 407K item-sharded"),
 }
@@ -51,6 +52,18 @@ def w_pair(fusion: str, D: int, H):
     fused vector depends on the pair (gated / attention)."""
     tail = 2 * (sum(a * b for a, b in zip(H[:-1], H[1:])) + H[-1])
     return tail + (0 if fusion == "concatenate" else 2 * D * H[0])
+
+
+def ncu_traffic(fusion: str, users_per_launch: int, items_per_rank: int):
+    """DRAM bytes (read + write) of ONE launch of the fused kernel from the committed `ncu --set full` capture of this
+    same workload shape (profiles/ncu_traffic.json, written by scripts/ncu_summary.py traffic); None when no capture matches."""
+    p = REPO / "profiles" / "ncu_traffic.json"
+    if not p.exists():
+        return None
+    for e in json.loads(p.read_text()).get("captures", []):
+        if e["fusion"] == fusion and e["users_per_launch"] == users_per_launch and e["items_per_rank"] == items_per_rank:
+            return e["dram_bytes_per_launch"]
+    return None
 
 
 def peaks():
@@ -313,7 +326,8 @@ def b200_arm(args):
     achieved_tf = pairs_per_launch * wp / (k_avg_ms * 1e-3) / 1e12 if k_n else None
     peak_tf = pk["tf_sustained"]
     roofline = {"bound": "tensor", "kernel": f"pair-scoring ({eng.active_path})", "achieved": achieved_tf, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf else None,
+                "traffic": ncu_traffic(fusion, B // world, hi - lo),
                 "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside a long step); burst {pk['tf_burst']}",
                 "flop_per_pair": wp, "pairs_per_launch": pairs_per_launch, "kernel_ms_avg": k_avg_ms, "kernel_launches": k_n,
                 "kernel_share_of_step": (k_ms / ms) if ms else None}
