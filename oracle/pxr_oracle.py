@@ -89,7 +89,7 @@ def gated_fusion(sd, feats, dt):
     return (stack * g[:, :, None]).sum(axis=1)
 
 
-def attention_fusion(sd, feats, num_heads, dt):
+def attention_fusion(sd, feats, num_heads, dt, return_token_sum=False):
     """src/models/layers.py:135-164 as documented (list -> stack dim 0 ->
     nn.MultiheadAttention(batch_first=False) -> residual + LayerNorm(eps 1e-5)
     -> mean over tokens).  The call at src/models/multimodal.py:513-519 hands a
@@ -115,6 +115,8 @@ def attention_fusion(sd, feats, num_heads, dt):
     mu = y.mean(axis=-1, keepdims=True)
     var = ((y - mu) ** 2).mean(axis=-1, keepdims=True)
     z = (y - mu) / np.sqrt(var + 1e-5)
+    if return_token_sum:        # sum over tokens of the normalised rows, before the LayerNorm affine and the 1/M
+        return z.sum(axis=0)
     z = z * sd["fusion_layer.norm.weight"].astype(dt) + sd["fusion_layer.norm.bias"].astype(dt)
     return z.mean(axis=0)
 
@@ -412,6 +414,16 @@ def forward_pairs_lowp(sd, cfg, user_idx, item_idx, tag_idx, vis=None, txt=None,
         pi = rnd(x[:, D:] @ ws[0][:, D:].T + bs[0])
         h = rnd(activation(pu + pi, act))
         start = 1
+    elif ft == "attention":
+        # The kernel rounds acc = sum over tokens of the normalised rows (fp32 on CUDA cores) to the operand format and
+        # folds the LayerNorm affine and the mean into layer 1: W1' = W1 diag(ln_w / M) (rounded), b1' = b1 + W1 ln_b.
+        M = len(feats)
+        g = sd["fusion_layer.norm.weight"].astype(dt); beta = sd["fusion_layer.norm.bias"].astype(dt)
+        h = rnd(attention_fusion(sd, feats, int(cfg.get("num_attention_heads", 4)), dt, return_token_sum=True))
+        ws = list(ws); bs = list(bs)
+        bs[0] = bs[0] + ws[0] @ beta
+        ws[0] = ws[0] * (g / M)[None, :]
+        start = 0
     else:
         raise ValueError("no reduced-precision kernel for fusion type " + ft)
     for li in range(start, len(ws) - 1):

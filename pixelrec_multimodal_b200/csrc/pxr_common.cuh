@@ -49,6 +49,7 @@ struct pxr_handle {
   bool fast_ok = false;
   uint32_t tc_attr_set = 0;   // bit per kernel whose max-dynamic-smem attribute has been set
   void* fast_w = nullptr;     // bf16 swizzled operand images + fp32 vectors (see score_tc.cu)
+  float tc_bias_host[1028];   // attention fast path: host copy of b1' b2 b3 w4 b4 (passed as kernel parameters)
 
   // live timing of the dominant kernel (pxr_profile_*)
   bool profile = false;

@@ -34,6 +34,7 @@
 //     of the leader CTA) and owns TMEM/TMA setup, 5 top-K, 8-11 / 12-15 two epilogue groups.
 //     All hand-offs are mbarriers; tcgen05.commit multicasts completion to both CTAs.
 #include <algorithm>
+#include <cstddef>
 
 #include <cuda_fp16.h>
 
@@ -49,6 +50,11 @@ constexpr int QCAP = 512;                 // candidate queue entries
 constexpr int THREADS = 512;
 constexpr uint32_t IDX_MASK = 0x0FFFFFFFu;   // 28-bit item index inside a queue / list key
 constexpr int FMT_BF16 = 0, FMT_FP16 = 1;
+constexpr int F_CONCAT = 0, F_GATED = 1, F_ATTN = 2;   // front ends of the kernel template
+constexpr int NH = 4, DH = D / NH;                      // attention: heads x head dim (fast path: 4 x 16)
+// attention: per-item record, ATT_TOKENS token blocks of ATT_TOK floats (see item_attn_kernel)
+constexpr int ATT_TOKENS = 5, ATT_TOK = 720, ATT_ITEM = ATT_TOKENS * ATT_TOK;
+constexpr int ATT_C = 0, ATT_NB = 64, ATT_U = 320, ATT_Q = 576, ATT_K = 640, ATT_L = 704;
 #ifndef PXR_TOPK_IDLE_NS
 #define PXR_TOPK_IDLE_NS 200
 #endif
@@ -60,12 +66,21 @@ enum {
   BAR_UNIT_RESET, N_BARS
 };
 
-struct Misc {
-  float b1[H1]; float b2[H2]; float b3[H3]; float w4[H3];
-  float eu[TU][D];
-  float lu[TU][8];
+// Per-CTA scratch in shared memory.  The attention front end needs 12 KB of per-user constants next to the weights,
+// so that variant keeps the epilogue biases in the kernel-parameter constant bank, a shorter candidate queue, and
+// stages E_u in the (idle) A1 tile during the per-unit setup.
+template <int FUS>
+struct MiscT {
+  static constexpr bool ATT = (FUS == F_ATTN);
+  static constexpr int QC = ATT ? 128 : QCAP;          // candidate queue entries
+  float b1[ATT ? 4 : H1]; float b2[ATT ? 4 : H2]; float b3[ATT ? 4 : H3]; float w4[ATT ? 4 : H3];   // contiguous
+  float eu[ATT ? 1 : TU][D];
+  float lu[ATT ? 1 : TU][8];
+  float qu[ATT ? TU : 1][D], ku[ATT ? TU : 1][D];       // attention: in_proj q / k of the user token (unscaled)
+  float U0c[ATT ? TU : 1][NH][D];                       // attention: per-head out_proj of v_u, centred over d
+  float S00[ATT ? TU : 1][NH];                          // attention: q_u,h . k_u,h / sqrt(dh)
   unsigned long long list[TU][KCAP];
-  unsigned long long queue[QCAP];
+  unsigned long long queue[QC];
   float thr[TU];
   uint32_t seen_mask[4][TU];
   uint32_t q_tail, q_head;
@@ -74,9 +89,10 @@ struct Misc {
   unsigned long long bars[N_BARS];
 };
 
-// shared / tensor memory maps per fusion type
-template <bool GATED>
+// shared / tensor memory maps per front end
+template <int FUS>
 struct Map {
+  static constexpr bool GATED = (FUS != F_CONCAT);               // layer 1 on the tensor pipe from an A1 tile
   // shared memory (bytes from a 1024-aligned base); the weight image is the first WIMG bytes
   static constexpr uint32_t OFF_W1 = 0;                          // gated: 8 N-chunks x (32 rows x 128 B) = 32 KB
   static constexpr uint32_t OFF_W2 = GATED ? 32768u : 0u;        // 8 K-blocks x (128 rows x 128 B) = 128 KB
@@ -88,7 +104,7 @@ struct Map {
   static constexpr uint32_t PU_STRIDE = 2064;                    // concat: 8 user partials (512 fp32), padded
   static constexpr uint32_t OFF_PU = OFF_PI + 2 * PI_BUF;
   static constexpr uint32_t OFF_MISC = GATED ? OFF_A1 + 16384u : OFF_PU + TU * PU_STRIDE;
-  static constexpr uint32_t SMEM = OFF_MISC + (uint32_t)sizeof(Misc) + 1024u;   // + alignment slack
+  static constexpr uint32_t SMEM = OFF_MISC + (uint32_t)sizeof(MiscT<FUS>) + 1024u;   // + alignment slack
   // tensor memory (columns)
   static constexpr uint32_t TM_D3 = 128, TM_D2 = 256;
   // H1 chunk buffer b.  gated: 64-col fp32 accumulators packed in place, buffers 2,3 share the D3 columns
@@ -97,8 +113,16 @@ struct Map {
     return GATED ? (b < 2 ? 64u * b : TM_D3 + 64u * (b - 2)) : 32u * b;
   }
 };
-static_assert(Map<true>::SMEM <= 232448 && Map<false>::SMEM <= 232448, "shared memory budget");
-static_assert(Map<false>::OFF_MISC % 16 == 0 && Map<true>::OFF_MISC % 16 == 0, "alignment");
+static_assert(Map<F_GATED>::SMEM <= 232448 && Map<F_CONCAT>::SMEM <= 232448 && Map<F_ATTN>::SMEM <= 232448, "shared memory budget");
+static_assert(Map<F_CONCAT>::OFF_MISC % 16 == 0 && Map<F_GATED>::OFF_MISC % 16 == 0, "alignment");
+static_assert(offsetof(MiscT<F_ATTN>, qu) % 16 == 0 && offsetof(MiscT<F_ATTN>, U0c) % 16 == 0 && offsetof(MiscT<F_ATTN>, list) % 8 == 0, "alignment");
+static_assert(offsetof(MiscT<F_GATED>, list) % 8 == 0 && offsetof(MiscT<F_GATED>, bars) % 8 == 0 && offsetof(MiscT<F_ATTN>, bars) % 8 == 0, "alignment");
+
+// attention: E_u + out_proj bias, centred over d, of one CTA's 8 users (rebuilt per unit by the front-end warps).
+// Read once per half tile, so it lives in global memory (one slot per CTA); the hot per-user constants are in smem.
+struct UserAttn {
+  float C0c[TU][D];
+};
 
 struct Params {
   const uint8_t* wimg;          // [2][WIMG] pre-swizzled 16-bit operand images (rank 0, rank 1)
@@ -108,6 +132,15 @@ struct Params {
   const float* item_logit;      // gated: [rows][8] fp32 item part of the gate logits (+ gate bias)
   const uint16_t* item_pi;      // concat: [rows][512] 16-bit item partial of layer 1 (+ b1)
   const float* w1u_t;           // concat: [64][512] fp32, user columns of W1 transposed
+  const float* attn_rec;        // attention: [rows][ATT_ITEM] fp32 per-item records
+  const float* attn_in_wt;      // attention: in_proj weight transposed [64][192], bias [192]
+  const float* attn_in_b;
+  const float* attn_out_wt;     // attention: out_proj weight transposed [64][64], bias [64]
+  const float* attn_out_b;
+  const float* ln_w;            // attention: LayerNorm weight / bias [64]
+  const float* ln_b;
+  UserAttn* user_scratch;       // attention: one UserAttn per CTA
+  float bias_c[H1 + H2 + H3 + H3 + 4];   // attention: b1' b2 b3 w4 b4 read through the constant bank (no room in smem)
   const float* user_emb;        // (n_users_total, D) fp32 table
   const int64_t* user_idx;      // (n_users,)
   const int64_t* seen_indptr;   // (n_users + 1,) or NULL
@@ -198,18 +231,243 @@ __device__ __forceinline__ void concat_h1_chunk(const uint8_t* pi_row, const uin
   ptx::tmem_st32(t_dst, o);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// attention fusion front end (src/models/layers.py:135-164 as documented; SURVEY.md A5 split)
+//
+// Tokens of pair (u, i): x_0 = E_u, x_1.. = the item-side modality vectors.  Everything that involves only
+// item tokens is folded into the per-item record once per catalogue (item_attn_kernel):
+//   row a >= 1:  softmax over [s_a0 | item part] => with L_ah = logsumexp_b>=1 s_ab,h the user column gets weight
+//                w_ah = sigmoid(q_a,h . k_u,h / sqrt(dh) - L_ah) and the item columns share 1 - w_ah, so
+//                y_a = x_a + attn_a = C_a + sum_h w_ah (U0_h[u] - Nbar_ah),   C_a = x_a + b_o + sum_h Nbar_ah,
+//                Nbar_ah = sum_b>=1 softmax_b(s_ab,h) U_bh,   U_bh = W_o[:, head h] v_b,h   (out_proj folded in)
+//   row 0:       softmax over [q_u.k_u, q_u.k_b ...] per head, y_0 = E_u + b_o + sum_h (p_h0 U0_h + sum_b p_hb U_bh)
+// LayerNorm only needs y - mean(y): every stored vector (C, Nbar, U, U0, E_u + b_o) is CENTRED over d in advance,
+// and as the weights of each row sum to one the combination is centred too -- no per-pair mean.  Then
+//   fused = ln_b + ln_w / M * sum_a (y_a - mean) * rstd_a;
+// the affine part is folded into layer 1 (W1' = W1 diag(ln_w / M), b1' = b1 + W1 ln_b), so the A1 operand is
+// the 16-bit rounding of   acc = sum_a (y_a - mean) * rstd_a.
+// Thread = (item j of a half tile of 8, 4-wide slice s of D; head of the slice = s / 4), all 8 users of the CTA.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream(const float* p) {      // item records: read once per tile, keep them out of L1
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float sum4_head(float v) {                // sum over the 4 lanes that share a head
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ float sum16_item(float v) {               // sum over the 16 lanes that share an item
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  return v;
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+__device__ __forceinline__ void fma4(float* acc, float w, const float4& v) {
+  acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]); acc[2] = fmaf(w, v.z, acc[2]); acc[3] = fmaf(w, v.w, acc[3]);
+}
+
+// per-unit constants of this CTA's 8 users (128 threads, named barrier 1).  `stage` = 4 KB of scratch shared memory
+// (the idle A1 tile): E_u at [0, 2 KB), v_u at [2 KB, 4 KB).
+template <class MiscA>
+__device__ __forceinline__ void attn_user_setup(const Params& p, MiscA& ms, float* stage, UserAttn* us, int tid) {
+  float (*eu)[D] = reinterpret_cast<float (*)[D]>(stage);
+  float (*vu)[D] = reinterpret_cast<float (*)[D]>(stage + TU * D);
+  for (int n = tid; n < 3 * D; n += 128) {                 // in_proj of the user token: q | k | v
+    float acc[TU];
+    const float b = p.attn_in_b[n];
+#pragma unroll
+    for (int u = 0; u < TU; ++u) acc[u] = b;
+#pragma unroll 4
+    for (int k = 0; k < D; ++k) {
+      const float w = p.attn_in_wt[k * 3 * D + n];
+#pragma unroll
+      for (int u = 0; u < TU; ++u) acc[u] = fmaf(w, eu[u][k], acc[u]);
+    }
+    float* dst = n < D ? &ms.qu[0][n] : (n < 2 * D ? &ms.ku[0][n - D] : &vu[0][n - 2 * D]);
+#pragma unroll
+    for (int u = 0; u < TU; ++u) dst[u * D] = acc[u];
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  {
+    const int d = tid & 63, hp = tid >> 6;                 // out_proj per head: U0[u][h][d] = sum_e W_o[d][16h+e] v_u[16h+e]
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int h = 2 * hp + hh;
+      float acc[TU];
+#pragma unroll
+      for (int u = 0; u < TU; ++u) acc[u] = 0.f;
+#pragma unroll 4
+      for (int e = 0; e < DH; ++e) {
+        const float w = p.attn_out_wt[(h * DH + e) * D + d];
+#pragma unroll
+        for (int u = 0; u < TU; ++u) acc[u] = fmaf(w, vu[u][h * DH + e], acc[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < TU; ++u) ms.U0c[u][h][d] = acc[u];
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  // centre over d: one warp-level pass per 64-vector (8 users x (4 heads + C0) = 40 vectors, 10 per warp)
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int v = warp; v < TU * (NH + 1); v += 4) {
+      const int u = v / (NH + 1), h = v % (NH + 1);
+      float a, b;
+      if (h < NH) { a = ms.U0c[u][h][lane]; b = ms.U0c[u][h][lane + 32]; }
+      else { a = eu[u][lane] + p.attn_out_b[lane]; b = eu[u][lane + 32] + p.attn_out_b[lane + 32]; }
+      float sm_ = a + b;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sm_ += __shfl_xor_sync(0xffffffffu, sm_, o);
+      const float mean = sm_ * (1.f / D);
+      if (h < NH) { ms.U0c[u][h][lane] = a - mean; ms.U0c[u][h][lane + 32] = b - mean; }
+      else { us->C0c[u][lane] = a - mean; us->C0c[u][lane + 32] = b - mean; }
+    }
+  }
+  if (tid < TU * NH) {
+    const int u = tid >> 2, h = tid & 3;
+    float dot = 0.f;
+    for (int e = 0; e < DH; ++e) dot = fmaf(ms.qu[u][h * DH + e], ms.ku[u][h * DH + e], dot);
+    ms.S00[u][h] = dot * 0.25f;                            // 1 / sqrt(dh), dh = 16
+  }
+}
+
+// acc = sum over tokens of the normalised rows, for the 8 users x 8 items of one half tile -> 16-bit A1 rows.
+// `wait_a1` is called once, right before the first store into A1.
+template <int FMT, class MiscA, typename WaitA1>
+__device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* us, const float* rec, int nt, uint8_t* a1,
+                                               int half, int tid, int lane, WaitA1 wait_a1) {
+  const int j8 = tid >> 4, s = tid & 15, hd = s >> 2;
+  const int gb = lane & 16;                                // first lane of this item's 16-lane group
+  float acc[TU][4];
+  {
+    // ---- token 0 (the user token): scores against every token, softmax per head, value mix, normalise
+    float S[TU][ATT_TOKENS];
+    {
+      float4 kb[ATT_TOKENS];
+#pragma unroll
+      for (int b = 0; b < ATT_TOKENS; ++b) kb[b] = ldg_stream(rec + min(b, nt - 1) * ATT_TOK + ATT_K + 4 * s);
+#pragma unroll
+      for (int u = 0; u < TU; ++u) {
+        const float4 qv = *reinterpret_cast<const float4*>(&ms.qu[u][4 * s]);
+#pragma unroll
+        for (int b = 0; b < ATT_TOKENS; ++b) S[u][b] = sum4_head(dot4(qv, kb[b]));
+      }
+    }
+    float p0[TU];
+#pragma unroll
+    for (int u = 0; u < TU; ++u) {
+      const float s00 = ms.S00[u][hd];
+      float m = s00;
+#pragma unroll
+      for (int b = 0; b < ATT_TOKENS; ++b) { if (b >= nt) S[u][b] = -INFINITY; m = fmaxf(m, S[u][b]); }
+      const float e0 = __expf(s00 - m);
+      float sum = e0;
+#pragma unroll
+      for (int b = 0; b < ATT_TOKENS; ++b) { S[u][b] = __expf(S[u][b] - m); sum += S[u][b]; }
+      const float inv = __fdividef(1.f, sum);
+      p0[u] = e0 * inv;
+#pragma unroll
+      for (int b = 0; b < ATT_TOKENS; ++b) S[u][b] *= inv;
+    }
+#pragma unroll
+    for (int u = 0; u < TU; ++u) {
+      const float4 c0 = __ldcg(reinterpret_cast<const float4*>(&us->C0c[u][4 * s]));
+      acc[u][0] = c0.x; acc[u][1] = c0.y; acc[u][2] = c0.z; acc[u][3] = c0.w;
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
+        fma4(acc[u], __shfl_sync(0xffffffffu, p0[u], gb | (4 * h)), *reinterpret_cast<const float4*>(&ms.U0c[u][h][4 * s]));
+    }
+#pragma unroll
+    for (int b = 0; b < ATT_TOKENS; ++b) {
+      float4 ub[NH];
+#pragma unroll
+      for (int h = 0; h < NH; ++h) ub[h] = ldg_stream(rec + min(b, nt - 1) * ATT_TOK + ATT_U + h * D + 4 * s);
+#pragma unroll
+      for (int u = 0; u < TU; ++u)
+#pragma unroll
+        for (int h = 0; h < NH; ++h) fma4(acc[u], __shfl_sync(0xffffffffu, S[u][b], gb | (4 * h)), ub[h]);   // weight 0 for b >= nt
+    }
+#pragma unroll
+    for (int u = 0; u < TU; ++u) {
+      const float ss = fmaf(acc[u][3], acc[u][3], fmaf(acc[u][2], acc[u][2], fmaf(acc[u][1], acc[u][1], acc[u][0] * acc[u][0])));
+      const float r = rsqrtf(sum16_item(ss) * (1.f / D) + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[u][i] *= r;
+    }
+  }
+  // ---- item tokens a >= 1 (token data of a + 1 is fetched while a is being combined)
+  float4 c, q, nb[NH]; float Lh;
+  auto load_tok = [&](int a, float4& c_, float4& q_, float4* nb_, float& L_) {
+    const float* tr = rec + a * ATT_TOK;
+    c_ = ldg_stream(tr + ATT_C + 4 * s);
+    q_ = ldg_stream(tr + ATT_Q + 4 * s);
+#pragma unroll
+    for (int h = 0; h < NH; ++h) nb_[h] = ldg_stream(tr + ATT_NB + h * D + 4 * s);
+    L_ = __ldg(tr + ATT_L + hd);
+  };
+  load_tok(0, c, q, nb, Lh);
+#pragma unroll 1
+  for (int a = 0; a < nt; ++a) {
+    float4 c2, q2, nb2[NH]; float L2;
+    load_tok(min(a + 1, nt - 1), c2, q2, nb2, L2);
+#pragma unroll
+    for (int u = 0; u < TU; ++u) {
+      const float d = sum4_head(dot4(q, *reinterpret_cast<const float4*>(&ms.ku[u][4 * s])));
+      const float w = __fdividef(1.f, 1.f + __expf(Lh - d));        // sigmoid(s_a0 - L_ah)
+      float y[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const float wh = __shfl_sync(0xffffffffu, w, gb | (4 * h));
+        const float4 uv = *reinterpret_cast<const float4*>(&ms.U0c[u][h][4 * s]);
+        y[0] = fmaf(wh, uv.x - nb[h].x, y[0]); y[1] = fmaf(wh, uv.y - nb[h].y, y[1]);
+        y[2] = fmaf(wh, uv.z - nb[h].z, y[2]); y[3] = fmaf(wh, uv.w - nb[h].w, y[3]);
+      }
+      const float ss = fmaf(y[3], y[3], fmaf(y[2], y[2], fmaf(y[1], y[1], y[0] * y[0])));
+      const float r = rsqrtf(sum16_item(ss) * (1.f / D) + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[u][i] = fmaf(r, y[i], acc[u][i]);
+    }
+    c = c2; q = q2; Lh = L2;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) nb[h] = nb2[h];
+  }
+  // ---- 16-bit pack into the swizzled A1 rows (row = user * 16 + item; 8 bytes per thread)
+  if (half == 0) wait_a1();
+  const int j = 8 * half + j8;
+#pragma unroll
+  for (int u = 0; u < TU; ++u) {
+    uint2 pk;
+    pk.x = pack2<FMT>(acc[u][0], acc[u][1]); pk.y = pack2<FMT>(acc[u][2], acc[u][3]);
+    const int r = u * TI + j;
+    *reinterpret_cast<uint2*>(a1 + (r >> 3) * 1024 + (r & 7) * 128 + (((s >> 1) ^ (r & 7)) << 4) + (s & 1) * 8) = pk;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <bool GATED, int FMT>
+// FUS selects the front end.  GATED below means "layer 1 runs on the tensor pipe from an A1 tile in shared memory"
+// (gated and attention fusion: the fused vector depends on the pair); concat feeds layer-1 partial sums instead.
+template <int FUS, int FMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 score_fused_kernel(const __grid_constant__ Params p) {
-  using MP = Map<GATED>;
+  constexpr bool GATED = (FUS != F_CONCAT);
+  constexpr bool ATT = (FUS == F_ATTN);
+  using MP = Map<FUS>;
+  using MiscF = MiscT<FUS>;
+  constexpr int QC = MiscF::QC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw_u32);
-  Misc& ms = *reinterpret_cast<Misc*>(sm + MP::OFF_MISC);
+  MiscF& ms = *reinterpret_cast<MiscF*>(sm + MP::OFF_MISC);
   const uint32_t bar0 = ptx::smem_u32(&ms.bars[0]);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
@@ -218,9 +476,14 @@ score_fused_kernel(const __grid_constant__ Params p) {
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
   // ------------------------------------------------------------------ setup
-  for (int i = threadIdx.x; i < H1 + H2 + H3 + H3; i += THREADS) ms.b1[i] = p.bias[i];   // b1,b2,b3,w4 are contiguous
+  if (!ATT) for (int i = threadIdx.x; i < H1 + H2 + H3 + H3; i += THREADS) ms.b1[i] = p.bias[i];   // b1,b2,b3,w4 are contiguous
+  // epilogue constants: shared memory, or (attention) the kernel-parameter constant bank
+  const float* const cb1 = ATT ? p.bias_c : ms.b1;
+  const float* const cb2 = ATT ? p.bias_c + H1 : ms.b2;
+  const float* const cb3 = ATT ? p.bias_c + H1 + H2 : ms.b3;
+  const float* const cw4 = ATT ? p.bias_c + H1 + H2 + H3 : ms.w4;
   if (threadIdx.x == 0) {
-    ms.b4 = p.bias[H1 + H2 + H3 + H3];
+    ms.b4 = ATT ? p.bias_c[H1 + H2 + H3 + H3] : p.bias[H1 + H2 + H3 + H3];
     ms.q_tail = 0; ms.q_head = 0;
     ptx::mbar_init(BAR(BAR_W), 1);
     ptx::mbar_init(BAR(BAR_A_FULL), 8);
@@ -240,7 +503,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
     ptx::fence_mbar_init();
   }
   for (int i = threadIdx.x; i < TU * KCAP; i += THREADS) (&ms.list[0][0])[i] = 0ull;
-  for (int i = threadIdx.x; i < QCAP; i += THREADS) ms.queue[i] = 0ull;
+  for (int i = threadIdx.x; i < QC; i += THREADS) ms.queue[i] = 0ull;
   if (threadIdx.x < TU) ms.thr[threadIdx.x] = -INFINITY;
   __syncthreads();
   if (warp == 4) {
@@ -277,13 +540,18 @@ score_fused_kernel(const __grid_constant__ Params p) {
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");              // previous unit's readers of eu/lu are done
       {
+        // attention stages E_u (and v_u) in the A1 tile: wait until the layer-1 MMAs of the previous tile have read it
+        if (ATT && T > 0) ptx::mbar_wait(BAR(BAR_A_EMPTY), (T - 1) & 1);
+        float (*eu_dst)[D] = ATT ? reinterpret_cast<float (*)[D]>(sm + MP::OFF_A1) : ms.eu;
         const int u = tid >> 4, d4 = (tid & 15) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ubase + u < p.n_users) v = *reinterpret_cast<const float4*>(p.user_emb + p.user_idx[ubase + u] * D + d4);
-        *reinterpret_cast<float4*>(&ms.eu[u][d4]) = v;
+        *reinterpret_cast<float4*>(&eu_dst[u][d4]) = v;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (GATED) {
+      if (FUS == F_ATTN) {
+        attn_user_setup(p, ms, reinterpret_cast<float*>(sm + MP::OFF_A1), p.user_scratch + blockIdx.x, tid);
+      } else if (FUS == F_GATED) {
         if (tid < 64) {                      // user part of the gate logits (layers.py:207 split per SURVEY A4)
           const int u = tid >> 3, m = tid & 7;
           float acc = 0.f;
@@ -340,7 +608,19 @@ score_fused_kernel(const __grid_constant__ Params p) {
             ms.seen_mask[T & 3][lane] = mask;
           }
         };
-        if (GATED) {
+        if (FUS == F_ATTN) {
+          write_seen_mask();
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            const int64_t row = row0 + 8 * half + (tid >> 4);
+            const int64_t rr = row < un.row_hi ? row : un.row_lo;    // padding rows recompute a valid item (discarded later)
+            attn_half_tile<FMT>(ms, p.user_scratch + blockIdx.x, p.attn_rec + rr * ATT_ITEM, Mm - 1, sm + MP::OFF_A1, half, tid,
+                                lane, [&]() { if (T > 0) ptx::mbar_wait(BAR(BAR_A_EMPTY), (T - 1) & 1); });
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster_release(BAR(BAR_A_FULL), 0);
+        } else if (FUS == F_GATED) {
           const int j = tid >> 3, s = tid & 7;    // item of the tile, 8-wide slice of D
           const int64_t row = row0 + j;
           const bool valid = row < un.row_hi;
@@ -498,12 +778,12 @@ score_fused_kernel(const __grid_constant__ Params p) {
       bool finished = false;
       while (true) {
         unsigned long long e = 0ull;
-        if (lane == 0) e = *reinterpret_cast<volatile unsigned long long*>(&ms.queue[head % QCAP]);
+        if (lane == 0) e = *reinterpret_cast<volatile unsigned long long*>(&ms.queue[head % QC]);
         e = __shfl_sync(0xffffffffu, e, 0);
         if (e != 0ull) {
           __syncwarp();
           if (lane == 0) {
-            *reinterpret_cast<volatile unsigned long long*>(&ms.queue[head % QCAP]) = 0ull;
+            *reinterpret_cast<volatile unsigned long long*>(&ms.queue[head % QC]) = 0ull;
             *reinterpret_cast<volatile uint32_t*>(&ms.q_head) = head + 1;
           }
           ++head;
@@ -575,8 +855,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
       ptx::mbar_wait(BAR(BAR_D2_FULL), Tp & 1);
       ptx::tc_fence_after();
       const uint32_t c0 = MP::TM_D2 + grp * 128;
-      epi_pack64<FMT>(tl + c0, tl + c0, ms.b2 + grp * 128);
-      epi_pack64<FMT>(tl + c0 + 64, tl + c0 + 32, ms.b2 + grp * 128 + 64);
+      epi_pack64<FMT>(tl + c0, tl + c0, cb2 + grp * 128);
+      epi_pack64<FMT>(tl + c0 + 64, tl + c0 + 32, cb2 + grp * 128 + 64);
       ptx::tc_wait_st();
       ptx::tc_fence_before();
       __syncwarp();
@@ -592,8 +872,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
         ptx::tmem_ld32(tl + MP::TM_D3 + h * 64, v0);
         ptx::tmem_ld32(tl + MP::TM_D3 + h * 64 + 32, v1);
         ptx::tc_wait_ld();
-        const float4* b3v = reinterpret_cast<const float4*>(ms.b3 + h * 64);
-        const float4* w4v = reinterpret_cast<const float4*>(ms.w4 + h * 64);
+        const float4* b3v = reinterpret_cast<const float4*>(cb3 + h * 64);
+        const float4* w4v = reinterpret_cast<const float4*>(cw4 + h * 64);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float4 b = b3v[i], wv = w4v[i];
@@ -615,8 +895,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
         const unsigned long long e = ((unsigned long long)pxr_ord(y) << 32) | ((unsigned long long)ru << 28) |
                                      (unsigned long long)(IDX_MASK - gidx);
         const uint32_t slot = atomicAdd(&ms.q_tail, 1u);
-        while (slot - *reinterpret_cast<volatile uint32_t*>(&ms.q_head) >= (uint32_t)QCAP) __nanosleep(64);
-        *reinterpret_cast<volatile unsigned long long*>(&ms.queue[slot % QCAP]) = e;
+        while (slot - *reinterpret_cast<volatile uint32_t*>(&ms.q_head) >= (uint32_t)QC) __nanosleep(64);
+        *reinterpret_cast<volatile unsigned long long*>(&ms.queue[slot % QC]) = e;
       }
       if (last_of_unit) {
         __syncwarp();
@@ -635,7 +915,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
       if (GATED) {
         ptx::mbar_wait(BAR(BAR_D1_FULL0 + b), (d1ph >> (ci & 1)) & 1u); d1ph ^= 1u << (ci & 1);
         ptx::tc_fence_after();
-        epi_pack64<FMT>(tl + MP::h1buf(b), tl + MP::h1buf(b), ms.b1 + c * 64);
+        epi_pack64<FMT>(tl + MP::h1buf(b), tl + MP::h1buf(b), cb1 + c * 64);
       } else {
         const int buf = T & 1;
         if (ci == 0) ptx::mbar_wait(BAR(BAR_PI_FULL0 + buf), (T >> 1) & 1);          // this tile's item partials landed
@@ -698,8 +978,9 @@ __device__ __forceinline__ uint16_t to16(float v, int fmt) {
 
 // Builds the two per-CTA-rank operand images: 16-bit, K-major, 128-byte swizzle (16-byte chunk index XOR
 // row-in-group), laid out exactly as the kernel's shared memory.  w1 / k1: layer-1 weight (row stride k1) or NULL.
-__global__ void build_wimg_kernel(const float* __restrict__ w1, int k1, const float* __restrict__ w2,
-                                  const float* __restrict__ w3, uint8_t* __restrict__ img, int gated, int fmt) {
+__global__ void build_wimg_kernel(const float* __restrict__ w1, int k1, const float* __restrict__ k1_scale,
+                                  const float* __restrict__ w2, const float* __restrict__ w3, uint8_t* __restrict__ img,
+                                  int gated, int fmt) {
   const uint32_t off_w2 = gated ? 32768u : 0u, off_w3 = off_w2 + 131072u, wimg = off_w3 + 32768u;
   const int total = (int)wimg;                                       // 2 ranks x wimg/2 elements
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -716,7 +997,7 @@ __global__ void build_wimg_kernel(const float* __restrict__ w1, int k1, const fl
     const uint32_t chunk = (inrow >> 4) ^ (nl & 7);                  // un-swizzle: stored chunk -> logical chunk
     const uint32_t kk = chunk * 8 + ((inrow & 15) >> 1);             // k inside the 64-wide block
     float v;
-    if (which == 1) v = w1[(size_t)(blk * 64 + rank * 32 + nl) * k1 + kk];          // N-chunk blk, rows [32 rank, +32)
+    if (which == 1) v = w1[(size_t)(blk * 64 + rank * 32 + nl) * k1 + kk] * (k1_scale ? k1_scale[kk] : 1.f);   // N-chunk blk, rows [32 rank, +32)
     else if (which == 2) v = w2[(size_t)(rank * 128 + nl) * H1 + blk * 64 + kk];     // K-block blk, rows [128 rank, +128)
     else v = w3[(size_t)(rank * 64 + nl) * H2 + blk * 64 + kk];
     reinterpret_cast<uint16_t*>(img + (size_t)rank * wimg)[off / 2] = to16(v, fmt);
@@ -767,21 +1048,138 @@ __global__ void __launch_bounds__(PXR_SIMT_THREADS) item_pi_kernel(const float* 
   }
 }
 
-struct FastWeights {       // lives in h->fast_w
-  uint8_t wimg[2 * Map<true>::WIMG];
+
+// attention: per-item record (once per catalogue shard).  4 items per block, thread = (item, d).  Record layout per
+// item token a (ATT_TOK floats): C[64] | Nbar[4][64] | U[4][64] | q[64] / sqrt(dh) | k[64] / sqrt(dh) | L[4] | pad,
+// with C, Nbar_h and U_h each centred over d (definitions above attn_half_tile).
+__global__ void __launch_bounds__(256) item_attn_kernel(const float* __restrict__ feats, const float* __restrict__ in_wt,
+                                                        const float* __restrict__ in_b, const float* __restrict__ out_wt,
+                                                        const float* __restrict__ out_b, int M, int64_t n_rows,
+                                                        float* __restrict__ rec) {
+  __shared__ float x[4][ATT_TOKENS][D], q[4][ATT_TOKENS][D], k[4][ATT_TOKENS][D], v[4][ATT_TOKENS][D];
+  __shared__ float Ssc[4][ATT_TOKENS][NH][ATT_TOKENS], P[4][ATT_TOKENS][NH][ATT_TOKENS], Lse[4][ATT_TOKENS][NH];
+  __shared__ float red[4][2][2 * NH + 1];
+  const int it = threadIdx.x >> 6, d = threadIdx.x & 63, nt = M - 1;
+  const int64_t row = (int64_t)blockIdx.x * 4 + it;
+  const bool valid = row < n_rows;
+  const float scale = rsqrtf((float)DH);
+  for (int b = 0; b < ATT_TOKENS; ++b) x[it][b][d] = (valid && b < nt) ? feats[(row * nt + b) * D + d] : 0.f;
+  __syncthreads();
+  {
+    float aq[ATT_TOKENS], ak[ATT_TOKENS], av[ATT_TOKENS];
+    for (int b = 0; b < ATT_TOKENS; ++b) { aq[b] = in_b[d]; ak[b] = in_b[D + d]; av[b] = in_b[2 * D + d]; }
+    for (int kk = 0; kk < D; ++kk) {
+      const float wq = in_wt[kk * 3 * D + d], wk = in_wt[kk * 3 * D + D + d], wv = in_wt[kk * 3 * D + 2 * D + d];
+#pragma unroll
+      for (int b = 0; b < ATT_TOKENS; ++b) {
+        const float xv = x[it][b][kk];
+        aq[b] = fmaf(wq, xv, aq[b]); ak[b] = fmaf(wk, xv, ak[b]); av[b] = fmaf(wv, xv, av[b]);
+      }
+    }
+    for (int b = 0; b < ATT_TOKENS; ++b) { q[it][b][d] = aq[b] * scale; k[it][b][d] = ak[b]; v[it][b][d] = av[b]; }
+  }
+  __syncthreads();
+  float U[ATT_TOKENS][NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) {
+#pragma unroll
+    for (int b = 0; b < ATT_TOKENS; ++b) U[b][h] = 0.f;
+    for (int e = 0; e < DH; ++e) {
+      const float w = out_wt[(h * DH + e) * D + d];
+#pragma unroll
+      for (int b = 0; b < ATT_TOKENS; ++b) U[b][h] = fmaf(w, v[it][b][h * DH + e], U[b][h]);
+    }
+  }
+  for (int i = d; i < ATT_TOKENS * ATT_TOKENS * NH; i += 64) {     // item-item scores (already scaled through q)
+    const int a = i / (ATT_TOKENS * NH), b = (i / NH) % ATT_TOKENS, h = i % NH;
+    float acc = 0.f;
+    for (int e = 0; e < DH; ++e) acc = fmaf(q[it][a][h * DH + e], k[it][b][h * DH + e], acc);
+    Ssc[it][a][h][b] = acc;
+  }
+  __syncthreads();
+  if (d < ATT_TOKENS * NH) {
+    const int a = d >> 2, h = d & 3;
+    float m = -INFINITY;
+    for (int b = 0; b < nt; ++b) m = fmaxf(m, Ssc[it][a][h][b]);
+    float sum = 0.f;
+    for (int b = 0; b < nt; ++b) { const float e = expf(Ssc[it][a][h][b] - m); P[it][a][h][b] = e; sum += e; }
+    for (int b = 0; b < ATT_TOKENS; ++b) P[it][a][h][b] = b < nt ? P[it][a][h][b] / sum : 0.f;
+    Lse[it][a][h] = nt > 0 ? m + logf(sum) : 0.f;
+  }
+  __syncthreads();
+  float* out = rec + row * ATT_ITEM;
+  const int warp2 = d >> 5, lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int a = 0; a < nt; ++a) {
+    // vals: Nbar_h (4), U_h (4), C -> centre each over the item's 64 threads (two warps)
+    float vals[2 * NH + 1];
+    float c = x[it][a][d] + out_b[d];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      float nb = 0.f;
+#pragma unroll
+      for (int b = 0; b < ATT_TOKENS; ++b) nb = fmaf(P[it][a][h][b], U[b][h], nb);
+      vals[h] = nb; c += nb;
+    }
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      float uah = 0.f;
+#pragma unroll
+      for (int b = 0; b < ATT_TOKENS; ++b) uah = (b == a) ? U[b][h] : uah;
+      vals[NH + h] = uah;
+    }
+    vals[2 * NH] = c;
+#pragma unroll
+    for (int i = 0; i < 2 * NH + 1; ++i) {
+      float part = vals[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (lane == 0) red[it][warp2][i] = part;
+    }
+    __syncthreads();
+    if (valid) {
+      float* tr = out + a * ATT_TOK;
+#pragma unroll
+      for (int i = 0; i < 2 * NH + 1; ++i) vals[i] -= (red[it][0][i] + red[it][1][i]) * (1.f / D);
+      tr[ATT_C + d] = vals[2 * NH];
+#pragma unroll
+      for (int h = 0; h < NH; ++h) { tr[ATT_NB + h * D + d] = vals[h]; tr[ATT_U + h * D + d] = vals[NH + h]; }
+      tr[ATT_Q + d] = q[it][a][d];
+      tr[ATT_K + d] = k[it][a][d] * scale;
+      if (d < NH) tr[ATT_L + d] = Lse[it][a][d];
+    }
+    __syncthreads();
+  }
+}
+
+// attention: b1' = b1 + W1 ln_b (LayerNorm bias folded into layer 1); s1[k] = ln_w[k] / M for the W1 image
+__global__ void attn_fold_ln_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ ln_w,
+                                    const float* __restrict__ ln_b, int M, float* __restrict__ b1_out, float* __restrict__ s1_out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < H1) {
+    float acc = b1[n];
+    for (int k = 0; k < D; ++k) acc = fmaf(w1[(size_t)n * D + k], ln_b[k], acc);
+    b1_out[n] = acc;
+  }
+  if (n < D) s1_out[n] = ln_w[n] / (float)M;
+}
+
+struct FastWeights {       // lives in h->fast_w; attention: followed by one UserAttn per SM
+  uint8_t wimg[2 * Map<F_GATED>::WIMG];
   float bias[H1 + H2 + H3 + H3 + 4];
+  float s1[D];             // attention: ln_w / M, the per-input scale folded into the layer-1 image
 };
 
-template <bool GATED, int FMT>
+template <int FUS, int FMT>
 static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_t st) {
-  auto kern = score_fused_kernel<GATED, FMT>;
-  const int slot = (GATED ? 0 : 2) + FMT;
+  auto kern = score_fused_kernel<FUS, FMT>;
+  const int slot = 2 * FUS + FMT;
   if (!(h->tc_attr_set & (1u << slot))) {
-    PXR_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Map<GATED>::SMEM));
+    PXR_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Map<FUS>::SMEM));
     h->tc_attr_set |= (1u << slot);
   }
   pxr_prof_begin(h, st);
-  kern<<<2 * n_pairs, THREADS, Map<GATED>::SMEM, st>>>(p);
+  kern<<<2 * n_pairs, THREADS, Map<FUS>::SMEM, st>>>(p);
   pxr_prof_end(h, st);
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
@@ -795,7 +1193,9 @@ static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_
 // ---------------------------------------------------------------------------------------------
 bool pxr_tc_supported(const pxr_handle* h) {
   const pxr_config& c = h->cfg;
-  return (c.fusion == PXR_FUSION_GATED || c.fusion == PXR_FUSION_CONCAT) && c.embedding_dim == tc::D && c.n_hidden == 3 &&
+  const bool fusion_ok = c.fusion == PXR_FUSION_GATED || c.fusion == PXR_FUSION_CONCAT ||
+                         (c.fusion == PXR_FUSION_ATTENTION && c.num_heads == tc::NH);
+  return fusion_ok && c.embedding_dim == tc::D && c.n_hidden == 3 &&
          c.hidden[0] == tc::H1 && c.hidden[1] == tc::H2 && c.hidden[2] == tc::H3 && c.activation == PXR_ACT_RELU &&
          h->M >= 4 && h->M <= 6 && h->n_sm >= 2;
 }
@@ -804,30 +1204,44 @@ bool pxr_tc_can_run(const pxr_handle* h, int32_t k) {
   return h->fast_ok && k <= tc::KCAP && h->n_rows > 0 && h->item_base + h->n_rows < (int64_t)tc::IDX_MASK;
 }
 
-size_t pxr_tc_weight_bytes(const pxr_handle* h) { (void)h; return sizeof(tc::FastWeights); }
+size_t pxr_tc_weight_bytes(const pxr_handle* h) {
+  return pxr_align_up(sizeof(tc::FastWeights), 256) +
+         (h->cfg.fusion == PXR_FUSION_ATTENTION ? (size_t)h->n_sm * sizeof(tc::UserAttn) : 0);
+}
 
 static int tc_fmt(const pxr_handle* h) { return h->cfg.precision == PXR_PRECISION_FP16 ? tc::FMT_FP16 : tc::FMT_BF16; }
 
 int pxr_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
-  if (!h->fast_w) PXR_CUDA(h, cudaMalloc(&h->fast_w, sizeof(tc::FastWeights)));
+  if (!h->fast_w) PXR_CUDA(h, cudaMalloc(&h->fast_w, pxr_tc_weight_bytes(h)));
   tc::FastWeights* fw = reinterpret_cast<tc::FastWeights*>(h->fast_w);
-  const bool gated = h->cfg.fusion == PXR_FUSION_GATED;
-  tc::build_wimg_kernel<<<296, 256, 0, st>>>(gated ? h->mlp[0].w : nullptr, h->mlp[0].k, h->mlp[1].w, h->mlp[2].w, fw->wimg,
-                                             gated ? 1 : 0, tc_fmt(h));
+  const bool gated = h->cfg.fusion != PXR_FUSION_CONCAT;    // layer 1 on the tensor pipe
+  const bool attn = h->cfg.fusion == PXR_FUSION_ATTENTION;
+  float* b = fw->bias;
+  if (attn) {     // LayerNorm affine folded into layer 1 (see attn_half_tile)
+    tc::attn_fold_ln_kernel<<<(tc::H1 + 127) / 128, 128, 0, st>>>(h->mlp[0].w, h->mlp[0].b, h->ln_w, h->ln_b, h->M, b, fw->s1);
+    h->launches++;
+  } else {
+    PXR_CUDA(h, cudaMemcpyAsync(b, h->mlp[0].b, sizeof(float) * tc::H1, cudaMemcpyDeviceToDevice, st));
+  }
+  tc::build_wimg_kernel<<<296, 256, 0, st>>>(gated ? h->mlp[0].w : nullptr, h->mlp[0].k, attn ? fw->s1 : nullptr, h->mlp[1].w,
+                                             h->mlp[2].w, fw->wimg, gated ? 1 : 0, tc_fmt(h));
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
-  float* b = fw->bias;
-  PXR_CUDA(h, cudaMemcpyAsync(b, h->mlp[0].b, sizeof(float) * tc::H1, cudaMemcpyDeviceToDevice, st));
   PXR_CUDA(h, cudaMemcpyAsync(b + tc::H1, h->mlp[1].b, sizeof(float) * tc::H2, cudaMemcpyDeviceToDevice, st));
   PXR_CUDA(h, cudaMemcpyAsync(b + tc::H1 + tc::H2, h->mlp[2].b, sizeof(float) * tc::H3, cudaMemcpyDeviceToDevice, st));
   PXR_CUDA(h, cudaMemcpyAsync(b + tc::H1 + tc::H2 + tc::H3, h->out.w, sizeof(float) * tc::H3, cudaMemcpyDeviceToDevice, st));
   PXR_CUDA(h, cudaMemcpyAsync(b + tc::H1 + tc::H2 + 2 * tc::H3, h->out.b, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (attn) {     // the attention kernel reads these through the kernel-parameter constant bank: keep a host copy
+    PXR_CUDA(h, cudaMemcpyAsync(h->tc_bias_host, b, sizeof(float) * (tc::H1 + tc::H2 + 2 * tc::H3 + 1), cudaMemcpyDeviceToHost, st));
+    PXR_CUDA(h, cudaStreamSynchronize(st));
+  }
   return PXR_OK;
 }
 
 size_t pxr_tc_item_bytes(const pxr_handle* h, int64_t n_rows) {
   const size_t rows = (size_t)((n_rows + 31) / 32 * 32);
   if (h->cfg.fusion == PXR_FUSION_GATED) return pxr_align_up(rows * 8 * sizeof(float), 256);
+  if (h->cfg.fusion == PXR_FUSION_ATTENTION) return pxr_align_up(rows * tc::ATT_ITEM * sizeof(float), 256);
   return pxr_align_up(rows * tc::H1 * sizeof(uint16_t), 256);
 }
 
@@ -837,12 +1251,15 @@ int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t s
     const int wpb = 8;
     tc::item_logit_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(h->item_feats, h->gate.w, h->gate.b, h->M,
                                                                                      n_rows, (float*)ws);
+  } else if (h->cfg.fusion == PXR_FUSION_ATTENTION) {
+    tc::item_attn_kernel<<<(unsigned)((n_rows + 3) / 4), 256, 0, st>>>(h->item_feats, h->attn_in.wt, h->attn_in.b, h->attn_out.wt,
+                                                                       h->attn_out.b, h->M, n_rows, (float*)ws);
   } else {
     const int FD = (h->M - 1) * tc::D;
     const size_t smem = (size_t)32 * (FD + tc::H1) * sizeof(float);
-    if (!(h->tc_attr_set & 16u)) {
+    if (!(h->tc_attr_set & 256u)) {
       PXR_CUDA(h, cudaFuncSetAttribute(tc::item_pi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      h->tc_attr_set |= 16u;
+      h->tc_attr_set |= 256u;
     }
     tc::item_pi_kernel<<<(unsigned)((n_rows + 31) / 32), PXR_SIMT_THREADS, smem, st>>>(h->item_feats, h->mlp[0].wt, h->mlp[0].b,
                                                                                        h->M, n_rows, (uint16_t*)ws, tc_fmt(h));
@@ -893,12 +1310,20 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
   const TcPlan pl = tc_plan(h, n_users);
   tc::FastWeights* fw = reinterpret_cast<tc::FastWeights*>(h->fast_w);
   const bool gated = h->cfg.fusion == PXR_FUSION_GATED;
+  const bool attn = h->cfg.fusion == PXR_FUSION_ATTENTION;
   tc::Params p;
   memset(&p, 0, sizeof(p));
   p.wimg = fw->wimg; p.bias = fw->bias; p.gate_w = h->gate.w;
   p.item_feats = h->item_feats;
   p.item_logit = gated ? (const float*)h->item_fast : nullptr;
-  p.item_pi = gated ? nullptr : (const uint16_t*)h->item_fast;
+  p.item_pi = (gated || attn) ? nullptr : (const uint16_t*)h->item_fast;
+  if (attn) {
+    p.attn_rec = (const float*)h->item_fast;
+    p.attn_in_wt = h->attn_in.wt; p.attn_in_b = h->attn_in.b; p.attn_out_wt = h->attn_out.wt; p.attn_out_b = h->attn_out.b;
+    p.ln_w = h->ln_w; p.ln_b = h->ln_b;
+    p.user_scratch = reinterpret_cast<tc::UserAttn*>((char*)h->fast_w + pxr_align_up(sizeof(tc::FastWeights), 256));
+    memcpy(p.bias_c, h->tc_bias_host, sizeof(float) * (tc::H1 + tc::H2 + 2 * tc::H3 + 1));
+  }
   p.w1u_t = h->mlp[0].wt;                   // [k][512]: rows 0..63 are the user columns of W1
   p.user_emb = user_embedding; p.user_idx = user_idx; p.seen_indptr = seen_indptr; p.seen_idx = seen_idx;
   p.n_users = n_users; p.n_rows = h->n_rows; p.item_base = h->item_base;
@@ -913,10 +1338,12 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
   p.out_scores = part_s; p.out_idx = part_i;
   int rc;
   const int fmt = tc_fmt(h);
-  if (gated) rc = fmt == tc::FMT_BF16 ? tc::launch_fused<true, tc::FMT_BF16>(h, p, pl.n_pairs, st)
-                                      : tc::launch_fused<true, tc::FMT_FP16>(h, p, pl.n_pairs, st);
-  else rc = fmt == tc::FMT_BF16 ? tc::launch_fused<false, tc::FMT_BF16>(h, p, pl.n_pairs, st)
-                                : tc::launch_fused<false, tc::FMT_FP16>(h, p, pl.n_pairs, st);
+  if (gated) rc = fmt == tc::FMT_BF16 ? tc::launch_fused<tc::F_GATED, tc::FMT_BF16>(h, p, pl.n_pairs, st)
+                                      : tc::launch_fused<tc::F_GATED, tc::FMT_FP16>(h, p, pl.n_pairs, st);
+  else if (attn) rc = fmt == tc::FMT_BF16 ? tc::launch_fused<tc::F_ATTN, tc::FMT_BF16>(h, p, pl.n_pairs, st)
+                                          : tc::launch_fused<tc::F_ATTN, tc::FMT_FP16>(h, p, pl.n_pairs, st);
+  else rc = fmt == tc::FMT_BF16 ? tc::launch_fused<tc::F_CONCAT, tc::FMT_BF16>(h, p, pl.n_pairs, st)
+                                : tc::launch_fused<tc::F_CONCAT, tc::FMT_FP16>(h, p, pl.n_pairs, st);
   if (rc) return rc;
   if (pl.S > 1) {
     rc = pxr_launch_merge(part_s, part_i, pl.S, n_users, k, out_scores, out_idx, st);

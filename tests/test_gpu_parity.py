@@ -295,6 +295,14 @@ def test_full_catalogue_evaluator():
 # exact oracle, differences only inside band (2).  Ties -> lower item index.
 # ======================================================================================
 TC_EMU_TOL = {"bf16": 2e-3, "fp16": 5e-4}      # kernel vs the oracle with the kernel's roundings
+# attention: the rounded operand is a sum of LayerNormed tokens (|x| up to ~6, against ~0.3 for the gated mix), so ONE
+# element landing on the other side of a 16-bit rounding boundary (fp32 kernel vs fp64 emulation) moves a score by up
+# to 3e-3 (measured 2.9e-3 bf16); such flips are rare: the 99th percentile of |ds| must stay below tol / 8.
+TC_EMU_FLIP = {"attention": 3.0}
+
+
+def _emu_tol(fusion, dtype):
+    return TC_EMU_TOL[dtype] * TC_EMU_FLIP.get(fusion, 1.0)
 TC_BAND = {"bf16": 3e-2, "fp16": 6e-3}         # 16-bit operands vs the exact oracle: the stated tolerance
 TC_BF16_TOL = TC_BAND["bf16"]
 _RND = {"bf16": orc.round_bf16, "fp16": orc.round_fp16}
@@ -345,7 +353,9 @@ def _structural_checks(s, i, k, n_items, indptr=None, idx=None, item_lo=0):
     ("gated", "bf16", 48, 1500, 50, True), ("gated", "bf16", 16, 48, 64, False), ("gated", "bf16", 33, 1000, 10, True),
     ("gated", "fp16", 48, 1500, 50, True),
     ("concatenate", "bf16", 48, 1500, 50, True), ("concatenate", "bf16", 16, 48, 64, False),
-    ("concatenate", "bf16", 33, 1000, 10, True), ("concatenate", "fp16", 48, 1500, 50, True)])
+    ("concatenate", "bf16", 33, 1000, 10, True), ("concatenate", "fp16", 48, 1500, 50, True),
+    ("attention", "bf16", 48, 1500, 50, True), ("attention", "bf16", 16, 48, 64, False),
+    ("attention", "bf16", 33, 1000, 10, True), ("attention", "fp16", 48, 1500, 50, True)])
 def test_tcgen05_matches_emulated_and_exact_oracle(fusion, dtype, n_users, n_items, k, filt):
     spec, sd, feats, indptr, idx, _ = _tc_workload(n_users, n_items, syn.SEED + 21, fusion)
     model, eng = _engine_for(spec, sd, feats, "tcgen05", dtype=dtype)
@@ -359,9 +369,11 @@ def test_tcgen05_matches_emulated_and_exact_oracle(fusion, dtype, n_users, n_ite
     ref = orc.score_block(sd, cs.spec_cfg(spec), users, 0, n_items, feats)
     assert np.max(np.abs(emu - ref)) <= TC_BAND[dtype]       # what 16-bit operands cost on this model
     same_emu = same_ref = total = 0
+    errs = np.concatenate([np.abs(s[u][i[u] >= 0] - emu[u][i[u][i[u] >= 0]]) for u in users])
+    assert np.quantile(errs, 0.99) <= TC_EMU_TOL[dtype] / 8, float(np.quantile(errs, 0.99))
     for u in users:
         seen = idx[indptr[u]:indptr[u + 1]] if filt else None
-        same_emu += _check_topk(s[u], i[u], emu[u], k, seen, TC_EMU_TOL[dtype], 0.0)
+        same_emu += _check_topk(s[u], i[u], emu[u], k, seen, _emu_tol(fusion, dtype), 0.0)
         same_ref += _check_topk(s[u], i[u], ref[u], k, seen, TC_BAND[dtype], 0.0)
         total += min(k, n_items - (len(seen) if seen is not None else 0))
     assert same_emu >= 0.97 * total, (same_emu, total)       # identical to the emulation except near-ties
@@ -369,7 +381,7 @@ def test_tcgen05_matches_emulated_and_exact_oracle(fusion, dtype, n_users, n_ite
           f"{same_ref}/{total} to the exact oracle; max|emu-exact| = {np.max(np.abs(emu - ref)):.2e}")
 
 
-@pytest.mark.parametrize("fusion", ["gated", "concatenate"])
+@pytest.mark.parametrize("fusion", ["gated", "concatenate", "attention"])
 def test_tcgen05_many_units_and_item_splits(fusion):
     """More user groups than CTA pairs (several units per pair: list reset between units) and an item
     range split across units (partial lists merged by K4): sampled users vs the emulated oracle, all
@@ -386,7 +398,7 @@ def test_tcgen05_many_units_and_item_splits(fusion):
     sample = np.array([0, 1, 7, 8, 15, 16, 17, 1183, 1184, 1199, 2047, 2048, 2491, 2496, 2499])
     emu = _lowp_scores(sd, spec, feats, sample)
     for r, u in enumerate(sample):
-        _check_topk(s[u].astype(np.float64), i[u], emu[r], k, idx[indptr[u]:indptr[u + 1]], TC_EMU_TOL["bf16"], 0.0)
+        _check_topk(s[u].astype(np.float64), i[u], emu[r], k, idx[indptr[u]:indptr[u + 1]], _emu_tol(fusion, "bf16"), 0.0)
     # a ragged user subset (not a multiple of 16, arbitrary order) gives the same lists
     sub = torch.tensor([2499, 3, 1184, 77, 16], device="cuda")
     sub_ptr = torch.zeros(6, dtype=torch.int64)
@@ -408,7 +420,7 @@ def test_tcgen05_many_units_and_item_splits(fusion):
     assert torch.equal(mi_, fi) and torch.equal(ms_, fs)
 
 
-@pytest.mark.parametrize("fusion", ["gated", "concatenate"])
+@pytest.mark.parametrize("fusion", ["gated", "concatenate", "attention"])
 def test_tcgen05_full_size_properties(fusion):
     """BASELINE.json configs[1] catalogue size (96 282 items), one block of users: structural properties
     of every list and agreement with the fp32 SIMT path inside the stated bf16 band."""
