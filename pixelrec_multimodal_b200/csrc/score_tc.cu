@@ -47,10 +47,12 @@ constexpr int D = 64, H1 = 512, H2 = 256, H3 = 128;
 constexpr int TU = 8, TI = 16;            // users x items per CTA tile (128 rows)
 constexpr int KCAP = 64;                  // slots of the per-user sorted list (K <= KCAP)
 constexpr int QCAP = 512;                 // candidate queue entries
-constexpr int THREADS = 512;
+constexpr int THREADS = 512;                 // gated / concat: 16 warps
+constexpr int THREADS_ATT = 640;             // attention: a second front-end warpgroup (warps 16-19)
 constexpr uint32_t IDX_MASK = 0x0FFFFFFFu;   // 28-bit item index inside a queue / list key
 constexpr int FMT_BF16 = 0, FMT_FP16 = 1;
 constexpr int F_CONCAT = 0, F_GATED = 1, F_ATTN = 2;   // front ends of the kernel template
+template <int FUS> __host__ __device__ constexpr int n_threads() { return FUS == F_ATTN ? THREADS_ATT : THREADS; }
 constexpr int NH = 4, DH = D / NH;                      // attention: heads x head dim (fast path: 4 x 16)
 // attention: per-item record, ATT_TOKENS token blocks of ATT_TOK floats (see item_attn_kernel)
 constexpr int ATT_TOKENS = 5, ATT_TOK = 720, ATT_ITEM = ATT_TOKENS * ATT_TOK;
@@ -340,12 +342,24 @@ __device__ __forceinline__ void attn_user_setup(const Params& p, MiscA& ms, floa
 
 // acc = sum over tokens of the normalised rows, for the 8 users x 8 items of one half tile -> 16-bit A1 rows.
 // `wait_a1` is called once, right before the first store into A1.
+// The front end is one warp per scheduler, so latency is hidden by instruction-level parallelism only: every step is
+// written as a loop over users (4 or 8 independent chains), with the shuffles of one step issued back to back.
 template <int FMT, class MiscA, typename WaitA1>
 __device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* us, const float* rec, int nt, uint8_t* a1,
                                                int half, int tid, int lane, WaitA1 wait_a1) {
   const int j8 = tid >> 4, s = tid & 15, hd = s >> 2;
   const int gb = lane & 16;                                // first lane of this item's 16-lane group
   float acc[TU][4];
+  // token data of the first item token: fetched now, consumed after the user-token row
+  float4 c, q, nb[NH]; float Lh;
+  auto load_tok = [&](int a, float4& c_, float4& q_, float4* nb_, float& L_) {
+    const float* tr = rec + a * ATT_TOK;
+    c_ = ldg_stream(tr + ATT_C + 4 * s);
+    q_ = ldg_stream(tr + ATT_Q + 4 * s);
+#pragma unroll
+    for (int h = 0; h < NH; ++h) nb_[h] = ldg_stream(tr + ATT_NB + h * D + 4 * s);
+    L_ = __ldg(tr + ATT_L + hd);
+  };
   {
     // ---- token 0 (the user token): scores against every token, softmax per head, value mix, normalise
     float S[TU][ATT_TOKENS];
@@ -355,11 +369,24 @@ __device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* 
       for (int b = 0; b < ATT_TOKENS; ++b) kb[b] = ldg_stream(rec + min(b, nt - 1) * ATT_TOK + ATT_K + 4 * s);
 #pragma unroll
       for (int u = 0; u < TU; ++u) {
+        const float4 c0 = __ldcg(reinterpret_cast<const float4*>(&us->C0c[u][4 * s]));
+        acc[u][0] = c0.x; acc[u][1] = c0.y; acc[u][2] = c0.z; acc[u][3] = c0.w;
+      }
+#pragma unroll
+      for (int u = 0; u < TU; ++u) {
         const float4 qv = *reinterpret_cast<const float4*>(&ms.qu[u][4 * s]);
 #pragma unroll
-        for (int b = 0; b < ATT_TOKENS; ++b) S[u][b] = sum4_head(dot4(qv, kb[b]));
+        for (int b = 0; b < ATT_TOKENS; ++b) S[u][b] = dot4(qv, kb[b]);
       }
     }
+#pragma unroll
+    for (int u = 0; u < TU; ++u)
+#pragma unroll
+      for (int b = 0; b < ATT_TOKENS; ++b) S[u][b] += __shfl_xor_sync(0xffffffffu, S[u][b], 1);
+#pragma unroll
+    for (int u = 0; u < TU; ++u)
+#pragma unroll
+      for (int b = 0; b < ATT_TOKENS; ++b) S[u][b] += __shfl_xor_sync(0xffffffffu, S[u][b], 2);
     float p0[TU];
 #pragma unroll
     for (int u = 0; u < TU; ++u) {
@@ -377,12 +404,12 @@ __device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* 
       for (int b = 0; b < ATT_TOKENS; ++b) S[u][b] *= inv;
     }
 #pragma unroll
-    for (int u = 0; u < TU; ++u) {
-      const float4 c0 = __ldcg(reinterpret_cast<const float4*>(&us->C0c[u][4 * s]));
-      acc[u][0] = c0.x; acc[u][1] = c0.y; acc[u][2] = c0.z; acc[u][3] = c0.w;
+    for (int h = 0; h < NH; ++h) {
+      float ph[TU];
 #pragma unroll
-      for (int h = 0; h < NH; ++h)
-        fma4(acc[u], __shfl_sync(0xffffffffu, p0[u], gb | (4 * h)), *reinterpret_cast<const float4*>(&ms.U0c[u][h][4 * s]));
+      for (int u = 0; u < TU; ++u) ph[u] = __shfl_sync(0xffffffffu, p0[u], gb | (4 * h));
+#pragma unroll
+      for (int u = 0; u < TU; ++u) fma4(acc[u], ph[u], *reinterpret_cast<const float4*>(&ms.U0c[u][h][4 * s]));
     }
 #pragma unroll
     for (int b = 0; b < ATT_TOKENS; ++b) {
@@ -390,56 +417,81 @@ __device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* 
 #pragma unroll
       for (int h = 0; h < NH; ++h) ub[h] = ldg_stream(rec + min(b, nt - 1) * ATT_TOK + ATT_U + h * D + 4 * s);
 #pragma unroll
-      for (int u = 0; u < TU; ++u)
+      for (int h = 0; h < NH; ++h) {
+        float ph[TU];
 #pragma unroll
-        for (int h = 0; h < NH; ++h) fma4(acc[u], __shfl_sync(0xffffffffu, S[u][b], gb | (4 * h)), ub[h]);   // weight 0 for b >= nt
+        for (int u = 0; u < TU; ++u) ph[u] = __shfl_sync(0xffffffffu, S[u][b], gb | (4 * h));   // weight 0 for b >= nt
+#pragma unroll
+        for (int u = 0; u < TU; ++u) fma4(acc[u], ph[u], ub[h]);
+      }
     }
+    load_tok(0, c, q, nb, Lh);
+    float ss[TU];
+#pragma unroll
+    for (int u = 0; u < TU; ++u)
+      ss[u] = fmaf(acc[u][3], acc[u][3], fmaf(acc[u][2], acc[u][2], fmaf(acc[u][1], acc[u][1], acc[u][0] * acc[u][0])));
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1)
+#pragma unroll
+      for (int u = 0; u < TU; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
 #pragma unroll
     for (int u = 0; u < TU; ++u) {
-      const float ss = fmaf(acc[u][3], acc[u][3], fmaf(acc[u][2], acc[u][2], fmaf(acc[u][1], acc[u][1], acc[u][0] * acc[u][0])));
-      const float r = rsqrtf(sum16_item(ss) * (1.f / D) + 1e-5f);
+      const float r = rsqrtf(ss[u] * (1.f / D) + 1e-5f);
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[u][i] *= r;
     }
   }
   // ---- item tokens a >= 1 (token data of a + 1 is fetched while a is being combined)
-  float4 c, q, nb[NH]; float Lh;
-  auto load_tok = [&](int a, float4& c_, float4& q_, float4* nb_, float& L_) {
-    const float* tr = rec + a * ATT_TOK;
-    c_ = ldg_stream(tr + ATT_C + 4 * s);
-    q_ = ldg_stream(tr + ATT_Q + 4 * s);
-#pragma unroll
-    for (int h = 0; h < NH; ++h) nb_[h] = ldg_stream(tr + ATT_NB + h * D + 4 * s);
-    L_ = __ldg(tr + ATT_L + hd);
-  };
-  load_tok(0, c, q, nb, Lh);
 #pragma unroll 1
   for (int a = 0; a < nt; ++a) {
     float4 c2, q2, nb2[NH]; float L2;
     load_tok(min(a + 1, nt - 1), c2, q2, nb2, L2);
 #pragma unroll
-    for (int u = 0; u < TU; ++u) {
-      const float d = sum4_head(dot4(q, *reinterpret_cast<const float4*>(&ms.ku[u][4 * s])));
-      const float w = __fdividef(1.f, 1.f + __expf(Lh - d));        // sigmoid(s_a0 - L_ah)
-      float y[4] = {c.x, c.y, c.z, c.w};
+    for (int ug = 0; ug < 2; ++ug) {
+      float w[4], y[4][4], ss[4];
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) w[u4] = dot4(q, *reinterpret_cast<const float4*>(&ms.ku[4 * ug + u4][4 * s]));
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) w[u4] += __shfl_xor_sync(0xffffffffu, w[u4], 1);
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) w[u4] += __shfl_xor_sync(0xffffffffu, w[u4], 2);
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) {
+        w[u4] = __fdividef(1.f, 1.f + __expf(Lh - w[u4]));           // sigmoid(s_a0 - L_ah)
+        y[u4][0] = c.x; y[u4][1] = c.y; y[u4][2] = c.z; y[u4][3] = c.w;
+      }
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
-        const float wh = __shfl_sync(0xffffffffu, w, gb | (4 * h));
-        const float4 uv = *reinterpret_cast<const float4*>(&ms.U0c[u][h][4 * s]);
-        y[0] = fmaf(wh, uv.x - nb[h].x, y[0]); y[1] = fmaf(wh, uv.y - nb[h].y, y[1]);
-        y[2] = fmaf(wh, uv.z - nb[h].z, y[2]); y[3] = fmaf(wh, uv.w - nb[h].w, y[3]);
-      }
-      const float ss = fmaf(y[3], y[3], fmaf(y[2], y[2], fmaf(y[1], y[1], y[0] * y[0])));
-      const float r = rsqrtf(sum16_item(ss) * (1.f / D) + 1e-5f);
+        float wh[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[u][i] = fmaf(r, y[i], acc[u][i]);
+        for (int u4 = 0; u4 < 4; ++u4) wh[u4] = __shfl_sync(0xffffffffu, w[u4], gb | (4 * h));
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) {
+          const float4 uv = *reinterpret_cast<const float4*>(&ms.U0c[4 * ug + u4][h][4 * s]);
+          y[u4][0] = fmaf(wh[u4], uv.x - nb[h].x, y[u4][0]); y[u4][1] = fmaf(wh[u4], uv.y - nb[h].y, y[u4][1]);
+          y[u4][2] = fmaf(wh[u4], uv.z - nb[h].z, y[u4][2]); y[u4][3] = fmaf(wh[u4], uv.w - nb[h].w, y[u4][3]);
+        }
+      }
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4)
+        ss[u4] = fmaf(y[u4][3], y[u4][3], fmaf(y[u4][2], y[u4][2], fmaf(y[u4][1], y[u4][1], y[u4][0] * y[u4][0])));
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1)
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) ss[u4] += __shfl_xor_sync(0xffffffffu, ss[u4], o);
+#pragma unroll
+      for (int u4 = 0; u4 < 4; ++u4) {
+        const float r = rsqrtf(ss[u4] * (1.f / D) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[4 * ug + u4][i] = fmaf(r, y[u4][i], acc[4 * ug + u4][i]);
+      }
     }
     c = c2; q = q2; Lh = L2;
 #pragma unroll
     for (int h = 0; h < NH; ++h) nb[h] = nb2[h];
   }
   // ---- 16-bit pack into the swizzled A1 rows (row = user * 16 + item; 8 bytes per thread)
-  if (half == 0) wait_a1();
+  wait_a1();
   const int j = 8 * half + j8;
 #pragma unroll
   for (int u = 0; u < TU; ++u) {
@@ -456,8 +508,9 @@ __device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* 
 // FUS selects the front end.  GATED below means "layer 1 runs on the tensor pipe from an A1 tile in shared memory"
 // (gated and attention fusion: the fused vector depends on the pair); concat feeds layer-1 partial sums instead.
 template <int FUS, int FMT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads<FUS>(), 1)
 score_fused_kernel(const __grid_constant__ Params p) {
+  constexpr int NT = n_threads<FUS>();
   constexpr bool GATED = (FUS != F_CONCAT);
   constexpr bool ATT = (FUS == F_ATTN);
   using MP = Map<FUS>;
@@ -476,7 +529,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
   // ------------------------------------------------------------------ setup
-  if (!ATT) for (int i = threadIdx.x; i < H1 + H2 + H3 + H3; i += THREADS) ms.b1[i] = p.bias[i];   // b1,b2,b3,w4 are contiguous
+  if (!ATT) for (int i = threadIdx.x; i < H1 + H2 + H3 + H3; i += NT) ms.b1[i] = p.bias[i];   // b1,b2,b3,w4 are contiguous
   // epilogue constants: shared memory, or (attention) the kernel-parameter constant bank
   const float* const cb1 = ATT ? p.bias_c : ms.b1;
   const float* const cb2 = ATT ? p.bias_c + H1 : ms.b2;
@@ -486,7 +539,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
     ms.b4 = ATT ? p.bias_c[H1 + H2 + H3 + H3] : p.bias[H1 + H2 + H3 + H3];
     ms.q_tail = 0; ms.q_head = 0;
     ptx::mbar_init(BAR(BAR_W), 1);
-    ptx::mbar_init(BAR(BAR_A_FULL), 8);
+    ptx::mbar_init(BAR(BAR_A_FULL), ATT ? 16 : 8);        // one arrival per front-end warp of both CTAs
     ptx::mbar_init(BAR(BAR_A_EMPTY), 1);
     for (int b = 0; b < 4; ++b) {
       ptx::mbar_init(BAR(BAR_D1_FULL0 + b), 1);
@@ -502,8 +555,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
     ptx::mbar_init(BAR(BAR_UNIT_RESET), 1);
     ptx::fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < TU * KCAP; i += THREADS) (&ms.list[0][0])[i] = 0ull;
-  for (int i = threadIdx.x; i < QC; i += THREADS) ms.queue[i] = 0ull;
+  for (int i = threadIdx.x; i < TU * KCAP; i += NT) (&ms.list[0][0])[i] = 0ull;
+  for (int i = threadIdx.x; i < QC; i += NT) ms.queue[i] = 0ull;
   if (threadIdx.x < TU) ms.thr[threadIdx.x] = -INFINITY;
   __syncthreads();
   if (warp == 4) {
@@ -526,9 +579,17 @@ score_fused_kernel(const __grid_constant__ Params p) {
   // units of this pair: w = pair, pair + n_pairs, ...; every role walks the same (unit, tile) sequence;
   // T counts tiles over all units of the pair
 
-  if (warp < 4) {
+  // attention: register budget per warpgroup.  640 threads are launched with 96 registers each and setmaxnreg can
+  // only move registers inside that pool (61 440): the MMA / top-K warpgroup drops to 40, the two front-end
+  // warpgroups take 120, the epilogue warpgroups keep 96  (2*128*120 + 128*40 + 2*128*96 = 60 416).
+  // (setmaxnreg sits at the top of each warpgroup's branch so that ptxas allocates per role).
+  if (warp < 4 || (ATT && warp >= 16)) {
+    if (ATT) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
     // =============================================================== front end
-    const int tid = threadIdx.x;            // 0..127
+    // attention: warpgroup A (warps 0-3) builds the per-unit user constants and the first half of every tile,
+    // warpgroup B (warps 16-19) the second half; named barriers 2 / 3 fence the user constants between units.
+    const bool feB = ATT && warp >= 16;
+    const int tid = threadIdx.x & 127;      // 0..127 inside the front-end warpgroup
     const int Mm = p.M;
     int T = 0;
     for (int w = pair; w < p.n_units; w += n_pairs) {
@@ -538,6 +599,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
         // Pu is read by the layer-1 producers of the previous unit's last tile: wait until they are done with it
         ptx::mbar_wait(BAR(BAR_PI_EMPTY0 + ((T - 1) & 1)), ((T - 1) >> 1) & 1);
       }
+      if (ATT) asm volatile("bar.sync 2, 256;" ::: "memory");      // both warpgroups are done with the previous unit
+      if (!feB) {
       asm volatile("bar.sync 1, 128;" ::: "memory");              // previous unit's readers of eu/lu are done
       {
         // attention stages E_u (and v_u) in the A1 tile: wait until the layer-1 MMAs of the previous tile have read it
@@ -583,6 +646,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
           *reinterpret_cast<float4*>(sm + MP::OFF_PU + u * MP::PU_STRIDE + 16 * tid) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (ATT) asm volatile("bar.sync 3, 256;" ::: "memory");      // user constants of this unit are in place
       // seen-item cursors: lanes 0..7 of warp 0 walk user u's ascending history with the item sweep
       int64_t cur = 0, cend = 0; int32_t nextv = 0x7fffffff;
       if (warp == 0 && lane < TU && p.seen_indptr && ubase + lane < p.n_users) {
@@ -610,8 +675,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
         };
         if (FUS == F_ATTN) {
           write_seen_mask();
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
+          {
+            const int half = feB ? 1 : 0;
             const int64_t row = row0 + 8 * half + (tid >> 4);
             const int64_t rr = row < un.row_hi ? row : un.row_lo;    // padding rows recompute a valid item (discarded later)
             attn_half_tile<FMT>(ms, p.user_scratch + blockIdx.x, p.attn_rec + rr * ATT_ITEM, Mm - 1, sm + MP::OFF_A1, half, tid,
@@ -693,7 +758,9 @@ score_fused_kernel(const __grid_constant__ Params p) {
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp < 8) {
+   if (ATT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+   if (warp == 4) {
     // =============================================================== MMA issuer (leader CTA, one thread)
     if (rank == 0 && lane == 0) {
       int NT = 0;
@@ -768,7 +835,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
         issue_m3(NT - 1);
       }
     }
-  } else if (warp == 5) {
+   } else if (warp == 5) {
     // =============================================================== top-K warp
     uint32_t head = 0, done_ph = 0;
     for (int w = pair; w < p.n_units; w += n_pairs) {
@@ -838,8 +905,9 @@ score_fused_kernel(const __grid_constant__ Params p) {
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_local(BAR(BAR_UNIT_RESET));
     }
-  } else if (warp >= 8) {
-    // =============================================================== epilogue groups
+   }
+  } else {
+    // =============================================================== epilogue groups (warps 8-15)
     const int grp = (warp - 8) >> 2;                 // 0: even layer-1 chunks, first half of layer 2, layer 3
     const int q = warp & 3;                          // TMEM lane quarter this warp may touch
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
@@ -1179,7 +1247,7 @@ static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_
     h->tc_attr_set |= (1u << slot);
   }
   pxr_prof_begin(h, st);
-  kern<<<2 * n_pairs, THREADS, Map<FUS>::SMEM, st>>>(p);
+  kern<<<2 * n_pairs, n_threads<FUS>(), Map<FUS>::SMEM, st>>>(p);
   pxr_prof_end(h, st);
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
