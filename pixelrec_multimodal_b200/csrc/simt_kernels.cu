@@ -6,6 +6,8 @@
 //   K5     metrics         Precision/Recall/F1/HitRate/NDCG/MRR@K sums
 // The tcgen05 path (score_tc.cu) replaces K3g+K3t for the supported shapes; these
 // kernels remain the path for every other configuration and for explicit pairs.
+#include <algorithm>
+
 #include "pxr_common.cuh"
 
 // ===========================================================================
@@ -450,30 +452,63 @@ int pxr_launch_topk_rows(pxr_handle* h, const float* scores, int64_t n_users, in
 // ===========================================================================
 // K4: merge S per-shard top-K lists per user (rank by counting; keys distinct)
 // ===========================================================================
-#define MERGE_THREADS 128
 #define MERGE_MAX_KEYS 4096
+#define MERGE_MAX_WARPS 8
 
-__global__ void __launch_bounds__(MERGE_THREADS) merge_topk_kernel(const float* __restrict__ scores_in,
-                                                                    const int32_t* __restrict__ idx_in, int n_shards,
-                                                                    int64_t n_users, int k, float* out_scores,
-                                                                    int32_t* out_idx) {
-  __shared__ unsigned long long keys[MERGE_MAX_KEYS];
-  const int64_t u = blockIdx.x;
-  const int n = n_shards * k;
-  for (int i = threadIdx.x; i < n; i += MERGE_THREADS) {
-    const int s = i / k, j = i % k;
-    const int64_t off = ((int64_t)s * n_users + u) * k + j;
-    const int32_t id = idx_in[off];
-    keys[i] = id < 0 ? 0ull : pxr_key(scores_in[off], (uint32_t)id);
-  }
-  for (int i = threadIdx.x; i < k; i += MERGE_THREADS) { out_scores[u * k + i] = -INFINITY; out_idx[u * k + i] = -1; }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += MERGE_THREADS) {
-    const unsigned long long me = keys[i];
-    if (me == 0ull) continue;
-    int rank = 0;
-    for (int j = 0; j < n; ++j) rank += (keys[j] > me);
-    if (rank < k) { out_scores[u * k + rank] = pxr_key_score(me); out_idx[u * k + rank] = (int32_t)pxr_key_idx(me); }
+// One warp per user.  Every per-shard list is already sorted by (score desc, index asc), so the S lists are merged
+// pairwise in a tree, each 2-way merge keeping only the best k: output position r of a pair is found by a
+// merge-path binary search (log2 k steps) and all positions are independent, so lanes take r = lane, lane + 32, ...
+// Keys are the 64-bit composites of pxr_key (unique per item; 0 = padding, smallest), staged in shared memory.
+// HBM traffic is the algorithmic 8 k S bytes in + 8 k bytes out per user (coalesced: a user's k entries of one
+// shard are contiguous, consecutive users of a block too).
+__global__ void __launch_bounds__(32 * MERGE_MAX_WARPS) merge_topk_kernel(const float* __restrict__ scores_in,
+                                                                           const int32_t* __restrict__ idx_in, int n_shards,
+                                                                           int64_t n_users, int k, int warps_per_block,
+                                                                           float* __restrict__ out_scores,
+                                                                           int32_t* __restrict__ out_idx) {
+  extern __shared__ unsigned long long merge_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= warps_per_block) return;
+  const int half_lists = (n_shards + 1) / 2;
+  unsigned long long* bufA = merge_smem + (size_t)warp * (n_shards + half_lists) * k;   // n_shards lists
+  unsigned long long* bufB = bufA + (size_t)n_shards * k;                               // ceil(n_shards / 2) lists
+  for (int64_t u = (int64_t)blockIdx.x * warps_per_block + warp; u < n_users; u += (int64_t)gridDim.x * warps_per_block) {
+    for (int s = 0; s < n_shards; ++s) {
+      const int64_t off = ((int64_t)s * n_users + u) * k;
+      for (int j = lane; j < k; j += 32) {
+        const int32_t id = idx_in[off + j];
+        bufA[s * k + j] = id < 0 ? 0ull : pxr_key(scores_in[off + j], (uint32_t)id);
+      }
+    }
+    __syncwarp();
+    unsigned long long* src = bufA; unsigned long long* dst = bufB;
+    int n = n_shards;
+    while (n > 1) {
+      const int pairs = n / 2;
+      for (int t = lane; t < pairs * k; t += 32) {
+        const int pr = t / k, r = t % k;
+        const unsigned long long* A = src + (2 * pr) * k;
+        const unsigned long long* B = A + k;
+        int lo = 0, hi = r;                      // i = number of the first r outputs that come from A (both lists hold k keys)
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (A[mid] > B[r - mid - 1]) lo = mid + 1; else hi = mid;
+        }
+        const int i = lo, j = r - lo;
+        const unsigned long long a = i < k ? A[i] : 0ull, b2 = j < k ? B[j] : 0ull;
+        dst[pr * k + r] = a > b2 ? a : b2;
+      }
+      if (n & 1) for (int j = lane; j < k; j += 32) dst[pairs * k + j] = src[(n - 1) * k + j];
+      __syncwarp();
+      unsigned long long* tmp = src; src = dst; dst = tmp;
+      n = pairs + (n & 1);
+    }
+    for (int j = lane; j < k; j += 32) {
+      const unsigned long long key = src[j];
+      out_scores[u * k + j] = key ? pxr_key_score(key) : -INFINITY;
+      out_idx[u * k + j] = key ? (int32_t)pxr_key_idx(key) : -1;
+    }
+    __syncwarp();
   }
 }
 
@@ -481,7 +516,21 @@ int pxr_launch_merge(const float* scores_in, const int32_t* idx_in, int32_t n_sh
                      float* out_scores, int32_t* out_idx, cudaStream_t st) {
   if ((int64_t)n_shards * k > MERGE_MAX_KEYS) return PXR_ERR_INVALID;
   if (n_users == 0) return PXR_OK;
-  merge_topk_kernel<<<(unsigned)n_users, MERGE_THREADS, 0, st>>>(scores_in, idx_in, n_shards, n_users, k, out_scores, out_idx);
+  const size_t per_warp = (size_t)(n_shards + (n_shards + 1) / 2) * k * sizeof(unsigned long long);
+  int wpb = (int)std::min<size_t>(MERGE_MAX_WARPS, (96 * 1024) / per_warp);
+  if (wpb < 1) return PXR_ERR_INVALID;
+  const size_t smem = per_warp * wpb;
+  static bool attr_set = false;                  // raising the limit is idempotent and per function, not per handle
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) return PXR_ERR_CUDA;
+    attr_set = true;
+  }
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (n_users + wpb - 1) / wpb;
+  const unsigned blocks = (unsigned)std::min<int64_t>(want, (int64_t)n_sm * 8);
+  merge_topk_kernel<<<blocks, 32 * wpb, smem, st>>>(scores_in, idx_in, n_shards, n_users, k, wpb, out_scores, out_idx);
   return cudaGetLastError() == cudaSuccess ? PXR_OK : PXR_ERR_CUDA;
 }
 
@@ -547,13 +596,86 @@ __global__ void __launch_bounds__(METRIC_THREADS) metrics_user_kernel(const int3
   }
 }
 
+// Fast variant for lists of at most 64 entries: one warp walks a contiguous range of users; the lanes hold the list
+// (coalesced row read), hits are found by ballot per positive, every cut-off is a popcount of the hit mask.  The
+// discounted gain is summed left to right over the hit positions, the order of the reference loop (tasks.py:733-747).
+// Per-warp partial sums live in shared memory; blocks and warps own fixed user ranges => deterministic result.
+#define METRIC_WARPS 4
+__global__ void __launch_bounds__(32 * METRIC_WARPS) metrics_warp_kernel(const int32_t* __restrict__ topk, int k_stride,
+                                                                         int64_t n_users, int64_t users_per_warp,
+                                                                         const int64_t* __restrict__ gt_indptr,
+                                                                         const int32_t* __restrict__ gt_idx, MetricKs ks,
+                                                                         const double* __restrict__ discount,
+                                                                         const double* __restrict__ ideal,
+                                                                         double* __restrict__ block_sums) {
+  __shared__ double acc[METRIC_WARPS][PXR_MAX_KS * METRIC_COLS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = lane; i < PXR_MAX_KS * METRIC_COLS; i += 32) acc[warp][i] = 0.0;
+  __syncwarp();
+  const int64_t w = (int64_t)blockIdx.x * METRIC_WARPS + warp;
+  const int64_t u0 = w * users_per_warp, u1 = min(n_users, u0 + users_per_warp);
+  for (int64_t u = u0; u < u1; ++u) {
+    const int64_t g0 = gt_indptr[u], g1 = gt_indptr[u + 1];
+    const int npos = (int)(g1 - g0);
+    if (npos <= 0) continue;                          // "if not pos_set: continue" (tasks.py:589-591): contributes zeros
+    const int32_t* rec = topk + u * k_stride;
+    const int32_t r0 = lane < k_stride ? rec[lane] : -1;
+    const int32_t r1 = lane + 32 < k_stride ? rec[lane + 32] : -1;
+    unsigned long long hit = 0ull;
+    for (int64_t g = g0; g < g1; g += 32) {           // positives, 32 at a time
+      const int32_t mine = g + lane < g1 ? gt_idx[g + lane] : -2;
+      const int cnt = (int)min((int64_t)32, g1 - g);
+      for (int t = 0; t < cnt; ++t) {
+        const int32_t pv = __shfl_sync(0xffffffffu, mine, t);
+        hit |= (unsigned long long)__ballot_sync(0xffffffffu, r0 == pv) |
+               ((unsigned long long)__ballot_sync(0xffffffffu, r1 == pv) << 32);
+      }
+    }
+    const unsigned long long valid = (unsigned long long)__ballot_sync(0xffffffffu, r0 >= 0) |
+                                     ((unsigned long long)__ballot_sync(0xffffffffu, r1 >= 0) << 32);
+    if (lane == 0) {
+      const int first = hit ? __ffsll((long long)hit) : 0;
+      double dcg = 0.0;
+      unsigned long long rest = hit;
+      for (int a = 0; a < ks.n; ++a) {
+        const int k = ks.k[a];
+        const unsigned long long km = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
+        while (rest) {                                // extend the left-to-right sum to the hits below this cut-off
+          const int j = __ffsll((long long)rest) - 1;
+          if (j >= k) break;
+          dcg += discount[j];
+          rest &= rest - 1;
+        }
+        const int hits = __popcll(hit & km), nrec = __popcll(valid & km);
+        const double prec = nrec > 0 ? (double)hits / (double)nrec : 0.0;   // denominator len(recs), tasks.py:577
+        const double rec_ = (double)hits / (double)npos;
+        const double f1 = (prec + rec_) > 0.0 ? 2.0 * prec * rec_ / (prec + rec_) : 0.0;
+        const double idcg = ideal[npos < k ? npos : k];
+        double* o = acc[warp] + a * METRIC_COLS;
+        o[0] += prec; o[1] += rec_; o[2] += f1; o[3] += hits > 0 ? 1.0 : 0.0;
+        o[4] += idcg > 0.0 ? dcg / idcg : 0.0;
+        o[5] += (first && first <= k) ? 1.0 / (double)first : 0.0;
+        o[6] += hits > 0 ? dcg / ideal[hits] : 0.0;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PXR_MAX_KS * METRIC_COLS; i += blockDim.x) {
+    double t = 0.0;
+    for (int ww = 0; ww < METRIC_WARPS; ++ww) t += acc[ww][i];
+    block_sums[(int64_t)blockIdx.x * (PXR_MAX_KS * METRIC_COLS) + i] = t;
+  }
+}
+
 __global__ void metrics_final_kernel(const double* __restrict__ block_sums, int64_t n_blocks, int n_ks, double* out) {
-  // one thread per (k, column); fixed summation order => deterministic
-  const int t = threadIdx.x;
+  // one warp (block) per (k, column): lanes take blocks lane, lane + 32, ... then a fixed-order butterfly => deterministic
+  const int t = blockIdx.x, lane = threadIdx.x & 31;
   if (t >= n_ks * METRIC_COLS) return;
   double s = 0.0;
-  for (int64_t b = 0; b < n_blocks; ++b) s += block_sums[b * (PXR_MAX_KS * METRIC_COLS) + t];
-  out[t] = s;
+  for (int64_t b = lane; b < n_blocks; b += 32) s += block_sums[b * (PXR_MAX_KS * METRIC_COLS) + t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[t] = s;
 }
 
 int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, const int64_t* gt_indptr,
@@ -561,10 +683,21 @@ int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_user
                        const double* ideal, double* out_sums, void* ws, cudaStream_t st) {
   MetricKs mk; mk.n = n_ks;
   for (int i = 0; i < n_ks; ++i) { mk.k[i] = ks[i]; if (i && ks[i] <= ks[i - 1]) return PXR_ERR_INVALID; if (ks[i] > k_stride || ks[i] <= 0) return PXR_ERR_INVALID; }
-  const int64_t blocks = (n_users + METRIC_THREADS - 1) / METRIC_THREADS;
+  int64_t blocks = (n_users + METRIC_THREADS - 1) / METRIC_THREADS;
   if (blocks == 0) { cudaMemsetAsync(out_sums, 0, sizeof(double) * n_ks * METRIC_COLS, st); return PXR_OK; }
-  metrics_user_kernel<<<(unsigned)blocks, METRIC_THREADS, 0, st>>>(topk_idx, k_stride, n_users, gt_indptr, gt_idx, mk,
-                                                                   discount, ideal, (double*)ws);
-  metrics_final_kernel<<<1, 64, 0, st>>>((const double*)ws, blocks, n_ks, out_sums);
+  if (k_stride <= 64) {
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    blocks = std::min<int64_t>(blocks, (int64_t)n_sm * 16);      // never more than the workspace holds (one row per 128 users)
+    const int64_t warps = blocks * METRIC_WARPS;
+    const int64_t upw = (n_users + warps - 1) / warps;
+    metrics_warp_kernel<<<(unsigned)blocks, 32 * METRIC_WARPS, 0, st>>>(topk_idx, k_stride, n_users, upw, gt_indptr, gt_idx, mk,
+                                                                       discount, ideal, (double*)ws);
+  } else {
+    metrics_user_kernel<<<(unsigned)blocks, METRIC_THREADS, 0, st>>>(topk_idx, k_stride, n_users, gt_indptr, gt_idx, mk,
+                                                                     discount, ideal, (double*)ws);
+  }
+  metrics_final_kernel<<<n_ks * METRIC_COLS, 32, 0, st>>>((const double*)ws, blocks, n_ks, out_sums);
   return cudaGetLastError() == cudaSuccess ? PXR_OK : PXR_ERR_CUDA;
 }

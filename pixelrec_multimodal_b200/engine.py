@@ -258,25 +258,36 @@ def merge_topk(scores: torch.Tensor, idx: torch.Tensor) -> Tuple[torch.Tensor, t
 _METRIC_COLS = ("precision", "recall", "f1", "hit_rate", "ndcg", "mrr", "ndcg_list_ideal")
 
 
+_METRIC_TABLES = {}
+
+
+def _metric_tables(kstride: int, dev):
+    """discount[j] = 1/log2(j+2) and its running sums, computed with numpy / Python left-to-right adds so the device
+    results are bit-identical to the reference's numpy arithmetic (tasks.py:733-747); cached per (K, device)."""
+    key = (kstride, str(dev))
+    if key not in _METRIC_TABLES:
+        disc = np.array([1.0 / np.log2(i + 2) for i in range(kstride)], dtype=np.float64)
+        ideal = np.zeros(kstride + 1, dtype=np.float64)
+        acc = 0
+        for i in range(kstride):
+            acc = acc + disc[i]          # Python left-to-right sum, as in tasks.py:744
+            ideal[i + 1] = acc
+        _METRIC_TABLES[key] = (torch.from_numpy(disc).to(dev), torch.from_numpy(ideal).to(dev))
+    return _METRIC_TABLES[key]
+
+
 def ranking_metric_sums(topk_idx: torch.Tensor, gt_indptr: torch.Tensor, gt_idx: torch.Tensor,
-                        ks: Sequence[int]) -> np.ndarray:
-    """K5: per-cut-off sums over users, shape (len(ks), 7) float64 (host).  Column
-    order: precision, recall, f1, hit_rate, ndcg (tasks.py), mrr, ndcg (metrics.py)."""
+                        ks: Sequence[int], as_device: bool = False):
+    """K5: per-cut-off sums over users, shape (len(ks), 7) float64 (host; the device tensor, without a
+    synchronisation, when ``as_device``).  Column order: precision, recall, f1, hit_rate, ndcg (tasks.py), mrr,
+    ndcg (metrics.py)."""
     lib = _lib.load()
     dev = topk_idx.device
     topk_idx = topk_idx.to(torch.int32).contiguous()
     n, kstride = topk_idx.shape
     ks = sorted(int(k) for k in ks)
-    # numpy-computed tables so device results are bit-identical to the reference's numpy arithmetic
-    disc = np.array([1.0 / np.log2(i + 2) for i in range(kstride)], dtype=np.float64)
-    ideal = np.zeros(kstride + 1, dtype=np.float64)
-    acc = 0
-    for i in range(kstride):
-        acc = acc + disc[i]          # Python left-to-right sum, as in tasks.py:744
-        ideal[i + 1] = acc
-    d_disc = torch.from_numpy(disc).to(dev)
-    d_ideal = torch.from_numpy(ideal).to(dev)
-    out = torch.zeros((len(ks), 7), dtype=torch.float64, device=dev)
+    d_disc, d_ideal = _metric_tables(kstride, dev)
+    out = torch.empty((len(ks), 7), dtype=torch.float64, device=dev)
     nbytes = int(lib.pxr_metrics_bytes(n, len(ks)))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     ks_arr = (C.c_int32 * len(ks))(*ks)
@@ -287,4 +298,4 @@ def ranking_metric_sums(topk_idx: torch.Tensor, gt_indptr: torch.Tensor, gt_idx:
                              _ptr(d_disc), _ptr(d_ideal), _ptr(out), _ptr(ws), nbytes, _stream())
     if rc != 0:
         raise PxrError(f"pxr_metrics failed ({rc})")
-    return out.cpu().numpy()
+    return out if as_device else out.cpu().numpy()

@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Achieved HBM GB/s of the memory-bound stages next to the fused scoring kernel:
+K1+K2 item precompute, K4 S-way top-K merge, K5 ranking metrics.  Algorithmic bytes per unit are the
+§8(d) figures (stated in DESIGN.md §5); time = CUDA events around `reps` back-to-back launches after
+a warm-up, L2 flushed before each timed group.  One JSON line per stage.
+
+  python scripts/bench_stages.py [--fusion gated] [--items 96282]
+"""
+import argparse, json, sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+from pixelrec_multimodal_b200 import FastMultimodalRecommender, synthetic as syn   # noqa: E402
+from pixelrec_multimodal_b200.engine import merge_topk, ranking_metric_sums        # noqa: E402
+
+
+def timed(fn, reps, flush):
+    fn(); torch.cuda.synchronize()
+    flush.zero_(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--fusion", default="gated")
+    ap.add_argument("--items", type=int, default=96282)
+    ap.add_argument("--users", type=int, default=1 << 20)
+    args = ap.parse_args()
+    peak = json.loads((REPO / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (REPO / "MEASURED_PEAKS.json").exists() else 6650.0
+    dev = torch.device("cuda:0")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    spec = syn.ModelSpec(n_users=4096, n_items=args.items, fusion_type=args.fusion)
+    sd, feats, _ = syn.torch_workload(spec, dev, seed=1, with_histories=False)
+    m = FastMultimodalRecommender(n_users=spec.n_users, n_items=spec.n_items, n_tags=spec.n_tags, num_numerical_features=7,
+                                  embedding_dim=64, vision_model_name="cached512", language_model_name="cached384",
+                                  fusion_type=args.fusion).to(dev)
+    m.load_state_dict(sd, strict=False)
+    e = m.engine("catalogue")
+    D, Dv, Dl, F, M = 64, 512, 384, 7, 6
+    out = []
+    # ---- K1 + K2: gather + projections -> item records (the fast-path extras of the fusion type are part of the stage)
+    ms = timed(lambda: e.precompute_items(m.item_embedding.weight.detach(), feats["tag_idx"], feats["vis"], feats["txt"], feats["num"]), 3, flush)
+    extra = {"gated": 8 * 4, "concatenate": 512 * 2, "attention": 3600 * 4}[args.fusion] if e.active_path == "tcgen05" else 0
+    b_item = 4 * (2 * D + Dv + Dl + F) + 8 + 4 * (M - 1) * D + extra      # read features/embeddings/tag index + write record
+    out.append(dict(stage="K1+K2 item precompute", fusion=args.fusion, units=args.items, unit="items", ms=ms,
+                    bytes_per_unit=b_item, achieved_gbs=args.items * b_item / ms / 1e6, peak_gbs=peak))
+    # ---- K4: S-way merge of per-shard top-K lists
+    S, K, n = 8, 50, args.users // 8
+    sc = torch.rand((S, n, K), device=dev).sort(dim=2, descending=True).values
+    ix = torch.randint(0, 1 << 20, (S, n, K), device=dev, dtype=torch.int32)
+    ms = timed(lambda: merge_topk(sc, ix), 5, flush)
+    b = 8 * K * S + 8 * K
+    out.append(dict(stage="K4 top-K merge", S=S, K=K, units=n, unit="users", ms=ms, bytes_per_unit=b,
+                    achieved_gbs=n * b / ms / 1e6, peak_gbs=peak))
+    # ---- K5: ranking metrics @10 / @50 (one positive per user, leave-one-out)
+    n = args.users
+    topk = torch.randint(0, args.items, (n, K), device=dev, dtype=torch.int32)
+    gt_indptr = torch.arange(n + 1, device=dev, dtype=torch.int64)
+    gt_idx = torch.randint(0, args.items, (n,), device=dev, dtype=torch.int32)
+    ms = timed(lambda: ranking_metric_sums(topk, gt_indptr, gt_idx, [10, 50], as_device=True), 5, flush)
+    b = 4 * K + 8 + 4
+    out.append(dict(stage="K5 metrics @10/@50", K=K, units=n, unit="users", ms=ms, bytes_per_unit=b,
+                    achieved_gbs=n * b / ms / 1e6, peak_gbs=peak, note="device time of pxr_metrics (two kernels), result left on the device"))
+    for o in out:
+        o["frac"] = o["achieved_gbs"] / o["peak_gbs"]
+        print(json.dumps(o), flush=True)
+
+
+if __name__ == "__main__":
+    main()

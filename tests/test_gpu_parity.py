@@ -169,6 +169,52 @@ def test_merge_topk_with_ties():
         assert np.array_equal(gs[u].astype(np.float64), rs)
 
 
+@pytest.mark.parametrize("S,n,k", [(1, 5, 7), (3, 70, 50), (8, 300, 50), (5, 9, 64), (64, 3, 64), (2, 1, 1)])
+def test_merge_topk_shapes(S, n, k):
+    """odd / large shard counts (tree of pairwise merges), ragged list tails, K up to 64: == oracle merge"""
+    from pixelrec_multimodal_b200.engine import merge_topk
+    rng = np.random.default_rng(100 + S * n + k)
+    sc = -np.sort(-np.round(rng.standard_normal((S, n, k)), 2).astype(np.float32), axis=2)
+    ix = np.stack([np.stack([np.sort(rng.choice(5000, k, replace=False)) + 5000 * s for _ in range(n)]) for s in range(S)]).astype(np.int32)
+    for s in range(S):                        # ragged tails: list s of user u keeps k - ((s + u) % 4) * (k // 5) entries
+        for u in range(n):
+            keep = max(0, k - ((s + u) % 4) * (k // 5))
+            sc[s, u, keep:] = -np.inf; ix[s, u, keep:] = -1
+    gs, gi = merge_topk(torch.from_numpy(sc).cuda(), torch.from_numpy(ix).cuda())
+    gs, gi = gs.cpu().numpy(), gi.cpu().numpy()
+    for u in range(n):
+        lists = [(ix[s, u][ix[s, u] >= 0].astype(np.int64), sc[s, u][ix[s, u] >= 0].astype(np.float64)) for s in range(S)]
+        ri, rs = orc.merge_topk(lists, k)
+        m = len(ri)
+        assert gi[u][:m].tolist() == ri.tolist() and np.all(gi[u][m:] == -1) and np.all(np.isneginf(gs[u][m:]))
+        assert np.array_equal(gs[u][:m].astype(np.float64), rs)
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,max_pos", [(50, 80), (64, 3), (100, 40), (7, 2)])
+def test_metrics_kernel_variants(K, max_pos):
+    """lists of <= 64 entries take the warp kernel (ballot hits), longer ones the per-thread kernel; users with more
+    than 32 positives exercise the chunked positive loop.  Both == oracle to 1e-12 for several cut-offs."""
+    from pixelrec_multimodal_b200 import ranking_metrics
+    rng = np.random.default_rng(K * 7 + max_pos)
+    n, NI = 1000, 300
+    recs = np.stack([rng.permutation(NI)[:K] for _ in range(n)]).astype(np.int32)
+    recs[3, K // 2:] = -1
+    npos = rng.integers(0, max_pos + 1, n)
+    gt = [rng.choice(NI, c, replace=False) for c in npos]
+    indptr = np.concatenate([[0], np.cumsum(npos)]).astype(np.int64)
+    gt_idx = np.concatenate(gt).astype(np.int32)
+    ks = sorted({1, min(5, K), K // 2 if K // 2 else 1, K})
+    got = ranking_metrics(torch.from_numpy(recs).cuda(), indptr, gt_idx, ks)
+    for k in ks:
+        all_recs = [[int(x) for x in recs[u][:k] if x >= 0] for u in range(n)]
+        all_pos = [set(int(x) for x in g) for g in gt]
+        want = orc.retrieval_metrics(all_recs, all_pos, k)
+        for key in ("avg_precision_at_k", "avg_recall_at_k", "avg_f1_at_k", "avg_hit_rate_at_k", "avg_ndcg_at_k", "avg_mrr"):
+            assert abs(got[k][key] - want[key]) <= 1e-12, (k, key, got[k][key], want[key])
+        alt = np.mean([orc.ndcg_metrics(r, p, k) if p else 0.0 for r, p in zip(all_recs, all_pos)])
+        assert abs(got[k]["avg_ndcg_list_ideal_at_k"] - alt) <= 1e-12
+
+
 def test_sharded_equals_unsharded_single_gpu():
     """Item-axis sharding emulated on one GPU: per-shard top-K
     lists merged by pxr_merge_topk == the unsharded top-K (bit-exact)."""
