@@ -42,6 +42,7 @@ extern "C" void pxr_destroy(pxr_handle* h) {
   if (!h) return;
   if (h->arena) cudaFree(h->arena);
   if (h->fast_w) cudaFree(h->fast_w);
+  if (h->tc_items_w) cudaFree(h->tc_items_w);
   if (h->prof_ev) { for (int i = 0; i < 2 * PXR_PROFILE_SLOTS; ++i) cudaEventDestroy(h->prof_ev[i]); delete[] h->prof_ev; }
   delete h;
 }
@@ -195,6 +196,7 @@ extern "C" int pxr_load_weights(pxr_handle* h, const pxr_weights* w, pxr_stream 
     in = N;
   }
   if (h->fast_ok && (rc = pxr_tc_prepare_weights(h, st))) return rc;
+  if (h->fast_ok && (rc = pxr_items_tc_prepare_weights(h, st))) return rc;
   h->weights_loaded = true;
   h->item_feats = nullptr; h->n_rows = 0;
   return PXR_OK;
@@ -227,7 +229,10 @@ extern "C" int pxr_precompute_items(pxr_handle* h, const float* item_embedding, 
   h->item_feats = (float*)workspace; h->n_rows = n_rows; h->item_base = item_base;
   h->item_fast = (char*)workspace + feats_bytes(h, n_rows);
   if (n_rows == 0) return PXR_OK;
-  int rc = pxr_launch_items_simt(h, item_embedding, item_idx, tag_idx, vis, txt, num, n_rows, item_base, h->item_feats, st);
+  // tensor-pipe (3xTF32, fp32-accurate) item path next to the fused scoring kernel; the fp32 SIMT kernel otherwise
+  const bool items_tc = h->path == PXR_PATH_TCGEN05 && pxr_items_tc_supported(h);
+  int rc = items_tc ? pxr_launch_items_tc(h, item_embedding, item_idx, tag_idx, vis, txt, num, n_rows, item_base, h->item_feats, st)
+                    : pxr_launch_items_simt(h, item_embedding, item_idx, tag_idx, vis, txt, num, n_rows, item_base, h->item_feats, st);
   if (rc) return rc;
   if (h->fast_ok) return pxr_tc_prepare_items(h, n_rows, h->item_fast, st);
   return PXR_OK;

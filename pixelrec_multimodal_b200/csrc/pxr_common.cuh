@@ -50,6 +50,8 @@ struct pxr_handle {
   uint32_t tc_attr_set = 0;   // bit per kernel whose max-dynamic-smem attribute has been set
   void* fast_w = nullptr;     // bf16 swizzled operand images + fp32 vectors (see score_tc.cu)
   float tc_bias_host[1028];   // attention fast path: host copy of b1' b2 b3 w4 b4 (passed as kernel parameters)
+  void* tc_items_w = nullptr;       // item precompute on the tensor pipe: hi / lo tf32 weight chunk images (items_tc.cu)
+  uint8_t* tc_items_img[3] = {nullptr, nullptr, nullptr};   // vision, language projections; concat layer-1 item columns
 
   // live timing of the dominant kernel (pxr_profile_*)
   bool profile = false;
@@ -232,6 +234,13 @@ int pxr_tc_prepare_weights(pxr_handle* h, cudaStream_t st);
 size_t pxr_tc_item_bytes(const pxr_handle* h, int64_t n_rows);
 int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t st);
 size_t pxr_tc_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k);
+// tensor-pipe item precompute (items_tc.cu)
+bool pxr_items_tc_supported(const pxr_handle* h);
+int pxr_items_tc_prepare_weights(pxr_handle* h, cudaStream_t st);
+int pxr_launch_items_tc(pxr_handle* h, const float* item_embedding, const int64_t* item_idx, const int64_t* tag_idx,
+                        const float* vis, const float* txt, const float* num, int64_t n_rows, int64_t item_base,
+                        float* feats_out, cudaStream_t st);
+int pxr_launch_item_pi_tc(pxr_handle* h, int64_t n_rows, uint16_t* out, int fmt16, cudaStream_t st);
 int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
                       const int64_t* seen_indptr, const int32_t* seen_idx, int32_t k, float* out_scores,
                       int32_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t st);

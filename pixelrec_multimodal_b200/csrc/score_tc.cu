@@ -1322,6 +1322,8 @@ int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t s
   } else if (h->cfg.fusion == PXR_FUSION_ATTENTION) {
     tc::item_attn_kernel<<<(unsigned)((n_rows + 3) / 4), 256, 0, st>>>(h->item_feats, h->attn_in.wt, h->attn_in.b, h->attn_out.wt,
                                                                        h->attn_out.b, h->M, n_rows, (float*)ws);
+  } else if (h->tc_items_img[2] && h->path == PXR_PATH_TCGEN05) {
+    return pxr_launch_item_pi_tc(h, n_rows, (uint16_t*)ws, tc_fmt(h), st);      // 3xTF32 GEMM on the tensor pipe
   } else {
     const int FD = (h->M - 1) * tc::D;
     const size_t smem = (size_t)32 * (FD + tc::H1) * sizeof(float);

@@ -596,10 +596,13 @@ __global__ void __launch_bounds__(METRIC_THREADS) metrics_user_kernel(const int3
   }
 }
 
-// Fast variant for lists of at most 64 entries: one warp walks a contiguous range of users; the lanes hold the list
-// (coalesced row read), hits are found by ballot per positive, every cut-off is a popcount of the hit mask.  The
-// discounted gain is summed left to right over the hit positions, the order of the reference loop (tasks.py:733-747).
-// Per-warp partial sums live in shared memory; blocks and warps own fixed user ranges => deterministic result.
+// Fast variant for lists of at most 64 entries.  A warp owns a contiguous range of users and takes them 32 at a
+// time: the 32 lists are contiguous in memory and are staged into shared memory with fully coalesced, independent
+// loads (the algorithmic 4 K bytes per user, many loads in flight); then lane t matches user t's list against that
+// user's positives (64-bit hit / valid masks) and does the float64 arithmetic (every cut-off is a popcount of the
+// hit mask; the discounted gain is summed left to right over the hit positions, the order of the reference loop,
+// tasks.py:733-747).  Lane partial sums are reduced in a fixed order; blocks / warps own fixed user ranges
+// => deterministic result.
 #define METRIC_WARPS 4
 __global__ void __launch_bounds__(32 * METRIC_WARPS) metrics_warp_kernel(const int32_t* __restrict__ topk, int k_stride,
                                                                          int64_t n_users, int64_t users_per_warp,
@@ -609,56 +612,71 @@ __global__ void __launch_bounds__(32 * METRIC_WARPS) metrics_warp_kernel(const i
                                                                          const double* __restrict__ ideal,
                                                                          double* __restrict__ block_sums) {
   __shared__ double acc[METRIC_WARPS][PXR_MAX_KS * METRIC_COLS];
+  __shared__ int32_t lists[METRIC_WARPS][32 * 65];     // row stride k_stride | 1 (odd => conflict-free per-lane rows)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = lane; i < PXR_MAX_KS * METRIC_COLS; i += 32) acc[warp][i] = 0.0;
-  __syncwarp();
+  const int ld = k_stride | 1;
+  int32_t* L = lists[warp];
+  double sums[PXR_MAX_KS][METRIC_COLS];
+#pragma unroll
+  for (int a = 0; a < PXR_MAX_KS; ++a)
+#pragma unroll
+    for (int c = 0; c < METRIC_COLS; ++c) sums[a][c] = 0.0;
   const int64_t w = (int64_t)blockIdx.x * METRIC_WARPS + warp;
   const int64_t u0 = w * users_per_warp, u1 = min(n_users, u0 + users_per_warp);
-  for (int64_t u = u0; u < u1; ++u) {
-    const int64_t g0 = gt_indptr[u], g1 = gt_indptr[u + 1];
-    const int npos = (int)(g1 - g0);
-    if (npos <= 0) continue;                          // "if not pos_set: continue" (tasks.py:589-591): contributes zeros
-    const int32_t* rec = topk + u * k_stride;
-    const int32_t r0 = lane < k_stride ? rec[lane] : -1;
-    const int32_t r1 = lane + 32 < k_stride ? rec[lane + 32] : -1;
-    unsigned long long hit = 0ull;
-    for (int64_t g = g0; g < g1; g += 32) {           // positives, 32 at a time
-      const int32_t mine = g + lane < g1 ? gt_idx[g + lane] : -2;
-      const int cnt = (int)min((int64_t)32, g1 - g);
-      for (int t = 0; t < cnt; ++t) {
-        const int32_t pv = __shfl_sync(0xffffffffu, mine, t);
-        hit |= (unsigned long long)__ballot_sync(0xffffffffu, r0 == pv) |
-               ((unsigned long long)__ballot_sync(0xffffffffu, r1 == pv) << 32);
-      }
-    }
-    const unsigned long long valid = (unsigned long long)__ballot_sync(0xffffffffu, r0 >= 0) |
-                                     ((unsigned long long)__ballot_sync(0xffffffffu, r1 >= 0) << 32);
-    if (lane == 0) {
-      const int first = hit ? __ffsll((long long)hit) : 0;
-      double dcg = 0.0;
-      unsigned long long rest = hit;
-      for (int a = 0; a < ks.n; ++a) {
-        const int k = ks.k[a];
-        const unsigned long long km = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
-        while (rest) {                                // extend the left-to-right sum to the hits below this cut-off
-          const int j = __ffsll((long long)rest) - 1;
-          if (j >= k) break;
-          dcg += discount[j];
-          rest &= rest - 1;
+  for (int64_t ub = u0; ub < u1; ub += 32) {
+    const int nb = (int)min((int64_t)32, u1 - ub);
+    const int32_t* src = topk + ub * k_stride;
+    for (int i = lane; i < nb * k_stride; i += 32) L[(i / k_stride) * ld + (i % k_stride)] = src[i];
+    __syncwarp();
+    if (lane < nb) {
+      const int64_t g0 = gt_indptr[ub + lane], g1 = gt_indptr[ub + lane + 1];
+      const int npos = (int)(g1 - g0);
+      if (npos > 0) {                                 // "if not pos_set: continue" (tasks.py:589-591): contributes zeros
+        unsigned long long hit = 0ull, valid = 0ull;
+        const int32_t* rec = L + lane * ld;
+        for (int j = 0; j < k_stride; ++j) valid |= (unsigned long long)(rec[j] >= 0) << j;
+        for (int64_t g = g0; g < g1; ++g) {
+          const int32_t pv = gt_idx[g];
+          for (int j = 0; j < k_stride; ++j) hit |= (unsigned long long)(rec[j] == pv) << j;
         }
-        const int hits = __popcll(hit & km), nrec = __popcll(valid & km);
-        const double prec = nrec > 0 ? (double)hits / (double)nrec : 0.0;   // denominator len(recs), tasks.py:577
-        const double rec_ = (double)hits / (double)npos;
-        const double f1 = (prec + rec_) > 0.0 ? 2.0 * prec * rec_ / (prec + rec_) : 0.0;
-        const double idcg = ideal[npos < k ? npos : k];
-        double* o = acc[warp] + a * METRIC_COLS;
-        o[0] += prec; o[1] += rec_; o[2] += f1; o[3] += hits > 0 ? 1.0 : 0.0;
-        o[4] += idcg > 0.0 ? dcg / idcg : 0.0;
-        o[5] += (first && first <= k) ? 1.0 / (double)first : 0.0;
-        o[6] += hits > 0 ? dcg / ideal[hits] : 0.0;
+        const int first = hit ? __ffsll((long long)hit) : 0;
+        double dcg = 0.0;
+        unsigned long long rest = hit;
+#pragma unroll
+        for (int a = 0; a < PXR_MAX_KS; ++a) {
+          if (a < ks.n) {
+            const int k = ks.k[a];
+            const unsigned long long km = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
+            while (rest) {                            // extend the left-to-right sum to the hits below this cut-off
+              const int j = __ffsll((long long)rest) - 1;
+              if (j >= k) break;
+              dcg += discount[j];
+              rest &= rest - 1;
+            }
+            const int hits = __popcll(hit & km), nrec = __popcll(valid & km);
+            const double prec = nrec > 0 ? (double)hits / (double)nrec : 0.0;   // denominator len(recs), tasks.py:577
+            const double rec_ = (double)hits / (double)npos;
+            const double f1 = (prec + rec_) > 0.0 ? 2.0 * prec * rec_ / (prec + rec_) : 0.0;
+            const double idcg = ideal[npos < k ? npos : k];
+            sums[a][0] += prec; sums[a][1] += rec_; sums[a][2] += f1; sums[a][3] += hits > 0 ? 1.0 : 0.0;
+            sums[a][4] += idcg > 0.0 ? dcg / idcg : 0.0;
+            sums[a][5] += (first && first <= k) ? 1.0 / (double)first : 0.0;
+            sums[a][6] += hits > 0 ? dcg / ideal[hits] : 0.0;
+          }
+        }
       }
     }
+    __syncwarp();
   }
+#pragma unroll
+  for (int a = 0; a < PXR_MAX_KS; ++a)
+#pragma unroll
+    for (int c = 0; c < METRIC_COLS; ++c) {
+      double v = a < ks.n ? sums[a][c] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) acc[warp][a * METRIC_COLS + c] = v;
+    }
   __syncthreads();
   for (int i = threadIdx.x; i < PXR_MAX_KS * METRIC_COLS; i += blockDim.x) {
     double t = 0.0;
