@@ -185,6 +185,26 @@ int pxr_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, cons
                 const double* ideal, double* out_sums, void* workspace, size_t workspace_bytes,
                 pxr_stream stream);
 
+/* Sampled evaluation protocol, candidate construction.  Replaces
+ * TopKRetrievalEvaluator._process_user / _sample_negatives with sampling_strategy 'random'
+ * (src/evaluation/tasks.py:181-224, 310-364): per user, the positives plus n_neg negatives drawn uniformly
+ * without replacement from the non-positive items, in a shuffled order.  Every draw is a pure function of
+ * (seed, global user index): a keyed Feistel permutation of [0, n_items) for the negatives, a 64-bit hash order
+ * for the shuffle (the reference seeds with Python's per-process salted hash() and is not reproducible).
+ *   user_idx   : (n_users,) int64 global user indices (NULL = 0..n_users-1), only used as sampling keys
+ *   pos_indptr : (n_users+1,) int64 ;  pos_idx : int32 positives, ASCENDING inside each user
+ *   stride     : row length of out_cand (<= 1024); positives beyond it are dropped, negatives fill what is left
+ *   out_cand   : (n_users, stride) int32 candidate item indices, -1 padded ;  out_len : (n_users,) int32 */
+int pxr_sample_candidates(const int64_t* user_idx, int64_t n_users, const int64_t* pos_indptr, const int32_t* pos_idx,
+                          int64_t n_items, int32_t n_neg, uint64_t seed, int32_t stride, int32_t* out_cand,
+                          int32_t* out_len, pxr_stream stream);
+
+/* K3t on its own: exact top-K of every row of a dense score matrix; -inf entries are masked; ties -> lower
+ * column.  Used to rank candidate lists (stable sort of src/inference/recommender.py:105 over the candidate order).
+ *   scores : (n_rows, n_cols) fp32 ;  out_scores / out_pos : (n_rows, K), padded with -inf / -1 */
+int pxr_topk_rows(pxr_handle* h, const float* scores, int64_t n_rows, int64_t n_cols, int32_t k, float* out_scores,
+                  int32_t* out_pos, pxr_stream stream);
+
 /* Live timing of the dominant kernel (the pair-scoring kernel of
  * pxr_score_topk) with CUDA events recorded on the launching stream, for the
  * roofline line of bench.py.  pxr_profile_read synchronises on the recorded

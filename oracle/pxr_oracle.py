@@ -434,3 +434,70 @@ def forward_pairs_lowp(sd, cfg, user_idx, item_idx, tag_idx, vis=None, txt=None,
     if return_logit:
         return z
     return final_activation(z, cfg.get("final_activation", "sigmoid"))
+
+
+# --------------------------------------------------------------------------
+# sampled evaluation protocol: candidate construction
+# --------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def mix64(z: int) -> int:
+    """splitmix64 step (Python ints, 64-bit wrap-around)."""
+    z = (z + 0x9E3779B97F4A7C15) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def _feistel_perm(ku: int, n_items: int):
+    bits = 1
+    while (1 << bits) < n_items:
+        bits += 1
+    h = (bits + 1) >> 1
+    mask = (1 << h) - 1
+    rk = [mix64((ku + r) & _M64) >> 32 for r in range(4)]
+
+    def at(j: int) -> int:
+        x = j
+        while True:
+            L, R = x >> h, x & mask
+            for r in range(4):
+                f = mix64((rk[r] << 32) | R) & 0xFFFFFFFF & mask
+                L, R = R, L ^ f
+            x = (L << h) | R
+            if x < n_items:
+                return x
+    return at
+
+
+def sample_candidates(global_user: int, positives: Sequence[int], n_items: int, n_neg: int, seed: int,
+                      stride: int = 1024) -> List[int]:
+    """Candidate list of one user for the sampled protocol (reference
+    src/evaluation/tasks.py:181-224 'random' strategy + the shuffle of :336-342),
+    with the reference's unreproducible salted-hash seeding replaced by a pure
+    function of (seed, global user index): negatives = the first n_neg images of a
+    keyed Feistel permutation of range(n_items) that are not positives (uniform,
+    without replacement); final order = ascending 64-bit hash of (user key, item),
+    ties -> lower item.  Pure-Python restatement of csrc/sampling.cu."""
+    pos = sorted(int(p) for p in positives)[:stride]
+    posset = set(int(p) for p in positives)
+    ku = mix64((seed & _M64) ^ mix64(global_user & _M64))
+    want = max(0, min(n_neg, stride - len(pos), n_items - len(posset)))
+    at = _feistel_perm(ku, n_items)
+    negs, j = [], 0
+    while len(negs) < want:
+        x = at(j)
+        j += 1
+        if x not in posset:
+            negs.append(x)
+    cand = pos + negs
+    key = lambda it: (mix64(ku ^ 0xD1B54A32D192ED03 ^ ((it & 0xFFFFFFFF) << 1)), it)
+    return sorted(cand, key=key)
+
+
+def rank_candidates(scores: Sequence[float], candidates: Sequence[int], k: int) -> List[int]:
+    """Stable descending sort over the candidate order, first k
+    (src/inference/recommender.py:97-106 with candidates=...)."""
+    order = sorted(range(len(candidates)), key=lambda i: -scores[i])      # Python's sort is stable
+    return [int(candidates[i]) for i in order[:k]]

@@ -235,6 +235,19 @@ class PxrEngine:
                                                  _ptr(out), _ptr(logit), _stream()), "pxr_score_pairs")
         return (out, logit) if want_logit else out
 
+    def topk_rows(self, scores: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Exact top-K of every row of a dense (n_rows, n_cols) fp32 score matrix (-inf = masked, ties -> lower
+        column): (scores, column positions), padded with -inf / -1."""
+        dev = self.device
+        scores = scores.to(device=dev, dtype=torch.float32).contiguous()
+        n, c = scores.shape
+        out_s = torch.empty((n, k), dtype=torch.float32, device=dev)
+        out_p = torch.empty((n, k), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            self._check(self.lib.pxr_topk_rows(self._h, _ptr(scores), n, c, k, _ptr(out_s), _ptr(out_p), _stream()),
+                        "pxr_topk_rows")
+        return out_s, out_p
+
     # ---------------------------------------------------------------- merges
     def merge_topk(self, scores: torch.Tensor, idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """(S, n_users, K) per-shard lists -> (n_users, K); ties -> lower global index."""
@@ -256,6 +269,31 @@ def merge_topk(scores: torch.Tensor, idx: torch.Tensor) -> Tuple[torch.Tensor, t
 
 
 _METRIC_COLS = ("precision", "recall", "f1", "hit_rate", "ndcg", "mrr", "ndcg_list_ideal")
+
+
+def sample_candidates(user_idx: torch.Tensor, pos_indptr: torch.Tensor, pos_idx: torch.Tensor, n_items: int,
+                      n_neg: int, seed: int, stride: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Candidate lists of the sampled protocol (pxr_sample_candidates): per user the positives
+    (``pos_idx`` ascending inside each user) plus ``n_neg`` uniformly sampled negatives, shuffled;
+    returns ((n_users, stride) int32 item indices, -1 padded, (n_users,) int32 lengths)."""
+    lib = _lib.load()
+    dev = pos_idx.device
+    n = int(pos_indptr.shape[0]) - 1
+    pos_indptr = pos_indptr.to(device=dev, dtype=torch.int64).contiguous()
+    pos_idx = pos_idx.to(device=dev, dtype=torch.int32).contiguous()
+    if stride is None:
+        max_pos = int((pos_indptr[1:] - pos_indptr[:-1]).max().item()) if n else 0
+        stride = max(1, min(1024, max_pos + int(n_neg)))
+    uidx = user_idx.to(device=dev, dtype=torch.int64).contiguous() if user_idx is not None else None
+    cand = torch.empty((n, stride), dtype=torch.int32, device=dev)
+    length = torch.empty((n,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.pxr_sample_candidates(_ptr(uidx), n, _ptr(pos_indptr), _ptr(pos_idx), int(n_items), int(n_neg),
+                                       C.c_uint64(int(seed) & ((1 << 64) - 1)), int(stride), _ptr(cand), _ptr(length),
+                                       _stream())
+    if rc != 0:
+        raise PxrError(f"pxr_sample_candidates failed ({rc})")
+    return cand, length
 
 
 _METRIC_TABLES = {}

@@ -15,7 +15,7 @@ from typing import Dict, Optional, Sequence
 import numpy as np
 import torch
 
-from .engine import ranking_metric_sums
+from .engine import ranking_metric_sums, sample_candidates
 
 _COLS = ("avg_precision_at_k", "avg_recall_at_k", "avg_f1_at_k", "avg_hit_rate_at_k", "avg_ndcg_at_k", "avg_mrr",
          "avg_ndcg_list_ideal_at_k")
@@ -79,4 +79,64 @@ class FullCatalogueEvaluator:
             s, i = scores.cpu().numpy(), idx.cpu().numpy()
             res["predictions"] = {str(r.user_ids[int(u)]): [(str(r.item_ids[int(b)]), float(a)) for a, b in zip(s[j], i[j]) if b >= 0]
                                   for j, u in enumerate(self.users)}
+        return res
+
+
+class SampledRetrievalEvaluator(FullCatalogueEvaluator):
+    """The reference's default protocol (``scripts/evaluate.py --use_sampling``,
+    ``TopKRetrievalEvaluator`` with ``sampling_strategy='random'``, ``src/evaluation/tasks.py:181-224,
+    310-364``) on the GPU: per user the test positives plus ``num_negatives`` uniformly sampled non-positive
+    items form a shuffled candidate list (``pxr_sample_candidates``), the recommender ranks exactly those
+    (``filter_seen=False``), and the accuracy block of ``evaluate`` (:567-635) is computed on the top-K lists.
+    Sampling is a pure function of ``(seed, user index)``; the reference seeds with Python's salted ``hash()`` and is
+    not reproducible across processes.  The 'popularity' strategies are not implemented on this path."""
+
+    def __init__(self, recommender, test_data, top_k: int = 50, ks: Optional[Sequence[int]] = None,
+                 num_negatives: int = 100, sampling_strategy: str = "random", seed: int = 20261018,
+                 keep_predictions: bool = False, num_workers: int = 0, user_block: int = 65536):
+        if sampling_strategy != "random":
+            raise ValueError("only sampling_strategy='random' is implemented on the GPU path")
+        super().__init__(recommender, test_data, top_k=top_k, ks=ks, filter_seen=False,
+                         keep_predictions=keep_predictions, num_workers=num_workers)
+        self.num_negatives = int(num_negatives)
+        self.seed = int(seed)
+        self.user_block = int(user_block)
+
+    def candidates(self, lo: int = 0, hi: Optional[int] = None):
+        """(n, stride) int32 candidate item indices (device) of evaluated users [lo, hi)."""
+        r = self.recommender
+        hi = len(self.users) if hi is None else hi
+        dev = r.device
+        indptr = torch.from_numpy(self.gt_indptr[lo:hi + 1] - self.gt_indptr[lo]).to(dev)
+        idx = torch.from_numpy(self.gt_idx[self.gt_indptr[lo]:self.gt_indptr[hi]]).to(dev)
+        max_pos = int(np.diff(self.gt_indptr).max()) if len(self.users) else 0
+        stride = max(1, min(1024, max_pos + self.num_negatives))
+        return sample_candidates(torch.from_numpy(self.users[lo:hi]).to(dev), indptr, idx, r.n_items, self.num_negatives,
+                                 self.seed, stride)
+
+    def evaluate(self) -> Dict:
+        r = self.recommender
+        kmax = max(self.ks)
+        sums = np.zeros((len(self.ks), 7))
+        preds = {}
+        for lo in range(0, len(self.users), self.user_block):
+            hi = min(len(self.users), lo + self.user_block)
+            cand, _ = self.candidates(lo, hi)
+            s, items = r.rank_candidates(self.users[lo:hi], cand, top_k=kmax)
+            sums += ranking_metric_sums(items, torch.from_numpy(self.gt_indptr[lo:hi + 1] - self.gt_indptr[lo]),
+                                        torch.from_numpy(self.gt_idx[self.gt_indptr[lo]:self.gt_indptr[hi]]), self.ks)
+            if self.keep_predictions:
+                hs, hi_ = s.cpu().numpy(), items.cpu().numpy()
+                for j, u in enumerate(self.users[lo:hi]):
+                    preds[str(r.user_ids[int(u)])] = [(str(r.item_ids[int(b)]), float(a)) for a, b in zip(hs[j], hi_[j]) if b >= 0]
+        n = len(self.users)
+        by_k = {}
+        for row, k in zip(sums, self.ks):
+            by_k[k] = {c: (float(v) / n if n else 0.0) for c, v in zip(_COLS, row)}
+            by_k[k]["num_users_evaluated"] = n
+        res = {k: v for k, v in by_k[self.top_k].items() if k != "avg_ndcg_list_ideal_at_k"}
+        res["evaluation_method"] = "negative_sampling"
+        res["by_k"] = by_k
+        if self.keep_predictions:
+            res["predictions"] = preds
         return res

@@ -245,6 +245,29 @@ class FastRecommender:
                     torch.empty((0, top_k), dtype=torch.int32, device=self.device))
         return torch.cat(outs_s), torch.cat(outs_i)
 
+    @torch.no_grad()
+    def rank_candidates(self, user_indices, candidates: torch.Tensor, top_k: int = 10
+                        ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Batched ``get_recommendations(candidates=..., filter_seen=False)`` (reference
+        src/inference/recommender.py:81-106): row r of ``candidates`` ((n, C) int32 item indices, -1 padded) is
+        ranked for user ``user_indices[r]`` -- stable descending order over the candidate order, first ``top_k``.
+        Returns device tensors (scores (n, K), item indices (n, K) int32, -inf / -1 padded)."""
+        eng = self.engine()
+        if self.item_lo != 0 or self.item_hi != self.n_items:
+            raise ValueError("rank_candidates needs the whole catalogue on this recommender (no item-axis shard)")
+        users = torch.as_tensor(user_indices, dtype=torch.int64, device=self.device)
+        cand = candidates.to(device=self.device, dtype=torch.int32)
+        n, C_ = cand.shape
+        valid = cand >= 0
+        rows, cols = valid.nonzero(as_tuple=True)
+        scores = torch.full((n, C_), float("-inf"), dtype=torch.float32, device=self.device)
+        if rows.numel():
+            sc = eng.score_pairs(self.model.user_embedding.weight.detach(), users[rows], cand[rows, cols].to(torch.int64))
+            scores[rows, cols] = sc
+        s, pos = eng.topk_rows(scores, top_k)
+        items = torch.where(pos >= 0, torch.gather(cand, 1, pos.clamp_min(0).to(torch.int64)), torch.full_like(pos, -1))
+        return s, items
+
     # --------------------------------------------------------- reference API
     def get_recommendations(self, user_id: str, top_k: int = 10, filter_seen: bool = True,
                             candidates: Optional[List[str]] = None) -> List[Tuple[str, float]]:
