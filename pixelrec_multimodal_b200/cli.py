@@ -1,0 +1,224 @@
+"""Command-line front ends of the GPU path: the work of the reference's
+``scripts/generate_recommendations.py`` and ``scripts/evaluate.py`` for the multimodal recommender, with the
+same flags and the same JSON outputs, on top of a packed feature cache and CSV interaction tables.
+
+  python -m pixelrec_multimodal_b200.cli generate --config C.yaml --checkpoint M.pth --cache DIR \\
+         --interactions train.csv [--users u1 u2 | --user_file F | --sample_users N | --all_users] --output recs.json
+  python -m pixelrec_multimodal_b200.cli evaluate --config C.yaml --checkpoint M.pth --cache DIR \\
+         --interactions train.csv --test_data test.csv [--use_sampling --num_negatives 100] --output results.json
+
+What replaces what: the encoders are the sorted unique ids of the interaction table and of the cache (the order
+sklearn's ``LabelEncoder`` gives, ``dataset.py:142-148``), built once; user histories are one CSR built once
+(the reference masks the whole interaction frame per user, ``dataset.py:462-476``); item features come from the
+packed cache in a few large copies.  ``--all_users`` and ``evaluate`` use the batched API; the per-user flags go
+through ``get_recommendations`` exactly like the reference script (``generate_recommendations.py:196-226``).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+
+# ----------------------------------------------------------------------------- configuration
+def load_config(path: Optional[str]) -> Dict:
+    """The subset of the reference YAML (``src/config.py``) this path reads; defaults as in ``config.py:41-62,512-519``."""
+    cfg = {"model": {}, "recommendation": {}, "data": {}}
+    if path:
+        import yaml
+        loaded = yaml.safe_load(Path(path).read_text()) or {}
+        for k in cfg:
+            cfg[k].update(loaded.get(k) or {})
+        cfg["results_dir"] = loaded.get("results_dir", "results")
+    m = cfg["model"]
+    m.setdefault("embedding_dim", 64)
+    m.setdefault("fusion_hidden_dims", [512, 256, 128])
+    m.setdefault("fusion_activation", "relu")
+    m.setdefault("use_batch_norm", True)
+    m.setdefault("projection_hidden_dim", None)
+    m.setdefault("final_activation", "sigmoid")
+    m.setdefault("fusion_type", "concatenate")
+    m.setdefault("num_attention_heads", 4)
+    r = cfg["recommendation"]
+    r.setdefault("top_k", 50)
+    r.setdefault("filter_seen", True)
+    cfg.setdefault("results_dir", "results")
+    return cfg
+
+
+class TableDataset:
+    """The attributes the recommender reads on its dataset (``recommender.py:58-90, 239-269``): encoders with
+    ``classes_``, the interaction frame, and a ``feature_cache`` with ``get(item_id)``."""
+
+    class _Encoder:
+        def __init__(self, classes):
+            self.classes_ = np.asarray(classes, dtype=object)
+
+    def __init__(self, interactions, cache):
+        users = np.sort(interactions["user_id"].astype(str).unique())
+        self.user_encoder = self._Encoder(users)
+        self.item_encoder = self._Encoder(sorted(cache.item_ids))
+        self.interactions = interactions
+        self.feature_cache = cache
+
+
+def build_recommender(cfg: Dict, checkpoint: Optional[str], cache_dir: str, interactions_csv: str, device: str = "cuda:0",
+                      n_tags: Optional[int] = None):
+    import pandas as pd
+    import torch
+    from . import FastMultimodalRecommender, FastRecommender
+    from .packed_cache import PackedFeatureCache
+    cache = PackedFeatureCache(cache_dir)
+    inter = pd.read_csv(interactions_csv, dtype={"user_id": str, "item_id": str})
+    ds = TableDataset(inter, cache)
+    m = cfg["model"]
+    sd = None
+    if checkpoint:
+        ck = torch.load(checkpoint, map_location="cpu", weights_only=False)
+        sd = ck["model_state_dict"] if isinstance(ck, dict) and "model_state_dict" in ck else ck
+    if n_tags is None:
+        n_tags = int(sd["tag_embedding.weight"].shape[0]) if sd is not None else int(np.max(cache.tag)) + 1
+    n_users = int(sd["user_embedding.weight"].shape[0]) if sd is not None else len(ds.user_encoder.classes_)
+    model = FastMultimodalRecommender(
+        n_users=n_users, n_items=len(ds.item_encoder.classes_), n_tags=n_tags,
+        num_numerical_features=cache.meta["num_numerical"], embedding_dim=m["embedding_dim"],
+        vision_model_name=f"cached{cache.meta['vision_dim']}" if cache.meta["vision_dim"] else None,
+        language_model_name=f"cached{cache.meta['language_dim']}" if cache.meta["language_dim"] else None,
+        use_contrastive=False, num_attention_heads=m["num_attention_heads"], fusion_hidden_dims=list(m["fusion_hidden_dims"]),
+        fusion_activation=m["fusion_activation"], use_batch_norm=m["use_batch_norm"],
+        projection_hidden_dim=m["projection_hidden_dim"], final_activation=m["final_activation"], fusion_type=m["fusion_type"])
+    if sd is not None:
+        model.load_state_dict(sd, strict=False)
+    dev = torch.device(device)
+    store = cache.to_store(dev, order=[str(i) for i in ds.item_encoder.classes_])
+    rec = FastRecommender(model, ds, dev, item_features=store)
+    return rec, ds
+
+
+# ----------------------------------------------------------------------------- generate
+def select_users(args, all_users: Sequence[str]) -> List[str]:
+    """``generate_recommendations.py:271-287``."""
+    if args.users:
+        return list(args.users)
+    if args.user_file:
+        return [ln.strip() for ln in Path(args.user_file).read_text().splitlines() if ln.strip()]
+    if args.sample_users:
+        import pandas as pd
+        if len(all_users) < args.sample_users:
+            return [str(u) for u in all_users]
+        return pd.Series(list(all_users)).sample(n=args.sample_users, random_state=42).tolist()
+    if getattr(args, "all_users", False):
+        return [str(u) for u in all_users]
+    return [str(u) for u in all_users[:5]]
+
+
+def format_results(user_ids: Sequence[str], recs_per_user) -> Dict:
+    """JSON shape of ``generate_recommendations.py:221-226``."""
+    return {str(u): {"recommendations": [{"item_id": str(i), "score": float(s)} for i, s in recs]}
+            for u, recs in zip(user_ids, recs_per_user)}
+
+
+def cmd_generate(args) -> Dict:
+    cfg = load_config(args.config)
+    top_k = args.top_k or cfg["recommendation"]["top_k"]
+    filter_seen = cfg["recommendation"]["filter_seen"] and not args.no_filter_seen
+    rec, ds = build_recommender(cfg, args.checkpoint, args.cache, args.interactions, args.device)
+    users = select_users(args, ds.user_encoder.classes_)
+    if args.all_users or len(users) > 256:
+        known = [u for u in users if u in rec.user_index]
+        idx = np.fromiter((rec.user_index[u] for u in known), dtype=np.int64, count=len(known))
+        s, i = rec.recommend_all(idx, top_k=top_k, filter_seen=filter_seen)
+        s, i = s.cpu().numpy(), i.cpu().numpy()
+        per_user = {u: [(rec.item_ids[int(b)], float(a)) for a, b in zip(s[r], i[r]) if b >= 0] for r, u in enumerate(known)}
+        lists = [per_user.get(u, []) for u in users]
+    else:
+        lists = [rec.get_recommendations(u, top_k=top_k, filter_seen=filter_seen) for u in users]
+    results = format_results(users, lists)
+    out = Path(cfg["results_dir"]) / args.output if not Path(args.output).is_absolute() else Path(args.output)
+    out.parent.mkdir(parents=True, exist_ok=True)
+    out.write_text(json.dumps(results, indent=2))
+    print(f"Saved recommendations for {len(users)} users to {out}")
+    return results
+
+
+# ----------------------------------------------------------------------------- evaluate
+def cmd_evaluate(args) -> Dict:
+    import pandas as pd
+    from . import FullCatalogueEvaluator, SampledRetrievalEvaluator
+    cfg = load_config(args.config)
+    top_k = args.top_k or cfg["recommendation"]["top_k"]
+    rec, ds = build_recommender(cfg, args.checkpoint, args.cache, args.interactions, args.device)
+    test = pd.read_csv(args.test_data, dtype={"user_id": str, "item_id": str})
+    ks = sorted(set([top_k] + [int(k) for k in (args.ks or [])]))
+    if args.use_sampling:
+        ev = SampledRetrievalEvaluator(rec, test, top_k=top_k, ks=ks, num_negatives=args.num_negatives,
+                                       sampling_strategy=args.sampling_strategy, seed=args.seed,
+                                       keep_predictions=bool(args.save_predictions))
+    else:
+        ev = FullCatalogueEvaluator(rec, test, top_k=top_k, ks=ks, filter_seen=cfg["recommendation"]["filter_seen"],
+                                    keep_predictions=bool(args.save_predictions))
+    results = ev.evaluate()
+    results_dir = Path(cfg["results_dir"])
+    if args.save_predictions and "predictions" in results:          # evaluate.py:417-426
+        preds = results.pop("predictions")
+        p = results_dir / args.save_predictions
+        p.parent.mkdir(parents=True, exist_ok=True)
+        p.write_text(json.dumps({str(u): [{"item_id": str(i), "score": float(s)} for i, s in r] for u, r in preds.items()}, indent=2))
+    results["evaluation_metadata"] = {"task": "retrieval", "recommender_type": "fast_multimodal", "top_k": top_k,      # evaluate.py:429-434
+                                      "test_file": args.test_data, "checkpoint_used": args.checkpoint}
+    results["by_k"] = {str(k): v for k, v in results["by_k"].items()}
+    out = results_dir / args.output if not Path(args.output).is_absolute() else Path(args.output)
+    out.parent.mkdir(parents=True, exist_ok=True)
+    out.write_text(json.dumps(results, indent=2))
+    print(json.dumps({k: v for k, v in results.items() if k.startswith("avg_") or k == "num_users_evaluated"}, indent=1))
+    print(f"Evaluation results saved to {out}")
+    return results
+
+
+def make_parser() -> argparse.ArgumentParser:
+    ap = argparse.ArgumentParser(prog="pixelrec_multimodal_b200.cli", description=__doc__.split("\n")[0])
+    sub = ap.add_subparsers(dest="cmd", required=True)
+
+    def common(p):
+        p.add_argument("--config", type=str, default=None, help="reference-style YAML (model / recommendation sections)")
+        p.add_argument("--checkpoint", type=str, default=None, help="reference checkpoint (.pth with model_state_dict)")
+        p.add_argument("--cache", type=str, required=True, help="packed feature cache directory (packed_cache.py)")
+        p.add_argument("--interactions", type=str, required=True, help="train interactions CSV (user_id, item_id): histories / encoders")
+        p.add_argument("--device", type=str, default="cuda:0")
+        p.add_argument("--top_k", type=int, default=None)
+
+    g = sub.add_parser("generate", help="scripts/generate_recommendations.py on the GPU path")
+    common(g)
+    g.add_argument("--users", type=str, nargs="+")
+    g.add_argument("--user_file", type=str)
+    g.add_argument("--sample_users", type=int)
+    g.add_argument("--all_users", action="store_true", help="every user of the interaction table (batched API)")
+    g.add_argument("--no_filter_seen", action="store_true")
+    g.add_argument("--output", type=str, default="recommendations.json")
+    g.set_defaults(fn=cmd_generate)
+
+    e = sub.add_parser("evaluate", help="scripts/evaluate.py (retrieval task) on the GPU path")
+    common(e)
+    e.add_argument("--test_data", type=str, required=True)
+    e.add_argument("--use_sampling", action="store_true", help="positives + sampled negatives (the reference default protocol)")
+    e.add_argument("--num_negatives", type=int, default=100)
+    e.add_argument("--sampling_strategy", type=str, default="random")
+    e.add_argument("--seed", type=int, default=20261018)
+    e.add_argument("--ks", type=int, nargs="*", help="extra cut-offs reported under by_k")
+    e.add_argument("--save_predictions", type=str, default=None)
+    e.add_argument("--output", type=str, default="evaluation_results.json")
+    e.set_defaults(fn=cmd_evaluate)
+    return ap
+
+
+def main(argv: Optional[Sequence[str]] = None):
+    args = make_parser().parse_args(argv)
+    return args.fn(args)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

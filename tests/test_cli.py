@@ -1,0 +1,86 @@
+"""CLI front ends.  CPU: argument surface, config defaults, user selection and JSON shape
+(reference scripts/generate_recommendations.py:221-226, 271-287).  GPU: both commands end to end on a tiny
+synthetic catalogue, equal to the Python API."""
+import json
+import types
+
+import numpy as np
+import pytest
+
+from pixelrec_multimodal_b200 import cli, synthetic as syn
+
+
+def test_parser_mirrors_reference_flags():
+    p = cli.make_parser()
+    a = p.parse_args(["generate", "--cache", "c", "--interactions", "i.csv", "--users", "u1", "u2", "--output", "o.json"])
+    assert a.users == ["u1", "u2"] and a.output == "o.json" and a.sample_users is None and a.user_file is None
+    a = p.parse_args(["evaluate", "--cache", "c", "--interactions", "i.csv", "--test_data", "t.csv", "--use_sampling"])
+    assert a.use_sampling and a.num_negatives == 100 and a.sampling_strategy == "random" and a.output == "evaluation_results.json"
+    with pytest.raises(SystemExit):
+        p.parse_args(["evaluate", "--cache", "c", "--interactions", "i.csv"])          # --test_data is required
+
+
+def test_config_defaults_and_yaml(tmp_path):
+    c = cli.load_config(None)
+    assert c["model"]["fusion_hidden_dims"] == [512, 256, 128] and c["recommendation"]["top_k"] == 50 and c["results_dir"] == "results"
+    y = tmp_path / "c.yaml"
+    y.write_text("model:\n  fusion_type: gated\n  embedding_dim: 64\nrecommendation:\n  top_k: 7\nresults_dir: out\n")
+    c = cli.load_config(str(y))
+    assert c["model"]["fusion_type"] == "gated" and c["recommendation"]["top_k"] == 7 and c["results_dir"] == "out"
+    assert c["recommendation"]["filter_seen"] is True and c["model"]["final_activation"] == "sigmoid"
+
+
+def test_user_selection_and_json_shape(tmp_path):
+    allu = [f"u{i}" for i in range(20)]
+    ns = lambda **k: types.SimpleNamespace(**{"users": None, "user_file": None, "sample_users": None, "all_users": False, **k})
+    assert cli.select_users(ns(), allu) == allu[:5]                                   # default: first five
+    assert cli.select_users(ns(users=["x"]), allu) == ["x"]
+    f = tmp_path / "u.txt"; f.write_text("u3\n\nu9\n")
+    assert cli.select_users(ns(user_file=str(f)), allu) == ["u3", "u9"]
+    s = cli.select_users(ns(sample_users=4), allu)
+    assert len(s) == 4 and s == cli.select_users(ns(sample_users=4), allu)            # random_state=42
+    assert cli.select_users(ns(sample_users=50), allu) == allu
+    assert cli.select_users(ns(all_users=True), allu) == allu
+    out = cli.format_results(["u1"], [[("i5", np.float32(0.25)), ("i2", 0.125)]])
+    assert out == {"u1": {"recommendations": [{"item_id": "i5", "score": 0.25}, {"item_id": "i2", "score": 0.125}]}}
+    json.dumps(out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fusion", ["gated", "attention"])
+def test_cli_end_to_end(tmp_path, fusion):
+    import pandas as pd
+    import torch
+    from pixelrec_multimodal_b200.packed_cache import write_packed_cache
+    from tests import _cases as cs
+    spec = syn.ModelSpec(n_users=60, n_items=300, fusion_type=fusion)
+    sd, feats = cs.make_workload(spec, syn.SEED + 41)
+    uids, iids = syn.user_ids(spec.n_users), syn.item_ids(spec.n_items)
+    write_packed_cache(tmp_path / "cache", iids, feats["tag_idx"], feats["vis"], feats["txt"], feats["num"])
+    indptr, idx, test_item = syn.make_histories(spec.n_users, spec.n_items, seed=3, lo=3, hi=20)
+    rows = [(uids[u], iids[int(i)]) for u in range(spec.n_users) for i in idx[indptr[u]:indptr[u + 1]]]
+    pd.DataFrame(rows, columns=["user_id", "item_id"]).to_csv(tmp_path / "train.csv", index=False)
+    pd.DataFrame([(uids[u], iids[int(test_item[u])]) for u in range(spec.n_users)], columns=["user_id", "item_id"]).to_csv(tmp_path / "test.csv", index=False)
+    torch.save({"model_state_dict": {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}}, tmp_path / "m.pth")
+    (tmp_path / "c.yaml").write_text(f"model:\n  fusion_type: {fusion}\nrecommendation:\n  top_k: 10\nresults_dir: {tmp_path / 'res'}\n")
+    common = ["--config", str(tmp_path / "c.yaml"), "--checkpoint", str(tmp_path / "m.pth"), "--cache", str(tmp_path / "cache"),
+              "--interactions", str(tmp_path / "train.csv")]
+    res = cli.main(["generate", *common, "--users", uids[3], uids[7], "ghost", "--output", "r.json"])
+    disk = json.loads((tmp_path / "res" / "r.json").read_text())
+    assert disk == res and list(disk) == [uids[3], uids[7], "ghost"] and disk["ghost"]["recommendations"] == []
+    assert len(disk[uids[3]]["recommendations"]) == 10
+    seen = {iids[int(i)] for i in idx[indptr[3]:indptr[4]]}
+    assert not seen & {r["item_id"] for r in disk[uids[3]]["recommendations"]}
+    allr = cli.main(["generate", *common, "--all_users", "--output", "all.json"])
+    assert len(allr) == spec.n_users
+    for u in (uids[3], uids[7]):                                                     # batched == per-user string API
+        assert [r["item_id"] for r in allr[u]["recommendations"]] == [r["item_id"] for r in disk[u]["recommendations"]]
+    ev = cli.main(["evaluate", *common, "--test_data", str(tmp_path / "test.csv"), "--ks", "5", "--output", "e.json"])
+    assert ev["evaluation_method"] == "full_evaluation" and ev["num_users_evaluated"] == spec.n_users
+    assert set(ev["by_k"]) == {"5", "10"} and 0.0 <= ev["avg_recall_at_k"] <= 1.0
+    hits = np.mean([iids[int(test_item[u])] in [r["item_id"] for r in allr[uids[u]]["recommendations"]] for u in range(spec.n_users)])
+    assert abs(ev["avg_hit_rate_at_k"] - hits) <= 1e-12                               # evaluator == lists written by generate
+    es = cli.main(["evaluate", *common, "--test_data", str(tmp_path / "test.csv"), "--use_sampling", "--output", "s.json",
+                   "--save_predictions", "p.json"])
+    assert es["evaluation_method"] == "negative_sampling" and (tmp_path / "res" / "p.json").exists()
+    assert es["avg_hit_rate_at_k"] >= ev["avg_hit_rate_at_k"]                         # 101 candidates instead of 300
