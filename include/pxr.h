@@ -135,6 +135,12 @@ int pxr_precompute_items(pxr_handle* h, const float* item_embedding, const int64
                          int64_t n_rows, int64_t item_base, void* workspace, size_t workspace_bytes,
                          pxr_stream stream);
 
+/* Items whose features could not be fetched.  The reference scores them 0.0 instead of running the model
+ * (src/inference/recommender.py:199-201, 229-230: `final_scores_map.get(original_id, 0.0)`), and they take part in
+ * the ranking with that score.  flags: (n_rows,) uint8 DEVICE array aligned with the precomputed rows, 1 = missing;
+ * caller-owned, must outlive the scoring calls; NULL clears.  Call after pxr_precompute_items (which clears it). */
+int pxr_set_missing_items(pxr_handle* h, const uint8_t* flags, int64_t n_rows);
+
 /* K3 (+ in-kernel top-K).  Replaces Recommender.get_recommendations with
  * candidates=None for a batch of users (src/inference/recommender.py:52-110):
  * every user of the batch against every precomputed item row, seen items

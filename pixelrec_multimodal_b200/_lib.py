@@ -53,6 +53,7 @@ _SIGNATURES = {
     "pxr_items_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
     "pxr_precompute_items": (C.c_int, [C.c_void_p, _F, _F, _F, _F, _F, _F, C.c_int64, C.c_int64, _F, C.c_size_t,
                                        C.c_void_p]),
+    "pxr_set_missing_items": (C.c_int, [C.c_void_p, _F, C.c_int64]),
     "pxr_score_topk_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int32]),
     "pxr_score_topk": (C.c_int, [C.c_void_p, _F, _F, C.c_int64, _F, _F, C.c_int32, _F, _F, _F, C.c_size_t,
                                  C.c_void_p]),

@@ -227,6 +227,7 @@ extern "C" int pxr_precompute_items(pxr_handle* h, const float* item_embedding, 
   if (((uintptr_t)workspace) & 255) PXR_FAIL(h, PXR_ERR_INVALID, "item workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   h->item_feats = (float*)workspace; h->n_rows = n_rows; h->item_base = item_base;
+  h->item_missing = nullptr;
   h->item_fast = (char*)workspace + feats_bytes(h, n_rows);
   if (n_rows == 0) return PXR_OK;
   // tensor-pipe (3xTF32, fp32-accurate) item path next to the fused scoring kernel; the fp32 SIMT kernel otherwise
@@ -235,6 +236,13 @@ extern "C" int pxr_precompute_items(pxr_handle* h, const float* item_embedding, 
                     : pxr_launch_items_simt(h, item_embedding, item_idx, tag_idx, vis, txt, num, n_rows, item_base, h->item_feats, st);
   if (rc) return rc;
   if (h->fast_ok) return pxr_tc_prepare_items(h, n_rows, h->item_fast, st);
+  return PXR_OK;
+}
+
+extern "C" int pxr_set_missing_items(pxr_handle* h, const uint8_t* flags, int64_t n_rows) {
+  if (!h) return PXR_ERR_INVALID;
+  if (flags && n_rows != h->n_rows) PXR_FAIL(h, PXR_ERR_INVALID, "pxr_set_missing_items: %lld flags for %lld precomputed item rows", (long long)n_rows, (long long)h->n_rows);
+  h->item_missing = flags;
   return PXR_OK;
 }
 

@@ -63,6 +63,7 @@ struct pxr_handle {
   void* item_fast = nullptr;     // fast-path per-item records
   int64_t n_rows = 0;
   int64_t item_base = 0;
+  const uint8_t* item_missing = nullptr;   // caller-owned [n_rows] flags (pxr_set_missing_items)
 };
 
 #define PXR_FAIL(h, code, ...)                                   \

@@ -147,6 +147,7 @@ struct Params {
   const int64_t* user_idx;      // (n_users,)
   const int64_t* seen_indptr;   // (n_users + 1,) or NULL
   const int32_t* seen_idx;      // global item indices, ascending per user
+  const uint8_t* item_missing;  // per item row: 1 = features missing, the score is 0.0 (recommender.py:229-230); NULL = none
   float* out_scores;            // [S][n_users][K]
   int32_t* out_idx;
   int64_t n_users, n_rows, item_base;
@@ -955,8 +956,9 @@ score_fused_kernel(const __grid_constant__ Params p) {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(BAR(BAR_D3_EMPTY), 0);
-      const float y = pxr_apply_final(z, p.final_act);
+      float y = pxr_apply_final(z, p.final_act);
       const int64_t row = un.row_lo + (int64_t)t * TI + rj;
+      if (p.item_missing && row < un.row_hi && p.item_missing[row]) y = 0.f;
       const bool ok = row < un.row_hi && (ubase + ru) < p.n_users && !((ms.seen_mask[Tp & 3][ru] >> rj) & 1u);
       if (ok && y >= *reinterpret_cast<volatile float*>(&ms.thr[ru])) {
         const uint32_t gidx = (uint32_t)(p.item_base + row);
@@ -1396,6 +1398,7 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
   }
   p.w1u_t = h->mlp[0].wt;                   // [k][512]: rows 0..63 are the user columns of W1
   p.user_emb = user_embedding; p.user_idx = user_idx; p.seen_indptr = seen_indptr; p.seen_idx = seen_idx;
+  p.item_missing = h->item_missing;
   p.n_users = n_users; p.n_rows = h->n_rows; p.item_base = h->item_base;
   p.M = h->M; p.K = k; p.S = pl.S; p.rows_per_split = pl.rows_per_split; p.n_units = pl.n_units;
   p.final_act = h->cfg.final_activation;

@@ -140,6 +140,7 @@ struct ScoreParams {
   const float* out_w; const float* out_b;
   const float* user_emb; const int64_t* user_idx; const int64_t* item_row;
   const float* item_feats; int64_t n_items; int64_t n_pairs; int dense; int64_t item_base;
+  const uint8_t* item_missing;                 // per item row: 1 = features missing, score is 0.0 (recommender.py:229-230)
   const int64_t* seen_indptr; const int32_t* seen_idx;
   float* out; float* out_logit;
 };
@@ -278,8 +279,9 @@ __global__ void __launch_bounds__(PXR_SIMT_THREADS) score_simt_kernel(ScoreParam
   if (threadIdx.x < ROWS) {
     const int64_t pair = row0 + threadIdx.x;
     if (pair < p.n_pairs) {
-      const float z = G[threadIdx.x * 8];
+      float z = G[threadIdx.x * 8];
       float s = pxr_apply_final(z, p.fin);
+      if (p.item_missing && p.item_missing[prow[threadIdx.x * 2 + 1]]) { s = 0.f; z = 0.f; }
       if (p.dense && p.seen_indptr) {
         const int64_t ul = pair / p.n_items;
         const int32_t gi = (int32_t)(p.item_base + pair % p.n_items);
@@ -344,7 +346,7 @@ int pxr_launch_score_simt(pxr_handle* h, const float* user_embedding, const int6
   p.user_emb = user_embedding; p.user_idx = user_idx; p.item_row = item_row;
   p.item_feats = h->item_feats; p.n_items = h->n_rows; p.n_pairs = n_pairs; p.dense = dense ? 1 : 0;
   p.item_base = h->item_base; p.seen_indptr = seen_indptr; p.seen_idx = seen_idx;
-  p.out = out; p.out_logit = out_logit;
+  p.out = out; p.out_logit = out_logit; p.item_missing = h->item_missing;
   (void)n_users_dense;
   switch (pxr_simt_smem_rows(h, false)) {
     case 32: return launch_score<32>(h, p, st);

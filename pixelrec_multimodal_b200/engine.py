@@ -202,7 +202,19 @@ class PxrEngine:
                 C.c_void_p(ws.data_ptr() + off), nbytes, _stream()), "pxr_precompute_items")
         self._items_ws = ws
         self._keep["items_in"] = (emb, tag, v, t, x, ii)   # inputs must outlive the async launch
+        self._keep.pop("missing", None)
         self.n_rows, self.item_base = n, int(item_base)
+
+    def set_missing_items(self, flags: Optional[torch.Tensor]):
+        """Per-row flags (bool / uint8, aligned with the precomputed rows): flagged items score exactly 0.0, as
+        items without features do in the reference (recommender.py:229-230).  ``None`` clears."""
+        if flags is None:
+            self._check(self.lib.pxr_set_missing_items(self._h, None, 0), "pxr_set_missing_items")
+            self._keep.pop("missing", None)
+            return
+        f = flags.to(device=self.device, dtype=torch.uint8).contiguous()
+        self._check(self.lib.pxr_set_missing_items(self._h, _ptr(f), int(f.shape[0])), "pxr_set_missing_items")
+        self._keep["missing"] = f
 
     # --------------------------------------------------------------- scoring
     def score_topk(self, user_embedding: torch.Tensor, user_idx: torch.Tensor, k: int,

@@ -134,10 +134,9 @@ class FastRecommender:
         if self.items.n_items != self.n_items:
             raise ValueError(f"item feature store has {self.items.n_items} rows, item encoder has {self.n_items}")
         if self.items.missing is not None:
-            # reference: items without features score 0.0 (recommender.py:229-230)
-            raise NotImplementedError(
-                f"{int(self.items.missing.sum())} items have no cached features; the GPU path needs a complete "
-                "feature store (missing-feature items scoring 0.0 is not implemented yet)")
+            # reference: items whose features cannot be fetched are not sent through the model and score 0.0
+            # (recommender.py:199-201, 229-230); here they carry a per-item flag the kernels honour
+            self.logger.warning(f"{int(np.asarray(self.items.missing).sum())} items have no cached features; they score 0.0")
 
         # train histories -> one CSR resident on the device (global item indices, ascending per user)
         if history is None and getattr(dataset, "interactions", None) is not None and self.n_users:
@@ -195,6 +194,8 @@ class FastRecommender:
                                  None if self.items.txt is None else self.items.txt[sl],
                                  None if self.items.num is None else self.items.num[sl],
                                  item_idx=None, item_base=lo, n_rows=hi - lo)
+            if self.items.missing is not None:
+                eng.set_missing_items(torch.from_numpy(np.ascontiguousarray(np.asarray(self.items.missing)[sl]).astype(np.uint8)))
             self._engine, self._engine_token = eng, token
         return eng
 
@@ -339,7 +340,7 @@ class FastRecommender:
     def _get_item_features(self, item_id_str: str):
         """reference recommender.py:239-269 (evaluators call this, tasks.py:455)."""
         i = self.item_index.get(str(item_id_str))
-        if i is None:
+        if i is None or (self.items.missing is not None and bool(self.items.missing[i])):
             return None
         feats = {"tag_idx": self.items.tag_idx[i]}
         if self.items.vis is not None:

@@ -149,6 +149,37 @@ def test_items_tensor_pipe_keeps_fp32_accuracy(fusion, n_items):
     assert float((z - z2).abs().max()) <= 1e-4
 
 
+@pytest.mark.parametrize("fusion,path", [("gated", "tcgen05"), ("concatenate", "tcgen05"), ("attention", "tcgen05"), ("gated", "simt")])
+def test_missing_feature_items_score_zero(fusion, path):
+    """Items whose features cannot be fetched score exactly 0.0 and are ranked with that score
+    (reference src/inference/recommender.py:199-201, 229-230), on both kernel paths and in score_pairs."""
+    spec, sd, feats, indptr, idx, _ = _topk_case(fusion, path, n_users=24, n_items=400)
+    model, eng = _engine_for(spec, sd, feats, path)
+    rng = np.random.default_rng(2)
+    miss = np.zeros(spec.n_items, dtype=bool)
+    miss[rng.choice(spec.n_items, 60, replace=False)] = True
+    miss[[0, 15, 16, 399]] = True
+    eng.set_missing_items(torch.from_numpy(miss))
+    users = np.arange(spec.n_users)
+    k = 400                                                   # whole catalogue: every item must appear once
+    kk = min(k, 64) if path == "tcgen05" else k
+    s, i = eng.score_topk(model.user_embedding.weight.detach(), torch.from_numpy(users).cuda(), kk)
+    s, i = s.cpu().numpy().astype(np.float64), i.cpu().numpy()
+    ref = _lowp_scores(sd, spec, feats, users) if path == "tcgen05" else orc.score_block(sd, cs.spec_cfg(spec), users, 0, spec.n_items, feats)
+    ref = np.where(miss[None, :], 0.0, ref)
+    tol = _emu_tol(fusion, "bf16") if path == "tcgen05" else SIMT_TOL
+    for u in users:
+        _check_topk(s[u], i[u], ref[u], kk, None, tol, 0.0)
+        got_missing = miss[i[u][i[u] >= 0]]
+        assert np.all(s[u][i[u] >= 0][got_missing] == 0.0)   # exactly 0.0, not a model output
+    ii = np.arange(spec.n_items)
+    sc = eng.score_pairs(model.user_embedding.weight.detach(), torch.full((spec.n_items,), 3).cuda(), torch.from_numpy(ii).cuda())
+    assert torch.all(sc[torch.from_numpy(miss).cuda()] == 0.0) and torch.all(sc[torch.from_numpy(~miss).cuda()] > 0.0)
+    eng.set_missing_items(None)
+    sc2 = eng.score_pairs(model.user_embedding.weight.detach(), torch.full((spec.n_items,), 3).cuda(), torch.from_numpy(ii).cuda())
+    assert torch.all(sc2 > 0.0)
+
+
 def test_topk_edge_cases():
     """k > catalogue, a user who has seen everything, empty user batch, empty shard."""
     spec, sd, feats, *_ = _topk_case("concatenate", "simt", n_users=6, n_items=20, full=False)
