@@ -211,6 +211,24 @@ int pxr_sample_candidates(const int64_t* user_idx, int64_t n_users, const int64_
 int pxr_topk_rows(pxr_handle* h, const float* scores, int64_t n_rows, int64_t n_cols, int32_t k, float* out_scores,
                   int32_t* out_pos, pxr_stream stream);
 
+/* Beyond-accuracy metrics over the ranked lists.  Replaces the per-user loop of
+ * NoveltyMetrics.calculate_metrics (src/evaluation/novelty.py:84-147, 149-226, 343-377) and
+ * TopKRetrievalEvaluator._calculate_personalization (src/evaluation/tasks.py:402-427) as aggregated in
+ * TopKRetrievalEvaluator.evaluate (tasks.py:637-714).
+ *   topk_idx    : (n_users, k_stride <= 64) int32 ranked item ids, -1 padded
+ *   self_info   : (n_items,) float64 DEVICE table -log2(max(pop_i / total, 1e-10)), NaN where the item has no
+ *                 popularity entry;  iif : (n_items,) float64 log(n_hist_users / (count_i + 1e-10)), NaN likewise
+ *   hist_indptr / hist_idx : interaction history CSR of these users (ascending per user), NULL = no history
+ *   out6        : DEVICE float64: sum over users with a non-empty list of [mean self-information, mean IIF,
+ *                 #distinct items, fraction of items outside the history, 1], then sum_i s_i^2 with
+ *                 s_i = sum over lists containing item i of 1/sqrt(|list|)   (pairwise cosine of the binary
+ *                 list vectors: sum_{u<v} cos = (sum_i s_i^2 - #non-empty lists) / 2)
+ *   workspace   : pxr_novelty_bytes(n_users, n_items) bytes */
+size_t pxr_novelty_bytes(int64_t n_users, int64_t n_items);
+int pxr_novelty_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, int64_t n_items,
+                        const double* self_info, const double* iif, const int64_t* hist_indptr, const int32_t* hist_idx,
+                        double* out6, void* workspace, size_t workspace_bytes, pxr_stream stream);
+
 /* Live timing of the dominant kernel (the pair-scoring kernel of
  * pxr_score_topk) with CUDA events recorded on the launching stream, for the
  * roofline line of bench.py.  pxr_profile_read synchronises on the recorded

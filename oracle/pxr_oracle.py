@@ -501,3 +501,54 @@ def rank_candidates(scores: Sequence[float], candidates: Sequence[int], k: int) 
     (src/inference/recommender.py:97-106 with candidates=...)."""
     order = sorted(range(len(candidates)), key=lambda i: -scores[i])      # Python's sort is stable
     return [int(candidates[i]) for i in order[:k]]
+
+
+# --------------------------------------------------------------------------
+# beyond-accuracy metrics (SURVEY.md §8(f) N4)
+# --------------------------------------------------------------------------
+def novelty_tables(interaction_items: Sequence[int], interaction_users: Sequence[int], n_items: int):
+    """Per-item tables of NoveltyMetrics (src/evaluation/novelty.py:26-65): popularity = interaction count per item
+    (``value_counts`` at tasks.py:646), self-information -log2(max(pop/total, 1e-10)) (:149-178), IIF
+    log(n_users / (count + 1e-10)) (:180-206); NaN where the item never occurs in the interactions."""
+    cnt = np.bincount(np.asarray(interaction_items, dtype=np.int64), minlength=n_items).astype(np.float64)
+    total = cnt.sum()
+    n_users = len(set(int(u) for u in interaction_users))
+    si = np.full(n_items, np.nan)
+    iif = np.full(n_items, np.nan)
+    has = cnt > 0
+    if total > 0:
+        si[has] = -np.log2(np.maximum(cnt[has] / total, 1e-10))
+    if n_users > 0:
+        iif[has] = np.log(n_users / (cnt[has] + 1e-10))
+    return si, iif, int(has.sum())
+
+
+def novelty_metrics(rec_lists: Sequence[Sequence[int]], histories: Sequence[Set[int]], si, iif, n_pop: int) -> Dict[str, float]:
+    """Aggregation of TopKRetrievalEvaluator.evaluate (src/evaluation/tasks.py:674-714) over per-user
+    NoveltyMetrics.calculate_metrics (novelty.py:84-147) and _calculate_personalization (tasks.py:402-427),
+    written as the direct loops (personalization as the explicit mean over all user pairs)."""
+    a_si, a_iif, a_cov, a_pn = [], [], [], []
+    for recs, hist in zip(rec_lists, histories):
+        recs = [int(r) for r in recs if r >= 0]
+        if not recs:
+            continue
+        v = [si[r] for r in recs if not np.isnan(si[r])]
+        a_si.append(np.mean(v) if v else 0.0)
+        v = [iif[r] for r in recs if not np.isnan(iif[r])]
+        a_iif.append(np.mean(v) if v else 0.0)
+        a_cov.append(len(set(recs)) / n_pop if n_pop else 0.0)
+        a_pn.append(len([r for r in recs if r not in hist]) / len(recs))
+    n = len(rec_lists)
+    if n <= 1:
+        pers = 1.0 if n == 1 else 0.0
+    else:
+        sets = [set(int(r) for r in recs if r >= 0) for recs in rec_lists]
+        tot = 0.0
+        for a in range(n):
+            for b in range(a + 1, n):
+                if sets[a] and sets[b]:
+                    tot += len(sets[a] & sets[b]) / math.sqrt(len(sets[a]) * len(sets[b]))
+        pers = 1.0 - tot / (n * (n - 1) / 2)
+    m = lambda x: float(np.mean(x)) if x else 0.0
+    return {"avg_self_information": m(a_si), "avg_iif": m(a_iif), "avg_catalog_coverage": m(a_cov),
+            "avg_personalization": pers, "avg_personalized_novelty": m(a_pn)}

@@ -161,7 +161,7 @@ def cmd_evaluate(args) -> Dict:
     else:
         ev = FullCatalogueEvaluator(rec, test, top_k=top_k, ks=ks, filter_seen=cfg["recommendation"]["filter_seen"],
                                     keep_predictions=bool(args.save_predictions))
-    results = ev.evaluate()
+    results = ev.evaluate(novelty=True) if (args.novelty and not args.use_sampling) else ev.evaluate()
     results_dir = Path(cfg["results_dir"])
     if args.save_predictions and "predictions" in results:          # evaluate.py:417-426
         preds = results.pop("predictions")
@@ -210,6 +210,7 @@ def make_parser() -> argparse.ArgumentParser:
     e.add_argument("--seed", type=int, default=20261018)
     e.add_argument("--ks", type=int, nargs="*", help="extra cut-offs reported under by_k")
     e.add_argument("--save_predictions", type=str, default=None)
+    e.add_argument("--novelty", action="store_true", help="add the novelty / coverage / personalization block (tasks.py:637-714)")
     e.add_argument("--output", type=str, default="evaluation_results.json")
     e.set_defaults(fn=cmd_evaluate)
     return ap

@@ -37,6 +37,56 @@ def ranking_metrics(topk_idx: torch.Tensor, gt_indptr, gt_idx, ks: Sequence[int]
     return out
 
 
+def novelty_tables(interactions_items: np.ndarray, n_hist_users: int, n_items: int):
+    """Per-item float64 tables of ``NoveltyMetrics`` (reference src/evaluation/novelty.py:26-65, 149-206) from the
+    interaction table: (self_information, iif, number of items with a popularity entry); NaN = no entry."""
+    cnt = np.bincount(np.asarray(interactions_items, dtype=np.int64), minlength=n_items).astype(np.float64)
+    total = cnt.sum()
+    has = cnt > 0
+    si = np.full(n_items, np.nan)
+    iif = np.full(n_items, np.nan)
+    if total > 0:
+        si[has] = -np.log2(np.maximum(cnt[has] / total, 1e-10))
+    if n_hist_users > 0:
+        iif[has] = np.log(n_hist_users / (cnt[has] + 1e-10))
+    return si, iif, int(has.sum())
+
+
+def beyond_accuracy_metrics(topk_idx: torch.Tensor, si: np.ndarray, iif: np.ndarray, n_pop: int,
+                            hist_indptr=None, hist_idx=None) -> Dict[str, float]:
+    """Novelty / coverage / personalization over the ranked lists on the GPU (``pxr_novelty_metrics``), keys and
+    aggregation of ``TopKRetrievalEvaluator.evaluate`` (tasks.py:674-714).  ``avg_intra_list_similarity`` is not
+    produced: the reference's embedding collection for it raises ``NameError`` (tasks.py:478) and yields no value."""
+    import ctypes as C
+    from . import _lib
+    from .engine import _ptr, _stream
+    lib = _lib.load()
+    dev = topk_idx.device
+    topk_idx = topk_idx.to(torch.int32).contiguous()
+    n, k = topk_idx.shape
+    n_items = len(si)
+    d_si, d_iif = torch.from_numpy(si).to(dev), torch.from_numpy(iif).to(dev)
+    ip = torch.as_tensor(hist_indptr).to(device=dev, dtype=torch.int64).contiguous() if hist_indptr is not None else None
+    ix = torch.as_tensor(hist_idx).to(device=dev, dtype=torch.int32).contiguous() if hist_idx is not None else None
+    out = torch.empty(6, dtype=torch.float64, device=dev)
+    nbytes = int(lib.pxr_novelty_bytes(n, n_items))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.pxr_novelty_metrics(_ptr(topk_idx), k, n, n_items, _ptr(d_si), _ptr(d_iif), _ptr(ip), _ptr(ix), _ptr(out),
+                                     _ptr(ws), nbytes, _stream())
+    if rc != 0:
+        raise _lib.PxrError(f"pxr_novelty_metrics failed ({rc})")
+    s_si, s_iif, s_uniq, s_pn, n_ne, ssq = out.cpu().tolist()
+    m = lambda x: float(x / n_ne) if n_ne else 0.0
+    if n <= 1:
+        pers = 1.0 if n == 1 else 0.0
+    else:
+        pers = 1.0 - ((ssq - n_ne) / 2.0) / (n * (n - 1) / 2.0)
+    return {"avg_self_information": m(s_si), "avg_iif": m(s_iif),
+            "avg_catalog_coverage": float(s_uniq / n_pop / n_ne) if (n_ne and n_pop) else 0.0,
+            "avg_personalization": float(pers), "avg_personalized_novelty": m(s_pn)}
+
+
 class FullCatalogueEvaluator:
     """``evaluate()`` returns the result-dict keys of tasks.py:623-635 for
     ``top_k`` (plus ``by_k`` with every requested cut-off)."""
@@ -67,7 +117,28 @@ class FullCatalogueEvaluator:
         self.gt_indptr = np.cumsum(cnt)
         self.gt_idx = i.astype(np.int32)
 
-    def evaluate(self) -> Dict:
+    def novelty(self, topk_idx: torch.Tensor) -> Dict[str, float]:
+        """Novelty / coverage / personalization block of ``evaluate`` (tasks.py:637-714) for lists aligned with
+        ``self.users``; {} when the recommender has no interaction history (tasks.py:650-652)."""
+        r = self.recommender
+        if not r.has_history:
+            return {}
+        ip, ix = r._host_history()
+        inter = getattr(r.dataset, "interactions", None)
+        if inter is not None and len(inter):
+            # popularity counts interaction ROWS (value_counts, tasks.py:646), duplicates included
+            ii = inter["item_id"].astype(str).map(r.item_index)
+            items_for_counts = ii[ii.notna()].to_numpy(dtype=np.int64)
+            n_hist_users = int(inter["user_id"].astype(str).nunique())
+        else:
+            items_for_counts, n_hist_users = ix, int(np.count_nonzero(np.diff(ip)))
+        si, iif, n_pop = novelty_tables(items_for_counts, n_hist_users, r.n_items)
+        lens = ip[self.users + 1] - ip[self.users]
+        sub_ip = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        sub_ix = np.concatenate([ix[ip[u]:ip[u + 1]] for u in self.users]).astype(np.int32) if len(self.users) and sub_ip[-1] else np.zeros(1, np.int32)
+        return beyond_accuracy_metrics(topk_idx[:, :self.top_k], si, iif, n_pop, sub_ip, sub_ix)
+
+    def evaluate(self, novelty: bool = False) -> Dict:
         r = self.recommender
         kmax = max(self.ks)
         scores, idx = r.recommend_all(self.users, top_k=kmax, filter_seen=self.filter_seen)
@@ -75,6 +146,8 @@ class FullCatalogueEvaluator:
         res = {k: v for k, v in by_k[self.top_k].items() if k != "avg_ndcg_list_ideal_at_k"}
         res["evaluation_method"] = "full_evaluation"
         res["by_k"] = by_k
+        if novelty:
+            res.update(self.novelty(idx))
         if self.keep_predictions:
             s, i = scores.cpu().numpy(), idx.cpu().numpy()
             res["predictions"] = {str(r.user_ids[int(u)]): [(str(r.item_ids[int(b)]), float(a)) for a, b in zip(s[j], i[j]) if b >= 0]

@@ -75,7 +75,9 @@ def test_cli_end_to_end(tmp_path, fusion):
     assert len(allr) == spec.n_users
     for u in (uids[3], uids[7]):                                                     # batched == per-user string API
         assert [r["item_id"] for r in allr[u]["recommendations"]] == [r["item_id"] for r in disk[u]["recommendations"]]
-    ev = cli.main(["evaluate", *common, "--test_data", str(tmp_path / "test.csv"), "--ks", "5", "--output", "e.json"])
+    ev = cli.main(["evaluate", *common, "--test_data", str(tmp_path / "test.csv"), "--ks", "5", "--output", "e.json", "--novelty"])
+    assert ev["avg_personalized_novelty"] == 1.0 and 0.0 < ev["avg_catalog_coverage"] <= 1.0        # filter_seen: every item is new
+    assert ev["avg_self_information"] > 0.0 and 0.0 <= ev["avg_personalization"] <= 1.0
     assert ev["evaluation_method"] == "full_evaluation" and ev["num_users_evaluated"] == spec.n_users
     assert set(ev["by_k"]) == {"5", "10"} and 0.0 <= ev["avg_recall_at_k"] <= 1.0
     hits = np.mean([iids[int(test_item[u])] in [r["item_id"] for r in allr[uids[u]]["recommendations"]] for u in range(spec.n_users)])
