@@ -35,6 +35,26 @@ def allgather_topk(scores: torch.Tensor, idx: torch.Tensor, group=None) -> Tuple
     return all_s.view(world, n, k), all_i.view(world, n, k)
 
 
+def allgather_topk_start(scores: torch.Tensor, idx: torch.Tensor, group=None):
+    """Start ONE asynchronous all-gather of the local lists (score bits and indices interleaved in a single
+    (n, K, 2) int32 buffer: 8*K bytes per user per rank).  Returns a handle for ``allgather_topk_finish``; the
+    collective runs on the communicator's own stream and overlaps whatever is launched next."""
+    world = dist.get_world_size(group)
+    n, k = scores.shape
+    local = torch.stack([scores.contiguous().view(torch.int32), idx.to(torch.int32)], dim=-1).contiguous()
+    out = torch.empty((world * n, k, 2), dtype=torch.int32, device=scores.device)
+    work = dist.all_gather_into_tensor(out, local, group=group, async_op=True)
+    return work, out, (world, n, k), local
+
+
+def allgather_topk_finish(handle) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Wait for a started all-gather: (world, n, K) fp32 scores and int32 indices stacked in rank order."""
+    work, out, (world, n, k), _local = handle
+    work.wait()
+    out = out.view(world, n, k, 2)
+    return out[..., 0].contiguous().view(torch.float32), out[..., 1].contiguous()
+
+
 class ShardedTopK:
     """Lock-step sharded scoring: ``local_topk(users, k, filter_seen)`` is the
     rank's scorer over its item range (``FastRecommender.recommend_all`` in
@@ -53,3 +73,21 @@ class ShardedTopK:
             return s, i
         all_s, all_i = allgather_topk(s, i, self.group)
         return self.merge(all_s, all_i)
+
+    def recommend_blocks(self, user_blocks, top_k: int, filter_seen: bool = True):
+        """Generator over user blocks with the exchange of block b overlapped with the scoring of block b + 1
+        (SURVEY.md §8(e)): the local kernel of the next block is launched before the previous block's all-gather
+        is waited for and merged.  Yields (scores, indices) per block, in order."""
+        sharded = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        pending = None
+        for blk in user_blocks:
+            s, i = self.local_topk(blk, top_k, filter_seen)
+            if not sharded:
+                yield s, i
+                continue
+            handle = allgather_topk_start(s, i, self.group)
+            if pending is not None:
+                yield self.merge(*allgather_topk_finish(pending))
+            pending = handle
+        if pending is not None:
+            yield self.merge(*allgather_topk_finish(pending))

@@ -158,6 +158,12 @@ s, i = st.recommend_all(np.arange(NU), K, False)
 for u in range(NU):
     sel, sc = orc.topk_from_scores(scores[u].astype(np.float64), K)
     assert i[u].tolist() == sel.tolist(), (rank, u, i[u].tolist(), sel.tolist())
+# pipelined variant: exchange of block b overlapped with scoring of block b + 1, single packed all-gather
+blocks = [np.arange(0, 3), np.arange(3, 4), np.arange(4, NU)]
+outs = list(st.recommend_blocks(blocks, K, False))
+assert len(outs) == 3
+ps, pi = torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+assert torch.equal(pi, i) and torch.equal(ps, s)
 dist.barrier(); dist.destroy_process_group()
 print("OK", rank)
 """
