@@ -259,12 +259,13 @@ struct GatherParams {
   const float* tag_emb; const int64_t* tag_idx;
   const float* num; int num_dim; const float* num_wt; const float* num_b; int num_slot; int act;
   float* feats; int FD, D; int64_t n_rows;
+  int rows;                          // items per block (<= 32; fewer for wide embeddings so the staging fits 48 KB)
 };
 
 __global__ void __launch_bounds__(128) gather_small_kernel(const GatherParams p) {
   extern __shared__ __align__(128) uint8_t gsm[];
   __shared__ unsigned long long bar;
-  const int rows = 32;
+  const int rows = p.rows;
   const int64_t row0 = (int64_t)blockIdx.x * rows;
   const int n = (int)min((int64_t)rows, p.n_rows - row0);
   const uint32_t rb = (uint32_t)p.D * 4;                            // bytes of one embedding row
@@ -311,6 +312,11 @@ struct ItemImages {          // device pointers into h->tc_items_w
 
 static size_t img_bytes(int N, int K) { return (size_t)2 * N * ((K + KC - 1) / KC) * KC * 4; }
 
+static int n_tile_for(int N) {          // largest divisor of N that is a multiple of 16 and at most 256
+  for (int nt = std::min(N, 256) / 16 * 16; nt >= 16; nt -= 16) if (N % nt == 0) return nt;
+  return 0;
+}
+
 static int launch_gemm(pxr_handle* h, const GemmParams& gp, cudaStream_t st) {
   GemmParams p = gp;
   p.n_stages = p.NT <= 64 ? 4 : 2;
@@ -335,7 +341,7 @@ static int launch_gemm(pxr_handle* h, const GemmParams& gp, cudaStream_t st) {
 // The tensor-pipe item path covers single-layer projections with 16-byte aligned feature rows.
 bool pxr_items_tc_supported(const pxr_handle* h) {
   const pxr_config& c = h->cfg;
-  if (!h->fast_ok || c.projection_hidden != 0 || c.embedding_dim != 64) return false;
+  if (!h->fast_ok || c.projection_hidden != 0 || c.embedding_dim % 16 != 0 || c.embedding_dim > 512) return false;
   if ((c.vision_dim && c.vision_dim % 4) || (c.language_dim && c.language_dim % 4) || c.num_numerical > 32) return false;
   return true;
 }
@@ -357,7 +363,7 @@ int pxr_items_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
     h->tc_items_img[m] = nullptr;
     if (!h->has_mod[m]) continue;
     h->tc_items_img[m] = cur;
-    itc::split_weights_kernel<<<256, 256, 0, st>>>(h->proj[m][0].w, kdim[m], 0, D, kdim[m], D, cur);
+    itc::split_weights_kernel<<<256, 256, 0, st>>>(h->proj[m][0].w, kdim[m], 0, D, kdim[m], itc::n_tile_for(D), cur);
     h->launches++;
     cur += pxr_align_up(itc::img_bytes(D, kdim[m]), 1024);
   }
@@ -387,7 +393,7 @@ int pxr_launch_items_tc(pxr_handle* h, const float* item_embedding, const int64_
     if (!ins[m]) PXR_FAIL(h, PXR_ERR_INVALID, "modality %d is configured but its feature pointer is NULL", m);
     itc::GemmParams gp;
     memset(&gp, 0, sizeof(gp));
-    gp.A = ins[m]; gp.lda = kdim[m]; gp.M = n_rows; gp.K = kdim[m]; gp.N = D; gp.NT = D;
+    gp.A = ins[m]; gp.lda = kdim[m]; gp.M = n_rows; gp.K = kdim[m]; gp.N = D; gp.NT = itc::n_tile_for(D);
     gp.wimg = h->tc_items_img[m]; gp.bias = h->proj[m][0].b;
     gp.mode = itc::OUT_F32_ACT; gp.act = c.activation; gp.out_f = feats_out + slot * D; gp.ldo = FD;
     int rc = itc::launch_gemm(h, gp, st);
@@ -403,7 +409,8 @@ int pxr_launch_items_tc(pxr_handle* h, const float* item_embedding, const int64_
     g.num = num; g.num_dim = c.num_numerical; g.num_wt = h->proj[2][0].wt; g.num_b = h->proj[2][0].b; g.num_slot = slot;
   }
   g.act = c.activation; g.feats = feats_out; g.FD = FD; g.D = D; g.n_rows = n_rows;
-  itc::gather_small_kernel<<<(unsigned)((n_rows + 31) / 32), 128, 32 * 2 * D * 4, st>>>(g);
+  g.rows = std::max(1, std::min(32, (40 * 1024) / (2 * D * 4)));
+  itc::gather_small_kernel<<<(unsigned)((n_rows + g.rows - 1) / g.rows), 128, (size_t)g.rows * 2 * D * 4, st>>>(g);
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
   return PXR_OK;

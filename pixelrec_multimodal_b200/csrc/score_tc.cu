@@ -152,6 +152,7 @@ struct Params {
   int32_t* out_idx;
   int64_t n_users, n_rows, item_base;
   int M, K, S, rows_per_split, n_units, final_act;
+  int Dm;                       // embedding dim of the model (concat: any multiple of 4 up to 512; gated / attention: 64)
 };
 
 struct Unit { int g, s; int64_t row_lo, row_hi; int ntiles; };
@@ -609,7 +610,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
         float (*eu_dst)[D] = ATT ? reinterpret_cast<float (*)[D]>(sm + MP::OFF_A1) : ms.eu;
         const int u = tid >> 4, d4 = (tid & 15) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ubase + u < p.n_users) v = *reinterpret_cast<const float4*>(p.user_emb + p.user_idx[ubase + u] * D + d4);
+        if (ubase + u < p.n_users && d4 < p.Dm) v = *reinterpret_cast<const float4*>(p.user_emb + p.user_idx[ubase + u] * p.Dm + d4);
         *reinterpret_cast<float4*>(&eu_dst[u][d4]) = v;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -627,20 +628,33 @@ score_fused_kernel(const __grid_constant__ Params p) {
           ms.lu[u][m] = acc;
         }
       } else {
-        // per-user partial of layer 1: Pu[u][n] = sum_k W1[n][k < 64] Eu[u][k]   (SURVEY.md A3), fp32
+        // per-user partial of layer 1: Pu[u][n] = sum_{k < D} W1[n][k] Eu[u][k]   (SURVEY.md A3), fp32.  The user
+        // embedding is staged 64 dims at a time, so any embedding_dim works (the MMA chain does not depend on it).
         float acc[TU][4];
 #pragma unroll
         for (int u = 0; u < TU; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f; }
         const float* wcol = p.w1u_t + 4 * tid;
+        for (int k0 = 0;; k0 += D) {
+          const int kn = min(D, p.Dm - k0);
 #pragma unroll 4
-        for (int k = 0; k < D; ++k) {
-          const float4 wv = *reinterpret_cast<const float4*>(wcol + (size_t)k * H1);
+          for (int k = 0; k < kn; ++k) {
+            const float4 wv = *reinterpret_cast<const float4*>(wcol + (size_t)(k0 + k) * H1);
 #pragma unroll
-          for (int u = 0; u < TU; ++u) {
-            const float e = ms.eu[u][k];
-            acc[u][0] = fmaf(e, wv.x, acc[u][0]); acc[u][1] = fmaf(e, wv.y, acc[u][1]);
-            acc[u][2] = fmaf(e, wv.z, acc[u][2]); acc[u][3] = fmaf(e, wv.w, acc[u][3]);
+            for (int u = 0; u < TU; ++u) {
+              const float e = ms.eu[u][k];
+              acc[u][0] = fmaf(e, wv.x, acc[u][0]); acc[u][1] = fmaf(e, wv.y, acc[u][1]);
+              acc[u][2] = fmaf(e, wv.z, acc[u][2]); acc[u][3] = fmaf(e, wv.w, acc[u][3]);
+            }
           }
+          if (k0 + D >= p.Dm) break;
+          asm volatile("bar.sync 1, 128;" ::: "memory");            // everyone is done with this 64-dim slice of E_u
+          {
+            const int u = tid >> 4, d4 = k0 + D + (tid & 15) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ubase + u < p.n_users && d4 < p.Dm) v = *reinterpret_cast<const float4*>(p.user_emb + p.user_idx[ubase + u] * p.Dm + d4);
+            *reinterpret_cast<float4*>(&ms.eu[u][(tid & 15) * 4]) = v;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
 #pragma unroll
         for (int u = 0; u < TU; ++u)
@@ -1098,10 +1112,10 @@ __global__ void item_logit_kernel(const float* __restrict__ feats, const float* 
 // concat: item partial of layer 1, Pi[row] = W1[:, D:] . concat(item-side vectors) + b1   -> 16 bit.
 // 32 rows per block; W1^T (k-major, [M*D][512]) rows D.. are the item part.
 __global__ void __launch_bounds__(PXR_SIMT_THREADS) item_pi_kernel(const float* __restrict__ feats, const float* __restrict__ w1t,
-                                                                    const float* __restrict__ b1, int M, int64_t n_rows,
+                                                                    const float* __restrict__ b1, int M, int Dm, int64_t n_rows,
                                                                     uint16_t* __restrict__ out, int fmt) {
   extern __shared__ __align__(16) float smem_pi[];
-  const int FD = (M - 1) * D;
+  const int FD = (M - 1) * Dm;
   float* in = smem_pi;                       // [32][FD]
   float* res = smem_pi + 32 * FD;            // [32][512]
   const int64_t row0 = (int64_t)blockIdx.x * 32;
@@ -1110,7 +1124,7 @@ __global__ void __launch_bounds__(PXR_SIMT_THREADS) item_pi_kernel(const float* 
     in[i] = row < n_rows ? feats[row * FD + i % FD] : 0.f;
   }
   __syncthreads();
-  linear_rows<32>(in, FD, FD, w1t + (size_t)D * H1, b1, H1, res, H1, -1);
+  linear_rows<32>(in, FD, FD, w1t + (size_t)Dm * H1, b1, H1, res, H1, -1);
   __syncthreads();
   for (int i = threadIdx.x; i < 32 * H1; i += PXR_SIMT_THREADS) {
     const int64_t row = row0 + i / H1;
@@ -1265,7 +1279,12 @@ bool pxr_tc_supported(const pxr_handle* h) {
   const pxr_config& c = h->cfg;
   const bool fusion_ok = c.fusion == PXR_FUSION_GATED || c.fusion == PXR_FUSION_CONCAT ||
                          (c.fusion == PXR_FUSION_ATTENTION && c.num_heads == tc::NH);
-  return fusion_ok && c.embedding_dim == tc::D && c.n_hidden == 3 &&
+  // concat: layer 1 is applied as per-user / per-item partials, so the fused kernel does not depend on embedding_dim
+  // (item side: 3xTF32 GEMMs of items_tc.cu, which need single-layer projections and 16-byte aligned rows)
+  const bool dim_ok = c.embedding_dim == tc::D ||
+                      (c.fusion == PXR_FUSION_CONCAT && c.embedding_dim % 16 == 0 && c.embedding_dim <= 512 && c.projection_hidden == 0 &&
+                       c.vision_dim % 4 == 0 && c.language_dim % 4 == 0 && c.num_numerical <= 32);
+  return fusion_ok && dim_ok && c.n_hidden == 3 &&
          c.hidden[0] == tc::H1 && c.hidden[1] == tc::H2 && c.hidden[2] == tc::H3 && c.activation == PXR_ACT_RELU &&
          h->M >= 4 && h->M <= 6 && h->n_sm >= 2;
 }
@@ -1327,14 +1346,15 @@ int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t s
   } else if (h->tc_items_img[2] && h->path == PXR_PATH_TCGEN05) {
     return pxr_launch_item_pi_tc(h, n_rows, (uint16_t*)ws, tc_fmt(h), st);      // 3xTF32 GEMM on the tensor pipe
   } else {
-    const int FD = (h->M - 1) * tc::D;
+    const int FD = (h->M - 1) * h->cfg.embedding_dim;
     const size_t smem = (size_t)32 * (FD + tc::H1) * sizeof(float);
+    if (smem > (size_t)h->max_smem_optin) PXR_FAIL(h, PXR_ERR_INVALID, "concat item partial: embedding_dim %d needs the tensor-pipe item path", h->cfg.embedding_dim);
     if (!(h->tc_attr_set & 256u)) {
       PXR_CUDA(h, cudaFuncSetAttribute(tc::item_pi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       h->tc_attr_set |= 256u;
     }
     tc::item_pi_kernel<<<(unsigned)((n_rows + 31) / 32), PXR_SIMT_THREADS, smem, st>>>(h->item_feats, h->mlp[0].wt, h->mlp[0].b,
-                                                                                       h->M, n_rows, (uint16_t*)ws, tc_fmt(h));
+                                                                                       h->M, h->cfg.embedding_dim, n_rows, (uint16_t*)ws, tc_fmt(h));
   }
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
@@ -1400,6 +1420,7 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
   p.user_emb = user_embedding; p.user_idx = user_idx; p.seen_indptr = seen_indptr; p.seen_idx = seen_idx;
   p.item_missing = h->item_missing;
   p.n_users = n_users; p.n_rows = h->n_rows; p.item_base = h->item_base;
+  p.Dm = h->cfg.embedding_dim;
   p.M = h->M; p.K = k; p.S = pl.S; p.rows_per_split = pl.rows_per_split; p.n_units = pl.n_units;
   p.final_act = h->cfg.final_activation;
   float* part_s = out_scores; int32_t* part_i = out_idx;

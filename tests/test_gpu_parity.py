@@ -482,6 +482,37 @@ def test_tcgen05_matches_emulated_and_exact_oracle(fusion, dtype, n_users, n_ite
           f"{same_ref}/{total} to the exact oracle; max|emu-exact| = {np.max(np.abs(emu - ref)):.2e}")
 
 
+@pytest.mark.parametrize("D", [16, 128, 320, 512])
+def test_tcgen05_concat_any_embedding_dim(D):
+    """concat fusion on the fused path for embedding dims other than 64 (BASELINE.json configs[4] sweeps 64-512):
+    layer 1 is applied as per-user / per-item partials, so only the partial builders depend on D (3xTF32 item GEMMs
+    with K = 5 D and N tiles of a divisor of D; the user partial staged 64 dims at a time)."""
+    n_users, n_items, k = 40, 700, 50
+    spec = syn.ModelSpec(n_users=n_users, n_items=n_items, fusion_type="concatenate", embedding_dim=D)
+    sd = syn.make_state_dict(spec, seed=syn.SEED + 23)
+    feats = syn.make_item_features(spec, seed=syn.SEED + 23)
+    syn.condition_like_trained(sd, spec, feats)
+    indptr, idx, _ = syn.make_histories(n_users, n_items, seed=syn.SEED + 23, lo=3, hi=40)
+    model, eng = _engine_for(spec, sd, feats, "tcgen05")
+    assert eng.active_path == "tcgen05"
+    users = np.arange(n_users)
+    s, i = eng.score_topk(model.user_embedding.weight.detach(), torch.from_numpy(users).cuda(), k,
+                          torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda())
+    s, i = _structural_checks(s, i, k, n_items, indptr, idx)
+    emu = _lowp_scores(sd, spec, feats, users)
+    errs = np.concatenate([np.abs(s[u].astype(np.float64) - emu[u][i[u]]) for u in users])
+    assert np.quantile(errs, 0.9) <= TC_EMU_TOL["bf16"] / 8
+    same = sum(_check_topk(s[u].astype(np.float64), i[u], emu[u], k, idx[indptr[u]:indptr[u + 1]], _emu_tol("concatenate", "bf16"), 0.0)
+               for u in users)
+    assert same >= 0.9 * k * n_users      # the rest are swaps inside the flip band (checked above); denser scores at large D
+    # the fp32 records behind it (forward / get_item_score) stay fp32-accurate at every D
+    rng = np.random.default_rng(D)
+    uu, ii = rng.integers(0, n_users, 500), rng.integers(0, n_items, 500)
+    z = eng.score_pairs(model.user_embedding.weight.detach(), torch.from_numpy(uu).cuda(), torch.from_numpy(ii).cuda(), want_logit=True)[1]
+    zr = orc.forward_pairs(sd, cs.spec_cfg(spec), uu, ii, feats["tag_idx"][ii], feats["vis"][ii], feats["txt"][ii], feats["num"][ii], return_logit=True)
+    assert np.max(np.abs(z.cpu().numpy() - zr)) <= 5e-4 * max(1.0, D / 128), float(np.max(np.abs(z.cpu().numpy() - zr)))   # fp32 sums over 6 D inputs
+
+
 @pytest.mark.parametrize("fusion", ["gated", "concatenate", "attention"])
 def test_tcgen05_many_units_and_item_splits(fusion):
     """More user groups than CTA pairs (several units per pair: list reset between units) and an item
