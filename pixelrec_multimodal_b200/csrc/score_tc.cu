@@ -342,14 +342,42 @@ __device__ __forceinline__ void attn_user_setup(const Params& p, MiscA& ms, floa
   }
 }
 
+// v[u4]: partial sums of 4 users held by every lane of a 4-lane head quad -> reduce-scatter: lane ql of the quad ends
+// up with the total of user u4 = ql (3 shuffles instead of 8, and the value is then transformed once, not four times)
+__device__ __forceinline__ float quad_scatter4(const float* v, int ql) {
+  const bool b1 = ql & 2, b0 = ql & 1;
+  const float k0 = (b1 ? v[2] : v[0]) + __shfl_xor_sync(0xffffffffu, b1 ? v[0] : v[2], 2);
+  const float k1 = (b1 ? v[3] : v[1]) + __shfl_xor_sync(0xffffffffu, b1 ? v[1] : v[3], 2);
+  return (b0 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, b0 ? k0 : k1, 1);
+}
+
+// y[u4][4]: 4 users x this lane's 4 dims, already centred over d.  r[u4] = LayerNorm rstd of each user: the sums of
+// squares are reduce-scattered over the 16 lanes of the item (5 shuffles), one rsqrt per lane, 4 indexed gathers.
+__device__ __forceinline__ void ln_rstd4(const float (*y)[4], int lane, float* r) {
+  float ss[4];
+#pragma unroll
+  for (int u4 = 0; u4 < 4; ++u4) ss[u4] = fmaf(y[u4][3], y[u4][3], fmaf(y[u4][2], y[u4][2], fmaf(y[u4][1], y[u4][1], y[u4][0] * y[u4][0])));
+  const bool b3 = lane & 8, b2 = lane & 4;
+  const float k0 = (b3 ? ss[2] : ss[0]) + __shfl_xor_sync(0xffffffffu, b3 ? ss[0] : ss[2], 8);
+  const float k1 = (b3 ? ss[3] : ss[1]) + __shfl_xor_sync(0xffffffffu, b3 ? ss[1] : ss[3], 8);
+  float t = (b2 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, b2 ? k0 : k1, 4);       // user u4 = 2 b3 + b2, summed over 4 lanes
+  t += __shfl_xor_sync(0xffffffffu, t, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+  const float rr = rsqrtf(fmaf(t, 1.f / D, 1e-5f));
+#pragma unroll
+  for (int u4 = 0; u4 < 4; ++u4) r[u4] = __shfl_sync(0xffffffffu, rr, (lane & 19) | (u4 << 2));
+}
+
 // acc = sum over tokens of the normalised rows, for the 8 users x 8 items of one half tile -> 16-bit A1 rows.
 // `wait_a1` is called once, right before the first store into A1.
-// The front end is one warp per scheduler, so latency is hidden by instruction-level parallelism only: every step is
-// written as a loop over users (4 or 8 independent chains), with the shuffles of one step issued back to back.
+// The front end is latency-bound per warp (two warps per scheduler), so latency is hidden by instruction-level
+// parallelism: every step is a loop over 4 users (independent chains) with its shuffles issued back to back, and
+// cross-lane sums are reduce-scatters + indexed gathers (28 shuffles per (token, 4 users) instead of 40; one
+// softmax / sigmoid / rsqrt per value instead of one per lane).
 template <int FMT, class MiscA, typename WaitA1>
 __device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* us, const float* rec, int nt, uint8_t* a1,
                                                int half, int tid, int lane, WaitA1 wait_a1) {
-  const int j8 = tid >> 4, s = tid & 15, hd = s >> 2;
+  const int j8 = tid >> 4, s = tid & 15, hd = s >> 2, ql = s & 3;
   const int gb = lane & 16;                                // first lane of this item's 16-lane group
   float acc[TU][4];
   // token data of the first item token: fetched now, consumed after the user-token row
@@ -364,7 +392,7 @@ __device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* 
   };
   {
     // ---- token 0 (the user token): scores against every token, softmax per head, value mix, normalise
-    float S[TU][ATT_TOKENS];
+    float pw[2][ATT_TOKENS + 1];                           // softmax weights of users ql and 4 + ql, head hd: [0] user token, [1 + b] item token b
     {
       float4 kb[ATT_TOKENS];
 #pragma unroll
@@ -375,41 +403,36 @@ __device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* 
         acc[u][0] = c0.x; acc[u][1] = c0.y; acc[u][2] = c0.z; acc[u][3] = c0.w;
       }
 #pragma unroll
-      for (int u = 0; u < TU; ++u) {
-        const float4 qv = *reinterpret_cast<const float4*>(&ms.qu[u][4 * s]);
+      for (int ug = 0; ug < 2; ++ug) {
+        float S[ATT_TOKENS][4];
 #pragma unroll
-        for (int b = 0; b < ATT_TOKENS; ++b) S[u][b] = dot4(qv, kb[b]);
+        for (int u4 = 0; u4 < 4; ++u4) {
+          const float4 qv = *reinterpret_cast<const float4*>(&ms.qu[4 * ug + u4][4 * s]);
+#pragma unroll
+          for (int b = 0; b < ATT_TOKENS; ++b) S[b][u4] = dot4(qv, kb[b]);
+        }
+        float sv[ATT_TOKENS];
+#pragma unroll
+        for (int b = 0; b < ATT_TOKENS; ++b) sv[b] = quad_scatter4(S[b], ql);
+        const float s00 = ms.S00[4 * ug + ql][hd];
+        float m = s00;
+#pragma unroll
+        for (int b = 0; b < ATT_TOKENS; ++b) { if (b >= nt) sv[b] = -INFINITY; m = fmaxf(m, sv[b]); }
+        const float e0 = __expf(s00 - m);
+        float sum = e0;
+#pragma unroll
+        for (int b = 0; b < ATT_TOKENS; ++b) { sv[b] = __expf(sv[b] - m); sum += sv[b]; }
+        const float inv = __fdividef(1.f, sum);
+        pw[ug][0] = e0 * inv;
+#pragma unroll
+        for (int b = 0; b < ATT_TOKENS; ++b) pw[ug][1 + b] = sv[b] * inv;
       }
-    }
-#pragma unroll
-    for (int u = 0; u < TU; ++u)
-#pragma unroll
-      for (int b = 0; b < ATT_TOKENS; ++b) S[u][b] += __shfl_xor_sync(0xffffffffu, S[u][b], 1);
-#pragma unroll
-    for (int u = 0; u < TU; ++u)
-#pragma unroll
-      for (int b = 0; b < ATT_TOKENS; ++b) S[u][b] += __shfl_xor_sync(0xffffffffu, S[u][b], 2);
-    float p0[TU];
-#pragma unroll
-    for (int u = 0; u < TU; ++u) {
-      const float s00 = ms.S00[u][hd];
-      float m = s00;
-#pragma unroll
-      for (int b = 0; b < ATT_TOKENS; ++b) { if (b >= nt) S[u][b] = -INFINITY; m = fmaxf(m, S[u][b]); }
-      const float e0 = __expf(s00 - m);
-      float sum = e0;
-#pragma unroll
-      for (int b = 0; b < ATT_TOKENS; ++b) { S[u][b] = __expf(S[u][b] - m); sum += S[u][b]; }
-      const float inv = __fdividef(1.f, sum);
-      p0[u] = e0 * inv;
-#pragma unroll
-      for (int b = 0; b < ATT_TOKENS; ++b) S[u][b] *= inv;
     }
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
       float ph[TU];
 #pragma unroll
-      for (int u = 0; u < TU; ++u) ph[u] = __shfl_sync(0xffffffffu, p0[u], gb | (4 * h));
+      for (int u = 0; u < TU; ++u) ph[u] = __shfl_sync(0xffffffffu, pw[u >> 2][0], gb | (4 * h) | (u & 3));
 #pragma unroll
       for (int u = 0; u < TU; ++u) fma4(acc[u], ph[u], *reinterpret_cast<const float4*>(&ms.U0c[u][h][4 * s]));
     }
@@ -422,25 +445,20 @@ __device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* 
       for (int h = 0; h < NH; ++h) {
         float ph[TU];
 #pragma unroll
-        for (int u = 0; u < TU; ++u) ph[u] = __shfl_sync(0xffffffffu, S[u][b], gb | (4 * h));   // weight 0 for b >= nt
+        for (int u = 0; u < TU; ++u) ph[u] = __shfl_sync(0xffffffffu, pw[u >> 2][1 + b], gb | (4 * h) | (u & 3));   // weight 0 for b >= nt
 #pragma unroll
         for (int u = 0; u < TU; ++u) fma4(acc[u], ph[u], ub[h]);
       }
     }
     load_tok(0, c, q, nb, Lh);
-    float ss[TU];
 #pragma unroll
-    for (int u = 0; u < TU; ++u)
-      ss[u] = fmaf(acc[u][3], acc[u][3], fmaf(acc[u][2], acc[u][2], fmaf(acc[u][1], acc[u][1], acc[u][0] * acc[u][0])));
+    for (int ug = 0; ug < 2; ++ug) {
+      float r[4];
+      ln_rstd4(&acc[4 * ug], lane, r);
 #pragma unroll
-    for (int o = 1; o < 16; o <<= 1)
+      for (int u4 = 0; u4 < 4; ++u4)
 #pragma unroll
-      for (int u = 0; u < TU; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
-#pragma unroll
-    for (int u = 0; u < TU; ++u) {
-      const float r = rsqrtf(ss[u] * (1.f / D) + 1e-5f);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[u][i] *= r;
+        for (int i = 0; i < 4; ++i) acc[4 * ug + u4][i] *= r[u4];
     }
   }
   // ---- item tokens a >= 1 (token data of a + 1 is fetched while a is being combined)
@@ -450,23 +468,17 @@ __device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* 
     load_tok(min(a + 1, nt - 1), c2, q2, nb2, L2);
 #pragma unroll
     for (int ug = 0; ug < 2; ++ug) {
-      float w[4], y[4][4], ss[4];
+      float d[4], y[4][4];
 #pragma unroll
-      for (int u4 = 0; u4 < 4; ++u4) w[u4] = dot4(q, *reinterpret_cast<const float4*>(&ms.ku[4 * ug + u4][4 * s]));
+      for (int u4 = 0; u4 < 4; ++u4) d[u4] = dot4(q, *reinterpret_cast<const float4*>(&ms.ku[4 * ug + u4][4 * s]));
+      const float w = __fdividef(1.f, 1.f + __expf(Lh - quad_scatter4(d, ql)));      // sigmoid(s_a0 - L_ah) of user 4 ug + ql
 #pragma unroll
-      for (int u4 = 0; u4 < 4; ++u4) w[u4] += __shfl_xor_sync(0xffffffffu, w[u4], 1);
-#pragma unroll
-      for (int u4 = 0; u4 < 4; ++u4) w[u4] += __shfl_xor_sync(0xffffffffu, w[u4], 2);
-#pragma unroll
-      for (int u4 = 0; u4 < 4; ++u4) {
-        w[u4] = __fdividef(1.f, 1.f + __expf(Lh - w[u4]));           // sigmoid(s_a0 - L_ah)
-        y[u4][0] = c.x; y[u4][1] = c.y; y[u4][2] = c.z; y[u4][3] = c.w;
-      }
+      for (int u4 = 0; u4 < 4; ++u4) { y[u4][0] = c.x; y[u4][1] = c.y; y[u4][2] = c.z; y[u4][3] = c.w; }
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
         float wh[4];
 #pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) wh[u4] = __shfl_sync(0xffffffffu, w[u4], gb | (4 * h));
+        for (int u4 = 0; u4 < 4; ++u4) wh[u4] = __shfl_sync(0xffffffffu, w, gb | (4 * h) | u4);
 #pragma unroll
         for (int u4 = 0; u4 < 4; ++u4) {
           const float4 uv = *reinterpret_cast<const float4*>(&ms.U0c[4 * ug + u4][h][4 * s]);
@@ -474,19 +486,12 @@ __device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* 
           y[u4][2] = fmaf(wh[u4], uv.z - nb[h].z, y[u4][2]); y[u4][3] = fmaf(wh[u4], uv.w - nb[h].w, y[u4][3]);
         }
       }
+      float r[4];
+      ln_rstd4(y, lane, r);
 #pragma unroll
       for (int u4 = 0; u4 < 4; ++u4)
-        ss[u4] = fmaf(y[u4][3], y[u4][3], fmaf(y[u4][2], y[u4][2], fmaf(y[u4][1], y[u4][1], y[u4][0] * y[u4][0])));
 #pragma unroll
-      for (int o = 1; o < 16; o <<= 1)
-#pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) ss[u4] += __shfl_xor_sync(0xffffffffu, ss[u4], o);
-#pragma unroll
-      for (int u4 = 0; u4 < 4; ++u4) {
-        const float r = rsqrtf(ss[u4] * (1.f / D) + 1e-5f);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[4 * ug + u4][i] = fmaf(r, y[u4][i], acc[4 * ug + u4][i]);
-      }
+        for (int i = 0; i < 4; ++i) acc[4 * ug + u4][i] = fmaf(r[u4], y[u4][i], acc[4 * ug + u4][i]);
     }
     c = c2; q = q2; Lh = L2;
 #pragma unroll
