@@ -588,10 +588,10 @@ score_fused_kernel(const __grid_constant__ Params p) {
 
   // attention: register budget per warpgroup.  640 threads are launched with 96 registers each and setmaxnreg can
   // only move registers inside that pool (61 440): the MMA / top-K warpgroup drops to 40, the two front-end
-  // warpgroups take 120, the epilogue warpgroups keep 96  (2*128*120 + 128*40 + 2*128*96 = 60 416).
+  // warpgroups take 128, the epilogue warpgroups drop to 88  (2*128*128 + 128*40 + 2*128*88 = 60 416).
   // (setmaxnreg sits at the top of each warpgroup's branch so that ptxas allocates per role).
   if (warp < 4 || (ATT && warp >= 16)) {
-    if (ATT) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    if (ATT) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     // =============================================================== front end
     // attention: warpgroup A (warps 0-3) builds the per-unit user constants and the first half of every tile,
     // warpgroup B (warps 16-19) the second half; named barriers 2 / 3 fence the user constants between units.
@@ -928,6 +928,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
    }
   } else {
     // =============================================================== epilogue groups (warps 8-15)
+    if (ATT) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     const int grp = (warp - 8) >> 2;                 // 0: even layer-1 chunks, first half of layer 2, layer 3
     const int q = warp & 3;                          // TMEM lane quarter this warp may touch
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
