@@ -121,6 +121,72 @@ def attention_fusion(sd, feats, num_heads, dt, return_token_sum=False):
     return z.mean(axis=0)
 
 
+def attention_token_sum_split(sd, feats, num_heads, dt=np.float64, r16=None):
+    """The attention fusion of src/models/layers.py:135-164 restated in the split form the fused kernel uses
+    (csrc/score_tc.cu: item_attn_kernel / attn_user_setup / attn_half_tile): everything that involves only item
+    tokens is folded into per-item quantities, the user column enters each item row through one sigmoid weight,
+    every stored vector is centred over d so LayerNorm needs no mean.  Returns sum over tokens of the normalised
+    rows (before the LayerNorm affine and the 1/M).  ``r16``: optional rounding of the stored value blocks (item
+    C / Nbar / U, user U0), used to study 16-bit storage of the records (measured: halves the load/store traffic of
+    the front end but the conversions make it issue-bound, no net gain -- the kernel keeps fp32 records);
+    None = exact, equal to attention_fusion(return_token_sum=True)."""
+    M = len(feats)
+    B, D = feats[0].shape
+    dh = D // num_heads
+    r16 = r16 or (lambda a: a)
+    w_in = sd["fusion_layer.attention.in_proj_weight"].astype(dt)
+    b_in = sd["fusion_layer.attention.in_proj_bias"].astype(dt)
+    w_o = sd["fusion_layer.attention.out_proj.weight"].astype(dt)
+    b_o = sd["fusion_layer.attention.out_proj.bias"].astype(dt)
+    scale = 1.0 / math.sqrt(dh)
+    centre = lambda a: a - a.mean(axis=-1, keepdims=True)
+
+    def qkv(x):
+        y = x @ w_in.T + b_in
+        return y[:, :D], y[:, D:2 * D], y[:, 2 * D:]
+
+    def per_head_out(v):                       # U[h] = W_o[:, head h] v_h  -> (B, heads, D)
+        return np.stack([v[:, h * dh:(h + 1) * dh] @ w_o[:, h * dh:(h + 1) * dh].T for h in range(num_heads)], axis=1)
+
+    head_dot = lambda a, b: np.stack([(a[:, h * dh:(h + 1) * dh] * b[:, h * dh:(h + 1) * dh]).sum(1) for h in range(num_heads)], 1)
+    # per-user constants
+    eu = feats[0]
+    qu, ku, vu = qkv(eu)
+    U0c = r16(centre(per_head_out(vu)))
+    C0c = centre(eu + b_o)
+    S00 = head_dot(qu, ku) * scale
+    # per-item records
+    nt = M - 1
+    xs = feats[1:]
+    q, k, v = zip(*[qkv(x) for x in xs])
+    U = [per_head_out(vb) for vb in v]
+    rec = []
+    for a in range(nt):
+        s = np.stack([head_dot(q[a] * scale, k[b]) for b in range(nt)], 2)            # (B, heads, nt)
+        m = s.max(2, keepdims=True)
+        e = np.exp(s - m)
+        L = (m + np.log(e.sum(2, keepdims=True)))[:, :, 0]
+        pn = e / e.sum(2, keepdims=True)
+        Nbar = sum(pn[:, :, b:b + 1] * U[b] for b in range(nt))
+        C = xs[a] + b_o + Nbar.sum(1)
+        rec.append(dict(C=r16(centre(C)), Nbar=r16(centre(Nbar)), U=r16(centre(U[a])), q=q[a] * scale, k=k[a] * scale, L=L))
+    rstd = lambda y: 1.0 / np.sqrt((y * y).mean(1, keepdims=True) + 1e-5)            # y is centred by construction
+    # user-token row
+    S0 = np.stack([head_dot(qu, rec[b]["k"]) for b in range(nt)], 2)                  # (B, heads, nt)
+    m = np.maximum(S00, S0.max(2))
+    e0 = np.exp(S00 - m); eb = np.exp(S0 - m[:, :, None])
+    inv = 1.0 / (e0 + eb.sum(2))
+    y0 = C0c + ((e0 * inv)[:, :, None] * U0c).sum(1)
+    for b in range(nt):
+        y0 = y0 + ((eb[:, :, b] * inv)[:, :, None] * rec[b]["U"]).sum(1)
+    acc = y0 * rstd(y0)
+    for a in range(nt):
+        w = 1.0 / (1.0 + np.exp(rec[a]["L"] - head_dot(rec[a]["q"], ku)))
+        y = rec[a]["C"] + (w[:, :, None] * (U0c - rec[a]["Nbar"])).sum(1)
+        acc = acc + y * rstd(y)
+    return acc
+
+
 def prediction_layout(sd, use_batch_norm: bool) -> Tuple[List[int], int]:
     """Indices of the hidden Linears and of the output Linear inside
     ``prediction_network`` (src/models/multimodal.py:371-386)."""
@@ -419,6 +485,7 @@ def forward_pairs_lowp(sd, cfg, user_idx, item_idx, tag_idx, vis=None, txt=None,
         # folds the LayerNorm affine and the mean into layer 1: W1' = W1 diag(ln_w / M) (rounded), b1' = b1 + W1 ln_b.
         M = len(feats)
         g = sd["fusion_layer.norm.weight"].astype(dt); beta = sd["fusion_layer.norm.bias"].astype(dt)
+        # (attention_token_sum_split restates the kernel's split evaluation order; with exact storage it equals this)
         h = rnd(attention_fusion(sd, feats, int(cfg.get("num_attention_heads", 4)), dt, return_token_sum=True))
         ws = list(ws); bs = list(bs)
         bs[0] = bs[0] + ws[0] @ beta
