@@ -538,10 +538,11 @@ score_fused_kernel(const __grid_constant__ Params p) {
   // ------------------------------------------------------------------ setup
   if (!ATT) for (int i = threadIdx.x; i < H1 + H2 + H3 + H3; i += NT) ms.b1[i] = p.bias[i];   // b1,b2,b3,w4 are contiguous
   // epilogue constants: shared memory, or (attention) the kernel-parameter constant bank
-  const float* const cb1 = ATT ? p.bias_c : ms.b1;
-  const float* const cb2 = ATT ? p.bias_c + H1 : ms.b2;
-  const float* const cb3 = ATT ? p.bias_c + H1 + H2 : ms.b3;
-  const float* const cw4 = ATT ? p.bias_c + H1 + H2 + H3 : ms.w4;
+  // (expressions, not variables: a pointer kept live across the whole kernel costs the epilogue registers)
+#define PXR_CB1 (ATT ? p.bias_c : ms.b1)
+#define PXR_CB2 (ATT ? p.bias_c + H1 : ms.b2)
+#define PXR_CB3 (ATT ? p.bias_c + H1 + H2 : ms.b3)
+#define PXR_CW4 (ATT ? p.bias_c + H1 + H2 + H3 : ms.w4)
   if (threadIdx.x == 0) {
     ms.b4 = ATT ? p.bias_c[H1 + H2 + H3 + H3] : p.bias[H1 + H2 + H3 + H3];
     ms.q_tail = 0; ms.q_head = 0;
@@ -937,21 +938,22 @@ score_fused_kernel(const __grid_constant__ Params p) {
     uint32_t d1ph = 0, reset_ph = 0;                 // d1ph: phase bits of chunk buffers grp (bit 0) and grp + 2 (bit 1)
     uint32_t h1use0 = 0, h1use1 = 0;                 // concat: uses so far of chunk buffers grp and grp + 2
     int T = 0;
-    Unit prev; prev.ntiles = 0; prev.row_lo = prev.row_hi = 0; prev.g = prev.s = 0;
-    int prev_t = 0; int64_t prev_ubase = 0; bool have_prev = false;
+    // what the deferred layer-3 epilogue needs to know about the previous tile, kept small (the loop below is short
+    // on registers): this thread's item row (-1: padding row or no such user) and two flags
+    int64_t prev_row = -1; int prev_flags = 0; bool have_prev = false;      // flags: 1 = first tile of its unit, 2 = last
 
     auto do_e2 = [&](int Tp) {                       // H2 half `grp` of tile Tp
       ptx::mbar_wait(BAR(BAR_D2_FULL), Tp & 1);
       ptx::tc_fence_after();
       const uint32_t c0 = MP::TM_D2 + grp * 128;
-      epi_pack64<FMT>(tl + c0, tl + c0, cb2 + grp * 128);
-      epi_pack64<FMT>(tl + c0 + 64, tl + c0 + 32, cb2 + grp * 128 + 64);
+      epi_pack64<FMT>(tl + c0, tl + c0, PXR_CB2 + grp * 128);
+      epi_pack64<FMT>(tl + c0 + 64, tl + c0 + 32, PXR_CB2 + grp * 128 + 64);
       ptx::tc_wait_st();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(BAR(BAR_H2_FULL0 + grp), 0);
     };
-    auto do_e3 = [&](int Tp, const Unit& un, int t, int64_t ubase, bool last_of_unit) {
+    auto do_e3 = [&](int Tp, int64_t row, bool last_of_unit) {
       ptx::mbar_wait(BAR(BAR_D3_FULL), Tp & 1);
       ptx::tc_fence_after();
       float z = ms.b4;
@@ -961,8 +963,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
         ptx::tmem_ld32(tl + MP::TM_D3 + h * 64, v0);
         ptx::tmem_ld32(tl + MP::TM_D3 + h * 64 + 32, v1);
         ptx::tc_wait_ld();
-        const float4* b3v = reinterpret_cast<const float4*>(cb3 + h * 64);
-        const float4* w4v = reinterpret_cast<const float4*>(cw4 + h * 64);
+        const float4* b3v = reinterpret_cast<const float4*>(PXR_CB3 + h * 64);
+        const float4* w4v = reinterpret_cast<const float4*>(PXR_CW4 + h * 64);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float4 b = b3v[i], wv = w4v[i];
@@ -977,9 +979,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(BAR(BAR_D3_EMPTY), 0);
       float y = pxr_apply_final(z, p.final_act);
-      const int64_t row = un.row_lo + (int64_t)t * TI + rj;
-      if (p.item_missing && row < un.row_hi && p.item_missing[row]) y = 0.f;
-      const bool ok = row < un.row_hi && (ubase + ru) < p.n_users && !((ms.seen_mask[Tp & 3][ru] >> rj) & 1u);
+      if (p.item_missing && row >= 0 && p.item_missing[row]) y = 0.f;
+      const bool ok = row >= 0 && !((ms.seen_mask[Tp & 3][ru] >> rj) & 1u);
       if (ok && y >= *reinterpret_cast<volatile float*>(&ms.thr[ru])) {
         const uint32_t gidx = (uint32_t)(p.item_base + row);
         const unsigned long long e = ((unsigned long long)pxr_ord(y) << 32) | ((unsigned long long)ru << 28) |
@@ -994,9 +995,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
       }
     };
     auto prev_e3 = [&]() {
-      const bool last = (prev_t == prev.ntiles - 1);
-      if (prev_t == 0 && (T - 1) > 0) { ptx::mbar_wait(BAR(BAR_UNIT_RESET), reset_ph); reset_ph ^= 1; }
-      do_e3(T - 1, prev, prev_t, prev_ubase, last);
+      if ((prev_flags & 1) && (T - 1) > 0) { ptx::mbar_wait(BAR(BAR_UNIT_RESET), reset_ph); reset_ph ^= 1; }
+      do_e3(T - 1, prev_row, (prev_flags & 2) != 0);
     };
     // layer-1 chunk ci (0..3) of this group for the current tile: chunk c = 2 ci + grp in buffer c % 4
     auto do_l1 = [&](int ci) {
@@ -1005,7 +1005,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
       if (GATED) {
         ptx::mbar_wait(BAR(BAR_D1_FULL0 + b), (d1ph >> (ci & 1)) & 1u); d1ph ^= 1u << (ci & 1);
         ptx::tc_fence_after();
-        epi_pack64<FMT>(tl + MP::h1buf(b), tl + MP::h1buf(b), cb1 + c * 64);
+        epi_pack64<FMT>(tl + MP::h1buf(b), tl + MP::h1buf(b), PXR_CB1 + c * 64);
       } else {
         const int buf = T & 1;
         if (ci == 0) ptx::mbar_wait(BAR(BAR_PI_FULL0 + buf), (T >> 1) & 1);          // this tile's item partials landed
@@ -1041,7 +1041,12 @@ score_fused_kernel(const __grid_constant__ Params p) {
             if (grp == 0 && ci == (GATED ? 0 : 1)) prev_e3();
           }
         }
-        prev = un; prev_t = t; prev_ubase = ubase; have_prev = true;
+        {
+          const int64_t row = un.row_lo + (int64_t)t * TI + rj;
+          prev_row = (row < un.row_hi && (ubase + ru) < p.n_users) ? row : -1;
+          prev_flags = (t == 0 ? 1 : 0) | (t == un.ntiles - 1 ? 2 : 0);
+          have_prev = true;
+        }
       }
     }
     if (have_prev) {

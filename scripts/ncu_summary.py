@@ -4,6 +4,8 @@
   ncu_summary.py launches <launches.csv> <out.json>     per-kernel totals / share of the profiled run
   ncu_summary.py full <raw.csv> <out.json> [kernel-substring]   key counters of one `--set full` capture
                  (raw.csv = `ncu -i x.ncu-rep --page raw --csv`)
+  ncu_summary.py traffic <raw.csv> <fusion> <users_per_launch> <items_per_rank> <source-label>
+                 add / replace the DRAM bytes of that launch shape in profiles/ncu_traffic.json (bench.py: roofline.traffic)
 """
 import csv
 import json
@@ -76,8 +78,27 @@ def full(path, out, sub=None):
             print(k, v)
 
 
+def traffic(path, fusion, users, items, label):
+    from pathlib import Path
+    rows = list(csv.reader(open(path, newline="")))
+    hdr, r = rows[0], rows[2]
+    d = {h: v for h, v in zip(hdr, r)}
+    u = {h: v for h, v in zip(hdr, rows[1])}
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = sum(float(d[k].replace(",", "")) * mult[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    out = Path(__file__).resolve().parent.parent / "profiles" / "ncu_traffic.json"
+    j = json.loads(out.read_text()) if out.exists() else {"note": "", "captures": []}
+    j["captures"] = [c for c in j["captures"] if not (c["fusion"] == fusion and c["users_per_launch"] == int(users) and c["items_per_rank"] == int(items))]
+    j["captures"].append({"fusion": fusion, "users_per_launch": int(users), "items_per_rank": int(items),
+                          "dram_bytes_per_launch": int(tot), "source": label})
+    out.write_text(json.dumps(j, indent=1))
+    print(fusion, users, items, int(tot))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:7])
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
