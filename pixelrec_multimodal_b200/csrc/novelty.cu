@@ -36,7 +36,13 @@ __global__ void __launch_bounds__(32 * NOV_WARPS) novelty_kernel(
   for (int64_t ub = u0; ub < u1; ub += 32) {
     const int nb = (int)min((int64_t)32, u1 - ub);
     const int32_t* src = topk + ub * k_stride;
-    for (int i = lane; i < nb * k_stride; i += 32) L[(i / k_stride) * ld + (i % k_stride)] = src[i];
+    for (int i0 = lane; i0 < nb * k_stride; i0 += 32 * 8) {          // 8 independent loads per lane in flight
+      int32_t v[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) { const int i = i0 + 32 * m; if (i < nb * k_stride) v[m] = src[i]; }
+#pragma unroll
+      for (int m = 0; m < 8; ++m) { const int i = i0 + 32 * m; if (i < nb * k_stride) L[(i / k_stride) * ld + (i % k_stride)] = v[m]; }
+    }
     __syncwarp();
     if (lane < nb) {
       const int32_t* rec = L + lane * ld;

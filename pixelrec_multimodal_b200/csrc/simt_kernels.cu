@@ -475,11 +475,21 @@ __global__ void __launch_bounds__(32 * MERGE_MAX_WARPS) merge_topk_kernel(const 
   unsigned long long* bufA = merge_smem + (size_t)warp * (n_shards + half_lists) * k;   // n_shards lists
   unsigned long long* bufB = bufA + (size_t)n_shards * k;                               // ceil(n_shards / 2) lists
   for (int64_t u = (int64_t)blockIdx.x * warps_per_block + warp; u < n_users; u += (int64_t)gridDim.x * warps_per_block) {
-    for (int s = 0; s < n_shards; ++s) {
-      const int64_t off = ((int64_t)s * n_users + u) * k;
+    // stage the S lists: the loads of 8 elements per lane are issued together (the copy is latency-bound otherwise)
+    // stage the S lists, 4 shards (8 independent loads per lane) at a time; no integer divisions in the loops
+    for (int s0 = 0; s0 < n_shards; s0 += 4) {
       for (int j = lane; j < k; j += 32) {
-        const int32_t id = idx_in[off + j];
-        bufA[s * k + j] = id < 0 ? 0ull : pxr_key(scores_in[off + j], (uint32_t)id);
+        int32_t id[4]; float sc[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          if (s0 + m < n_shards) {
+            const int64_t off = ((int64_t)(s0 + m) * n_users + u) * k + j;
+            id[m] = idx_in[off]; sc[m] = scores_in[off];
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (s0 + m < n_shards) bufA[(s0 + m) * k + j] = id[m] < 0 ? 0ull : pxr_key(sc[m], (uint32_t)id[m]);
       }
     }
     __syncwarp();
@@ -487,18 +497,19 @@ __global__ void __launch_bounds__(32 * MERGE_MAX_WARPS) merge_topk_kernel(const 
     int n = n_shards;
     while (n > 1) {
       const int pairs = n / 2;
-      for (int t = lane; t < pairs * k; t += 32) {
-        const int pr = t / k, r = t % k;
+      for (int pr = 0; pr < pairs; ++pr) {
         const unsigned long long* A = src + (2 * pr) * k;
         const unsigned long long* B = A + k;
-        int lo = 0, hi = r;                      // i = number of the first r outputs that come from A (both lists hold k keys)
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (A[mid] > B[r - mid - 1]) lo = mid + 1; else hi = mid;
+        for (int r = lane; r < k; r += 32) {
+          int lo = 0, hi = r;                    // i = number of the first r outputs that come from A (both lists hold k keys)
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (A[mid] > B[r - mid - 1]) lo = mid + 1; else hi = mid;
+          }
+          const int i = lo, j = r - lo;
+          const unsigned long long a = i < k ? A[i] : 0ull, b2 = j < k ? B[j] : 0ull;
+          dst[pr * k + r] = a > b2 ? a : b2;
         }
-        const int i = lo, j = r - lo;
-        const unsigned long long a = i < k ? A[i] : 0ull, b2 = j < k ? B[j] : 0ull;
-        dst[pr * k + r] = a > b2 ? a : b2;
       }
       if (n & 1) for (int j = lane; j < k; j += 32) dst[pairs * k + j] = src[(n - 1) * k + j];
       __syncwarp();
@@ -606,6 +617,7 @@ __global__ void __launch_bounds__(METRIC_THREADS) metrics_user_kernel(const int3
 // tasks.py:733-747).  Lane partial sums are reduced in a fixed order; blocks / warps own fixed user ranges
 // => deterministic result.
 #define METRIC_WARPS 4
+template <int NKS>     // cut-offs kept in registers (2 covers the usual @10 / @50; 8 = PXR_MAX_KS): occupancy
 __global__ void __launch_bounds__(32 * METRIC_WARPS) metrics_warp_kernel(const int32_t* __restrict__ topk, int k_stride,
                                                                          int64_t n_users, int64_t users_per_warp,
                                                                          const int64_t* __restrict__ gt_indptr,
@@ -618,9 +630,9 @@ __global__ void __launch_bounds__(32 * METRIC_WARPS) metrics_warp_kernel(const i
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = k_stride | 1;
   int32_t* L = lists[warp];
-  double sums[PXR_MAX_KS][METRIC_COLS];
+  double sums[NKS][METRIC_COLS];
 #pragma unroll
-  for (int a = 0; a < PXR_MAX_KS; ++a)
+  for (int a = 0; a < NKS; ++a)
 #pragma unroll
     for (int c = 0; c < METRIC_COLS; ++c) sums[a][c] = 0.0;
   const int64_t w = (int64_t)blockIdx.x * METRIC_WARPS + warp;
@@ -628,7 +640,13 @@ __global__ void __launch_bounds__(32 * METRIC_WARPS) metrics_warp_kernel(const i
   for (int64_t ub = u0; ub < u1; ub += 32) {
     const int nb = (int)min((int64_t)32, u1 - ub);
     const int32_t* src = topk + ub * k_stride;
-    for (int i = lane; i < nb * k_stride; i += 32) L[(i / k_stride) * ld + (i % k_stride)] = src[i];
+    for (int i0 = lane; i0 < nb * k_stride; i0 += 32 * 8) {          // 8 independent loads per lane in flight
+      int32_t v[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) { const int i = i0 + 32 * m; if (i < nb * k_stride) v[m] = src[i]; }
+#pragma unroll
+      for (int m = 0; m < 8; ++m) { const int i = i0 + 32 * m; if (i < nb * k_stride) L[(i / k_stride) * ld + (i % k_stride)] = v[m]; }
+    }
     __syncwarp();
     if (lane < nb) {
       const int64_t g0 = gt_indptr[ub + lane], g1 = gt_indptr[ub + lane + 1];
@@ -645,7 +663,7 @@ __global__ void __launch_bounds__(32 * METRIC_WARPS) metrics_warp_kernel(const i
         double dcg = 0.0;
         unsigned long long rest = hit;
 #pragma unroll
-        for (int a = 0; a < PXR_MAX_KS; ++a) {
+        for (int a = 0; a < NKS; ++a) {
           if (a < ks.n) {
             const int k = ks.k[a];
             const unsigned long long km = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
@@ -674,7 +692,7 @@ __global__ void __launch_bounds__(32 * METRIC_WARPS) metrics_warp_kernel(const i
   for (int a = 0; a < PXR_MAX_KS; ++a)
 #pragma unroll
     for (int c = 0; c < METRIC_COLS; ++c) {
-      double v = a < ks.n ? sums[a][c] : 0.0;
+      double v = (a < NKS && a < ks.n) ? sums[a < NKS ? a : 0][c] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0) acc[warp][a * METRIC_COLS + c] = v;
@@ -712,8 +730,12 @@ int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_user
     blocks = std::min<int64_t>(blocks, (int64_t)n_sm * 16);      // never more than the workspace holds (one row per 128 users)
     const int64_t warps = blocks * METRIC_WARPS;
     const int64_t upw = (n_users + warps - 1) / warps;
-    metrics_warp_kernel<<<(unsigned)blocks, 32 * METRIC_WARPS, 0, st>>>(topk_idx, k_stride, n_users, upw, gt_indptr, gt_idx, mk,
-                                                                       discount, ideal, (double*)ws);
+    if (n_ks <= 2)
+      metrics_warp_kernel<2><<<(unsigned)blocks, 32 * METRIC_WARPS, 0, st>>>(topk_idx, k_stride, n_users, upw, gt_indptr, gt_idx, mk,
+                                                                            discount, ideal, (double*)ws);
+    else
+      metrics_warp_kernel<PXR_MAX_KS><<<(unsigned)blocks, 32 * METRIC_WARPS, 0, st>>>(topk_idx, k_stride, n_users, upw, gt_indptr, gt_idx,
+                                                                                     mk, discount, ideal, (double*)ws);
   } else {
     metrics_user_kernel<<<(unsigned)blocks, METRIC_THREADS, 0, st>>>(topk_idx, k_stride, n_users, gt_indptr, gt_idx, mk,
                                                                      discount, ideal, (double*)ws);
