@@ -1,0 +1,46 @@
+"""bench.py output contract (one JSON line with the keys the driver reads): the CPU reference arm here,
+the B200 arm on the GPU box (small configs[0] workload so it takes seconds)."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+REPO = Path(__file__).resolve().parent.parent
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e"}
+
+
+def _run(args, timeout=600):
+    p = subprocess.run([sys.executable, str(REPO / "bench.py"), *args], capture_output=True, text=True, timeout=timeout,
+                       env=dict(os.environ, OMP_NUM_THREADS="4"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, p.stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_json_contract():
+    d = _run(["--impl", "reference", "--config", "A", "--steps", "1", "--warmup", "0"])
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["vs_baseline"] is None and "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.gpu
+def test_b200_arm_json_contract():
+    d = _run(["--config", "A", "--steps", "2", "--warmup", "3", "--user-block", "256", "--cpu-seconds", "1"])
+    assert BASE_KEYS | {"roofline", "cpu_baseline", "clocks", "gpu_launches"} <= set(d) and "impl" not in d
+    assert d["n_gpus"] == 1 and d["dtype"] == "bf16" and d["data"] == "synthetic" and d["scaling"] == "weak"
+    assert d["config"]["kernel_path"] == "tcgen05" and d["gpu_launches"] >= 2
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and 0 < r["frac"] < 1.5 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["kernel_launches"] == 2 and 0.0 < r["kernel_share_of_step"] <= 1.0
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == 256 * 50 * 8
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

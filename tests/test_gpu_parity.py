@@ -585,3 +585,40 @@ def test_tcgen05_full_size_properties(fusion):
         a = {int(x): float(y) for x, y in zip(i[u], s[u])}
         b = {int(x): float(y) for x, y in zip(i2[u], s2[u])}
         assert max(abs(a[c] - b[c]) for c in common.tolist()) <= TC_BF16_TOL
+
+
+def test_merge_and_metrics_full_size_properties():
+    """BASELINE-scale inputs (131 072 users x 8 shards x 50; 1 M users for the metrics) through size-independent
+    properties: the merge of a partition equals the merge of its coarser partition (associativity), merging one
+    list is the identity, every output list is sorted by (score desc, index asc); metric sums are additive over
+    user blocks and invariant under a permutation of the users."""
+    from pixelrec_multimodal_b200.engine import merge_topk, ranking_metric_sums
+    g = torch.Generator(device="cuda").manual_seed(5)
+    S, n, k = 8, 131072, 50
+    sc = torch.randn((S, n, k), device="cuda", generator=g).sort(dim=2, descending=True).values
+    ix = (torch.rand((S, n, k), device="cuda", generator=g) * 40000).to(torch.int32).sort(dim=2).values
+    ix = ix + (torch.arange(S, device="cuda", dtype=torch.int32) * 50000)[:, None, None]     # disjoint, ascending shards
+    ms, mi = merge_topk(sc, ix)
+    assert torch.all(ms[:, :-1] >= ms[:, 1:])
+    tie = ms[:, :-1] == ms[:, 1:]
+    assert torch.all(mi[:, :-1][tie] < mi[:, 1:][tie])
+    a_s, a_i = merge_topk(sc[:4], ix[:4]); b_s, b_i = merge_topk(sc[4:], ix[4:])
+    cs_, ci_ = merge_topk(torch.stack([a_s, b_s]), torch.stack([a_i, b_i]))
+    assert torch.equal(cs_, ms) and torch.equal(ci_, mi)
+    one_s, one_i = merge_topk(sc[:1], ix[:1])
+    assert torch.equal(one_s, sc[0]) and torch.equal(one_i, ix[0])
+    # metrics
+    nu, ni = 1 << 20, 100000
+    topk = (torch.rand((nu, k), device="cuda", generator=g) * ni).to(torch.int32)
+    gt_idx = (torch.rand((nu,), device="cuda", generator=g) * ni).to(torch.int32)
+    topk[::7, 3] = gt_idx[::7]                                                              # plant hits
+    indptr = torch.arange(nu + 1, device="cuda", dtype=torch.int64)
+    total = ranking_metric_sums(topk, indptr, gt_idx, [10, 50])
+    half = nu // 2
+    parts = ranking_metric_sums(topk[:half], indptr[:half + 1], gt_idx[:half], [10, 50]) + \
+        ranking_metric_sums(topk[half:], indptr[half:] - half, gt_idx[half:], [10, 50])
+    assert np.allclose(total, parts, rtol=1e-12, atol=0)
+    perm = torch.randperm(nu, device="cuda", generator=g)
+    shuffled = ranking_metric_sums(topk[perm], indptr, gt_idx[perm], [10, 50])
+    assert np.allclose(total, shuffled, rtol=1e-12, atol=0)
+    assert total[0][3] >= nu // 7 and total[1][3] >= total[0][3]                          # hit-rate sums: planted hits, @50 >= @10
