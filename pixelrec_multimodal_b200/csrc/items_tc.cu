@@ -191,10 +191,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3x_kernel(const __grid_constan
         ptx::tc_wait_ld();
         if (row < p.M) {
           const float* b = p.bias + nt * p.NT + n0;
+          const int ncol = min(32, p.NT - n0);           // NT is a multiple of 16: the last chunk may be half full
           if (p.mode == OUT_F32_ACT) {
             float* o = p.out_f + row * p.ldo + nt * p.NT + n0;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
+              if (i >= ncol) break;
               float4 r;
               r.x = pxr_apply_act(__uint_as_float(v[i]) + b[i], p.act);
               r.y = pxr_apply_act(__uint_as_float(v[i + 1]) + b[i + 1], p.act);
