@@ -66,8 +66,24 @@ class TableDataset:
         self.feature_cache = cache
 
 
+def distributed_context(device: str):
+    """(world, rank, device) -- under ``torchrun`` (WORLD_SIZE > 1) the NCCL process group is initialised and every
+    rank takes the GPU LOCAL_RANK; the catalogue is then split into contiguous item shards, one per rank."""
+    import os
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 1, 0, device
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    return world, dist.get_rank(), f"cuda:{local}"
+
+
 def build_recommender(cfg: Dict, checkpoint: Optional[str], cache_dir: str, interactions_csv: str, device: str = "cuda:0",
-                      n_tags: Optional[int] = None):
+                      n_tags: Optional[int] = None, shard=None):
     import pandas as pd
     import torch
     from . import FastMultimodalRecommender, FastRecommender
@@ -95,7 +111,11 @@ def build_recommender(cfg: Dict, checkpoint: Optional[str], cache_dir: str, inte
         model.load_state_dict(sd, strict=False)
     dev = torch.device(device)
     store = cache.to_store(dev, order=[str(i) for i in ds.item_encoder.classes_])
-    rec = FastRecommender(model, ds, dev, item_features=store)
+    item_range = None
+    if shard is not None:                                   # (world, rank): contiguous item shard of this rank
+        from .sharding import shard_range
+        item_range = shard_range(len(ds.item_encoder.classes_), shard[0], shard[1])
+    rec = FastRecommender(model, ds, dev, item_features=store, item_range=item_range)
     return rec, ds
 
 
@@ -151,17 +171,27 @@ def cmd_evaluate(args) -> Dict:
     from . import FullCatalogueEvaluator, SampledRetrievalEvaluator
     cfg = load_config(args.config)
     top_k = args.top_k or cfg["recommendation"]["top_k"]
-    rec, ds = build_recommender(cfg, args.checkpoint, args.cache, args.interactions, args.device)
+    world, rank, device = distributed_context(args.device)
+    if world > 1 and args.use_sampling:
+        raise SystemExit("--use_sampling scores explicit candidates: run it on one GPU (no item-axis sharding)")
+    rec, ds = build_recommender(cfg, args.checkpoint, args.cache, args.interactions, device,
+                                shard=(world, rank) if world > 1 else None)
     test = pd.read_csv(args.test_data, dtype={"user_id": str, "item_id": str})
     ks = sorted(set([top_k] + [int(k) for k in (args.ks or [])]))
+    sharded = None
+    if world > 1:
+        from .sharding import ShardedTopK
+        sharded = ShardedTopK(lambda users, k, fs: rec.recommend_all(users, top_k=k, filter_seen=fs))
     if args.use_sampling:
         ev = SampledRetrievalEvaluator(rec, test, top_k=top_k, ks=ks, num_negatives=args.num_negatives,
                                        sampling_strategy=args.sampling_strategy, seed=args.seed,
                                        keep_predictions=bool(args.save_predictions))
     else:
         ev = FullCatalogueEvaluator(rec, test, top_k=top_k, ks=ks, filter_seen=cfg["recommendation"]["filter_seen"],
-                                    keep_predictions=bool(args.save_predictions))
+                                    keep_predictions=bool(args.save_predictions), sharded=sharded)
     results = ev.evaluate(novelty=True) if (args.novelty and not args.use_sampling) else ev.evaluate()
+    if rank != 0:                                           # every rank holds the same results; rank 0 writes them
+        return results
     results_dir = Path(cfg["results_dir"])
     if args.save_predictions and "predictions" in results:          # evaluate.py:417-426
         preds = results.pop("predictions")

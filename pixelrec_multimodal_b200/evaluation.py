@@ -92,7 +92,15 @@ class FullCatalogueEvaluator:
     ``top_k`` (plus ``by_k`` with every requested cut-off)."""
 
     def __init__(self, recommender, test_data, top_k: int = 50, ks: Optional[Sequence[int]] = None,
-                 filter_seen: bool = True, keep_predictions: bool = False, num_workers: int = 0):
+                 filter_seen: bool = True, keep_predictions: bool = False, num_workers: int = 0,
+                 sharded=None, user_block: int = 32768):
+        """``sharded``: a ``sharding.ShardedTopK`` when ``recommender`` holds one item-axis shard per rank
+        (``torch.distributed`` initialised): the per-shard lists of every user block are exchanged and merged, each
+        rank computes the metric sums of its slice of the block, and ONE all-reduce of the (n_ks, 7) float64 sums
+        closes the evaluation."""
+        self.sharded = sharded
+        self.user_block = int(user_block)
+        self._metric_sums = ranking_metric_sums
         if num_workers and num_workers > 1:
             # the reference forks worker processes holding the model (tasks.py:546-561);
             # a CUDA context cannot be forked
@@ -138,11 +146,40 @@ class FullCatalogueEvaluator:
         sub_ix = np.concatenate([ix[ip[u]:ip[u + 1]] for u in self.users]).astype(np.int32) if len(self.users) and sub_ip[-1] else np.zeros(1, np.int32)
         return beyond_accuracy_metrics(topk_idx[:, :self.top_k], si, iif, n_pop, sub_ip, sub_ix)
 
+    def _evaluate_sharded(self, kmax: int):
+        """Item-sharded ranks in lock step; returns (scores, idx) of all users (every rank holds the merged lists) and
+        ``by_k`` from all-reduced metric sums."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(self.sharded.group), dist.get_rank(self.sharded.group)
+        n = len(self.users)
+        blocks = [self.users[i:i + self.user_block] for i in range(0, n, self.user_block)]
+        sums = np.zeros((len(self.ks), 7))
+        outs_s, outs_i, row = [], [], 0
+        for (s, i), blk in zip(self.sharded.recommend_blocks(blocks, kmax, self.filter_seen), blocks):
+            per = (len(blk) + world - 1) // world               # this rank's slice of the block
+            lo, hi = min(len(blk), rank * per), min(len(blk), (rank + 1) * per)
+            if hi > lo:
+                ip = self.gt_indptr[row + lo:row + hi + 1]
+                sums += self._metric_sums(i[lo:hi], torch.from_numpy(ip - ip[0]),
+                                          torch.from_numpy(self.gt_idx[ip[0]:ip[-1]] if ip[-1] > ip[0] else np.zeros(1, np.int32)), self.ks)
+            outs_s.append(s); outs_i.append(i); row += len(blk)
+        t = torch.from_numpy(sums).to(outs_i[0].device if outs_i else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.sharded.group)
+        sums = t.cpu().numpy()
+        by_k = {}
+        for rowv, k in zip(sums, self.ks):
+            by_k[k] = {c: (float(v) / n if n else 0.0) for c, v in zip(_COLS, rowv)}
+            by_k[k]["num_users_evaluated"] = n
+        return (torch.cat(outs_s) if outs_s else None), (torch.cat(outs_i) if outs_i else None), by_k
+
     def evaluate(self, novelty: bool = False) -> Dict:
         r = self.recommender
         kmax = max(self.ks)
-        scores, idx = r.recommend_all(self.users, top_k=kmax, filter_seen=self.filter_seen)
-        by_k = ranking_metrics(idx, self.gt_indptr, self.gt_idx, self.ks)
+        if self.sharded is not None:
+            scores, idx, by_k = self._evaluate_sharded(kmax)
+        else:
+            scores, idx = r.recommend_all(self.users, top_k=kmax, filter_seen=self.filter_seen)
+            by_k = ranking_metrics(idx, self.gt_indptr, self.gt_idx, self.ks)
         res = {k: v for k, v in by_k[self.top_k].items() if k != "avg_ndcg_list_ideal_at_k"}
         res["evaluation_method"] = "full_evaluation"
         res["by_k"] = by_k

@@ -164,6 +164,34 @@ outs = list(st.recommend_blocks(blocks, K, False))
 assert len(outs) == 3
 ps, pi = torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
 assert torch.equal(pi, i) and torch.equal(ps, s)
+# sharded evaluation: every rank scores its shard, metric sums of disjoint user slices, one all-reduce
+import pandas as pd
+from pixelrec_multimodal_b200.evaluation import FullCatalogueEvaluator
+class _Rec:
+    user_index = {f"u{u}": u for u in range(NU)}
+    item_index = {f"i{j}": j for j in range(NI)}
+rng2 = np.random.default_rng(11)
+test = pd.DataFrame([(f"u{u}", f"i{int(j)}") for u in range(NU) for j in rng2.choice(NI, 2, replace=False)], columns=["user_id", "item_id"])
+ev = FullCatalogueEvaluator(_Rec(), test, top_k=K, ks=[3, K], filter_seen=False, sharded=st, user_block=4)
+def cpu_metric_sums(topk, gt_indptr, gt_idx, ks):      # K5 restated with the oracle (no GPU here)
+    out = np.zeros((len(ks), 7))
+    ip, gi = gt_indptr.numpy(), gt_idx.numpy()
+    for r_ in range(topk.shape[0]):
+        pos = set(int(x) for x in gi[ip[r_]:ip[r_ + 1]])
+        for a, k in enumerate(sorted(ks)):
+            recs = [int(x) for x in topk[r_][:k].tolist() if x >= 0]
+            m = orc.retrieval_metrics([recs], [pos], k)
+            out[a, :6] += [m["avg_precision_at_k"], m["avg_recall_at_k"], m["avg_f1_at_k"], m["avg_hit_rate_at_k"], m["avg_ndcg_at_k"], m["avg_mrr"]]
+    return out
+ev._metric_sums = cpu_metric_sums
+res = ev.evaluate()
+recs_all = [[int(x) for x in i[u].tolist() if x >= 0] for u in range(NU)]
+pos_all = [set(int(x) for x in ev.gt_idx[ev.gt_indptr[j]:ev.gt_indptr[j + 1]]) for j in range(NU)]
+for k in (3, K):
+    want = orc.retrieval_metrics([r_[:k] for r_ in recs_all], pos_all, k)
+    for key in ("avg_precision_at_k", "avg_recall_at_k", "avg_ndcg_at_k", "avg_mrr"):
+        assert abs(res["by_k"][k][key] - want[key]) < 1e-12, (rank, k, key, res["by_k"][k][key], want[key])
+assert res["num_users_evaluated"] == NU
 dist.barrier(); dist.destroy_process_group()
 print("OK", rank)
 """

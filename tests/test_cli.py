@@ -86,3 +86,41 @@ def test_cli_end_to_end(tmp_path, fusion):
                    "--save_predictions", "p.json"])
     assert es["evaluation_method"] == "negative_sampling" and (tmp_path / "res" / "p.json").exists()
     assert es["avg_hit_rate_at_k"] >= ev["avg_hit_rate_at_k"]                         # 101 candidates instead of 300
+
+
+@pytest.mark.gpu
+def test_cli_sharded_evaluate_two_gpus(tmp_path):
+    """`torchrun --nproc-per-node 2 -m pixelrec_multimodal_b200.cli evaluate`: item-axis shards, NCCL all-gather of the
+    per-shard lists, metric sums all-reduced == the single-GPU evaluation (needs two GPUs; skipped otherwise)."""
+    import os
+    import subprocess
+    import sys
+    import pandas as pd
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from pixelrec_multimodal_b200.packed_cache import write_packed_cache
+    from tests import _cases as cs
+    spec = syn.ModelSpec(n_users=300, n_items=1001, fusion_type="gated")
+    sd, feats = cs.make_workload(spec, syn.SEED + 43)
+    uids, iids = syn.user_ids(spec.n_users), syn.item_ids(spec.n_items)
+    write_packed_cache(tmp_path / "cache", iids, feats["tag_idx"], feats["vis"], feats["txt"], feats["num"])
+    indptr, idx, test_item = syn.make_histories(spec.n_users, spec.n_items, seed=5, lo=3, hi=20)
+    pd.DataFrame([(uids[u], iids[int(i)]) for u in range(spec.n_users) for i in idx[indptr[u]:indptr[u + 1]]],
+                 columns=["user_id", "item_id"]).to_csv(tmp_path / "train.csv", index=False)
+    pd.DataFrame([(uids[u], iids[int(test_item[u])]) for u in range(spec.n_users)], columns=["user_id", "item_id"]).to_csv(tmp_path / "test.csv", index=False)
+    torch.save({"model_state_dict": {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}}, tmp_path / "m.pth")
+    (tmp_path / "c.yaml").write_text(f"model:\n  fusion_type: gated\nrecommendation:\n  top_k: 50\nresults_dir: {tmp_path / 'res'}\n")
+    common = ["--config", str(tmp_path / "c.yaml"), "--checkpoint", str(tmp_path / "m.pth"), "--cache", str(tmp_path / "cache"),
+              "--interactions", str(tmp_path / "train.csv"), "--test_data", str(tmp_path / "test.csv"), "--ks", "10"]
+    one = cli.main(["evaluate", *common, "--output", "one.json"])
+    repo = str(__import__("pathlib").Path(__file__).resolve().parent.parent)
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", "-m", "pixelrec_multimodal_b200.cli", "evaluate", *common, "--output", "two.json"],
+                       capture_output=True, text=True, timeout=600, cwd=repo, env=dict(os.environ, PYTHONPATH=repo))
+    assert p.returncode == 0, p.stderr[-3000:]
+    two = json.loads((tmp_path / "res" / "two.json").read_text())
+    for k in ("10", "50"):
+        for key in ("avg_precision_at_k", "avg_recall_at_k", "avg_hit_rate_at_k", "avg_ndcg_at_k", "avg_mrr"):
+            assert abs(two["by_k"][k][key] - one["by_k"][k][key]) <= 1e-12, (k, key)
+    assert two["num_users_evaluated"] == spec.n_users == one["num_users_evaluated"]
