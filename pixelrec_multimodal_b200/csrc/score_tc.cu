@@ -31,7 +31,7 @@
 //   * Seen items (filter_seen, recommender.py:88-90): the user's ascending history is walked with a
 //     cursor in step with the ascending item sweep -> a 16-bit mask per (user, tile); no per-pair search.
 //   * Warp roles (16 warps): 0-3 front end (A1 tiles / Pi staging + Pu), 4 issues every MMA (one thread
-//     of the leader CTA) and owns TMEM/TMA setup, 5 top-K, 8-11 / 12-15 two epilogue groups.
+//     of the leader CTA) and owns TMEM/TMA setup, 5 / 6 top-K (four users each), 8-11 / 12-15 two epilogue groups.
 //     All hand-offs are mbarriers; tcgen05.commit multicasts completion to both CTAs.
 #include <algorithm>
 #include <cstddef>
@@ -85,7 +85,7 @@ struct MiscT {
   unsigned long long queue[QC];
   float thr[TU];
   uint32_t seen_mask[4][TU];
-  uint32_t q_tail, q_head;
+  uint32_t q_tail[2], q_head[2];                     // two candidate queues: users 0-3 -> top-K warp 5, users 4-7 -> warp 6
   uint32_t tmem_base;
   float b4;
   unsigned long long bars[N_BARS];
@@ -514,7 +514,8 @@ __device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* 
 // ---------------------------------------------------------------------------------------------
 // FUS selects the front end.  GATED below means "layer 1 runs on the tensor pipe from an A1 tile in shared memory"
 // (gated and attention fusion: the fused vector depends on the pair); concat feeds layer-1 partial sums instead.
-template <int FUS, int FMT>
+// TK2: two top-K warps (short units, where list updates are a visible share of the work) instead of one.
+template <int FUS, int FMT, bool TK2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads<FUS>(), 1)
 score_fused_kernel(const __grid_constant__ Params p) {
   constexpr int NT = n_threads<FUS>();
@@ -545,7 +546,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
 #define PXR_CW4 (ATT ? p.bias_c + H1 + H2 + H3 : ms.w4)
   if (threadIdx.x == 0) {
     ms.b4 = ATT ? p.bias_c[H1 + H2 + H3 + H3] : p.bias[H1 + H2 + H3 + H3];
-    ms.q_tail = 0; ms.q_head = 0;
+    ms.q_tail[0] = ms.q_tail[1] = 0; ms.q_head[0] = ms.q_head[1] = 0;
     ptx::mbar_init(BAR(BAR_W), 1);
     ptx::mbar_init(BAR(BAR_A_FULL), ATT ? 16 : 8);        // one arrival per front-end warp of both CTAs
     ptx::mbar_init(BAR(BAR_A_EMPTY), 1);
@@ -560,7 +561,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
     ptx::mbar_init(BAR(BAR_D3_FULL), 1);
     ptx::mbar_init(BAR(BAR_D3_EMPTY), 8);
     ptx::mbar_init(BAR(BAR_UNIT_DONE), 4);
-    ptx::mbar_init(BAR(BAR_UNIT_RESET), 1);
+    ptx::mbar_init(BAR(BAR_UNIT_RESET), TK2 ? 2 : 1);   // one arrival per active top-K warp
     ptx::fence_mbar_init();
   }
   for (int i = threadIdx.x; i < TU * KCAP; i += NT) (&ms.list[0][0])[i] = 0ull;
@@ -856,8 +857,13 @@ score_fused_kernel(const __grid_constant__ Params p) {
         issue_m3(NT - 1);
       }
     }
-   } else if (warp == 5) {
-    // =============================================================== top-K warp
+   } else if (warp == 5 || (warp == 6 && TK2)) {
+    // =============================================================== top-K warp(s)
+    // TK2: warp 5 owns users 0-3 and warp 6 users 4-7, one queue each (see launch_fused for when)
+    const int qh = warp - 5;
+    constexpr uint32_t QM = (TK2 ? QC / 2 : QC) - 1;      // queue capacities are powers of two
+    const int u_lo = TK2 ? 4 * qh : 0, u_hi = TK2 ? 4 * qh + 4 : TU;
+    unsigned long long* const queue = ms.queue + qh * (QC / 2);
     uint32_t head = 0, done_ph = 0;
     for (int w = pair; w < p.n_units; w += n_pairs) {
       const Unit un = decode_unit(p, w);
@@ -866,13 +872,13 @@ score_fused_kernel(const __grid_constant__ Params p) {
       bool finished = false;
       while (true) {
         unsigned long long e = 0ull;
-        if (lane == 0) e = *reinterpret_cast<volatile unsigned long long*>(&ms.queue[head % QC]);
+        if (lane == 0) e = *reinterpret_cast<volatile unsigned long long*>(&queue[head & QM]);
         e = __shfl_sync(0xffffffffu, e, 0);
         if (e != 0ull) {
           __syncwarp();
           if (lane == 0) {
-            *reinterpret_cast<volatile unsigned long long*>(&ms.queue[head % QC]) = 0ull;
-            *reinterpret_cast<volatile uint32_t*>(&ms.q_head) = head + 1;
+            *reinterpret_cast<volatile unsigned long long*>(&queue[head & QM]) = 0ull;
+            *reinterpret_cast<volatile uint32_t*>(&ms.q_head[qh]) = head + 1;
           }
           ++head;
           const int u = (int)((e >> 28) & 7ull);
@@ -898,7 +904,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
         }
         if (finished) {
           uint32_t tail = 0;
-          if (lane == 0) tail = *reinterpret_cast<volatile uint32_t*>(&ms.q_tail);
+          if (lane == 0) tail = *reinterpret_cast<volatile uint32_t*>(&ms.q_tail[qh]);
           tail = __shfl_sync(0xffffffffu, tail, 0);
           if (head == tail) break;
           continue;
@@ -910,7 +916,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
         else __nanosleep(PXR_TOPK_IDLE_NS);    // idle: do not burn issue slots / power while the queue is empty
       }
       // write the K best of every user of this unit, then reset for the next unit
-      for (int u = 0; u < TU; ++u) {
+      for (int u = u_lo; u < u_hi; ++u) {
         const int64_t ord = ubase + u;
         for (int i = lane; i < KCAP; i += 32) {
           const unsigned long long kv = ms.list[u][i];
@@ -985,9 +991,11 @@ score_fused_kernel(const __grid_constant__ Params p) {
         const uint32_t gidx = (uint32_t)(p.item_base + row);
         const unsigned long long e = ((unsigned long long)pxr_ord(y) << 32) | ((unsigned long long)ru << 28) |
                                      (unsigned long long)(IDX_MASK - gidx);
-        const uint32_t slot = atomicAdd(&ms.q_tail, 1u);
-        while (slot - *reinterpret_cast<volatile uint32_t*>(&ms.q_head) >= (uint32_t)QC) __nanosleep(64);
-        *reinterpret_cast<volatile unsigned long long*>(&ms.queue[slot % QC]) = e;
+        const int qh = TK2 ? (ru >> 2) : 0;
+        constexpr uint32_t qcap = TK2 ? QC / 2 : QC;
+        const uint32_t slot = atomicAdd(&ms.q_tail[qh], 1u);
+        while (slot - *reinterpret_cast<volatile uint32_t*>(&ms.q_head[qh]) >= qcap) __nanosleep(64);
+        *reinterpret_cast<volatile unsigned long long*>(&ms.queue[qh * (QC / 2) + (slot & (qcap - 1))]) = e;
       }
       if (last_of_unit) {
         __syncwarp();
@@ -1265,10 +1273,10 @@ struct FastWeights {       // lives in h->fast_w; attention: followed by one Use
   float s1[D];             // attention: ln_w / M, the per-input scale folded into the layer-1 image
 };
 
-template <int FUS, int FMT>
-static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_t st) {
-  auto kern = score_fused_kernel<FUS, FMT>;
-  const int slot = 2 * FUS + FMT;
+template <int FUS, int FMT, bool TK2>
+static int launch_fused_tk(pxr_handle* h, const Params& p, int n_pairs, cudaStream_t st) {
+  auto kern = score_fused_kernel<FUS, FMT, TK2>;
+  const int slot = 2 * FUS + FMT + (TK2 ? 16 : 0);
   if (!(h->tc_attr_set & (1u << slot))) {
     PXR_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Map<FUS>::SMEM));
     h->tc_attr_set |= (1u << slot);
@@ -1279,6 +1287,14 @@ static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
   return PXR_OK;
+}
+
+// The number of list updates per user grows like K (1 + ln(n / K)) with the n item rows of a unit, most of them at its
+// start: below ~8 K rows per unit one inserting warp is the bottleneck (measured: 10 K items x 1 024 users 5.1 -> 3.5 ms with
+// two); for long units the second warp only costs the front end issue slots (-2.8 % on the gated headline config).
+template <int FUS, int FMT>
+static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_t st) {
+  return p.rows_per_split < 8192 ? launch_fused_tk<FUS, FMT, true>(h, p, n_pairs, st) : launch_fused_tk<FUS, FMT, false>(h, p, n_pairs, st);
 }
 
 }  // namespace tc
