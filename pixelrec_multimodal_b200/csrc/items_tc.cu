@@ -43,7 +43,8 @@ struct GemmParams {
   int64_t M; int K, N, NT;              // NT = columns per N tile (N % NT == 0, NT <= 256, NT % 16 == 0)
   const uint8_t* wimg;                  // [N / NT][chunks][2][NT x 128 B] swizzled hi / lo chunk images
   const float* bias;                    // [N]
-  int mode, act, fmt16;                 // OUT_F32_ACT: out_f[row * ldo + n] = act(acc + b); OUT_16: 16-bit, no act
+  int mode, act, fmt16;                 // OUT_F32_ACT: out_f[row * ldo + n] = act(acc + b) (act < 0: identity); OUT_16: 16-bit, no act
+  int n_store;                          // columns of each N tile that are stored (0 = all): padded outputs
   float* out_f; uint16_t* out_h; int64_t ldo;
   int n_stages;
 };
@@ -191,17 +192,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3x_kernel(const __grid_constan
         ptx::tc_wait_ld();
         if (row < p.M) {
           const float* b = p.bias + nt * p.NT + n0;
-          const int ncol = min(32, p.NT - n0);           // NT is a multiple of 16: the last chunk may be half full
+          const int ncol = min(32, (p.n_store ? p.n_store : p.NT) - n0);   // NT is a multiple of 16: the last chunk may be half full
           if (p.mode == OUT_F32_ACT) {
             float* o = p.out_f + row * p.ldo + nt * p.NT + n0;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               if (i >= ncol) break;
               float4 r;
-              r.x = pxr_apply_act(__uint_as_float(v[i]) + b[i], p.act);
-              r.y = pxr_apply_act(__uint_as_float(v[i + 1]) + b[i + 1], p.act);
-              r.z = pxr_apply_act(__uint_as_float(v[i + 2]) + b[i + 2], p.act);
-              r.w = pxr_apply_act(__uint_as_float(v[i + 3]) + b[i + 3], p.act);
+              r.x = __uint_as_float(v[i]) + b[i]; r.y = __uint_as_float(v[i + 1]) + b[i + 1];
+              r.z = __uint_as_float(v[i + 2]) + b[i + 2]; r.w = __uint_as_float(v[i + 3]) + b[i + 3];
+              if (p.act >= 0) { r.x = pxr_apply_act(r.x, p.act); r.y = pxr_apply_act(r.y, p.act); r.z = pxr_apply_act(r.z, p.act); r.w = pxr_apply_act(r.w, p.act); }
               *reinterpret_cast<float4*>(o + i) = r;
             }
           } else {
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3x_kernel(const __grid_constan
 // Weight W[N x K] (row stride ldw, first column k_off) -> per N tile, per K chunk: hi image | lo image, each NT rows of
 // 128 bytes in the swizzled K-major layout (16-byte chunk index XOR row-in-group); columns past K are zero.
 __global__ void split_weights_kernel(const float* __restrict__ W, int64_t ldw, int k_off, int N, int K, int NT,
-                                     uint8_t* __restrict__ img) {
+                                     uint8_t* __restrict__ img, int n_valid) {
   const int n_chunks = (K + KC - 1) / KC;
   const int64_t total = (int64_t)N * n_chunks * KC;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -240,7 +240,7 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int64_t ldw, i
     const int n = (int)(e / ((int64_t)KC * n_chunks));
     const int nt = n / NT, nl = n % NT;
     const int k = kc * KC + kin;
-    const float v = k < K ? W[(int64_t)n * ldw + k_off + k] : 0.f;
+    const float v = (k < K && n < n_valid) ? W[(int64_t)n * ldw + k_off + k] : 0.f;   // rows past n_valid: zero padding
     uint32_t hb, lb;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
     const float hi = __uint_as_float(hb);
@@ -358,6 +358,8 @@ int pxr_items_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
   const bool concat = c.fusion == PXR_FUSION_CONCAT;
   const int FD = (h->M - 1) * D;
   if (concat) total += pxr_align_up(itc::img_bytes(c.hidden[0], FD), 1024);
+  const bool gated = c.fusion == PXR_FUSION_GATED;
+  if (gated) total += pxr_align_up(itc::img_bytes(16, FD), 1024) + 1024;      // gate logits: 16 padded outputs + padded bias
   if (h->tc_items_w) { cudaFree(h->tc_items_w); h->tc_items_w = nullptr; }
   PXR_CUDA(h, cudaMalloc(&h->tc_items_w, total + 1024));
   uint8_t* cur = reinterpret_cast<uint8_t*>(h->tc_items_w);
@@ -365,18 +367,41 @@ int pxr_items_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
     h->tc_items_img[m] = nullptr;
     if (!h->has_mod[m]) continue;
     h->tc_items_img[m] = cur;
-    itc::split_weights_kernel<<<256, 256, 0, st>>>(h->proj[m][0].w, kdim[m], 0, D, kdim[m], itc::n_tile_for(D), cur);
+    itc::split_weights_kernel<<<256, 256, 0, st>>>(h->proj[m][0].w, kdim[m], 0, D, kdim[m], itc::n_tile_for(D), cur, D);
     h->launches++;
     cur += pxr_align_up(itc::img_bytes(D, kdim[m]), 1024);
   }
   h->tc_items_img[2] = nullptr;
   if (concat) {
     h->tc_items_img[2] = cur;
-    itc::split_weights_kernel<<<512, 256, 0, st>>>(h->mlp[0].w, h->mlp[0].k, D, c.hidden[0], FD, 256, cur);
+    itc::split_weights_kernel<<<512, 256, 0, st>>>(h->mlp[0].w, h->mlp[0].k, D, c.hidden[0], FD, 256, cur, c.hidden[0]);
     h->launches++;
+  }
+  h->tc_items_img[3] = nullptr; h->tc_gate_bias = nullptr;
+  if (gated) {
+    if (concat) cur += pxr_align_up(itc::img_bytes(c.hidden[0], FD), 1024);
+    h->tc_items_img[3] = cur;
+    itc::split_weights_kernel<<<64, 256, 0, st>>>(h->gate.w, (int64_t)h->M * D, D, 16, FD, 16, cur, h->M);
+    h->launches++;
+    cur += pxr_align_up(itc::img_bytes(16, FD), 1024);
+    h->tc_gate_bias = reinterpret_cast<float*>(cur);
+    PXR_CUDA(h, cudaMemsetAsync(cur, 0, 64, st));
+    PXR_CUDA(h, cudaMemcpyAsync(cur, h->gate.b, sizeof(float) * h->M, cudaMemcpyDeviceToDevice, st));
   }
   PXR_CUDA(h, cudaGetLastError());
   return PXR_OK;
+}
+
+// gated: item part of the gate logits, Wg[:, D:] . record + bg  (layers.py:207 split) -> [rows][8] fp32
+int pxr_launch_item_logit_tc(pxr_handle* h, int64_t n_rows, float* out, cudaStream_t st) {
+  const pxr_config& c = h->cfg;
+  const int D = c.embedding_dim, FD = (h->M - 1) * D;
+  itc::GemmParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.A = h->item_feats; gp.lda = FD; gp.M = n_rows; gp.K = FD; gp.N = 16; gp.NT = 16;
+  gp.wimg = h->tc_items_img[3]; gp.bias = h->tc_gate_bias;
+  gp.mode = itc::OUT_F32_ACT; gp.act = -1; gp.out_f = out; gp.ldo = 8; gp.n_store = 8;
+  return itc::launch_gemm(h, gp, st);
 }
 
 // K1 + K2 for n_rows items -> feats_out [rows][M-1][D] fp32 (same record as pxr_launch_items_simt)

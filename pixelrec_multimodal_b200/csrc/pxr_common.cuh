@@ -51,7 +51,8 @@ struct pxr_handle {
   void* fast_w = nullptr;     // bf16 swizzled operand images + fp32 vectors (see score_tc.cu)
   float tc_bias_host[1028];   // attention fast path: host copy of b1' b2 b3 w4 b4 (passed as kernel parameters)
   void* tc_items_w = nullptr;       // item precompute on the tensor pipe: hi / lo tf32 weight chunk images (items_tc.cu)
-  uint8_t* tc_items_img[3] = {nullptr, nullptr, nullptr};   // vision, language projections; concat layer-1 item columns
+  uint8_t* tc_items_img[4] = {nullptr, nullptr, nullptr, nullptr};   // vision, language projections; concat layer-1 item columns; gate logits
+  float* tc_gate_bias = nullptr;    // gate bias padded to 16
 
   // live timing of the dominant kernel (pxr_profile_*)
   bool profile = false;
@@ -242,6 +243,7 @@ int pxr_launch_items_tc(pxr_handle* h, const float* item_embedding, const int64_
                         const float* vis, const float* txt, const float* num, int64_t n_rows, int64_t item_base,
                         float* feats_out, cudaStream_t st);
 int pxr_launch_item_pi_tc(pxr_handle* h, int64_t n_rows, uint16_t* out, int fmt16, cudaStream_t st);
+int pxr_launch_item_logit_tc(pxr_handle* h, int64_t n_rows, float* out, cudaStream_t st);
 int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
                       const int64_t* seen_indptr, const int32_t* seen_idx, int32_t k, float* out_scores,
                       int32_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -1363,7 +1363,9 @@ size_t pxr_tc_item_bytes(const pxr_handle* h, int64_t n_rows) {
 
 int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t st) {
   if (n_rows == 0) return PXR_OK;
-  if (h->cfg.fusion == PXR_FUSION_GATED) {
+  if (h->cfg.fusion == PXR_FUSION_GATED && h->tc_items_img[3] && h->path == PXR_PATH_TCGEN05) {
+    return pxr_launch_item_logit_tc(h, n_rows, (float*)ws, st);                  // 3xTF32 GEMM on the tensor pipe (N = 6 padded to 16)
+  } else if (h->cfg.fusion == PXR_FUSION_GATED) {
     const int wpb = 8;
     tc::item_logit_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(h->item_feats, h->gate.w, h->gate.b, h->M,
                                                                                      n_rows, (float*)ws);
