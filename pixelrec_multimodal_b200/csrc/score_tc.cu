@@ -2,9 +2,9 @@
 //
 // Replace, for a block of users against a shard of the catalogue, the loop of reference
 // src/inference/recommender.py:97-106 around MultimodalRecommender.forward
-// (src/models/multimodal.py:528-610) for fusion_type 'gated' (src/models/layers.py:195-225) and
-// 'concatenate' (multimodal.py:583-584) with the default prediction MLP [512, 256, 128] -> 1
-// (multimodal.py:366-386).  One kernel template, two front ends.
+// (src/models/multimodal.py:528-610) for fusion_type 'gated' (src/models/layers.py:195-225),
+// 'concatenate' (multimodal.py:583-584) and 'attention' (layers.py:135-164) with the default prediction MLP
+// [512, 256, 128] -> 1 (multimodal.py:366-386).  One kernel template, three front ends.
 //
 // Design (DESIGN.md §5 has the derivation and the measurements):
 //   * One persistent CTA PAIR (cluster of 2, tcgen05 cta_group::2) per two SMs.  A tile is 256
@@ -19,6 +19,8 @@
 //               H1[c] = 16bit(relu(D1[c] + b1)) in place      (tcgen05.ld / cvt.relu / tcgen05.st)
 //       concat  H1[c] = 16bit(relu(Pu[user] + Pi[item]))      (CUDA cores straight into TMEM: layer 1 is
 //               split into per-user / per-item partials; Pi tiles staged by TMA bulk copies)
+//       attention  as gated, with A1 = sum over the 6 tokens of the LayerNormed attention rows (CUDA cores; the
+//               item-item part of the attention lives in per-item records, see "attention fusion front end" below)
 //       both    D2 += H1[c] . W2[:, c]^T                      (tcgen05.mma TS: A from TMEM, N=256)
 //               H2  = 16bit(relu(D2 + b2)) in place;  D3 = H2 . W3^T (TS, N=128, K=256)
 //               z   = w4 . relu(D3 + b3) + b4 ; score = final(z)   (layer-3 epilogue, CUDA cores)
@@ -31,7 +33,9 @@
 //   * Seen items (filter_seen, recommender.py:88-90): the user's ascending history is walked with a
 //     cursor in step with the ascending item sweep -> a 16-bit mask per (user, tile); no per-pair search.
 //   * Warp roles (16 warps): 0-3 front end (A1 tiles / Pi staging + Pu), 4 issues every MMA (one thread
-//     of the leader CTA) and owns TMEM/TMA setup, 5 / 6 top-K (four users each), 8-11 / 12-15 two epilogue groups.
+//     of the leader CTA) and owns TMEM/TMA setup, 5 top-K (plus 6 for short units, template switch TK2),
+//     8-11 / 12-15 two epilogue groups; attention adds a second front-end warpgroup (warps 16-19) and
+//     moves registers between the roles with setmaxnreg.
 //     All hand-offs are mbarriers; tcgen05.commit multicasts completion to both CTAs.
 #include <algorithm>
 #include <cstddef>
@@ -256,18 +260,6 @@ __device__ __forceinline__ void concat_h1_chunk(const uint8_t* pi_row, const uin
 __device__ __forceinline__ float4 ldg_stream(const float* p) {      // item records: read once per tile, keep them out of L1
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ float sum4_head(float v) {                // sum over the 4 lanes that share a head
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  return v;
-}
-__device__ __forceinline__ float sum16_item(float v) {               // sum over the 16 lanes that share an item
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
-  v += __shfl_xor_sync(0xffffffffu, v, 8);
   return v;
 }
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
