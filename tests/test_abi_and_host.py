@@ -210,3 +210,22 @@ def test_sharded_topk_world2_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "OK" in o
+
+
+def test_synthetic_generators_are_reproducible():
+    """every synthetic input is a pure function of (seed, stream name)."""
+    from pixelrec_multimodal_b200 import synthetic as syn
+    spec = syn.ModelSpec(n_users=50, n_items=70, fusion_type="gated")
+    a, b = syn.make_state_dict(spec, seed=5), syn.make_state_dict(spec, seed=5)
+    assert a.keys() == b.keys() and all(np.array_equal(a[k], b[k]) for k in a)
+    c = syn.make_state_dict(spec, seed=6)
+    assert any(not np.array_equal(a[k], c[k]) for k in a)
+    f1, f2 = syn.make_item_features(spec, seed=5), syn.make_item_features(spec, seed=5)
+    assert all(np.array_equal(f1[k], f2[k]) for k in f1)
+    assert abs(np.linalg.norm(f1["vis"], axis=1).mean() - 10.0) < 1e-3 and abs(np.linalg.norm(f1["txt"], axis=1).mean() - 1.0) < 1e-3
+    ip1, ix1, t1 = syn.make_histories(50, 70, seed=5, lo=3, hi=20)
+    ip2, ix2, t2 = syn.make_histories(50, 70, seed=5, lo=3, hi=20)
+    assert np.array_equal(ip1, ip2) and np.array_equal(ix1, ix2) and np.array_equal(t1, t2)
+    for u in range(50):                              # ascending, unique, the held-out test item is not in the history
+        h = ix1[ip1[u]:ip1[u + 1]]
+        assert np.all(np.diff(h) > 0) and int(t1[u]) not in set(h.tolist())
