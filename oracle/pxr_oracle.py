@@ -619,3 +619,39 @@ def novelty_metrics(rec_lists: Sequence[Sequence[int]], histories: Sequence[Set[
     m = lambda x: float(np.mean(x)) if x else 0.0
     return {"avg_self_information": m(a_si), "avg_iif": m(a_iif), "avg_catalog_coverage": m(a_cov),
             "avg_personalization": pers, "avg_personalized_novelty": m(a_pn)}
+
+
+# --------------------------------------------------------------------------
+# ranking task (--eval_task ranking)
+# --------------------------------------------------------------------------
+def ranking_task_metrics(users: Sequence[str], test_items: Sequence[Sequence[str]],
+                         score_fn, k: int) -> Dict[str, object]:
+    """TopKRankingEvaluator.evaluate (src/evaluation/tasks.py:776-901) as the direct per-user loop: the user's test
+    items are scored one by one (``get_item_score``), sorted by score with Python's stable descending sort
+    (:830), and every test item counts as relevant -- ranks are 1..n (:835-837), MRR is 1/ranks[0] (:845),
+    hit rate counts ranks <= k over len(test_items) (:848-849), NDCG is ``ndcg_tasks`` of the sorted list against
+    the SET of test items (:853-854; duplicates in the table shrink the ideal, not the gain).  ``users`` are in
+    ``groupby('user_id')`` order; ``score_fn(user, item) -> float``.  Means / population std as :877-893."""
+    per = {"avg_rank": [], "median_rank": [], "mrr": [], "hit_rate_at_k": [], "ndcg_at_k": []}
+    predictions = {}
+    for u, items in zip(users, test_items):
+        scored = [(str(i), float(score_fn(str(u), str(i)))) for i in items]
+        if not scored:
+            for v in per.values():
+                v.append(0.0)
+            continue
+        scored.sort(key=lambda x: x[1], reverse=True)
+        predictions[str(u)] = scored
+        ranks = list(range(1, len(scored) + 1))
+        per["avg_rank"].append(float(np.mean(ranks)))
+        per["median_rank"].append(float(np.median(ranks)))
+        per["mrr"].append(1.0 / ranks[0])
+        per["hit_rate_at_k"].append(sum(1 for r in ranks if r <= k) / len(items))
+        per["ndcg_at_k"].append(ndcg_tasks([i for i, _ in scored], set(str(i) for i in items), k))
+    out: Dict[str, object] = {}
+    for name, vals in per.items():
+        out[f"avg_{name}"] = float(np.mean(vals)) if vals else 0.0
+        out[f"std_{name}"] = float(np.std(vals)) if vals else 0.0
+    out["num_users_evaluated"] = len(users)
+    out["predictions"] = predictions
+    return out

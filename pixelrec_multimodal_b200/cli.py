@@ -168,12 +168,13 @@ def cmd_generate(args) -> Dict:
 # ----------------------------------------------------------------------------- evaluate
 def cmd_evaluate(args) -> Dict:
     import pandas as pd
-    from . import FullCatalogueEvaluator, SampledRetrievalEvaluator
+    from . import FullCatalogueEvaluator, RankingEvaluator, SampledRetrievalEvaluator
     cfg = load_config(args.config)
     top_k = args.top_k or cfg["recommendation"]["top_k"]
     world, rank, device = distributed_context(args.device)
-    if world > 1 and args.use_sampling:
-        raise SystemExit("--use_sampling scores explicit candidates: run it on one GPU (no item-axis sharding)")
+    ranking = args.eval_task == "ranking"
+    if world > 1 and (args.use_sampling or ranking):
+        raise SystemExit("--use_sampling / --eval_task ranking score explicit pairs: run them on one GPU (no item-axis sharding)")
     rec, ds = build_recommender(cfg, args.checkpoint, args.cache, args.interactions, device,
                                 shard=(world, rank) if world > 1 else None)
     test = pd.read_csv(args.test_data, dtype={"user_id": str, "item_id": str})
@@ -182,14 +183,16 @@ def cmd_evaluate(args) -> Dict:
     if world > 1:
         from .sharding import ShardedTopK
         sharded = ShardedTopK(lambda users, k, fs: rec.recommend_all(users, top_k=k, filter_seen=fs))
-    if args.use_sampling:
+    if ranking:                                             # evaluate.py:402-408: sampling is a retrieval-only switch
+        ev = RankingEvaluator(rec, test, top_k=top_k, keep_predictions=bool(args.save_predictions))
+    elif args.use_sampling:
         ev = SampledRetrievalEvaluator(rec, test, top_k=top_k, ks=ks, num_negatives=args.num_negatives,
                                        sampling_strategy=args.sampling_strategy, seed=args.seed,
                                        keep_predictions=bool(args.save_predictions))
     else:
         ev = FullCatalogueEvaluator(rec, test, top_k=top_k, ks=ks, filter_seen=cfg["recommendation"]["filter_seen"],
                                     keep_predictions=bool(args.save_predictions), sharded=sharded)
-    results = ev.evaluate(novelty=True) if (args.novelty and not args.use_sampling) else ev.evaluate()
+    results = ev.evaluate(novelty=True) if (args.novelty and not args.use_sampling and not ranking) else ev.evaluate()
     if rank != 0:                                           # every rank holds the same results; rank 0 writes them
         return results
     results_dir = Path(cfg["results_dir"])
@@ -198,9 +201,10 @@ def cmd_evaluate(args) -> Dict:
         p = results_dir / args.save_predictions
         p.parent.mkdir(parents=True, exist_ok=True)
         p.write_text(json.dumps({str(u): [{"item_id": str(i), "score": float(s)} for i, s in r] for u, r in preds.items()}, indent=2))
-    results["evaluation_metadata"] = {"task": "retrieval", "recommender_type": "fast_multimodal", "top_k": top_k,      # evaluate.py:429-434
+    results["evaluation_metadata"] = {"task": args.eval_task, "recommender_type": "fast_multimodal", "top_k": top_k,      # evaluate.py:429-434
                                       "test_file": args.test_data, "checkpoint_used": args.checkpoint}
-    results["by_k"] = {str(k): v for k, v in results["by_k"].items()}
+    if "by_k" in results:
+        results["by_k"] = {str(k): v for k, v in results["by_k"].items()}
     out = results_dir / args.output if not Path(args.output).is_absolute() else Path(args.output)
     out.parent.mkdir(parents=True, exist_ok=True)
     out.write_text(json.dumps(results, indent=2))
@@ -231,9 +235,11 @@ def make_parser() -> argparse.ArgumentParser:
     g.add_argument("--output", type=str, default="recommendations.json")
     g.set_defaults(fn=cmd_generate)
 
-    e = sub.add_parser("evaluate", help="scripts/evaluate.py (retrieval task) on the GPU path")
+    e = sub.add_parser("evaluate", help="scripts/evaluate.py (retrieval and ranking tasks) on the GPU path")
     common(e)
     e.add_argument("--test_data", type=str, required=True)
+    e.add_argument("--eval_task", type=str, default="retrieval", choices=["retrieval", "ranking"],
+                   help="retrieval: top-K lists against the test positives; ranking: order of each user's own test items (tasks.py:776-901)")
     e.add_argument("--use_sampling", action="store_true", help="positives + sampled negatives (the reference default protocol)")
     e.add_argument("--num_negatives", type=int, default=100)
     e.add_argument("--sampling_strategy", type=str, default="random")

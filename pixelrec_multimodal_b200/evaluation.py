@@ -250,3 +250,66 @@ class SampledRetrievalEvaluator(FullCatalogueEvaluator):
         if self.keep_predictions:
             res["predictions"] = preds
         return res
+
+
+class RankingEvaluator:
+    """The reference's ranking task (``scripts/evaluate.py --eval_task ranking``, ``TopKRankingEvaluator.evaluate``,
+    ``src/evaluation/tasks.py:776-901``) on the GPU path: every (user, test item) pair of the table is scored in one
+    batched ``pxr_score_pairs`` launch instead of one ``get_item_score`` forward per pair (:812-820); unknown users
+    or items score 0.0 like the reference call (``recommender.py:119-125``).  Inside a user the items are ordered by
+    score, descending and stable over the table order (Python's ``sort(reverse=True)``, :830), and every test item
+    is relevant, so the per-user values follow :835-854 -- ranks 1..n, MRR 1/ranks[0], hit rate = ranks <= K over
+    n, NDCG of the sorted list against the SET of test items.  Result keys, means and population standard
+    deviations as :877-897; ``predictions`` holds the sorted (item, score) lists (the reference stores the list
+    object it then sorts in place, :827-830).  Users appear in ``groupby('user_id')`` order of the string ids."""
+
+    def __init__(self, recommender, test_data, top_k: int = 50, keep_predictions: bool = True, num_workers: int = 0):
+        if num_workers and num_workers > 1:
+            raise ValueError("num_workers > 1 is not supported on the GPU path (a CUDA context cannot be forked)")
+        self.recommender = recommender
+        self.test_data = test_data
+        self.top_k = int(top_k)
+        self.keep_predictions = keep_predictions
+
+    def evaluate(self) -> Dict:
+        r = self.recommender
+        uid = self.test_data["user_id"].astype(str).to_numpy(dtype=object)
+        iid = self.test_data["item_id"].astype(str).to_numpy(dtype=object)
+        users, inv = np.unique(uid.astype(str), return_inverse=True)
+        order = np.argsort(inv, kind="stable")                       # rows grouped by user, table order inside a user
+        seg, items = inv[order], iid[order]
+        n_rows, n_users = len(items), len(users)
+        umap, imap = r.user_index, r.item_index
+        u_of_user = np.fromiter((umap.get(str(u), -1) for u in users), dtype=np.int64, count=n_users)
+        ui = u_of_user[seg] if n_rows else np.zeros(0, np.int64)
+        ii = np.fromiter((imap.get(str(i), -1) for i in items), dtype=np.int64, count=n_rows)
+        known = (ui >= 0) & (ii >= 0)
+        scores = np.zeros(n_rows, dtype=np.float32)                  # get_item_score -> 0.0 for unknown ids
+        if known.any():
+            scores[known] = r.score_pairs_batch(ui[known], ii[known]).cpu().numpy()
+        perm = np.lexsort((-scores, seg))                            # stable: ties keep the table order
+        cnt = np.bincount(seg, minlength=n_users).astype(np.int64) if n_rows else np.zeros(n_users, np.int64)
+        pair_codes = np.unique(np.stack([seg, np.unique(items.astype(str), return_inverse=True)[1]], 1), axis=0) if n_rows else np.zeros((0, 2), np.int64)
+        n_set = np.bincount(pair_codes[:, 0], minlength=n_users).astype(np.int64)   # len(set(test_items))
+        k = max(self.top_k, 0)
+        gains = np.concatenate([[0.0], np.cumsum(1.0 / np.log2(np.arange(1, k + 1) + 1.0))])   # left-to-right sums of :737-744
+        nf = cnt.astype(np.float64)
+        ideal = gains[np.minimum(n_set, k)]
+        per = {
+            "avg_rank": (nf + 1.0) / 2.0,                            # np.mean / np.median of 1..n
+            "median_rank": (nf + 1.0) / 2.0,
+            "mrr": np.ones(n_users),
+            "hit_rate_at_k": np.minimum(cnt, k) / nf,
+            "ndcg_at_k": np.divide(gains[np.minimum(cnt, k)], ideal, out=np.zeros(n_users), where=ideal > 0),
+        }
+        res: Dict = {}
+        for name, vals in per.items():
+            res[f"avg_{name}"] = float(np.mean(vals)) if n_users else 0.0
+            res[f"std_{name}"] = float(np.std(vals)) if n_users else 0.0
+        res["num_users_evaluated"] = int(n_users)
+        if self.keep_predictions:
+            s_sorted, i_sorted = scores[perm], items[perm]
+            bounds = np.concatenate([[0], np.cumsum(cnt)])
+            res["predictions"] = {str(users[j]): [(str(i_sorted[t]), float(s_sorted[t])) for t in range(bounds[j], bounds[j + 1])]
+                                  for j in range(n_users)}
+        return res

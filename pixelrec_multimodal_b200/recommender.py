@@ -269,6 +269,21 @@ class FastRecommender:
         items = torch.where(pos >= 0, torch.gather(cand, 1, pos.clamp_min(0).to(torch.int64)), torch.full_like(pos, -1))
         return s, items
 
+    def score_pairs_batch(self, user_indices, item_indices) -> torch.Tensor:
+        """Batched ``get_item_score`` (reference src/inference/recommender.py:112-141, one forward per (user, item)):
+        fp32 device tensor with the score of every (user index, global item index) pair, in ONE ``pxr_score_pairs``
+        launch.  Used by the ranking task (``evaluation.RankingEvaluator``)."""
+        eng = self.engine()
+        users = torch.as_tensor(user_indices, dtype=torch.int64, device=self.device)
+        items = torch.as_tensor(item_indices, dtype=torch.int64, device=self.device)
+        if users.shape != items.shape or users.dim() != 1:
+            raise ValueError("user_indices and item_indices must be 1-D and of equal length")
+        if items.numel() == 0:
+            return torch.empty(0, dtype=torch.float32, device=self.device)
+        if int(items.min()) < self.item_lo or int(items.max()) >= self.item_hi:
+            raise ValueError("items outside this recommender's item range")
+        return eng.score_pairs(self.model.user_embedding.weight.detach(), users, items - self.item_lo)
+
     # --------------------------------------------------------- reference API
     def get_recommendations(self, user_id: str, top_k: int = 10, filter_seen: bool = True,
                             candidates: Optional[List[str]] = None) -> List[Tuple[str, float]]:

@@ -16,8 +16,13 @@ def test_parser_mirrors_reference_flags():
     assert a.users == ["u1", "u2"] and a.output == "o.json" and a.sample_users is None and a.user_file is None
     a = p.parse_args(["evaluate", "--cache", "c", "--interactions", "i.csv", "--test_data", "t.csv", "--use_sampling"])
     assert a.use_sampling and a.num_negatives == 100 and a.sampling_strategy == "random" and a.output == "evaluation_results.json"
+    assert a.eval_task == "retrieval"                                                  # evaluate.py:242
+    a = p.parse_args(["evaluate", "--cache", "c", "--interactions", "i.csv", "--test_data", "t.csv", "--eval_task", "ranking"])
+    assert a.eval_task == "ranking"
     with pytest.raises(SystemExit):
         p.parse_args(["evaluate", "--cache", "c", "--interactions", "i.csv"])          # --test_data is required
+    with pytest.raises(SystemExit):
+        p.parse_args(["evaluate", "--cache", "c", "--interactions", "i.csv", "--test_data", "t.csv", "--eval_task", "other"])
 
 
 def test_config_defaults_and_yaml(tmp_path):
@@ -86,6 +91,12 @@ def test_cli_end_to_end(tmp_path, fusion):
                    "--save_predictions", "p.json"])
     assert es["evaluation_method"] == "negative_sampling" and (tmp_path / "res" / "p.json").exists()
     assert es["avg_hit_rate_at_k"] >= ev["avg_hit_rate_at_k"]                         # 101 candidates instead of 300
+    er = cli.main(["evaluate", *common, "--test_data", str(tmp_path / "test.csv"), "--eval_task", "ranking", "--output", "rk.json",
+                   "--save_predictions", "rp.json"])                                   # evaluate.py:242, 402-408
+    assert er["evaluation_metadata"]["task"] == "ranking" and er["num_users_evaluated"] == spec.n_users
+    assert er["avg_avg_rank"] == 1.0 and er["avg_mrr"] == 1.0 and er["avg_ndcg_at_k"] == 1.0   # one test item per user
+    rp = json.loads((tmp_path / "res" / "rp.json").read_text())
+    assert len(rp) == spec.n_users and rp[uids[3]][0]["item_id"] == iids[int(test_item[3])] and 0.0 < rp[uids[3]][0]["score"] < 1.0
 
 
 @pytest.mark.gpu
