@@ -452,12 +452,12 @@ int pxr_launch_topk_rows(pxr_handle* h, const float* scores, int64_t n_users, in
 }
 
 // ===========================================================================
-// K4: merge S per-shard top-K lists per user (rank by counting; keys distinct)
+// K4: merge S per-shard top-K lists per user (keys distinct; k <= 64: registers + shuffles, k > 64: shared memory)
 // ===========================================================================
 #define MERGE_MAX_KEYS 4096
 #define MERGE_MAX_WARPS 8
 
-// One warp per user.  Every per-shard list is already sorted by (score desc, index asc), so the S lists are merged
+// Shared-memory variant (k > 64).  One warp per user.  Every per-shard list is already sorted by (score desc, index asc), so the S lists are merged
 // pairwise in a tree, each 2-way merge keeping only the best k: output position r of a pair is found by a
 // merge-path binary search (log2 k steps) and all positions are independent, so lanes take r = lane, lane + 32, ...
 // Keys are the 64-bit composites of pxr_key (unique per item; 0 = padding, smallest), staged in shared memory.
@@ -525,10 +525,80 @@ __global__ void __launch_bounds__(32 * MERGE_MAX_WARPS) merge_topk_kernel(const 
   }
 }
 
+// Register variant for k <= 64 (every list fits a warp: slot j of a list lives in lane j & 31, register j >> 5).
+// No shared memory: the S lists are folded into one accumulator list by bitonic top-64 merges.  Both lists are
+// descending, so max(A[j], B[63 - j]) is a bitonic sequence that holds the best 64 keys of the union (B is
+// reversed by one lane-mirror shuffle and a register swap); six compare-exchange stages (distance 32 inside the
+// lane, 16..1 by shfl.xor) sort it again.  24 32-bit shuffles and ~60 integer instructions per 2-way merge instead
+// of k merge-path searches through shared memory; the loads of MERGE_GROUP lists (2 * MERGE_GROUP scores + indices
+// per lane) are issued together before the first merge, so a resident warp keeps 1.6 KB in flight at k = 50.
+#define MERGE_GROUP 4
+__device__ __forceinline__ unsigned long long merge_max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+__device__ __forceinline__ unsigned long long merge_min(unsigned long long a, unsigned long long b) { return a > b ? b : a; }
+
+__device__ __forceinline__ void merge_top64(unsigned long long& a0, unsigned long long& a1, unsigned long long b0,
+                                            unsigned long long b1, int lane) {
+  const unsigned long long r0 = __shfl_xor_sync(0xffffffffu, b1, 31);      // reversed B: slot lane      <- B[63 - lane]
+  const unsigned long long r1 = __shfl_xor_sync(0xffffffffu, b0, 31);      //             slot 32 + lane <- B[31 - lane]
+  unsigned long long x0 = merge_max(a0, r0), x1 = merge_max(a1, r1);
+  { const unsigned long long hi = merge_max(x0, x1), lo = merge_min(x0, x1); x0 = hi; x1 = lo; }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, x0, d), p1 = __shfl_xor_sync(0xffffffffu, x1, d);
+    const bool keep_max = (lane & d) == 0;                                  // descending: the lower lane keeps the larger key
+    x0 = keep_max ? merge_max(x0, p0) : merge_min(x0, p0);
+    x1 = keep_max ? merge_max(x1, p1) : merge_min(x1, p1);
+  }
+  a0 = x0; a1 = x1;
+}
+
+__global__ void __launch_bounds__(256) merge_topk_reg_kernel(const float* __restrict__ scores_in,
+                                                             const int32_t* __restrict__ idx_in, int n_shards,
+                                                             int64_t n_users, int k, float* __restrict__ out_scores,
+                                                             int32_t* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const bool in0 = lane < k, in1 = lane + 32 < k;
+  for (int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < n_users; u += warps) {
+    unsigned long long a0 = 0ull, a1 = 0ull;
+    for (int s0 = 0; s0 < n_shards; s0 += MERGE_GROUP) {
+      float sc[MERGE_GROUP][2]; int32_t id[MERGE_GROUP][2];
+#pragma unroll
+      for (int m = 0; m < MERGE_GROUP; ++m) {
+        id[m][0] = id[m][1] = -1; sc[m][0] = sc[m][1] = 0.f;
+        if (s0 + m < n_shards) {
+          const int64_t off = ((int64_t)(s0 + m) * n_users + u) * k + lane;
+          if (in0) { id[m][0] = __ldg(idx_in + off); sc[m][0] = __ldg(scores_in + off); }
+          if (in1) { id[m][1] = __ldg(idx_in + off + 32); sc[m][1] = __ldg(scores_in + off + 32); }
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < MERGE_GROUP; ++m) {
+        if (s0 + m < n_shards) {                                            // warp-uniform
+          const unsigned long long b0 = id[m][0] < 0 ? 0ull : pxr_key(sc[m][0], (uint32_t)id[m][0]);
+          const unsigned long long b1 = id[m][1] < 0 ? 0ull : pxr_key(sc[m][1], (uint32_t)id[m][1]);
+          if (s0 + m == 0) { a0 = b0; a1 = b1; } else merge_top64(a0, a1, b0, b1, lane);
+        }
+      }
+    }
+    if (in0) { out_scores[u * k + lane] = a0 ? pxr_key_score(a0) : -INFINITY; out_idx[u * k + lane] = a0 ? (int32_t)pxr_key_idx(a0) : -1; }
+    if (in1) { out_scores[u * k + lane + 32] = a1 ? pxr_key_score(a1) : -INFINITY; out_idx[u * k + lane + 32] = a1 ? (int32_t)pxr_key_idx(a1) : -1; }
+  }
+}
+
 int pxr_launch_merge(const float* scores_in, const int32_t* idx_in, int32_t n_shards, int64_t n_users, int32_t k,
                      float* out_scores, int32_t* out_idx, cudaStream_t st) {
   if ((int64_t)n_shards * k > MERGE_MAX_KEYS) return PXR_ERR_INVALID;
   if (n_users == 0) return PXR_OK;
+  if (k <= 64) {
+    int dev_ = 0, sms = 148;
+    cudaGetDevice(&dev_);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_);
+    const int64_t want_blocks = (n_users + 7) / 8;                          // 8 warps per block, one user per warp and pass
+    const unsigned nb = (unsigned)std::min<int64_t>(want_blocks, (int64_t)sms * 8 * 4);
+    merge_topk_reg_kernel<<<nb, 256, 0, st>>>(scores_in, idx_in, n_shards, n_users, k, out_scores, out_idx);
+    return cudaGetLastError() == cudaSuccess ? PXR_OK : PXR_ERR_CUDA;
+  }
   const size_t per_warp = (size_t)(n_shards + (n_shards + 1) / 2) * k * sizeof(unsigned long long);
   int wpb = (int)std::min<size_t>(MERGE_MAX_WARPS, (96 * 1024) / per_warp);
   if (wpb < 1) return PXR_ERR_INVALID;

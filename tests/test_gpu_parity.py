@@ -223,9 +223,11 @@ def test_merge_topk_with_ties():
         assert np.array_equal(gs[u].astype(np.float64), rs)
 
 
-@pytest.mark.parametrize("S,n,k", [(1, 5, 7), (3, 70, 50), (8, 300, 50), (5, 9, 64), (64, 3, 64), (2, 1, 1)])
+@pytest.mark.parametrize("S,n,k", [(1, 5, 7), (3, 70, 50), (8, 300, 50), (5, 9, 64), (64, 3, 64), (2, 1, 1), (9, 40, 33), (4, 17, 32),
+                                   (13, 2100, 50), (3, 11, 100), (7, 30, 65), (1, 4, 128)])
 def test_merge_topk_shapes(S, n, k):
-    """odd / large shard counts (tree of pairwise merges), ragged list tails, K up to 64: == oracle merge"""
+    """odd / large shard counts, ragged list tails; K <= 64 takes the register kernel (bitonic top-64 merges, groups of
+    4 lists), K > 64 the shared-memory tree of merge-path merges: == oracle merge"""
     from pixelrec_multimodal_b200.engine import merge_topk
     rng = np.random.default_rng(100 + S * n + k)
     sc = -np.sort(-np.round(rng.standard_normal((S, n, k)), 2).astype(np.float32), axis=2)
