@@ -7,6 +7,7 @@
 // The tcgen05 path (score_tc.cu) replaces K3g+K3t for the supported shapes; these
 // kernels remain the path for every other configuration and for explicit pairs.
 #include <algorithm>
+#include <climits>
 
 #include "pxr_common.cuh"
 
@@ -680,15 +681,17 @@ __global__ void __launch_bounds__(METRIC_THREADS) metrics_user_kernel(const int3
 }
 
 // Fast variant for lists of at most 64 entries.  A warp owns a contiguous range of users and takes them 32 at a
-// time: the 32 lists are contiguous in memory and are staged into shared memory with fully coalesced, independent
-// loads (the algorithmic 4 K bytes per user, many loads in flight); then lane t matches user t's list against that
-// user's positives (64-bit hit / valid masks) and does the float64 arithmetic (every cut-off is a popcount of the
+// time.  Their lists are one contiguous run of 32 k entries: the lanes stream it with coalesced loads
+// (METRIC_BATCH per lane in flight), each entry is compared with the positives of its user (held one user per
+// lane, fetched by a shuffle) and a match sets one bit of that user's 64-bit hit mask in shared memory.  Only users
+// with a hit have non-zero metrics: those lanes then do the float64 arithmetic (every cut-off is a popcount of the
 // hit mask; the discounted gain is summed left to right over the hit positions, the order of the reference loop,
-// tasks.py:733-747).  Lane partial sums are reduced in a fixed order; blocks / warps own fixed user ranges
-// => deterministic result.
+// tasks.py:733-747); everybody else adds exact zeros, i.e. nothing.  Lane partial sums are reduced in a fixed
+// order; blocks / warps own fixed user ranges => deterministic result.
 #define METRIC_WARPS 4
+#define METRIC_BATCH 8
 template <int NKS>     // cut-offs kept in registers (2 covers the usual @10 / @50; 8 = PXR_MAX_KS): occupancy
-__global__ void __launch_bounds__(32 * METRIC_WARPS) metrics_warp_kernel(const int32_t* __restrict__ topk, int k_stride,
+__global__ void __launch_bounds__(32 * METRIC_WARPS, (NKS <= 2 ? 8 : 2)) metrics_warp_kernel(const int32_t* __restrict__ topk, int k_stride,
                                                                          int64_t n_users, int64_t users_per_warp,
                                                                          const int64_t* __restrict__ gt_indptr,
                                                                          const int32_t* __restrict__ gt_idx, MetricKs ks,
@@ -696,10 +699,8 @@ __global__ void __launch_bounds__(32 * METRIC_WARPS) metrics_warp_kernel(const i
                                                                          const double* __restrict__ ideal,
                                                                          double* __restrict__ block_sums) {
   __shared__ double acc[METRIC_WARPS][PXR_MAX_KS * METRIC_COLS];
-  __shared__ int32_t lists[METRIC_WARPS][32 * 65];     // row stride k_stride | 1 (odd => conflict-free per-lane rows)
+  __shared__ unsigned long long hitmask[METRIC_WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ld = k_stride | 1;
-  int32_t* L = lists[warp];
   double sums[NKS][METRIC_COLS];
 #pragma unroll
   for (int a = 0; a < NKS; ++a)
@@ -707,28 +708,51 @@ __global__ void __launch_bounds__(32 * METRIC_WARPS) metrics_warp_kernel(const i
     for (int c = 0; c < METRIC_COLS; ++c) sums[a][c] = 0.0;
   const int64_t w = (int64_t)blockIdx.x * METRIC_WARPS + warp;
   const int64_t u0 = w * users_per_warp, u1 = min(n_users, u0 + users_per_warp);
+  const int step_u = 32 / k_stride, step_p = 32 % k_stride;          // element i + 32 belongs to user + step_u (+1), position + step_p (- k)
+  unsigned long long* hm = hitmask[warp];
   for (int64_t ub = u0; ub < u1; ub += 32) {
     const int nb = (int)min((int64_t)32, u1 - ub);
+    int64_t g0 = 0;                                    // lane t: positives of user ub + t
+    int npos = 0;
+    if (lane < nb) { g0 = gt_indptr[ub + lane]; npos = (int)(gt_indptr[ub + lane + 1] - g0); }
+    int max_pos = npos;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) max_pos = max(max_pos, __shfl_xor_sync(0xffffffffu, max_pos, o));
+    hm[lane] = 0ull;
+    __syncwarp();
+    // the nb lists are one contiguous run of nb * k_stride entries: lane l takes entries l, l + 32, ... (coalesced,
+    // METRIC_BATCH loads in flight), fetches the q-th positive of the entry's user from that user's lane and, on the
+    // rare match, sets bit `position` of the user's hit mask
+    const int n_el = nb * k_stride;
     const int32_t* src = topk + ub * k_stride;
-    for (int i0 = lane; i0 < nb * k_stride; i0 += 32 * 8) {          // 8 independent loads per lane in flight
-      int32_t v[8];
+    int eu = lane / k_stride, ep = lane - eu * k_stride;
+    for (int base = 0; base < n_el; base += 32 * METRIC_BATCH) {      // warp-uniform trip count (shuffles inside)
+      const int i0 = base + lane;
+      int32_t v[METRIC_BATCH];
 #pragma unroll
-      for (int m = 0; m < 8; ++m) { const int i = i0 + 32 * m; if (i < nb * k_stride) v[m] = src[i]; }
+      for (int m = 0; m < METRIC_BATCH; ++m) v[m] = (i0 + 32 * m < n_el) ? __ldg(src + i0 + 32 * m) : -1;
+      for (int q = 0; q < max_pos; ++q) {
+        const int32_t pq = q < npos ? __ldg(gt_idx + g0 + q) : INT_MIN;       // never equals an entry (entries >= -1)
+        int u = eu, pp = ep;
 #pragma unroll
-      for (int m = 0; m < 8; ++m) { const int i = i0 + 32 * m; if (i < nb * k_stride) L[(i / k_stride) * ld + (i % k_stride)] = v[m]; }
+        for (int m = 0; m < METRIC_BATCH; ++m) {
+          const int32_t x = __shfl_sync(0xffffffffu, pq, u & 31);
+          if (v[m] == x && v[m] >= 0) atomicOr(&hm[u], 1ull << pp);
+          u += step_u; pp += step_p;
+          if (pp >= k_stride) { pp -= k_stride; ++u; }
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < METRIC_BATCH; ++m) { eu += step_u; ep += step_p; if (ep >= k_stride) { ep -= k_stride; ++eu; } }
     }
     __syncwarp();
-    if (lane < nb) {
-      const int64_t g0 = gt_indptr[ub + lane], g1 = gt_indptr[ub + lane + 1];
-      const int npos = (int)(g1 - g0);
-      if (npos > 0) {                                 // "if not pos_set: continue" (tasks.py:589-591): contributes zeros
-        unsigned long long hit = 0ull, valid = 0ull;
-        const int32_t* rec = L + lane * ld;
-        for (int j = 0; j < k_stride; ++j) valid |= (unsigned long long)(rec[j] >= 0) << j;
-        for (int64_t g = g0; g < g1; ++g) {
-          const int32_t pv = gt_idx[g];
-          for (int j = 0; j < k_stride; ++j) hit |= (unsigned long long)(rec[j] == pv) << j;
-        }
+    const unsigned long long hit = hm[lane];
+    __syncwarp();
+    if (hit) {                                        // a user without hits (or without positives, tasks.py:589-591) adds exact zeros
+      {
+        unsigned long long valid = 0ull;
+        const int32_t* rec = topk + (ub + lane) * k_stride;
+        for (int j = 0; j < k_stride; ++j) valid |= (unsigned long long)(__ldg(rec + j) >= 0) << j;
         const int first = hit ? __ffsll((long long)hit) : 0;
         double dcg = 0.0;
         unsigned long long rest = hit;
