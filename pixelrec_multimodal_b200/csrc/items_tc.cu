@@ -152,6 +152,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3x_kernel(const __grid_constan
     // ============================================================ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = ptx::idesc_tf32(TM, p.NT);
+      // N <= 128: the hi and lo weight tiles are adjacent in the stage, so ONE MMA with N = 2 NT multiplies A_hi by both
+      // (columns [0, NT) collect A_hi.B_hi, columns [NT, 2 NT) collect A_hi.B_lo; the epilogue adds the halves).  An SS MMA
+      // re-reads both operand tiles from shared memory (4 KB of A per K step), which -- not the math -- bounds N = 64:
+      // two MMAs per K step read 14 KB instead of 18 KB in three.
+      const bool fold = p.NT <= 128;
+      const uint32_t idesc2 = ptx::idesc_tf32(TM, fold ? 2 * p.NT : p.NT);
       int it = 0, t_local = 0;
       for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, ++t_local) {
         const int acc = t_local & 1;
@@ -166,9 +172,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3x_kernel(const __grid_constan
           const uint64_t dBh = ptx::smem_desc_sw128(sb + 2 * A_TILE), dBl = ptx::smem_desc_sw128(sb + 2 * A_TILE + b_tile);
 #pragma unroll
           for (int kk = 0; kk < KC / 8; ++kk) {          // K = 8 per tf32 MMA = 32 bytes along the swizzled row
-            ptx::mma1_tf32_ss(d, dAl + 2 * kk, dBh + 2 * kk, idesc, (kc > 0 || kk > 0));
-            ptx::mma1_tf32_ss(d, dAh + 2 * kk, dBl + 2 * kk, idesc, 1);
-            ptx::mma1_tf32_ss(d, dAh + 2 * kk, dBh + 2 * kk, idesc, 1);
+            if (fold) {
+              ptx::mma1_tf32_ss(d, dAh + 2 * kk, dBh + 2 * kk, idesc2, (kc > 0 || kk > 0));
+              ptx::mma1_tf32_ss(d, dAl + 2 * kk, dBh + 2 * kk, idesc, 1);
+            } else {
+              ptx::mma1_tf32_ss(d, dAl + 2 * kk, dBh + 2 * kk, idesc, (kc > 0 || kk > 0));
+              ptx::mma1_tf32_ss(d, dAh + 2 * kk, dBl + 2 * kk, idesc, 1);
+              ptx::mma1_tf32_ss(d, dAh + 2 * kk, dBh + 2 * kk, idesc, 1);
+            }
           }
           ptx::commit1(EMPTY(s));
         }
@@ -189,6 +200,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3x_kernel(const __grid_constan
       for (int n0 = 0; n0 < p.NT; n0 += 32) {
         uint32_t v[32];
         ptx::tmem_ld32(t0 + n0, v);
+        if (p.NT <= 128) {                 // folded form: second half of the accumulator holds A_hi.B_lo
+          uint32_t v2[32];
+          ptx::tmem_ld32(t0 + p.NT + n0, v2);
+          ptx::tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+        }
         ptx::tc_wait_ld();
         if (row < p.M) {
           const float* b = p.bias + nt * p.NT + n0;
