@@ -939,6 +939,10 @@ score_fused_kernel(const __grid_constant__ Params p) {
     // what the deferred layer-3 epilogue needs to know about the previous tile, kept small (the loop below is short
     // on registers): this thread's item row (-1: padding row or no such user) and two flags
     int64_t prev_row = -1; int prev_flags = 0; bool have_prev = false;      // flags: 1 = first tile of its unit, 2 = last
+    // attention (88-register epilogue): ptxas spills less when the previous unit itself is kept and the row is derived
+    // where it is used (measured on config C: 1.46 vs 1.36 G pairs/s); gated / concat keep the compact form above
+    Unit prev; prev.ntiles = 0; prev.row_lo = prev.row_hi = 0; prev.g = prev.s = 0;
+    int prev_t = 0; int64_t prev_ubase = 0;
 
     auto do_e2 = [&](int Tp) {                       // H2 half `grp` of tile Tp
       ptx::mbar_wait(BAR(BAR_D2_FULL), Tp & 1);
@@ -951,7 +955,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(BAR(BAR_H2_FULL0 + grp), 0);
     };
-    auto do_e3 = [&](int Tp, int64_t row, bool last_of_unit) {
+    auto do_e3 = [&](int Tp, auto&& row_of, bool last_of_unit) {       // row_of(): this thread's item row or -1, evaluated late
       ptx::mbar_wait(BAR(BAR_D3_FULL), Tp & 1);
       ptx::tc_fence_after();
       float z = ms.b4;
@@ -977,6 +981,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(BAR(BAR_D3_EMPTY), 0);
       float y = pxr_apply_final(z, p.final_act);
+      const int64_t row = row_of();
       if (p.item_missing && row >= 0 && p.item_missing[row]) y = 0.f;
       const bool ok = row >= 0 && !((ms.seen_mask[Tp & 3][ru] >> rj) & 1u);
       if (ok && y >= *reinterpret_cast<volatile float*>(&ms.thr[ru])) {
@@ -995,8 +1000,16 @@ score_fused_kernel(const __grid_constant__ Params p) {
       }
     };
     auto prev_e3 = [&]() {
-      if ((prev_flags & 1) && (T - 1) > 0) { ptx::mbar_wait(BAR(BAR_UNIT_RESET), reset_ph); reset_ph ^= 1; }
-      do_e3(T - 1, prev_row, (prev_flags & 2) != 0);
+      if (ATT) {
+        if (prev_t == 0 && (T - 1) > 0) { ptx::mbar_wait(BAR(BAR_UNIT_RESET), reset_ph); reset_ph ^= 1; }
+        do_e3(T - 1, [&]() -> int64_t {
+          const int64_t row = prev.row_lo + (int64_t)prev_t * TI + rj;
+          return (row < prev.row_hi && (prev_ubase + ru) < p.n_users) ? row : -1;
+        }, prev_t == prev.ntiles - 1);
+      } else {
+        if ((prev_flags & 1) && (T - 1) > 0) { ptx::mbar_wait(BAR(BAR_UNIT_RESET), reset_ph); reset_ph ^= 1; }
+        do_e3(T - 1, [&]() -> int64_t { return prev_row; }, (prev_flags & 2) != 0);
+      }
     };
     // layer-1 chunk ci (0..3) of this group for the current tile: chunk c = 2 ci + grp in buffer c % 4
     auto do_l1 = [&](int ci) {
@@ -1041,7 +1054,9 @@ score_fused_kernel(const __grid_constant__ Params p) {
             if (grp == 0 && ci == (GATED ? 0 : 1)) prev_e3();
           }
         }
-        {
+        if (ATT) {
+          prev = un; prev_t = t; prev_ubase = ubase; have_prev = true;
+        } else {
           const int64_t row = un.row_lo + (int64_t)t * TI + rj;
           prev_row = (row < un.row_hi && (ubase + ru) < p.n_users) ? row : -1;
           prev_flags = (t == 0 ? 1 : 0) | (t == un.ntiles - 1 ? 2 : 0);

@@ -14,3 +14,8 @@ for f in gated concatenate attention; do timeout 120 python scripts/bench_stages
 timeout 600 python scripts/sweep.py > gpurun_out/${TAG}_sweep.jsonl 2>/dev/null
 tail -n 3 gpurun_out/${TAG}_pytest_gpu.log gpurun_out/${TAG}_smoke.log
 grep '^{' gpurun_out/${TAG}_bench.log | cut -c1-200
+# stage kernels (K1/K4/K5) under ncu, after the plain runs above
+if [ -n "$NCU_STAGES" ]; then
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"merge_topk|metrics_warp|gemm3x" -c 12 -o gpurun_out/${TAG}_prof_stages -f python scripts/bench_stages.py > gpurun_out/${TAG}_ncu_stages.log 2>&1
+ncu -i gpurun_out/${TAG}_prof_stages.ncu-rep --page raw --csv > gpurun_out/${TAG}_prof_stages_raw.csv 2>/dev/null
+fi
