@@ -536,21 +536,27 @@ __global__ void __launch_bounds__(32 * MERGE_MAX_WARPS) merge_topk_kernel(const 
 // (Issuing them one step ahead of the merges costs 20 registers and measured slower, 0.27 vs 0.24 ms: the kernel is
 // bound by instruction issue -- 168 shuffles and ~600 integer instructions per user -- not by load latency.)
 #define MERGE_GROUP 4
-__device__ __forceinline__ unsigned long long merge_max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
-__device__ __forceinline__ unsigned long long merge_min(unsigned long long a, unsigned long long b) { return a > b ? b : a; }
+// one compare (2 ISETP on the 64-bit key) and one conditional move (2 SEL) per compare-exchange half: the lane keeps its
+// own key or takes the partner's, never computes max and min separately
+__device__ __forceinline__ void merge_cx(unsigned long long& x, unsigned long long partner, bool keep_max) {
+  const bool take = (partner > x) == keep_max;
+  x = take ? partner : x;
+}
 
 __device__ __forceinline__ void merge_top64(unsigned long long& a0, unsigned long long& a1, unsigned long long b0,
                                             unsigned long long b1, int lane) {
   const unsigned long long r0 = __shfl_xor_sync(0xffffffffu, b1, 31);      // reversed B: slot lane      <- B[63 - lane]
   const unsigned long long r1 = __shfl_xor_sync(0xffffffffu, b0, 31);      //             slot 32 + lane <- B[31 - lane]
-  unsigned long long x0 = merge_max(a0, r0), x1 = merge_max(a1, r1);
-  { const unsigned long long hi = merge_max(x0, x1), lo = merge_min(x0, x1); x0 = hi; x1 = lo; }
+  unsigned long long x0 = a0, x1 = a1;
+  merge_cx(x0, r0, true);
+  merge_cx(x1, r1, true);
+  { const bool sw = x1 > x0; const unsigned long long hi = sw ? x1 : x0, lo = sw ? x0 : x1; x0 = hi; x1 = lo; }
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) {
     const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, x0, d), p1 = __shfl_xor_sync(0xffffffffu, x1, d);
     const bool keep_max = (lane & d) == 0;                                  // descending: the lower lane keeps the larger key
-    x0 = keep_max ? merge_max(x0, p0) : merge_min(x0, p0);
-    x1 = keep_max ? merge_max(x1, p1) : merge_min(x1, p1);
+    merge_cx(x0, p0, keep_max);
+    merge_cx(x1, p1, keep_max);
   }
   a0 = x0; a1 = x1;
 }
@@ -562,17 +568,19 @@ __global__ void __launch_bounds__(256) merge_topk_reg_kernel(const float* __rest
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const bool in0 = lane < k, in1 = lane + 32 < k;
+  const int64_t list_stride = n_users * k;
   for (int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < n_users; u += warps) {
     unsigned long long a0 = 0ull, a1 = 0ull;
-    for (int s0 = 0; s0 < n_shards; s0 += MERGE_GROUP) {
+    const float* sp = scores_in + u * k + lane;                             // list s of this user: + s * list_stride
+    const int32_t* ip = idx_in + u * k + lane;
+    for (int s0 = 0; s0 < n_shards; s0 += MERGE_GROUP, sp += MERGE_GROUP * list_stride, ip += MERGE_GROUP * list_stride) {
       float sc[MERGE_GROUP][2]; int32_t id[MERGE_GROUP][2];
 #pragma unroll
       for (int m = 0; m < MERGE_GROUP; ++m) {
         id[m][0] = id[m][1] = -1; sc[m][0] = sc[m][1] = 0.f;
         if (s0 + m < n_shards) {
-          const int64_t off = ((int64_t)(s0 + m) * n_users + u) * k + lane;
-          if (in0) { id[m][0] = __ldg(idx_in + off); sc[m][0] = __ldg(scores_in + off); }
-          if (in1) { id[m][1] = __ldg(idx_in + off + 32); sc[m][1] = __ldg(scores_in + off + 32); }
+          if (in0) { id[m][0] = __ldg(ip + m * list_stride); sc[m][0] = __ldg(sp + m * list_stride); }
+          if (in1) { id[m][1] = __ldg(ip + m * list_stride + 32); sc[m][1] = __ldg(sp + m * list_stride + 32); }
         }
       }
 #pragma unroll
