@@ -655,3 +655,26 @@ def ranking_task_metrics(users: Sequence[str], test_items: Sequence[Sequence[str
     out["num_users_evaluated"] = len(users)
     out["predictions"] = predictions
     return out
+
+
+# --------------------------------------------------------------------------
+# K4 register merge: the compare-exchange network, lane by lane
+# --------------------------------------------------------------------------
+def merge_top64_network(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Restatement of ``merge_top64`` in csrc/simt_kernels.cu (the k <= 64 path of ``pxr_merge_topk``; the reference
+    has no counterpart -- it sorts one full score list per user, src/inference/recommender.py:105).  ``a`` and ``b`` are
+    descending lists of 64 distinct uint64 keys (0 = padding); slot j lives in lane j & 31, register j >> 5.  Returns
+    the best 64 keys of the union, descending: max(A[j], B[63 - j]) is bitonic, six compare-exchange stages sort it."""
+    lane = np.arange(32)
+    a0, a1, b0, b1 = a[:32].copy(), a[32:].copy(), b[:32], b[32:]
+    r0, r1 = b1[lane ^ 31], b0[lane ^ 31]                     # reversed B: one lane-mirror shuffle, registers swapped
+    x0, x1 = np.maximum(a0, r0), np.maximum(a1, r1)
+    x0, x1 = np.maximum(x0, x1), np.minimum(x0, x1)           # distance 32: inside the lane
+    d = 16
+    while d >= 1:                                             # distances 16 .. 1: shfl.xor partners
+        p0, p1 = x0[lane ^ d], x1[lane ^ d]
+        keep_max = (lane & d) == 0
+        take0, take1 = (p0 > x0) == keep_max, (p1 > x1) == keep_max
+        x0, x1 = np.where(take0, p0, x0), np.where(take1, p1, x1)
+        d >>= 1
+    return np.concatenate([x0, x1])
