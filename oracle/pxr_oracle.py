@@ -563,6 +563,41 @@ def sample_candidates(global_user: int, positives: Sequence[int], n_items: int, 
     return sorted(cand, key=key)
 
 
+def sampling_weights(test_items: Sequence[int], n_items: int, strategy: str) -> np.ndarray:
+    """Per-item sampling weight of the 'popularity' / 'popularity_inverse' strategies
+    (src/evaluation/tasks.py:227-243, 266-280): the number of rows of the TEST table that hold the item (default 1
+    for items that never occur there), or its reciprocal."""
+    cnt = np.bincount(np.asarray(test_items, dtype=np.int64), minlength=n_items).astype(np.float64)
+    cnt[cnt == 0] = 1.0
+    return cnt if strategy == "popularity" else 1.0 / cnt
+
+
+def sample_candidates_weighted(global_user: int, positives: Sequence[int], weights: np.ndarray, n_neg: int, seed: int,
+                               stride: int = 1024) -> List[int]:
+    """Candidate list of one user for the popularity-biased strategies (src/evaluation/tasks.py:225-308: negatives drawn
+    without replacement with probability proportional to the weight, ``np.random.choice(..., replace=False, p=...)``),
+    made reproducible like ``sample_candidates``: item i gets the exponential key log(u_i) / w_i with u_i a hash-uniform
+    of (seed, user, item); the n_neg largest keys among the non-positive items are the sample (Efraimidis-Spirakis:
+    the same distribution as successive weighted draws without replacement).  Ties -> lower item.  Final order as in
+    ``sample_candidates``.  Direct restatement of ``evaluation.weighted_candidates`` (torch, any device)."""
+    n_items = len(weights)
+    pos = sorted(int(p) for p in positives)[:stride]
+    posset = set(int(p) for p in positives)
+    ku = mix64((seed & _M64) ^ mix64(global_user & _M64))
+    want = max(0, min(n_neg, stride - len(pos), n_items - len(posset)))
+    keyed = []
+    for it in range(n_items):
+        if it in posset:
+            continue
+        u = ((mix64(ku ^ 0xA0761D6478BD642F ^ ((it & 0xFFFFFFFF) << 1)) >> 11) + 0.5) * (1.0 / 9007199254740992.0)
+        keyed.append((-(math.log(u) / float(weights[it])), it))
+    keyed.sort()
+    negs = [it for _, it in keyed[:want]]
+    cand = pos + negs
+    key = lambda it: (mix64(ku ^ 0xD1B54A32D192ED03 ^ ((it & 0xFFFFFFFF) << 1)), it)
+    return sorted(cand, key=key)
+
+
 def rank_candidates(scores: Sequence[float], candidates: Sequence[int], k: int) -> List[int]:
     """Stable descending sort over the candidate order, first k
     (src/inference/recommender.py:97-106 with candidates=...)."""

@@ -242,7 +242,8 @@ def make_parser() -> argparse.ArgumentParser:
                    help="retrieval: top-K lists against the test positives; ranking: order of each user's own test items (tasks.py:776-901)")
     e.add_argument("--use_sampling", action="store_true", help="positives + sampled negatives (the reference default protocol)")
     e.add_argument("--num_negatives", type=int, default=100)
-    e.add_argument("--sampling_strategy", type=str, default="random")
+    e.add_argument("--sampling_strategy", type=str, default="random", choices=["random", "popularity", "popularity_inverse"],
+                   help="how the negatives are drawn (evaluate.py / tasks.py:221-308)")
     e.add_argument("--seed", type=int, default=20261018)
     e.add_argument("--ks", type=int, nargs="*", help="extra cut-offs reported under by_k")
     e.add_argument("--save_predictions", type=str, default=None)

@@ -39,6 +39,76 @@ def test_rank_candidates_is_stable():
     assert orc.rank_candidates([0.5, 0.9, 0.5, 0.1], [10, 11, 12, 13], 3) == [11, 10, 12]
 
 
+@pytest.mark.parametrize("strategy", ["popularity", "popularity_inverse"])
+@pytest.mark.parametrize("n_items,n_neg,max_pos,stride", [(300, 40, 5, 64), (37, 100, 6, 128), (50, 10, 0, 16), (12, 8, 12, 16), (9, 4, 3, 5)])
+def test_weighted_candidates_match_oracle(strategy, n_items, n_neg, max_pos, stride):
+    """product (torch tensor code, here on the CPU device) == the per-user Python restatement, item for item"""
+    import torch
+    from pixelrec_multimodal_b200.evaluation import sampling_weights, weighted_candidates
+    rng = np.random.default_rng(n_items * 7 + n_neg)
+    n = 40
+    npos = rng.integers(0, max_pos + 1, n)
+    pos = [np.sort(rng.choice(n_items, min(c, n_items), replace=False)) for c in npos]
+    indptr = np.concatenate([[0], np.cumsum([len(p) for p in pos])]).astype(np.int64)
+    idx = (np.concatenate(pos) if indptr[-1] else np.zeros(0)).astype(np.int32)
+    users = rng.integers(0, 10 ** 9, n).astype(np.int64)
+    test_items = rng.zipf(1.5, 400) % n_items
+    w = sampling_weights(test_items, n_items, strategy)
+    assert np.array_equal(w, orc.sampling_weights(test_items, n_items, strategy))
+    cand, length = weighted_candidates(torch.from_numpy(users), torch.from_numpy(indptr), torch.from_numpy(idx), torch.from_numpy(w),
+                                       n_neg, seed=77, stride=stride, max_elems=n_items * 7)      # several user blocks
+    cand, length = cand.numpy(), length.numpy()
+    for r in range(n):
+        want = orc.sample_candidates_weighted(int(users[r]), pos[r].tolist(), w, n_neg, seed=77, stride=stride)
+        assert length[r] == len(want) and cand[r][:length[r]].tolist() == want and np.all(cand[r][length[r]:] == -1), r
+        assert set(pos[r].tolist()[:stride]) <= set(want) and len(set(want)) == len(want)
+
+
+def test_weighted_sampling_follows_the_weights():
+    """inclusion frequency grows with the weight (popularity) and shrinks with it (inverse); positives are never negatives"""
+    import torch
+    from pixelrec_multimodal_b200.evaluation import weighted_candidates
+    n_items, n = 60, 3000
+    w = np.ones(n_items); w[:10] = 8.0
+    users = torch.arange(n, dtype=torch.int64)
+    indptr = torch.arange(n + 1, dtype=torch.int64)
+    pos = torch.full((n,), 59, dtype=torch.int32)
+    for weights, heavy_more in ((w, True), (1.0 / w, False)):
+        cand, length = weighted_candidates(users, indptr, pos, torch.from_numpy(weights), 5, seed=3, stride=8)
+        c = cand.numpy()
+        assert np.all(length.numpy() == 6) and np.all((c == 59).sum(axis=1) == 1)
+        cnt = np.bincount(c[c >= 0], minlength=n_items).astype(float)
+        heavy, light = cnt[:10].mean(), cnt[10:59].mean()
+        assert (heavy > 3 * light) if heavy_more else (light > 3 * heavy)
+
+
+def test_sampled_evaluator_builds_weighted_candidates_from_the_test_table():
+    """SampledRetrievalEvaluator(sampling_strategy='popularity'): weights = item counts of the test table (tasks.py:227),
+    candidates = positives + weighted negatives; host plumbing checked with a stand-in recommender on the CPU device"""
+    import pandas as pd
+    import torch
+    from pixelrec_multimodal_b200 import SampledRetrievalEvaluator
+
+    class _Rec:
+        device = torch.device("cpu")
+        n_items = 30
+        user_index = {f"u{j}": j for j in range(6)}
+        item_index = {f"i{j:02d}": j for j in range(30)}
+
+    rows = [(f"u{j}", f"i{(3 * j) % 30:02d}") for j in range(6)] + [("u0", "i07"), ("u1", "i07"), ("u2", "i07"), ("nobody", "i01")]
+    df = pd.DataFrame(rows, columns=["user_id", "item_id"])
+    ev = SampledRetrievalEvaluator(_Rec(), df, top_k=5, num_negatives=10, sampling_strategy="popularity", seed=1)
+    w = orc.sampling_weights([_Rec.item_index[i] for u, i in rows if u in _Rec.user_index], 30, "popularity")
+    assert np.array_equal(ev._weights, w) and w[7] == 3.0 and w[0] == 1.0
+    cand, length = ev.candidates()
+    for j, u in enumerate(ev.users):
+        pos = ev.gt_idx[ev.gt_indptr[j]:ev.gt_indptr[j + 1]].tolist()
+        want = orc.sample_candidates_weighted(int(u), pos, w, 10, seed=1, stride=cand.shape[1])
+        assert cand[j][:int(length[j])].tolist() == want
+    with pytest.raises(ValueError):
+        SampledRetrievalEvaluator(_Rec(), df, sampling_strategy="other")
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_items,n_neg,max_pos", [(500, 100, 4), (37, 100, 6), (100000, 100, 1), (2000, 1000, 30), (5, 3, 5)])
 def test_sampler_kernel_matches_oracle(n_items, n_neg, max_pos):
