@@ -12,6 +12,10 @@ embedding of every item, once, as dense row-aligned arrays that go to the GPU wi
     vis.f32 / txt.f32 / num.f32   row-major float32 [n_items, dim]   (absent when dim == 0)
     tag.i64        int64 [n_items]
 
+``dtype="float16"`` stores vis / txt as ``vis.f16`` / ``txt.f16`` (half the bytes on disk and over PCIe; the upload
+widens them to the fp32 rows ``pxr_precompute_items`` reads; the numerical features stay fp32).  Opt-in: the cached
+embeddings are then rounded to 11 significant bits, which the reference never does.
+
 ``convert_reference_cache`` builds it from the reference's per-item files with caller-supplied encoders
 (the frozen backbones run once per item); ``PackedFeatureCache`` memory-maps it, serves the reference-style
 feature dict per item id (``feature_cache.get(item_id)``, ``recommender.py:239-269``) and uploads
@@ -30,8 +34,18 @@ VERSION = 1
 _FILES = {"vis": ("vis.f32", np.float32), "txt": ("txt.f32", np.float32), "num": ("num.f32", np.float32)}
 
 
-def write_packed_cache(path, item_ids: Sequence[str], tag_idx, vis=None, txt=None, num=None) -> Path:
-    """Write a packed cache; arrays are row-aligned with ``item_ids``."""
+def _file_of(key: str, dtype: str):
+    """(file name, numpy dtype) of one feature array under the cache's storage dtype."""
+    if dtype == "float16" and key in ("vis", "txt"):
+        return _FILES[key][0].replace(".f32", ".f16"), np.float16
+    return _FILES[key]
+
+
+def write_packed_cache(path, item_ids: Sequence[str], tag_idx, vis=None, txt=None, num=None, dtype: str = "float32") -> Path:
+    """Write a packed cache; arrays are row-aligned with ``item_ids``.  ``dtype``: storage of vis / txt
+    ("float32" | "float16")."""
+    if dtype not in ("float32", "float16"):
+        raise ValueError("dtype must be 'float32' or 'float16'")
     path = Path(path)
     path.mkdir(parents=True, exist_ok=True)
     n = len(item_ids)
@@ -41,11 +55,12 @@ def write_packed_cache(path, item_ids: Sequence[str], tag_idx, vis=None, txt=Non
         if a is None:
             dims[k] = 0
             continue
+        fname, ftype = _file_of(k, dtype)
         a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
         if a.ndim != 2 or a.shape[0] != n:
             raise ValueError(f"{k} must be ({n}, dim), got {a.shape}")
         dims[k] = int(a.shape[1])
-        a.tofile(path / _FILES[k][0])
+        a.astype(ftype, copy=False).tofile(path / fname)
     tag = np.ascontiguousarray(np.asarray(tag_idx, dtype=np.int64))
     if tag.shape != (n,):
         raise ValueError(f"tag_idx must be ({n},), got {tag.shape}")
@@ -53,7 +68,7 @@ def write_packed_cache(path, item_ids: Sequence[str], tag_idx, vis=None, txt=Non
     (path / "item_ids.txt").write_text("\n".join(str(i) for i in item_ids) + ("\n" if n else ""))
     (path / "meta.json").write_text(json.dumps({"version": VERSION, "n_items": n, "vision_dim": dims["vis"],
                                                 "language_dim": dims["txt"], "num_numerical": dims["num"],
-                                                "dtype": "float32"}, indent=1))
+                                                "dtype": dtype}, indent=1))
     return path
 
 
@@ -74,8 +89,10 @@ class PackedFeatureCache:
         self._index: Optional[Dict[str, int]] = None
         dims = {"vis": meta["vision_dim"], "txt": meta["language_dim"], "num": meta["num_numerical"]}
         self.arrays = {}
+        self.dtype = meta.get("dtype", "float32")
         for k, d in dims.items():
-            self.arrays[k] = (np.memmap(self.path / _FILES[k][0], dtype=np.float32, mode="r", shape=(self.n_items, int(d)))
+            fname, ftype = _file_of(k, self.dtype)
+            self.arrays[k] = (np.memmap(self.path / fname, dtype=ftype, mode="r", shape=(self.n_items, int(d)))
                               if d and self.n_items else None)
         self.tag = np.memmap(self.path / "tag.i64", dtype=np.int64, mode="r", shape=(self.n_items,)) if self.n_items else \
             np.zeros(0, np.int64)
@@ -100,9 +117,9 @@ class PackedFeatureCache:
             return default
         out = {"tag_idx": torch.tensor(int(self.tag[r]), dtype=torch.long)}
         if self.arrays["vis"] is not None:
-            out["image"] = torch.from_numpy(np.array(self.arrays["vis"][r]))
+            out["image"] = torch.from_numpy(np.array(self.arrays["vis"][r], dtype=np.float32))
         if self.arrays["txt"] is not None:
-            out["text_input_ids"] = torch.from_numpy(np.array(self.arrays["txt"][r]))
+            out["text_input_ids"] = torch.from_numpy(np.array(self.arrays["txt"][r], dtype=np.float32))
             out["text_attention_mask"] = torch.ones(1, dtype=torch.long)
         if self.arrays["num"] is not None:
             out["numerical_features"] = torch.from_numpy(np.array(self.arrays["num"][r]))

@@ -59,3 +59,25 @@ def test_convert_reference_cache(tmp_path):
         assert torch.allclose(torch.from_numpy(np.array(c.arrays["txt"][r])), enc_txt(raw[it]["text_input_ids"][None], raw[it]["text_attention_mask"][None])[0])
     with pytest.raises(FileNotFoundError):
         convert_reference_cache(ref, tmp_path / "p2", ids + ["ghost"], tag_idx=np.arange(10), encode_image=enc_img)
+
+
+def test_float16_storage(tmp_path):
+    """dtype='float16': vis / txt on disk at half the size, widened to fp32 by get() and to_store(); num stays fp32"""
+    spec = syn.ModelSpec(n_users=4, n_items=21)
+    f = syn.make_item_features(spec, seed=5)
+    ids = syn.item_ids(spec.n_items)
+    write_packed_cache(tmp_path / "h", ids, f["tag_idx"], f["vis"], f["txt"], f["num"], dtype="float16")
+    write_packed_cache(tmp_path / "s", ids, f["tag_idx"], f["vis"], f["txt"], f["num"])
+    assert (tmp_path / "h" / "vis.f16").stat().st_size * 2 == (tmp_path / "s" / "vis.f32").stat().st_size
+    assert (tmp_path / "h" / "num.f32").stat().st_size == (tmp_path / "s" / "num.f32").stat().st_size
+    c = PackedFeatureCache(tmp_path / "h")
+    assert c.dtype == "float16" and PackedFeatureCache(tmp_path / "s").dtype == "float32"
+    st = c.to_store("cpu", chunk_rows=8)
+    assert st.vis.dtype == torch.float32 and st.txt.dtype == torch.float32
+    assert torch.equal(st.vis, torch.from_numpy(f["vis"].astype(np.float16).astype(np.float32)))
+    assert torch.equal(st.num, torch.from_numpy(f["num"]))
+    assert np.abs(st.vis.numpy() - f["vis"]).max() <= 5e-4 * np.abs(f["vis"]).max() + 1e-6
+    d = c.get(ids[3])
+    assert d["image"].dtype == torch.float32 and torch.equal(d["image"], st.vis[3])
+    with pytest.raises(ValueError):
+        write_packed_cache(tmp_path / "x", ids, f["tag_idx"], f["vis"], dtype="int8")
