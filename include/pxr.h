@@ -29,9 +29,10 @@
 extern "C" {
 #endif
 
-#define PXR_VERSION 1
+#define PXR_VERSION 2
 #define PXR_MAX_HIDDEN 8
 #define PXR_MAX_KS 8
+#define PXR_METRIC_COLS 9
 
 typedef struct pxr_handle pxr_handle;
 typedef void* pxr_stream; /* cudaStream_t */
@@ -156,6 +157,16 @@ int pxr_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* us
                    float* out_scores, int32_t* out_idx, void* workspace, size_t workspace_bytes,
                    pxr_stream stream);
 
+/* Exact mode of pxr_score_topk on the tcgen05 path (default: on).  The fused kernel ranks with 16-bit operands
+ * (bf16: |score error| up to ~5e-2 at catalogue scale); in exact mode it keeps its 64 best
+ * candidates per user, these are scored again with the fp32 arithmetic of pxr_score_pairs -- i.e. the reference
+ * forward, src/models/multimodal.py:528-610 -- and ranked again with the reference's stable order
+ * (src/inference/recommender.py:105-106, ties -> lower item index).  Returned scores then meet the fp32 tolerance
+ * (1e-4) and the list equals the reference's whenever its top-K lies inside the 16-bit top-64.  The SIMT path is
+ * always exact.  on = 0 returns the 16-bit scores and order as they are (K <= 64 either way). */
+int pxr_set_rescore(pxr_handle* h, int on);
+int pxr_get_rescore(const pxr_handle* h);
+
 /* Scores of explicit (user, item-row) pairs against the precomputed records.
  * Replaces MultimodalRecommender.forward (src/models/multimodal.py:528-610),
  * Recommender._score_items_batch / get_item_score and the candidate-list mode
@@ -173,23 +184,31 @@ int pxr_merge_topk(const float* scores_in, const int32_t* idx_in, int32_t n_shar
                    int32_t k, float* out_scores, int32_t* out_idx, pxr_stream stream);
 
 /* K5.  Replaces the accuracy block of TopKRetrievalEvaluator.evaluate and
- * _calculate_ndcg (src/evaluation/tasks.py:567-635, 718-747) for several
- * cut-offs at once (@10 is a prefix of @50).
+ * _calculate_ndcg (src/evaluation/tasks.py:567-635, 718-747) and the standalone
+ * per-user functions of src/evaluation/metrics.py:11-133 for several cut-offs at
+ * once (@10 is a prefix of @50).
  *   topk_idx   : (n_users, k_stride) int32 ranked GLOBAL item ids, -1 padded
- *   gt_indptr  : (n_users+1,) int64 ;  gt_idx : int32 relevant items (any order)
+ *   gt_indptr  : (n_users+1,) int64 ;  gt_idx : int32 relevant items (any order), the
+ *                SET of positives of each user (its size is what IDCG and MAP use)
+ *   recall_den : (n_users,) int32 recall denominators = len(positive_items), the raw
+ *                number of test rows of the user (tasks.py:579: duplicates and items
+ *                unknown to the encoder included); NULL = the set size
  *   ks         : host array of n_ks cut-offs, each <= k_stride
  *   discount   : (k_stride,) float64 DEVICE table 1/log2(i+2) (host-computed so it
  *                is bit-identical to numpy's);  ideal : (k_stride+1,) float64
  *                DEVICE prefix sums of it in Python's left-to-right order
- *   out_sums   : (n_ks, 7) float64 DEVICE: sums over users of precision, recall,
- *                f1, hit_rate, ndcg (tasks.py variant), mrr, ndcg (metrics.py
- *                variant, src/evaluation/metrics.py:63-100)
+ *   out_sums   : (n_ks, PXR_METRIC_COLS = 9) float64 DEVICE: sums over users of
+ *                precision (hits / len(recs), tasks.py:577), recall, f1, hit_rate,
+ *                ndcg (tasks.py variant), mrr, ndcg (metrics.py variant,
+ *                src/evaluation/metrics.py:63-100), precision (hits / k,
+ *                metrics.py:29-35), average precision of the first k entries
+ *                (metrics.py:102-133)
  *   workspace  : pxr_metrics_bytes(n_users, n_ks) bytes */
 size_t pxr_metrics_bytes(int64_t n_users, int32_t n_ks);
 int pxr_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, const int64_t* gt_indptr,
-                const int32_t* gt_idx, const int32_t* ks, int32_t n_ks, const double* discount,
-                const double* ideal, double* out_sums, void* workspace, size_t workspace_bytes,
-                pxr_stream stream);
+                const int32_t* gt_idx, const int32_t* recall_den, const int32_t* ks, int32_t n_ks,
+                const double* discount, const double* ideal, double* out_sums, void* workspace,
+                size_t workspace_bytes, pxr_stream stream);
 
 /* Sampled evaluation protocol, candidate construction.  Replaces
  * TopKRetrievalEvaluator._process_user / _sample_negatives with sampling_strategy 'random'

@@ -8,6 +8,7 @@ from pathlib import Path
 
 PXR_MAX_HIDDEN = 8
 PXR_MAX_KS = 8
+PXR_METRIC_COLS = 9
 
 FUSION = {"concatenate": 0, "gated": 1, "attention": 2}
 ACT = {"relu": 0, "gelu": 1, "tanh": 2, "leaky_relu": 3, "silu": 4}
@@ -60,7 +61,7 @@ _SIGNATURES = {
     "pxr_score_pairs": (C.c_int, [C.c_void_p, _F, _F, _F, C.c_int64, _F, _F, C.c_void_p]),
     "pxr_merge_topk": (C.c_int, [_F, _F, C.c_int32, C.c_int64, C.c_int32, _F, _F, C.c_void_p]),
     "pxr_metrics_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
-    "pxr_metrics": (C.c_int, [_F, C.c_int32, C.c_int64, _F, _F, C.POINTER(C.c_int32), C.c_int32, _F, _F, _F, _F,
+    "pxr_metrics": (C.c_int, [_F, C.c_int32, C.c_int64, _F, _F, _F, C.POINTER(C.c_int32), C.c_int32, _F, _F, _F, _F,
                               C.c_size_t, C.c_void_p]),
     "pxr_sample_candidates": (C.c_int, [_F, C.c_int64, _F, _F, C.c_int64, C.c_int32, C.c_uint64, C.c_int32, _F, _F, C.c_void_p]),
     "pxr_topk_rows": (C.c_int, [C.c_void_p, _F, C.c_int64, C.c_int64, C.c_int32, _F, _F, C.c_void_p]),
@@ -71,6 +72,8 @@ _SIGNATURES = {
     "pxr_launch_count": (C.c_int64, [C.c_void_p]),
     "pxr_active_path": (C.c_int, [C.c_void_p]),
     "pxr_set_path": (C.c_int, [C.c_void_p, C.c_int]),
+    "pxr_set_rescore": (C.c_int, [C.c_void_p, C.c_int]),
+    "pxr_get_rescore": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None
@@ -94,9 +97,12 @@ def load() -> C.CDLL:
     try:
         if path == Path(__file__).resolve().parent / "libpxr.so" and _build.needs_build():
             _build.build()
-    except Exception as e:  # a prebuilt .so (the GPU box has one) is still fine
+    except Exception as e:  # a prebuilt .so (the GPU box has one) is still usable, but say that it is stale
         if not path.exists():
             raise PxrError(f"libpxr.so is missing and could not be built: {e}") from e
+        import warnings
+        warnings.warn(f"libpxr.so is older than its sources and the rebuild failed ({e}); loading the existing library",
+                      RuntimeWarning, stacklevel=2)
     if not path.exists():
         raise PxrError(f"{path} not found: the CUDA extension is required (no CPU fallback)")
     lib = C.CDLL(str(path))

@@ -50,18 +50,54 @@ def load_config(path: Optional[str]) -> Dict:
     return cfg
 
 
+def find_encoders(checkpoint: Optional[str], encoders: Optional[str]) -> Optional[Path]:
+    """Directory holding the training-time ``user_encoder.pkl`` / ``item_encoder.pkl`` (``scripts/train.py:503-508``).
+    Search order of ``scripts/evaluate.py:113-167`` relative to the checkpoint file: ``<ckpt dir>/encoders``,
+    ``<ckpt dir>``, then the same two one level up (checkpoints live in ``<checkpoint_dir>/<vision>_<language>/``,
+    ``evaluate.py:54-110``); ``--encoders DIR`` overrides the search.  None when there are no pickled encoders."""
+    cands = []
+    if encoders:
+        cands.append(Path(encoders))
+    elif checkpoint:
+        d = Path(checkpoint).resolve().parent
+        cands += [d / "encoders", d, d.parent / "encoders", d.parent]
+    for c in cands:
+        if (c / "user_encoder.pkl").exists() and (c / "item_encoder.pkl").exists():
+            return c
+    if encoders:
+        raise FileNotFoundError(f"user_encoder.pkl / item_encoder.pkl not found in {encoders}")
+    return None
+
+
 class TableDataset:
     """The attributes the recommender reads on its dataset (``recommender.py:58-90, 239-269``): encoders with
-    ``classes_``, the interaction frame, and a ``feature_cache`` with ``get(item_id)``."""
+    ``classes_``, the interaction frame, and a ``feature_cache`` with ``get(item_id)``.
+
+    With ``encoders_dir`` the pickled training-time ``LabelEncoder`` objects are loaded as the reference scripts do
+    (``evaluate.py:301-304``, ``generate_recommendations.py:116-119``), so embedding rows line up with the
+    checkpoint whatever ids the CSV / cache hold today.  Without it the encoders are rebuilt as the sorted unique
+    ids of the interaction table and the cache (what ``LabelEncoder.fit`` gives on the same tables,
+    ``dataset.py:142-148``) -- only valid when those are the training tables; ``build_recommender`` checks the
+    row counts against the checkpoint either way."""
 
     class _Encoder:
         def __init__(self, classes):
             self.classes_ = np.asarray(classes, dtype=object)
 
-    def __init__(self, interactions, cache):
-        users = np.sort(interactions["user_id"].astype(str).unique())
-        self.user_encoder = self._Encoder(users)
-        self.item_encoder = self._Encoder(sorted(cache.item_ids))
+    def __init__(self, interactions, cache, encoders_dir: Optional[Path] = None):
+        if encoders_dir is not None:
+            import pickle
+            with open(Path(encoders_dir) / "user_encoder.pkl", "rb") as f:
+                self.user_encoder = pickle.load(f)
+            with open(Path(encoders_dir) / "item_encoder.pkl", "rb") as f:
+                self.item_encoder = pickle.load(f)
+            for name, enc in (("user", self.user_encoder), ("item", self.item_encoder)):
+                if not hasattr(enc, "classes_"):
+                    raise ValueError(f"{name}_encoder.pkl holds no fitted encoder (no classes_)")
+        else:
+            users = np.sort(interactions["user_id"].astype(str).unique())
+            self.user_encoder = self._Encoder(users)
+            self.item_encoder = self._Encoder(sorted(cache.item_ids))
         self.interactions = interactions
         self.feature_cache = cache
 
@@ -83,24 +119,37 @@ def distributed_context(device: str):
 
 
 def build_recommender(cfg: Dict, checkpoint: Optional[str], cache_dir: str, interactions_csv: str, device: str = "cuda:0",
-                      n_tags: Optional[int] = None, shard=None):
+                      n_tags: Optional[int] = None, shard=None, encoders: Optional[str] = None):
     import pandas as pd
     import torch
     from . import FastMultimodalRecommender, FastRecommender
+    from .model import _IGNORED_PREFIXES
     from .packed_cache import PackedFeatureCache
     cache = PackedFeatureCache(cache_dir)
     inter = pd.read_csv(interactions_csv, dtype={"user_id": str, "item_id": str})
-    ds = TableDataset(inter, cache)
+    enc_dir = find_encoders(checkpoint, encoders)
+    ds = TableDataset(inter, cache, enc_dir)
     m = cfg["model"]
     sd = None
     if checkpoint:
         ck = torch.load(checkpoint, map_location="cpu", weights_only=False)
         sd = ck["model_state_dict"] if isinstance(ck, dict) and "model_state_dict" in ck else ck
+    n_user_cls, n_item_cls = len(ds.user_encoder.classes_), len(ds.item_encoder.classes_)
+    if sd is not None:
+        # embedding rows are addressed by encoder index: a mismatch means the encoders are not the training-time
+        # ones and every lookup would silently hit the wrong row (the reference raises IndexError at best)
+        for what, key, n_cls in (("user", "user_embedding.weight", n_user_cls), ("item", "item_embedding.weight", n_item_cls)):
+            rows = int(sd[key].shape[0])
+            if rows != n_cls:
+                src = f"the pickled encoders in {enc_dir}" if enc_dir is not None else \
+                    "encoders rebuilt from the interactions CSV / feature cache (pass --encoders DIR with the training-time pickles)"
+                raise ValueError(f"checkpoint has {rows} {what} embedding rows but {src} define {n_cls} {what} ids")
     if n_tags is None:
         n_tags = int(sd["tag_embedding.weight"].shape[0]) if sd is not None else int(np.max(cache.tag)) + 1
-    n_users = int(sd["user_embedding.weight"].shape[0]) if sd is not None else len(ds.user_encoder.classes_)
+    if len(cache.tag) and (int(np.max(cache.tag)) >= n_tags or int(np.min(cache.tag)) < 0):
+        raise ValueError(f"feature cache holds tag index {int(np.max(cache.tag))} but the model has {n_tags} tag embeddings")
     model = FastMultimodalRecommender(
-        n_users=n_users, n_items=len(ds.item_encoder.classes_), n_tags=n_tags,
+        n_users=n_user_cls, n_items=n_item_cls, n_tags=n_tags,
         num_numerical_features=cache.meta["num_numerical"], embedding_dim=m["embedding_dim"],
         vision_model_name=f"cached{cache.meta['vision_dim']}" if cache.meta["vision_dim"] else None,
         language_model_name=f"cached{cache.meta['language_dim']}" if cache.meta["language_dim"] else None,
@@ -108,13 +157,20 @@ def build_recommender(cfg: Dict, checkpoint: Optional[str], cache_dir: str, inte
         fusion_activation=m["fusion_activation"], use_batch_norm=m["use_batch_norm"],
         projection_hidden_dim=m["projection_hidden_dim"], final_activation=m["final_activation"], fusion_type=m["fusion_type"])
     if sd is not None:
-        model.load_state_dict(sd, strict=False)
+        # strict: every parameter of the scoring path must come from the checkpoint (backbone / contrastive-head keys
+        # are dropped by load_state_dict itself; BatchNorm's num_batches_tracked counters are not used)
+        sd = {k: v for k, v in sd.items() if not k.startswith(_IGNORED_PREFIXES)}
+        model.load_state_dict(sd, strict=True)
     dev = torch.device(device)
+    missing_in_cache = [str(i) for i in ds.item_encoder.classes_ if str(i) not in cache.index]
+    if missing_in_cache:
+        print(f"warning: {len(missing_in_cache)} items of the item encoder have no row in the feature cache; "
+              f"they score 0.0 like items without features in the reference (recommender.py:229-230)", file=sys.stderr)
     store = cache.to_store(dev, order=[str(i) for i in ds.item_encoder.classes_])
     item_range = None
     if shard is not None:                                   # (world, rank): contiguous item shard of this rank
         from .sharding import shard_range
-        item_range = shard_range(len(ds.item_encoder.classes_), shard[0], shard[1])
+        item_range = shard_range(n_item_cls, shard[0], shard[1])
     rec = FastRecommender(model, ds, dev, item_features=store, item_range=item_range)
     return rec, ds
 
@@ -146,7 +202,7 @@ def cmd_generate(args) -> Dict:
     cfg = load_config(args.config)
     top_k = args.top_k or cfg["recommendation"]["top_k"]
     filter_seen = cfg["recommendation"]["filter_seen"] and not args.no_filter_seen
-    rec, ds = build_recommender(cfg, args.checkpoint, args.cache, args.interactions, args.device)
+    rec, ds = build_recommender(cfg, args.checkpoint, args.cache, args.interactions, args.device, encoders=args.encoders)
     users = select_users(args, ds.user_encoder.classes_)
     if args.all_users or len(users) > 256:
         known = [u for u in users if u in rec.user_index]
@@ -176,7 +232,7 @@ def cmd_evaluate(args) -> Dict:
     if world > 1 and (args.use_sampling or ranking):
         raise SystemExit("--use_sampling / --eval_task ranking score explicit pairs: run them on one GPU (no item-axis sharding)")
     rec, ds = build_recommender(cfg, args.checkpoint, args.cache, args.interactions, device,
-                                shard=(world, rank) if world > 1 else None)
+                                shard=(world, rank) if world > 1 else None, encoders=args.encoders)
     test = pd.read_csv(args.test_data, dtype={"user_id": str, "item_id": str})
     ks = sorted(set([top_k] + [int(k) for k in (args.ks or [])]))
     sharded = None
@@ -222,6 +278,9 @@ def make_parser() -> argparse.ArgumentParser:
         p.add_argument("--checkpoint", type=str, default=None, help="reference checkpoint (.pth with model_state_dict)")
         p.add_argument("--cache", type=str, required=True, help="packed feature cache directory (packed_cache.py)")
         p.add_argument("--interactions", type=str, required=True, help="train interactions CSV (user_id, item_id): histories / encoders")
+        p.add_argument("--encoders", type=str, default=None,
+                       help="directory with the training-time user_encoder.pkl / item_encoder.pkl (default: searched next to the "
+                            "checkpoint like scripts/evaluate.py; rebuilt from the tables only when none exist)")
         p.add_argument("--device", type=str, default="cuda:0")
         p.add_argument("--top_k", type=int, default=None)
 

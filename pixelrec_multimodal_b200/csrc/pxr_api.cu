@@ -24,6 +24,8 @@ extern "C" int pxr_create(const pxr_config* cfg, pxr_handle** out) {
   if (cudaGetDevice(&dev) != cudaSuccess) { snprintf(g_create_err, sizeof(g_create_err), "no CUDA device: libpxr has no CPU fallback"); return PXR_ERR_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { snprintf(g_create_err, sizeof(g_create_err), "cudaGetDeviceProperties failed"); return PXR_ERR_CUDA; }
+  // libpxr.so carries sm_100a code only (no PTX for other architectures, no second backend)
+  if (prop.major != 10) { snprintf(g_create_err, sizeof(g_create_err), "device %d is sm_%d%d: libpxr.so is built for sm_100a (B200) only", dev, prop.major, prop.minor); return PXR_ERR_INVALID; }
   pxr_handle* h = new pxr_handle();
   h->cfg = *cfg; h->device = dev; h->n_sm = prop.multiProcessorCount; h->err[0] = 0;
   h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
@@ -72,6 +74,12 @@ extern "C" int pxr_profile_read(pxr_handle* h, double* total_ms, int64_t* n_laun
 
 extern "C" int64_t pxr_launch_count(const pxr_handle* h) { return h ? h->launches : 0; }
 extern "C" int pxr_active_path(const pxr_handle* h) { return h ? h->path : PXR_ERR_INVALID; }
+extern "C" int pxr_set_rescore(pxr_handle* h, int on) {
+  if (!h) return PXR_ERR_INVALID;
+  h->rescore = on != 0;
+  return PXR_OK;
+}
+extern "C" int pxr_get_rescore(const pxr_handle* h) { return h ? (h->rescore ? 1 : 0) : PXR_ERR_INVALID; }
 extern "C" int pxr_set_path(pxr_handle* h, int path) {
   if (!h) return PXR_ERR_INVALID;
   if (path == PXR_PATH_TCGEN05 && !h->fast_ok) PXR_FAIL(h, PXR_ERR_INVALID, "tcgen05 path not supported for this configuration");
@@ -198,7 +206,7 @@ extern "C" int pxr_load_weights(pxr_handle* h, const pxr_weights* w, pxr_stream 
   if (h->fast_ok && (rc = pxr_tc_prepare_weights(h, st))) return rc;
   if (h->fast_ok && (rc = pxr_items_tc_prepare_weights(h, st))) return rc;
   h->weights_loaded = true;
-  h->item_feats = nullptr; h->n_rows = 0;
+  h->item_feats = nullptr; h->n_rows = 0; h->items_ready = false;
   return PXR_OK;
 }
 
@@ -227,7 +235,7 @@ extern "C" int pxr_precompute_items(pxr_handle* h, const float* item_embedding, 
   if (((uintptr_t)workspace) & 255) PXR_FAIL(h, PXR_ERR_INVALID, "item workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   h->item_feats = (float*)workspace; h->n_rows = n_rows; h->item_base = item_base;
-  h->item_missing = nullptr;
+  h->item_missing = nullptr; h->items_ready = true;
   h->item_fast = (char*)workspace + feats_bytes(h, n_rows);
   if (n_rows == 0) return PXR_OK;
   // tensor-pipe (3xTF32, fp32-accurate) item path next to the fused scoring kernel; the fp32 SIMT kernel otherwise
@@ -267,8 +275,8 @@ extern "C" int pxr_score_topk(pxr_handle* h, const float* user_embedding, const 
                               const int64_t* seen_indptr, const int32_t* seen_idx, int32_t k, float* out_scores,
                               int32_t* out_idx, void* workspace, size_t workspace_bytes, pxr_stream stream) {
   if (!h) return PXR_ERR_INVALID;
-  if (!h->item_feats && h->n_rows != 0) PXR_FAIL(h, PXR_ERR_STATE, "pxr_precompute_items must be called before scoring");
   if (!h->weights_loaded) PXR_FAIL(h, PXR_ERR_STATE, "weights not loaded");
+  if (!h->items_ready) PXR_FAIL(h, PXR_ERR_STATE, "pxr_precompute_items must be called (after pxr_load_weights) before scoring");
   if (k <= 0 || n_users < 0 || (n_users && (!user_embedding || !user_idx || !out_scores || !out_idx))) PXR_FAIL(h, PXR_ERR_INVALID, "pxr_score_topk: bad arguments");
   if (seen_indptr && !seen_idx) PXR_FAIL(h, PXR_ERR_INVALID, "seen_indptr given without seen_idx");
   if (n_users == 0) return PXR_OK;
@@ -297,7 +305,7 @@ extern "C" int pxr_score_topk(pxr_handle* h, const float* user_embedding, const 
 extern "C" int pxr_score_pairs(pxr_handle* h, const float* user_embedding, const int64_t* user_idx,
                                const int64_t* item_row, int64_t n, float* out, float* out_logit, pxr_stream stream) {
   if (!h) return PXR_ERR_INVALID;
-  if (!h->weights_loaded || !h->item_feats) PXR_FAIL(h, PXR_ERR_STATE, "weights / items not loaded");
+  if (!h->weights_loaded || !h->items_ready || !h->item_feats) PXR_FAIL(h, PXR_ERR_STATE, "weights / items not loaded");
   if (n < 0 || (n && (!user_embedding || !user_idx || !item_row || !out))) PXR_FAIL(h, PXR_ERR_INVALID, "pxr_score_pairs: bad arguments");
   return pxr_launch_score_simt(h, user_embedding, user_idx, item_row, n, 0, nullptr, nullptr, out, out_logit, false, (cudaStream_t)stream);
 }
@@ -311,15 +319,15 @@ extern "C" int pxr_merge_topk(const float* scores_in, const int32_t* idx_in, int
 extern "C" size_t pxr_metrics_bytes(int64_t n_users, int32_t n_ks) {
   (void)n_ks;
   const int64_t blocks = (n_users + 127) / 128;
-  return pxr_align_up((size_t)(blocks > 0 ? blocks : 1) * PXR_MAX_KS * 7 * sizeof(double), 256);
+  return pxr_align_up((size_t)(blocks > 0 ? blocks : 1) * PXR_MAX_KS * PXR_METRIC_COLS * sizeof(double), 256);
 }
 
 extern "C" int pxr_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, const int64_t* gt_indptr,
-                           const int32_t* gt_idx, const int32_t* ks, int32_t n_ks, const double* discount,
+                           const int32_t* gt_idx, const int32_t* recall_den, const int32_t* ks, int32_t n_ks, const double* discount,
                            const double* ideal, double* out_sums, void* workspace, size_t workspace_bytes,
                            pxr_stream stream) {
   if (n_ks <= 0 || n_ks > PXR_MAX_KS || !ks || !out_sums || n_users < 0) return PXR_ERR_INVALID;
   if (workspace_bytes < pxr_metrics_bytes(n_users, n_ks)) return PXR_ERR_WORKSPACE;
-  return pxr_launch_metrics(topk_idx, k_stride, n_users, gt_indptr, gt_idx, ks, n_ks, discount, ideal, out_sums,
+  return pxr_launch_metrics(topk_idx, k_stride, n_users, gt_indptr, gt_idx, recall_den, ks, n_ks, discount, ideal, out_sums,
                             workspace, (cudaStream_t)stream);
 }

@@ -32,6 +32,7 @@ struct pxr_handle {
   int64_t launches = 0;
   int path = PXR_PATH_SIMT;   // resolved path
   bool weights_loaded = false;
+  bool items_ready = false;   // pxr_precompute_items ran since the last pxr_load_weights
 
   // weight arena (device)
   void* arena = nullptr;
@@ -47,6 +48,7 @@ struct pxr_handle {
 
   // fast (tcgen05) path images
   bool fast_ok = false;
+  bool rescore = true;        // exact mode of the fused path: fp32 re-score + re-rank of the 64-slot lists (pxr_set_rescore)
   uint32_t tc_attr_set = 0;   // bit per kernel whose max-dynamic-smem attribute has been set
   void* fast_w = nullptr;     // bf16 swizzled operand images + fp32 vectors (see score_tc.cu)
   float tc_bias_host[1028];   // attention fast path: host copy of b1' b2 b3 w4 b4 (passed as kernel parameters)
@@ -224,8 +226,12 @@ int pxr_launch_topk_rows(pxr_handle* h, const float* scores, int64_t n_users, in
                          int32_t k, float* out_scores, int32_t* out_idx, cudaStream_t st);
 int pxr_launch_merge(const float* scores_in, const int32_t* idx_in, int32_t n_shards, int64_t n_users, int32_t k,
                      float* out_scores, int32_t* out_idx, cudaStream_t st);
+// exact mode: fp32 re-score + re-rank of (n_users, 64) candidate lists (global indices, -1 padded) -> (n_users, k)
+size_t pxr_rescore_bytes(int64_t n_users);
+int pxr_launch_rescore(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
+                       const int32_t* list_idx, int32_t k, float* out_scores, int32_t* out_idx, void* ws, cudaStream_t st);
 int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, const int64_t* gt_indptr,
-                       const int32_t* gt_idx, const int32_t* ks, int32_t n_ks, const double* discount,
+                       const int32_t* gt_idx, const int32_t* recall_den, const int32_t* ks, int32_t n_ks, const double* discount,
                        const double* ideal, double* out_sums, void* ws, cudaStream_t st);
 
 // tcgen05 path (score_tc.cu)

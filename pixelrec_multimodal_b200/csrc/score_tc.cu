@@ -1424,11 +1424,15 @@ static TcPlan tc_plan(const pxr_handle* h, int64_t n_users) {
   return pl;
 }
 
+// workspace: [S > 1: per-split partial lists][exact mode: the merged 64-slot lists + the re-score pair arrays]
 size_t pxr_tc_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k) {
   if (n_users <= 0 || h->n_rows <= 0) return 256;
   const TcPlan pl = tc_plan(h, n_users);
-  if (pl.S == 1) return 256;
-  return pxr_align_up((size_t)pl.S * n_users * k * 8, 256) + 256;
+  const int kk = h->rescore ? tc::KCAP : k;
+  size_t b = 256;
+  if (pl.S > 1) b += pxr_align_up((size_t)pl.S * n_users * kk * 8, 256);
+  if (h->rescore) b += pxr_align_up((size_t)n_users * kk * 8, 256) + pxr_rescore_bytes(n_users);
+  return b;
 }
 
 int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
@@ -1457,13 +1461,26 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
   p.item_missing = h->item_missing;
   p.n_users = n_users; p.n_rows = h->n_rows; p.item_base = h->item_base;
   p.Dm = h->cfg.embedding_dim;
-  p.M = h->M; p.K = k; p.S = pl.S; p.rows_per_split = pl.rows_per_split; p.n_units = pl.n_units;
+  // exact mode: the kernel keeps its full 64-slot list per user (admission threshold = 64th best); the lists are
+  // re-scored in fp32 and re-ranked afterwards (pxr_launch_rescore)
+  const bool exact = h->rescore;
+  const int32_t kk = exact ? tc::KCAP : k;
+  p.M = h->M; p.K = kk; p.S = pl.S; p.rows_per_split = pl.rows_per_split; p.n_units = pl.n_units;
   p.final_act = h->cfg.final_activation;
-  float* part_s = out_scores; int32_t* part_i = out_idx;
+  if (ws_bytes < pxr_tc_topk_bytes(h, n_users, k)) PXR_FAIL(h, PXR_ERR_WORKSPACE, "tcgen05 top-K workspace too small");
+  char* wp = (char*)ws;
+  float* part_s = out_scores; int32_t* part_i = out_idx;       // what the kernel writes
+  float* list_s = out_scores; int32_t* list_i = out_idx;       // the merged lists
   if (pl.S > 1) {
-    const size_t need = (size_t)pl.S * n_users * k;
-    if (ws_bytes < need * 8) PXR_FAIL(h, PXR_ERR_WORKSPACE, "tcgen05 top-K workspace too small");
-    part_s = (float*)ws; part_i = (int32_t*)((char*)ws + need * 4);
+    const size_t need = (size_t)pl.S * n_users * kk;
+    part_s = (float*)wp; part_i = (int32_t*)(wp + need * 4);
+    wp += pxr_align_up(need * 8, 256);
+  }
+  if (exact) {
+    const size_t need = (size_t)n_users * kk;
+    list_s = (float*)wp; list_i = (int32_t*)(wp + need * 4);
+    wp += pxr_align_up(need * 8, 256);
+    if (pl.S == 1) { part_s = list_s; part_i = list_i; }
   }
   p.out_scores = part_s; p.out_idx = part_i;
   int rc;
@@ -1476,9 +1493,10 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
                                 : tc::launch_fused<tc::F_CONCAT, tc::FMT_FP16>(h, p, pl.n_pairs, st);
   if (rc) return rc;
   if (pl.S > 1) {
-    rc = pxr_launch_merge(part_s, part_i, pl.S, n_users, k, out_scores, out_idx, st);
+    rc = pxr_launch_merge(part_s, part_i, pl.S, n_users, kk, list_s, list_i, st);
     h->launches++;
     if (rc) PXR_FAIL(h, rc, "top-K merge of %d item splits failed", pl.S);
   }
+  if (exact) return pxr_launch_rescore(h, user_embedding, user_idx, n_users, list_i, k, out_scores, out_idx, wp, st);
   return PXR_OK;
 }

@@ -626,16 +626,87 @@ int pxr_launch_merge(const float* scores_in, const int32_t* idx_in, int32_t n_sh
 }
 
 // ===========================================================================
+// Exact mode of the fused path: fp32 re-score of the candidate lists the 16-bit kernel kept (K3r).
+// The fused kernel ranks with 16-bit operands; its 64-slot list per user is a superset of the exact top-K whenever the
+// exact top-K lies inside the 16-bit top-64 (measured at catalogue scale: always, tests/test_gpu_parity.py).  The
+// candidates are scored again with the literal fp32 arithmetic of pxr_score_pairs (score_simt_kernel) and ranked
+// again with the reference's tie-break (stable sort over index order, recommender.py:105 -> lower index first).
+// ===========================================================================
+__global__ void rescore_prep_kernel(const int64_t* __restrict__ user_idx, const int32_t* __restrict__ list_idx, int64_t n_pairs,
+                                    int L, int64_t item_base, int64_t* __restrict__ pair_user, int64_t* __restrict__ pair_row) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  const int32_t gi = list_idx[i];
+  pair_user[i] = gi < 0 ? -1 : user_idx[i / L];     // -1: padding slot, score_simt_kernel computes on zeros and the sort drops it
+  pair_row[i] = gi < 0 ? 0 : (int64_t)gi - item_base;
+}
+
+// full bitonic sort (descending) of 64 keys held two per lane: slot lane in x0, slot lane + 32 in x1
+__device__ __forceinline__ void sort64_desc(unsigned long long& x0, unsigned long long& x1, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride == 32) {                                   // size == 64: partner is the other register of the lane
+        if (x1 > x0) { const unsigned long long t = x0; x0 = x1; x1 = t; }
+      } else {
+        const unsigned long long p0 = __shfl_xor_sync(0xffffffffu, x0, stride), p1 = __shfl_xor_sync(0xffffffffu, x1, stride);
+        const bool lower = (lane & stride) == 0;
+        const bool desc0 = size == 64 ? true : (size == 32 ? true : (lane & size) == 0);    // element index lane
+        const bool desc1 = size == 64 ? true : (size == 32 ? false : (lane & size) == 0);   // element index lane + 32
+        merge_cx(x0, p0, lower == desc0);
+        merge_cx(x1, p1, lower == desc1);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) rescore_sort_kernel(const float* __restrict__ rescored, const int32_t* __restrict__ list_idx,
+                                                           int64_t n_users, int k, float* __restrict__ out_scores,
+                                                           int32_t* __restrict__ out_idx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (u >= n_users) return;
+  const int32_t i0 = list_idx[u * 64 + lane], i1 = list_idx[u * 64 + 32 + lane];
+  unsigned long long x0 = i0 < 0 ? 0ull : pxr_key(rescored[u * 64 + lane], (uint32_t)i0);
+  unsigned long long x1 = i1 < 0 ? 0ull : pxr_key(rescored[u * 64 + 32 + lane], (uint32_t)i1);
+  sort64_desc(x0, x1, lane);
+  if (lane < k) { out_scores[u * k + lane] = x0 ? pxr_key_score(x0) : -INFINITY; out_idx[u * k + lane] = x0 ? (int32_t)pxr_key_idx(x0) : -1; }
+  if (lane + 32 < k) { out_scores[u * k + lane + 32] = x1 ? pxr_key_score(x1) : -INFINITY; out_idx[u * k + lane + 32] = x1 ? (int32_t)pxr_key_idx(x1) : -1; }
+}
+
+size_t pxr_rescore_bytes(int64_t n_users) { return pxr_align_up((size_t)n_users * 64 * (8 + 8 + 4), 256); }
+
+int pxr_launch_rescore(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
+                       const int32_t* list_idx, int32_t k, float* out_scores, int32_t* out_idx, void* ws, cudaStream_t st) {
+  if (n_users == 0) return PXR_OK;
+  const int64_t n_pairs = n_users * 64;
+  int64_t* pair_user = (int64_t*)ws;
+  int64_t* pair_row = pair_user + n_pairs;
+  float* resc = (float*)(pair_row + n_pairs);
+  rescore_prep_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(user_idx, list_idx, n_pairs, 64, h->item_base, pair_user, pair_row);
+  h->launches++;
+  PXR_CUDA(h, cudaGetLastError());
+  const int rc = pxr_launch_score_simt(h, user_embedding, pair_user, pair_row, n_pairs, 0, nullptr, nullptr, resc, nullptr, false, st);
+  if (rc) return rc;
+  rescore_sort_kernel<<<(unsigned)((n_users + 7) / 8), 256, 0, st>>>(resc, list_idx, n_users, k, out_scores, out_idx);
+  h->launches++;
+  PXR_CUDA(h, cudaGetLastError());
+  return PXR_OK;
+}
+
+// ===========================================================================
 // K5: ranking metrics (reference tasks.py:567-635, 718-747; metrics.py:63-100)
 // ===========================================================================
-#define METRIC_COLS 7
+#define METRIC_COLS 9      // precision, recall, f1, hit_rate, ndcg, mrr, ndcg (metrics.py), precision hits/k (metrics.py:35), MAP (metrics.py:102-133)
 #define METRIC_THREADS 128
 
 struct MetricKs { int n; int k[PXR_MAX_KS]; };
 
 __global__ void __launch_bounds__(METRIC_THREADS) metrics_user_kernel(const int32_t* __restrict__ topk, int k_stride,
                                                                        int64_t n_users, const int64_t* __restrict__ gt_indptr,
-                                                                       const int32_t* __restrict__ gt_idx, MetricKs ks,
+                                                                       const int32_t* __restrict__ gt_idx,
+                                                                       const int32_t* __restrict__ recall_den, MetricKs ks,
                                                                        const double* __restrict__ discount,
                                                                        const double* __restrict__ ideal,
                                                                        double* __restrict__ block_sums) {
@@ -649,25 +720,28 @@ __global__ void __launch_bounds__(METRIC_THREADS) metrics_user_kernel(const int3
     if (npos > 0) {                                   // "if not pos_set: continue" (tasks.py:589-591)
       const int32_t* rec = topk + u * k_stride;
       int hits = 0, nrec = 0, first = 0, ki = 0;
-      double dcg = 0.0;
+      double dcg = 0.0, apsum = 0.0;
+      const int rden = recall_den ? recall_den[u] : npos;          // len(positive_items): raw rows, tasks.py:579
       for (int j = 0; j < k_stride && ki < ks.n; ++j) {
         const int32_t it = rec[j];
         if (it >= 0) {
           nrec++;
           bool hit = false;
           for (int64_t g = g0; g < g1; ++g) if (gt_idx[g] == it) { hit = true; break; }
-          if (hit) { hits++; dcg += discount[j]; if (!first) first = j + 1; }
+          if (hit) { hits++; dcg += discount[j]; apsum += (double)hits / (double)(j + 1); if (!first) first = j + 1; }
         }
         while (ki < ks.n && j + 1 == ks.k[ki]) {     // cut-offs ascending
           const int k = ks.k[ki];
           const double prec = nrec > 0 ? (double)hits / (double)nrec : 0.0;   // denominator len(recs), tasks.py:577
-          const double rec_ = (double)hits / (double)npos;
+          const double rec_ = rden > 0 ? (double)hits / (double)rden : 0.0;
           const double f1 = (prec + rec_) > 0.0 ? 2.0 * prec * rec_ / (prec + rec_) : 0.0;
           const double idcg = ideal[npos < k ? npos : k];
           vals[ki][0] = prec; vals[ki][1] = rec_; vals[ki][2] = f1; vals[ki][3] = hits > 0 ? 1.0 : 0.0;
           vals[ki][4] = idcg > 0.0 ? dcg / idcg : 0.0;
           vals[ki][5] = first ? 1.0 / (double)first : 0.0;
           vals[ki][6] = hits > 0 ? dcg / ideal[hits] : 0.0;
+          vals[ki][7] = nrec > 0 ? (double)hits / (double)k : 0.0;           // metrics.py:29-35
+          vals[ki][8] = hits > 0 ? apsum / (double)npos : 0.0;               // metrics.py:119-133 on the first k entries
           ki++;
         }
       }
@@ -701,7 +775,8 @@ template <int NKS>     // cut-offs kept in registers (2 covers the usual @10 / @
 __global__ void __launch_bounds__(32 * METRIC_WARPS, (NKS <= 2 ? 8 : 2)) metrics_warp_kernel(const int32_t* __restrict__ topk, int k_stride,
                                                                          int64_t n_users, int64_t users_per_warp,
                                                                          const int64_t* __restrict__ gt_indptr,
-                                                                         const int32_t* __restrict__ gt_idx, MetricKs ks,
+                                                                         const int32_t* __restrict__ gt_idx,
+                                                                         const int32_t* __restrict__ recall_den, MetricKs ks,
                                                                          const double* __restrict__ discount,
                                                                          const double* __restrict__ ideal,
                                                                          double* __restrict__ block_sums) {
@@ -761,7 +836,9 @@ __global__ void __launch_bounds__(32 * METRIC_WARPS, (NKS <= 2 ? 8 : 2)) metrics
         const int32_t* rec = topk + (ub + lane) * k_stride;
         for (int j = 0; j < k_stride; ++j) valid |= (unsigned long long)(__ldg(rec + j) >= 0) << j;
         const int first = hit ? __ffsll((long long)hit) : 0;
-        double dcg = 0.0;
+        double dcg = 0.0, apsum = 0.0;
+        int nh = 0;
+        const int rden = recall_den ? __ldg(recall_den + ub + lane) : npos;   // len(positive_items): raw rows, tasks.py:579
         unsigned long long rest = hit;
 #pragma unroll
         for (int a = 0; a < NKS; ++a) {
@@ -772,17 +849,20 @@ __global__ void __launch_bounds__(32 * METRIC_WARPS, (NKS <= 2 ? 8 : 2)) metrics
               const int j = __ffsll((long long)rest) - 1;
               if (j >= k) break;
               dcg += discount[j];
+              apsum += (double)(++nh) / (double)(j + 1);
               rest &= rest - 1;
             }
             const int hits = __popcll(hit & km), nrec = __popcll(valid & km);
             const double prec = nrec > 0 ? (double)hits / (double)nrec : 0.0;   // denominator len(recs), tasks.py:577
-            const double rec_ = (double)hits / (double)npos;
+            const double rec_ = rden > 0 ? (double)hits / (double)rden : 0.0;
             const double f1 = (prec + rec_) > 0.0 ? 2.0 * prec * rec_ / (prec + rec_) : 0.0;
             const double idcg = ideal[npos < k ? npos : k];
             sums[a][0] += prec; sums[a][1] += rec_; sums[a][2] += f1; sums[a][3] += hits > 0 ? 1.0 : 0.0;
             sums[a][4] += idcg > 0.0 ? dcg / idcg : 0.0;
             sums[a][5] += (first && first <= k) ? 1.0 / (double)first : 0.0;
             sums[a][6] += hits > 0 ? dcg / ideal[hits] : 0.0;
+            sums[a][7] += nrec > 0 ? (double)hits / (double)k : 0.0;            // metrics.py:29-35
+            sums[a][8] += hits > 0 ? apsum / (double)npos : 0.0;                // metrics.py:119-133 on the first k entries
           }
         }
       }
@@ -818,7 +898,7 @@ __global__ void metrics_final_kernel(const double* __restrict__ block_sums, int6
 }
 
 int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, const int64_t* gt_indptr,
-                       const int32_t* gt_idx, const int32_t* ks, int32_t n_ks, const double* discount,
+                       const int32_t* gt_idx, const int32_t* recall_den, const int32_t* ks, int32_t n_ks, const double* discount,
                        const double* ideal, double* out_sums, void* ws, cudaStream_t st) {
   MetricKs mk; mk.n = n_ks;
   for (int i = 0; i < n_ks; ++i) { mk.k[i] = ks[i]; if (i && ks[i] <= ks[i - 1]) return PXR_ERR_INVALID; if (ks[i] > k_stride || ks[i] <= 0) return PXR_ERR_INVALID; }
@@ -832,13 +912,13 @@ int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_user
     const int64_t warps = blocks * METRIC_WARPS;
     const int64_t upw = (n_users + warps - 1) / warps;
     if (n_ks <= 2)
-      metrics_warp_kernel<2><<<(unsigned)blocks, 32 * METRIC_WARPS, 0, st>>>(topk_idx, k_stride, n_users, upw, gt_indptr, gt_idx, mk,
+      metrics_warp_kernel<2><<<(unsigned)blocks, 32 * METRIC_WARPS, 0, st>>>(topk_idx, k_stride, n_users, upw, gt_indptr, gt_idx, recall_den, mk,
                                                                             discount, ideal, (double*)ws);
     else
       metrics_warp_kernel<PXR_MAX_KS><<<(unsigned)blocks, 32 * METRIC_WARPS, 0, st>>>(topk_idx, k_stride, n_users, upw, gt_indptr, gt_idx,
-                                                                                     mk, discount, ideal, (double*)ws);
+                                                                                     recall_den, mk, discount, ideal, (double*)ws);
   } else {
-    metrics_user_kernel<<<(unsigned)blocks, METRIC_THREADS, 0, st>>>(topk_idx, k_stride, n_users, gt_indptr, gt_idx, mk,
+    metrics_user_kernel<<<(unsigned)blocks, METRIC_THREADS, 0, st>>>(topk_idx, k_stride, n_users, gt_indptr, gt_idx, recall_den, mk,
                                                                      discount, ideal, (double*)ws);
   }
   metrics_final_kernel<<<n_ks * METRIC_COLS, 32, 0, st>>>((const double*)ws, blocks, n_ks, out_sums);

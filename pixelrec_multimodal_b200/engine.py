@@ -27,6 +27,24 @@ def _dev_f32(t, device):
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+def _dev_idx(t, device, dtype=torch.int64):
+    """Index tensors reach the kernels as raw pointers: normalise dtype / device / layout here (no-ops when the caller
+    already passes the right thing)."""
+    return torch.as_tensor(t).detach().to(device=device, dtype=dtype).contiguous()
+
+
+def check_index_range(idx, n: int, what: str):
+    """The reference raises IndexError from ``nn.Embedding`` on an out-of-range index (multimodal.py:553-555); the
+    kernels would read out of bounds instead.  One min/max reduction (a device sync for CUDA tensors): used on the
+    API entry points that take caller-supplied indices, not inside the block loop."""
+    t = torch.as_tensor(idx)
+    if t.numel() == 0:
+        return
+    lo, hi = int(t.min()), int(t.max())
+    if lo < 0 or hi >= n:
+        raise IndexError(f"{what} out of range: [{lo}, {hi}] not inside [0, {n})")
+
+
 class PxrEngine:
     """One handle = one model configuration on one GPU (not thread-safe)."""
 
@@ -34,7 +52,7 @@ class PxrEngine:
                  num_numerical: int, hidden_dims: Sequence[int], n_tags: int, num_heads: int = 4,
                  activation: str = "relu", final_activation: str = "sigmoid", use_batch_norm: bool = True,
                  projection_hidden_dim: Optional[int] = None, path: str = "auto", precision: str = "bf16",
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, rescore: bool = True):
         if not torch.cuda.is_available():
             raise PxrError("PxrEngine needs a CUDA device: the scoring path has no CPU fallback")
         self.lib = _lib.load()
@@ -73,11 +91,13 @@ class PxrEngine:
             rc = self.lib.pxr_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             raise PxrError(f"pxr_create failed ({rc}): {self.lib.pxr_last_error(None).decode()}")
+        self.set_rescore(rescore)
         self._keep: Dict[str, object] = {}
         self._items_ws: Optional[torch.Tensor] = None
         self._score_ws: Optional[torch.Tensor] = None
         self.n_rows = 0
         self.item_base = 0
+        self.items_token = None
 
     # ------------------------------------------------------------------ util
     def close(self):
@@ -112,6 +132,15 @@ class PxrEngine:
         ms, n = C.c_double(0.0), C.c_int64(0)
         self._check(self.lib.pxr_profile_read(self._h, C.byref(ms), C.byref(n)), "pxr_profile_read")
         return float(ms.value), int(n.value)
+
+    def set_rescore(self, on: bool):
+        """Exact mode of the fused path (include/pxr.h: pxr_set_rescore): fp32 re-score + re-rank of the 64
+        candidates the 16-bit kernel keeps per user.  On by default."""
+        self._check(self.lib.pxr_set_rescore(self._h, int(bool(on))), "pxr_set_rescore")
+
+    @property
+    def rescore(self) -> bool:
+        return bool(self.lib.pxr_get_rescore(self._h))
 
     def set_path(self, path: str):
         self._check(self.lib.pxr_set_path(self._h, _lib.PATH[path]), "pxr_set_path")
@@ -183,7 +212,12 @@ class PxrEngine:
         dev = self.device
         n = int(n_rows if n_rows is not None else tag_idx.shape[0])
         emb = _dev_f32(item_embedding, dev)
-        tag = tag_idx.to(device=dev, dtype=torch.int64).contiguous()
+        if emb.dim() != 2 or emb.shape[1] != self.D:
+            raise ValueError(f"item_embedding must be (n_items, {self.D}), got {tuple(emb.shape)}")
+        tag = _dev_idx(tag_idx, dev)
+        if tag.shape[0] < n:
+            raise ValueError(f"tag_idx has {tag.shape[0]} entries for {n} item rows")
+        check_index_range(tag[:n], int(self.cfg.n_tags), "tag_idx")
         v = _dev_f32(vis, dev) if vis is not None and self.cfg.vision_dim else None
         t = _dev_f32(txt, dev) if txt is not None and self.cfg.language_dim else None
         x = _dev_f32(num, dev) if num is not None and self.cfg.num_numerical else None
@@ -192,7 +226,11 @@ class PxrEngine:
             if dim and (ten is None or ten.shape[0] < n or ten.shape[-1] != dim):
                 raise ValueError(f"{name} features must be ({n}, {dim}), got "
                                  f"{None if ten is None else tuple(ten.shape)}")
-        ii = item_idx.to(device=dev, dtype=torch.int64).contiguous() if item_idx is not None else None
+        ii = _dev_idx(item_idx, dev) if item_idx is not None else None
+        if ii is not None:
+            check_index_range(ii[:n], int(emb.shape[0]), "item_idx")
+        elif int(item_base) < 0 or int(item_base) + n > int(emb.shape[0]):
+            raise IndexError(f"item rows [{item_base}, {int(item_base) + n}) not inside the item embedding table ({emb.shape[0]} rows)")
         nbytes = int(self.lib.pxr_items_bytes(self._h, n))
         ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
         off = (-ws.data_ptr()) % 256
@@ -204,6 +242,7 @@ class PxrEngine:
         self._keep["items_in"] = (emb, tag, v, t, x, ii)   # inputs must outlive the async launch
         self._keep.pop("missing", None)
         self.n_rows, self.item_base = n, int(item_base)
+        self.items_token = None                            # set by the owner of the records (FastRecommender.engine)
 
     def set_missing_items(self, flags: Optional[torch.Tensor]):
         """Per-row flags (bool / uint8, aligned with the precomputed rows): flagged items score exactly 0.0, as
@@ -217,10 +256,30 @@ class PxrEngine:
         self._keep["missing"] = f
 
     # --------------------------------------------------------------- scoring
+    def _user_args(self, user_embedding: torch.Tensor, user_idx):
+        """dtype / device / layout of the two tensors every scoring call hands to the kernels as raw pointers
+        (index RANGES are checked by the callers that receive them from outside: FastRecommender, forward)."""
+        dev = self.device
+        if not isinstance(user_embedding, torch.Tensor) or user_embedding.dim() != 2 or user_embedding.shape[1] != self.D:
+            raise ValueError(f"user_embedding must be a (n_users, {self.D}) tensor")
+        if user_embedding.device != dev or user_embedding.dtype != torch.float32 or not user_embedding.is_contiguous():
+            user_embedding = _dev_f32(user_embedding, dev)
+        user_idx = _dev_idx(user_idx, dev)
+        if user_idx.dim() != 1:
+            raise ValueError("user_idx must be 1-D")
+        return user_embedding, user_idx
+
     def score_topk(self, user_embedding: torch.Tensor, user_idx: torch.Tensor, k: int,
                    seen_indptr: Optional[torch.Tensor] = None, seen_idx: Optional[torch.Tensor] = None
                    ) -> Tuple[torch.Tensor, torch.Tensor]:
         dev = self.device
+        user_embedding, user_idx = self._user_args(user_embedding, user_idx)
+        if (seen_indptr is None) != (seen_idx is None):
+            raise ValueError("seen_indptr and seen_idx go together")
+        if seen_indptr is not None:
+            seen_indptr, seen_idx = _dev_idx(seen_indptr, dev), _dev_idx(seen_idx, dev, torch.int32)
+            if seen_indptr.shape[0] != user_idx.shape[0] + 1:
+                raise ValueError("seen_indptr must have n_users + 1 entries")
         n = int(user_idx.shape[0])
         out_s = torch.empty((n, k), dtype=torch.float32, device=dev)
         out_i = torch.empty((n, k), dtype=torch.int32, device=dev)
@@ -239,6 +298,10 @@ class PxrEngine:
     def score_pairs(self, user_embedding: torch.Tensor, user_idx: torch.Tensor, item_row: torch.Tensor,
                     want_logit: bool = False):
         dev = self.device
+        user_embedding, user_idx = self._user_args(user_embedding, user_idx)
+        item_row = _dev_idx(item_row, dev)
+        if item_row.shape != user_idx.shape:
+            raise ValueError("user_idx and item_row must have the same length")
         n = int(user_idx.shape[0])
         out = torch.empty(n, dtype=torch.float32, device=dev)
         logit = torch.empty(n, dtype=torch.float32, device=dev) if want_logit else None
@@ -280,7 +343,7 @@ def merge_topk(scores: torch.Tensor, idx: torch.Tensor) -> Tuple[torch.Tensor, t
     return out_s, out_i
 
 
-_METRIC_COLS = ("precision", "recall", "f1", "hit_rate", "ndcg", "mrr", "ndcg_list_ideal")
+_METRIC_COLS = ("precision", "recall", "f1", "hit_rate", "ndcg", "mrr", "ndcg_list_ideal", "precision_hits_over_k", "map")
 
 
 def sample_candidates(user_idx: torch.Tensor, pos_indptr: torch.Tensor, pos_idx: torch.Tensor, n_items: int,
@@ -327,24 +390,29 @@ def _metric_tables(kstride: int, dev):
 
 
 def ranking_metric_sums(topk_idx: torch.Tensor, gt_indptr: torch.Tensor, gt_idx: torch.Tensor,
-                        ks: Sequence[int], as_device: bool = False):
-    """K5: per-cut-off sums over users, shape (len(ks), 7) float64 (host; the device tensor, without a
-    synchronisation, when ``as_device``).  Column order: precision, recall, f1, hit_rate, ndcg (tasks.py), mrr,
-    ndcg (metrics.py)."""
+                        ks: Sequence[int], as_device: bool = False, recall_den: Optional[torch.Tensor] = None):
+    """K5: per-cut-off sums over users, shape (len(ks), 9) float64 (host; the device tensor, without a
+    synchronisation, when ``as_device``).  Column order: precision (hits / len(recs)), recall, f1, hit_rate, ndcg
+    (tasks.py), mrr, ndcg (metrics.py), precision (hits / k, metrics.py:35), average precision (metrics.py:102-133).
+    ``recall_den``: per-user recall denominators (raw number of test rows, tasks.py:579); default = the number of
+    distinct positives in the CSR."""
     lib = _lib.load()
     dev = topk_idx.device
     topk_idx = topk_idx.to(torch.int32).contiguous()
     n, kstride = topk_idx.shape
     ks = sorted(int(k) for k in ks)
     d_disc, d_ideal = _metric_tables(kstride, dev)
-    out = torch.empty((len(ks), 7), dtype=torch.float64, device=dev)
+    out = torch.empty((len(ks), _lib.PXR_METRIC_COLS), dtype=torch.float64, device=dev)
+    rden = recall_den.to(device=dev, dtype=torch.int32).contiguous() if recall_den is not None else None
+    if rden is not None and rden.shape[0] != n:
+        raise ValueError("recall_den must have one entry per user")
     nbytes = int(lib.pxr_metrics_bytes(n, len(ks)))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     ks_arr = (C.c_int32 * len(ks))(*ks)
     gt_indptr = gt_indptr.to(device=dev, dtype=torch.int64).contiguous()
     gt_idx = gt_idx.to(device=dev, dtype=torch.int32).contiguous()
     with torch.cuda.device(dev):
-        rc = lib.pxr_metrics(_ptr(topk_idx), kstride, n, _ptr(gt_indptr), _ptr(gt_idx), ks_arr, len(ks),
+        rc = lib.pxr_metrics(_ptr(topk_idx), kstride, n, _ptr(gt_indptr), _ptr(gt_idx), _ptr(rden), ks_arr, len(ks),
                              _ptr(d_disc), _ptr(d_ideal), _ptr(out), _ptr(ws), nbytes, _stream())
     if rc != 0:
         raise PxrError(f"pxr_metrics failed ({rc})")

@@ -18,23 +18,82 @@ import torch
 from .engine import ranking_metric_sums, sample_candidates
 
 _COLS = ("avg_precision_at_k", "avg_recall_at_k", "avg_f1_at_k", "avg_hit_rate_at_k", "avg_ndcg_at_k", "avg_mrr",
-         "avg_ndcg_list_ideal_at_k")
+         "avg_ndcg_list_ideal_at_k", "avg_precision_hits_over_k", "avg_map_at_k")
+# columns of by_k that are not keys of the reference result dict (tasks.py:623-630): the standalone definitions of
+# src/evaluation/metrics.py (NDCG normalised by the list's own ideal :63-100, precision = hits / k :35, MAP :102-133)
+_EXTRA_COLS = ("avg_ndcg_list_ideal_at_k", "avg_precision_hits_over_k", "avg_map_at_k")
 
 
-def ranking_metrics(topk_idx: torch.Tensor, gt_indptr, gt_idx, ks: Sequence[int]) -> Dict[int, Dict[str, float]]:
+def ranking_metrics(topk_idx: torch.Tensor, gt_indptr, gt_idx, ks: Sequence[int], recall_den=None,
+                    n_total: Optional[int] = None) -> Dict[int, Dict[str, float]]:
     """Means over ALL users of the batch (users without positives contribute
-    zeros, tasks.py:589-591, 623-630).  Keys follow tasks.py:623-630;
-    ``avg_ndcg_list_ideal_at_k`` is the other NDCG definition the reference ships
-    (``src/evaluation/metrics.py:63-100``)."""
+    zeros, tasks.py:589-591, 623-630).  Keys follow tasks.py:623-630; the ``_EXTRA_COLS`` are the standalone
+    definitions the reference ships in ``src/evaluation/metrics.py``.  ``recall_den``: raw positive-row counts
+    (tasks.py:579); ``n_total``: number of users in the mean when it exceeds the rows of ``topk_idx`` (test users
+    unknown to the encoder get no list and count as zeros, tasks.py:537-540)."""
     gt_indptr = torch.as_tensor(gt_indptr)
     gt_idx = torch.as_tensor(gt_idx)
-    n = int(topk_idx.shape[0])
-    sums = ranking_metric_sums(topk_idx, gt_indptr, gt_idx, ks)
+    n = int(n_total if n_total is not None else topk_idx.shape[0])
+    sums = ranking_metric_sums(topk_idx, gt_indptr, gt_idx, ks,
+                               recall_den=None if recall_den is None else torch.as_tensor(recall_den))
+    return _by_k(sums, ks, n)
+
+
+def _by_k(sums, ks, n: int) -> Dict[int, Dict[str, float]]:
     out = {}
     for row, k in zip(sums, sorted(int(k) for k in ks)):
         out[k] = {c: (float(v) / n if n else 0.0) for c, v in zip(_COLS, row)}
         out[k]["num_users_evaluated"] = n
     return out
+
+
+def build_ground_truth(recommender, test_data):
+    """The per-user ground truth of ``TopKRetrievalEvaluator`` (tasks.py:537-540, 322-326, 576-603) as arrays.
+
+    Every distinct ``user_id`` of the test table is one evaluated user (``groupby('user_id')``, string order), known
+    to the encoders or not.  For a user the reference keeps ``positive_items`` = ALL its rows as strings: the recall
+    denominator is the raw row count (duplicates and items unknown to the item encoder included, :579), hits / NDCG /
+    MRR use the SET of those strings (:586-603, ideal DCG over ``min(len(set), K)``).  An unknown item can never be
+    recommended, so it only widens the set: it is given a virtual index >= n_items that no list entry equals.
+
+    Returns a dict: ``users`` (encoder indices of the KNOWN test users, string order), ``n_total`` (all distinct test
+    users), ``unknown_users`` (their ids), ``gt_indptr / gt_idx`` (the positive SET per known user, ascending, virtual
+    indices last), ``recall_den`` (raw row counts), ``pos_indptr / pos_idx`` (known positives only, for samplers)."""
+    r = recommender
+    uid = test_data["user_id"].astype(str).to_numpy(dtype=object).astype(str)
+    iid = test_data["item_id"].astype(str).to_numpy(dtype=object).astype(str)
+    users_all, inv = np.unique(uid, return_inverse=True) if len(uid) else (np.zeros(0, dtype=str), np.zeros(0, np.int64))
+    umap, imap = r.user_index, r.item_index
+    u_enc = np.fromiter((umap.get(str(u), -1) for u in users_all), dtype=np.int64, count=len(users_all))
+    known_u = u_enc >= 0
+    slot = np.cumsum(known_u) - 1                                  # position among the known users
+    rows = known_u[inv] if len(inv) else np.zeros(0, bool)
+    seg = slot[inv[rows]] if len(inv) else np.zeros(0, np.int64)
+    items = iid[rows]
+    n_known = int(known_u.sum())
+    n_items = int(r.n_items)
+    it = np.fromiter((imap.get(str(i), -1) for i in items), dtype=np.int64, count=len(items))
+    unk = it < 0
+    if unk.any():
+        _, code = np.unique(items[unk], return_inverse=True)
+        it[unk] = n_items + code
+        if n_items + int(code.max()) >= (1 << 31) - 1:
+            raise ValueError("too many unknown test items for int32 virtual indices")
+    recall_den = np.bincount(seg, minlength=n_known).astype(np.int32) if n_known else np.zeros(0, np.int32)
+    pairs = np.unique(seg * (1 << 32) + it) if len(seg) else np.zeros(0, np.int64)
+    pu, pi = pairs >> 32, pairs & 0xFFFFFFFF
+
+    def csr(u, i):
+        ptr = np.zeros(n_known + 1, dtype=np.int64)
+        if len(u):
+            np.add.at(ptr, u + 1, 1)
+        return np.cumsum(ptr), i.astype(np.int32)
+
+    gt_indptr, gt_idx = csr(pu, pi)
+    kn = pi < n_items
+    pos_indptr, pos_idx = csr(pu[kn], pi[kn])
+    return dict(users=u_enc[known_u], n_total=len(users_all), unknown_users=[str(u) for u in users_all[~known_u]],
+                gt_indptr=gt_indptr, gt_idx=gt_idx, recall_den=recall_den, pos_indptr=pos_indptr, pos_idx=pos_idx)
 
 
 def novelty_tables(interactions_items: np.ndarray, n_hist_users: int, n_items: int):
@@ -204,20 +263,12 @@ class FullCatalogueEvaluator:
         self.ks = sorted(set(int(k) for k in (ks or [top_k])) | {self.top_k})
         self.filter_seen = filter_seen
         self.keep_predictions = keep_predictions
-        r = recommender
-        uu = test_data["user_id"].astype(str).map(r.user_index)
-        ii = test_data["item_id"].astype(str).map(r.item_index)
-        ok = uu.notna() & ii.notna()
-        u = uu[ok].to_numpy(dtype=np.int64)
-        i = ii[ok].to_numpy(dtype=np.int64)
-        pairs = np.unique(u * (1 << 32) + i)
-        u, i = pairs >> 32, pairs & 0xFFFFFFFF
-        self.users = np.unique(u)                              # groupby('user_id') order (tasks.py:537)
-        remap = {int(x): j for j, x in enumerate(self.users)}
-        cnt = np.zeros(len(self.users) + 1, dtype=np.int64)
-        np.add.at(cnt, np.array([remap[int(x)] for x in u], dtype=np.int64) + 1, 1)
-        self.gt_indptr = np.cumsum(cnt)
-        self.gt_idx = i.astype(np.int32)
+        gt = build_ground_truth(recommender, test_data)
+        self.users = gt["users"]                                # known test users, groupby('user_id') order (tasks.py:537)
+        self.n_total = gt["n_total"]                            # every distinct test user counts in the means
+        self.unknown_users = gt["unknown_users"]
+        self.gt_indptr, self.gt_idx, self.recall_den = gt["gt_indptr"], gt["gt_idx"], gt["recall_den"]
+        self.pos_indptr, self.pos_idx = gt["pos_indptr"], gt["pos_idx"]
 
     def novelty(self, topk_idx: torch.Tensor) -> Dict[str, float]:
         """Novelty / coverage / personalization block of ``evaluate`` (tasks.py:637-714) for lists aligned with
@@ -247,7 +298,7 @@ class FullCatalogueEvaluator:
         world, rank = dist.get_world_size(self.sharded.group), dist.get_rank(self.sharded.group)
         n = len(self.users)
         blocks = [self.users[i:i + self.user_block] for i in range(0, n, self.user_block)]
-        sums = np.zeros((len(self.ks), 7))
+        sums = np.zeros((len(self.ks), len(_COLS)))
         outs_s, outs_i, row = [], [], 0
         for (s, i), blk in zip(self.sharded.recommend_blocks(blocks, kmax, self.filter_seen), blocks):
             per = (len(blk) + world - 1) // world               # this rank's slice of the block
@@ -255,15 +306,13 @@ class FullCatalogueEvaluator:
             if hi > lo:
                 ip = self.gt_indptr[row + lo:row + hi + 1]
                 sums += self._metric_sums(i[lo:hi], torch.from_numpy(ip - ip[0]),
-                                          torch.from_numpy(self.gt_idx[ip[0]:ip[-1]] if ip[-1] > ip[0] else np.zeros(1, np.int32)), self.ks)
+                                          torch.from_numpy(self.gt_idx[ip[0]:ip[-1]] if ip[-1] > ip[0] else np.zeros(1, np.int32)), self.ks,
+                                          recall_den=torch.from_numpy(self.recall_den[row + lo:row + hi]))
             outs_s.append(s); outs_i.append(i); row += len(blk)
-        t = torch.from_numpy(sums).to(outs_i[0].device if outs_i else "cpu")
+        dev = outs_i[0].device if outs_i else self.recommender.device
+        t = torch.from_numpy(sums).to("cpu" if dist.get_backend(self.sharded.group) == "gloo" else dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.sharded.group)
-        sums = t.cpu().numpy()
-        by_k = {}
-        for rowv, k in zip(sums, self.ks):
-            by_k[k] = {c: (float(v) / n if n else 0.0) for c, v in zip(_COLS, rowv)}
-            by_k[k]["num_users_evaluated"] = n
+        by_k = _by_k(t.cpu().numpy(), self.ks, self.n_total)
         return (torch.cat(outs_s) if outs_s else None), (torch.cat(outs_i) if outs_i else None), by_k
 
     def evaluate(self, novelty: bool = False) -> Dict:
@@ -273,8 +322,8 @@ class FullCatalogueEvaluator:
             scores, idx, by_k = self._evaluate_sharded(kmax)
         else:
             scores, idx = r.recommend_all(self.users, top_k=kmax, filter_seen=self.filter_seen)
-            by_k = ranking_metrics(idx, self.gt_indptr, self.gt_idx, self.ks)
-        res = {k: v for k, v in by_k[self.top_k].items() if k != "avg_ndcg_list_ideal_at_k"}
+            by_k = ranking_metrics(idx, self.gt_indptr, self.gt_idx, self.ks, recall_den=self.recall_den, n_total=self.n_total)
+        res = {k: v for k, v in by_k[self.top_k].items() if k not in _EXTRA_COLS}
         res["evaluation_method"] = "full_evaluation"
         res["by_k"] = by_k
         if novelty:
@@ -283,6 +332,7 @@ class FullCatalogueEvaluator:
             s, i = scores.cpu().numpy(), idx.cpu().numpy()
             res["predictions"] = {str(r.user_ids[int(u)]): [(str(r.item_ids[int(b)]), float(a)) for a, b in zip(s[j], i[j]) if b >= 0]
                                   for j, u in enumerate(self.users)}
+            res["predictions"].update({u: [] for u in self.unknown_users})      # get_recommendations -> [] (recommender.py:65-67)
         return res
 
 
@@ -318,9 +368,11 @@ class SampledRetrievalEvaluator(FullCatalogueEvaluator):
         r = self.recommender
         hi = len(self.users) if hi is None else hi
         dev = r.device
-        indptr = torch.from_numpy(self.gt_indptr[lo:hi + 1] - self.gt_indptr[lo]).to(dev)
-        idx = torch.from_numpy(self.gt_idx[self.gt_indptr[lo]:self.gt_indptr[hi]]).to(dev)
-        max_pos = int(np.diff(self.gt_indptr).max()) if len(self.users) else 0
+        indptr = torch.from_numpy(self.pos_indptr[lo:hi + 1] - self.pos_indptr[lo]).to(dev)
+        idx = torch.from_numpy(self.pos_idx[self.pos_indptr[lo]:self.pos_indptr[hi]]).to(dev)
+        if idx.numel() == 0:
+            idx = torch.zeros(1, dtype=torch.int32, device=dev)
+        max_pos = int(np.diff(self.pos_indptr).max()) if len(self.users) else 0
         stride = max(1, min(1024, max_pos + self.num_negatives))
         if self._weights is not None:
             return weighted_candidates(torch.from_numpy(self.users[lo:hi]).to(dev), indptr, idx,
@@ -331,27 +383,26 @@ class SampledRetrievalEvaluator(FullCatalogueEvaluator):
     def evaluate(self) -> Dict:
         r = self.recommender
         kmax = max(self.ks)
-        sums = np.zeros((len(self.ks), 7))
+        sums = np.zeros((len(self.ks), len(_COLS)))
         preds = {}
         for lo in range(0, len(self.users), self.user_block):
             hi = min(len(self.users), lo + self.user_block)
             cand, _ = self.candidates(lo, hi)
             s, items = r.rank_candidates(self.users[lo:hi], cand, top_k=kmax)
+            g_idx = self.gt_idx[self.gt_indptr[lo]:self.gt_indptr[hi]]
             sums += ranking_metric_sums(items, torch.from_numpy(self.gt_indptr[lo:hi + 1] - self.gt_indptr[lo]),
-                                        torch.from_numpy(self.gt_idx[self.gt_indptr[lo]:self.gt_indptr[hi]]), self.ks)
+                                        torch.from_numpy(g_idx if len(g_idx) else np.zeros(1, np.int32)), self.ks,
+                                        recall_den=torch.from_numpy(self.recall_den[lo:hi]))
             if self.keep_predictions:
                 hs, hi_ = s.cpu().numpy(), items.cpu().numpy()
                 for j, u in enumerate(self.users[lo:hi]):
                     preds[str(r.user_ids[int(u)])] = [(str(r.item_ids[int(b)]), float(a)) for a, b in zip(hs[j], hi_[j]) if b >= 0]
-        n = len(self.users)
-        by_k = {}
-        for row, k in zip(sums, self.ks):
-            by_k[k] = {c: (float(v) / n if n else 0.0) for c, v in zip(_COLS, row)}
-            by_k[k]["num_users_evaluated"] = n
-        res = {k: v for k, v in by_k[self.top_k].items() if k != "avg_ndcg_list_ideal_at_k"}
+        by_k = _by_k(sums, self.ks, self.n_total)
+        res = {k: v for k, v in by_k[self.top_k].items() if k not in _EXTRA_COLS}
         res["evaluation_method"] = "negative_sampling"
         res["by_k"] = by_k
         if self.keep_predictions:
+            preds.update({u: [] for u in self.unknown_users})
             res["predictions"] = preds
         return res
 

@@ -22,7 +22,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn as nn
 
-from .engine import PxrEngine
+from .engine import PxrEngine, check_index_range
 
 # dims of the reference's backbone registry (reference src/config.py:18-31); 'cached<N>' is the
 # hoisted-backbone spelling used by this framework's tests and benches
@@ -80,7 +80,7 @@ class FastMultimodalRecommender(nn.Module):
                  final_activation: str = "sigmoid", init_method: str = "xavier_uniform",
                  contrastive_temperature: float = 0.07, fusion_type: str = "concatenate",
                  vision_dim: Optional[int] = None, language_dim: Optional[int] = None, kernel_path: str = "auto",
-                 operand_dtype: str = "bf16"):
+                 operand_dtype: str = "bf16", exact_rescore: bool = True):
         super().__init__()
         self.fusion_type = fusion_type
         self.n_users, self.n_items, self.n_tags = n_users, n_items, n_tags
@@ -97,6 +97,9 @@ class FastMultimodalRecommender(nn.Module):
         self.final_activation = final_activation
         self.kernel_path = kernel_path
         self.operand_dtype = operand_dtype      # 16-bit operand format of the fused tcgen05 kernels: "bf16" | "fp16"
+        # exact mode of the fused path: the 64 candidates it keeps per user are re-scored in fp32 and re-ranked, so
+        # full-catalogue lists carry the same fp32 scores as forward() / get_item_score (False: raw 16-bit scores)
+        self.exact_rescore = bool(exact_rescore)
         # the contrastive heads and backbones are training / feature-production concerns (out of scope)
         self.use_contrastive = False
         self.vision_model = None
@@ -192,7 +195,7 @@ class FastMultimodalRecommender(nn.Module):
                 hidden_dims=self.fusion_hidden_dims, n_tags=self.n_tags, num_heads=self.num_attention_heads,
                 activation=self.fusion_activation, final_activation=self.final_activation,
                 use_batch_norm=self.use_batch_norm, projection_hidden_dim=self.projection_hidden_dim,
-                path=self.kernel_path, precision=self.operand_dtype, device=dev)
+                path=self.kernel_path, precision=self.operand_dtype, device=dev, rescore=self.exact_rescore)
             slot[1] = None
         if slot[1] != ver:
             sd = {k: v for k, v in self.state_dict().items() if not k.endswith("num_batches_tracked")}
@@ -236,8 +239,9 @@ class FastMultimodalRecommender(nn.Module):
             raise ValueError("numerical_features are required by this model configuration")
         if B == 0:
             return torch.empty((0, 1), dtype=torch.float32, device=dev)
+        check_index_range(user_idx, self.n_users, "user_idx")          # nn.Embedding raises IndexError (multimodal.py:553)
         eng.precompute_items(self.item_embedding.weight, tag_idx, image, text_input_ids, numerical_features,
-                             item_idx=item_idx, n_rows=B)
+                             item_idx=item_idx, n_rows=B)                   # checks item_idx / tag_idx ranges
         rows = torch.arange(B, dtype=torch.int64, device=dev)
         uidx = user_idx.to(device=dev, dtype=torch.int64).contiguous()
         uemb = self.user_embedding.weight.detach()

@@ -135,7 +135,15 @@ class PackedFeatureCache:
         (a few large asynchronous copies instead of one small copy per item)."""
         from .recommender import ItemFeatureStore
         device = torch.device(device)
-        rows = None if order is None else self.rows_for(order)
+        rows, absent = None, None
+        if order is not None:
+            idx = self.index
+            rows = np.fromiter((idx.get(str(i), -1) for i in order), dtype=np.int64, count=len(order))
+            if (rows < 0).any():
+                # ids of the encoder without a cache row: zero features + the per-item 'missing' flag (they score 0.0 like
+                # items whose features cannot be fetched in the reference, recommender.py:199-201, 229-230)
+                absent = rows < 0
+                rows = np.where(absent, 0, rows)
         n = self.n_items if rows is None else len(rows)
 
         def up(a, dtype):
@@ -146,6 +154,8 @@ class PackedFeatureCache:
             for r0 in range(0, n, chunk_rows):
                 r1 = min(n, r0 + chunk_rows)
                 blk = np.array(a[r0:r1] if rows is None else a[rows[r0:r1]])      # copy out of the read-only memmap
+                if absent is not None:
+                    blk[absent[r0:r1]] = 0
                 t = torch.from_numpy(blk)
                 if pin:
                     t = t.pin_memory()
@@ -155,7 +165,8 @@ class PackedFeatureCache:
             return out
 
         return ItemFeatureStore(up(self.tag, torch.int64), up(self.arrays["vis"], torch.float32),
-                                up(self.arrays["txt"], torch.float32), up(self.arrays["num"], torch.float32))
+                                up(self.arrays["txt"], torch.float32), up(self.arrays["num"], torch.float32),
+                                None if absent is None else absent.copy())
 
 
 def convert_reference_cache(ref_cache_dir, out_dir, item_ids: Sequence[str], tag_idx, num=None,

@@ -22,7 +22,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from .engine import PxrEngine, merge_topk
+from .engine import PxrEngine, check_index_range, merge_topk
 from .model import FastMultimodalRecommender
 
 
@@ -185,8 +185,10 @@ class FastRecommender:
     def engine(self) -> PxrEngine:
         """Engine with this recommender's item range precomputed (K1+K2 run once)."""
         eng = self.model.engine("catalogue")
-        token = (id(eng), self.model._engines["catalogue"][1], self.item_lo, self.item_hi)
-        if self._engine_token != token:
+        # the records live in the ENGINE (one per model): the token is kept there, so a second recommender on the same
+        # model with another item range re-runs the precompute instead of scoring against the other one's shard
+        token = (id(self), self.model._engines["catalogue"][1], self.item_lo, self.item_hi)
+        if eng.items_token != token:
             lo, hi = self.item_lo, self.item_hi
             sl = slice(lo, hi)
             eng.precompute_items(self.model.item_embedding.weight.detach(), self.items.tag_idx[sl],
@@ -196,7 +198,8 @@ class FastRecommender:
                                  item_idx=None, item_base=lo, n_rows=hi - lo)
             if self.items.missing is not None:
                 eng.set_missing_items(torch.from_numpy(np.ascontiguousarray(np.asarray(self.items.missing)[sl]).astype(np.uint8)))
-            self._engine, self._engine_token = eng, token
+            eng.items_token = token
+            self._engine = eng
         return eng
 
     # ------------------------------------------------------------ batched API
@@ -230,6 +233,8 @@ class FastRecommender:
         users = np.asarray(user_indices.cpu() if isinstance(user_indices, torch.Tensor) else user_indices,
                            dtype=np.int64)
         uemb = self.model.user_embedding.weight.detach()
+        if len(users) and (int(users.min()) < 0 or int(users.max()) >= int(uemb.shape[0])):
+            raise IndexError(f"user index out of range: [{int(users.min())}, {int(users.max())}] not inside [0, {int(uemb.shape[0])})")
         outs_s, outs_i = [], []
         for u0 in range(0, len(users), self.user_block):
             blk = users[u0:u0 + self.user_block]
@@ -258,6 +263,9 @@ class FastRecommender:
             raise ValueError("rank_candidates needs the whole catalogue on this recommender (no item-axis shard)")
         users = torch.as_tensor(user_indices, dtype=torch.int64, device=self.device)
         cand = candidates.to(device=self.device, dtype=torch.int32)
+        check_index_range(users, int(self.model.user_embedding.weight.shape[0]), "user index")
+        if cand.numel() and int(cand.max()) >= self.n_items:
+            raise IndexError(f"candidate item index {int(cand.max())} outside the catalogue ({self.n_items} items)")
         n, C_ = cand.shape
         valid = cand >= 0
         rows, cols = valid.nonzero(as_tuple=True)
@@ -282,6 +290,7 @@ class FastRecommender:
             return torch.empty(0, dtype=torch.float32, device=self.device)
         if int(items.min()) < self.item_lo or int(items.max()) >= self.item_hi:
             raise ValueError("items outside this recommender's item range")
+        check_index_range(users, int(self.model.user_embedding.weight.shape[0]), "user index")
         return eng.score_pairs(self.model.user_embedding.weight.detach(), users, items - self.item_lo)
 
     # --------------------------------------------------------- reference API

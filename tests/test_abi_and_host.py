@@ -170,28 +170,37 @@ from pixelrec_multimodal_b200.evaluation import FullCatalogueEvaluator
 class _Rec:
     user_index = {f"u{u}": u for u in range(NU)}
     item_index = {f"i{j}": j for j in range(NI)}
+    n_items, device = NI, torch.device("cpu")
 rng2 = np.random.default_rng(11)
-test = pd.DataFrame([(f"u{u}", f"i{int(j)}") for u in range(NU) for j in rng2.choice(NI, 2, replace=False)], columns=["user_id", "item_id"])
+rows = [(f"u{u}", f"i{int(j)}") for u in range(NU) for j in rng2.choice(NI, 2, replace=False)]
+# the reference keeps every distinct test user in the means and every raw row in the recall denominator
+# (tasks.py:537-540, 579): an unknown user, an unknown item and a duplicated row
+rows += [("ghost", "i1"), ("u0", "nope"), rows[2]]
+test = pd.DataFrame(rows, columns=["user_id", "item_id"])
 ev = FullCatalogueEvaluator(_Rec(), test, top_k=K, ks=[3, K], filter_seen=False, sharded=st, user_block=4)
-def cpu_metric_sums(topk, gt_indptr, gt_idx, ks):      # K5 restated with the oracle (no GPU here)
-    out = np.zeros((len(ks), 7))
+assert ev.n_total == NU + 1 and ev.unknown_users == ["ghost"] and int(ev.recall_den.sum()) == len(rows) - 1
+def cpu_metric_sums(topk, gt_indptr, gt_idx, ks, recall_den=None):      # K5 restated with the oracle (no GPU here)
+    out = np.zeros((len(ks), 9))
     ip, gi = gt_indptr.numpy(), gt_idx.numpy()
     for r_ in range(topk.shape[0]):
-        pos = set(int(x) for x in gi[ip[r_]:ip[r_ + 1]])
+        pos = [int(x) for x in gi[ip[r_]:ip[r_ + 1]]]
+        raw = pos + pos[:1] * (int(recall_den[r_]) - len(pos)) if recall_den is not None else pos
         for a, k in enumerate(sorted(ks)):
             recs = [int(x) for x in topk[r_][:k].tolist() if x >= 0]
-            m = orc.retrieval_metrics([recs], [pos], k)
+            m = orc.retrieval_metrics([recs], [raw], k)
             out[a, :6] += [m["avg_precision_at_k"], m["avg_recall_at_k"], m["avg_f1_at_k"], m["avg_hit_rate_at_k"], m["avg_ndcg_at_k"], m["avg_mrr"]]
     return out
 ev._metric_sums = cpu_metric_sums
 res = ev.evaluate()
-recs_all = [[int(x) for x in i[u].tolist() if x >= 0] for u in range(NU)]
-pos_all = [set(int(x) for x in ev.gt_idx[ev.gt_indptr[j]:ev.gt_indptr[j + 1]]) for j in range(NU)]
+# the reference loop on the table itself: string ids, groupby order, [] for the unknown user
+names = sorted(set(t[0] for t in rows))
+recs_all = [[f"i{int(x)}" for x in i[int(n_[1:])].tolist() if x >= 0] if n_ != "ghost" else [] for n_ in names]
+pos_all = [[t[1] for t in rows if t[0] == n_] for n_ in names]
 for k in (3, K):
     want = orc.retrieval_metrics([r_[:k] for r_ in recs_all], pos_all, k)
-    for key in ("avg_precision_at_k", "avg_recall_at_k", "avg_ndcg_at_k", "avg_mrr"):
+    for key in ("avg_precision_at_k", "avg_recall_at_k", "avg_f1_at_k", "avg_hit_rate_at_k", "avg_ndcg_at_k", "avg_mrr"):
         assert abs(res["by_k"][k][key] - want[key]) < 1e-12, (rank, k, key, res["by_k"][k][key], want[key])
-assert res["num_users_evaluated"] == NU
+assert res["num_users_evaluated"] == NU + 1
 dist.barrier(); dist.destroy_process_group()
 print("OK", rank)
 """

@@ -51,6 +51,45 @@ def test_user_selection_and_json_shape(tmp_path):
     json.dumps(out)
 
 
+def test_encoders_come_from_the_checkpoint_dir(tmp_path):
+    """scripts/evaluate.py:113-167, 301-304: the training-time user_encoder.pkl / item_encoder.pkl define the embedding
+    rows; a table whose ids differ from training must not silently re-number them."""
+    import pickle
+    import pandas as pd
+    import torch
+    from sklearn.preprocessing import LabelEncoder
+    from pixelrec_multimodal_b200.packed_cache import PackedFeatureCache, write_packed_cache
+    spec = syn.ModelSpec(n_users=12, n_items=20, fusion_type="concatenate")
+    feats = syn.make_item_features(spec, seed=3)
+    uids, iids = syn.user_ids(spec.n_users), syn.item_ids(spec.n_items)
+    write_packed_cache(tmp_path / "cache", iids[:18], feats["tag_idx"][:18], feats["vis"][:18], feats["txt"][:18], feats["num"][:18])
+    # today's table only holds 5 of the 12 training users
+    pd.DataFrame({"user_id": uids[:5], "item_id": iids[:5]}).to_csv(tmp_path / "train.csv", index=False)
+    ck_dir = tmp_path / "ckpt" / "clip_sentence-bert"
+    (tmp_path / "ckpt" / "encoders").mkdir(parents=True)
+    ck_dir.mkdir(parents=True)
+    for name, ids in (("user", uids), ("item", iids)):
+        with open(tmp_path / "ckpt" / "encoders" / f"{name}_encoder.pkl", "wb") as f:
+            pickle.dump(LabelEncoder().fit(ids), f)
+    assert cli.find_encoders(str(ck_dir / "best_model.pth"), None) == tmp_path / "ckpt" / "encoders"
+    assert cli.find_encoders(str(tmp_path / "elsewhere" / "m.pth"), None) is None
+    with pytest.raises(FileNotFoundError):
+        cli.find_encoders(None, str(tmp_path / "nothing"))
+    cache = PackedFeatureCache(tmp_path / "cache")
+    inter = pd.read_csv(tmp_path / "train.csv", dtype=str)
+    ds = cli.TableDataset(inter, cache, tmp_path / "ckpt" / "encoders")
+    assert list(ds.user_encoder.classes_) == uids and list(ds.item_encoder.classes_) == iids
+    assert len(cli.TableDataset(inter, cache).user_encoder.classes_) == 5           # rebuilt from the table: NOT the training ids
+    # encoder ids without a cache row are flagged missing (they score 0.0), not an error
+    store = cache.to_store("cpu", order=iids)
+    assert store.missing.tolist() == [False] * 18 + [True] * 2 and float(store.vis[18:].abs().sum()) == 0.0
+    # a checkpoint whose tables do not match the (rebuilt) encoders is refused before anything is scored
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in syn.make_state_dict(spec, seed=3).items()}
+    torch.save({"model_state_dict": sd}, tmp_path / "elsewhere.pth")
+    with pytest.raises(ValueError, match="12 user embedding rows"):
+        cli.build_recommender(cli.load_config(None), str(tmp_path / "elsewhere.pth"), str(tmp_path / "cache"), str(tmp_path / "train.csv"))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("fusion", ["gated", "attention"])
 def test_cli_end_to_end(tmp_path, fusion):
