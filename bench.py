@@ -3,18 +3,24 @@
 
 A "step" is one pass of the hot path over one block of users: every user of the
 block scored against EVERY item of the catalogue, seen items filtered, top-50
-kept (pxr_score_topk; with N>1 GPUs each rank owns a contiguous item shard and
-the per-shard lists are merged after one NCCL all-gather).
+kept (pxr_score_topk in its default exact mode: the fused 16-bit kernel keeps 64
+candidates per user, they are re-scored in fp32 and re-ranked; with N>1 GPUs each
+rank owns a contiguous item shard and the per-shard lists are exchanged with one
+all-to-all over NVLink and merged by the rank that owns the user).
 
 Workload at N=1 = BASELINE.json configs[1]: gated fusion, CLIP-512 + SBERT-384
 cached features, Pixel200K-shaped synthetic (200 000 users x 96 282 items), top-50.
 Per-GPU work is fixed as N grows (users per step = user_block * N, items per
-rank = NI / N): "scaling": "weak".
+rank = NI / N): "scaling": "weak".  The same JSON object carries an `also` array
+with short runs of the other BASELINE configs (configs[2] attention at every N,
+the concat shape at N=1, configs[3] Pixel8M-shaped at N=8, and at N>1 the
+user-axis-sharded variant of the headline for comparison), each with its own
+roofline and clocks.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-`--impl reference` times the reference's CPU path (the numpy oracle port: the
-reference is pure Python/PyTorch and cannot travel to the GPU box) on the
+`--impl reference` times the reference's CPU path (the PyTorch-eager oracle port:
+the reference is pure Python/PyTorch and cannot travel to the GPU box) on the
 host cores for the same metric and config.  The oracle is only ever the CPU
 arm here; the product path never touches it.
 """
@@ -44,6 +50,19 @@ CONFIGS = {
 TOP_K = 50
 METRIC = "scored user-item pairs/sec (full catalogue, top-50 per user)"
 UNIT = "pairs/s"
+EMBEDDING_DIM, HIDDEN = 64, [512, 256, 128]
+
+
+def config_dict(cfg_name: str, n_gpus: int, user_block: int, shard: str = "items"):
+    """The workload description both arms print (identical dicts for the same command line)."""
+    NU, NI, fusion, desc = CONFIGS[cfg_name]
+    par = "single GPU" if n_gpus == 1 else (
+        f"item-shard x{n_gpus}: one all-to-all of the per-shard top-K lists per step, overlapped with the scoring of the next step, "
+        f"merge by the owning rank" if shard == "items" else f"user-shard x{n_gpus}: replicas of the catalogue, no exchange")
+    return {"workload": desc, "n_users": NU, "n_items": NI, "fusion": fusion, "top_k": TOP_K, "embedding_dim": EMBEDDING_DIM,
+            "hidden": HIDDEN, "filter_seen": True, "users_per_step": user_block * n_gpus,
+            "parallelism": f"B200 arm: {par}; CPU arm: one process, all host threads",
+            "l2": "B200 arm: flushed between steps by a 256 MiB memset inside the timed region; CPU arm: not applicable"}
 
 
 def w_pair(fusion: str, D: int, H):
@@ -60,10 +79,11 @@ def ncu_traffic(fusion: str, users_per_launch: int, items_per_rank: int):
     p = REPO / "profiles" / "ncu_traffic.json"
     if not p.exists():
         return None
+    best = None
     for e in json.loads(p.read_text()).get("captures", []):
         if e["fusion"] == fusion and e["users_per_launch"] == users_per_launch and e["items_per_rank"] == items_per_rank:
-            return e["dram_bytes_per_launch"]
-    return None
+            best = e["dram_bytes_per_launch"]          # later entries (newer rounds) win
+    return best
 
 
 def peaks():
@@ -115,7 +135,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
-# CPU arm: the oracle port (batched reference forward + stable top-K)
+# CPU arm: the oracle port (batched reference forward + stable top-K; literal per-user loop)
 # ---------------------------------------------------------------------------
 _CPU_WL = {}
 
@@ -131,7 +151,7 @@ def cpu_workload(cfg_name: str, seed: int):
         syn.condition_like_trained(sd, spec, feats)
         torch.set_num_threads(os.cpu_count() or 1)
         _CPU_WL[(cfg_name, seed)] = dict(sd=sd, feats=feats, indptr=hist["train_indptr"], idx=hist["train_idx"],
-                                         cfg=cs.spec_cfg(spec), NU=NU, NI=NI, fusion=fusion)
+                                         cfg=cs.spec_cfg(spec), NU=NU, NI=NI, fusion=fusion, spec=spec)
     return _CPU_WL[(cfg_name, seed)]
 
 
@@ -160,6 +180,53 @@ def cpu_arm(cfg_name: str, seconds: float, seed: int, first_user: int = 0):
                        f"+ seen filter + stable top-{TOP_K}")
 
 
+def cpu_literal(cfg_name: str, seconds: float, seed: int, max_items: int = 20_000):
+    """The LITERAL path a reference user runs: one `Recommender.get_recommendations(user,
+    top_k=50, filter_seen=True)` call per user -- per-call id lists, 256-item batches, per-item feature-dict fetches,
+    torch.stack, sklearn LabelEncoder.transform, one forward per batch, Python sort (oracle/pxr_oracle_torch.py::
+    LiteralRecommender, src/inference/recommender.py:52-236 step by step; pinned to the real reference's lists in tests/).
+    The per-item feature dicts of a big catalogue take minutes to build, so the catalogue is cut to its first
+    `max_items` items (the cost per pair does not depend on the catalogue size beyond that)."""
+    import torch
+    from sklearn.preprocessing import LabelEncoder
+    from oracle import pxr_oracle_torch as ot
+    from pixelrec_multimodal_b200 import synthetic as syn
+    wl = cpu_workload(cfg_name, seed)
+    NU, NI = wl["NU"], min(wl["NI"], max_items)
+    n_enc_users = min(NU, 20_000)                         # the per-call user id list is O(n_users) (recommender.py:64)
+    feats, indptr, idx = wl["feats"], wl["indptr"].numpy(), wl["idx"].numpy()
+    iids, uids = syn.item_ids(NI), syn.user_ids(n_enc_users)
+
+    class _DS:
+        pass
+    ds = _DS()
+    ds.user_encoder, ds.item_encoder = LabelEncoder().fit(uids), LabelEncoder().fit(iids)
+    ds.feature_cache = {}
+    for i, iid in enumerate(iids):
+        d = {"tag_idx": feats["tag_idx"][i]}
+        if "vis" in feats:
+            d["image"] = feats["vis"][i]
+        if "txt" in feats:
+            d["text_input_ids"] = feats["txt"][i]
+        if "num" in feats:
+            d["numerical_features"] = feats["num"][i]
+        ds.feature_cache[iid] = d
+    ds.get_user_history = lambda uid: {iids[int(j)] for j in idx[indptr[int(uid[1:])]:indptr[int(uid[1:]) + 1]] if j < NI}
+    sd = dict(wl["sd"])
+    sd["item_embedding.weight"] = sd["item_embedding.weight"][:NI]
+    lit = ot.LiteralRecommender(sd, wl["cfg"], ds)
+    t0 = time.perf_counter(); lit.get_recommendations(uids[0], top_k=TOP_K, filter_seen=True); t1 = time.perf_counter() - t0
+    n = int(max(1, min(64, seconds / max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    for u in range(1, 1 + n):
+        r = lit.get_recommendations(uids[u], top_k=TOP_K, filter_seen=True)
+        assert len(r) == TOP_K
+    dt = time.perf_counter() - t0
+    return dict(value=n * NI / dt, users_per_sec=n / dt, users=n, items=NI, seconds=dt,
+                sample=f"{n} get_recommendations calls (top-{TOP_K}, filter_seen) over the first {NI} items of config {cfg_name}, "
+                       f"{n_enc_users} users in the encoder")
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -173,13 +240,17 @@ def reference_arm(args):
     tot_pairs = sum(r["users"] for r in vals) * CONFIGS[args.config][1]
     tot_s = sum(r["seconds"] for r in vals)
     v = tot_pairs / tot_s
-    NU, NI, fusion, desc = CONFIGS[args.config]
+    NI = CONFIGS[args.config][1]
+    base = {"value": v, "unit": UNIT, "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"]}
+    if args.literal_seconds > 0:
+        lit = cpu_literal(args.config, args.literal_seconds, args.seed)
+        base.update(literal_value=lit["value"], literal_users_per_sec=lit["users_per_sec"], literal_sample=lit["sample"])
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(1, len(vals)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "users_per_sec": v / NI,
-            "config": {"workload": desc, "n_users": NU, "n_items": NI, "fusion": fusion, "top_k": TOP_K},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"]},
+            "config": config_dict(args.config, args.gpus, args.user_block),
+            "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -187,34 +258,42 @@ def reference_arm(args):
 # ---------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------
-def b200_arm(args):
+class _LazyIds:
+    """Zero-padded id strings without materialising millions of them."""
+
+    def __init__(self, n, prefix):
+        self.n, self.prefix = n, prefix
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return f"{self.prefix}{int(i):08d}"
+
+
+def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: int, dev, shard: str = "items",
+               with_e2e: bool = True, with_cpu: bool = False, with_checks: bool = True):
+    """One measured run of `cfg_name` on the current process group; returns the JSON line as a dict (every rank)."""
     import torch
     import torch.distributed as dist
     from pixelrec_multimodal_b200 import FastMultimodalRecommender, FastRecommender, ItemFeatureStore, synthetic as syn
     from pixelrec_multimodal_b200.engine import merge_topk
-    from pixelrec_multimodal_b200.sharding import allgather_topk, allgather_topk_finish, allgather_topk_start, shard_range
+    from pixelrec_multimodal_b200.sharding import exchange_owned_finish, exchange_owned_start, owned_slice, shard_range
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    NU, NI, fusion, desc = CONFIGS[args.config]
+    NU, NI, fusion, desc = CONFIGS[cfg_name]
     spec = syn.ModelSpec(n_users=NU, n_items=NI, fusion_type=fusion)
     sd, feats, hist = syn.torch_workload(spec, dev, seed=args.seed)      # identical on every rank (same seed)
     # BatchNorm statistics matched to the activations and logits spread to std 2, like a trained checkpoint
     syn.condition_like_trained(sd, spec, feats)
 
-    model = FastMultimodalRecommender(
-        n_users=NU, n_items=NI, n_tags=spec.n_tags, num_numerical_features=spec.num_numerical_features,
-        embedding_dim=spec.embedding_dim, vision_model_name=f"cached{spec.vision_dim}",
-        language_model_name=f"cached{spec.language_dim}", use_contrastive=False, fusion_type=fusion,
-        fusion_hidden_dims=list(spec.fusion_hidden_dims), kernel_path=args.path).to(dev)
-    model.load_state_dict(sd, strict=False)
+    def make_model():
+        m = FastMultimodalRecommender(
+            n_users=NU, n_items=NI, n_tags=spec.n_tags, num_numerical_features=spec.num_numerical_features,
+            embedding_dim=spec.embedding_dim, vision_model_name=f"cached{spec.vision_dim}",
+            language_model_name=f"cached{spec.language_dim}", use_contrastive=False, fusion_type=fusion,
+            fusion_hidden_dims=list(spec.fusion_hidden_dims), kernel_path=args.path).to(dev)
+        m.load_state_dict(sd, strict=False)
+        return m
 
     class _Enc:
         def __init__(self, n, p): self.classes_ = _LazyIds(n, p)
@@ -222,50 +301,59 @@ def b200_arm(args):
     class _DS:
         user_encoder, item_encoder, interactions = _Enc(NU, "u"), _Enc(NI, "i"), None
 
-    lo, hi = shard_range(NI, world, rank)
+    model = make_model()
+    item_sharded = world > 1 and shard == "items"
+    lo, hi = shard_range(NI, world, rank) if item_sharded else (0, NI)
     store = ItemFeatureStore(feats["tag_idx"], feats["vis"], feats["txt"], feats["num"])
+    B = args.user_block * world                                   # users per step (whole job)
     rec = FastRecommender(model, _DS(), dev, item_features=store, n_users=NU, n_items=NI,
-                          history=(hist["train_indptr"], hist["train_idx"]), item_range=(lo, hi),
-                          user_block=args.user_block * world)
+                          history=(hist["train_indptr"], hist["train_idx"]), item_range=(lo, hi), user_block=B)
     eng = rec.engine()
     torch.cuda.synchronize()
 
-    B = args.user_block * world                                   # users per step (whole job)
     n_blocks = max(1, NU // B)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     uemb = model.user_embedding.weight.detach()
     d_indptr, d_idx = rec.device_history()
     merges = [0]
-
     all_users = torch.arange(NU, device=dev)
 
-    def score_block(s):
-        """inputs already in HBM: the block's user indices and the resident history CSR"""
+    def block_users(s):
+        """(first user, count) this rank scores in step s: the whole block when items are sharded, its 1/world slice
+        of the block under user-axis sharding"""
         b = s % n_blocks
         u0 = b * B
         n = min(NU, u0 + B) - u0
+        if world > 1 and not item_sharded:
+            a, z = owned_slice(n, world, rank)
+            return u0 + a, z - a, n
+        return u0, n, n
+
+    def score_block(s):
+        """inputs already in HBM: the block's user indices and the resident history CSR"""
+        u0, n, n_job = block_users(s)
         sc, ix = eng.score_topk(uemb, all_users[u0:u0 + n], TOP_K, d_indptr[u0:u0 + n + 1], d_idx)
-        return sc, ix, n
+        return sc, ix, n_job
 
     def run_steps(first, count):
-        """`count` steps.  N > 1: the all-gather of step s (one packed collective on NCCL's stream) overlaps the
-        scoring kernel of step s + 1; its merge is enqueued behind that kernel."""
+        """`count` steps.  Item shards: the all-to-all of step s (one packed collective on NCCL's stream) overlaps the
+        scoring kernel of step s + 1; the owning rank's merge is enqueued behind that kernel."""
         users = 0
         pending = None
         for s in range(first, first + count):
             sc, ix, n = score_block(s)
             users += n
-            if world > 1:
-                handle = allgather_topk_start(sc, ix)
+            if item_sharded:
+                handle = exchange_owned_start(sc, ix)
                 if pending is not None:
-                    merge_topk(*allgather_topk_finish(pending)); merges[0] += 1
+                    merge_topk(*exchange_owned_finish(pending)); merges[0] += 1
                 pending = handle
             flush.zero_()                                         # L2 flush between steps (inside the timed region)
         if pending is not None:
-            merge_topk(*allgather_topk_finish(pending)); merges[0] += 1
+            merge_topk(*exchange_owned_finish(pending)); merges[0] += 1
         return users
 
-    run_steps(0, args.warmup)
+    run_steps(0, warmup)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -273,11 +361,11 @@ def b200_arm(args):
     eng.profile(True)
     launches0 = eng.launch_count
     merges[0] = 0
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    users_done = run_steps(args.warmup, args.steps)
+    users_done = run_steps(warmup, steps)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -296,80 +384,157 @@ def b200_arm(args):
     value = pairs / (ms * 1e-3)
 
     # ---- e2e: the public API with HOST buffers (user ids in, top-K lists out), copies inside the timed region
-    h_users = [np.arange(((args.warmup + s) % n_blocks) * B, min(NU, (((args.warmup + s) % n_blocks) + 1) * B)) for s in range(args.steps)]
-    def step_e2e(users_np):
-        sc, ix = rec.recommend_all(users_np, top_k=TOP_K, filter_seen=True)
-        if world > 1:
-            all_s, all_i = allgather_topk(sc, ix)
-            sc, ix = merge_topk(all_s, all_i)
-        return sc.cpu(), ix.cpu()
-    step_e2e(h_users[0])
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    n_e2e = 0
-    for u in h_users:
-        hs, hi_ = step_e2e(u)
-        n_e2e += len(u)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e_val = n_e2e * NI / dt
-    h2d = int(len(h_users[0]) * 8 + (len(h_users[0]) + 1) * 8)      # user indices + block CSR offsets (int64)
-    d2h = int(len(h_users[0]) * TOP_K * 8)                          # fp32 score + int32 index per slot
+    e2e = None
+    if with_e2e:
+        def host_users(s):
+            u0, n, _ = block_users(warmup + s)
+            return np.arange(u0, u0 + n)
+        h_users = [host_users(s) for s in range(steps)]
 
-    if rank != 0:
+        def step_e2e(users_np):
+            sc, ix = rec.recommend_all(users_np, top_k=TOP_K, filter_seen=True)
+            if item_sharded:                                      # every rank scored the whole block against its shard
+                sc, ix = merge_topk(*exchange_owned_finish(exchange_owned_start(sc, ix)))
+            return sc.cpu(), ix.cpu()                             # the lists of the users this rank owns
+        step_e2e(h_users[0])
+        torch.cuda.synchronize()
         if world > 1:
-            dist.destroy_process_group()
-        return
+            dist.barrier()
+        t0 = time.perf_counter()
+        n_e2e = 0
+        for s, u in enumerate(h_users):
+            step_e2e(u)
+            n_e2e += block_users(warmup + s)[2]
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        n_job = block_users(warmup)[2]
+        e2e = {"value": n_e2e * NI / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(world * (len(h_users[0]) * 8 + (len(h_users[0]) + 1) * 8)),   # user indices + block CSR offsets (int64), every rank
+               "d2h_bytes_per_step": int(n_job * TOP_K * 8),                                           # fp32 score + int32 index per slot
+               "api": "FastRecommender.recommend_all(host user ids) -> top-K lists copied to host" +
+                      (" (each rank: the lists of the users it owns after the all-to-all)" if item_sharded else "")}
+
+    # ---- checks outside the timed region
+    checks = {}
+    if with_checks and eng.active_path == "tcgen05":
+        # raw 16-bit lists vs the exact-mode lists (fp32 re-scored) of the same users on this rank's item range
+        u0, n, _ = block_users(warmup)
+        nu = min(256, n)
+        uu = all_users[u0:u0 + nu]
+        xs, xi = eng.score_topk(uemb, uu, TOP_K, d_indptr[u0:u0 + nu + 1], d_idx)
+        eng.set_rescore(False)
+        rs, ri = eng.score_topk(uemb, uu, TOP_K, d_indptr[u0:u0 + nu + 1], d_idx)
+        eng.set_rescore(True)
+        ov = (xi.unsqueeze(2) == ri.unsqueeze(1)).any(dim=2).sum(dim=1).float()
+        fp32_of_raw = eng.score_pairs(uemb, uu.repeat_interleave(TOP_K), (ri.reshape(-1).clamp_min(lo) - lo).to(torch.int64)).view(nu, TOP_K)
+        checks["parity_sample"] = {
+            "users": int(nu), "items": int(hi - lo),
+            "raw16_vs_exact_top50_overlap_mean": float(ov.mean()), "raw16_vs_exact_top50_overlap_min": float(ov.min()),
+            "raw16_max_abs_score_error_vs_fp32": float((rs - fp32_of_raw)[ri >= 0].abs().max()),
+            "note": "exact mode (default): the 64 candidates the 16-bit kernel keeps per user are re-scored with the fp32 arithmetic of "
+                    "forward() and re-ranked; tests/test_gpu_parity.py::test_catalogue_scale_parity checks both against the exact forward"}
+    if with_checks and item_sharded:
+        # merged sharded lists == the unsharded lists of rank 0, bit for bit (raw 16-bit lists: the per-pair arithmetic does not
+        # depend on the tiling; exact mode re-scores per shard, so its candidate sets may differ in rare near-ties)
+        nu = 64
+        uu = all_users[:nu]
+        res = {}
+        for mode in ("raw", "exact"):
+            eng.set_rescore(mode == "exact")
+            sc, ix = eng.score_topk(uemb, uu, TOP_K, d_indptr[:nu + 1], d_idx)
+            gs = [torch.empty_like(sc) for _ in range(world)]; gi = [torch.empty_like(ix) for _ in range(world)]
+            dist.all_gather(gs, sc); dist.all_gather(gi, ix)
+            res[mode] = merge_topk(torch.stack(gs), torch.stack(gi))
+        eng.set_rescore(True)
+        if rank == 0:
+            full_model = make_model()
+            full = FastRecommender(full_model, _DS(), dev, item_features=store, n_users=NU, n_items=NI,
+                                   history=(hist["train_indptr"], hist["train_idx"]), user_block=B)
+            fe = full.engine()
+            out = {}
+            for mode in ("raw", "exact"):
+                fe.set_rescore(mode == "exact")
+                fs, fi = fe.score_topk(full_model.user_embedding.weight.detach(), uu, TOP_K, d_indptr[:nu + 1], d_idx)
+                out[mode] = (bool(torch.equal(fi, res[mode][1]) and torch.equal(fs, res[mode][0])),
+                             int((fi == res[mode][1]).all(dim=1).sum()))
+            checks["shard_check"] = "ok" if out["raw"][0] else "MISMATCH"
+            checks["shard_check_detail"] = {"users": nu, "raw16_lists_bit_identical": out["raw"][0],
+                                            "exact_mode_users_identical": out["exact"][1]}
+            del full, fe, full_model
+        dist.barrier()
+
     pk = peaks()
     H = list(spec.fusion_hidden_dims)
     wp = w_pair(fusion, spec.embedding_dim, H)
-    pairs_per_launch = (users_done * (hi - lo)) / max(1, k_n)
+    rank_users = users_done if (world == 1 or item_sharded) else users_done / world
+    pairs_per_launch = (rank_users * (hi - lo)) / max(1, k_n)
     k_avg_ms = k_ms / max(1, k_n)
     achieved_tf = pairs_per_launch * wp / (k_avg_ms * 1e-3) / 1e12 if k_n else None
     peak_tf = pk["tf_sustained"]
     roofline = {"bound": "tensor", "kernel": f"pair-scoring ({eng.active_path})", "achieved": achieved_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf else None,
-                "traffic": ncu_traffic(fusion, B // world, hi - lo),
+                "traffic": ncu_traffic(fusion, int(rank_users / max(1, steps)), hi - lo),
                 "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside a long step); burst {pk['tf_burst']}",
                 "flop_per_pair": wp, "pairs_per_launch": pairs_per_launch, "kernel_ms_avg": k_avg_ms, "kernel_launches": k_n,
                 "kernel_share_of_step": (k_ms / ms) if ms else None}
-    cpu = cpu_arm(args.config, args.cpu_seconds, args.seed) if (world == 1 and args.cpu_seconds > 0) else None
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if eng.active_path == "tcgen05" else "f32", "data": "synthetic",
             "users_per_sec": value / NI,
-            "config": {"workload": desc, "n_users": NU, "n_items": NI, "fusion": fusion, "top_k": TOP_K,
-                       "embedding_dim": spec.embedding_dim, "hidden": H, "users_per_step": B,
-                       "items_per_rank": hi - lo, "parallelism": f"item-shard x{world}, all-gather of step s overlapped with scoring of step s+1" if world > 1 else "single GPU",
-                       "kernel_path": eng.active_path, "filter_seen": True,
-                       "l2": "flushed between steps by a 256 MiB memset inside the timed region"},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "FastRecommender.recommend_all(host user ids) -> top-K lists copied to host"},
+            "config": config_dict(cfg_name, world, args.user_block, shard),
+            "run": {"items_per_rank": hi - lo, "kernel_path": eng.active_path, "exact_rescore": bool(eng.rescore),
+                    "shard_axis": shard if world > 1 else None},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
-    if cpu is not None:
+    if e2e is not None:
+        line["e2e"] = e2e
+    line.update(checks)
+    if with_cpu and rank == 0:
+        cpu = cpu_arm(cfg_name, args.cpu_seconds, args.seed)
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line), flush=True)
+        if args.literal_seconds > 0:
+            lit = cpu_literal(cfg_name, args.literal_seconds, args.seed)
+            line["cpu_baseline"].update(literal_value=lit["value"], literal_users_per_sec=lit["users_per_sec"], literal_sample=lit["sample"])
+    # free this configuration's device memory before the next one
+    del rec, eng, model, store, feats, hist, sd, flush, uemb, d_indptr, d_idx, all_users
+    torch.cuda.empty_cache()
+    return line
+
+
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    line = run_config(args, args.config, args.steps, args.warmup, world, rank, dev, shard=args.shard, with_e2e=True,
+                      with_cpu=(world == 1 and args.cpu_seconds > 0))
+    also = []
+    if args.also and args.config == "B":
+        extra = [("C", "items")] + ([("Bc", "items")] if world == 1 else [("B", "users")]) + ([("D", "items")] if world == 8 else [])
+        for cfg_name, shard in extra:
+            try:
+                r = run_config(args, cfg_name, args.also_steps, 3, world, rank, dev, shard=shard, with_e2e=False, with_checks=(shard == "items"))
+                also.append({k: r[k] for k in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "users_per_sec", "dtype", "config",
+                                               "run", "gpu_launches", "clocks", "roofline") + tuple(c for c in ("parity_sample", "shard_check", "shard_check_detail") if c in r)})
+            except Exception as e:                                  # an extra run must never take the headline line down
+                also.append({"config": config_dict(cfg_name, world, args.user_block, shard), "error": f"{type(e).__name__}: {e}"[:300]})
+                torch.cuda.empty_cache()
+    if rank == 0:
+        if also:
+            line["also"] = also
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-class _LazyIds:
-    """Zero-padded id strings without materialising millions of them."""
-
-    def __init__(self, n, prefix):
-        self.n, self.prefix = n, prefix
-
-    def __len__(self):
-        return self.n
-
-    def __getitem__(self, i):
-        return f"{self.prefix}{int(i):08d}"
 
 
 def main():
@@ -381,7 +546,12 @@ def main():
     ap.add_argument("--config", default="B", choices=list(CONFIGS))
     ap.add_argument("--user-block", type=int, default=4096, help="users per step per GPU")
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--shard", default="items", choices=["items", "users"],
+                    help="N > 1: item-axis shards + exchange (north_star) or user-axis shards (replicas, no exchange)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample length (0 = skip)")
+    ap.add_argument("--literal-seconds", type=float, default=8.0, help="literal per-user CPU baseline sample length (0 = skip)")
+    ap.add_argument("--no-also", dest="also", action="store_false", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--also-steps", type=int, default=5)
     ap.add_argument("--seed", type=int, default=20261018)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -248,6 +248,30 @@ int pxr_novelty_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_use
                         const double* self_info, const double* iif, const int64_t* hist_indptr, const int32_t* hist_idx,
                         double* out6, void* workspace, size_t workspace_bytes, pxr_stream stream);
 
+/* Gini coefficient of the per-item recommendation counts over the ranked lists.  Replaces
+ * AdvancedMetrics.calculate_gini_coefficient (src/evaluation/advanced_metrics.py:72-105) applied to
+ * {item: number of lists holding it}: counts sorted ascending, G = 2 sum_i i c_(i) / (n sum c) - (n + 1) / n.
+ *   include_zero : 1 = every one of the n_items items is in the distribution (never-recommended items count 0, as in
+ *                  the reference's own test, tests/unit/src/evaluation/test_advanced_metrics.py:70-73); 0 = only items
+ *                  recommended at least once
+ *   out3         : DEVICE float64 [gini, n, sum of counts] ;  workspace : pxr_gini_bytes(n_users, n_items) bytes */
+size_t pxr_gini_bytes(int64_t n_users, int64_t n_items);
+int pxr_gini(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, int64_t n_items, int32_t include_zero,
+             double* out3, void* workspace, size_t workspace_bytes, pxr_stream stream);
+
+/* Intra-list similarity: per user the mean pairwise cosine similarity of the embeddings of its listed items; lists
+ * with fewer than two embedded items give 0.0.  Replaces NoveltyMetrics.calculate_diversity
+ * (src/evaluation/novelty.py:295-340) as averaged in TopKRetrievalEvaluator.evaluate (src/evaluation/tasks.py:695-701;
+ * the reference's own embedding collection, tasks.py:430-507, raises NameError and yields nothing).
+ *   emb       : (n_rows, dim <= 512) fp32 DEVICE item embeddings, row r = item item_base + r; NULL = the item records
+ *               resident in `h` for scoring (the projected item-side modality vectors of pxr_precompute_items)
+ *   out2      : DEVICE float64 [sum over users of their intra-list similarity, users counted]
+ *   workspace : pxr_ils_bytes(n_users, n_rows) bytes (n_rows of the handle when emb is NULL) */
+size_t pxr_ils_bytes(int64_t n_users, int64_t n_rows);
+int pxr_intra_list_similarity(pxr_handle* h, const int32_t* topk_idx, int32_t k_stride, int64_t n_users, const float* emb,
+                              int64_t n_rows, int32_t dim, int64_t item_base, double* out2, void* workspace,
+                              size_t workspace_bytes, pxr_stream stream);
+
 /* Live timing of the dominant kernel (the pair-scoring kernel of
  * pxr_score_topk) with CUDA events recorded on the launching stream, for the
  * roofline line of bench.py.  pxr_profile_read synchronises on the recorded

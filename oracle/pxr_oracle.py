@@ -121,68 +121,78 @@ def attention_fusion(sd, feats, num_heads, dt, return_token_sum=False):
     return z.mean(axis=0)
 
 
-def attention_token_sum_split(sd, feats, num_heads, dt=np.float64, r16=None):
-    """The attention fusion of src/models/layers.py:135-164 restated in the split form the fused kernel uses
-    (csrc/score_tc.cu: item_attn_kernel / attn_user_setup / attn_half_tile): everything that involves only item
-    tokens is folded into per-item quantities, the user column enters each item row through one sigmoid weight,
-    every stored vector is centred over d so LayerNorm needs no mean.  Returns sum over tokens of the normalised
-    rows (before the LayerNorm affine and the 1/M).  ``r16``: optional rounding of the stored value blocks (item
-    C / Nbar / U, user U0), used to study 16-bit storage of the records (measured: halves the load/store traffic of
-    the front end but the conversions make it issue-bound, no net gain -- the kernel keeps fp32 records);
-    None = exact, equal to attention_fusion(return_token_sum=True)."""
+def attention_token_sum_mma(sd, feats, num_heads, rnd=None, dt=np.float64):
+    """The attention fusion of src/models/layers.py:135-164 in the form the fused kernel's register-MMA front end
+    evaluates it (csrc/score_tc.cu: attn_item_step), with that kernel's operand roundings ``rnd`` (None = exact,
+    then equal to attention_fusion(return_token_sum=True)).
+
+    With P = I - 11^T/D (centring over d), Wc = P W_o, xc_a = P (x_a + b_o) and o_a the concatenated per-head
+    attention outputs of row a, LayerNorm only needs yc_a = xc_a + Wc o_a.  Item rows a >= 1: the user column gets
+    the weight w_ah = sigmoid(s_a0,h - L_ah) (L_ah = logsumexp of the item-item scores, per item), so
+        yc_a = xc_a + sum_h (1 - w_ah) Nc_ah + Wc (w_a (.) v_u),     Nc_ah = Wc[:, head h] vbar_ah  (per item)
+    and the user row:  yc_0 = xc_0 + Wc (p_00 (.) v_u) + sum_{h,b} p_0b,h Uc_bh,   Uc_bh = Wc[:, head h] v_b,h.
+    Every product "coefficients x vectors" is a 16-bit MMA with fp32 accumulation: operands q / k (scores), w v_u,
+    p_00 v_u, 1 - w, p_0b, Wc, Uc are rounded once; Nc and xc are carried as hi + lo pairs (two K rows of the same
+    MMA), so they are exact to 2^-17.  Returns sum_a yc_a rstd_a (before the LayerNorm affine and the 1/M)."""
+    r = rnd or (lambda a: a)
     M = len(feats)
     B, D = feats[0].shape
     dh = D // num_heads
-    r16 = r16 or (lambda a: a)
+    H = num_heads
     w_in = sd["fusion_layer.attention.in_proj_weight"].astype(dt)
     b_in = sd["fusion_layer.attention.in_proj_bias"].astype(dt)
     w_o = sd["fusion_layer.attention.out_proj.weight"].astype(dt)
     b_o = sd["fusion_layer.attention.out_proj.bias"].astype(dt)
     scale = 1.0 / math.sqrt(dh)
     centre = lambda a: a - a.mean(axis=-1, keepdims=True)
+    Wc = w_o - w_o.mean(axis=0, keepdims=True)                   # P W_o: every column centred over the output index d
+    Wc16 = r(Wc)
+    hi_lo = (lambda a: (r(a), r(a - r(a)))) if rnd else (lambda a: (a, np.zeros_like(a)))
 
     def qkv(x):
         y = x @ w_in.T + b_in
-        return y[:, :D], y[:, D:2 * D], y[:, 2 * D:]
+        return y[:, :D] * scale, y[:, D:2 * D], y[:, 2 * D:]
 
-    def per_head_out(v):                       # U[h] = W_o[:, head h] v_h  -> (B, heads, D)
-        return np.stack([v[:, h * dh:(h + 1) * dh] @ w_o[:, h * dh:(h + 1) * dh].T for h in range(num_heads)], axis=1)
-
-    head_dot = lambda a, b: np.stack([(a[:, h * dh:(h + 1) * dh] * b[:, h * dh:(h + 1) * dh]).sum(1) for h in range(num_heads)], 1)
-    # per-user constants
+    heads = lambda a: a.reshape(B, H, dh)
     eu = feats[0]
     qu, ku, vu = qkv(eu)
-    U0c = r16(centre(per_head_out(vu)))
-    C0c = centre(eu + b_o)
-    S00 = head_dot(qu, ku) * scale
-    # per-item records
+    s00 = (heads(qu) * heads(ku)).sum(2)                          # fp32 on CUDA cores, unrounded operands
+    xc0 = centre(eu + b_o)
+    qu16, ku16, vu16 = r(qu), r(ku), r(vu)
     nt = M - 1
     xs = feats[1:]
     q, k, v = zip(*[qkv(x) for x in xs])
-    U = [per_head_out(vb) for vb in v]
+    # ---- per-item record (item_attn_kernel): exact fp32 item-item softmax, then the stored 16-bit operands
     rec = []
     for a in range(nt):
-        s = np.stack([head_dot(q[a] * scale, k[b]) for b in range(nt)], 2)            # (B, heads, nt)
+        s = np.stack([(heads(q[a]) * heads(k[b])).sum(2) for b in range(nt)], 2)      # (B, H, nt)
         m = s.max(2, keepdims=True)
         e = np.exp(s - m)
         L = (m + np.log(e.sum(2, keepdims=True)))[:, :, 0]
-        pn = e / e.sum(2, keepdims=True)
-        Nbar = sum(pn[:, :, b:b + 1] * U[b] for b in range(nt))
-        C = xs[a] + b_o + Nbar.sum(1)
-        rec.append(dict(C=r16(centre(C)), Nbar=r16(centre(Nbar)), U=r16(centre(U[a])), q=q[a] * scale, k=k[a] * scale, L=L))
-    rstd = lambda y: 1.0 / np.sqrt((y * y).mean(1, keepdims=True) + 1e-5)            # y is centred by construction
-    # user-token row
-    S0 = np.stack([head_dot(qu, rec[b]["k"]) for b in range(nt)], 2)                  # (B, heads, nt)
-    m = np.maximum(S00, S0.max(2))
-    e0 = np.exp(S00 - m); eb = np.exp(S0 - m[:, :, None])
+        pi = e / e.sum(2, keepdims=True)
+        vbar = sum(pi[:, :, b:b + 1] * heads(v[b]) for b in range(nt))                 # (B, H, dh)
+        Nc = np.stack([vbar[:, h] @ Wc[:, h * dh:(h + 1) * dh].T for h in range(H)], 1)   # (B, H, D)
+        Uc = np.stack([heads(v[a])[:, h] @ Wc[:, h * dh:(h + 1) * dh].T for h in range(H)], 1)
+        rec.append(dict(L=L, q16=r(q[a]), k16=r(k[a]), Nc=hi_lo(Nc), xc=hi_lo(centre(xs[a] + b_o)), Uc16=r(Uc)))
+    rstd = lambda y: 1.0 / np.sqrt((y * y).mean(1, keepdims=True) + 1e-5)
+    per_head = lambda c: np.repeat(c, dh, axis=1)                  # (B, H) -> (B, D)
+    # ---- user row
+    S0 = np.stack([(heads(qu16) * heads(rec[b]["k16"])).sum(2) for b in range(nt)], 2)   # (B, H, nt)
+    m = np.maximum(s00, S0.max(2))
+    e0 = np.exp(s00 - m); eb = np.exp(S0 - m[:, :, None])
     inv = 1.0 / (e0 + eb.sum(2))
-    y0 = C0c + ((e0 * inv)[:, :, None] * U0c).sum(1)
+    p00, p0b = r(e0 * inv), r(eb * inv[:, :, None])
+    y0 = xc0 + r(per_head(p00) * vu16) @ Wc16.T
     for b in range(nt):
-        y0 = y0 + ((eb[:, :, b] * inv)[:, :, None] * rec[b]["U"]).sum(1)
+        y0 = y0 + (p0b[:, :, b][:, :, None] * rec[b]["Uc16"]).sum(1)
     acc = y0 * rstd(y0)
+    # ---- item rows
     for a in range(nt):
-        w = 1.0 / (1.0 + np.exp(rec[a]["L"] - head_dot(rec[a]["q"], ku)))
-        y = rec[a]["C"] + (w[:, :, None] * (U0c - rec[a]["Nbar"])).sum(1)
+        sa0 = (heads(rec[a]["q16"]) * heads(ku16)).sum(2)
+        w = r(1.0 / (1.0 + np.exp(rec[a]["L"] - sa0)))          # the weight is rounded once, both uses start from it
+        omw = r(1.0 - w)
+        y = rec[a]["xc"][0] + rec[a]["xc"][1] + (omw[:, :, None] * (rec[a]["Nc"][0] + rec[a]["Nc"][1])).sum(1) + \
+            r(per_head(w) * vu16) @ Wc16.T
         acc = acc + y * rstd(y)
     return acc
 
@@ -481,12 +491,13 @@ def forward_pairs_lowp(sd, cfg, user_idx, item_idx, tag_idx, vis=None, txt=None,
         h = rnd(activation(pu + pi, act))
         start = 1
     elif ft == "attention":
-        # The kernel rounds acc = sum over tokens of the normalised rows (fp32 on CUDA cores) to the operand format and
+        # The kernel rounds acc = sum over tokens of the normalised rows to the operand format and
         # folds the LayerNorm affine and the mean into layer 1: W1' = W1 diag(ln_w / M) (rounded), b1' = b1 + W1 ln_b.
         M = len(feats)
         g = sd["fusion_layer.norm.weight"].astype(dt); beta = sd["fusion_layer.norm.bias"].astype(dt)
         # (attention_token_sum_split restates the kernel's split evaluation order; with exact storage it equals this)
-        h = rnd(attention_fusion(sd, feats, int(cfg.get("num_attention_heads", 4)), dt, return_token_sum=True))
+        # the token sum itself comes from the front end's 16-bit register MMAs: attention_token_sum_mma restates them
+        h = rnd(attention_token_sum_mma(sd, feats, int(cfg.get("num_attention_heads", 4)), rnd, dt))
         ws = list(ws); bs = list(bs)
         bs[0] = bs[0] + ws[0] @ beta
         ws[0] = ws[0] * (g / M)[None, :]
@@ -659,6 +670,29 @@ def novelty_metrics(rec_lists: Sequence[Sequence[int]], histories: Sequence[Set[
 # --------------------------------------------------------------------------
 # ranking task (--eval_task ranking)
 # --------------------------------------------------------------------------
+def gini_coefficient(counts: Sequence[int]) -> float:
+    """AdvancedMetrics.calculate_gini_coefficient (src/evaluation/advanced_metrics.py:72-105) of the dict values."""
+    c = np.sort(np.asarray(list(counts), dtype=np.float64))
+    n = len(c)
+    if n == 0 or c.sum() == 0:
+        return 0.0
+    idx = np.arange(1, n + 1)
+    return float((2 * np.sum(idx * c)) / (n * c.sum()) - (n + 1) / n)
+
+
+def intra_list_similarity(items: Sequence[int], emb: np.ndarray) -> float:
+    """NoveltyMetrics.calculate_diversity (src/evaluation/novelty.py:295-340): mean of the upper triangle of the
+    cosine-similarity matrix of the listed items' embeddings; < 2 embeddings -> 0.0 (zero rows count as missing)."""
+    rows = [np.asarray(emb[i], dtype=np.float64) for i in items if i >= 0 and np.any(emb[i] != 0)]
+    if len(rows) < 2:
+        return 0.0
+    X = np.stack(rows)
+    X = X / np.linalg.norm(X, axis=1, keepdims=True)
+    S = X @ X.T
+    iu = np.triu_indices(len(rows), k=1)
+    return float(S[iu].mean())
+
+
 def ranking_task_metrics(users: Sequence[str], test_items: Sequence[Sequence[str]],
                          score_fn, k: int) -> Dict[str, object]:
     """TopKRankingEvaluator.evaluate (src/evaluation/tasks.py:776-901) as the direct per-user loop: the user's test

@@ -115,3 +115,77 @@ def recommend_block(sd, cfg, users: torch.Tensor, feats: Dict[str, torch.Tensor]
             out_i[u0 + r, :len(keep)] = keep
             out_s[u0 + r, :len(keep)] = s[r][keep]
     return out_i, out_s
+
+
+# --------------------------------------------------------------------------
+# The LITERAL per-user path of the reference (what a reference user experiences): one get_recommendations call per
+# user, 256-item batches, per-item feature-dict fetches, torch.stack per key, sklearn LabelEncoder.transform per batch,
+# one forward per batch, .cpu().tolist(), Python sort.  Restated step by step so bench.py can time it beside the
+# batched forward; pinned in tests/ to the lists the real reference Recommender produced
+# (tests/golden/recommender_lists.json).
+# --------------------------------------------------------------------------
+class LiteralRecommender:
+    """src/inference/recommender.py:30-110, 144-269 with the model call replaced by ``forward_pairs`` above (the same
+    arithmetic, pinned to the reference module's outputs).  ``dataset`` is duck-typed like the reference's:
+    ``user_encoder`` / ``item_encoder`` (sklearn LabelEncoder), ``feature_cache`` (dict-like ``get``),
+    ``get_user_history(user_id) -> set``."""
+
+    def __init__(self, sd, cfg, dataset):
+        self.sd, self.cfg, self.dataset = sd, cfg, dataset
+
+    def _get_item_features(self, item_id_str):                       # recommender.py:239-246 (cache hit path)
+        item_id_str = str(item_id_str)
+        if self.dataset.feature_cache and self.dataset.feature_cache.get(item_id_str):
+            return self.dataset.feature_cache.get(item_id_str)
+        return None
+
+    @torch.no_grad()
+    def _score_items_batch(self, user_tensor, item_ids_str):         # recommender.py:144-236
+        if len(item_ids_str) == 0:
+            return []
+        item_features_list, valid_ids = [], []
+        for item_id in item_ids_str:                                  # :162-166
+            features = self._get_item_features(item_id)
+            if features:
+                item_features_list.append(features)
+                valid_ids.append(item_id)
+        if not valid_ids:
+            return [0.0] * len(item_ids_str)
+        keys = item_features_list[0].keys()
+        collated = {key: torch.stack([d[key] for d in item_features_list]) for key in keys}          # :175-178
+        user_batch = user_tensor.repeat(len(valid_ids))                                              # :182
+        item_idx = torch.tensor(self.dataset.item_encoder.transform(valid_ids), dtype=torch.long)   # :191
+        scores = forward_pairs(self.sd, self.cfg, user_batch, item_idx, collated["tag_idx"], collated.get("image"),
+                               collated.get("text_input_ids"), collated.get("numerical_features"))   # :221-222
+        scores = scores.squeeze().cpu().tolist()                                                     # :224
+        if not isinstance(scores, list):
+            scores = [scores]
+        final = {i: s for i, s in zip(valid_ids, scores)}                                            # :229-230
+        return [final.get(i, 0.0) for i in item_ids_str]
+
+    def get_recommendations(self, user_id, top_k=10, filter_seen=True, candidates=None):            # recommender.py:52-110
+        user_id = str(user_id)
+        user_classes = [str(c) for c in self.dataset.user_encoder.classes_]                          # :64 (O(n_users) per call)
+        if user_id not in user_classes:
+            return []
+        user_encoded = self.dataset.user_encoder.transform([user_id])[0]                             # :69
+        user_tensor = torch.tensor([user_encoded], dtype=torch.long)
+        if candidates is None:
+            cand = [str(i) for i in self.dataset.item_encoder.classes_]                              # :76
+        else:
+            item_classes = [str(c) for c in self.dataset.item_encoder.classes_]
+            cand = [str(i) for i in candidates if str(i) in item_classes]                            # :81-82
+        if not cand:
+            return []
+        if filter_seen:
+            seen = self.dataset.get_user_history(user_id)                                            # :88-90
+            cand = [i for i in cand if i not in seen]
+        if not cand:
+            return []
+        item_scores = []
+        for i in range(0, len(cand), 256):                                                           # :97-103
+            batch = cand[i:i + 256]
+            for item_id, sc in zip(batch, self._score_items_batch(user_tensor, batch)):
+                item_scores.append((item_id, sc))
+        item_scores.sort(key=lambda x: x[1], reverse=True)                                           # :105 (stable)
+        return item_scores[:top_k]

@@ -67,6 +67,11 @@ _SIGNATURES = {
     "pxr_topk_rows": (C.c_int, [C.c_void_p, _F, C.c_int64, C.c_int64, C.c_int32, _F, _F, C.c_void_p]),
     "pxr_novelty_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "pxr_novelty_metrics": (C.c_int, [_F, C.c_int32, C.c_int64, C.c_int64, _F, _F, _F, _F, _F, _F, C.c_size_t, C.c_void_p]),
+    "pxr_gini_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "pxr_gini": (C.c_int, [_F, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _F, _F, C.c_size_t, C.c_void_p]),
+    "pxr_ils_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "pxr_intra_list_similarity": (C.c_int, [C.c_void_p, _F, C.c_int32, C.c_int64, _F, C.c_int64, C.c_int32, C.c_int64, _F, _F,
+                                            C.c_size_t, C.c_void_p]),
     "pxr_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "pxr_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pxr_launch_count": (C.c_int64, [C.c_void_p]),

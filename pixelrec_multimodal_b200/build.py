@@ -11,7 +11,7 @@ PKG = Path(__file__).resolve().parent
 REPO = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libpxr.so"
-SOURCES = ["pxr_api.cu", "simt_kernels.cu", "score_tc.cu", "items_tc.cu", "sampling.cu", "novelty.cu"]
+SOURCES = ["pxr_api.cu", "simt_kernels.cu", "score_tc.cu", "items_tc.cu", "sampling.cu", "novelty.cu", "diversity.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math" if False else "-DPXR_PRECISE_MATH", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
               "-I", str(REPO / "include"), "-I", str(CSRC)]

@@ -48,19 +48,25 @@
 namespace tc {
 
 constexpr int D = 64, H1 = 512, H2 = 256, H3 = 128;
-constexpr int TU = 8, TI = 16;            // users x items per CTA tile (128 rows)
 constexpr int KCAP = 64;                  // slots of the per-user sorted list (K <= KCAP)
 constexpr int QCAP = 512;                 // candidate queue entries
-constexpr int THREADS = 512;                 // gated / concat: 16 warps
-constexpr int THREADS_ATT = 640;             // attention: a second front-end warpgroup (warps 16-19)
+constexpr int THREADS = 512;                 // 16 warps
 constexpr uint32_t IDX_MASK = 0x0FFFFFFFu;   // 28-bit item index inside a queue / list key
 constexpr int FMT_BF16 = 0, FMT_FP16 = 1;
 constexpr int F_CONCAT = 0, F_GATED = 1, F_ATTN = 2;   // front ends of the kernel template
-template <int FUS> __host__ __device__ constexpr int n_threads() { return FUS == F_ATTN ? THREADS_ATT : THREADS; }
+// users x items of one CTA tile (128 rows).  gated / concat: 8 x 16, row = user * 16 + item.  attention: 16 x 8,
+// row = item * 16 + user -- the 16 rows of an item are the M dimension of the front end's register MMAs
+template <int FUS> __host__ __device__ constexpr int tile_users() { return FUS == F_ATTN ? 16 : 8; }
+template <int FUS> __host__ __device__ constexpr int tile_items() { return FUS == F_ATTN ? 8 : 16; }
+template <int FUS> __host__ __device__ constexpr int n_threads() { return THREADS; }
 constexpr int NH = 4, DH = D / NH;                      // attention: heads x head dim (fast path: 4 x 16)
-// attention: per-item record, ATT_TOKENS token blocks of ATT_TOK floats (see item_attn_kernel)
-constexpr int ATT_TOKENS = 5, ATT_TOK = 720, ATT_ITEM = ATT_TOKENS * ATT_TOK;
-constexpr int ATT_C = 0, ATT_NB = 64, ATT_U = 320, ATT_Q = 576, ATT_K = 640, ATT_L = 704;
+// attention: per-item record = 16-bit MMA B fragments in lane order (see item_attn_kernel), in 16-byte units
+constexpr int ATT_TOKENS = 5;
+constexpr int REC_S = 0;                                // [4 heads][32 lanes]      q / k score fragments
+constexpr int REC_L = REC_S + NH * 32;                  // [4 quad lanes][2]        logsumexp of the item-item scores (fp32)
+constexpr int REC_T = REC_L + 8;                        // [5 tokens][4][32 lanes]  tail K rows: Nc hi, xc hi / lo, Nc lo
+constexpr int REC_U = REC_T + ATT_TOKENS * 128;         // [2 head pairs][4][32]    per-head out-projected item values
+constexpr int ATT_REC_U4 = REC_U + 256;                 // 1032 x 16 B = 16 512 B per item
 #ifndef PXR_TOPK_IDLE_NS
 #define PXR_TOPK_IDLE_NS 200
 #endif
@@ -72,24 +78,21 @@ enum {
   BAR_UNIT_RESET, N_BARS
 };
 
-// Per-CTA scratch in shared memory.  The attention front end needs 12 KB of per-user constants next to the weights,
-// so that variant keeps the epilogue biases in the kernel-parameter constant bank, a shorter candidate queue, and
-// stages E_u in the (idle) A1 tile during the per-unit setup.
+// Per-CTA scratch in shared memory.  (The attention variant keeps the epilogue biases in the kernel-parameter constant
+// bank and stages its per-unit user constants in the idle A1 tile; its per-user operands then live in registers.)
 template <int FUS>
 struct MiscT {
   static constexpr bool ATT = (FUS == F_ATTN);
-  static constexpr int QC = ATT ? 128 : QCAP;          // candidate queue entries
+  static constexpr int TU = tile_users<FUS>();
+  static constexpr int QC = ATT ? 256 : QCAP;          // candidate queue entries
   float b1[ATT ? 4 : H1]; float b2[ATT ? 4 : H2]; float b3[ATT ? 4 : H3]; float w4[ATT ? 4 : H3];   // contiguous
   float eu[ATT ? 1 : TU][D];
   float lu[ATT ? 1 : TU][8];
-  float qu[ATT ? TU : 1][D], ku[ATT ? TU : 1][D];       // attention: in_proj q / k of the user token (unscaled)
-  float U0c[ATT ? TU : 1][NH][D];                       // attention: per-head out_proj of v_u, centred over d
-  float S00[ATT ? TU : 1][NH];                          // attention: q_u,h . k_u,h / sqrt(dh)
   unsigned long long list[TU][KCAP];
   unsigned long long queue[QC];
   float thr[TU];
   uint32_t seen_mask[4][TU];
-  uint32_t q_tail[2], q_head[2];                     // two candidate queues: users 0-3 -> top-K warp 5, users 4-7 -> warp 6
+  uint32_t q_tail[2], q_head[2];                     // two candidate queues: lower half of the users -> top-K warp 5, upper half -> warp 6
   uint32_t tmem_base;
   float b4;
   unsigned long long bars[N_BARS];
@@ -105,11 +108,11 @@ struct Map {
   static constexpr uint32_t OFF_W3 = OFF_W2 + 131072u;           // 4 K-blocks x (64 rows x 128 B)  = 32 KB
   static constexpr uint32_t WIMG = OFF_W3 + 32768u;
   static constexpr uint32_t OFF_A1 = WIMG;                       // gated: 128 rows x 128 B, SWIZZLE_128B
-  static constexpr uint32_t PI_STRIDE = 1040, PI_BUF = TI * PI_STRIDE;   // concat: 16 item partials (512 x 16 bit)
+  static constexpr uint32_t PI_STRIDE = 1040, PI_BUF = tile_items<F_CONCAT>() * PI_STRIDE;   // concat: 16 item partials (512 x 16 bit)
   static constexpr uint32_t OFF_PI = WIMG;                       // padded by 16 B per row: conflict-free reads
   static constexpr uint32_t PU_STRIDE = 2064;                    // concat: 8 user partials (512 fp32), padded
   static constexpr uint32_t OFF_PU = OFF_PI + 2 * PI_BUF;
-  static constexpr uint32_t OFF_MISC = GATED ? OFF_A1 + 16384u : OFF_PU + TU * PU_STRIDE;
+  static constexpr uint32_t OFF_MISC = GATED ? OFF_A1 + 16384u : OFF_PU + tile_users<F_CONCAT>() * PU_STRIDE;
   static constexpr uint32_t SMEM = OFF_MISC + (uint32_t)sizeof(MiscT<FUS>) + 1024u;   // + alignment slack
   // tensor memory (columns)
   static constexpr uint32_t TM_D3 = 128, TM_D2 = 256;
@@ -121,14 +124,8 @@ struct Map {
 };
 static_assert(Map<F_GATED>::SMEM <= 232448 && Map<F_CONCAT>::SMEM <= 232448 && Map<F_ATTN>::SMEM <= 232448, "shared memory budget");
 static_assert(Map<F_CONCAT>::OFF_MISC % 16 == 0 && Map<F_GATED>::OFF_MISC % 16 == 0, "alignment");
-static_assert(offsetof(MiscT<F_ATTN>, qu) % 16 == 0 && offsetof(MiscT<F_ATTN>, U0c) % 16 == 0 && offsetof(MiscT<F_ATTN>, list) % 8 == 0, "alignment");
+static_assert(offsetof(MiscT<F_ATTN>, list) % 8 == 0, "alignment");
 static_assert(offsetof(MiscT<F_GATED>, list) % 8 == 0 && offsetof(MiscT<F_GATED>, bars) % 8 == 0 && offsetof(MiscT<F_ATTN>, bars) % 8 == 0, "alignment");
-
-// attention: E_u + out_proj bias, centred over d, of one CTA's 8 users (rebuilt per unit by the front-end warps).
-// Read once per half tile, so it lives in global memory (one slot per CTA); the hot per-user constants are in smem.
-struct UserAttn {
-  float C0c[TU][D];
-};
 
 struct Params {
   const uint8_t* wimg;          // [2][WIMG] pre-swizzled 16-bit operand images (rank 0, rank 1)
@@ -138,14 +135,15 @@ struct Params {
   const float* item_logit;      // gated: [rows][8] fp32 item part of the gate logits (+ gate bias)
   const uint16_t* item_pi;      // concat: [rows][512] 16-bit item partial of layer 1 (+ b1)
   const float* w1u_t;           // concat: [64][512] fp32, user columns of W1 transposed
-  const float* attn_rec;        // attention: [rows][ATT_ITEM] fp32 per-item records
+  const uint4* attn_rec;        // attention: [rows][ATT_REC_U4] per-item records (16-bit MMA B fragments in lane order)
+  const uint4* wo_frag;         // attention: centred out_proj weight as B fragments, [4 k-steps][4][32 lanes]
+  uint4* xc0_scratch;           // attention: per CTA, xc_0 of its 16 users in accumulator layout (ATT_XC0_U4 x 16 B)
   const float* attn_in_wt;      // attention: in_proj weight transposed [64][192], bias [192]
   const float* attn_in_b;
   const float* attn_out_wt;     // attention: out_proj weight transposed [64][64], bias [64]
   const float* attn_out_b;
   const float* ln_w;            // attention: LayerNorm weight / bias [64]
   const float* ln_b;
-  UserAttn* user_scratch;       // attention: one UserAttn per CTA
   float bias_c[H1 + H2 + H3 + H3 + 4];   // attention: b1' b2 b3 w4 b4 read through the constant bank (no room in smem)
   const float* user_emb;        // (n_users_total, D) fp32 table
   const int64_t* user_idx;      // (n_users,)
@@ -161,6 +159,7 @@ struct Params {
 
 struct Unit { int g, s; int64_t row_lo, row_hi; int ntiles; };
 
+template <int TI>
 __device__ __forceinline__ Unit decode_unit(const Params& p, int w) {
   Unit u;
   u.g = w / p.S; u.s = w % p.S;
@@ -241,263 +240,300 @@ __device__ __forceinline__ void concat_h1_chunk(const uint8_t* pi_row, const uin
 
 
 // ---------------------------------------------------------------------------------------------
-// attention fusion front end (src/models/layers.py:135-164 as documented; SURVEY.md A5 split)
+// attention fusion front end (src/models/layers.py:135-164 as documented; SURVEY.md A5 split) on register-level MMAs
 //
-// Tokens of pair (u, i): x_0 = E_u, x_1.. = the item-side modality vectors.  Everything that involves only
-// item tokens is folded into the per-item record once per catalogue (item_attn_kernel):
-//   row a >= 1:  softmax over [s_a0 | item part] => with L_ah = logsumexp_b>=1 s_ab,h the user column gets weight
-//                w_ah = sigmoid(q_a,h . k_u,h / sqrt(dh) - L_ah) and the item columns share 1 - w_ah, so
-//                y_a = x_a + attn_a = C_a + sum_h w_ah (U0_h[u] - Nbar_ah),   C_a = x_a + b_o + sum_h Nbar_ah,
-//                Nbar_ah = sum_b>=1 softmax_b(s_ab,h) U_bh,   U_bh = W_o[:, head h] v_b,h   (out_proj folded in)
-//   row 0:       softmax over [q_u.k_u, q_u.k_b ...] per head, y_0 = E_u + b_o + sum_h (p_h0 U0_h + sum_b p_hb U_bh)
-// LayerNorm only needs y - mean(y): every stored vector (C, Nbar, U, U0, E_u + b_o) is CENTRED over d in advance,
-// and as the weights of each row sum to one the combination is centred too -- no per-pair mean.  Then
-//   fused = ln_b + ln_w / M * sum_a (y_a - mean) * rstd_a;
-// the affine part is folded into layer 1 (W1' = W1 diag(ln_w / M), b1' = b1 + W1 ln_b), so the A1 operand is
-// the 16-bit rounding of   acc = sum_a (y_a - mean) * rstd_a.
-// Thread = (item j of a half tile of 8, 4-wide slice s of D; head of the slice = s / 4), all 8 users of the CTA.
+// Tokens of pair (u, i): x_0 = E_u, x_1.. = the item-side modality vectors; o_a = concatenated per-head attention
+// outputs of row a; y_a = x_a + b_o + W_o o_a; fused = mean_a LayerNorm(y_a).  LayerNorm only needs y - mean(y), so
+// with P = I - 11^T / D everything is carried centred over d: Wc = P W_o, xc_a = P (x_a + b_o), yc_a = xc_a + Wc o_a.
+//   item row a >= 1: the user column gets w_ah = sigmoid(s_a0,h - L_ah), L_ah = logsumexp_b>=1 s_ab,h (per item), and
+//       yc_a = xc_a + sum_h (1 - w_ah) Nc_ah + Wc (w_a (.) v_u),      Nc_ah = Wc[:, head h] vbar_ah   (per item)
+//   user row:    softmax over [q_u.k_u, q_u.k_b ...] per head,
+//       yc_0 = xc_0 + Wc (p_00 (.) v_u) + sum_h sum_b p_0b,h Uc_bh,   Uc_bh = Wc[:, head h] v_b,h     (per item)
+//   fused = ln_b + ln_w / M * sum_a yc_a rstd_a; the affine part is folded into layer 1 (W1' = W1 diag(ln_w / M),
+//   b1' = b1 + W1 ln_b), so the A1 operand is the 16-bit rounding of acc = sum_a yc_a rstd_a.
+// Every "coefficients x vectors" product above is a small GEMM whose B operand depends on the ITEM only (or on nothing:
+// Wc), so for one item and 16 users it is a chain of mma.sync.m16n8k16 (M = the 16 users of the CTA, fp32 accumulators in
+// registers -- the tcgen05 chain owns all 512 TMEM columns, and these GEMMs are 1/6 of its FLOPs): scores (K = 16 per
+// head), per token [w_a (.) v_u | 1 - w_a, 1] (K = 80) x [Wc ; Nc_a hi, xc_a hi, xc_a lo, Nc_a lo] -> yc_a (16 x 64),
+// the user row with K = 64 + 32.  The per-item B fragments are stored in the record in lane order (one coalesced
+// 16-byte load per lane and fragment pair), Wc's fragments stay in L1.  CUDA cores only produce coefficients (20 sigmoids, a
+// 6-way softmax per head), the A fragments (packed 16-bit multiplies by the per-user value fragments kept in registers),
+// sum y^2, and the rstd-weighted token sum: ~95 warp instructions per pair instead of ~360 for the all-CUDA-core form.
+// A front-end warp owns one item x 16 users at a time (tile = 8 items x 16 users, two items per warp).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 ldg_stream(const float* p) {      // item records: read once per tile, keep them out of L1
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {      // item records: read once per (item, 16 users), keep them out of L1
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
-__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
-  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+template <int FMT>
+__device__ __forceinline__ void hmma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (FMT == FMT_BF16)
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void fma4(float* acc, float w, const float4& v) {
-  acc[0] = fmaf(w, v.x, acc[0]); acc[1] = fmaf(w, v.y, acc[1]); acc[2] = fmaf(w, v.z, acc[2]); acc[3] = fmaf(w, v.w, acc[3]);
+template <int FMT> __device__ __forceinline__ uint32_t mul2(uint32_t a, uint32_t b) {     // packed 16-bit multiply, rounded once
+  uint32_t d;
+  if (FMT == FMT_BF16) asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  else asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
 }
+__device__ __forceinline__ uint32_t dup_lo(uint32_t x) { return __byte_perm(x, x, 0x1010); }
+__device__ __forceinline__ uint32_t dup_hi(uint32_t x) { return __byte_perm(x, x, 0x3232); }
 
-// per-unit constants of this CTA's 8 users (128 threads, named barrier 1).  `stage` = 4 KB of scratch shared memory
-// (the idle A1 tile): E_u at [0, 2 KB), v_u at [2 KB, 4 KB).
-template <class MiscA>
-__device__ __forceinline__ void attn_user_setup(const Params& p, MiscA& ms, float* stage, UserAttn* us, int tid) {
-  float (*eu)[D] = reinterpret_cast<float (*)[D]>(stage);
-  float (*vu)[D] = reinterpret_cast<float (*)[D]>(stage + TU * D);
+// per-unit constants of a front-end thread: A fragments (rows = the CTA's 16 users) of k_u, q_u / sqrt(dh), v_u per head,
+// xc_0 = P (E_u + b_o) in accumulator layout, q_u.k_u / sqrt(dh) of rows g and g + 8
+struct AttnUserFrag {
+  uint32_t ku[NH][4], qu[NH][4], vu[NH][4];
+  float s00[2][NH];
+};
+// xc_0 in accumulator layout, [8 n-tiles][32 lanes] x 16 B per CTA: only read once per item step (it initialises the user
+// row's accumulators), so it lives in a per-CTA global scratch line set (L2) instead of 32 registers
+constexpr int ATT_XC0_U4 = 8 * 32;
+
+// `stage` = the idle A1 tile (16 KB): [16][192] fp32 in_proj outputs, then [16][64] fp32 E_u.  128 threads, named barrier 1.
+template <int FMT>
+__device__ __forceinline__ void attn_user_setup(const Params& p, float* stage, int tid, int64_t ubase, AttnUserFrag& U, uint4* xc0_out) {
+  constexpr int TUA = tile_users<F_ATTN>();
+  float (*qkv)[3 * D] = reinterpret_cast<float (*)[3 * D]>(stage);
+  float (*eu)[D] = reinterpret_cast<float (*)[D]>(stage + TUA * 3 * D);
+  for (int i = tid; i < TUA * (D / 4); i += 128) {
+    const int u = i >> 4, d4 = (i & 15) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ubase + u < p.n_users) v = *reinterpret_cast<const float4*>(p.user_emb + p.user_idx[ubase + u] * D + d4);
+    *reinterpret_cast<float4*>(&eu[u][d4]) = v;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
   for (int n = tid; n < 3 * D; n += 128) {                 // in_proj of the user token: q | k | v
-    float acc[TU];
+    float acc[TUA];
     const float b = p.attn_in_b[n];
 #pragma unroll
-    for (int u = 0; u < TU; ++u) acc[u] = b;
+    for (int u = 0; u < TUA; ++u) acc[u] = b;
 #pragma unroll 4
     for (int k = 0; k < D; ++k) {
       const float w = p.attn_in_wt[k * 3 * D + n];
 #pragma unroll
-      for (int u = 0; u < TU; ++u) acc[u] = fmaf(w, eu[u][k], acc[u]);
+      for (int u = 0; u < TUA; ++u) acc[u] = fmaf(w, eu[u][k], acc[u]);
     }
-    float* dst = n < D ? &ms.qu[0][n] : (n < 2 * D ? &ms.ku[0][n - D] : &vu[0][n - 2 * D]);
+    const float sc = n < D ? 0.25f : 1.f;                  // q / sqrt(dh), dh = 16
 #pragma unroll
-    for (int u = 0; u < TU; ++u) dst[u * D] = acc[u];
+    for (int u = 0; u < TUA; ++u) qkv[u][n] = acc[u] * sc;
   }
   asm volatile("bar.sync 1, 128;" ::: "memory");
-  {
-    const int d = tid & 63, hp = tid >> 6;                 // out_proj per head: U0[u][h][d] = sum_e W_o[d][16h+e] v_u[16h+e]
+  const int lane = tid & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const int h = 2 * hp + hh;
-      float acc[TU];
+  for (int h = 0; h < NH; ++h) {
+    const int c = DH * h + 2 * t;
 #pragma unroll
-      for (int u = 0; u < TU; ++u) acc[u] = 0.f;
-#pragma unroll 4
-      for (int e = 0; e < DH; ++e) {
-        const float w = p.attn_out_wt[(h * DH + e) * D + d];
+    for (int m = 0; m < 3; ++m) {                          // 0: q, 1: k, 2: v
+      uint32_t* dst = m == 0 ? U.qu[h] : (m == 1 ? U.ku[h] : U.vu[h]);
+      const int o = m * D + c;
+      dst[0] = pack2<FMT>(qkv[g][o], qkv[g][o + 1]);         dst[1] = pack2<FMT>(qkv[g + 8][o], qkv[g + 8][o + 1]);
+      dst[2] = pack2<FMT>(qkv[g][o + 8], qkv[g][o + 9]);     dst[3] = pack2<FMT>(qkv[g + 8][o + 8], qkv[g + 8][o + 9]);
+    }
 #pragma unroll
-        for (int u = 0; u < TU; ++u) acc[u] = fmaf(w, vu[u][h * DH + e], acc[u]);
+    for (int r = 0; r < 2; ++r) {
+      float dot = 0.f;
+#pragma unroll
+      for (int e = 0; e < DH; ++e) dot = fmaf(qkv[g + 8 * r][DH * h + e], qkv[g + 8 * r][D + DH * h + e], dot);
+      U.s00[r][h] = dot;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {                            // xc_0 = (E_u + b_o) centred over d
+    const float* e = eu[g + 8 * r];
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) part += e[16 * t + i] + p.attn_out_b[16 * t + i];
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    const float mean = part * (1.f / D);
+    if (tid < 32) {                                         // identical in every front-end warp: warp 0 writes the scratch
+#pragma unroll
+      for (int nn = 0; nn < 8; ++nn) {
+        const int c = 8 * nn + 2 * t;
+        float2 v2 = make_float2(e[c] + p.attn_out_b[c] - mean, e[c + 1] + p.attn_out_b[c + 1] - mean);
+        reinterpret_cast<float2*>(xc0_out + nn * 32 + lane)[r] = v2;      // .xy: row g, .zw: row g + 8
       }
-#pragma unroll
-      for (int u = 0; u < TU; ++u) ms.U0c[u][h][d] = acc[u];
     }
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  // centre over d: one warp-level pass per 64-vector (8 users x (4 heads + C0) = 40 vectors, 10 per warp)
-  {
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int v = warp; v < TU * (NH + 1); v += 4) {
-      const int u = v / (NH + 1), h = v % (NH + 1);
-      float a, b;
-      if (h < NH) { a = ms.U0c[u][h][lane]; b = ms.U0c[u][h][lane + 32]; }
-      else { a = eu[u][lane] + p.attn_out_b[lane]; b = eu[u][lane + 32] + p.attn_out_b[lane + 32]; }
-      float sm_ = a + b;
+  __threadfence_block();
+  asm volatile("bar.sync 1, 128;" ::: "memory");              // the stage (A1 tile) may be overwritten now; xc_0 is visible to the CTA
+}
+
+// Y += [x_h (.) v_u]_h . Wc^T: x[h] = (coefficient of row g, coefficient of row g + 8) packed; one k-step per head
+template <int FMT>
+__device__ __forceinline__ void attn_wo_pass(float (&Y)[8][4], const uint32_t (&x)[NH], const AttnUserFrag& U,
+                                             const uint4* __restrict__ wo, int lane) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sm_ += __shfl_xor_sync(0xffffffffu, sm_, o);
-      const float mean = sm_ * (1.f / D);
-      if (h < NH) { ms.U0c[u][h][lane] = a - mean; ms.U0c[u][h][lane + 32] = b - mean; }
-      else { us->C0c[u][lane] = a - mean; us->C0c[u][lane + 32] = b - mean; }
+  for (int h = 0; h < NH; ++h) {
+    const uint32_t lo = dup_lo(x[h]), hi = dup_hi(x[h]);
+    uint32_t a[4];
+    a[0] = mul2<FMT>(lo, U.vu[h][0]); a[1] = mul2<FMT>(hi, U.vu[h][1]);
+    a[2] = mul2<FMT>(lo, U.vu[h][2]); a[3] = mul2<FMT>(hi, U.vu[h][3]);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      const uint4 w = __ldg(wo + (h * 4 + np) * 32 + lane);
+      hmma<FMT>(Y[2 * np], a, w.x, w.y);
+      hmma<FMT>(Y[2 * np + 1], a, w.z, w.w);
     }
-  }
-  if (tid < TU * NH) {
-    const int u = tid >> 2, h = tid & 3;
-    float dot = 0.f;
-    for (int e = 0; e < DH; ++e) dot = fmaf(ms.qu[u][h * DH + e], ms.ku[u][h * DH + e], dot);
-    ms.S00[u][h] = dot * 0.25f;                            // 1 / sqrt(dh), dh = 16
   }
 }
 
-// v[u4]: partial sums of 4 users held by every lane of a 4-lane head quad -> reduce-scatter: lane ql of the quad ends
-// up with the total of user u4 = ql (3 shuffles instead of 8, and the value is then transformed once, not four times)
-__device__ __forceinline__ float quad_scatter4(const float* v, int ql) {
-  const bool b1 = ql & 2, b0 = ql & 1;
-  const float k0 = (b1 ? v[2] : v[0]) + __shfl_xor_sync(0xffffffffu, b1 ? v[0] : v[2], 2);
-  const float k1 = (b1 ? v[3] : v[1]) + __shfl_xor_sync(0xffffffffu, b1 ? v[1] : v[3], 2);
-  return (b0 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, b0 ? k0 : k1, 1);
-}
-
-// y[u4][4]: 4 users x this lane's 4 dims, already centred over d.  r[u4] = LayerNorm rstd of each user: the sums of
-// squares are reduce-scattered over the 16 lanes of the item (5 shuffles), one rsqrt per lane, 4 indexed gathers.
-__device__ __forceinline__ void ln_rstd4(const float (*y)[4], int lane, float* r) {
-  float ss[4];
+// acc (+)= Y * rstd(Y) for the rows g (entries 0, 1) and g + 8 (entries 2, 3); Y is centred by construction
+template <bool FIRST>
+__device__ __forceinline__ void attn_norm_acc(const float (&Y)[8][4], float (&acc)[8][4]) {
+  float p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f};      // independent partial sums: short dependency chains
 #pragma unroll
-  for (int u4 = 0; u4 < 4; ++u4) ss[u4] = fmaf(y[u4][3], y[u4][3], fmaf(y[u4][2], y[u4][2], fmaf(y[u4][1], y[u4][1], y[u4][0] * y[u4][0])));
-  const bool b3 = lane & 8, b2 = lane & 4;
-  const float k0 = (b3 ? ss[2] : ss[0]) + __shfl_xor_sync(0xffffffffu, b3 ? ss[0] : ss[2], 8);
-  const float k1 = (b3 ? ss[3] : ss[1]) + __shfl_xor_sync(0xffffffffu, b3 ? ss[1] : ss[3], 8);
-  float t = (b2 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, b2 ? k0 : k1, 4);       // user u4 = 2 b3 + b2, summed over 4 lanes
-  t += __shfl_xor_sync(0xffffffffu, t, 2);
-  t += __shfl_xor_sync(0xffffffffu, t, 1);
-  const float rr = rsqrtf(fmaf(t, 1.f / D, 1e-5f));
+  for (int nn = 0; nn < 8; ++nn) {
+    p0[nn & 3] = fmaf(Y[nn][0], Y[nn][0], fmaf(Y[nn][1], Y[nn][1], p0[nn & 3]));
+    p1[nn & 3] = fmaf(Y[nn][2], Y[nn][2], fmaf(Y[nn][3], Y[nn][3], p1[nn & 3]));
+  }
+  float s0 = (p0[0] + p0[1]) + (p0[2] + p0[3]), s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  const float r0 = rsqrtf(fmaf(s0, 1.f / D, 1e-5f)), r1 = rsqrtf(fmaf(s1, 1.f / D, 1e-5f));
 #pragma unroll
-  for (int u4 = 0; u4 < 4; ++u4) r[u4] = __shfl_sync(0xffffffffu, rr, (lane & 19) | (u4 << 2));
-}
-
-// acc = sum over tokens of the normalised rows, for the 8 users x 8 items of one half tile -> 16-bit A1 rows.
-// `wait_a1` is called once, right before the first store into A1.
-// The front end is latency-bound per warp (two warps per scheduler), so latency is hidden by instruction-level
-// parallelism: every step is a loop over 4 users (independent chains) with its shuffles issued back to back, and
-// cross-lane sums are reduce-scatters + indexed gathers (28 shuffles per (token, 4 users) instead of 40; one
-// softmax / sigmoid / rsqrt per value instead of one per lane).
-template <int FMT, class MiscA, typename WaitA1>
-__device__ __forceinline__ void attn_half_tile(const MiscA& ms, const UserAttn* us, const float* rec, int nt, uint8_t* a1,
-                                               int half, int tid, int lane, WaitA1 wait_a1) {
-  const int j8 = tid >> 4, s = tid & 15, hd = s >> 2, ql = s & 3;
-  const int gb = lane & 16;                                // first lane of this item's 16-lane group
-  float acc[TU][4];
-  // token data of the first item token: fetched now, consumed after the user-token row
-  float4 c, q, nb[NH]; float Lh;
-  auto load_tok = [&](int a, float4& c_, float4& q_, float4* nb_, float& L_) {
-    const float* tr = rec + a * ATT_TOK;
-    c_ = ldg_stream(tr + ATT_C + 4 * s);
-    q_ = ldg_stream(tr + ATT_Q + 4 * s);
-#pragma unroll
-    for (int h = 0; h < NH; ++h) nb_[h] = ldg_stream(tr + ATT_NB + h * D + 4 * s);
-    L_ = __ldg(tr + ATT_L + hd);
-  };
-  {
-    // ---- token 0 (the user token): scores against every token, softmax per head, value mix, normalise
-    float pw[2][ATT_TOKENS + 1];                           // softmax weights of users ql and 4 + ql, head hd: [0] user token, [1 + b] item token b
-    {
-      float4 kb[ATT_TOKENS];
-#pragma unroll
-      for (int b = 0; b < ATT_TOKENS; ++b) kb[b] = ldg_stream(rec + min(b, nt - 1) * ATT_TOK + ATT_K + 4 * s);
-#pragma unroll
-      for (int u = 0; u < TU; ++u) {
-        const float4 c0 = __ldcg(reinterpret_cast<const float4*>(&us->C0c[u][4 * s]));
-        acc[u][0] = c0.x; acc[u][1] = c0.y; acc[u][2] = c0.z; acc[u][3] = c0.w;
-      }
-#pragma unroll
-      for (int ug = 0; ug < 2; ++ug) {
-        float S[ATT_TOKENS][4];
-#pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) {
-          const float4 qv = *reinterpret_cast<const float4*>(&ms.qu[4 * ug + u4][4 * s]);
-#pragma unroll
-          for (int b = 0; b < ATT_TOKENS; ++b) S[b][u4] = dot4(qv, kb[b]);
-        }
-        float sv[ATT_TOKENS];
-#pragma unroll
-        for (int b = 0; b < ATT_TOKENS; ++b) sv[b] = quad_scatter4(S[b], ql);
-        const float s00 = ms.S00[4 * ug + ql][hd];
-        float m = s00;
-#pragma unroll
-        for (int b = 0; b < ATT_TOKENS; ++b) { if (b >= nt) sv[b] = -INFINITY; m = fmaxf(m, sv[b]); }
-        const float e0 = __expf(s00 - m);
-        float sum = e0;
-#pragma unroll
-        for (int b = 0; b < ATT_TOKENS; ++b) { sv[b] = __expf(sv[b] - m); sum += sv[b]; }
-        const float inv = __fdividef(1.f, sum);
-        pw[ug][0] = e0 * inv;
-#pragma unroll
-        for (int b = 0; b < ATT_TOKENS; ++b) pw[ug][1 + b] = sv[b] * inv;
-      }
+  for (int nn = 0; nn < 8; ++nn) {
+    if (FIRST) { acc[nn][0] = r0 * Y[nn][0]; acc[nn][1] = r0 * Y[nn][1]; acc[nn][2] = r1 * Y[nn][2]; acc[nn][3] = r1 * Y[nn][3]; }
+    else {
+      acc[nn][0] = fmaf(r0, Y[nn][0], acc[nn][0]); acc[nn][1] = fmaf(r0, Y[nn][1], acc[nn][1]);
+      acc[nn][2] = fmaf(r1, Y[nn][2], acc[nn][2]); acc[nn][3] = fmaf(r1, Y[nn][3], acc[nn][3]);
     }
+  }
+}
+
+// B fragments of one token's tail k-step (16 registers per lane)
+struct TailFrag { uint4 f[4]; };
+__device__ __forceinline__ void attn_load_tail(TailFrag& tf, const uint4* __restrict__ rec, int a, int lane) {
+#pragma unroll
+  for (int np = 0; np < 4; ++np) tf.f[np] = ldg_stream_u4(rec + REC_T + (a * 4 + np) * 32 + lane);
+}
+
+// Y = yc_a of item row a (token a of the record): tail k-step first (its fragments are then dead, so the next token's can be
+// fetched into the same registers a whole token ahead of their use), then the Wc pass.  x[h] = (w_ah row g, w_ah row g + 8).
+template <int FMT>
+__device__ __forceinline__ void attn_token(float (&Y)[8][4], const uint32_t (&x)[NH], const AttnUserFrag& U, TailFrag& tf,
+                                           const uint4* __restrict__ rec, const uint4* __restrict__ wo, int a_next, int lane) {
+  const int t = lane & 3;
+  const uint32_t one2 = FMT == FMT_BF16 ? 0x3F803F80u : 0x3C003C00u;
+  // tail k-step, K columns: 0-3 (1 - w_h) -> Nc_h hi, 4 / 5: 1 -> xc hi / lo, 8-11 (1 - w_h) -> Nc_h lo
+  const float2 fa = unpack2<FMT>((t & 1) ? x[2] : x[0]), fb = unpack2<FMT>((t & 1) ? x[3] : x[1]);   // .x: row g, .y: row g + 8
+  uint32_t r0 = pack2<FMT>(1.f - fa.x, 1.f - fb.x), r1 = pack2<FMT>(1.f - fa.y, 1.f - fb.y);
+  if (t == 2) { r0 = one2; r1 = one2; }
+  if (t == 3) { r0 = 0u; r1 = 0u; }
+  const uint32_t at[4] = {r0, r1, t < 2 ? r0 : 0u, t < 2 ? r1 : 0u};
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {
+    Y[2 * np][0] = Y[2 * np][1] = Y[2 * np][2] = Y[2 * np][3] = 0.f;
+    Y[2 * np + 1][0] = Y[2 * np + 1][1] = Y[2 * np + 1][2] = Y[2 * np + 1][3] = 0.f;
+    hmma<FMT>(Y[2 * np], at, tf.f[np].x, tf.f[np].y);
+    hmma<FMT>(Y[2 * np + 1], at, tf.f[np].z, tf.f[np].w);
+  }
+  if (a_next >= 0) attn_load_tail(tf, rec, a_next, lane);
+  attn_wo_pass<FMT>(Y, x, U, wo, lane);
+}
+
+// acc[nn][..] (accumulator layout: rows g / g + 8 of the 16 users, columns 8 nn + 2 t, + 1) = sum over the 1 + nt tokens of
+// the normalised rows of pair (user row, this item).  The front end is latency-bound per warp (one warp per scheduler), so
+// the token chain is software-pipelined: the MMAs of token a + 1 are issued before the norm / accumulate of token a (two
+// accumulator sets), every record fragment is fetched one token ahead of its use, and the record of the item this warp
+// takes in the next tile is pulled into L2 while this one is processed.
+template <int FMT>
+__device__ __forceinline__ void attn_item_step(const AttnUserFrag& U, const uint4* __restrict__ rec, const uint4* __restrict__ rec_next,
+                                               const uint4* __restrict__ wo, const uint4* __restrict__ xc0, int nt, int lane,
+                                               float (&acc)[8][4]) {
+  const int t = lane & 3;
+  uint4 sf[NH];
+#pragma unroll
+  for (int h = 0; h < NH; ++h) sf[h] = ldg_stream_u4(rec + REC_S + h * 32 + lane);
+  const uint4 La4 = __ldg(rec + REC_L + 2 * t), Lb4 = __ldg(rec + REC_L + 2 * t + 1);     // L of tokens 2t, 2t + 1 x 4 heads
+  float YA[8][4], YB[8][4];
+#pragma unroll
+  for (int nn = 0; nn < 8; ++nn) {                                                       // user row starts from xc_0
+    const uint4 v = __ldcg(xc0 + nn * 32 + lane);
+    YA[nn][0] = __uint_as_float(v.x); YA[nn][1] = __uint_as_float(v.y); YA[nn][2] = __uint_as_float(v.z); YA[nn][3] = __uint_as_float(v.w);
+  }
+  uint4 uf[2][4];
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+    for (int np = 0; np < 4; ++np) uf[kk][np] = ldg_stream_u4(rec + REC_U + (kk * 4 + np) * 32 + lane);
+  TailFrag tf;
+  attn_load_tail(tf, rec, 0, lane);
+  if (rec_next) {                                                                        // 129 lines of 128 B
+    const char* pn = reinterpret_cast<const char*>(rec_next) + lane * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + i * 4096));
+    if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + 16384));
+  }
+  const float La[NH] = {__uint_as_float(La4.x), __uint_as_float(La4.y), __uint_as_float(La4.z), __uint_as_float(La4.w)};
+  const float Lb[NH] = {__uint_as_float(Lb4.x), __uint_as_float(Lb4.y), __uint_as_float(Lb4.z), __uint_as_float(Lb4.w)};
+  // ---- scores: c1[h] = k_u,h . q_a,h (item rows, their user column), c0[h] = q_u,h . k_b,h (user row); entry 0 / 1: row g,
+  //      token 2t / 2t + 1; entry 2 / 3: row g + 8
+  uint32_t wpk[2][NH];                                     // sigmoid weights of tokens 2t / 2t + 1: (row g, row g + 8) packed
+  {
+    uint32_t x0[NH], pa[2][4];
+    const bool v0 = 2 * t < nt, v1 = 2 * t + 1 < nt;
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
-      float ph[TU];
-#pragma unroll
-      for (int u = 0; u < TU; ++u) ph[u] = __shfl_sync(0xffffffffu, pw[u >> 2][0], gb | (4 * h) | (u & 3));
-#pragma unroll
-      for (int u = 0; u < TU; ++u) fma4(acc[u], ph[u], *reinterpret_cast<const float4*>(&ms.U0c[u][h][4 * s]));
+      float c1[4] = {0.f, 0.f, 0.f, 0.f}, c0[4] = {0.f, 0.f, 0.f, 0.f};
+      hmma<FMT>(c1, U.ku[h], sf[h].x, sf[h].y);
+      hmma<FMT>(c0, U.qu[h], sf[h].z, sf[h].w);
+      wpk[0][h] = pack2<FMT>(__fdividef(1.f, 1.f + __expf(La[h] - c1[0])), __fdividef(1.f, 1.f + __expf(La[h] - c1[2])));
+      wpk[1][h] = pack2<FMT>(__fdividef(1.f, 1.f + __expf(Lb[h] - c1[1])), __fdividef(1.f, 1.f + __expf(Lb[h] - c1[3])));
+      // user row: softmax over [q_u.k_u, q_u.k_b ...] of head h, rows g and g + 8 (the tokens are spread over the quad)
+      const float a0 = v0 ? c0[0] : -INFINITY, a1 = v1 ? c0[1] : -INFINITY, b0 = v0 ? c0[2] : -INFINITY, b1 = v1 ? c0[3] : -INFINITY;
+      float mg = fmaxf(fmaxf(a0, a1), U.s00[0][h]), mh = fmaxf(fmaxf(b0, b1), U.s00[1][h]);
+      mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, 1)); mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, 1));
+      mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, 2)); mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, 2));
+      const float ea0 = __expf(a0 - mg), ea1 = __expf(a1 - mg), eb0 = __expf(b0 - mh), eb1 = __expf(b1 - mh);
+      float sg = ea0 + ea1, sh = eb0 + eb1;
+      sg += __shfl_xor_sync(0xffffffffu, sg, 1); sh += __shfl_xor_sync(0xffffffffu, sh, 1);
+      sg += __shfl_xor_sync(0xffffffffu, sg, 2); sh += __shfl_xor_sync(0xffffffffu, sh, 2);
+      const float e0g = __expf(U.s00[0][h] - mg), e0h = __expf(U.s00[1][h] - mh);
+      const float ig = __fdividef(1.f, sg + e0g), ih = __fdividef(1.f, sh + e0h);
+      x0[h] = pack2<FMT>(e0g * ig, e0h * ih);
+      pa[h >> 1][(h & 1) * 2] = pack2<FMT>(ea0 * ig, ea1 * ig);          // A fragment: K column 8 (h & 1) + token, k-step h >> 1
+      pa[h >> 1][(h & 1) * 2 + 1] = pack2<FMT>(eb0 * ih, eb1 * ih);
     }
 #pragma unroll
-    for (int b = 0; b < ATT_TOKENS; ++b) {
-      float4 ub[NH];
+    for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
-      for (int h = 0; h < NH; ++h) ub[h] = ldg_stream(rec + min(b, nt - 1) * ATT_TOK + ATT_U + h * D + 4 * s);
-#pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        float ph[TU];
-#pragma unroll
-        for (int u = 0; u < TU; ++u) ph[u] = __shfl_sync(0xffffffffu, pw[u >> 2][1 + b], gb | (4 * h) | (u & 3));   // weight 0 for b >= nt
-#pragma unroll
-        for (int u = 0; u < TU; ++u) fma4(acc[u], ph[u], ub[h]);
+      for (int np = 0; np < 4; ++np) {
+        hmma<FMT>(YA[2 * np], pa[kk], uf[kk][np].x, uf[kk][np].y);
+        hmma<FMT>(YA[2 * np + 1], pa[kk], uf[kk][np].z, uf[kk][np].w);
       }
-    }
-    load_tok(0, c, q, nb, Lh);
-#pragma unroll
-    for (int ug = 0; ug < 2; ++ug) {
-      float r[4];
-      ln_rstd4(&acc[4 * ug], lane, r);
-#pragma unroll
-      for (int u4 = 0; u4 < 4; ++u4)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[4 * ug + u4][i] *= r[u4];
-    }
+    attn_wo_pass<FMT>(YA, x0, U, wo, lane);
   }
-  // ---- item tokens a >= 1 (token data of a + 1 is fetched while a is being combined)
-#pragma unroll 1
-  for (int a = 0; a < nt; ++a) {
-    float4 c2, q2, nb2[NH]; float L2;
-    load_tok(min(a + 1, nt - 1), c2, q2, nb2, L2);
+  // ---- item rows: token a's MMAs are issued before the norm / accumulate of the previous row (two accumulator sets)
+  auto bcast = [&](int a, uint32_t (&x)[NH]) {
 #pragma unroll
-    for (int ug = 0; ug < 2; ++ug) {
-      float d[4], y[4][4];
-#pragma unroll
-      for (int u4 = 0; u4 < 4; ++u4) d[u4] = dot4(q, *reinterpret_cast<const float4*>(&ms.ku[4 * ug + u4][4 * s]));
-      const float w = __fdividef(1.f, 1.f + __expf(Lh - quad_scatter4(d, ql)));      // sigmoid(s_a0 - L_ah) of user 4 ug + ql
-#pragma unroll
-      for (int u4 = 0; u4 < 4; ++u4) { y[u4][0] = c.x; y[u4][1] = c.y; y[u4][2] = c.z; y[u4][3] = c.w; }
-#pragma unroll
-      for (int h = 0; h < NH; ++h) {
-        float wh[4];
-#pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) wh[u4] = __shfl_sync(0xffffffffu, w, gb | (4 * h) | u4);
-#pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) {
-          const float4 uv = *reinterpret_cast<const float4*>(&ms.U0c[4 * ug + u4][h][4 * s]);
-          y[u4][0] = fmaf(wh[u4], uv.x - nb[h].x, y[u4][0]); y[u4][1] = fmaf(wh[u4], uv.y - nb[h].y, y[u4][1]);
-          y[u4][2] = fmaf(wh[u4], uv.z - nb[h].z, y[u4][2]); y[u4][3] = fmaf(wh[u4], uv.w - nb[h].w, y[u4][3]);
-        }
-      }
-      float r[4];
-      ln_rstd4(y, lane, r);
-#pragma unroll
-      for (int u4 = 0; u4 < 4; ++u4)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[4 * ug + u4][i] = fmaf(r[u4], y[u4][i], acc[4 * ug + u4][i]);
+    for (int h = 0; h < NH; ++h) x[h] = __shfl_sync(0xffffffffu, wpk[a & 1][h], (lane & ~3) | (a >> 1));
+  };
+  uint32_t x[NH];
+  // token 0 -> YB | norm(YA: user row) ; token 1 -> YA | norm(YB) ; token 2 -> YB | norm(YA) ; ...   (nt >= 3 on this path)
+  bcast(0, x); attn_token<FMT>(YB, x, U, tf, rec, wo, 1, lane);
+  attn_norm_acc<true>(YA, acc);
+  bcast(1, x); attn_token<FMT>(YA, x, U, tf, rec, wo, 2, lane);
+  attn_norm_acc<false>(YB, acc);
+  bcast(2, x); attn_token<FMT>(YB, x, U, tf, rec, wo, nt > 3 ? 3 : -1, lane);
+  attn_norm_acc<false>(YA, acc);
+  if (nt > 3) {
+    bcast(3, x); attn_token<FMT>(YA, x, U, tf, rec, wo, nt > 4 ? 4 : -1, lane);
+    attn_norm_acc<false>(YB, acc);
+    if (nt > 4) {
+      bcast(4, x); attn_token<FMT>(YB, x, U, tf, rec, wo, -1, lane);
+      attn_norm_acc<false>(YA, acc);
+      attn_norm_acc<false>(YB, acc);
+    } else {
+      attn_norm_acc<false>(YA, acc);
     }
-    c = c2; q = q2; Lh = L2;
-#pragma unroll
-    for (int h = 0; h < NH; ++h) nb[h] = nb2[h];
-  }
-  // ---- 16-bit pack into the swizzled A1 rows (row = user * 16 + item; 8 bytes per thread)
-  wait_a1();
-  const int j = 8 * half + j8;
-#pragma unroll
-  for (int u = 0; u < TU; ++u) {
-    uint2 pk;
-    pk.x = pack2<FMT>(acc[u][0], acc[u][1]); pk.y = pack2<FMT>(acc[u][2], acc[u][3]);
-    const int r = u * TI + j;
-    *reinterpret_cast<uint2*>(a1 + (r >> 3) * 1024 + (r & 7) * 128 + (((s >> 1) ^ (r & 7)) << 4) + (s & 1) * 8) = pk;
+  } else {
+    attn_norm_acc<false>(YB, acc);
   }
 }
 
@@ -513,6 +549,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
   constexpr int NT = n_threads<FUS>();
   constexpr bool GATED = (FUS != F_CONCAT);
   constexpr bool ATT = (FUS == F_ATTN);
+  constexpr int TU = tile_users<FUS>(), TI = tile_items<FUS>();
   using MP = Map<FUS>;
   using MiscF = MiscT<FUS>;
   constexpr int QC = MiscF::QC;
@@ -540,7 +577,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
     ms.b4 = ATT ? p.bias_c[H1 + H2 + H3 + H3] : p.bias[H1 + H2 + H3 + H3];
     ms.q_tail[0] = ms.q_tail[1] = 0; ms.q_head[0] = ms.q_head[1] = 0;
     ptx::mbar_init(BAR(BAR_W), 1);
-    ptx::mbar_init(BAR(BAR_A_FULL), ATT ? 16 : 8);        // one arrival per front-end warp of both CTAs
+    ptx::mbar_init(BAR(BAR_A_FULL), 8);                   // one arrival per front-end warp of both CTAs
     ptx::mbar_init(BAR(BAR_A_EMPTY), 1);
     for (int b = 0; b < 4; ++b) {
       ptx::mbar_init(BAR(BAR_D1_FULL0 + b), 1);
@@ -580,41 +617,38 @@ score_fused_kernel(const __grid_constant__ Params p) {
   // units of this pair: w = pair, pair + n_pairs, ...; every role walks the same (unit, tile) sequence;
   // T counts tiles over all units of the pair
 
-  // attention: register budget per warpgroup.  640 threads are launched with 96 registers each and setmaxnreg can
-  // only move registers inside that pool (61 440): the MMA / top-K warpgroup drops to 40, the two front-end
-  // warpgroups take 128, the epilogue warpgroups drop to 88  (2*128*128 + 128*40 + 2*128*88 = 60 416).
-  // (setmaxnreg sits at the top of each warpgroup's branch so that ptxas allocates per role).
-  if (warp < 4 || (ATT && warp >= 16)) {
-    if (ATT) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+  // attention: register budget per warpgroup.  512 threads are launched with 128 registers each and setmaxnreg moves
+  // registers inside that pool (65 536): the MMA / top-K warpgroup drops to 56, the two epilogue warpgroups to 112, the
+  // front-end warpgroup (per-user MMA fragments + two 16 x 64 fp32 accumulator sets per thread) takes 232
+  // (128*232 + 128*56 + 256*112 = 65 536).  setmaxnreg sits at the top of each warpgroup's branch so that ptxas
+  // allocates per role.
+  if (warp < 4) {
+    if (ATT) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     // =============================================================== front end
-    // attention: warpgroup A (warps 0-3) builds the per-unit user constants and the first half of every tile,
-    // warpgroup B (warps 16-19) the second half; named barriers 2 / 3 fence the user constants between units.
-    const bool feB = ATT && warp >= 16;
     const int tid = threadIdx.x & 127;      // 0..127 inside the front-end warpgroup
     const int Mm = p.M;
     int T = 0;
+    AttnUserFrag UF;                        // attention: per-unit user operands of this thread (registers)
     for (int w = pair; w < p.n_units; w += n_pairs) {
-      const Unit un = decode_unit(p, w);
+      const Unit un = decode_unit<TI>(p, w);
       const int64_t ubase = ((int64_t)un.g * 2 + rank) * TU;     // first user ordinal of this CTA's group
       if (!GATED && T > 0) {
         // Pu is read by the layer-1 producers of the previous unit's last tile: wait until they are done with it
         ptx::mbar_wait(BAR(BAR_PI_EMPTY0 + ((T - 1) & 1)), ((T - 1) >> 1) & 1);
       }
-      if (ATT) asm volatile("bar.sync 2, 256;" ::: "memory");      // both warpgroups are done with the previous unit
-      if (!feB) {
       asm volatile("bar.sync 1, 128;" ::: "memory");              // previous unit's readers of eu/lu are done
-      {
-        // attention stages E_u (and v_u) in the A1 tile: wait until the layer-1 MMAs of the previous tile have read it
-        if (ATT && T > 0) ptx::mbar_wait(BAR(BAR_A_EMPTY), (T - 1) & 1);
-        float (*eu_dst)[D] = ATT ? reinterpret_cast<float (*)[D]>(sm + MP::OFF_A1) : ms.eu;
+      if (ATT) {
+        // the per-unit user operands are staged in the A1 tile: wait until the layer-1 MMAs of the previous tile have read it
+        if (T > 0) ptx::mbar_wait(BAR(BAR_A_EMPTY), (T - 1) & 1);
+        attn_user_setup<FMT>(p, reinterpret_cast<float*>(sm + MP::OFF_A1), tid, ubase, UF, p.xc0_scratch + (size_t)blockIdx.x * ATT_XC0_U4);
+      } else {
         const int u = tid >> 4, d4 = (tid & 15) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ubase + u < p.n_users && d4 < p.Dm) v = *reinterpret_cast<const float4*>(p.user_emb + p.user_idx[ubase + u] * p.Dm + d4);
-        *reinterpret_cast<float4*>(&eu_dst[u][d4]) = v;
+        *reinterpret_cast<float4*>(&ms.eu[u][d4]) = v;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (FUS == F_ATTN) {
-        attn_user_setup(p, ms, reinterpret_cast<float*>(sm + MP::OFF_A1), p.user_scratch + blockIdx.x, tid);
       } else if (FUS == F_GATED) {
         if (tid < 64) {                      // user part of the gate logits (layers.py:207 split per SURVEY A4)
           const int u = tid >> 3, m = tid & 7;
@@ -660,9 +694,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
           *reinterpret_cast<float4*>(sm + MP::OFF_PU + u * MP::PU_STRIDE + 16 * tid) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-      if (ATT) asm volatile("bar.sync 3, 256;" ::: "memory");      // user constants of this unit are in place
-      // seen-item cursors: lanes 0..7 of warp 0 walk user u's ascending history with the item sweep
+      // seen-item cursors: lanes 0..TU-1 of warp 0 walk user u's ascending history with the item sweep
       int64_t cur = 0, cend = 0; int32_t nextv = 0x7fffffff;
       if (warp == 0 && lane < TU && p.seen_indptr && ubase + lane < p.n_users) {
         cur = p.seen_indptr[ubase + lane]; cend = p.seen_indptr[ubase + lane + 1];
@@ -675,7 +707,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
       if (!GATED && warp != 0) { T += un.ntiles; continue; }     // concat: warp 0 alone stages the tiles
       for (int t = 0; t < un.ntiles; ++t, ++T) {
         const int64_t row0 = un.row_lo + (int64_t)t * TI;
-        auto write_seen_mask = [&]() {         // lanes 0..7 of warp 0: the 16-bit seen mask of this tile per user
+        auto write_seen_mask = [&]() {         // lanes 0..TU-1 of warp 0: the TI-bit seen mask of this tile per user
           if (warp == 0 && lane < TU) {
             uint32_t mask = 0;
             const int32_t i0 = (int32_t)(p.item_base + row0);
@@ -689,12 +721,25 @@ score_fused_kernel(const __grid_constant__ Params p) {
         };
         if (FUS == F_ATTN) {
           write_seen_mask();
-          {
-            const int half = feB ? 1 : 0;
-            const int64_t row = row0 + 8 * half + (tid >> 4);
+#pragma unroll 1
+          for (int jj = 0; jj < 2; ++jj) {                            // this warp's two items of the tile x the CTA's 16 users
+            const int j = 2 * warp + jj;
+            const int64_t row = row0 + j;
             const int64_t rr = row < un.row_hi ? row : un.row_lo;    // padding rows recompute a valid item (discarded later)
-            attn_half_tile<FMT>(ms, p.user_scratch + blockIdx.x, p.attn_rec + rr * ATT_ITEM, Mm - 1, sm + MP::OFF_A1, half, tid,
-                                lane, [&]() { if (T > 0) ptx::mbar_wait(BAR(BAR_A_EMPTY), (T - 1) & 1); });
+            // the item this warp takes next: its second item of this tile, then the same slot of the next tile
+            const int64_t rn = jj == 0 ? row + 1 : row + TI - 1;
+            float acc[8][4];
+            attn_item_step<FMT>(UF, p.attn_rec + rr * ATT_REC_U4, rn < un.row_hi ? p.attn_rec + rn * ATT_REC_U4 : nullptr, p.wo_frag,
+                                p.xc0_scratch + (size_t)blockIdx.x * ATT_XC0_U4, Mm - 1, lane, acc);
+            if (jj == 0 && T > 0) ptx::mbar_wait(BAR(BAR_A_EMPTY), (T - 1) & 1);   // layer-1 MMAs of the previous tile have read A1
+            // 16-bit pack into the swizzled A1 rows: row = item * 16 + user, user rows g and g + 8 of this lane
+            const int g = lane >> 2, t4 = (lane & 3) * 4;
+            uint8_t* a1 = sm + MP::OFF_A1 + (2 * j) * 1024 + g * 128 + t4;
+#pragma unroll
+            for (int nn = 0; nn < 8; ++nn) {
+              *reinterpret_cast<uint32_t*>(a1 + ((nn ^ g) << 4)) = pack2<FMT>(acc[nn][0], acc[nn][1]);
+              *reinterpret_cast<uint32_t*>(a1 + 1024 + ((nn ^ g) << 4)) = pack2<FMT>(acc[nn][2], acc[nn][3]);
+            }
           }
           ptx::fence_proxy_async();
           __syncwarp();
@@ -773,12 +818,12 @@ score_fused_kernel(const __grid_constant__ Params p) {
       }
     }
   } else if (warp < 8) {
-   if (ATT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+   if (ATT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
    if (warp == 4) {
     // =============================================================== MMA issuer (leader CTA, one thread)
     if (rank == 0 && lane == 0) {
       int NT = 0;
-      for (int w = pair; w < p.n_units; w += n_pairs) NT += decode_unit(p, w).ntiles;
+      for (int w = pair; w < p.n_units; w += n_pairs) NT += decode_unit<TI>(p, w).ntiles;
       const uint64_t dA1 = ptx::smem_desc_sw128(base + MP::OFF_A1);
       const uint64_t dW1 = ptx::smem_desc_sw128(base + MP::OFF_W1);
       const uint64_t dW2 = ptx::smem_desc_sw128(base + MP::OFF_W2);
@@ -854,11 +899,11 @@ score_fused_kernel(const __grid_constant__ Params p) {
     // TK2: warp 5 owns users 0-3 and warp 6 users 4-7, one queue each (see launch_fused for when)
     const int qh = warp - 5;
     constexpr uint32_t QM = (TK2 ? QC / 2 : QC) - 1;      // queue capacities are powers of two
-    const int u_lo = TK2 ? 4 * qh : 0, u_hi = TK2 ? 4 * qh + 4 : TU;
+    const int u_lo = TK2 ? (TU / 2) * qh : 0, u_hi = TK2 ? (TU / 2) * (qh + 1) : TU;
     unsigned long long* const queue = ms.queue + qh * (QC / 2);
     uint32_t head = 0, done_ph = 0;
     for (int w = pair; w < p.n_units; w += n_pairs) {
-      const Unit un = decode_unit(p, w);
+      const Unit un = decode_unit<TI>(p, w);
       if (un.ntiles == 0) continue;
       const int64_t ubase = ((int64_t)un.g * 2 + rank) * TU;
       bool finished = false;
@@ -873,7 +918,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
             *reinterpret_cast<volatile uint32_t*>(&ms.q_head[qh]) = head + 1;
           }
           ++head;
-          const int u = (int)((e >> 28) & 7ull);
+          const int u = (int)((e >> 28) & (unsigned long long)(TU - 1));
           const unsigned long long key = e & 0xFFFFFFFF0FFFFFFFull;
           // sorted (descending) insertion into list[u]: lanes hold slots lane and lane + 32
           unsigned long long* L = ms.list[u];
@@ -927,12 +972,12 @@ score_fused_kernel(const __grid_constant__ Params p) {
    }
   } else {
     // =============================================================== epilogue groups (warps 8-15)
-    if (ATT) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if (ATT) asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
     const int grp = (warp - 8) >> 2;                 // 0: even layer-1 chunks, first half of layer 2, layer 3
     const int q = warp & 3;                          // TMEM lane quarter this warp may touch
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
     const int r = q * 32 + lane;                     // row of the tile this thread owns
-    const int ru = r >> 4, rj = r & 15;              // user slot / item slot of the row
+    const int ru = ATT ? (r & 15) : (r >> 4), rj = ATT ? (r >> 4) : (r & 15);   // user slot / item slot of the row
     uint32_t d1ph = 0, reset_ph = 0;                 // d1ph: phase bits of chunk buffers grp (bit 0) and grp + 2 (bit 1)
     uint32_t h1use0 = 0, h1use1 = 0;                 // concat: uses so far of chunk buffers grp and grp + 2
     int T = 0;
@@ -988,7 +1033,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
         const uint32_t gidx = (uint32_t)(p.item_base + row);
         const unsigned long long e = ((unsigned long long)pxr_ord(y) << 32) | ((unsigned long long)ru << 28) |
                                      (unsigned long long)(IDX_MASK - gidx);
-        const int qh = TK2 ? (ru >> 2) : 0;
+        const int qh = TK2 ? (ru >= TU / 2 ? 1 : 0) : 0;
         constexpr uint32_t qcap = TK2 ? QC / 2 : QC;
         const uint32_t slot = atomicAdd(&ms.q_tail[qh], 1u);
         while (slot - *reinterpret_cast<volatile uint32_t*>(&ms.q_head[qh]) >= qcap) __nanosleep(64);
@@ -1037,7 +1082,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
     };
 
     for (int w = pair; w < p.n_units; w += n_pairs) {
-      const Unit un = decode_unit(p, w);
+      const Unit un = decode_unit<TI>(p, w);
       const int64_t ubase = ((int64_t)un.g * 2 + rank) * TU;
       for (int t = 0; t < un.ntiles; ++t, ++T) {
         // One rolled loop over this group's four layer-1 chunks (the body must stay resident in the instruction
@@ -1159,21 +1204,32 @@ __global__ void __launch_bounds__(PXR_SIMT_THREADS) item_pi_kernel(const float* 
 }
 
 
-// attention: per-item record (once per catalogue shard).  4 items per block, thread = (item, d).  Record layout per
-// item token a (ATT_TOK floats): C[64] | Nbar[4][64] | U[4][64] | q[64] / sqrt(dh) | k[64] / sqrt(dh) | L[4] | pad,
-// with C, Nbar_h and U_h each centred over d (definitions above attn_half_tile).
-__global__ void __launch_bounds__(256) item_attn_kernel(const float* __restrict__ feats, const float* __restrict__ in_wt,
-                                                        const float* __restrict__ in_b, const float* __restrict__ out_wt,
-                                                        const float* __restrict__ out_b, int M, int64_t n_rows,
-                                                        float* __restrict__ rec) {
-  __shared__ float x[4][ATT_TOKENS][D], q[4][ATT_TOKENS][D], k[4][ATT_TOKENS][D], v[4][ATT_TOKENS][D];
-  __shared__ float Ssc[4][ATT_TOKENS][NH][ATT_TOKENS], P[4][ATT_TOKENS][NH][ATT_TOKENS], Lse[4][ATT_TOKENS][NH];
-  __shared__ float red[4][2][2 * NH + 1];
-  const int it = threadIdx.x >> 6, d = threadIdx.x & 63, nt = M - 1;
-  const int64_t row = (int64_t)blockIdx.x * 4 + it;
-  const bool valid = row < n_rows;
-  const float scale = rsqrtf((float)DH);
-  for (int b = 0; b < ATT_TOKENS; ++b) x[it][b][d] = (valid && b < nt) ? feats[(row * nt + b) * D + d] : 0.f;
+// attention: per-item record (once per catalogue shard): everything of the attention layer that involves item tokens
+// only, stored as the 16-bit B fragments of the front end's register MMAs in lane order (layout: REC_* above,
+// definitions above attn_item_step).  One item per 64-thread block, thread = d.
+//   wc : [64][64] fp32 centred out_proj weight, Wc[d][j] = W_o[d][j] - mean_d' W_o[d'][j]
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, int fmt) {
+  return (uint32_t)to16(lo, fmt) | ((uint32_t)to16(hi, fmt) << 16);
+}
+__device__ __forceinline__ float from16(uint16_t v, int fmt) {
+  if (fmt == FMT_BF16) return __uint_as_float((uint32_t)v << 16);
+  return __half2float(*reinterpret_cast<const __half*>(&v));
+}
+__device__ __forceinline__ float lo_part(float x, int fmt) { return x - from16(to16(x, fmt), fmt); }   // x = hi + lo, both 16-bit
+
+__global__ void __launch_bounds__(64) item_attn_kernel(const float* __restrict__ feats, const float* __restrict__ in_wt,
+                                                       const float* __restrict__ in_b, const float* __restrict__ wc,
+                                                       const float* __restrict__ out_b, int M, int64_t n_rows, int fmt,
+                                                       uint4* __restrict__ rec) {
+  __shared__ float x[ATT_TOKENS][D], q[ATT_TOKENS][D], k[ATT_TOKENS][D], v[ATT_TOKENS][D];
+  __shared__ float Ssc[ATT_TOKENS][NH][ATT_TOKENS], P[ATT_TOKENS][NH][ATT_TOKENS], Lse[ATT_TOKENS][NH];
+  __shared__ float vbar[ATT_TOKENS][D];                       // [a][16 h + e] = sum_b softmax_b(s_ab,h) v_b,h[e]
+  __shared__ float Nc[ATT_TOKENS][NH][D], Uc[ATT_TOKENS][NH][D], xc[ATT_TOKENS][D];
+  __shared__ float red[2];
+  const int d = threadIdx.x, nt = M - 1, lane = d & 31;
+  const int64_t row = blockIdx.x;
+  if (row >= n_rows) return;
+  for (int b = 0; b < ATT_TOKENS; ++b) x[b][d] = b < nt ? feats[(row * nt + b) * D + d] : 0.f;
   __syncthreads();
   {
     float aq[ATT_TOKENS], ak[ATT_TOKENS], av[ATT_TOKENS];
@@ -1182,83 +1238,132 @@ __global__ void __launch_bounds__(256) item_attn_kernel(const float* __restrict_
       const float wq = in_wt[kk * 3 * D + d], wk = in_wt[kk * 3 * D + D + d], wv = in_wt[kk * 3 * D + 2 * D + d];
 #pragma unroll
       for (int b = 0; b < ATT_TOKENS; ++b) {
-        const float xv = x[it][b][kk];
+        const float xv = x[b][kk];
         aq[b] = fmaf(wq, xv, aq[b]); ak[b] = fmaf(wk, xv, ak[b]); av[b] = fmaf(wv, xv, av[b]);
       }
     }
-    for (int b = 0; b < ATT_TOKENS; ++b) { q[it][b][d] = aq[b] * scale; k[it][b][d] = ak[b]; v[it][b][d] = av[b]; }
+    for (int b = 0; b < ATT_TOKENS; ++b) { q[b][d] = aq[b] * 0.25f; k[b][d] = ak[b]; v[b][d] = av[b]; }   // q / sqrt(dh)
   }
   __syncthreads();
-  float U[ATT_TOKENS][NH];
-#pragma unroll
-  for (int h = 0; h < NH; ++h) {
-#pragma unroll
-    for (int b = 0; b < ATT_TOKENS; ++b) U[b][h] = 0.f;
-    for (int e = 0; e < DH; ++e) {
-      const float w = out_wt[(h * DH + e) * D + d];
-#pragma unroll
-      for (int b = 0; b < ATT_TOKENS; ++b) U[b][h] = fmaf(w, v[it][b][h * DH + e], U[b][h]);
-    }
-  }
   for (int i = d; i < ATT_TOKENS * ATT_TOKENS * NH; i += 64) {     // item-item scores (already scaled through q)
     const int a = i / (ATT_TOKENS * NH), b = (i / NH) % ATT_TOKENS, h = i % NH;
     float acc = 0.f;
-    for (int e = 0; e < DH; ++e) acc = fmaf(q[it][a][h * DH + e], k[it][b][h * DH + e], acc);
-    Ssc[it][a][h][b] = acc;
+    for (int e = 0; e < DH; ++e) acc = fmaf(q[a][h * DH + e], k[b][h * DH + e], acc);
+    Ssc[a][h][b] = acc;
   }
   __syncthreads();
   if (d < ATT_TOKENS * NH) {
     const int a = d >> 2, h = d & 3;
     float m = -INFINITY;
-    for (int b = 0; b < nt; ++b) m = fmaxf(m, Ssc[it][a][h][b]);
+    for (int b = 0; b < nt; ++b) m = fmaxf(m, Ssc[a][h][b]);
     float sum = 0.f;
-    for (int b = 0; b < nt; ++b) { const float e = expf(Ssc[it][a][h][b] - m); P[it][a][h][b] = e; sum += e; }
-    for (int b = 0; b < ATT_TOKENS; ++b) P[it][a][h][b] = b < nt ? P[it][a][h][b] / sum : 0.f;
-    Lse[it][a][h] = nt > 0 ? m + logf(sum) : 0.f;
+    for (int b = 0; b < nt; ++b) { const float e = expf(Ssc[a][h][b] - m); P[a][h][b] = e; sum += e; }
+    for (int b = 0; b < ATT_TOKENS; ++b) P[a][h][b] = b < nt ? P[a][h][b] / sum : 0.f;
+    Lse[a][h] = (nt > 0 && a < nt) ? m + logf(sum) : 0.f;
   }
   __syncthreads();
-  float* out = rec + row * ATT_ITEM;
-  const int warp2 = d >> 5, lane = threadIdx.x & 31;
-#pragma unroll 1
-  for (int a = 0; a < nt; ++a) {
-    // vals: Nbar_h (4), U_h (4), C -> centre each over the item's 64 threads (two warps)
-    float vals[2 * NH + 1];
-    float c = x[it][a][d] + out_b[d];
+  {
+    const int h = d >> 4;
+    for (int a = 0; a < ATT_TOKENS; ++a) {
+      float acc = 0.f;
+      for (int b = 0; b < nt; ++b) acc = fmaf(P[a][h][b], v[b][d], acc);
+      vbar[a][d] = acc;
+    }
+  }
+  // xc_a = (x_a + b_o) centred over d
+  for (int a = 0; a < ATT_TOKENS; ++a) {
+    const float val = x[a][d] + out_b[d];
+    float part = val;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncthreads();
+    if (lane == 0) red[d >> 5] = part;
+    __syncthreads();
+    xc[a][d] = a < nt ? val - (red[0] + red[1]) * (1.f / D) : 0.f;
+  }
+  __syncthreads();
+  for (int a = 0; a < ATT_TOKENS; ++a)
 #pragma unroll
     for (int h = 0; h < NH; ++h) {
-      float nb = 0.f;
-#pragma unroll
-      for (int b = 0; b < ATT_TOKENS; ++b) nb = fmaf(P[it][a][h][b], U[b][h], nb);
-      vals[h] = nb; c += nb;
+      float n_ = 0.f, u_ = 0.f;
+      for (int e = 0; e < DH; ++e) {
+        const float w = wc[d * D + h * DH + e];
+        n_ = fmaf(w, vbar[a][h * DH + e], n_);
+        u_ = fmaf(w, v[a][h * DH + e], u_);
+      }
+      Nc[a][h][d] = a < nt ? n_ : 0.f;
+      Uc[a][h][d] = a < nt ? u_ : 0.f;
     }
+  __syncthreads();
+  uint4* out = rec + row * ATT_REC_U4;
+  for (int o = d; o < ATT_REC_U4; o += 64) {
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (o < REC_L) {                                              // scores: [h][lane] = (q b0, q b1, k b0, k b1), n = token g
+      const int h = o >> 5, ln = o & 31, g = ln >> 2, t = ln & 3, c = h * DH + 2 * t;
+      if (g < nt) {
+        w.x = pack16(q[g][c], q[g][c + 1], fmt); w.y = pack16(q[g][c + 8], q[g][c + 9], fmt);
+        w.z = pack16(k[g][c], k[g][c + 1], fmt); w.w = pack16(k[g][c + 8], k[g][c + 9], fmt);
+      }
+    } else if (o < REC_T) {                                       // L: [t][2 tokens] x 4 heads, fp32
+      const int i = o - REC_L, a = i;                             // token a = 2 t + tok = i
+      if (a < ATT_TOKENS) w = make_uint4(__float_as_uint(Lse[a][0]), __float_as_uint(Lse[a][1]), __float_as_uint(Lse[a][2]), __float_as_uint(Lse[a][3]));
+    } else if (o < REC_U) {                                       // token tails: [a][np][lane] = (b0, b1 of n-tile 2 np; of 2 np + 1)
+      const int i = o - REC_T, a = i >> 7, np = (i >> 5) & 3, ln = i & 31, g = ln >> 2, t = ln & 3;
+      uint32_t r[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int h = 0; h < NH; ++h) {
-      float uah = 0.f;
+      for (int e = 0; e < 2; ++e) {
+        const int n = 8 * (2 * np + e) + g;
+        if (t < 2) {                                              // K rows 2t, 2t+1: Nc_h hi; rows 8+2t, 9+2t: Nc_h lo
+          r[2 * e] = pack16(Nc[a][2 * t][n], Nc[a][2 * t + 1][n], fmt);
+          r[2 * e + 1] = pack16(lo_part(Nc[a][2 * t][n], fmt), lo_part(Nc[a][2 * t + 1][n], fmt), fmt);
+        } else if (t == 2) {                                      // K rows 4, 5: xc hi, xc lo
+          r[2 * e] = pack16(xc[a][n], lo_part(xc[a][n], fmt), fmt);
+        }
+      }
+      w = make_uint4(r[0], r[1], r[2], r[3]);
+    } else {                                                      // user-row item values: [kk][np][lane], K row 8 (h & 1) + token
+      const int i = o - REC_U, kk = i >> 7, np = (i >> 5) & 3, ln = i & 31, g = ln >> 2, t = ln & 3;
+      uint32_t r[4] = {0u, 0u, 0u, 0u};
+      const int b0 = 2 * t, b1 = 2 * t + 1;
 #pragma unroll
-      for (int b = 0; b < ATT_TOKENS; ++b) uah = (b == a) ? U[b][h] : uah;
-      vals[NH + h] = uah;
+      for (int e = 0; e < 2; ++e) {
+        const int n = 8 * (2 * np + e) + g;
+        const float u00 = b0 < ATT_TOKENS ? Uc[b0][2 * kk][n] : 0.f, u01 = b1 < ATT_TOKENS ? Uc[b1][2 * kk][n] : 0.f;
+        const float u10 = b0 < ATT_TOKENS ? Uc[b0][2 * kk + 1][n] : 0.f, u11 = b1 < ATT_TOKENS ? Uc[b1][2 * kk + 1][n] : 0.f;
+        r[2 * e] = pack16(u00, u01, fmt);                          // head 2 kk:     K rows 2t, 2t + 1
+        r[2 * e + 1] = pack16(u10, u11, fmt);                      // head 2 kk + 1: K rows 8 + 2t, 9 + 2t
+      }
+      w = make_uint4(r[0], r[1], r[2], r[3]);
     }
-    vals[2 * NH] = c;
+    out[o] = w;
+  }
+}
+
+// attention: centred out_proj weight Wc = (I - 11^T / D) W_o as fp32 [d][j], and as the B fragments of Y = A Wc^T
+// (B[k = j][n = d]) in lane order: [4 k-steps][4 n-tile pairs][32 lanes] x 16 B
+__global__ void attn_wc_kernel(const float* __restrict__ out_w, float* __restrict__ wc, uint4* __restrict__ frag, int fmt) {
+  __shared__ float w[D][D + 1];
+  const int tid = threadIdx.x;                                   // 256 threads
+  for (int i = tid; i < D * D; i += blockDim.x) w[i / D][i % D] = out_w[i];
+  __syncthreads();
+  if (tid < D) {                                                  // column j = tid: subtract its mean over d
+    float m = 0.f;
+    for (int dd = 0; dd < D; ++dd) m += w[dd][tid];
+    m *= (1.f / D);
+    for (int dd = 0; dd < D; ++dd) w[dd][tid] -= m;
+  }
+  __syncthreads();
+  for (int i = tid; i < D * D; i += blockDim.x) wc[i] = w[i / D][i % D];
+  for (int o = tid; o < 4 * 4 * 32; o += blockDim.x) {
+    const int kk = o >> 7, np = (o >> 5) & 3, ln = o & 31, g = ln >> 2, t = ln & 3, j = 16 * kk + 2 * t;
+    uint32_t r[4];
 #pragma unroll
-    for (int i = 0; i < 2 * NH + 1; ++i) {
-      float part = vals[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if (lane == 0) red[it][warp2][i] = part;
+    for (int e = 0; e < 2; ++e) {
+      const int n = 8 * (2 * np + e) + g;
+      r[2 * e] = pack16(w[n][j], w[n][j + 1], fmt);
+      r[2 * e + 1] = pack16(w[n][j + 8], w[n][j + 9], fmt);
     }
-    __syncthreads();
-    if (valid) {
-      float* tr = out + a * ATT_TOK;
-#pragma unroll
-      for (int i = 0; i < 2 * NH + 1; ++i) vals[i] -= (red[it][0][i] + red[it][1][i]) * (1.f / D);
-      tr[ATT_C + d] = vals[2 * NH];
-#pragma unroll
-      for (int h = 0; h < NH; ++h) { tr[ATT_NB + h * D + d] = vals[h]; tr[ATT_U + h * D + d] = vals[NH + h]; }
-      tr[ATT_Q + d] = q[it][a][d];
-      tr[ATT_K + d] = k[it][a][d] * scale;
-      if (d < NH) tr[ATT_L + d] = Lse[it][a][d];
-    }
-    __syncthreads();
+    frag[o] = make_uint4(r[0], r[1], r[2], r[3]);
   }
 }
 
@@ -1274,10 +1379,12 @@ __global__ void attn_fold_ln_kernel(const float* __restrict__ w1, const float* _
   if (n < D) s1_out[n] = ln_w[n] / (float)M;
 }
 
-struct FastWeights {       // lives in h->fast_w; attention: followed by one UserAttn per SM
+struct FastWeights {       // lives in h->fast_w; attention: followed by one xc_0 scratch (ATT_XC0_U4 x 16 B) per SM
   uint8_t wimg[2 * Map<F_GATED>::WIMG];
   float bias[H1 + H2 + H3 + H3 + 4];
   float s1[D];             // attention: ln_w / M, the per-input scale folded into the layer-1 image
+  float wc[D * D];         // attention: centred out_proj weight (fp32), for the per-item records
+  uint4 wo_frag[4 * 4 * 32];   // attention: its 16-bit B fragments for the front end's register MMAs
 };
 
 template <int FUS, int FMT, bool TK2>
@@ -1329,7 +1436,7 @@ bool pxr_tc_can_run(const pxr_handle* h, int32_t k) {
 
 size_t pxr_tc_weight_bytes(const pxr_handle* h) {
   return pxr_align_up(sizeof(tc::FastWeights), 256) +
-         (h->cfg.fusion == PXR_FUSION_ATTENTION ? (size_t)h->n_sm * sizeof(tc::UserAttn) : 0);
+         (h->cfg.fusion == PXR_FUSION_ATTENTION ? (size_t)h->n_sm * tc::ATT_XC0_U4 * sizeof(uint4) : 0);
 }
 
 static int tc_fmt(const pxr_handle* h) { return h->cfg.precision == PXR_PRECISION_FP16 ? tc::FMT_FP16 : tc::FMT_BF16; }
@@ -1340,9 +1447,10 @@ int pxr_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
   const bool gated = h->cfg.fusion != PXR_FUSION_CONCAT;    // layer 1 on the tensor pipe
   const bool attn = h->cfg.fusion == PXR_FUSION_ATTENTION;
   float* b = fw->bias;
-  if (attn) {     // LayerNorm affine folded into layer 1 (see attn_half_tile)
+  if (attn) {     // LayerNorm affine folded into layer 1 (see attn_item_step); centred out_proj weight and its MMA fragments
     tc::attn_fold_ln_kernel<<<(tc::H1 + 127) / 128, 128, 0, st>>>(h->mlp[0].w, h->mlp[0].b, h->ln_w, h->ln_b, h->M, b, fw->s1);
-    h->launches++;
+    tc::attn_wc_kernel<<<1, 256, 0, st>>>(h->attn_out.w, fw->wc, fw->wo_frag, tc_fmt(h));
+    h->launches += 2;
   } else {
     PXR_CUDA(h, cudaMemcpyAsync(b, h->mlp[0].b, sizeof(float) * tc::H1, cudaMemcpyDeviceToDevice, st));
   }
@@ -1364,7 +1472,7 @@ int pxr_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
 size_t pxr_tc_item_bytes(const pxr_handle* h, int64_t n_rows) {
   const size_t rows = (size_t)((n_rows + 31) / 32 * 32);
   if (h->cfg.fusion == PXR_FUSION_GATED) return pxr_align_up(rows * 8 * sizeof(float), 256);
-  if (h->cfg.fusion == PXR_FUSION_ATTENTION) return pxr_align_up(rows * tc::ATT_ITEM * sizeof(float), 256);
+  if (h->cfg.fusion == PXR_FUSION_ATTENTION) return pxr_align_up(rows * tc::ATT_REC_U4 * sizeof(uint4), 256);
   return pxr_align_up(rows * tc::H1 * sizeof(uint16_t), 256);
 }
 
@@ -1377,8 +1485,9 @@ int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t s
     tc::item_logit_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(h->item_feats, h->gate.w, h->gate.b, h->M,
                                                                                      n_rows, (float*)ws);
   } else if (h->cfg.fusion == PXR_FUSION_ATTENTION) {
-    tc::item_attn_kernel<<<(unsigned)((n_rows + 3) / 4), 256, 0, st>>>(h->item_feats, h->attn_in.wt, h->attn_in.b, h->attn_out.wt,
-                                                                       h->attn_out.b, h->M, n_rows, (float*)ws);
+    tc::item_attn_kernel<<<(unsigned)n_rows, 64, 0, st>>>(h->item_feats, h->attn_in.wt, h->attn_in.b,
+                                                          reinterpret_cast<tc::FastWeights*>(h->fast_w)->wc, h->attn_out.b, h->M,
+                                                          n_rows, tc_fmt(h), (uint4*)ws);
   } else if (h->tc_items_img[2] && h->path == PXR_PATH_TCGEN05) {
     return pxr_launch_item_pi_tc(h, n_rows, (uint16_t*)ws, tc_fmt(h), st);      // 3xTF32 GEMM on the tensor pipe
   } else {
@@ -1402,8 +1511,11 @@ struct TcPlan { int n_groups, S, rows_per_split, n_units, n_pairs; };
 static TcPlan tc_plan(const pxr_handle* h, int64_t n_users) {
   TcPlan pl;
   const int max_pairs = h->n_sm / 2;
-  pl.n_groups = (int)((n_users + 2 * tc::TU - 1) / (2 * tc::TU));
-  const int64_t max_tiles = (h->n_rows + tc::TI - 1) / tc::TI;
+  const bool att = h->cfg.fusion == PXR_FUSION_ATTENTION;
+  const int TU = att ? tc::tile_users<tc::F_ATTN>() : tc::tile_users<tc::F_GATED>();
+  const int TI = att ? tc::tile_items<tc::F_ATTN>() : tc::tile_items<tc::F_GATED>();
+  pl.n_groups = (int)((n_users + 2 * TU - 1) / (2 * TU));
+  const int64_t max_tiles = (h->n_rows + TI - 1) / TI;
   // split the item range so that the (equal-cost) units fill the CTA pairs evenly: pick the smallest S whose
   // last scheduling round is at least 97 % full (or the best one seen), capped by K4's merge width
   int best_s = 1; double best_eff = 0.0;
@@ -1416,7 +1528,7 @@ static TcPlan tc_plan(const pxr_handle* h, int64_t n_users) {
     if (eff >= 0.97) break;
   }
   int64_t rps = (h->n_rows + best_s - 1) / best_s;
-  rps = (rps + tc::TI - 1) / tc::TI * tc::TI;
+  rps = (rps + 15) / 16 * 16;
   pl.rows_per_split = (int)rps;
   pl.S = (int)((h->n_rows + rps - 1) / rps);
   pl.n_units = pl.n_groups * pl.S;
@@ -1450,10 +1562,11 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
   p.item_logit = gated ? (const float*)h->item_fast : nullptr;
   p.item_pi = (gated || attn) ? nullptr : (const uint16_t*)h->item_fast;
   if (attn) {
-    p.attn_rec = (const float*)h->item_fast;
+    p.attn_rec = (const uint4*)h->item_fast;
+    p.wo_frag = fw->wo_frag;
+    p.xc0_scratch = reinterpret_cast<uint4*>((char*)h->fast_w + pxr_align_up(sizeof(tc::FastWeights), 256));
     p.attn_in_wt = h->attn_in.wt; p.attn_in_b = h->attn_in.b; p.attn_out_wt = h->attn_out.wt; p.attn_out_b = h->attn_out.b;
     p.ln_w = h->ln_w; p.ln_b = h->ln_b;
-    p.user_scratch = reinterpret_cast<tc::UserAttn*>((char*)h->fast_w + pxr_align_up(sizeof(tc::FastWeights), 256));
     memcpy(p.bias_c, h->tc_bias_host, sizeof(float) * (tc::H1 + tc::H2 + 2 * tc::H3 + 1));
   }
   p.w1u_t = h->mlp[0].wt;                   // [k][512]: rows 0..63 are the user columns of W1

@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <climits>
 
+#include <stdlib.h>
+
 #include "pxr_common.cuh"
 
 // ===========================================================================
@@ -312,7 +314,12 @@ static size_t score_smem(const pxr_handle* h, int rows) {
 int pxr_simt_smem_rows(const pxr_handle* h, bool items_kernel) {
   if (items_kernel) { int a, b; size_t s; return items_rows_for(h, &a, &b, &s); }
   const int cands[4] = {32, 16, 8, 4};
-  for (int i = 0; i < 4; ++i) if (score_smem(h, cands[i]) <= (size_t)h->max_smem_optin - 1024) return cands[i];
+  static int forced = -1;                                   // PXR_SIMT_ROWS=16|8|4: experiments with more resident blocks per SM
+  if (forced < 0) { const char* e = getenv("PXR_SIMT_ROWS"); forced = e ? atoi(e) : 0; }
+  for (int i = 0; i < 4; ++i) {
+    if (forced && cands[i] > forced) continue;
+    if (score_smem(h, cands[i]) <= (size_t)h->max_smem_optin - 1024) return cands[i];
+  }
   return 0;
 }
 

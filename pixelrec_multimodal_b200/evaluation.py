@@ -114,8 +114,8 @@ def novelty_tables(interactions_items: np.ndarray, n_hist_users: int, n_items: i
 def beyond_accuracy_metrics(topk_idx: torch.Tensor, si: np.ndarray, iif: np.ndarray, n_pop: int,
                             hist_indptr=None, hist_idx=None) -> Dict[str, float]:
     """Novelty / coverage / personalization over the ranked lists on the GPU (``pxr_novelty_metrics``), keys and
-    aggregation of ``TopKRetrievalEvaluator.evaluate`` (tasks.py:674-714).  ``avg_intra_list_similarity`` is not
-    produced: the reference's embedding collection for it raises ``NameError`` (tasks.py:478) and yields no value."""
+    aggregation of ``TopKRetrievalEvaluator.evaluate`` (tasks.py:674-714).  (``avg_intra_list_similarity`` and the Gini
+    coefficient are separate kernels: ``intra_list_similarity`` / ``gini_coefficient`` below.)"""
     import ctypes as C
     from . import _lib
     from .engine import _ptr, _stream
@@ -144,6 +144,58 @@ def beyond_accuracy_metrics(topk_idx: torch.Tensor, si: np.ndarray, iif: np.ndar
     return {"avg_self_information": m(s_si), "avg_iif": m(s_iif),
             "avg_catalog_coverage": float(s_uniq / n_pop / n_ne) if (n_ne and n_pop) else 0.0,
             "avg_personalization": float(pers), "avg_personalized_novelty": m(s_pn)}
+
+
+def gini_coefficient(topk_idx: torch.Tensor, n_items: int, include_zero: bool = False) -> float:
+    """Gini coefficient of the per-item recommendation counts of the ranked lists on the GPU (``pxr_gini``):
+    ``AdvancedMetrics.calculate_gini_coefficient`` (src/evaluation/advanced_metrics.py:72-105) of
+    {item: number of lists holding it}; ``include_zero`` puts the never-recommended items into the distribution."""
+    import ctypes as C
+    from . import _lib
+    from .engine import _ptr, _stream
+    lib = _lib.load()
+    dev = topk_idx.device
+    topk_idx = topk_idx.to(torch.int32).contiguous()
+    n, k = topk_idx.shape
+    nbytes = int(lib.pxr_gini_bytes(n, int(n_items)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.empty(3, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.pxr_gini(_ptr(topk_idx), k, n, int(n_items), int(bool(include_zero)), _ptr(out), _ptr(ws), nbytes, _stream())
+    if rc != 0:
+        raise _lib.PxrError(f"pxr_gini failed ({rc})")
+    return float(out[0].item())
+
+
+def intra_list_similarity(topk_idx: torch.Tensor, engine=None, embeddings: Optional[torch.Tensor] = None, item_base: int = 0) -> float:
+    """Mean over users of the intra-list similarity (``NoveltyMetrics.calculate_diversity``,
+    src/evaluation/novelty.py:295-340, averaged as in tasks.py:695-701) on the GPU (``pxr_intra_list_similarity``).
+    Embeddings: a caller-provided (n_items, dim) fp32 table, or -- ``engine`` given -- the item records already
+    resident for scoring (the projected item-side modality vectors)."""
+    import ctypes as C
+    from . import _lib
+    from .engine import _ptr, _stream
+    lib = _lib.load()
+    dev = topk_idx.device
+    topk_idx = topk_idx.to(torch.int32).contiguous()
+    n, k = topk_idx.shape
+    if embeddings is not None:
+        emb = embeddings.to(device=dev, dtype=torch.float32).contiguous()
+        n_rows, dim = int(emb.shape[0]), int(emb.shape[1])
+    elif engine is not None:
+        emb, n_rows, dim, item_base = None, int(engine.n_rows), 0, 0
+    else:
+        raise ValueError("intra_list_similarity needs an engine (resident item records) or an embedding table")
+    nbytes = int(lib.pxr_ils_bytes(n, n_rows))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.empty(2, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.pxr_intra_list_similarity(engine._h if engine is not None else None, _ptr(topk_idx), k, n, _ptr(emb), n_rows, dim,
+                                           int(item_base), _ptr(out), _ptr(ws), nbytes, _stream())
+    if rc != 0:
+        raise _lib.PxrError(f"pxr_intra_list_similarity failed ({rc})")
+    s, c = out.cpu().tolist()
+    return float(s / c) if c else 0.0
 
 
 # ----------------------------------------------------------------------------- popularity-biased candidate sampling
@@ -289,7 +341,12 @@ class FullCatalogueEvaluator:
         lens = ip[self.users + 1] - ip[self.users]
         sub_ip = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
         sub_ix = np.concatenate([ix[ip[u]:ip[u + 1]] for u in self.users]).astype(np.int32) if len(self.users) and sub_ip[-1] else np.zeros(1, np.int32)
-        return beyond_accuracy_metrics(topk_idx[:, :self.top_k], si, iif, n_pop, sub_ip, sub_ix)
+        out = beyond_accuracy_metrics(topk_idx[:, :self.top_k], si, iif, n_pop, sub_ip, sub_ix)
+        lists = topk_idx[:, :self.top_k].contiguous()
+        out["gini_coefficient"] = gini_coefficient(lists, r.n_items)                    # advanced_metrics.py:72-105
+        if r.item_lo == 0 and r.item_hi == r.n_items:                                  # needs every record on this rank
+            out["avg_intra_list_similarity"] = intra_list_similarity(lists, engine=r.engine())   # novelty.py:295-340, tasks.py:695-701
+        return out
 
     def _evaluate_sharded(self, kmax: int):
         """Item-sharded ranks in lock step; returns (scores, idx) of all users (every rank holds the merged lists) and

@@ -4,9 +4,17 @@ Items [0, NI) are split into ``world`` contiguous ranges (contiguous so that
 "lower global index wins ties" survives concatenating shards in rank order).
 Each rank scores its shard for the same user block (``pxr_score_topk``), the
 per-shard top-K lists (fp32 score, int32 global index: 8*K bytes per user) are
-exchanged with ONE all-gather, and every rank merges them (``pxr_merge_topk``).
-No other communication is on the data path; metric sums need no collective
-because every rank ends up with the full lists.
+exchanged with ONE collective and merged (``pxr_merge_topk``).  Two forms:
+
+  * all-gather (``allgather_topk*``): every rank ends up with the merged lists of
+    the whole block (what the evaluators use: metric sums then need no list
+    traffic);
+  * owned exchange (``exchange_owned_*``, an all-to-all): rank r receives only
+    the lists of ITS 1/world slice of the block's users and merges those --
+    reduce-scatter ownership: 1/world of the traffic and
+    of the merge work per rank, the merged block stays distributed over the ranks.
+
+No other communication is on the data path.
 """
 from __future__ import annotations
 
@@ -55,6 +63,40 @@ def allgather_topk_finish(handle) -> Tuple[torch.Tensor, torch.Tensor]:
     return out[..., 0].contiguous().view(torch.float32), out[..., 1].contiguous()
 
 
+def owned_slice(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Users [lo, hi) of an n-user block that rank ``rank`` owns after ``exchange_owned_*``."""
+    per = (n + world - 1) // world
+    return min(n, rank * per), min(n, (rank + 1) * per)
+
+
+def exchange_owned_start(scores: torch.Tensor, idx: torch.Tensor, group=None):
+    """Start ONE asynchronous all-to-all of the local per-shard lists: rank r receives, from every rank, the lists of
+    the users it owns (``owned_slice``).  Same packed (score bits, index) int32 rows as ``allgather_topk_start``; the
+    block is padded to a multiple of ``world`` users with empty lists."""
+    world = dist.get_world_size(group)
+    n, k = scores.shape
+    per = (n + world - 1) // world
+    local = torch.empty((world * per, k, 2), dtype=torch.int32, device=scores.device)
+    local[:n, :, 0] = scores.contiguous().view(torch.int32)
+    local[:n, :, 1] = idx.to(torch.int32)
+    if world * per > n:
+        local[n:, :, 0] = torch.tensor(float("-inf"), dtype=torch.float32).view(torch.int32).item()
+        local[n:, :, 1] = -1
+    out = torch.empty((world * per, k, 2), dtype=torch.int32, device=scores.device)
+    work = dist.all_to_all_single(out, local, group=group, async_op=True)
+    return work, out, (world, per, k, n), local
+
+
+def exchange_owned_finish(handle, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Wait for a started owned exchange: (world, m, K) fp32 scores and int32 indices of this rank's m owned users,
+    stacked in shard (rank) order, ready for ``pxr_merge_topk``."""
+    work, out, (world, per, k, n), _local = handle
+    work.wait()
+    lo, hi = owned_slice(n, world, dist.get_rank(group))
+    out = out.view(world, per, k, 2)[:, :hi - lo]
+    return out[..., 0].contiguous().view(torch.float32), out[..., 1].contiguous()
+
+
 class ShardedTopK:
     """Lock-step sharded scoring: ``local_topk(users, k, filter_seen)`` is the
     rank's scorer over its item range (``FastRecommender.recommend_all`` in
@@ -73,6 +115,24 @@ class ShardedTopK:
             return s, i
         all_s, all_i = allgather_topk(s, i, self.group)
         return self.merge(all_s, all_i)
+
+    def recommend_blocks_owned(self, user_blocks, top_k: int, filter_seen: bool = True):
+        """As ``recommend_blocks`` with reduce-scatter ownership: yields, per block, the merged lists of the users THIS
+        rank owns (``owned_slice(len(block), world, rank)``); the exchange of block b again overlaps the scoring of
+        block b + 1.  1/world of the all-gather's traffic and merge work per rank."""
+        sharded = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        pending = None
+        for blk in user_blocks:
+            s, i = self.local_topk(blk, top_k, filter_seen)
+            if not sharded:
+                yield s, i
+                continue
+            handle = exchange_owned_start(s, i, self.group)
+            if pending is not None:
+                yield self.merge(*exchange_owned_finish(pending, self.group))
+            pending = handle
+        if pending is not None:
+            yield self.merge(*exchange_owned_finish(pending, self.group))
 
     def recommend_blocks(self, user_blocks, top_k: int, filter_seen: bool = True):
         """Generator over user blocks with the exchange of block b overlapped with the scoring of block b + 1

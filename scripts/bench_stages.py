@@ -53,7 +53,7 @@ def main():
     out = []
     # ---- K1 + K2: gather + projections -> item records (the fast-path extras of the fusion type are part of the stage)
     ms = timed(lambda: e.precompute_items(m.item_embedding.weight.detach(), feats["tag_idx"], feats["vis"], feats["txt"], feats["num"]), 3, flush)
-    extra = {"gated": 8 * 4, "concatenate": 512 * 2, "attention": 3600 * 4}[args.fusion] if e.active_path == "tcgen05" else 0
+    extra = {"gated": 8 * 4, "concatenate": 512 * 2, "attention": 1032 * 16}[args.fusion] if e.active_path == "tcgen05" else 0
     b_item = 4 * (2 * D + Dv + Dl + F) + 8 + 4 * (M - 1) * D + extra      # read features/embeddings/tag index + write record
     out.append(dict(stage="K1+K2 item precompute", fusion=args.fusion, units=args.items, unit="items", ms=ms,
                     bytes_per_unit=b_item, achieved_gbs=args.items * b_item / ms / 1e6, peak_gbs=peak))
@@ -84,6 +84,16 @@ def main():
     for o in out:
         o["frac"] = o["achieved_gbs"] / o["peak_gbs"]
         print(json.dumps(o), flush=True)
+    # ---- K3r: the fp32 re-score of exact mode = pxr_score_pairs over 64 candidates per user of a 4 096-user block
+    # (CUDA-core fp32 arithmetic: reported as pairs/s and fp32 TFLOP/s, not against the HBM roof)
+    npairs = 4096 * 64
+    uu = torch.arange(4096, device=dev).repeat_interleave(64)
+    ii = torch.randint(0, args.items, (npairs,), device=dev)
+    uemb = m.user_embedding.weight.detach()
+    ms = timed(lambda: e.score_pairs(uemb, uu, ii), 5, flush)
+    flop = 2 * (64 * 512 + 512 * 256 + 256 * 128 + 128) if args.fusion != "concatenate" else 2 * (384 * 512 + 512 * 256 + 256 * 128 + 128)
+    print(json.dumps(dict(stage="K3r fp32 re-score (pxr_score_pairs)", fusion=args.fusion, units=npairs, unit="pairs", ms=ms,
+                          pairs_per_s=npairs / ms * 1e3, fp32_tflops=npairs * flop / ms / 1e9)), flush=True)
 
 
 if __name__ == "__main__":

@@ -164,6 +164,15 @@ outs = list(st.recommend_blocks(blocks, K, False))
 assert len(outs) == 3
 ps, pi = torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
 assert torch.equal(pi, i) and torch.equal(ps, s)
+# reduce-scatter ownership: one all-to-all, every rank merges (and keeps) only its slice of each block
+from pixelrec_multimodal_b200.sharding import owned_slice
+owned = list(st.recommend_blocks_owned(blocks, K, False))
+row = 0
+for blk, (os_, oi_) in zip(blocks, owned):
+    lo_, hi_ = owned_slice(len(blk), world, rank)
+    assert oi_.shape[0] == hi_ - lo_
+    assert torch.equal(oi_, i[row + lo_:row + hi_]) and torch.equal(os_, s[row + lo_:row + hi_]), (rank, row)
+    row += len(blk)
 # sharded evaluation: every rank scores its shard, metric sums of disjoint user slices, one all-reduce
 import pandas as pd
 from pixelrec_multimodal_b200.evaluation import FullCatalogueEvaluator

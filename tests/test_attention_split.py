@@ -1,7 +1,8 @@
 """CPU check of the algebra behind the fused attention front end (csrc/score_tc.cu: item_attn_kernel +
-attn_user_setup + attn_tile): the per-item record / per-user constants / per-pair combination, restated in
-numpy fp64 exactly as the kernels compute them, must reproduce the oracle's attention fusion
-(reference src/models/layers.py:135-164) for every pair."""
+attn_user_setup + attn_item_step): the per-item record / per-user operands / per-pair small GEMMs, restated in
+numpy fp64 exactly as the kernels compute them (oracle.attention_token_sum_mma), must reproduce the oracle's
+attention fusion (reference src/models/layers.py:135-164) for every pair; with the kernel's 16-bit operand
+roundings switched on the result moves by less than the final 16-bit rounding of the fused vector itself."""
 import math
 
 import numpy as np
@@ -14,7 +15,7 @@ from pixelrec_multimodal_b200 import synthetic as syn
 def _split_attention(sd, feats_list, heads):
     """fused vector through the split form of the oracle (exact storage) + the LayerNorm affine and mean"""
     M = len(feats_list)
-    acc = orc.attention_token_sum_split(sd, feats_list, heads)
+    acc = orc.attention_token_sum_mma(sd, feats_list, heads)
     return sd["fusion_layer.norm.bias"].astype(np.float64) + sd["fusion_layer.norm.weight"].astype(np.float64) / M * acc
 
 
@@ -38,8 +39,12 @@ def test_attention_split_matches_oracle(missing):
     got = _split_attention(sdd, feats, spec.num_attention_heads)
     assert len(feats) == (6 if missing is None else 5)
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
-    # token sum == the un-split oracle; fp16 storage of the value blocks moves it by ~1e-3 of its magnitude at most
+    # token sum == the un-split oracle; the 16-bit MMA operands (scores, coefficient x value products, Wc, per-head
+    # out-projected item values; Nc / xc carried as hi + lo) cost less than rounding the token sum itself once
     tok = orc.attention_fusion(sdd, feats, spec.num_attention_heads, np.float64, return_token_sum=True)
-    np.testing.assert_allclose(orc.attention_token_sum_split(sdd, feats, spec.num_attention_heads), tok, rtol=0, atol=1e-11)
-    low = orc.attention_token_sum_split(sdd, feats, spec.num_attention_heads, r16=orc.round_fp16)
-    assert 0 < np.abs(low - tok).max() < 2e-2
+    np.testing.assert_allclose(orc.attention_token_sum_mma(sdd, feats, spec.num_attention_heads), tok, rtol=0, atol=1e-11)
+    for rnd in (orc.round_bf16, orc.round_fp16):
+        low = orc.attention_token_sum_mma(sdd, feats, spec.num_attention_heads, rnd)
+        once = rnd(tok)
+        assert 0 < np.sqrt(np.mean((low - tok) ** 2)) < 0.6 * np.sqrt(np.mean((once - tok) ** 2))
+        assert np.abs(low - tok).max() < np.abs(once - tok).max()

@@ -792,8 +792,11 @@ def test_catalogue_scale_parity(fusion, n_items):
 @pytest.mark.parametrize("fusion,n_items", CATALOGUE_CASES)
 def test_catalogue_scale_metric_deltas(fusion, n_items):
     """Recall / NDCG @10 / @50 of 4 096 users at catalogue scale: raw 16-bit path and exact mode against the fp32
-    SIMT path (the literal forward).  Exact mode must reproduce the fp32 lists (identical metrics); the raw path's
-    deltas are reported and bounded."""
+    SIMT path (the literal forward).  The synthetic histories carry no signal the random model could rank (recall@50
+    of the held-out item is ~5e-4), so the positives are PLANTED: user u's positive is the item the fp32 path ranks at
+    position (7 u) mod 120, i.e. recall@50 ~ 0.42 and recall@10 ~ 0.08 by construction, and every rank shift across a
+    cut-off shows up in the metrics.  Exact mode must reproduce the fp32 metrics (lists differ only by swaps of
+    near-ties between the two engines' item records); the raw path's deltas are reported and bounded."""
     from pixelrec_multimodal_b200 import FastMultimodalRecommender
     from pixelrec_multimodal_b200.engine import ranking_metric_sums
     n_users, k = 4096, 50
@@ -802,34 +805,39 @@ def test_catalogue_scale_metric_deltas(fusion, n_items):
     syn.condition_like_trained(sd, spec, feats)
     users = torch.arange(n_users).cuda()
     gt_ptr = torch.arange(n_users + 1, dtype=torch.int64).cuda()
-    gt_idx = hist["test_item"].to(torch.int32).cuda()
     res = {}
-    for name, path, resc in (("raw", "tcgen05", False), ("exact", "tcgen05", True), ("fp32", "simt", False)):
+    for name, path, resc, kk in (("fp32", "simt", False, 128), ("raw", "tcgen05", False, k), ("exact", "tcgen05", True, k)):
         m = FastMultimodalRecommender(n_users=n_users, n_items=n_items, n_tags=spec.n_tags, num_numerical_features=7,
                                       embedding_dim=64, vision_model_name="cached512", language_model_name="cached384",
                                       fusion_type=fusion, kernel_path=path, exact_rescore=resc).cuda()
         m.load_state_dict(sd, strict=False)
         e = m.engine("catalogue")
         e.precompute_items(m.item_embedding.weight.detach(), feats["tag_idx"], feats["vis"], feats["txt"], feats["num"])
-        s, i = e.score_topk(m.user_embedding.weight.detach(), users, k, hist["train_indptr"][:n_users + 1], hist["train_idx"])
+        s, i = e.score_topk(m.user_embedding.weight.detach(), users, kk, hist["train_indptr"][:n_users + 1], hist["train_idx"])
+        if name == "fp32":
+            gt_idx = i[users, (7 * users) % 120].contiguous()            # planted positives
+            s, i = s[:, :k].contiguous(), i[:, :k].contiguous()
         res[name] = (s, i, ranking_metric_sums(i, gt_ptr, gt_idx, [10, 50]) / n_users)
         del m, e
-    diff_users = int((res["exact"][1] != res["fp32"][1]).any(dim=1).sum())
+    diff = (res["exact"][1] != res["fp32"][1])
+    diff_users = int(diff.any(dim=1).sum())
     raw_diff_users = int((res["raw"][1] != res["fp32"][1]).any(dim=1).sum())
-    # columns: precision, recall, f1, hit_rate, ndcg, mrr, ndcg (metrics.py)
+    # columns: precision, recall, f1, hit_rate, ndcg, mrr, ndcg (metrics.py), precision hits/k, MAP
     d_exact = np.abs(res["exact"][2] - res["fp32"][2]).max()
     d_raw = np.abs(res["raw"][2] - res["fp32"][2])
-    print(f"metric deltas {fusion} x {n_items}, {n_users} users: exact-mode lists differ from fp32 for {diff_users} users "
-          f"(max metric delta {d_exact:.2e}); raw lists differ for {raw_diff_users} users, "
-          f"|d recall@10| {d_raw[0][1]:.2e} |d ndcg@10| {d_raw[0][4]:.2e} |d recall@50| {d_raw[1][1]:.2e} |d ndcg@50| {d_raw[1][4]:.2e}; "
-          f"fp32 recall@50 {res['fp32'][2][1][1]:.4f} ndcg@50 {res['fp32'][2][1][4]:.4f}")
-    assert diff_users <= n_users // 200              # only exact ties / fp32-order swaps may differ
+    f = res["fp32"][2]
+    print(f"metric deltas {fusion} x {n_items}, {n_users} users: fp32 recall@10 {f[0][1]:.4f} ndcg@10 {f[0][4]:.4f} recall@50 {f[1][1]:.4f} "
+          f"ndcg@50 {f[1][4]:.4f}; exact-mode lists differ from fp32 for {diff_users} users (max metric delta {d_exact:.2e}); "
+          f"raw lists differ for {raw_diff_users} users, |d recall@10| {d_raw[0][1]:.2e} |d ndcg@10| {d_raw[0][4]:.2e} "
+          f"|d recall@50| {d_raw[1][1]:.2e} |d ndcg@50| {d_raw[1][4]:.2e} |d mrr| {d_raw[1][5]:.2e}")
+    assert 0.3 < f[1][1] < 0.5 and 0.05 < f[0][1] < 0.12                  # the planted positives are where they should be
+    # the two engines build their item records with different kernels (3xTF32 tensor-pipe GEMMs vs the fp32 SIMT kernel),
+    # so sigmoid-saturated near-ties can swap: a differing position must be such a swap, and they are rare
+    assert diff_users <= n_users // 40
+    ds = (res["exact"][0] - res["fp32"][0]).abs()
+    assert float(ds.max()) <= 2e-5
     assert d_exact <= 1e-3
-    assert d_raw.max() <= 5e-3
-    # where the lists agree the scores agree to fp32 rounding (the two engines build their item records with
-    # different kernels -- 3xTF32 tensor-pipe GEMMs vs the fp32 SIMT kernel -- so not bit for bit)
-    agree = res["exact"][1] == res["fp32"][1]
-    assert float((res["exact"][0] - res["fp32"][0])[agree].abs().max()) <= 2e-5
+    assert d_raw.max() <= 2e-2
 
 
 def test_merge_and_metrics_full_size_properties():

@@ -57,3 +57,65 @@ def test_novelty_kernel_matches_oracle(n_users, n_items, K):
         assert abs(got[k] - v) <= 1e-9, (k, got[k], v)
     again = beyond_accuracy_metrics(torch.from_numpy(recs).cuda(), si, iif, n_pop, indptr, idx if len(idx) else np.zeros(1, np.int32))
     assert again == got                            # fixed-point accumulation: bitwise reproducible
+
+
+def test_oracle_gini_known_answers():
+    """reference tests/unit/src/evaluation/test_advanced_metrics.py:63-81"""
+    assert orc.gini_coefficient([1, 1, 1, 1]) == pytest.approx(0.0)
+    assert orc.gini_coefficient([4, 0, 0, 0]) == pytest.approx(1.0 - 1.0 / 4.0)
+    assert 0 < orc.gini_coefficient([10, 5, 1, 1]) < 1
+    assert orc.gini_coefficient([]) == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_users,n_items,K", [(300, 120, 10), (5000, 700, 50), (3, 4, 2)])
+def test_gini_and_intra_list_similarity_gpu(n_users, n_items, K):
+    """pxr_gini (count-of-counts form, no sort) and pxr_intra_list_similarity (norm of the summed unit vectors, no K x K
+    matrix) vs the direct restatements of advanced_metrics.py:72-105 and novelty.py:295-340."""
+    import torch
+    from pixelrec_multimodal_b200.evaluation import gini_coefficient, intra_list_similarity
+    rng = np.random.default_rng(n_users + K)
+    # skewed popularity so the counts spread; a short list, an empty list, a one-item list
+    p = 1.0 / np.arange(1, n_items + 1); p /= p.sum()
+    recs = np.stack([rng.choice(n_items, K, replace=False, p=p) for _ in range(n_users)]).astype(np.int32)
+    recs[1, K // 2:] = -1
+    recs[2, :] = -1
+    if n_users > 3:
+        recs[3, 1:] = -1
+    d_recs = torch.from_numpy(recs).cuda()
+    counts = np.bincount(recs[recs >= 0], minlength=n_items)
+    assert gini_coefficient(d_recs, n_items, include_zero=True) == pytest.approx(orc.gini_coefficient(counts), abs=1e-12)
+    assert gini_coefficient(d_recs, n_items, include_zero=False) == pytest.approx(orc.gini_coefficient(counts[counts > 0]), abs=1e-12)
+    emb = rng.standard_normal((n_items, 320)).astype(np.float32) + 0.5
+    emb[5] = 0.0                                                     # an item without embedding is skipped
+    want = np.mean([orc.intra_list_similarity(recs[u].tolist(), emb) for u in range(n_users)])
+    got = intra_list_similarity(d_recs, embeddings=torch.from_numpy(emb).cuda())
+    assert got == pytest.approx(want, abs=2e-6)                       # fp32 sums of up to K unit vectors
+    # reference known answers (gini of [1,1,1,1] and [4,0,0,0]) through the kernel
+    one_each = torch.arange(4, dtype=torch.int32).view(4, 1).cuda()
+    assert gini_coefficient(one_each, 4, include_zero=True) == pytest.approx(0.0, abs=1e-15)
+    only_one = torch.zeros((4, 1), dtype=torch.int32).cuda()
+    assert gini_coefficient(only_one, 4, include_zero=True) == pytest.approx(1.0 - 1.0 / 4.0, abs=1e-15)
+
+
+@pytest.mark.gpu
+def test_intra_list_similarity_from_resident_records():
+    """embeddings = the item records pxr_precompute_items left on the device: equal to the oracle on the
+    projected item-side modality vectors the oracle computes for the same items"""
+    import torch
+    from pixelrec_multimodal_b200 import synthetic as syn
+    from pixelrec_multimodal_b200.evaluation import intra_list_similarity
+    from tests import _cases as cs
+    spec = syn.ModelSpec(n_users=8, n_items=90, fusion_type="gated")
+    sd, feats = cs.make_workload(spec, syn.SEED + 51)
+    model = cs.torch_model_from(spec, sd)
+    eng = model.engine("catalogue")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    eng.precompute_items(model.item_embedding.weight.detach(), t(feats["tag_idx"]), t(feats["vis"]), t(feats["txt"]), t(feats["num"]))
+    ii = np.arange(spec.n_items)
+    f = orc.modality_features(sd, "relu", np.zeros(spec.n_items, np.int64), ii, feats["tag_idx"], feats["vis"], feats["txt"], feats["num"])
+    emb = np.concatenate(f[1:], axis=1)                              # item, tag, vision, text, numerical vectors: 5 x 64
+    rng = np.random.default_rng(7)
+    recs = np.stack([rng.permutation(spec.n_items)[:12] for _ in range(40)]).astype(np.int32)
+    want = np.mean([orc.intra_list_similarity(r.tolist(), emb) for r in recs])
+    assert intra_list_similarity(t(recs), engine=eng) == pytest.approx(want, abs=5e-6)
