@@ -47,6 +47,7 @@ CONFIGS = {
     "C": (1_001_822, 100_541, "attention", "configs[2] attention + numerical, Pixel1M-shaped 1M x 100K"),
     "D": (8_886_078, 407_082, "gated", "configs[3] Pixel8M-shaped 8.9M x 407K item-sharded"),
 }
+CONFIG_DIMS = {}          # config name -> embedding_dim when it is not 64 (scripts/sweep.py registers its sweep points here)
 TOP_K = 50
 METRIC = "scored user-item pairs/sec (full catalogue, top-50 per user)"
 UNIT = "pairs/s"
@@ -59,7 +60,7 @@ def config_dict(cfg_name: str, n_gpus: int, user_block: int, shard: str = "items
     par = "single GPU" if n_gpus == 1 else (
         f"item-shard x{n_gpus}: one all-to-all of the per-shard top-K lists per step, overlapped with the scoring of the next step, "
         f"merge by the owning rank" if shard == "items" else f"user-shard x{n_gpus}: replicas of the catalogue, no exchange")
-    return {"workload": desc, "n_users": NU, "n_items": NI, "fusion": fusion, "top_k": TOP_K, "embedding_dim": EMBEDDING_DIM,
+    return {"workload": desc, "n_users": NU, "n_items": NI, "fusion": fusion, "top_k": TOP_K, "embedding_dim": CONFIG_DIMS.get(cfg_name, EMBEDDING_DIM),
             "hidden": HIDDEN, "filter_seen": True, "users_per_step": user_block * n_gpus,
             "parallelism": f"B200 arm: {par}; CPU arm: one process, all host threads",
             "l2": "B200 arm: flushed between steps by a 256 MiB memset inside the timed region; CPU arm: not applicable"}
@@ -281,7 +282,7 @@ def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: i
     from pixelrec_multimodal_b200.sharding import exchange_owned_finish, exchange_owned_start, owned_slice, shard_range
 
     NU, NI, fusion, desc = CONFIGS[cfg_name]
-    spec = syn.ModelSpec(n_users=NU, n_items=NI, fusion_type=fusion)
+    spec = syn.ModelSpec(n_users=NU, n_items=NI, fusion_type=fusion, embedding_dim=CONFIG_DIMS.get(cfg_name, EMBEDDING_DIM))
     sd, feats, hist = syn.torch_workload(spec, dev, seed=args.seed)      # identical on every rank (same seed)
     # BatchNorm statistics matched to the activations and logits spread to std 2, like a trained checkpoint
     syn.condition_like_trained(sd, spec, feats)

@@ -284,6 +284,10 @@ int pxr_profile_read(pxr_handle* h, double* total_ms, int64_t* n_launches);
 /* Introspection used by bench.py / tests. */
 int64_t pxr_launch_count(const pxr_handle* h);       /* kernels launched through this handle */
 int pxr_active_path(const pxr_handle* h);            /* pxr_path pxr_score_topk will use      */
+/* why PXR_PATH_AUTO resolved to the generic fp32 SIMT kernels ("" when the fused tcgen05 kernel is active): the
+ * generic path is ~100x slower, so the host logs this once per model (it is exact, and it too keeps the running
+ * top-K on chip: no users x items score matrix in HBM).  A call with top_k > 64 on a tcgen05 handle also takes it. */
+const char* pxr_path_reason(const pxr_handle* h);
 int pxr_set_path(pxr_handle* h, int path);           /* force SIMT / tcgen05 (tests)          */
 
 #ifdef __cplusplus

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "pxr_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "pxr_launch_count": (C.c_int64, [C.c_void_p]),
     "pxr_active_path": (C.c_int, [C.c_void_p]),
+    "pxr_path_reason": (C.c_char_p, [C.c_void_p]),
     "pxr_set_path": (C.c_int, [C.c_void_p, C.c_int]),
     "pxr_set_rescore": (C.c_int, [C.c_void_p, C.c_int]),
     "pxr_get_rescore": (C.c_int, [C.c_void_p]),

@@ -74,6 +74,13 @@ extern "C" int pxr_profile_read(pxr_handle* h, double* total_ms, int64_t* n_laun
 
 extern "C" int64_t pxr_launch_count(const pxr_handle* h) { return h ? h->launches : 0; }
 extern "C" int pxr_active_path(const pxr_handle* h) { return h ? h->path : PXR_ERR_INVALID; }
+extern "C" const char* pxr_path_reason(const pxr_handle* h) {
+  if (!h) return "";
+  if (h->path == PXR_PATH_TCGEN05) return "";
+  if (h->cfg.path == PXR_PATH_SIMT) return "the SIMT path was requested";
+  const char* r = pxr_tc_unsupported_reason(h);
+  return r ? r : "";
+}
 extern "C" int pxr_set_rescore(pxr_handle* h, int on) {
   if (!h) return PXR_ERR_INVALID;
   h->rescore = on != 0;
@@ -257,18 +264,10 @@ extern "C" int pxr_set_missing_items(pxr_handle* h, const uint8_t* flags, int64_
 // ---------------------------------------------------------------------------
 // scoring
 // ---------------------------------------------------------------------------
-static int64_t simt_chunk_users(const pxr_handle* h, int64_t n_users) {
-  const int64_t per_user = (h->n_rows > 0 ? h->n_rows : 1);
-  int64_t chunk = (int64_t)(1ll << 28) / per_user;      // <= 1 GiB of fp32 scores per chunk
-  if (chunk < 1) chunk = 1;
-  return chunk < n_users ? chunk : n_users;
-}
-
 extern "C" size_t pxr_score_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k) {
   if (!h || n_users <= 0) return 256;
-  size_t simt = pxr_align_up((size_t)simt_chunk_users(h, n_users) * (size_t)(h->n_rows > 0 ? h->n_rows : 1) * sizeof(float), 256);
   if (h->path == PXR_PATH_TCGEN05 && pxr_tc_can_run(h, k)) return pxr_tc_topk_bytes(h, n_users, k) + 256;
-  return simt + 256;
+  return pxr_simt_topk_bytes(h, n_users, k) + 256;
 }
 
 extern "C" int pxr_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
@@ -289,17 +288,9 @@ extern "C" int pxr_score_topk(pxr_handle* h, const float* user_embedding, const 
     // -inf bit pattern 0xFF800000 cannot be memset byte-wise; reuse the row top-K kernel on zero items
     return pxr_launch_topk_rows(h, (const float*)workspace, n_users, 0, h->item_base, k, out_scores, out_idx, st);
   }
-  const int64_t chunk = simt_chunk_users(h, n_users);
-  float* dense = (float*)workspace;
-  for (int64_t u0 = 0; u0 < n_users; u0 += chunk) {
-    const int64_t nu = (n_users - u0 < chunk) ? n_users - u0 : chunk;
-    int rc = pxr_launch_score_simt(h, user_embedding, user_idx + u0, nullptr, nu * h->n_rows, nu,
-                                   seen_indptr ? seen_indptr + u0 : nullptr, seen_idx, dense, nullptr, true, st);
-    if (rc) return rc;
-    rc = pxr_launch_topk_rows(h, dense, nu, h->n_rows, h->item_base, k, out_scores + u0 * k, out_idx + u0 * k, st);
-    if (rc) return rc;
-  }
-  return PXR_OK;
+  // generic fp32 path: per-user blocks sweep the catalogue and keep the running top-K in shared memory
+  return pxr_launch_score_topk_simt(h, user_embedding, user_idx, n_users, seen_indptr, seen_idx, k, out_scores, out_idx,
+                                    workspace, workspace_bytes, st);
 }
 
 extern "C" int pxr_score_pairs(pxr_handle* h, const float* user_embedding, const int64_t* user_idx,
@@ -307,7 +298,7 @@ extern "C" int pxr_score_pairs(pxr_handle* h, const float* user_embedding, const
   if (!h) return PXR_ERR_INVALID;
   if (!h->weights_loaded || !h->items_ready || !h->item_feats) PXR_FAIL(h, PXR_ERR_STATE, "weights / items not loaded");
   if (n < 0 || (n && (!user_embedding || !user_idx || !item_row || !out))) PXR_FAIL(h, PXR_ERR_INVALID, "pxr_score_pairs: bad arguments");
-  return pxr_launch_score_simt(h, user_embedding, user_idx, item_row, n, 0, nullptr, nullptr, out, out_logit, false, (cudaStream_t)stream);
+  return pxr_launch_score_simt(h, user_embedding, user_idx, item_row, n, out, out_logit, (cudaStream_t)stream);
 }
 
 extern "C" int pxr_merge_topk(const float* scores_in, const int32_t* idx_in, int32_t n_shards, int64_t n_users,

@@ -216,12 +216,14 @@ int pxr_simt_smem_rows(const pxr_handle* h, bool items_kernel);
 int pxr_launch_items_simt(pxr_handle* h, const float* item_embedding, const int64_t* item_idx,
                           const int64_t* tag_idx, const float* vis, const float* txt, const float* num,
                           int64_t n_rows, int64_t item_base, float* feats_out, cudaStream_t st);
-// dense == true: rows are (u, i) over user_idx[0..n_users) x item rows [0..n_rows); scores (masked = -inf)
-// are written to out[(u * n_rows + i)].  dense == false: explicit pairs.
+// explicit (user, item row) pairs -> scores (and logits)
 int pxr_launch_score_simt(pxr_handle* h, const float* user_embedding, const int64_t* user_idx,
-                          const int64_t* item_row, int64_t n_pairs, int64_t n_users_dense,
-                          const int64_t* seen_indptr, const int32_t* seen_idx, float* out, float* out_logit,
-                          bool dense, cudaStream_t st);
+                          const int64_t* item_row, int64_t n_pairs, float* out, float* out_logit, cudaStream_t st);
+// generic full-catalogue scoring with the running top-K kept in shared memory (no dense score matrix)
+size_t pxr_simt_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k);
+int pxr_launch_score_topk_simt(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
+                               const int64_t* seen_indptr, const int32_t* seen_idx, int32_t k, float* out_scores,
+                               int32_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t st);
 int pxr_launch_topk_rows(pxr_handle* h, const float* scores, int64_t n_users, int64_t n_items, int64_t item_base,
                          int32_t k, float* out_scores, int32_t* out_idx, cudaStream_t st);
 int pxr_launch_merge(const float* scores_in, const int32_t* idx_in, int32_t n_shards, int64_t n_users, int32_t k,
@@ -236,6 +238,7 @@ int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_user
 
 // tcgen05 path (score_tc.cu)
 bool pxr_tc_supported(const pxr_handle* h);
+const char* pxr_tc_unsupported_reason(const pxr_handle* h);   // NULL = supported
 bool pxr_tc_can_run(const pxr_handle* h, int32_t k);   // this call (k, shard size) fits the kernel's limits
 size_t pxr_tc_weight_bytes(const pxr_handle* h);
 int pxr_tc_prepare_weights(pxr_handle* h, cudaStream_t st);

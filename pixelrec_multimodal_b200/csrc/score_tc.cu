@@ -39,6 +39,7 @@
 //     All hand-offs are mbarriers; tcgen05.commit multicasts completion to both CTAs.
 #include <algorithm>
 #include <cstddef>
+#include <cstdlib>
 
 #include <cuda_fp16.h>
 
@@ -58,7 +59,8 @@ constexpr int F_CONCAT = 0, F_GATED = 1, F_ATTN = 2;   // front ends of the kern
 // row = item * 16 + user -- the 16 rows of an item are the M dimension of the front end's register MMAs
 template <int FUS> __host__ __device__ constexpr int tile_users() { return FUS == F_ATTN ? 16 : 8; }
 template <int FUS> __host__ __device__ constexpr int tile_items() { return FUS == F_ATTN ? 8 : 16; }
-template <int FUS> __host__ __device__ constexpr int n_threads() { return THREADS; }
+constexpr int THREADS_ATT = 640;             // attention: a second front-end warpgroup (warps 16-19)
+template <int FUS> __host__ __device__ constexpr int n_threads() { return FUS == F_ATTN ? THREADS_ATT : THREADS; }
 constexpr int NH = 4, DH = D / NH;                      // attention: heads x head dim (fast path: 4 x 16)
 // attention: per-item record = 16-bit MMA B fragments in lane order (see item_attn_kernel), in 16-byte units
 constexpr int ATT_TOKENS = 5;
@@ -137,7 +139,7 @@ struct Params {
   const float* w1u_t;           // concat: [64][512] fp32, user columns of W1 transposed
   const uint4* attn_rec;        // attention: [rows][ATT_REC_U4] per-item records (16-bit MMA B fragments in lane order)
   const uint4* wo_frag;         // attention: centred out_proj weight as B fragments, [4 k-steps][4][32 lanes]
-  uint4* xc0_scratch;           // attention: per CTA, xc_0 of its 16 users in accumulator layout (ATT_XC0_U4 x 16 B)
+  uint4* xc0_scratch;           // attention: per CTA, the per-unit user operands of its 16 users in lane order (ATT_XC0_U4 x 16 B, SCR_*)
   const float* attn_in_wt;      // attention: in_proj weight transposed [64][192], bias [192]
   const float* attn_in_b;
   const float* attn_out_wt;     // attention: out_proj weight transposed [64][64], bias [64]
@@ -286,17 +288,23 @@ __device__ __forceinline__ uint32_t dup_hi(uint32_t x) { return __byte_perm(x, x
 
 // per-unit constants of a front-end thread: A fragments (rows = the CTA's 16 users) of k_u, q_u / sqrt(dh), v_u per head,
 // xc_0 = P (E_u + b_o) in accumulator layout, q_u.k_u / sqrt(dh) of rows g and g + 8
-struct AttnUserFrag {
-  uint32_t ku[NH][4], qu[NH][4], vu[NH][4];
+struct AttnUserFrag {            // what a front-end thread keeps in registers for the whole unit
+  uint32_t vu[NH][4];
   float s00[2][NH];
 };
-// xc_0 in accumulator layout, [8 n-tiles][32 lanes] x 16 B per CTA: only read once per item step (it initialises the user
-// row's accumulators), so it lives in a per-CTA global scratch line set (L2) instead of 32 registers
-constexpr int ATT_XC0_U4 = 8 * 32;
+// Per-CTA global scratch (L2) with the per-unit user operands in lane order, written by warp 0 of the front end during the
+// unit setup and read by all eight front-end warps: the k_u / q_u fragments and xc_0 are only needed once per item step,
+// so they are fetched per step instead of occupying 64 of the 128 registers a front-end thread has.  16-byte units:
+constexpr int SCR_XC0 = 0;                  // [8 n-tiles][32 lanes]  xc_0 in accumulator layout
+constexpr int SCR_KU = 8 * 32;              // [4 heads][32 lanes]    A fragments of k_u
+constexpr int SCR_QU = SCR_KU + 4 * 32;     // [4 heads][32 lanes]    A fragments of q_u / sqrt(dh)
+constexpr int SCR_VU = SCR_QU + 4 * 32;     // [4 heads][32 lanes]    A fragments of v_u
+constexpr int SCR_S00 = SCR_VU + 4 * 32;    // [2][32 lanes]          q_u.k_u / sqrt(dh) of rows g / g + 8 x 4 heads
+constexpr int ATT_XC0_U4 = SCR_S00 + 2 * 32;
 
 // `stage` = the idle A1 tile (16 KB): [16][192] fp32 in_proj outputs, then [16][64] fp32 E_u.  128 threads, named barrier 1.
 template <int FMT>
-__device__ __forceinline__ void attn_user_setup(const Params& p, float* stage, int tid, int64_t ubase, AttnUserFrag& U, uint4* xc0_out) {
+__device__ __forceinline__ void attn_user_setup(const Params& p, float* stage, int tid, int64_t ubase, uint4* scr) {
   constexpr int TUA = tile_users<F_ATTN>();
   float (*qkv)[3 * D] = reinterpret_cast<float (*)[3 * D]>(stage);
   float (*eu)[D] = reinterpret_cast<float (*)[D]>(stage + TUA * 3 * D);
@@ -323,45 +331,47 @@ __device__ __forceinline__ void attn_user_setup(const Params& p, float* stage, i
     for (int u = 0; u < TUA; ++u) qkv[u][n] = acc[u] * sc;
   }
   asm volatile("bar.sync 1, 128;" ::: "memory");
-  const int lane = tid & 31, g = lane >> 2, t = lane & 3;
+  if (tid < 32) {                                             // identical for every front-end warp: warp 0 writes the scratch
+    const int lane = tid, g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int h = 0; h < NH; ++h) {
-    const int c = DH * h + 2 * t;
+    for (int h = 0; h < NH; ++h) {
+      const int c = DH * h + 2 * t;
 #pragma unroll
-    for (int m = 0; m < 3; ++m) {                          // 0: q, 1: k, 2: v
-      uint32_t* dst = m == 0 ? U.qu[h] : (m == 1 ? U.ku[h] : U.vu[h]);
-      const int o = m * D + c;
-      dst[0] = pack2<FMT>(qkv[g][o], qkv[g][o + 1]);         dst[1] = pack2<FMT>(qkv[g + 8][o], qkv[g + 8][o + 1]);
-      dst[2] = pack2<FMT>(qkv[g][o + 8], qkv[g][o + 9]);     dst[3] = pack2<FMT>(qkv[g + 8][o + 8], qkv[g + 8][o + 9]);
+      for (int m = 0; m < 3; ++m) {                          // 0: q, 1: k, 2: v
+        const int o = m * D + c;
+        uint4 f;
+        f.x = pack2<FMT>(qkv[g][o], qkv[g][o + 1]);         f.y = pack2<FMT>(qkv[g + 8][o], qkv[g + 8][o + 1]);
+        f.z = pack2<FMT>(qkv[g][o + 8], qkv[g][o + 9]);     f.w = pack2<FMT>(qkv[g + 8][o + 8], qkv[g + 8][o + 9]);
+        scr[(m == 0 ? SCR_QU : (m == 1 ? SCR_KU : SCR_VU)) + h * 32 + lane] = f;
+      }
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      float dot = 0.f;
+      float dots[NH];
 #pragma unroll
-      for (int e = 0; e < DH; ++e) dot = fmaf(qkv[g + 8 * r][DH * h + e], qkv[g + 8 * r][D + DH * h + e], dot);
-      U.s00[r][h] = dot;
-    }
-  }
+      for (int h = 0; h < NH; ++h) {
+        float dot = 0.f;
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {                            // xc_0 = (E_u + b_o) centred over d
-    const float* e = eu[g + 8 * r];
-    float part = 0.f;
+        for (int e = 0; e < DH; ++e) dot = fmaf(qkv[g + 8 * r][DH * h + e], qkv[g + 8 * r][D + DH * h + e], dot);
+        dots[h] = dot;
+      }
+      scr[SCR_S00 + r * 32 + lane] = make_uint4(__float_as_uint(dots[0]), __float_as_uint(dots[1]), __float_as_uint(dots[2]), __float_as_uint(dots[3]));
+      // xc_0 = (E_u + b_o) centred over d
+      const float* e = eu[g + 8 * r];
+      float part = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) part += e[16 * t + i] + p.attn_out_b[16 * t + i];
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    const float mean = part * (1.f / D);
-    if (tid < 32) {                                         // identical in every front-end warp: warp 0 writes the scratch
+      for (int i = 0; i < 16; ++i) part += e[16 * t + i] + p.attn_out_b[16 * t + i];
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      const float mean = part * (1.f / D);
 #pragma unroll
       for (int nn = 0; nn < 8; ++nn) {
         const int c = 8 * nn + 2 * t;
-        float2 v2 = make_float2(e[c] + p.attn_out_b[c] - mean, e[c + 1] + p.attn_out_b[c + 1] - mean);
-        reinterpret_cast<float2*>(xc0_out + nn * 32 + lane)[r] = v2;      // .xy: row g, .zw: row g + 8
+        reinterpret_cast<float2*>(scr + SCR_XC0 + nn * 32 + lane)[r] = make_float2(e[c] + p.attn_out_b[c] - mean, e[c + 1] + p.attn_out_b[c + 1] - mean);
       }
     }
   }
-  __threadfence_block();
-  asm volatile("bar.sync 1, 128;" ::: "memory");              // the stage (A1 tile) may be overwritten now; xc_0 is visible to the CTA
+  asm volatile("bar.sync 1, 128;" ::: "memory");              // the stage (A1 tile) may be overwritten now
 }
 
 // Y += [x_h (.) v_u]_h . Wc^T: x[h] = (coefficient of row g, coefficient of row g + 8) packed; one k-step per head
@@ -406,134 +416,106 @@ __device__ __forceinline__ void attn_norm_acc(const float (&Y)[8][4], float (&ac
   }
 }
 
-// B fragments of one token's tail k-step (16 registers per lane)
-struct TailFrag { uint4 f[4]; };
-__device__ __forceinline__ void attn_load_tail(TailFrag& tf, const uint4* __restrict__ rec, int a, int lane) {
-#pragma unroll
-  for (int np = 0; np < 4; ++np) tf.f[np] = ldg_stream_u4(rec + REC_T + (a * 4 + np) * 32 + lane);
-}
-
-// Y = yc_a of item row a (token a of the record): tail k-step first (its fragments are then dead, so the next token's can be
-// fetched into the same registers a whole token ahead of their use), then the Wc pass.  x[h] = (w_ah row g, w_ah row g + 8).
+// Y (+)= A . B for the 8 n-tiles, B fragments streamed from the record two n-tiles (16 bytes per lane) at a time
 template <int FMT>
-__device__ __forceinline__ void attn_token(float (&Y)[8][4], const uint32_t (&x)[NH], const AttnUserFrag& U, TailFrag& tf,
-                                           const uint4* __restrict__ rec, const uint4* __restrict__ wo, int a_next, int lane) {
-  const int t = lane & 3;
-  const uint32_t one2 = FMT == FMT_BF16 ? 0x3F803F80u : 0x3C003C00u;
-  // tail k-step, K columns: 0-3 (1 - w_h) -> Nc_h hi, 4 / 5: 1 -> xc hi / lo, 8-11 (1 - w_h) -> Nc_h lo
-  const float2 fa = unpack2<FMT>((t & 1) ? x[2] : x[0]), fb = unpack2<FMT>((t & 1) ? x[3] : x[1]);   // .x: row g, .y: row g + 8
-  uint32_t r0 = pack2<FMT>(1.f - fa.x, 1.f - fb.x), r1 = pack2<FMT>(1.f - fa.y, 1.f - fb.y);
-  if (t == 2) { r0 = one2; r1 = one2; }
-  if (t == 3) { r0 = 0u; r1 = 0u; }
-  const uint32_t at[4] = {r0, r1, t < 2 ? r0 : 0u, t < 2 ? r1 : 0u};
+__device__ __forceinline__ void attn_rec_mma(float (&Y)[8][4], const uint32_t (&a)[4], const uint4* __restrict__ frag, int lane) {
 #pragma unroll
   for (int np = 0; np < 4; ++np) {
-    Y[2 * np][0] = Y[2 * np][1] = Y[2 * np][2] = Y[2 * np][3] = 0.f;
-    Y[2 * np + 1][0] = Y[2 * np + 1][1] = Y[2 * np + 1][2] = Y[2 * np + 1][3] = 0.f;
-    hmma<FMT>(Y[2 * np], at, tf.f[np].x, tf.f[np].y);
-    hmma<FMT>(Y[2 * np + 1], at, tf.f[np].z, tf.f[np].w);
+    const uint4 f = ldg_stream_u4(frag + np * 32 + lane);
+    hmma<FMT>(Y[2 * np], a, f.x, f.y);
+    hmma<FMT>(Y[2 * np + 1], a, f.z, f.w);
   }
-  if (a_next >= 0) attn_load_tail(tf, rec, a_next, lane);
-  attn_wo_pass<FMT>(Y, x, U, wo, lane);
 }
 
 // acc[nn][..] (accumulator layout: rows g / g + 8 of the 16 users, columns 8 nn + 2 t, + 1) = sum over the 1 + nt tokens of
-// the normalised rows of pair (user row, this item).  The front end is latency-bound per warp (one warp per scheduler), so
-// the token chain is software-pipelined: the MMAs of token a + 1 are issued before the norm / accumulate of token a (two
-// accumulator sets), every record fragment is fetched one token ahead of its use, and the record of the item this warp
-// takes in the next tile is pulled into L2 while this one is processed.
+// the normalised rows of pair (user row, this item).  Eight front-end warps (two per scheduler) cover each other's
+// latencies, so the step is written for few registers (128 per thread): one accumulator set for the row being built, one for
+// the token sum, record fragments consumed as they arrive; what the next token / the next item needs is pulled into L1 / L2
+// by prefetches issued a token / a tile ahead.
 template <int FMT>
 __device__ __forceinline__ void attn_item_step(const AttnUserFrag& U, const uint4* __restrict__ rec, const uint4* __restrict__ rec_next,
-                                               const uint4* __restrict__ wo, const uint4* __restrict__ xc0, int nt, int lane,
+                                               const uint4* __restrict__ wo, const uint4* __restrict__ scr, int nt, int lane,
                                                float (&acc)[8][4]) {
   const int t = lane & 3;
-  uint4 sf[NH];
-#pragma unroll
-  for (int h = 0; h < NH; ++h) sf[h] = ldg_stream_u4(rec + REC_S + h * 32 + lane);
-  const uint4 La4 = __ldg(rec + REC_L + 2 * t), Lb4 = __ldg(rec + REC_L + 2 * t + 1);     // L of tokens 2t, 2t + 1 x 4 heads
-  float YA[8][4], YB[8][4];
-#pragma unroll
-  for (int nn = 0; nn < 8; ++nn) {                                                       // user row starts from xc_0
-    const uint4 v = __ldcg(xc0 + nn * 32 + lane);
-    YA[nn][0] = __uint_as_float(v.x); YA[nn][1] = __uint_as_float(v.y); YA[nn][2] = __uint_as_float(v.z); YA[nn][3] = __uint_as_float(v.w);
-  }
-  uint4 uf[2][4];
-#pragma unroll
-  for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-    for (int np = 0; np < 4; ++np) uf[kk][np] = ldg_stream_u4(rec + REC_U + (kk * 4 + np) * 32 + lane);
-  TailFrag tf;
-  attn_load_tail(tf, rec, 0, lane);
-  if (rec_next) {                                                                        // 129 lines of 128 B
+  if (rec_next) {                                                                        // next tile's record -> L2 (129 lines of 128 B)
     const char* pn = reinterpret_cast<const char*>(rec_next) + lane * 128;
 #pragma unroll
     for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + i * 4096));
     if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + 16384));
   }
-  const float La[NH] = {__uint_as_float(La4.x), __uint_as_float(La4.y), __uint_as_float(La4.z), __uint_as_float(La4.w)};
-  const float Lb[NH] = {__uint_as_float(Lb4.x), __uint_as_float(Lb4.y), __uint_as_float(Lb4.z), __uint_as_float(Lb4.w)};
-  // ---- scores: c1[h] = k_u,h . q_a,h (item rows, their user column), c0[h] = q_u,h . k_b,h (user row); entry 0 / 1: row g,
-  //      token 2t / 2t + 1; entry 2 / 3: row g + 8
-  uint32_t wpk[2][NH];                                     // sigmoid weights of tokens 2t / 2t + 1: (row g, row g + 8) packed
-  {
-    uint32_t x0[NH], pa[2][4];
-    const bool v0 = 2 * t < nt, v1 = 2 * t + 1 < nt;
-#pragma unroll
-    for (int h = 0; h < NH; ++h) {
-      float c1[4] = {0.f, 0.f, 0.f, 0.f}, c0[4] = {0.f, 0.f, 0.f, 0.f};
-      hmma<FMT>(c1, U.ku[h], sf[h].x, sf[h].y);
-      hmma<FMT>(c0, U.qu[h], sf[h].z, sf[h].w);
-      wpk[0][h] = pack2<FMT>(__fdividef(1.f, 1.f + __expf(La[h] - c1[0])), __fdividef(1.f, 1.f + __expf(La[h] - c1[2])));
-      wpk[1][h] = pack2<FMT>(__fdividef(1.f, 1.f + __expf(Lb[h] - c1[1])), __fdividef(1.f, 1.f + __expf(Lb[h] - c1[3])));
-      // user row: softmax over [q_u.k_u, q_u.k_b ...] of head h, rows g and g + 8 (the tokens are spread over the quad)
-      const float a0 = v0 ? c0[0] : -INFINITY, a1 = v1 ? c0[1] : -INFINITY, b0 = v0 ? c0[2] : -INFINITY, b1 = v1 ? c0[3] : -INFINITY;
-      float mg = fmaxf(fmaxf(a0, a1), U.s00[0][h]), mh = fmaxf(fmaxf(b0, b1), U.s00[1][h]);
-      mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, 1)); mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, 1));
-      mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, 2)); mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, 2));
-      const float ea0 = __expf(a0 - mg), ea1 = __expf(a1 - mg), eb0 = __expf(b0 - mh), eb1 = __expf(b1 - mh);
-      float sg = ea0 + ea1, sh = eb0 + eb1;
-      sg += __shfl_xor_sync(0xffffffffu, sg, 1); sh += __shfl_xor_sync(0xffffffffu, sh, 1);
-      sg += __shfl_xor_sync(0xffffffffu, sg, 2); sh += __shfl_xor_sync(0xffffffffu, sh, 2);
-      const float e0g = __expf(U.s00[0][h] - mg), e0h = __expf(U.s00[1][h] - mh);
-      const float ig = __fdividef(1.f, sg + e0g), ih = __fdividef(1.f, sh + e0h);
-      x0[h] = pack2<FMT>(e0g * ig, e0h * ih);
-      pa[h >> 1][(h & 1) * 2] = pack2<FMT>(ea0 * ig, ea1 * ig);          // A fragment: K column 8 (h & 1) + token, k-step h >> 1
-      pa[h >> 1][(h & 1) * 2 + 1] = pack2<FMT>(eb0 * ih, eb1 * ih);
-    }
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        hmma<FMT>(YA[2 * np], pa[kk], uf[kk][np].x, uf[kk][np].y);
-        hmma<FMT>(YA[2 * np + 1], pa[kk], uf[kk][np].z, uf[kk][np].w);
-      }
-    attn_wo_pass<FMT>(YA, x0, U, wo, lane);
-  }
-  // ---- item rows: token a's MMAs are issued before the norm / accumulate of the previous row (two accumulator sets)
-  auto bcast = [&](int a, uint32_t (&x)[NH]) {
-#pragma unroll
-    for (int h = 0; h < NH; ++h) x[h] = __shfl_sync(0xffffffffu, wpk[a & 1][h], (lane & ~3) | (a >> 1));
+  auto prefetch_tail = [&](int a) {                                                      // token a's tail fragments (2 KB) -> L1
+    if (lane < 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(rec + REC_T + a * 128) + lane * 128));
   };
-  uint32_t x[NH];
-  // token 0 -> YB | norm(YA: user row) ; token 1 -> YA | norm(YB) ; token 2 -> YB | norm(YA) ; ...   (nt >= 3 on this path)
-  bcast(0, x); attn_token<FMT>(YB, x, U, tf, rec, wo, 1, lane);
-  attn_norm_acc<true>(YA, acc);
-  bcast(1, x); attn_token<FMT>(YA, x, U, tf, rec, wo, 2, lane);
-  attn_norm_acc<false>(YB, acc);
-  bcast(2, x); attn_token<FMT>(YB, x, U, tf, rec, wo, nt > 3 ? 3 : -1, lane);
-  attn_norm_acc<false>(YA, acc);
-  if (nt > 3) {
-    bcast(3, x); attn_token<FMT>(YA, x, U, tf, rec, wo, nt > 4 ? 4 : -1, lane);
-    attn_norm_acc<false>(YB, acc);
-    if (nt > 4) {
-      bcast(4, x); attn_token<FMT>(YB, x, U, tf, rec, wo, -1, lane);
-      attn_norm_acc<false>(YA, acc);
-      attn_norm_acc<false>(YB, acc);
-    } else {
-      attn_norm_acc<false>(YA, acc);
+  uint32_t wpk[2][NH];                                     // sigmoid weights of tokens 2t / 2t + 1: (row g, row g + 8) packed
+  float Y[8][4];
+  {
+    // ---- scores: c1 = k_u,h . q_a,h (item rows, their user column), c0 = q_u,h . k_b,h (user row); entry 0 / 1: row g,
+    //      token 2t / 2t + 1; entry 2 / 3: row g + 8
+    uint32_t x0[NH], pa[2][4];
+    {
+      const uint4 La4 = __ldg(rec + REC_L + 2 * t), Lb4 = __ldg(rec + REC_L + 2 * t + 1);   // L of tokens 2t, 2t + 1 x 4 heads
+      const float La[NH] = {__uint_as_float(La4.x), __uint_as_float(La4.y), __uint_as_float(La4.z), __uint_as_float(La4.w)};
+      const float Lb[NH] = {__uint_as_float(Lb4.x), __uint_as_float(Lb4.y), __uint_as_float(Lb4.z), __uint_as_float(Lb4.w)};
+      const bool v0 = 2 * t < nt, v1 = 2 * t + 1 < nt;
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const uint4 sf = ldg_stream_u4(rec + REC_S + h * 32 + lane);
+        const uint4 kf = __ldcg(scr + SCR_KU + h * 32 + lane), qf = __ldcg(scr + SCR_QU + h * 32 + lane);
+        const uint32_t ku[4] = {kf.x, kf.y, kf.z, kf.w}, qu[4] = {qf.x, qf.y, qf.z, qf.w};
+        float c1[4] = {0.f, 0.f, 0.f, 0.f}, c0[4] = {0.f, 0.f, 0.f, 0.f};
+        hmma<FMT>(c1, ku, sf.x, sf.y);
+        hmma<FMT>(c0, qu, sf.z, sf.w);
+        wpk[0][h] = pack2<FMT>(__fdividef(1.f, 1.f + __expf(La[h] - c1[0])), __fdividef(1.f, 1.f + __expf(La[h] - c1[2])));
+        wpk[1][h] = pack2<FMT>(__fdividef(1.f, 1.f + __expf(Lb[h] - c1[1])), __fdividef(1.f, 1.f + __expf(Lb[h] - c1[3])));
+        // user row: softmax over [q_u.k_u, q_u.k_b ...] of head h, rows g and g + 8 (the tokens are spread over the quad)
+        const float a0 = v0 ? c0[0] : -INFINITY, a1 = v1 ? c0[1] : -INFINITY, b0 = v0 ? c0[2] : -INFINITY, b1 = v1 ? c0[3] : -INFINITY;
+        float mg = fmaxf(fmaxf(a0, a1), U.s00[0][h]), mh = fmaxf(fmaxf(b0, b1), U.s00[1][h]);
+        mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, 1)); mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, 1));
+        mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, 2)); mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, 2));
+        const float ea0 = __expf(a0 - mg), ea1 = __expf(a1 - mg), eb0 = __expf(b0 - mh), eb1 = __expf(b1 - mh);
+        float sg = ea0 + ea1, sh = eb0 + eb1;
+        sg += __shfl_xor_sync(0xffffffffu, sg, 1); sh += __shfl_xor_sync(0xffffffffu, sh, 1);
+        sg += __shfl_xor_sync(0xffffffffu, sg, 2); sh += __shfl_xor_sync(0xffffffffu, sh, 2);
+        const float e0g = __expf(U.s00[0][h] - mg), e0h = __expf(U.s00[1][h] - mh);
+        const float ig = __fdividef(1.f, sg + e0g), ih = __fdividef(1.f, sh + e0h);
+        x0[h] = pack2<FMT>(e0g * ig, e0h * ih);
+        pa[h >> 1][(h & 1) * 2] = pack2<FMT>(ea0 * ig, ea1 * ig);          // A fragment: K column 8 (h & 1) + token, k-step h >> 1
+        pa[h >> 1][(h & 1) * 2 + 1] = pack2<FMT>(eb0 * ih, eb1 * ih);
+      }
     }
-  } else {
-    attn_norm_acc<false>(YB, acc);
+    prefetch_tail(0);
+    // ---- user row: xc_0 + [p_0b] . Uc + Wc (p_00 (.) v_u)
+#pragma unroll
+    for (int nn = 0; nn < 8; ++nn) {
+      const uint4 v = __ldcg(scr + SCR_XC0 + nn * 32 + lane);
+      Y[nn][0] = __uint_as_float(v.x); Y[nn][1] = __uint_as_float(v.y); Y[nn][2] = __uint_as_float(v.z); Y[nn][3] = __uint_as_float(v.w);
+    }
+    attn_rec_mma<FMT>(Y, pa[0], rec + REC_U, lane);
+    attn_rec_mma<FMT>(Y, pa[1], rec + REC_U + 128, lane);
+    attn_wo_pass<FMT>(Y, x0, U, wo, lane);
+    attn_norm_acc<true>(Y, acc);
+  }
+  // ---- item rows
+  const uint32_t one2 = FMT == FMT_BF16 ? 0x3F803F80u : 0x3C003C00u;
+#pragma unroll 1
+  for (int a = 0; a < nt; ++a) {
+    if (a + 1 < nt) prefetch_tail(a + 1);
+    uint32_t x[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) x[h] = __shfl_sync(0xffffffffu, (a & 1) ? wpk[1][h] : wpk[0][h], (lane & ~3) | (a >> 1));
+    // tail k-step, K columns: 0-3 (1 - w_h) -> Nc_h hi, 4 / 5: 1 -> xc hi / lo, 8-11 (1 - w_h) -> Nc_h lo
+    {
+      const float2 fa = unpack2<FMT>((t & 1) ? x[2] : x[0]), fb = unpack2<FMT>((t & 1) ? x[3] : x[1]);   // .x: row g, .y: row g + 8
+      uint32_t r0 = pack2<FMT>(1.f - fa.x, 1.f - fb.x), r1 = pack2<FMT>(1.f - fa.y, 1.f - fb.y);
+      if (t == 2) { r0 = one2; r1 = one2; }
+      if (t == 3) { r0 = 0u; r1 = 0u; }
+      const uint32_t at[4] = {r0, r1, t < 2 ? r0 : 0u, t < 2 ? r1 : 0u};
+#pragma unroll
+      for (int nn = 0; nn < 8; ++nn) { Y[nn][0] = 0.f; Y[nn][1] = 0.f; Y[nn][2] = 0.f; Y[nn][3] = 0.f; }
+      attn_rec_mma<FMT>(Y, at, rec + REC_T + a * 128, lane);
+    }
+    attn_wo_pass<FMT>(Y, x, U, wo, lane);
+    attn_norm_acc<false>(Y, acc);
   }
 }
 
@@ -577,7 +559,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
     ms.b4 = ATT ? p.bias_c[H1 + H2 + H3 + H3] : p.bias[H1 + H2 + H3 + H3];
     ms.q_tail[0] = ms.q_tail[1] = 0; ms.q_head[0] = ms.q_head[1] = 0;
     ptx::mbar_init(BAR(BAR_W), 1);
-    ptx::mbar_init(BAR(BAR_A_FULL), 8);                   // one arrival per front-end warp of both CTAs
+    ptx::mbar_init(BAR(BAR_A_FULL), ATT ? 16 : 8);        // one arrival per front-end warp of both CTAs
     ptx::mbar_init(BAR(BAR_A_EMPTY), 1);
     for (int b = 0; b < 4; ++b) {
       ptx::mbar_init(BAR(BAR_D1_FULL0 + b), 1);
@@ -617,18 +599,22 @@ score_fused_kernel(const __grid_constant__ Params p) {
   // units of this pair: w = pair, pair + n_pairs, ...; every role walks the same (unit, tile) sequence;
   // T counts tiles over all units of the pair
 
-  // attention: register budget per warpgroup.  512 threads are launched with 128 registers each and setmaxnreg moves
-  // registers inside that pool (65 536): the MMA / top-K warpgroup drops to 56, the two epilogue warpgroups to 112, the
-  // front-end warpgroup (per-user MMA fragments + two 16 x 64 fp32 accumulator sets per thread) takes 232
-  // (128*232 + 128*56 + 256*112 = 65 536).  setmaxnreg sits at the top of each warpgroup's branch so that ptxas
-  // allocates per role.
-  if (warp < 4) {
-    if (ATT) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  // attention: register budget per warpgroup.  640 threads are launched with 96 registers each and setmaxnreg can only move
+  // registers inside that pool (61 440): the MMA / top-K warpgroup drops to 40, the two front-end warpgroups take 128, the
+  // epilogue warpgroups drop to 88  (2*128*128 + 128*40 + 2*128*88 = 60 416).  setmaxnreg sits at the top of each
+  // warpgroup's branch so that ptxas allocates per role.
+  if (warp < 4 || (ATT && warp >= 16)) {
+    if (ATT) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     // =============================================================== front end
+    // attention: eight front-end warps (warpgroups A = warps 0-3 and B = warps 16-19), one item of the tile each, two per
+    // scheduler; warpgroup A also builds the per-unit user operands; named barriers 2 / 3 fence them between units.
+    const bool feB = ATT && warp >= 16;
+    const int fw = feB ? warp - 12 : warp;  // front-end warp 0..7 (attention) / 0..3
     const int tid = threadIdx.x & 127;      // 0..127 inside the front-end warpgroup
     const int Mm = p.M;
     int T = 0;
     AttnUserFrag UF;                        // attention: per-unit user operands of this thread (registers)
+    uint4* const scr = ATT ? p.xc0_scratch + (size_t)blockIdx.x * ATT_XC0_U4 : nullptr;
     for (int w = pair; w < p.n_units; w += n_pairs) {
       const Unit un = decode_unit<TI>(p, w);
       const int64_t ubase = ((int64_t)un.g * 2 + rank) * TU;     // first user ordinal of this CTA's group
@@ -636,11 +622,13 @@ score_fused_kernel(const __grid_constant__ Params p) {
         // Pu is read by the layer-1 producers of the previous unit's last tile: wait until they are done with it
         ptx::mbar_wait(BAR(BAR_PI_EMPTY0 + ((T - 1) & 1)), ((T - 1) >> 1) & 1);
       }
+      if (ATT) asm volatile("bar.sync 2, 256;" ::: "memory");      // both warpgroups are done with the previous unit's scratch
+      if (!feB) {
       asm volatile("bar.sync 1, 128;" ::: "memory");              // previous unit's readers of eu/lu are done
       if (ATT) {
         // the per-unit user operands are staged in the A1 tile: wait until the layer-1 MMAs of the previous tile have read it
         if (T > 0) ptx::mbar_wait(BAR(BAR_A_EMPTY), (T - 1) & 1);
-        attn_user_setup<FMT>(p, reinterpret_cast<float*>(sm + MP::OFF_A1), tid, ubase, UF, p.xc0_scratch + (size_t)blockIdx.x * ATT_XC0_U4);
+        attn_user_setup<FMT>(p, reinterpret_cast<float*>(sm + MP::OFF_A1), tid, ubase, scr);
       } else {
         const int u = tid >> 4, d4 = (tid & 15) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -694,6 +682,20 @@ score_fused_kernel(const __grid_constant__ Params p) {
           *reinterpret_cast<float4*>(sm + MP::OFF_PU + u * MP::PU_STRIDE + 16 * tid) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (ATT) {
+        asm volatile("bar.sync 3, 256;" ::: "memory");            // the user operands of this unit are in the scratch
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const uint4 f = __ldcg(scr + SCR_VU + h * 32 + lane);
+          UF.vu[h][0] = f.x; UF.vu[h][1] = f.y; UF.vu[h][2] = f.z; UF.vu[h][3] = f.w;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const uint4 f = __ldcg(scr + SCR_S00 + r * 32 + lane);
+          UF.s00[r][0] = __uint_as_float(f.x); UF.s00[r][1] = __uint_as_float(f.y); UF.s00[r][2] = __uint_as_float(f.z); UF.s00[r][3] = __uint_as_float(f.w);
+        }
+      }
       // seen-item cursors: lanes 0..TU-1 of warp 0 walk user u's ascending history with the item sweep
       int64_t cur = 0, cend = 0; int32_t nextv = 0x7fffffff;
       if (warp == 0 && lane < TU && p.seen_indptr && ubase + lane < p.n_users) {
@@ -721,17 +723,15 @@ score_fused_kernel(const __grid_constant__ Params p) {
         };
         if (FUS == F_ATTN) {
           write_seen_mask();
-#pragma unroll 1
-          for (int jj = 0; jj < 2; ++jj) {                            // this warp's two items of the tile x the CTA's 16 users
-            const int j = 2 * warp + jj;
+          {                                                           // this warp's item of the tile x the CTA's 16 users
+            const int j = fw;
             const int64_t row = row0 + j;
             const int64_t rr = row < un.row_hi ? row : un.row_lo;    // padding rows recompute a valid item (discarded later)
-            // the item this warp takes next: its second item of this tile, then the same slot of the next tile
-            const int64_t rn = jj == 0 ? row + 1 : row + TI - 1;
+            const int64_t rn = row + TI;                             // the item this warp takes in the next tile
             float acc[8][4];
             attn_item_step<FMT>(UF, p.attn_rec + rr * ATT_REC_U4, rn < un.row_hi ? p.attn_rec + rn * ATT_REC_U4 : nullptr, p.wo_frag,
-                                p.xc0_scratch + (size_t)blockIdx.x * ATT_XC0_U4, Mm - 1, lane, acc);
-            if (jj == 0 && T > 0) ptx::mbar_wait(BAR(BAR_A_EMPTY), (T - 1) & 1);   // layer-1 MMAs of the previous tile have read A1
+                                scr, Mm - 1, lane, acc);
+            if (T > 0) ptx::mbar_wait(BAR(BAR_A_EMPTY), (T - 1) & 1);   // layer-1 MMAs of the previous tile have read A1
             // 16-bit pack into the swizzled A1 rows: row = item * 16 + user, user rows g and g + 8 of this lane
             const int g = lane >> 2, t4 = (lane & 3) * 4;
             uint8_t* a1 = sm + MP::OFF_A1 + (2 * j) * 1024 + g * 128 + t4;
@@ -818,7 +818,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
       }
     }
   } else if (warp < 8) {
-   if (ATT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (ATT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
    if (warp == 4) {
     // =============================================================== MMA issuer (leader CTA, one thread)
     if (rank == 0 && lane == 0) {
@@ -972,7 +972,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
    }
   } else {
     // =============================================================== epilogue groups (warps 8-15)
-    if (ATT) asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    if (ATT) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     const int grp = (warp - 8) >> 2;                 // 0: even layer-1 chunks, first half of layer 2, layer 3
     const int q = warp & 3;                          // TMEM lane quarter this warp may touch
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
@@ -1408,7 +1408,9 @@ static int launch_fused_tk(pxr_handle* h, const Params& p, int n_pairs, cudaStre
 // two); for long units the second warp only costs the front end issue slots (-2.8 % on the gated headline config).
 template <int FUS, int FMT>
 static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_t st) {
-  return p.rows_per_split < 8192 ? launch_fused_tk<FUS, FMT, true>(h, p, n_pairs, st) : launch_fused_tk<FUS, FMT, false>(h, p, n_pairs, st);
+  static int thr = -1;                    // PXR_TK2_ROWS: rows per unit below which the second top-K warp is used (experiments)
+  if (thr < 0) { const char* e = getenv("PXR_TK2_ROWS"); thr = e ? atoi(e) : 8192; }
+  return p.rows_per_split < thr ? launch_fused_tk<FUS, FMT, true>(h, p, n_pairs, st) : launch_fused_tk<FUS, FMT, false>(h, p, n_pairs, st);
 }
 
 }  // namespace tc
@@ -1416,19 +1418,26 @@ static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-bool pxr_tc_supported(const pxr_handle* h) {
+// NULL when the fused tcgen05 kernel covers this model configuration, else why it does not
+const char* pxr_tc_unsupported_reason(const pxr_handle* h) {
   const pxr_config& c = h->cfg;
-  const bool fusion_ok = c.fusion == PXR_FUSION_GATED || c.fusion == PXR_FUSION_CONCAT ||
-                         (c.fusion == PXR_FUSION_ATTENTION && c.num_heads == tc::NH);
+  if (h->n_sm < 2) return "the device has fewer than 2 SMs (the kernel runs on CTA pairs)";
+  if (c.n_hidden != 3 || c.hidden[0] != tc::H1 || c.hidden[1] != tc::H2 || c.hidden[2] != tc::H3)
+    return "fusion_hidden_dims is not [512, 256, 128] (the three weight matrices are resident in the CTA pair's shared memory)";
+  if (c.activation != PXR_ACT_RELU) return "fusion_activation is not relu (the in-place TMEM epilogues use cvt.relu)";
+  if (h->M < 4 || h->M > 6) return "fewer than 4 modalities";
+  if (c.fusion == PXR_FUSION_ATTENTION && c.num_heads != tc::NH) return "attention fusion with num_attention_heads != 4";
+  if (c.fusion != PXR_FUSION_CONCAT && c.embedding_dim != tc::D) return "gated / attention fusion with embedding_dim != 64 (layer 1 is a K = 64 MMA)";
   // concat: layer 1 is applied as per-user / per-item partials, so the fused kernel does not depend on embedding_dim
   // (item side: 3xTF32 GEMMs of items_tc.cu, which need single-layer projections and 16-byte aligned rows)
-  const bool dim_ok = c.embedding_dim == tc::D ||
-                      (c.fusion == PXR_FUSION_CONCAT && c.embedding_dim % 16 == 0 && c.embedding_dim <= 512 && c.projection_hidden == 0 &&
-                       c.vision_dim % 4 == 0 && c.language_dim % 4 == 0 && c.num_numerical <= 32);
-  return fusion_ok && dim_ok && c.n_hidden == 3 &&
-         c.hidden[0] == tc::H1 && c.hidden[1] == tc::H2 && c.hidden[2] == tc::H3 && c.activation == PXR_ACT_RELU &&
-         h->M >= 4 && h->M <= 6 && h->n_sm >= 2;
+  if (c.fusion == PXR_FUSION_CONCAT && c.embedding_dim != tc::D &&
+      !(c.embedding_dim % 16 == 0 && c.embedding_dim <= 512 && c.projection_hidden == 0 && c.vision_dim % 4 == 0 &&
+        c.language_dim % 4 == 0 && c.num_numerical <= 32))
+    return "concat fusion with embedding_dim != 64 needs embedding_dim % 16 == 0, single-layer projections and feature dims % 4 == 0";
+  return nullptr;
 }
+
+bool pxr_tc_supported(const pxr_handle* h) { return pxr_tc_unsupported_reason(h) == nullptr; }
 
 bool pxr_tc_can_run(const pxr_handle* h, int32_t k) {
   return h->fast_ok && k <= tc::KCAP && h->n_rows > 0 && h->item_base + h->n_rows < (int64_t)tc::IDX_MASK;

@@ -148,27 +148,19 @@ struct ScoreParams {
   float* out; float* out_logit;
 };
 
+#define MERGE_MAX_KEYS_SIMT 4096
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int n_pow2);
+
+// The forward of ROWS pairs whose (user row, item row) are in prow[2 r], prow[2 r + 1] (user < 0: padding row, computed
+// on zeros): leaves the pre-activation logit of row r in G[8 r].  Called by every thread of the block.
 template <int ROWS>
-__global__ void __launch_bounds__(PXR_SIMT_THREADS) score_simt_kernel(ScoreParams p) {
-  extern __shared__ __align__(16) float smem[];
+__device__ __forceinline__ void score_rows(const ScoreParams& p, float* smem) {
   const int D = p.D, M = p.M, MD = M * D, maxdim = p.maxdim;
   float* X = smem;                                   // [ROWS][M*D]: the token stack == the concat vector
   float* A = X + (size_t)ROWS * MD;                  // [ROWS][maxdim]
   float* B = A + (size_t)ROWS * maxdim;              // [ROWS][maxdim]
   float* G = B + (size_t)ROWS * maxdim;              // [ROWS][8]
-  long long* prow = reinterpret_cast<long long*>(G + ROWS * 8);   // [ROWS][2] (user row, item row)
-  const int64_t row0 = (int64_t)blockIdx.x * ROWS;
-
-  if (threadIdx.x < ROWS) {
-    const int64_t pair = row0 + threadIdx.x;
-    long long u = -1, ir = -1;
-    if (pair < p.n_pairs) {
-      if (p.dense) { u = p.user_idx[pair / p.n_items]; ir = pair % p.n_items; }
-      else { u = p.user_idx[pair]; ir = p.item_row[pair]; }
-    }
-    prow[threadIdx.x * 2] = u; prow[threadIdx.x * 2 + 1] = ir;
-  }
-  __syncthreads();
+  const long long* prow = reinterpret_cast<const long long*>(G + ROWS * 8);   // [ROWS][2] (user row, item row)
   for (int idx = threadIdx.x; idx < ROWS * (MD / 4); idx += PXR_SIMT_THREADS) {
     const int r = idx / (MD / 4), c = (idx % (MD / 4)) * 4;
     const long long u = prow[r * 2], ir = prow[r * 2 + 1];
@@ -279,22 +271,104 @@ __global__ void __launch_bounds__(PXR_SIMT_THREADS) score_simt_kernel(ScoreParam
   }
   linear_small<ROWS>(cur, ldcur, Kcur, p.out_w, p.out_b, 1, G, 8);
   __syncthreads();
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(PXR_SIMT_THREADS) score_simt_kernel(ScoreParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int MD = p.M * p.D, maxdim = p.maxdim;
+  float* G = smem + (size_t)ROWS * MD + 2 * (size_t)ROWS * maxdim;
+  long long* prow = reinterpret_cast<long long*>(G + ROWS * 8);
+  const int64_t row0 = (int64_t)blockIdx.x * ROWS;
+  if (threadIdx.x < ROWS) {
+    const int64_t pair = row0 + threadIdx.x;
+    long long u = -1, ir = 0;
+    if (pair < p.n_pairs) { u = p.user_idx[pair]; ir = p.item_row[pair]; }
+    if (u < 0) ir = 0;
+    prow[threadIdx.x * 2] = u; prow[threadIdx.x * 2 + 1] = ir;
+  }
+  __syncthreads();
+  score_rows<ROWS>(p, smem);
   if (threadIdx.x < ROWS) {
     const int64_t pair = row0 + threadIdx.x;
     if (pair < p.n_pairs) {
       float z = G[threadIdx.x * 8];
       float s = pxr_apply_final(z, p.fin);
       if (p.item_missing && p.item_missing[prow[threadIdx.x * 2 + 1]]) { s = 0.f; z = 0.f; }
-      if (p.dense && p.seen_indptr) {
-        const int64_t ul = pair / p.n_items;
-        const int32_t gi = (int32_t)(p.item_base + pair % p.n_items);
-        int64_t lo = p.seen_indptr[ul], hi = p.seen_indptr[ul + 1];
-        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (p.seen_idx[mid] < gi) lo = mid + 1; else hi = mid; }
-        if (lo < p.seen_indptr[ul + 1] && p.seen_idx[lo] == gi) s = -INFINITY;   // filtered (recommender.py:88-90)
-      }
       p.out[pair] = s;
       if (p.out_logit) p.out_logit[pair] = z;
     }
+  }
+}
+
+// K3g + K3t fused: one block = one user x one item split.  The block sweeps its items ROWS at a time through the same
+// literal forward and keeps the user's running top-K in shared memory (64-bit keys (score, ~index): ties -> lower index):
+// a row enters the candidate buffer only if it beats the current K-th key; a full buffer is compacted by a bitonic sort.
+// The users x items scores never reach HBM on this path either.
+#define TOPKS_MAX_K 1024
+struct TopkSimtParams {
+  int64_t n_users; int S; int64_t rows_per_split; int k, kp, cap;
+  float* out_scores; int32_t* out_idx;               // [S][n_users][k]
+};
+
+template <int ROWS>
+__global__ void __launch_bounds__(PXR_SIMT_THREADS) score_topk_simt_kernel(ScoreParams p, TopkSimtParams tp) {
+  extern __shared__ __align__(16) float smem[];
+  const int MD = p.M * p.D, maxdim = p.maxdim;
+  float* G = smem + (size_t)ROWS * MD + 2 * (size_t)ROWS * maxdim;
+  long long* prow = reinterpret_cast<long long*>(G + ROWS * 8);
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(prow + ROWS * 2);      // [cap]
+  __shared__ int s_cnt;
+  __shared__ unsigned long long s_thr;
+  const int64_t ul = blockIdx.x / tp.S;
+  const int sp = blockIdx.x % tp.S;
+  const int64_t lo = (int64_t)sp * tp.rows_per_split, hi = min(p.n_items, lo + tp.rows_per_split);
+  const long long user = p.user_idx[ul];
+  for (int i = threadIdx.x; i < tp.cap; i += PXR_SIMT_THREADS) buf[i] = 0ull;
+  if (threadIdx.x == 0) { s_cnt = 0; s_thr = 0ull; }
+  int64_t seen_lo = 0, seen_hi = 0;
+  if (p.seen_indptr) { seen_lo = p.seen_indptr[ul]; seen_hi = p.seen_indptr[ul + 1]; }
+  __syncthreads();
+  auto compact = [&]() {            // keep the best k of the buffer, sorted; refresh the admission threshold
+    bitonic_sort_desc(buf, tp.cap);
+    for (int i = tp.k + threadIdx.x; i < tp.cap; i += PXR_SIMT_THREADS) buf[i] = 0ull;
+    __syncthreads();
+    if (threadIdx.x == 0) { s_cnt = min(s_cnt, tp.k); s_thr = s_cnt >= tp.k ? buf[tp.k - 1] : 0ull; }
+    __syncthreads();
+  };
+  for (int64_t r0 = lo; r0 < hi; r0 += ROWS) {
+    if (threadIdx.x < ROWS) {
+      const int64_t ir = r0 + threadIdx.x;
+      prow[threadIdx.x * 2] = ir < hi ? user : -1;
+      prow[threadIdx.x * 2 + 1] = ir < hi ? ir : 0;
+    }
+    __syncthreads();
+    score_rows<ROWS>(p, smem);
+    if (s_cnt > tp.cap - ROWS) compact();            // block-uniform: s_cnt is only written between barriers
+    if (threadIdx.x < ROWS) {
+      const int64_t ir = r0 + threadIdx.x;
+      if (ir < hi) {
+        float s = pxr_apply_final(G[threadIdx.x * 8], p.fin);
+        if (p.item_missing && p.item_missing[ir]) s = 0.f;
+        const int32_t gi = (int32_t)(p.item_base + ir);
+        bool seen = false;
+        if (p.seen_indptr) {
+          int64_t a = seen_lo, b = seen_hi;
+          while (a < b) { const int64_t mid = (a + b) >> 1; if (p.seen_idx[mid] < gi) a = mid + 1; else b = mid; }
+          seen = a < seen_hi && p.seen_idx[a] == gi;   // filtered (recommender.py:88-90)
+        }
+        const unsigned long long key = pxr_key(s, (uint32_t)gi);
+        if (!seen && key > s_thr) buf[atomicAdd(&s_cnt, 1)] = key;
+      }
+    }
+    __syncthreads();
+  }
+  compact();
+  for (int i = threadIdx.x; i < tp.k; i += PXR_SIMT_THREADS) {
+    const unsigned long long kv = buf[i];
+    const int64_t o = ((int64_t)sp * tp.n_users + ul) * tp.k + i;
+    tp.out_scores[o] = kv ? pxr_key_score(kv) : -INFINITY;
+    tp.out_idx[o] = kv ? (int32_t)pxr_key_idx(kv) : -1;
   }
 }
 
@@ -313,9 +387,12 @@ static size_t score_smem(const pxr_handle* h, int rows) {
 
 int pxr_simt_smem_rows(const pxr_handle* h, bool items_kernel) {
   if (items_kernel) { int a, b; size_t s; return items_rows_for(h, &a, &b, &s); }
+  // 16 rows per block, not the largest that fits: two resident blocks per SM hide the weight-load latency better than one
+  // block with twice the rows (262 144 pairs of the default MLP: 8.05 ms with 32 rows, 5.56 ms with 16, 6.32 ms with 8;
+  // profiles/r02_rescore_rows.log).  PXR_SIMT_ROWS overrides for experiments.
   const int cands[4] = {32, 16, 8, 4};
-  static int forced = -1;                                   // PXR_SIMT_ROWS=16|8|4: experiments with more resident blocks per SM
-  if (forced < 0) { const char* e = getenv("PXR_SIMT_ROWS"); forced = e ? atoi(e) : 0; }
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("PXR_SIMT_ROWS"); forced = e ? atoi(e) : 16; }
   for (int i = 0; i < 4; ++i) {
     if (forced && cands[i] > forced) continue;
     if (score_smem(h, cands[i]) <= (size_t)h->max_smem_optin - 1024) return cands[i];
@@ -329,20 +406,13 @@ static int launch_score(pxr_handle* h, const ScoreParams& p, cudaStream_t st) {
   PXR_CUDA(h, cudaFuncSetAttribute(score_simt_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t blocks = (p.n_pairs + ROWS - 1) / ROWS;
   if (blocks > 0x7fffffffLL) PXR_FAIL(h, PXR_ERR_INVALID, "too many pairs for one launch");
-  if (p.dense) pxr_prof_begin(h, st);
   score_simt_kernel<ROWS><<<(unsigned)blocks, PXR_SIMT_THREADS, smem, st>>>(p);
-  if (p.dense) pxr_prof_end(h, st);
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
   return PXR_OK;
 }
 
-int pxr_launch_score_simt(pxr_handle* h, const float* user_embedding, const int64_t* user_idx,
-                          const int64_t* item_row, int64_t n_pairs, int64_t n_users_dense,
-                          const int64_t* seen_indptr, const int32_t* seen_idx, float* out, float* out_logit,
-                          bool dense, cudaStream_t st) {
-  if (n_pairs == 0) return PXR_OK;
-  ScoreParams p;
+static void fill_score_params(const pxr_handle* h, ScoreParams& p) {
   memset(&p, 0, sizeof(p));
   p.fusion = h->cfg.fusion; p.D = h->cfg.embedding_dim; p.M = h->M; p.n_hidden = h->cfg.n_hidden;
   for (int l = 0; l < p.n_hidden; ++l) { p.hidden[l] = h->cfg.hidden[l]; p.mlp_wt[l] = h->mlp[l].wt; p.mlp_b[l] = h->mlp[l].b; }
@@ -351,11 +421,17 @@ int pxr_launch_score_simt(pxr_handle* h, const float* user_embedding, const int6
   p.attn_in_wt = h->attn_in.wt; p.attn_in_b = h->attn_in.b; p.attn_out_wt = h->attn_out.wt; p.attn_out_b = h->attn_out.b;
   p.ln_w = h->ln_w; p.ln_b = h->ln_b;
   p.out_w = h->out.w; p.out_b = h->out.b;
-  p.user_emb = user_embedding; p.user_idx = user_idx; p.item_row = item_row;
-  p.item_feats = h->item_feats; p.n_items = h->n_rows; p.n_pairs = n_pairs; p.dense = dense ? 1 : 0;
-  p.item_base = h->item_base; p.seen_indptr = seen_indptr; p.seen_idx = seen_idx;
-  p.out = out; p.out_logit = out_logit; p.item_missing = h->item_missing;
-  (void)n_users_dense;
+  p.item_feats = h->item_feats; p.n_items = h->n_rows; p.item_base = h->item_base; p.item_missing = h->item_missing;
+}
+
+// explicit (user, item row) pairs -> scores (and logits)
+int pxr_launch_score_simt(pxr_handle* h, const float* user_embedding, const int64_t* user_idx,
+                          const int64_t* item_row, int64_t n_pairs, float* out, float* out_logit, cudaStream_t st) {
+  if (n_pairs == 0) return PXR_OK;
+  ScoreParams p;
+  fill_score_params(h, p);
+  p.user_emb = user_embedding; p.user_idx = user_idx; p.item_row = item_row; p.n_pairs = n_pairs;
+  p.out = out; p.out_logit = out_logit;
   switch (pxr_simt_smem_rows(h, false)) {
     case 32: return launch_score<32>(h, p, st);
     case 16: return launch_score<16>(h, p, st);
@@ -363,6 +439,82 @@ int pxr_launch_score_simt(pxr_handle* h, const float* user_embedding, const int6
     case 4: return launch_score<4>(h, p, st);
   }
   PXR_FAIL(h, PXR_ERR_INVALID, "layer dims too large for the SIMT scoring kernel");
+}
+
+// ---- generic full-catalogue path: per-user blocks with the running top-K in shared memory (no dense score matrix)
+static int topk_simt_kp(int k, int rows) { int kp = 1; while (kp < k || kp < rows) kp <<= 1; return kp; }
+
+static int topk_simt_rows(const pxr_handle* h, int k) {
+  const int cands[4] = {32, 16, 8, 4};
+  const int base = pxr_simt_smem_rows(h, false);
+  for (int i = 0; i < 4; ++i) {
+    if (cands[i] > base) continue;
+    const size_t sm = score_smem(h, cands[i]) + (size_t)2 * topk_simt_kp(k, cands[i]) * 8;
+    if (sm <= (size_t)h->max_smem_optin - 1024) return cands[i];
+  }
+  return 0;
+}
+
+static int topk_simt_splits(const pxr_handle* h, int64_t n_users, int k) {
+  // enough blocks to fill the SMs twice when the user block is small; bounded by K4's merge width and the tile count
+  int64_t s = (2 * (int64_t)h->n_sm + n_users - 1) / (n_users > 0 ? n_users : 1);
+  s = std::min<int64_t>(s, MERGE_MAX_KEYS_SIMT / k);
+  s = std::min<int64_t>(s, (h->n_rows + 255) / 256);
+  return (int)std::max<int64_t>(s, 1);
+}
+
+size_t pxr_simt_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k) {
+  const int S = topk_simt_splits(h, n_users, k);
+  return S > 1 ? pxr_align_up((size_t)S * n_users * k * 8, 256) + 256 : 256;
+}
+
+template <int ROWS>
+static int launch_score_topk(pxr_handle* h, const ScoreParams& p, TopkSimtParams tp, cudaStream_t st) {
+  tp.kp = topk_simt_kp(tp.k, ROWS); tp.cap = 2 * tp.kp;
+  const size_t smem = score_smem(h, ROWS) + (size_t)tp.cap * 8;
+  PXR_CUDA(h, cudaFuncSetAttribute(score_topk_simt_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = tp.n_users * tp.S;
+  if (blocks > 0x7fffffffLL) PXR_FAIL(h, PXR_ERR_INVALID, "too many users for one launch");
+  pxr_prof_begin(h, st);
+  score_topk_simt_kernel<ROWS><<<(unsigned)blocks, PXR_SIMT_THREADS, smem, st>>>(p, tp);
+  pxr_prof_end(h, st);
+  h->launches++;
+  PXR_CUDA(h, cudaGetLastError());
+  return PXR_OK;
+}
+
+int pxr_launch_score_topk_simt(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
+                               const int64_t* seen_indptr, const int32_t* seen_idx, int32_t k, float* out_scores,
+                               int32_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (k > TOPKS_MAX_K) PXR_FAIL(h, PXR_ERR_INVALID, "k=%d exceeds %d", k, TOPKS_MAX_K);
+  ScoreParams p;
+  fill_score_params(h, p);
+  p.user_emb = user_embedding; p.user_idx = user_idx; p.seen_indptr = seen_indptr; p.seen_idx = seen_idx;
+  TopkSimtParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.n_users = n_users; tp.k = k; tp.S = topk_simt_splits(h, n_users, k);
+  tp.rows_per_split = (h->n_rows + tp.S - 1) / tp.S;
+  tp.out_scores = out_scores; tp.out_idx = out_idx;
+  if (tp.S > 1) {
+    const size_t need = (size_t)tp.S * n_users * k;
+    if (ws_bytes < need * 8) PXR_FAIL(h, PXR_ERR_WORKSPACE, "top-K workspace too small");
+    tp.out_scores = (float*)ws; tp.out_idx = (int32_t*)((char*)ws + need * 4);
+  }
+  int rc;
+  switch (topk_simt_rows(h, k)) {
+    case 32: rc = launch_score_topk<32>(h, p, tp, st); break;
+    case 16: rc = launch_score_topk<16>(h, p, tp, st); break;
+    case 8: rc = launch_score_topk<8>(h, p, tp, st); break;
+    case 4: rc = launch_score_topk<4>(h, p, tp, st); break;
+    default: PXR_FAIL(h, PXR_ERR_INVALID, "layer dims / top_k too large for the SIMT scoring kernel");
+  }
+  if (rc) return rc;
+  if (tp.S > 1) {
+    rc = pxr_launch_merge(tp.out_scores, tp.out_idx, tp.S, n_users, k, out_scores, out_idx, st);
+    h->launches++;
+    if (rc) PXR_FAIL(h, rc, "top-K merge of %d item splits failed", tp.S);
+  }
+  return PXR_OK;
 }
 
 // ===========================================================================
@@ -694,7 +846,7 @@ int pxr_launch_rescore(pxr_handle* h, const float* user_embedding, const int64_t
   rescore_prep_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(user_idx, list_idx, n_pairs, 64, h->item_base, pair_user, pair_row);
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
-  const int rc = pxr_launch_score_simt(h, user_embedding, pair_user, pair_row, n_pairs, 0, nullptr, nullptr, resc, nullptr, false, st);
+  const int rc = pxr_launch_score_simt(h, user_embedding, pair_user, pair_row, n_pairs, resc, nullptr, st);
   if (rc) return rc;
   rescore_sort_kernel<<<(unsigned)((n_users + 7) / 8), 256, 0, st>>>(resc, list_idx, n_users, k, out_scores, out_idx);
   h->launches++;

@@ -6,6 +6,7 @@ touches a score is in libpxr.so.
 from __future__ import annotations
 
 import ctypes as C
+import logging
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -92,6 +93,12 @@ class PxrEngine:
         if rc != 0:
             raise PxrError(f"pxr_create failed ({rc}): {self.lib.pxr_last_error(None).decode()}")
         self.set_rescore(rescore)
+        if path == "auto" and self.active_path != "tcgen05":
+            # never silent: the generic kernels are a correctness path, two orders of magnitude slower
+            logging.getLogger(__name__).warning(
+                "PxrEngine: the fused tcgen05 kernel does not cover this model configuration (%s); scoring runs on the generic "
+                "fp32 SIMT kernels (exact, ~100x slower)", self.path_reason)
+        self._warned_k = False
         self._keep: Dict[str, object] = {}
         self._items_ws: Optional[torch.Tensor] = None
         self._score_ws: Optional[torch.Tensor] = None
@@ -122,6 +129,11 @@ class PxrEngine:
     @property
     def active_path(self) -> str:
         return {1: "simt", 2: "tcgen05"}.get(self.lib.pxr_active_path(self._h), "?")
+
+    @property
+    def path_reason(self) -> str:
+        """Why the generic SIMT kernels are active ('' on the fused path)."""
+        return self.lib.pxr_path_reason(self._h).decode()
 
     def profile(self, on: bool = True):
         """Time the dominant kernel with CUDA events on the launching stream."""
@@ -281,6 +293,11 @@ class PxrEngine:
             if seen_indptr.shape[0] != user_idx.shape[0] + 1:
                 raise ValueError("seen_indptr must have n_users + 1 entries")
         n = int(user_idx.shape[0])
+        if k > 64 and self.active_path == "tcgen05" and not self._warned_k:
+            self._warned_k = True
+            logging.getLogger(__name__).warning(
+                "PxrEngine.score_topk: top_k=%d exceeds the 64 list slots of the fused tcgen05 kernel; this call runs on the "
+                "generic fp32 SIMT kernels (exact, ~100x slower)", k)
         out_s = torch.empty((n, k), dtype=torch.float32, device=dev)
         out_i = torch.empty((n, k), dtype=torch.int32, device=dev)
         nbytes = int(self.lib.pxr_score_topk_bytes(self._h, n, k))

@@ -206,6 +206,25 @@ def test_topk_edge_cases():
     assert np.all(i.cpu().numpy() == -1) and np.all(np.isneginf(s.cpu().numpy()))
 
 
+@pytest.mark.parametrize("fusion,n_users,n_items,k,path", [
+    ("gated", 3, 900, 100, "simt"), ("concatenate", 70, 333, 200, "simt"), ("attention", 2, 40, 64, "simt"),
+    ("gated", 5, 700, 128, "auto"), ("gated", 400, 64, 10, "simt")])
+def test_generic_path_keeps_topk_on_chip(fusion, n_users, n_items, k, path):
+    """The generic fp32 path (any K up to 1 024, any shape; what a tcgen05 handle uses for top_k > 64): per-user blocks
+    sweep the catalogue and keep the running top-K in shared memory (score_topk_simt_kernel) -- no users x items score
+    matrix in HBM; few users => the item range is split over several blocks and merged by K4.  == oracle, ties -> lower
+    index, K larger than the catalogue -> padded tail."""
+    spec, sd, feats, indptr, idx, _ = _topk_case(fusion, path, n_users=n_users, n_items=n_items, seed_off=k)
+    model, eng = _engine_for(spec, sd, feats, path)
+    users = np.arange(n_users)
+    ref = orc.score_block(sd, cs.spec_cfg(spec), users, 0, n_items, feats, dtype=np.float64)
+    s, i = eng.score_topk(model.user_embedding.weight.detach(), torch.from_numpy(users).cuda(), k,
+                          torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda())
+    s, i = _structural_checks(s, i, k, n_items, indptr, idx)
+    for u in users:
+        _check_topk(s[u].astype(np.float64), i[u], ref[u], k, idx[indptr[u]:indptr[u + 1]], SIMT_TOL, 0.0)
+
+
 def test_merge_topk_with_ties():
     from pixelrec_multimodal_b200.engine import merge_topk
     rng = np.random.default_rng(9)
