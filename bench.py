@@ -310,6 +310,12 @@ def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: i
     rec = FastRecommender(model, _DS(), dev, item_features=store, n_users=NU, n_items=NI,
                           history=(hist["train_indptr"], hist["train_idx"]), item_range=(lo, hi), user_block=B)
     eng = rec.engine()
+    # exact mode across item shards: the shards exchange their raw 64-slot lists and the rank that owns a user re-scores the
+    # merged candidates against fp32 records of the whole catalogue (1 280 B per item, kept by every rank)
+    rs_eng = rec.rescore_engine() if item_sharded else None
+    K_EX = 64 if item_sharded else TOP_K
+    if item_sharded:
+        eng.set_rescore(False)
     torch.cuda.synchronize()
 
     n_blocks = max(1, NU // B)
@@ -333,8 +339,16 @@ def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: i
     def score_block(s):
         """inputs already in HBM: the block's user indices and the resident history CSR"""
         u0, n, n_job = block_users(s)
-        sc, ix = eng.score_topk(uemb, all_users[u0:u0 + n], TOP_K, d_indptr[u0:u0 + n + 1], d_idx)
+        sc, ix = eng.score_topk(uemb, all_users[u0:u0 + n], K_EX, d_indptr[u0:u0 + n + 1], d_idx)
         return sc, ix, n_job
+
+    def finish_owned(pending):
+        """merge the shards' raw lists of the users this rank owns, then the fp32 re-score of the merged candidates"""
+        handle, u0, n = pending
+        ms_, mi_ = merge_topk(*exchange_owned_finish(handle))
+        a, z = owned_slice(n, world, rank)
+        merges[0] += 1
+        return rs_eng.rescore_topk(uemb, all_users[u0 + a:u0 + z], mi_, TOP_K) if z > a else (ms_[:, :TOP_K], mi_[:, :TOP_K])
 
     def run_steps(first, count):
         """`count` steps.  Item shards: the all-to-all of step s (one packed collective on NCCL's stream) overlaps the
@@ -347,11 +361,11 @@ def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: i
             if item_sharded:
                 handle = exchange_owned_start(sc, ix)
                 if pending is not None:
-                    merge_topk(*exchange_owned_finish(pending)); merges[0] += 1
-                pending = handle
+                    finish_owned(pending)
+                pending = (handle, block_users(s)[0], n)
             flush.zero_()                                         # L2 flush between steps (inside the timed region)
         if pending is not None:
-            merge_topk(*exchange_owned_finish(pending)); merges[0] += 1
+            finish_owned(pending)
         return users
 
     run_steps(0, warmup)
@@ -360,7 +374,7 @@ def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: i
         dist.barrier()
     torch.cuda.synchronize()
     eng.profile(True)
-    launches0 = eng.launch_count
+    launches0 = eng.launch_count + (rs_eng.launch_count if rs_eng is not None else 0)
     merges[0] = 0
     sampler = ClockSampler(dev.index)
     sampler.start()
@@ -376,7 +390,7 @@ def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: i
     ms = e0.elapsed_time(e1)
     k_ms, k_n = eng.profile_read()
     eng.profile(False)
-    launches = eng.launch_count - launches0 + merges[0]
+    launches = eng.launch_count + (rs_eng.launch_count if rs_eng is not None else 0) - launches0 + merges[0]
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -393,9 +407,9 @@ def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: i
         h_users = [host_users(s) for s in range(steps)]
 
         def step_e2e(users_np):
-            sc, ix = rec.recommend_all(users_np, top_k=TOP_K, filter_seen=True)
+            sc, ix = rec.recommend_all(users_np, top_k=K_EX, filter_seen=True)
             if item_sharded:                                      # every rank scored the whole block against its shard
-                sc, ix = merge_topk(*exchange_owned_finish(exchange_owned_start(sc, ix)))
+                sc, ix = finish_owned((exchange_owned_start(sc, ix), int(users_np[0]), len(users_np)))
             return sc.cpu(), ix.cpu()                             # the lists of the users this rank owns
         step_e2e(h_users[0])
         torch.cuda.synchronize()
@@ -421,7 +435,7 @@ def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: i
 
     # ---- checks outside the timed region
     checks = {}
-    if with_checks and eng.active_path == "tcgen05":
+    if with_checks and eng.active_path == "tcgen05" and not item_sharded:
         # raw 16-bit lists vs the exact-mode lists (fp32 re-scored) of the same users on this rank's item range
         u0, n, _ = block_users(warmup)
         nu = min(256, n)
@@ -439,32 +453,32 @@ def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: i
             "note": "exact mode (default): the 64 candidates the 16-bit kernel keeps per user are re-scored with the fp32 arithmetic of "
                     "forward() and re-ranked; tests/test_gpu_parity.py::test_catalogue_scale_parity checks both against the exact forward"}
     if with_checks and item_sharded:
-        # merged sharded lists == the unsharded lists of rank 0, bit for bit (raw 16-bit lists: the per-pair arithmetic does not
-        # depend on the tiling; exact mode re-scores per shard, so its candidate sets may differ in rare near-ties)
+        # merged sharded lists == the unsharded lists of rank 0, bit for bit: the raw 16-bit lists (the per-pair arithmetic does
+        # not depend on the tiling) and the exact-mode lists (same global candidates, same fp32 records)
+        from pixelrec_multimodal_b200.sharding import gather_owned
         nu = 64
         uu = all_users[:nu]
-        res = {}
-        for mode in ("raw", "exact"):
-            eng.set_rescore(mode == "exact")
-            sc, ix = eng.score_topk(uemb, uu, TOP_K, d_indptr[:nu + 1], d_idx)
-            gs = [torch.empty_like(sc) for _ in range(world)]; gi = [torch.empty_like(ix) for _ in range(world)]
-            dist.all_gather(gs, sc); dist.all_gather(gi, ix)
-            res[mode] = merge_topk(torch.stack(gs), torch.stack(gi))
-        eng.set_rescore(True)
+        sc, ix = eng.score_topk(uemb, uu, K_EX, d_indptr[:nu + 1], d_idx)
+        ms_, mi_ = merge_topk(*exchange_owned_finish(exchange_owned_start(sc, ix)))
+        a, z = owned_slice(nu, world, rank)
+        xs_, xi_ = rs_eng.rescore_topk(uemb, uu[a:z], mi_, TOP_K)
+        raw_s, raw_i = gather_owned(ms_, mi_, nu)
+        ex_s, ex_i = gather_owned(xs_, xi_, nu)
         if rank == 0:
             full_model = make_model()
             full = FastRecommender(full_model, _DS(), dev, item_features=store, n_users=NU, n_items=NI,
                                    history=(hist["train_indptr"], hist["train_idx"]), user_block=B)
             fe = full.engine()
-            out = {}
-            for mode in ("raw", "exact"):
-                fe.set_rescore(mode == "exact")
-                fs, fi = fe.score_topk(full_model.user_embedding.weight.detach(), uu, TOP_K, d_indptr[:nu + 1], d_idx)
-                out[mode] = (bool(torch.equal(fi, res[mode][1]) and torch.equal(fs, res[mode][0])),
-                             int((fi == res[mode][1]).all(dim=1).sum()))
-            checks["shard_check"] = "ok" if out["raw"][0] else "MISMATCH"
-            checks["shard_check_detail"] = {"users": nu, "raw16_lists_bit_identical": out["raw"][0],
-                                            "exact_mode_users_identical": out["exact"][1]}
+            fu = full_model.user_embedding.weight.detach()
+            fe.set_rescore(False)
+            fs, fi = fe.score_topk(fu, uu, K_EX, d_indptr[:nu + 1], d_idx)
+            raw_ok = bool(torch.equal(fi, raw_i) and torch.equal(fs, raw_s))
+            fe.set_rescore(True)
+            fs, fi = fe.score_topk(fu, uu, TOP_K, d_indptr[:nu + 1], d_idx)
+            exact_ok = bool(torch.equal(fi, ex_i) and torch.equal(fs, ex_s))
+            checks["shard_check"] = "ok" if (raw_ok and exact_ok) else "MISMATCH"
+            checks["shard_check_detail"] = {"users": nu, "raw16_top64_lists_bit_identical": raw_ok, "exact_top50_lists_bit_identical": exact_ok,
+                                            "exact_users_identical": int((fi == ex_i).all(dim=1).sum())}
             del full, fe, full_model
         dist.barrier()
 
@@ -487,7 +501,7 @@ def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: i
             "dtype": "bf16" if eng.active_path == "tcgen05" else "f32", "data": "synthetic",
             "users_per_sec": value / NI,
             "config": config_dict(cfg_name, world, args.user_block, shard),
-            "run": {"items_per_rank": hi - lo, "kernel_path": eng.active_path, "exact_rescore": bool(eng.rescore),
+            "run": {"items_per_rank": hi - lo, "kernel_path": eng.active_path, "exact_rescore": bool(eng.rescore) or item_sharded,
                     "shard_axis": shard if world > 1 else None},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if e2e is not None:
@@ -500,7 +514,7 @@ def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: i
             lit = cpu_literal(cfg_name, args.literal_seconds, args.seed)
             line["cpu_baseline"].update(literal_value=lit["value"], literal_users_per_sec=lit["users_per_sec"], literal_sample=lit["sample"])
     # free this configuration's device memory before the next one
-    del rec, eng, model, store, feats, hist, sd, flush, uemb, d_indptr, d_idx, all_users
+    del rec, eng, rs_eng, model, store, feats, hist, sd, flush, uemb, d_indptr, d_idx, all_users
     torch.cuda.empty_cache()
     return line
 

@@ -167,6 +167,24 @@ int pxr_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* us
 int pxr_set_rescore(pxr_handle* h, int on);
 int pxr_get_rescore(const pxr_handle* h);
 
+/* The re-score step of exact mode on its own: candidate lists (for instance the merged 16-bit top-64 lists of several item
+ * shards) are scored with the fp32 arithmetic of pxr_score_pairs against the records of THIS handle and ranked (ties ->
+ * lower item index); the first K come back.  Under item-axis sharding the exchange carries the raw 64-slot lists and the
+ * rank that owns a user re-scores the merged list once, against fp32 records of the whole catalogue (1 280 B per item),
+ * instead of every shard re-scoring its own 64 candidates of every user.
+ *   cand_idx : (n_users, 64) int32 GLOBAL item indices inside [item_base, item_base + n_rows) of this handle, -1 padded
+ *   out_*    : (n_users, K), K <= 64, padded with -inf / -1 ;  workspace : pxr_rescore_bytes(n_users) bytes */
+size_t pxr_rescore_bytes(int64_t n_users);
+int pxr_rescore_topk(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
+                     const int32_t* cand_idx, int32_t k, float* out_scores, int32_t* out_idx, void* workspace,
+                     size_t workspace_bytes, pxr_stream stream);
+
+/* on = 1: pxr_precompute_items of this handle keeps only the fp32 item records (1 280 B per item at D = 64) and skips the
+ * fused kernel's per-item extras (up to 16.5 KB per item for attention): for a handle that only serves pxr_rescore_topk /
+ * pxr_score_pairs, e.g. the whole-catalogue re-score records every rank of an item-sharded job keeps.  Call before
+ * pxr_precompute_items. */
+int pxr_set_records_only(pxr_handle* h, int on);
+
 /* Scores of explicit (user, item-row) pairs against the precomputed records.
  * Replaces MultimodalRecommender.forward (src/models/multimodal.py:528-610),
  * Recommender._score_items_batch / get_item_score and the candidate-list mode

@@ -238,7 +238,8 @@ def cmd_evaluate(args) -> Dict:
     sharded = None
     if world > 1:
         from .sharding import ShardedTopK
-        sharded = ShardedTopK(lambda users, k, fs: rec.recommend_all(users, top_k=k, filter_seen=fs))
+        # exact mode across shards: raw 64-slot lists are exchanged, the owning rank re-scores the merged candidates
+        sharded = ShardedTopK(lambda users, k, fs: rec.recommend_all(users, top_k=k, filter_seen=fs, raw=True), rescore=rec.rescore)
     if ranking:                                             # evaluate.py:402-408: sampling is a retrieval-only switch
         ev = RankingEvaluator(rec, test, top_k=top_k, keep_predictions=bool(args.save_predictions))
     elif args.use_sampling:

@@ -87,6 +87,12 @@ extern "C" int pxr_set_rescore(pxr_handle* h, int on) {
   return PXR_OK;
 }
 extern "C" int pxr_get_rescore(const pxr_handle* h) { return h ? (h->rescore ? 1 : 0) : PXR_ERR_INVALID; }
+extern "C" int pxr_set_records_only(pxr_handle* h, int on) {
+  if (!h) return PXR_ERR_INVALID;
+  h->records_only = on != 0;
+  h->items_ready = false;                 // the item workspace layout changes: pxr_precompute_items must run again
+  return PXR_OK;
+}
 extern "C" int pxr_set_path(pxr_handle* h, int path) {
   if (!h) return PXR_ERR_INVALID;
   if (path == PXR_PATH_TCGEN05 && !h->fast_ok) PXR_FAIL(h, PXR_ERR_INVALID, "tcgen05 path not supported for this configuration");
@@ -228,7 +234,7 @@ static size_t feats_bytes(const pxr_handle* h, int64_t n_rows) {
 
 extern "C" size_t pxr_items_bytes(const pxr_handle* h, int64_t n_rows) {
   if (!h || n_rows < 0) return 0;
-  return feats_bytes(h, n_rows) + (h->fast_ok ? pxr_tc_item_bytes(h, n_rows) : 0) + 256;
+  return feats_bytes(h, n_rows) + ((h->fast_ok && !h->records_only) ? pxr_tc_item_bytes(h, n_rows) : 0) + 256;
 }
 
 extern "C" int pxr_precompute_items(pxr_handle* h, const float* item_embedding, const int64_t* item_idx,
@@ -250,7 +256,7 @@ extern "C" int pxr_precompute_items(pxr_handle* h, const float* item_embedding, 
   int rc = items_tc ? pxr_launch_items_tc(h, item_embedding, item_idx, tag_idx, vis, txt, num, n_rows, item_base, h->item_feats, st)
                     : pxr_launch_items_simt(h, item_embedding, item_idx, tag_idx, vis, txt, num, n_rows, item_base, h->item_feats, st);
   if (rc) return rc;
-  if (h->fast_ok) return pxr_tc_prepare_items(h, n_rows, h->item_fast, st);
+  if (h->fast_ok && !h->records_only) return pxr_tc_prepare_items(h, n_rows, h->item_fast, st);
   return PXR_OK;
 }
 
@@ -266,7 +272,7 @@ extern "C" int pxr_set_missing_items(pxr_handle* h, const uint8_t* flags, int64_
 // ---------------------------------------------------------------------------
 extern "C" size_t pxr_score_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k) {
   if (!h || n_users <= 0) return 256;
-  if (h->path == PXR_PATH_TCGEN05 && pxr_tc_can_run(h, k)) return pxr_tc_topk_bytes(h, n_users, k) + 256;
+  if (h->path == PXR_PATH_TCGEN05 && !h->records_only && pxr_tc_can_run(h, k)) return pxr_tc_topk_bytes(h, n_users, k) + 256;
   return pxr_simt_topk_bytes(h, n_users, k) + 256;
 }
 
@@ -281,7 +287,7 @@ extern "C" int pxr_score_topk(pxr_handle* h, const float* user_embedding, const 
   if (n_users == 0) return PXR_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (workspace_bytes < pxr_score_topk_bytes(h, n_users, k)) PXR_FAIL(h, PXR_ERR_WORKSPACE, "score workspace too small: %zu < %zu", workspace_bytes, pxr_score_topk_bytes(h, n_users, k));
-  if (h->path == PXR_PATH_TCGEN05 && pxr_tc_can_run(h, k))
+  if (h->path == PXR_PATH_TCGEN05 && !h->records_only && pxr_tc_can_run(h, k))
     return pxr_tc_score_topk(h, user_embedding, user_idx, n_users, seen_indptr, seen_idx, k, out_scores, out_idx, workspace, workspace_bytes, st);
   if (h->n_rows == 0) {   // empty catalogue shard: every list is padding
     PXR_CUDA(h, cudaMemsetAsync(out_idx, 0xFF, sizeof(int32_t) * n_users * k, st));
@@ -299,6 +305,20 @@ extern "C" int pxr_score_pairs(pxr_handle* h, const float* user_embedding, const
   if (!h->weights_loaded || !h->items_ready || !h->item_feats) PXR_FAIL(h, PXR_ERR_STATE, "weights / items not loaded");
   if (n < 0 || (n && (!user_embedding || !user_idx || !item_row || !out))) PXR_FAIL(h, PXR_ERR_INVALID, "pxr_score_pairs: bad arguments");
   return pxr_launch_score_simt(h, user_embedding, user_idx, item_row, n, out, out_logit, (cudaStream_t)stream);
+}
+
+extern "C" size_t pxr_rescore_bytes(int64_t n_users) { return n_users > 0 ? pxr_rescore_list_bytes(n_users) + 256 : 256; }
+
+extern "C" int pxr_rescore_topk(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
+                                const int32_t* cand_idx, int32_t k, float* out_scores, int32_t* out_idx, void* workspace,
+                                size_t workspace_bytes, pxr_stream stream) {
+  if (!h) return PXR_ERR_INVALID;
+  if (!h->weights_loaded || !h->items_ready || !h->item_feats) PXR_FAIL(h, PXR_ERR_STATE, "weights / items not loaded");
+  if (k <= 0 || k > 64 || n_users < 0 || (n_users && (!user_embedding || !user_idx || !cand_idx || !out_scores || !out_idx)))
+    PXR_FAIL(h, PXR_ERR_INVALID, "pxr_rescore_topk: bad arguments (1 <= k <= 64)");
+  if (n_users == 0) return PXR_OK;
+  if (workspace_bytes < pxr_rescore_bytes(n_users) || !workspace) PXR_FAIL(h, PXR_ERR_WORKSPACE, "re-score workspace too small");
+  return pxr_launch_rescore(h, user_embedding, user_idx, n_users, cand_idx, k, out_scores, out_idx, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int pxr_merge_topk(const float* scores_in, const int32_t* idx_in, int32_t n_shards, int64_t n_users,

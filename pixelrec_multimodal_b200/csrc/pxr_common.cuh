@@ -48,6 +48,7 @@ struct pxr_handle {
 
   // fast (tcgen05) path images
   bool fast_ok = false;
+  bool records_only = false;  // pxr_set_records_only: keep only the fp32 item records (a handle used for re-scoring / explicit pairs)
   bool rescore = true;        // exact mode of the fused path: fp32 re-score + re-rank of the 64-slot lists (pxr_set_rescore)
   uint32_t tc_attr_set = 0;   // bit per kernel whose max-dynamic-smem attribute has been set
   void* fast_w = nullptr;     // bf16 swizzled operand images + fp32 vectors (see score_tc.cu)
@@ -229,7 +230,7 @@ int pxr_launch_topk_rows(pxr_handle* h, const float* scores, int64_t n_users, in
 int pxr_launch_merge(const float* scores_in, const int32_t* idx_in, int32_t n_shards, int64_t n_users, int32_t k,
                      float* out_scores, int32_t* out_idx, cudaStream_t st);
 // exact mode: fp32 re-score + re-rank of (n_users, 64) candidate lists (global indices, -1 padded) -> (n_users, k)
-size_t pxr_rescore_bytes(int64_t n_users);
+size_t pxr_rescore_list_bytes(int64_t n_users);
 int pxr_launch_rescore(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
                        const int32_t* list_idx, int32_t k, float* out_scores, int32_t* out_idx, void* ws, cudaStream_t st);
 int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, const int64_t* gt_indptr,

@@ -263,10 +263,27 @@ __device__ __forceinline__ void concat_h1_chunk(const uint8_t* pi_row, const uin
 // sum y^2, and the rstd-weighted token sum: ~95 warp instructions per pair instead of ~360 for the all-CUDA-core form.
 // A front-end warp owns one item x 16 users at a time (tile = 8 items x 16 users, two items per warp).
 // ---------------------------------------------------------------------------------------------
+// experiment switches of the attention front end (scripts/ab_build.sh -DPXR_ATT_...=1)
+#ifndef PXR_ATT_REC_L1
+#define PXR_ATT_REC_L1 0        // 1: record fragments allocate in L1 (plain ld.global.nc) instead of streaming past it
+#endif
+#ifndef PXR_ATT_WCBATCH
+#define PXR_ATT_WCBATCH 0       // 1: the four Wc fragment loads of a k-step are issued before its eight MMAs
+#endif
+#ifndef PXR_ATT_NOPF
+#define PXR_ATT_NOPF 0          // 1: no L1 / L2 prefetches
+#endif
+#ifndef PXR_ATT_PFS
+#define PXR_ATT_PFS 0           // 1: the score fragments of the next tile's item are prefetched into L1 at the end of a step
+#endif
 __device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {      // item records: read once per (item, 16 users), keep them out of L1
+#if PXR_ATT_REC_L1
+  return __ldg(p);
+#else
   uint4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
+#endif
 }
 template <int FMT>
 __device__ __forceinline__ void hmma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -384,12 +401,23 @@ __device__ __forceinline__ void attn_wo_pass(float (&Y)[8][4], const uint32_t (&
     uint32_t a[4];
     a[0] = mul2<FMT>(lo, U.vu[h][0]); a[1] = mul2<FMT>(hi, U.vu[h][1]);
     a[2] = mul2<FMT>(lo, U.vu[h][2]); a[3] = mul2<FMT>(hi, U.vu[h][3]);
+#if PXR_ATT_WCBATCH
+    uint4 w[4];
+#pragma unroll
+    for (int np = 0; np < 4; ++np) w[np] = __ldg(wo + (h * 4 + np) * 32 + lane);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      hmma<FMT>(Y[2 * np], a, w[np].x, w[np].y);
+      hmma<FMT>(Y[2 * np + 1], a, w[np].z, w[np].w);
+    }
+#else
 #pragma unroll
     for (int np = 0; np < 4; ++np) {
       const uint4 w = __ldg(wo + (h * 4 + np) * 32 + lane);
       hmma<FMT>(Y[2 * np], a, w.x, w.y);
       hmma<FMT>(Y[2 * np + 1], a, w.z, w.w);
     }
+#endif
   }
 }
 
@@ -437,14 +465,14 @@ __device__ __forceinline__ void attn_item_step(const AttnUserFrag& U, const uint
                                                const uint4* __restrict__ wo, const uint4* __restrict__ scr, int nt, int lane,
                                                float (&acc)[8][4]) {
   const int t = lane & 3;
-  if (rec_next) {                                                                        // next tile's record -> L2 (129 lines of 128 B)
+  if (rec_next && !PXR_ATT_NOPF) {                                                       // next tile's record -> L2 (129 lines of 128 B)
     const char* pn = reinterpret_cast<const char*>(rec_next) + lane * 128;
 #pragma unroll
     for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + i * 4096));
     if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + 16384));
   }
   auto prefetch_tail = [&](int a) {                                                      // token a's tail fragments (2 KB) -> L1
-    if (lane < 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(rec + REC_T + a * 128) + lane * 128));
+    if (lane < 16 && !PXR_ATT_NOPF) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(rec + REC_T + a * 128) + lane * 128));
   };
   uint32_t wpk[2][NH];                                     // sigmoid weights of tokens 2t / 2t + 1: (row g, row g + 8) packed
   float Y[8][4];
@@ -517,6 +545,9 @@ __device__ __forceinline__ void attn_item_step(const AttnUserFrag& U, const uint
     attn_wo_pass<FMT>(Y, x, U, wo, lane);
     attn_norm_acc<false>(Y, acc);
   }
+#if PXR_ATT_PFS
+  if (rec_next && lane < 17) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(rec_next + REC_S) + lane * 128));
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1552,7 +1583,7 @@ size_t pxr_tc_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k) {
   const int kk = h->rescore ? tc::KCAP : k;
   size_t b = 256;
   if (pl.S > 1) b += pxr_align_up((size_t)pl.S * n_users * kk * 8, 256);
-  if (h->rescore) b += pxr_align_up((size_t)n_users * kk * 8, 256) + pxr_rescore_bytes(n_users);
+  if (h->rescore) b += pxr_align_up((size_t)n_users * kk * 8, 256) + pxr_rescore_list_bytes(n_users);
   return b;
 }
 

@@ -792,12 +792,15 @@ int pxr_launch_merge(const float* scores_in, const int32_t* idx_in, int32_t n_sh
 // again with the reference's tie-break (stable sort over index order, recommender.py:105 -> lower index first).
 // ===========================================================================
 __global__ void rescore_prep_kernel(const int64_t* __restrict__ user_idx, const int32_t* __restrict__ list_idx, int64_t n_pairs,
-                                    int L, int64_t item_base, int64_t* __restrict__ pair_user, int64_t* __restrict__ pair_row) {
+                                    int L, int64_t item_base, int64_t n_rows, int64_t* __restrict__ pair_user,
+                                    int64_t* __restrict__ pair_row) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pairs) return;
   const int32_t gi = list_idx[i];
-  pair_user[i] = gi < 0 ? -1 : user_idx[i / L];     // -1: padding slot, score_simt_kernel computes on zeros and the sort drops it
-  pair_row[i] = gi < 0 ? 0 : (int64_t)gi - item_base;
+  const int64_t r = (int64_t)gi - item_base;
+  const bool ok = gi >= 0 && r >= 0 && r < n_rows;
+  pair_user[i] = ok ? user_idx[i / L] : -1;        // -1: padding slot, score_simt_kernel computes on zeros and the sort drops it
+  pair_row[i] = ok ? r : 0;
 }
 
 // full bitonic sort (descending) of 64 keys held two per lane: slot lane in x0, slot lane + 32 in x1
@@ -821,20 +824,21 @@ __device__ __forceinline__ void sort64_desc(unsigned long long& x0, unsigned lon
 }
 
 __global__ void __launch_bounds__(256) rescore_sort_kernel(const float* __restrict__ rescored, const int32_t* __restrict__ list_idx,
-                                                           int64_t n_users, int k, float* __restrict__ out_scores,
-                                                           int32_t* __restrict__ out_idx) {
+                                                           int64_t n_users, int k, int64_t item_base, int64_t n_rows,
+                                                           float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
   const int lane = threadIdx.x & 31;
   const int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (u >= n_users) return;
   const int32_t i0 = list_idx[u * 64 + lane], i1 = list_idx[u * 64 + 32 + lane];
-  unsigned long long x0 = i0 < 0 ? 0ull : pxr_key(rescored[u * 64 + lane], (uint32_t)i0);
-  unsigned long long x1 = i1 < 0 ? 0ull : pxr_key(rescored[u * 64 + 32 + lane], (uint32_t)i1);
+  const bool ok0 = i0 >= 0 && i0 >= item_base && i0 < item_base + n_rows, ok1 = i1 >= 0 && i1 >= item_base && i1 < item_base + n_rows;
+  unsigned long long x0 = ok0 ? pxr_key(rescored[u * 64 + lane], (uint32_t)i0) : 0ull;
+  unsigned long long x1 = ok1 ? pxr_key(rescored[u * 64 + 32 + lane], (uint32_t)i1) : 0ull;
   sort64_desc(x0, x1, lane);
   if (lane < k) { out_scores[u * k + lane] = x0 ? pxr_key_score(x0) : -INFINITY; out_idx[u * k + lane] = x0 ? (int32_t)pxr_key_idx(x0) : -1; }
   if (lane + 32 < k) { out_scores[u * k + lane + 32] = x1 ? pxr_key_score(x1) : -INFINITY; out_idx[u * k + lane + 32] = x1 ? (int32_t)pxr_key_idx(x1) : -1; }
 }
 
-size_t pxr_rescore_bytes(int64_t n_users) { return pxr_align_up((size_t)n_users * 64 * (8 + 8 + 4), 256); }
+size_t pxr_rescore_list_bytes(int64_t n_users) { return pxr_align_up((size_t)n_users * 64 * (8 + 8 + 4), 256); }
 
 int pxr_launch_rescore(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
                        const int32_t* list_idx, int32_t k, float* out_scores, int32_t* out_idx, void* ws, cudaStream_t st) {
@@ -843,12 +847,12 @@ int pxr_launch_rescore(pxr_handle* h, const float* user_embedding, const int64_t
   int64_t* pair_user = (int64_t*)ws;
   int64_t* pair_row = pair_user + n_pairs;
   float* resc = (float*)(pair_row + n_pairs);
-  rescore_prep_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(user_idx, list_idx, n_pairs, 64, h->item_base, pair_user, pair_row);
+  rescore_prep_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(user_idx, list_idx, n_pairs, 64, h->item_base, h->n_rows, pair_user, pair_row);
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
   const int rc = pxr_launch_score_simt(h, user_embedding, pair_user, pair_row, n_pairs, resc, nullptr, st);
   if (rc) return rc;
-  rescore_sort_kernel<<<(unsigned)((n_users + 7) / 8), 256, 0, st>>>(resc, list_idx, n_users, k, out_scores, out_idx);
+  rescore_sort_kernel<<<(unsigned)((n_users + 7) / 8), 256, 0, st>>>(resc, list_idx, n_users, k, h->item_base, h->n_rows, out_scores, out_idx);
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
   return PXR_OK;

@@ -154,6 +154,11 @@ class PxrEngine:
     def rescore(self) -> bool:
         return bool(self.lib.pxr_get_rescore(self._h))
 
+    def set_records_only(self, on: bool = True):
+        """Keep only the fp32 item records at the next ``precompute_items`` (a handle that serves ``rescore_topk`` /
+        ``score_pairs`` only, e.g. the whole-catalogue re-score records of an item-sharded rank)."""
+        self._check(self.lib.pxr_set_records_only(self._h, int(bool(on))), "pxr_set_records_only")
+
     def set_path(self, path: str):
         self._check(self.lib.pxr_set_path(self._h, _lib.PATH[path]), "pxr_set_path")
 
@@ -310,6 +315,27 @@ class PxrEngine:
                 self._h, _ptr(user_embedding), _ptr(user_idx), n, _ptr(seen_indptr), _ptr(seen_idx), k,
                 _ptr(out_s), _ptr(out_i), C.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream()),
                 "pxr_score_topk")
+        return out_s, out_i
+
+    def rescore_topk(self, user_embedding: torch.Tensor, user_idx: torch.Tensor, cand_idx: torch.Tensor, k: int
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The re-score step of exact mode on its own (``pxr_rescore_topk``): (n, 64) candidate lists of GLOBAL item
+        indices (-1 padded) -> the K best by the fp32 arithmetic of ``score_pairs`` against this engine's records."""
+        dev = self.device
+        user_embedding, user_idx = self._user_args(user_embedding, user_idx)
+        cand = _dev_idx(cand_idx, dev, torch.int32)
+        n = int(user_idx.shape[0])
+        if cand.shape != (n, 64):
+            raise ValueError(f"cand_idx must be ({n}, 64), got {tuple(cand.shape)}")
+        out_s = torch.empty((n, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((n, k), dtype=torch.int32, device=dev)
+        nbytes = int(self.lib.pxr_rescore_bytes(n))
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 256
+        with torch.cuda.device(dev):
+            self._check(self.lib.pxr_rescore_topk(self._h, _ptr(user_embedding), _ptr(user_idx), n, _ptr(cand), int(k), _ptr(out_s),
+                                                  _ptr(out_i), C.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream()),
+                        "pxr_rescore_topk")
         return out_s, out_i
 
     def score_pairs(self, user_embedding: torch.Tensor, user_idx: torch.Tensor, item_row: torch.Tensor,

@@ -348,25 +348,29 @@ class FullCatalogueEvaluator:
             out["avg_intra_list_similarity"] = intra_list_similarity(lists, engine=r.engine())   # novelty.py:295-340, tasks.py:695-701
         return out
 
-    def _evaluate_sharded(self, kmax: int):
-        """Item-sharded ranks in lock step; returns (scores, idx) of all users (every rank holds the merged lists) and
-        ``by_k`` from all-reduced metric sums."""
+    def _evaluate_sharded(self, kmax: int, want_lists: bool):
+        """Item-sharded ranks in lock step: every rank ends up with the final lists of the users it owns in each block
+        (``ShardedTopK.recommend_blocks_owned``), computes their metric sums, and ONE all-reduce of the (n_ks, 9) float64
+        sums closes the evaluation.  ``want_lists``: also gather the lists (predictions / novelty)."""
         import torch.distributed as dist
+        from .sharding import gather_owned, owned_slice
         world, rank = dist.get_world_size(self.sharded.group), dist.get_rank(self.sharded.group)
         n = len(self.users)
         blocks = [self.users[i:i + self.user_block] for i in range(0, n, self.user_block)]
         sums = np.zeros((len(self.ks), len(_COLS)))
         outs_s, outs_i, row = [], [], 0
-        for (s, i), blk in zip(self.sharded.recommend_blocks(blocks, kmax, self.filter_seen), blocks):
-            per = (len(blk) + world - 1) // world               # this rank's slice of the block
-            lo, hi = min(len(blk), rank * per), min(len(blk), (rank + 1) * per)
+        for (s, i), blk in zip(self.sharded.recommend_blocks_owned(blocks, kmax, self.filter_seen), blocks):
+            lo, hi = owned_slice(len(blk), world, rank)
             if hi > lo:
                 ip = self.gt_indptr[row + lo:row + hi + 1]
-                sums += self._metric_sums(i[lo:hi], torch.from_numpy(ip - ip[0]),
+                sums += self._metric_sums(i, torch.from_numpy(ip - ip[0]),
                                           torch.from_numpy(self.gt_idx[ip[0]:ip[-1]] if ip[-1] > ip[0] else np.zeros(1, np.int32)), self.ks,
                                           recall_den=torch.from_numpy(self.recall_den[row + lo:row + hi]))
-            outs_s.append(s); outs_i.append(i); row += len(blk)
-        dev = outs_i[0].device if outs_i else self.recommender.device
+            if want_lists:
+                gs, gi = gather_owned(s, i, len(blk), self.sharded.group)
+                outs_s.append(gs); outs_i.append(gi)
+            row += len(blk)
+        dev = self.recommender.device
         t = torch.from_numpy(sums).to("cpu" if dist.get_backend(self.sharded.group) == "gloo" else dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.sharded.group)
         by_k = _by_k(t.cpu().numpy(), self.ks, self.n_total)
@@ -376,7 +380,7 @@ class FullCatalogueEvaluator:
         r = self.recommender
         kmax = max(self.ks)
         if self.sharded is not None:
-            scores, idx, by_k = self._evaluate_sharded(kmax)
+            scores, idx, by_k = self._evaluate_sharded(kmax, want_lists=novelty or self.keep_predictions)
         else:
             scores, idx = r.recommend_all(self.users, top_k=kmax, filter_seen=self.filter_seen)
             by_k = ranking_metrics(idx, self.gt_indptr, self.gt_idx, self.ks, recall_den=self.recall_den, n_total=self.n_total)

@@ -202,6 +202,29 @@ class FastRecommender:
             self._engine = eng
         return eng
 
+    def rescore_engine(self) -> PxrEngine:
+        """Engine holding the fp32 records of the WHOLE catalogue (records only: 1 280 B per item), used by an item-sharded
+        rank to re-score the merged candidate lists of the users it owns (exact mode, ``ShardedTopK``)."""
+        eng = self.model.engine("rescore")
+        token = ("rescore", self.model._engines["rescore"][1], 0, self.n_items)
+        if eng.items_token != token:
+            eng.set_records_only(True)
+            eng.precompute_items(self.model.item_embedding.weight.detach(), self.items.tag_idx, self.items.vis, self.items.txt,
+                                 self.items.num, item_idx=None, item_base=0, n_rows=self.n_items)
+            if self.items.missing is not None:
+                eng.set_missing_items(torch.from_numpy(np.ascontiguousarray(np.asarray(self.items.missing)).astype(np.uint8)))
+            eng.items_token = token
+        return eng
+
+    @torch.no_grad()
+    def rescore(self, user_indices, cand_idx: torch.Tensor, top_k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(n, 64) candidate lists of global item indices (-1 padded) -> exact (fp32) top-K, ties -> lower index."""
+        users = torch.as_tensor(np.asarray(user_indices.cpu() if isinstance(user_indices, torch.Tensor) else user_indices, dtype=np.int64)).to(self.device)
+        if users.numel() == 0:
+            return (torch.empty((0, top_k), dtype=torch.float32, device=self.device),
+                    torch.empty((0, top_k), dtype=torch.int32, device=self.device))
+        return self.rescore_engine().rescore_topk(self.model.user_embedding.weight.detach(), users, cand_idx, top_k)
+
     # ------------------------------------------------------------ batched API
     def _seen_csr_for(self, users: np.ndarray, d_users: torch.Tensor):
         """(seen_indptr, seen_idx) device tensors for ``pxr_score_topk``: offsets
@@ -224,12 +247,20 @@ class FastRecommender:
         return indptr, self._d_hist_idx[pos]
 
     @torch.no_grad()
-    def recommend_all(self, user_indices, top_k: int = 10, filter_seen: bool = True
+    def recommend_all(self, user_indices, top_k: int = 10, filter_seen: bool = True, raw: bool = False
                       ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Every user of ``user_indices`` (encoder indices) against every item of
         this recommender's item range.  Returns device tensors
-        (scores (n, K) fp32 descending, item indices (n, K) int32, -inf / -1 padded)."""
+        (scores (n, K) fp32 descending, item indices (n, K) int32, -inf / -1 padded).
+        ``raw``: the fused kernel's 16-bit lists as they are (no fp32 re-score), e.g. the 64-slot per-shard lists an
+        item-sharded job exchanges before the owning rank re-scores the merged candidates."""
         eng = self.engine()
+        if raw and eng.rescore:
+            eng.set_rescore(False)
+            try:
+                return self.recommend_all(user_indices, top_k, filter_seen, raw=False)
+            finally:
+                eng.set_rescore(True)
         users = np.asarray(user_indices.cpu() if isinstance(user_indices, torch.Tensor) else user_indices,
                            dtype=np.int64)
         uemb = self.model.user_embedding.weight.detach()

@@ -97,57 +97,84 @@ def exchange_owned_finish(handle, group=None) -> Tuple[torch.Tensor, torch.Tenso
     return out[..., 0].contiguous().view(torch.float32), out[..., 1].contiguous()
 
 
-class ShardedTopK:
-    """Lock-step sharded scoring: ``local_topk(users, k, filter_seen)`` is the
-    rank's scorer over its item range (``FastRecommender.recommend_all`` in
-    production), ``merge`` the S-way merge (``pxr_merge_topk``)."""
+def gather_owned(scores: torch.Tensor, idx: torch.Tensor, n: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Owned final lists of an n-user block ((m, K) per rank, ``owned_slice``) -> the (n, K) lists of the whole block on every
+    rank (one small all-gather: K * 8 bytes per user)."""
+    world = dist.get_world_size(group)
+    per = (n + world - 1) // world
+    k = scores.shape[1]
+    local = torch.empty((per, k, 2), dtype=torch.int32, device=scores.device)
+    m = scores.shape[0]
+    local[:m, :, 0] = scores.contiguous().view(torch.int32)
+    local[:m, :, 1] = idx.to(torch.int32)
+    if m < per:
+        local[m:] = 0
+    out = torch.empty((world * per, k, 2), dtype=torch.int32, device=scores.device)
+    dist.all_gather_into_tensor(out, local, group=group)
+    out = out[:n]
+    return out[..., 0].contiguous().view(torch.float32), out[..., 1].contiguous()
 
-    def __init__(self, local_topk: Callable, merge: Optional[Callable] = None, group=None):
+
+class ShardedTopK:
+    """Lock-step sharded scoring: ``local_topk(users, k, filter_seen)`` is the rank's scorer over its item range
+    (``FastRecommender.recommend_all`` in production), ``merge`` the S-way merge (``pxr_merge_topk``).
+
+    Exact mode across shards (``rescore`` given, e.g. ``FastRecommender.rescore``): ``local_topk`` must then return the RAW
+    16-bit lists (``recommend_all(..., raw=True)``); the exchange carries their 64 slots, the rank that owns a user merges
+    the shards' lists into the global 16-bit top-64 and re-scores THOSE in fp32 against whole-catalogue records --
+    the same candidates, hence the same lists, as the unsharded exact mode, and 1 / world of the re-score work per rank
+    instead of every shard re-scoring every user."""
+
+    RAW_K = 64
+
+    def __init__(self, local_topk: Callable, merge: Optional[Callable] = None, group=None, rescore: Optional[Callable] = None):
         self.local_topk = local_topk
         if merge is None:
             from .engine import merge_topk as merge
         self.merge = merge
         self.group = group
+        self.rescore = rescore
 
-    def recommend_all(self, user_indices, top_k: int, filter_seen: bool = True):
-        s, i = self.local_topk(user_indices, top_k, filter_seen)
-        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
-            return s, i
-        all_s, all_i = allgather_topk(s, i, self.group)
-        return self.merge(all_s, all_i)
+    def _sharded(self) -> bool:
+        return dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _k_exchange(self, top_k: int) -> int:
+        return self.RAW_K if self.rescore is not None else top_k
+
+    def _finish_owned(self, handle, blk, top_k: int):
+        s, i = self.merge(*exchange_owned_finish(handle, self.group))
+        if self.rescore is not None:
+            lo, hi = owned_slice(len(blk), dist.get_world_size(self.group), dist.get_rank(self.group))
+            s, i = self.rescore(blk[lo:hi], i, top_k)
+        return s, i
 
     def recommend_blocks_owned(self, user_blocks, top_k: int, filter_seen: bool = True):
-        """As ``recommend_blocks`` with reduce-scatter ownership: yields, per block, the merged lists of the users THIS
-        rank owns (``owned_slice(len(block), world, rank)``); the exchange of block b again overlaps the scoring of
-        block b + 1.  1/world of the all-gather's traffic and merge work per rank."""
-        sharded = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        """Generator over user blocks with reduce-scatter ownership: yields, per block, the final lists of the users THIS
+        rank owns (``owned_slice(len(block), world, rank)``).  The exchange of block b (one all-to-all on the
+        communicator's stream) overlaps the scoring of block b + 1: the local kernel of the next block is launched before
+        the previous block's exchange is waited for, merged and re-scored."""
         pending = None
         for blk in user_blocks:
-            s, i = self.local_topk(blk, top_k, filter_seen)
-            if not sharded:
+            s, i = self.local_topk(blk, self._k_exchange(top_k), filter_seen)
+            if not self._sharded():
+                if self.rescore is not None:
+                    s, i = self.rescore(blk, i, top_k)
                 yield s, i
                 continue
             handle = exchange_owned_start(s, i, self.group)
             if pending is not None:
-                yield self.merge(*exchange_owned_finish(pending, self.group))
-            pending = handle
+                yield self._finish_owned(pending[0], pending[1], top_k)
+            pending = (handle, blk)
         if pending is not None:
-            yield self.merge(*exchange_owned_finish(pending, self.group))
+            yield self._finish_owned(pending[0], pending[1], top_k)
 
     def recommend_blocks(self, user_blocks, top_k: int, filter_seen: bool = True):
-        """Generator over user blocks with the exchange of block b overlapped with the scoring of block b + 1
-        (SURVEY.md §8(e)): the local kernel of the next block is launched before the previous block's all-gather
-        is waited for and merged.  Yields (scores, indices) per block, in order."""
-        sharded = dist.is_initialized() and dist.get_world_size(self.group) > 1
-        pending = None
-        for blk in user_blocks:
-            s, i = self.local_topk(blk, top_k, filter_seen)
-            if not sharded:
-                yield s, i
-                continue
-            handle = allgather_topk_start(s, i, self.group)
-            if pending is not None:
-                yield self.merge(*allgather_topk_finish(pending))
-            pending = handle
-        if pending is not None:
-            yield self.merge(*allgather_topk_finish(pending))
+        """As ``recommend_blocks_owned``, then the owned lists are gathered so that every rank holds the whole block."""
+        user_blocks = list(user_blocks)
+        for blk, (s, i) in zip(user_blocks, self.recommend_blocks_owned(user_blocks, top_k, filter_seen)):
+            if self._sharded():
+                s, i = gather_owned(s, i, len(blk), self.group)
+            yield s, i
+
+    def recommend_all(self, user_indices, top_k: int, filter_seen: bool = True):
+        return next(iter(self.recommend_blocks([user_indices], top_k, filter_seen)))

@@ -3,7 +3,7 @@
 name=$1; shift
 cd "$(dirname "$0")/../pixelrec_multimodal_b200"
 mkdir -p variants/$name
-for f in pxr_api simt_kernels score_tc items_tc sampling novelty; do
+for f in pxr_api simt_kernels score_tc items_tc sampling novelty diversity; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -DPXR_PRECISE_MATH -Xcompiler -fPIC -I ../include -I csrc "$@" -c csrc/$f.cu -o variants/$name/$f.o &
 done
 wait
