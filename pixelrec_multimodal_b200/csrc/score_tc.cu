@@ -1164,9 +1164,11 @@ __device__ __forceinline__ uint16_t to16(float v, int fmt) {
 
 // Builds the two per-CTA-rank operand images: 16-bit, K-major, 128-byte swizzle (16-byte chunk index XOR
 // row-in-group), laid out exactly as the kernel's shared memory.  w1 / k1: layer-1 weight (row stride k1) or NULL.
+// (n1, n2, n3) = the model's hidden dims: rows / columns beyond them are zero, i.e. a smaller MLP runs zero-padded to the
+// kernel's [512, 256, 128] (a padded unit has bias 0 and weight 0: relu(0) = 0 feeds nothing forward -- exact).
 __global__ void build_wimg_kernel(const float* __restrict__ w1, int k1, const float* __restrict__ k1_scale,
                                   const float* __restrict__ w2, const float* __restrict__ w3, uint8_t* __restrict__ img,
-                                  int gated, int fmt) {
+                                  int gated, int fmt, int n1, int n2, int n3) {
   const uint32_t off_w2 = gated ? 32768u : 0u, off_w3 = off_w2 + 131072u, wimg = off_w3 + 32768u;
   const int total = (int)wimg;                                       // 2 ranks x wimg/2 elements
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -1182,10 +1184,17 @@ __global__ void build_wimg_kernel(const float* __restrict__ w1, int k1, const fl
     const uint32_t nl = inb / 128, inrow = inb % 128;
     const uint32_t chunk = (inrow >> 4) ^ (nl & 7);                  // un-swizzle: stored chunk -> logical chunk
     const uint32_t kk = chunk * 8 + ((inrow & 15) >> 1);             // k inside the 64-wide block
-    float v;
-    if (which == 1) v = w1[(size_t)(blk * 64 + rank * 32 + nl) * k1 + kk] * (k1_scale ? k1_scale[kk] : 1.f);   // N-chunk blk, rows [32 rank, +32)
-    else if (which == 2) v = w2[(size_t)(rank * 128 + nl) * H1 + blk * 64 + kk];     // K-block blk, rows [128 rank, +128)
-    else v = w3[(size_t)(rank * 64 + nl) * H2 + blk * 64 + kk];
+    float v = 0.f;
+    if (which == 1) {                                                // N-chunk blk, rows [32 rank, +32)
+      const int n = blk * 64 + rank * 32 + nl;
+      if (n < n1) v = w1[(size_t)n * k1 + kk] * (k1_scale ? k1_scale[kk] : 1.f);
+    } else if (which == 2) {                                         // K-block blk, rows [128 rank, +128)
+      const int n = rank * 128 + nl, k = blk * 64 + kk;
+      if (n < n2 && k < n1) v = w2[(size_t)n * n1 + k];
+    } else {
+      const int n = rank * 64 + nl, k = blk * 64 + kk;
+      if (n < n3 && k < n2) v = w3[(size_t)n * n2 + k];
+    }
     reinterpret_cast<uint16_t*>(img + (size_t)rank * wimg)[off / 2] = to16(v, fmt);
   }
 }
@@ -1400,11 +1409,14 @@ __global__ void attn_wc_kernel(const float* __restrict__ out_w, float* __restric
 
 // attention: b1' = b1 + W1 ln_b (LayerNorm bias folded into layer 1); s1[k] = ln_w[k] / M for the W1 image
 __global__ void attn_fold_ln_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ ln_w,
-                                    const float* __restrict__ ln_b, int M, float* __restrict__ b1_out, float* __restrict__ s1_out) {
+                                    const float* __restrict__ ln_b, int M, int n1, float* __restrict__ b1_out, float* __restrict__ s1_out) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n < H1) {
-    float acc = b1[n];
-    for (int k = 0; k < D; ++k) acc = fmaf(w1[(size_t)n * D + k], ln_b[k], acc);
+    float acc = 0.f;
+    if (n < n1) {
+      acc = b1[n];
+      for (int k = 0; k < D; ++k) acc = fmaf(w1[(size_t)n * D + k], ln_b[k], acc);
+    }
     b1_out[n] = acc;
   }
   if (n < D) s1_out[n] = ln_w[n] / (float)M;
@@ -1453,8 +1465,11 @@ static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_
 const char* pxr_tc_unsupported_reason(const pxr_handle* h) {
   const pxr_config& c = h->cfg;
   if (h->n_sm < 2) return "the device has fewer than 2 SMs (the kernel runs on CTA pairs)";
-  if (c.n_hidden != 3 || c.hidden[0] != tc::H1 || c.hidden[1] != tc::H2 || c.hidden[2] != tc::H3)
-    return "fusion_hidden_dims is not [512, 256, 128] (the three weight matrices are resident in the CTA pair's shared memory)";
+  if (c.n_hidden != 3) return "the prediction MLP does not have three hidden layers";
+  if (c.hidden[0] > tc::H1 || c.hidden[1] > tc::H2 || c.hidden[2] > tc::H3)
+    return "fusion_hidden_dims exceeds [512, 256, 128] (the three weight matrices are resident in the CTA pair's shared memory)";
+  // smaller hidden layers run zero-padded to [512, 256, 128]; concat feeds layer-1 partials of exactly 512 columns
+  if (c.fusion == PXR_FUSION_CONCAT && c.hidden[0] != tc::H1) return "concat fusion with fusion_hidden_dims[0] != 512";
   if (c.activation != PXR_ACT_RELU) return "fusion_activation is not relu (the in-place TMEM epilogues use cvt.relu)";
   if (h->M < 4 || h->M > 6) return "fewer than 4 modalities";
   if (c.fusion == PXR_FUSION_ATTENTION && c.num_heads != tc::NH) return "attention fusion with num_attention_heads != 4";
@@ -1487,20 +1502,22 @@ int pxr_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
   const bool gated = h->cfg.fusion != PXR_FUSION_CONCAT;    // layer 1 on the tensor pipe
   const bool attn = h->cfg.fusion == PXR_FUSION_ATTENTION;
   float* b = fw->bias;
+  const int n1 = h->cfg.hidden[0], n2 = h->cfg.hidden[1], n3 = h->cfg.hidden[2];     // <= 512 / 256 / 128: zero-padded to the kernel's shape
+  PXR_CUDA(h, cudaMemsetAsync(b, 0, sizeof(fw->bias), st));
   if (attn) {     // LayerNorm affine folded into layer 1 (see attn_item_step); centred out_proj weight and its MMA fragments
-    tc::attn_fold_ln_kernel<<<(tc::H1 + 127) / 128, 128, 0, st>>>(h->mlp[0].w, h->mlp[0].b, h->ln_w, h->ln_b, h->M, b, fw->s1);
+    tc::attn_fold_ln_kernel<<<(tc::H1 + 127) / 128, 128, 0, st>>>(h->mlp[0].w, h->mlp[0].b, h->ln_w, h->ln_b, h->M, n1, b, fw->s1);
     tc::attn_wc_kernel<<<1, 256, 0, st>>>(h->attn_out.w, fw->wc, fw->wo_frag, tc_fmt(h));
     h->launches += 2;
   } else {
-    PXR_CUDA(h, cudaMemcpyAsync(b, h->mlp[0].b, sizeof(float) * tc::H1, cudaMemcpyDeviceToDevice, st));
+    PXR_CUDA(h, cudaMemcpyAsync(b, h->mlp[0].b, sizeof(float) * n1, cudaMemcpyDeviceToDevice, st));
   }
   tc::build_wimg_kernel<<<296, 256, 0, st>>>(gated ? h->mlp[0].w : nullptr, h->mlp[0].k, attn ? fw->s1 : nullptr, h->mlp[1].w,
-                                             h->mlp[2].w, fw->wimg, gated ? 1 : 0, tc_fmt(h));
+                                             h->mlp[2].w, fw->wimg, gated ? 1 : 0, tc_fmt(h), n1, n2, n3);
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
-  PXR_CUDA(h, cudaMemcpyAsync(b + tc::H1, h->mlp[1].b, sizeof(float) * tc::H2, cudaMemcpyDeviceToDevice, st));
-  PXR_CUDA(h, cudaMemcpyAsync(b + tc::H1 + tc::H2, h->mlp[2].b, sizeof(float) * tc::H3, cudaMemcpyDeviceToDevice, st));
-  PXR_CUDA(h, cudaMemcpyAsync(b + tc::H1 + tc::H2 + tc::H3, h->out.w, sizeof(float) * tc::H3, cudaMemcpyDeviceToDevice, st));
+  PXR_CUDA(h, cudaMemcpyAsync(b + tc::H1, h->mlp[1].b, sizeof(float) * n2, cudaMemcpyDeviceToDevice, st));
+  PXR_CUDA(h, cudaMemcpyAsync(b + tc::H1 + tc::H2, h->mlp[2].b, sizeof(float) * n3, cudaMemcpyDeviceToDevice, st));
+  PXR_CUDA(h, cudaMemcpyAsync(b + tc::H1 + tc::H2 + tc::H3, h->out.w, sizeof(float) * n3, cudaMemcpyDeviceToDevice, st));
   PXR_CUDA(h, cudaMemcpyAsync(b + tc::H1 + tc::H2 + 2 * tc::H3, h->out.b, sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (attn) {     // the attention kernel reads these through the kernel-parameter constant bank: keep a host copy
     PXR_CUDA(h, cudaMemcpyAsync(h->tc_bias_host, b, sizeof(float) * (tc::H1 + tc::H2 + 2 * tc::H3 + 1), cudaMemcpyDeviceToHost, st));

@@ -56,7 +56,8 @@ def main():
                     continue                               # generic fp32 kernels: ~40 M pairs/s
                 users = torch.arange(B, device=dev)
                 ip, ix = hist["train_indptr"][:B + 1], hist["train_idx"]
-                for _ in range(3):
+                huge = B * NI > 1.5e10                     # a 10 M-item catalogue x 8 192 users is ~30 s per call
+                for _ in range(1 if huge else 3):
                     e.score_topk(uemb, users, 50, ip, ix)
                 torch.cuda.synchronize()
                 flush.zero_()
@@ -64,10 +65,10 @@ def main():
                 reps, est = 0, 0.0
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                while reps < 3 or (est < args.min_ms and reps < 200):
+                while reps < (1 if huge else 3) or (est < args.min_ms and reps < 200):
                     e.score_topk(uemb, users, 50, ip, ix)
                     reps += 1
-                    if reps % 3 == 0:
+                    if huge or reps % 3 == 0:
                         e1.record(); torch.cuda.synchronize(); est = e0.elapsed_time(e1)
                 e1.record(); torch.cuda.synchronize()
                 k_ms, k_n = e.profile_read()

@@ -595,6 +595,33 @@ def test_tcgen05_matches_emulated_and_exact_oracle(fusion, dtype, n_users, n_ite
           f"{same_ref}/{total} to the exact oracle; max|emu-exact| = {np.max(np.abs(emu - ref)):.2e}")
 
 
+@pytest.mark.parametrize("fusion,hidden", [("gated", [256, 128, 64]), ("attention", [384, 200, 100]), ("gated", [512, 256, 32]),
+                                           ("concatenate", [512, 128, 64])])
+def test_tcgen05_smaller_mlp_zero_padded(fusion, hidden):
+    """Prediction MLPs smaller than the kernel's resident [512, 256, 128] run on the fused path zero-padded (a padded unit
+    has weight 0 and bias 0, relu(0) = 0: exact): kernel == the emulated oracle of the UNPADDED model, exact mode == the
+    fp32 oracle."""
+    n_users, n_items, k = 40, 900, 50
+    spec = syn.ModelSpec(n_users=n_users, n_items=n_items, fusion_type=fusion, fusion_hidden_dims=hidden)
+    sd = syn.make_state_dict(spec, seed=syn.SEED + 27)
+    feats = syn.make_item_features(spec, seed=syn.SEED + 27)
+    syn.condition_like_trained(sd, spec, feats)
+    indptr, idx, _ = syn.make_histories(n_users, n_items, seed=syn.SEED + 27, lo=3, hi=40)
+    model, eng = _engine_for(spec, sd, feats, "auto")
+    assert eng.active_path == "tcgen05", eng.path_reason
+    users = np.arange(n_users)
+    args = (model.user_embedding.weight.detach(), torch.from_numpy(users).cuda(), k, torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda())
+    s, i = _structural_checks(*eng.score_topk(*args), k, n_items, indptr, idx)
+    emu = _lowp_scores(sd, spec, feats, users)
+    same = sum(_check_topk(s[u].astype(np.float64), i[u], emu[u], k, idx[indptr[u]:indptr[u + 1]], _emu_tol(fusion, "bf16"), 0.0) for u in users)
+    assert same >= 0.9 * k * n_users      # the rest are swaps inside the flip band (checked position by position above)
+    eng.set_rescore(True)
+    xs, xi = _structural_checks(*eng.score_topk(*args), k, n_items, indptr, idx)
+    ref = orc.score_block(sd, cs.spec_cfg(spec), users, 0, n_items, feats)
+    for u in users:
+        _check_topk(xs[u].astype(np.float64), xi[u], ref[u], k, idx[indptr[u]:indptr[u + 1]], SIMT_TOL, 0.0)
+
+
 @pytest.mark.parametrize("D", [16, 128, 320, 512])
 def test_tcgen05_concat_any_embedding_dim(D):
     """concat fusion on the fused path for embedding dims other than 64 (BASELINE.json configs[4] sweeps 64-512):
