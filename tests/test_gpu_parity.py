@@ -830,6 +830,19 @@ def test_catalogue_scale_parity(fusion, n_items):
             if xi[r][j] != ref_lists[r][j]:
                 assert abs(float(ref[r][xi[r][j]]) - float(ref[r][ref_lists[r][j]])) <= 2e-4, (r, j)
     assert same >= 0.99 * k * n_users, same
+    # the band of the raw path over ALL pairs (not only the sigmoid-saturated top of the list): the oracle with the kernel's
+    # operand roundings against the exact forward, every item of the catalogue for four users
+    cpu = lambda d: {a: b.cpu().numpy() for a, b in d.items()}
+    sdn, fn = cpu(sd), cpu(feats)
+    ii = np.arange(n_items)
+    band_abs = band_rel = 0.0
+    for r in range(4):
+        emu = orc.forward_pairs_lowp(sdn, cs.spec_cfg(spec), np.full(n_items, users[r]), ii, fn["tag_idx"], fn["vis"], fn["txt"], fn["num"])
+        d = np.abs(emu - ref[r].astype(np.float64))
+        band_abs = max(band_abs, float(d.max()))
+        band_rel = max(band_rel, float((d / np.maximum(np.abs(ref[r]), 1e-3)).max()))
+    assert band_abs <= RAW_BAND_SCALE["bf16"], band_abs
+    print(f"catalogue scale {fusion} x {n_items}: 16-bit operands vs exact over all pairs of 4 users: max |ds| {band_abs:.2e}, max relative {band_rel:.1%}")
     print(f"catalogue scale {fusion} x {n_items}: raw top-50 overlap mean {overlap.mean():.2f} min {overlap.min()}, "
           f"raw max|ds| {raw_err:.3e}, exact top-50 inside raw top-64 for {int(inside64.sum())}/{n_users} users, "
           f"exact mode identical positions {same}/{k * n_users}")
