@@ -242,6 +242,16 @@ int pxr_sample_candidates(const int64_t* user_idx, int64_t n_users, const int64_
                           int64_t n_items, int32_t n_neg, uint64_t seed, int32_t stride, int32_t* out_cand,
                           int32_t* out_len, pxr_stream stream);
 
+/* The same for sampling_strategy 'popularity' / 'popularity_inverse' (src/evaluation/tasks.py:225-308:
+ * np.random.choice(pool, n, replace=False, p = normalised item weight)): item i of user u gets the key
+ * log(uniform(seed, u, i)) / weights[i]; the n_neg largest keys among the non-positive items are the sample
+ * (Efraimidis-Spirakis weighted sampling without replacement), ties -> lower item; shuffle order as above.
+ * One pass over the catalogue per user, nothing of size users x items is stored.
+ *   weights : (n_items,) float64, > 0 (test-set item counts or their reciprocals; n_items < 2^31) */
+int pxr_weighted_candidates(const int64_t* user_idx, int64_t n_users, const int64_t* pos_indptr, const int32_t* pos_idx,
+                            const double* weights, int64_t n_items, int32_t n_neg, uint64_t seed, int32_t stride,
+                            int32_t* out_cand, int32_t* out_len, pxr_stream stream);
+
 /* K3t on its own: exact top-K of every row of a dense score matrix; -inf entries are masked; ties -> lower
  * column.  Used to rank candidate lists (stable sort of src/inference/recommender.py:105 over the candidate order).
  *   scores : (n_rows, n_cols) fp32 ;  out_scores / out_pos : (n_rows, K), padded with -inf / -1 */

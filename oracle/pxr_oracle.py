@@ -590,7 +590,7 @@ def sample_candidates_weighted(global_user: int, positives: Sequence[int], weigh
     made reproducible like ``sample_candidates``: item i gets the exponential key log(u_i) / w_i with u_i a hash-uniform
     of (seed, user, item); the n_neg largest keys among the non-positive items are the sample (Efraimidis-Spirakis:
     the same distribution as successive weighted draws without replacement).  Ties -> lower item.  Final order as in
-    ``sample_candidates``.  Direct restatement of ``evaluation.weighted_candidates`` (torch, any device)."""
+    ``sample_candidates``.  Pure-Python restatement of csrc/sampling.cu::weighted_candidates_kernel."""
     n_items = len(weights)
     pos = sorted(int(p) for p in positives)[:stride]
     posset = set(int(p) for p in positives)

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "pxr_metrics": (C.c_int, [_F, C.c_int32, C.c_int64, _F, _F, _F, C.POINTER(C.c_int32), C.c_int32, _F, _F, _F, _F,
                               C.c_size_t, C.c_void_p]),
     "pxr_sample_candidates": (C.c_int, [_F, C.c_int64, _F, _F, C.c_int64, C.c_int32, C.c_uint64, C.c_int32, _F, _F, C.c_void_p]),
+    "pxr_weighted_candidates": (C.c_int, [_F, C.c_int64, _F, _F, _F, C.c_int64, C.c_int32, C.c_uint64, C.c_int32, _F, _F, C.c_void_p]),
     "pxr_topk_rows": (C.c_int, [C.c_void_p, _F, C.c_int64, C.c_int64, C.c_int32, _F, _F, C.c_void_p]),
     "pxr_novelty_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "pxr_novelty_metrics": (C.c_int, [_F, C.c_int32, C.c_int64, C.c_int64, _F, _F, _F, _F, _F, _F, C.c_size_t, C.c_void_p]),

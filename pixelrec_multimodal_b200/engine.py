@@ -414,6 +414,36 @@ def sample_candidates(user_idx: torch.Tensor, pos_indptr: torch.Tensor, pos_idx:
     return cand, length
 
 
+def weighted_candidates(user_idx: torch.Tensor, pos_indptr: torch.Tensor, pos_idx: torch.Tensor, weights: torch.Tensor,
+                        n_neg: int, seed: int, stride: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Candidate lists of the popularity-biased strategies (pxr_weighted_candidates; reference
+    src/evaluation/tasks.py:225-308): per user the positives plus ``n_neg`` negatives drawn without replacement with
+    probability proportional to ``weights`` (float64, one per item), shuffled like ``sample_candidates``.  A pure
+    function of (seed, user index).  ``weights`` must live on the GPU: there is no host path."""
+    lib = _lib.load()
+    dev = weights.device
+    if dev.type != "cuda":
+        raise PxrError("weighted_candidates runs on the GPU only (pxr_weighted_candidates): pass CUDA tensors")
+    n = int(pos_indptr.shape[0]) - 1
+    n_items = int(weights.shape[0])
+    w = weights.to(dtype=torch.float64).contiguous()
+    pos_indptr = pos_indptr.to(device=dev, dtype=torch.int64).contiguous()
+    pos_idx = pos_idx.to(device=dev, dtype=torch.int32).contiguous()
+    if stride is None:
+        max_pos = int((pos_indptr[1:] - pos_indptr[:-1]).max().item()) if n else 0
+        stride = max(1, min(1024, max_pos + int(n_neg)))
+    uidx = user_idx.to(device=dev, dtype=torch.int64).contiguous() if user_idx is not None else None
+    cand = torch.empty((n, stride), dtype=torch.int32, device=dev)
+    length = torch.empty((n,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.pxr_weighted_candidates(_ptr(uidx), n, _ptr(pos_indptr), _ptr(pos_idx), _ptr(w), n_items, int(n_neg),
+                                         C.c_uint64(int(seed) & ((1 << 64) - 1)), int(stride), _ptr(cand), _ptr(length),
+                                         _stream())
+    if rc != 0:
+        raise PxrError(f"pxr_weighted_candidates failed ({rc})")
+    return cand, length
+
+
 _METRIC_TABLES = {}
 
 

@@ -15,7 +15,7 @@ from typing import Dict, Optional, Sequence
 import numpy as np
 import torch
 
-from .engine import ranking_metric_sums, sample_candidates
+from .engine import ranking_metric_sums, sample_candidates, weighted_candidates
 
 _COLS = ("avg_precision_at_k", "avg_recall_at_k", "avg_f1_at_k", "avg_hit_rate_at_k", "avg_ndcg_at_k", "avg_mrr",
          "avg_ndcg_list_ideal_at_k", "avg_precision_hits_over_k", "avg_map_at_k")
@@ -199,97 +199,12 @@ def intra_list_similarity(topk_idx: torch.Tensor, engine=None, embeddings: Optio
 
 
 # ----------------------------------------------------------------------------- popularity-biased candidate sampling
-_U64 = (1 << 64) - 1
-
-
-def _i64(x: int) -> int:
-    """Python int -> the same 64 bits as a signed value (torch has no uint64 arithmetic)."""
-    x &= _U64
-    return x - (1 << 64) if x >= (1 << 63) else x
-
-
-def _lsr(z: torch.Tensor, s: int) -> torch.Tensor:
-    return (z >> s) & ((1 << (64 - s)) - 1)               # logical shift right on int64
-
-
-def _mix64(z: torch.Tensor) -> torch.Tensor:
-    """splitmix64 step on int64 tensors (two's-complement wrap-around), the hash of csrc/sampling.cu."""
-    z = z + _i64(0x9E3779B97F4A7C15)
-    z = (z ^ _lsr(z, 30)) * _i64(0xBF58476D1CE4E5B9)
-    z = (z ^ _lsr(z, 27)) * _i64(0x94D049BB133111EB)
-    return z ^ _lsr(z, 31)
-
-
 def sampling_weights(test_items: np.ndarray, n_items: int, strategy: str) -> np.ndarray:
     """Item weights of the 'popularity' / 'popularity_inverse' strategies (src/evaluation/tasks.py:227-243, 266-280):
     rows of the TEST table holding the item (1 for items that never occur there), or the reciprocal."""
     cnt = np.bincount(np.asarray(test_items, dtype=np.int64), minlength=n_items).astype(np.float64)
     cnt[cnt == 0] = 1.0
     return cnt if strategy == "popularity" else 1.0 / cnt
-
-
-def weighted_candidates(user_idx: torch.Tensor, pos_indptr: torch.Tensor, pos_idx: torch.Tensor, weights: torch.Tensor,
-                        n_neg: int, seed: int, stride: int, max_elems: int = 1 << 25):
-    """Candidate lists for the popularity-biased strategies (src/evaluation/tasks.py:225-308: ``n_neg`` negatives
-    drawn without replacement with probability proportional to the item weight), as a pure function of
-    (seed, user index) like ``pxr_sample_candidates``: item i gets the key log(u_i) / w_i with u_i a hash-uniform of
-    (seed, user, item) and the ``n_neg`` largest keys among the user's non-positive items are the sample
-    (Efraimidis-Spirakis: the distribution of successive weighted draws without replacement).  Candidate
-    construction only -- device-agnostic tensor code (it is not on the scoring path); users are processed in blocks
-    of at most ``max_elems`` (user, item) keys.  Returns ((n, stride) int32, -1 padded; (n,) int32 lengths), ordered
-    by the same per-user shuffle hash as the uniform sampler."""
-    dev = weights.device
-    n_items = int(weights.shape[0])
-    n = int(user_idx.shape[0])
-    users = user_idx.to(device=dev, dtype=torch.int64)
-    indptr = pos_indptr.to(device=dev, dtype=torch.int64)
-    pidx = pos_idx.to(device=dev, dtype=torch.int64)
-    cand = torch.full((n, stride), -1, dtype=torch.int32, device=dev)
-    length = torch.zeros((n,), dtype=torch.int32, device=dev)
-    if n == 0:
-        return cand, length
-    items = torch.arange(n_items, device=dev, dtype=torch.int64)
-    kmax = max(0, min(int(n_neg), n_items, stride))
-    inv_w = 1.0 / weights.to(torch.float64)
-    big = torch.iinfo(torch.int64).max
-    block = max(1, max_elems // max(1, n_items))
-    for lo in range(0, n, block):
-        hi = min(n, lo + block)
-        b = hi - lo
-        ku = _mix64(_i64(seed) ^ _mix64(users[lo:hi]))                                   # (b,)
-        npos = (indptr[lo + 1:hi + 1] - indptr[lo:hi])
-        max_pos = min(int(npos.max().item()), stride)
-        # positives, ascending, -1 padded (b, max_pos)
-        col = torch.arange(max_pos, device=dev)
-        pmask = col[None, :] < npos[:, None]
-        src = (indptr[lo:hi, None] + col[None, :]).clamp_max(max(int(pidx.shape[0]) - 1, 0))
-        pos = torch.where(pmask, pidx[src] if pidx.numel() else torch.zeros_like(src), torch.full_like(src, -1))
-        # keys of every (user, item); positives can never be drawn
-        h = _mix64(ku[:, None] ^ _i64(0xA0761D6478BD642F) ^ (items[None, :] << 1))
-        u = (_lsr(h, 11).to(torch.float64) + 0.5) * (1.0 / 9007199254740992.0)
-        key = torch.log(u) * inv_w[None, :]
-        if max_pos:
-            rows = torch.arange(b, device=dev)[:, None].expand(b, max_pos)[pmask]
-            key[rows, pos[pmask]] = float("-inf")
-        want = torch.minimum(torch.full_like(npos, kmax), torch.minimum(stride - npos.clamp_max(stride), n_items - npos)).clamp_min(0)
-        if kmax:
-            kv, ki = torch.topk(key, kmax, dim=1)
-            ok = (torch.arange(kmax, device=dev)[None, :] < want[:, None]) & torch.isfinite(kv)
-            negs = torch.where(ok, ki, torch.full_like(ki, -1))
-        else:
-            negs = torch.zeros((b, 0), dtype=torch.int64, device=dev)
-        both = torch.cat([pos, negs], dim=1)                                             # (b, max_pos + kmax)
-        valid = both >= 0
-        by_item = torch.where(valid, both, torch.full_like(both, big)).sort(dim=1).values
-        valid = by_item != big
-        hs = _mix64(ku[:, None] ^ _i64(0xD1B54A32D192ED03) ^ (torch.where(valid, by_item, torch.zeros_like(by_item)) << 1))
-        hs = torch.where(valid, hs ^ _i64(1 << 63), torch.full_like(hs, big))            # unsigned order as signed; padding last
-        order = torch.sort(hs, dim=1, stable=True).indices                               # stable: equal hashes keep the lower item first
-        out = torch.gather(torch.where(valid, by_item, torch.full_like(by_item, -1)), 1, order)
-        w = min(stride, out.shape[1])
-        cand[lo:hi, :w] = out[:, :w].to(torch.int32)
-        length[lo:hi] = (out[:, :w] >= 0).sum(dim=1).to(torch.int32)
-    return cand, length
 
 
 class FullCatalogueEvaluator:

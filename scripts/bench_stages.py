@@ -15,7 +15,7 @@ import torch
 REPO = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(REPO))
 from pixelrec_multimodal_b200 import FastMultimodalRecommender, synthetic as syn   # noqa: E402
-from pixelrec_multimodal_b200.engine import merge_topk, ranking_metric_sums        # noqa: E402
+from pixelrec_multimodal_b200.engine import merge_topk, ranking_metric_sums, sample_candidates, weighted_candidates   # noqa: E402
 
 
 def timed(fn, reps, flush):
@@ -94,6 +94,19 @@ def main():
     flop = 2 * (64 * 512 + 512 * 256 + 256 * 128 + 128) if args.fusion != "concatenate" else 2 * (384 * 512 + 512 * 256 + 256 * 128 + 128)
     print(json.dumps(dict(stage="K3r fp32 re-score (pxr_score_pairs)", fusion=args.fusion, units=npairs, unit="pairs", ms=ms,
                           pairs_per_s=npairs / ms * 1e3, fp32_tflops=npairs * flop / ms / 1e9)), flush=True)
+    # ---- K6: candidate samplers of the sampled protocol, 100 negatives + 1 positive per user (compute-bound: per (user, item) a
+    # hash and a float64 log for the weighted one; reported as users/s and (user, item) keys/s)
+    nu = 8192
+    pos_ptr = torch.arange(nu + 1, device=dev, dtype=torch.int64)
+    pos = torch.randint(0, args.items, (nu,), device=dev, dtype=torch.int32)
+    us = torch.arange(nu, device=dev, dtype=torch.int64)
+    w = torch.from_numpy(np.random.default_rng(0).zipf(1.5, args.items).clip(max=1000).astype(np.float64)).to(dev)
+    ms = timed(lambda: sample_candidates(us, pos_ptr, pos, args.items, 100, seed=1, stride=101), 5, flush)
+    print(json.dumps(dict(stage="K6 uniform sampler (pxr_sample_candidates)", units=nu, unit="users", items=args.items, ms=ms,
+                          users_per_s=nu / ms * 1e3)), flush=True)
+    ms = timed(lambda: weighted_candidates(us, pos_ptr, pos, w, 100, seed=1, stride=101), 3, flush)
+    print(json.dumps(dict(stage="K6 weighted sampler (pxr_weighted_candidates)", units=nu, unit="users", items=args.items, ms=ms,
+                          users_per_s=nu / ms * 1e3, keys_per_s=nu * args.items / ms * 1e3)), flush=True)
 
 
 if __name__ == "__main__":

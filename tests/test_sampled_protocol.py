@@ -39,58 +39,95 @@ def test_rank_candidates_is_stable():
     assert orc.rank_candidates([0.5, 0.9, 0.5, 0.1], [10, 11, 12, 13], 3) == [11, 10, 12]
 
 
-@pytest.mark.parametrize("strategy", ["popularity", "popularity_inverse"])
-@pytest.mark.parametrize("n_items,n_neg,max_pos,stride", [(300, 40, 5, 64), (37, 100, 6, 128), (50, 10, 0, 16), (12, 8, 12, 16), (9, 4, 3, 5)])
-def test_weighted_candidates_match_oracle(strategy, n_items, n_neg, max_pos, stride):
-    """product (torch tensor code, here on the CPU device) == the per-user Python restatement, item for item"""
-    import torch
-    from pixelrec_multimodal_b200.evaluation import sampling_weights, weighted_candidates
+def _weighted_case(n_items, n_neg, max_pos, strategy, n=40):
+    from pixelrec_multimodal_b200.evaluation import sampling_weights
     rng = np.random.default_rng(n_items * 7 + n_neg)
-    n = 40
     npos = rng.integers(0, max_pos + 1, n)
     pos = [np.sort(rng.choice(n_items, min(c, n_items), replace=False)) for c in npos]
     indptr = np.concatenate([[0], np.cumsum([len(p) for p in pos])]).astype(np.int64)
     idx = (np.concatenate(pos) if indptr[-1] else np.zeros(0)).astype(np.int32)
     users = rng.integers(0, 10 ** 9, n).astype(np.int64)
-    test_items = rng.zipf(1.5, 400) % n_items
+    test_items = rng.zipf(1.5, 400 + n_items // 10) % n_items
     w = sampling_weights(test_items, n_items, strategy)
     assert np.array_equal(w, orc.sampling_weights(test_items, n_items, strategy))
-    cand, length = weighted_candidates(torch.from_numpy(users), torch.from_numpy(indptr), torch.from_numpy(idx), torch.from_numpy(w),
-                                       n_neg, seed=77, stride=stride, max_elems=n_items * 7)      # several user blocks
-    cand, length = cand.numpy(), length.numpy()
+    return users, pos, indptr, idx, w
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("strategy", ["popularity", "popularity_inverse"])
+@pytest.mark.parametrize("n_items,n_neg,max_pos,stride", [(300, 40, 5, 64), (37, 100, 6, 128), (50, 10, 0, 16), (12, 8, 12, 16), (9, 4, 3, 5),
+                                                          (20000, 100, 3, 128), (3000, 1000, 20, 1024)])
+def test_weighted_candidates_kernel_matches_oracle(strategy, n_items, n_neg, max_pos, stride):
+    """pxr_weighted_candidates == the per-user Python restatement, item for item (keys are float64 on both sides; a
+    difference would need two keys within an ulp of each other)"""
+    import torch
+    from pixelrec_multimodal_b200.engine import weighted_candidates
+    n = 40 if n_items <= 3000 else 12
+    users, pos, indptr, idx, w = _weighted_case(n_items, n_neg, max_pos, strategy, n)
+    d_idx = torch.from_numpy(idx).cuda() if len(idx) else torch.zeros(1, dtype=torch.int32).cuda()[:0]
+    cand, length = weighted_candidates(torch.from_numpy(users).cuda(), torch.from_numpy(indptr).cuda(), d_idx,
+                                       torch.from_numpy(w).cuda(), n_neg, seed=77, stride=stride)
+    cand, length = cand.cpu().numpy(), length.cpu().numpy()
     for r in range(n):
         want = orc.sample_candidates_weighted(int(users[r]), pos[r].tolist(), w, n_neg, seed=77, stride=stride)
         assert length[r] == len(want) and cand[r][:length[r]].tolist() == want and np.all(cand[r][length[r]:] == -1), r
         assert set(pos[r].tolist()[:stride]) <= set(want) and len(set(want)) == len(want)
 
 
-def test_weighted_sampling_follows_the_weights():
-    """inclusion frequency grows with the weight (popularity) and shrinks with it (inverse); positives are never negatives"""
+def test_weighted_candidates_need_the_gpu():
+    """no host path: CPU tensors are refused, not sampled by other code"""
     import torch
-    from pixelrec_multimodal_b200.evaluation import weighted_candidates
+    from pixelrec_multimodal_b200.engine import weighted_candidates, PxrError
+    with pytest.raises(PxrError):
+        weighted_candidates(torch.zeros(1, dtype=torch.int64), torch.zeros(2, dtype=torch.int64), torch.zeros(0, dtype=torch.int32),
+                            torch.ones(4, dtype=torch.float64), 2, seed=1, stride=4)
+
+
+def _follows_the_weights(sampler):
     n_items, n = 60, 3000
     w = np.ones(n_items); w[:10] = 8.0
-    users = torch.arange(n, dtype=torch.int64)
-    indptr = torch.arange(n + 1, dtype=torch.int64)
-    pos = torch.full((n,), 59, dtype=torch.int32)
     for weights, heavy_more in ((w, True), (1.0 / w, False)):
-        cand, length = weighted_candidates(users, indptr, pos, torch.from_numpy(weights), 5, seed=3, stride=8)
-        c = cand.numpy()
-        assert np.all(length.numpy() == 6) and np.all((c == 59).sum(axis=1) == 1)
+        c = sampler(n, weights)
+        assert np.all((c >= 0).sum(axis=1) == 6) and np.all((c == 59).sum(axis=1) == 1)
         cnt = np.bincount(c[c >= 0], minlength=n_items).astype(float)
         heavy, light = cnt[:10].mean(), cnt[10:59].mean()
         assert (heavy > 3 * light) if heavy_more else (light > 3 * heavy)
 
 
+def test_weighted_sampling_follows_the_weights():
+    """the algorithm (oracle): inclusion frequency grows with the weight (popularity) and shrinks with it (inverse);
+    positives are never negatives"""
+    def sampler(n, weights):
+        out = np.full((n, 8), -1, dtype=np.int64)
+        for u in range(n):
+            c = orc.sample_candidates_weighted(u, [59], weights, 5, seed=3, stride=8)
+            out[u, :len(c)] = c
+        return out
+    _follows_the_weights(sampler)
+
+
+@pytest.mark.gpu
+def test_weighted_sampling_kernel_follows_the_weights():
+    import torch
+    from pixelrec_multimodal_b200.engine import weighted_candidates
+
+    def sampler(n, weights):
+        cand, _ = weighted_candidates(torch.arange(n, dtype=torch.int64).cuda(), torch.arange(n + 1, dtype=torch.int64).cuda(),
+                                      torch.full((n,), 59, dtype=torch.int32).cuda(), torch.from_numpy(weights).cuda(), 5, seed=3, stride=8)
+        return cand.cpu().numpy()
+    _follows_the_weights(sampler)
+
+
+@pytest.mark.gpu
 def test_sampled_evaluator_builds_weighted_candidates_from_the_test_table():
     """SampledRetrievalEvaluator(sampling_strategy='popularity'): weights = item counts of the test table (tasks.py:227),
-    candidates = positives + weighted negatives; host plumbing checked with a stand-in recommender on the CPU device"""
+    candidates = positives + weighted negatives; host plumbing checked with a stand-in recommender"""
     import pandas as pd
     import torch
     from pixelrec_multimodal_b200 import SampledRetrievalEvaluator
 
     class _Rec:
-        device = torch.device("cpu")
+        device = torch.device("cuda:0")
         n_items = 30
         user_index = {f"u{j}": j for j in range(6)}
         item_index = {f"i{j:02d}": j for j in range(30)}
@@ -101,6 +138,7 @@ def test_sampled_evaluator_builds_weighted_candidates_from_the_test_table():
     w = orc.sampling_weights([_Rec.item_index[i] for u, i in rows if u in _Rec.user_index], 30, "popularity")
     assert np.array_equal(ev._weights, w) and w[7] == 3.0 and w[0] == 1.0
     cand, length = ev.candidates()
+    cand, length = cand.cpu().numpy(), length.cpu().numpy()
     for j, u in enumerate(ev.users):
         pos = ev.gt_idx[ev.gt_indptr[j]:ev.gt_indptr[j + 1]].tolist()
         want = orc.sample_candidates_weighted(int(u), pos, w, 10, seed=1, stride=cand.shape[1])
