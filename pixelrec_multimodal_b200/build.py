@@ -12,6 +12,9 @@ REPO = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libpxr.so"
 SOURCES = ["pxr_api.cu", "simt_kernels.cu", "score_tc.cu", "items_tc.cu", "sampling.cu", "novelty.cu", "diversity.cu"]
+# score_tc.cu is compiled once per fusion_activation (pxr_act value -> -DPXR_TC_TU): object 0 = ReLU kernels + host side,
+# objects 1-4 = the fused kernels of gelu / tanh / leaky_relu / silu.  (source, extra flags, object name)
+UNITS = [(s, [], s + ".o") for s in SOURCES] + [("score_tc.cu", [f"-DPXR_TC_TU={a}"], f"score_tc_act{a}.o") for a in (1, 2, 3, 4)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math" if False else "-DPXR_PRECISE_MATH", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
               "-I", str(REPO / "include"), "-I", str(CSRC)]
@@ -39,12 +42,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     bdir = PKG / "build"
     bdir.mkdir(exist_ok=True)
     procs = []
-    for s in SOURCES:
-        o = bdir / (s + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / s), "-o", str(o)]
+    for s, extra, oname in UNITS:
+        o = bdir / oname
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", str(CSRC / s), "-o", str(o)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        procs.append((oname, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(str(o))
     for s, p in procs:
         out, _ = p.communicate()

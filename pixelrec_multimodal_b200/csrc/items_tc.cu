@@ -341,9 +341,9 @@ static int launch_gemm(pxr_handle* h, const GemmParams& gp, cudaStream_t st) {
   GemmParams p = gp;
   p.n_stages = p.NT <= 64 ? 4 : 2;
   const size_t smem = (size_t)p.n_stages * (2 * A_TILE + 2 * (size_t)p.NT * 128) + 1024;
-  if (!(h->tc_attr_set & 512u)) {
+  if (!(h->tc_attr_set & (1ull << 62))) {
     PXR_CUDA(h, cudaFuncSetAttribute(gemm3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    h->tc_attr_set |= 512u;
+    h->tc_attr_set |= (1ull << 62);
   }
   const int64_t n_work = ((p.M + TM - 1) / TM) * (p.N / p.NT);
   const unsigned grid = (unsigned)std::min<int64_t>(n_work, h->n_sm);

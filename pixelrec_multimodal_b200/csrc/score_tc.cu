@@ -46,6 +46,13 @@
 #include "pxr_common.cuh"
 #include "tc_ptx.cuh"
 
+// This source is compiled once per fusion_activation (build.py: -DPXR_TC_TU=<pxr_act>), one object each, so that the twelve
+// kernel instantiations of an activation build in parallel.  TU 0 (ReLU) also holds the one-off preparation kernels and the
+// host side; TU a > 0 only exports pxr_tc_launch_act<a>().
+#ifndef PXR_TC_TU
+#define PXR_TC_TU 0
+#endif
+
 namespace tc {
 
 constexpr int D = 64, H1 = 512, H2 = 256, H3 = 128;
@@ -174,10 +181,27 @@ __device__ __forceinline__ Unit decode_unit(const Params& p, int w) {
 // ---------------------------------------------------------------------------------------------
 // 16-bit operand format helpers
 // ---------------------------------------------------------------------------------------------
-template <int FMT> __device__ __forceinline__ uint32_t relu_pack(float lo, float hi) {
+// fusion_activation (multimodal.py:150-167) of the hidden layers inside the fused chain.  ReLU is one cvt.relu per pair of
+// values; the others are evaluated on the fp32 accumulator before the 16-bit rounding: leaky_relu = max(x, 0.01 x),
+// silu = x / (1 + e^-x) and tanh = 1 - 2 / (1 + e^2x) with MUFU exp / reciprocal (relative error ~1e-6, far below half a
+// 16-bit ulp), gelu with erff as in the fp32 kernels.  act(0) = 0 for all five, so zero-padded hidden units stay exact.
+template <int ACT> __device__ __forceinline__ float act_fast(float x) {
+  if (ACT == PXR_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == PXR_ACT_LEAKY_RELU) return fmaxf(x, 0.01f * x);
+  if (ACT == PXR_ACT_SILU) return __fdividef(x, 1.f + __expf(-x));
+  if (ACT == PXR_ACT_TANH) return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x));
+  return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));      // PXR_ACT_GELU (erf form, nn.GELU default)
+}
+template <int ACT, int FMT> __device__ __forceinline__ uint32_t act_pack(float lo, float hi) {
   uint32_t d;
-  if (FMT == FMT_BF16) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  else asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));   // saturate: no inf from fp16 range
+  if (ACT == PXR_ACT_RELU) {
+    if (FMT == FMT_BF16) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));   // saturate: no inf from fp16 range
+  } else {
+    lo = act_fast<ACT>(lo); hi = act_fast<ACT>(hi);
+    if (FMT == FMT_BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  }
   return d;
 }
 template <int FMT> __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
@@ -199,31 +223,31 @@ template <int FMT> __host__ __device__ constexpr uint32_t idesc(int M, int N) {
 // ---------------------------------------------------------------------------------------------
 // epilogue pieces (one warp = 32 TMEM lanes = 32 rows; taddr already carries the lane base)
 // ---------------------------------------------------------------------------------------------
-template <int FMT>
-__device__ __forceinline__ void bias_relu_pack32(const uint32_t* v, const float* bias, uint32_t* o) {
+template <int ACT, int FMT>
+__device__ __forceinline__ void bias_act_pack32(const uint32_t* v, const float* bias, uint32_t* o) {
   const float4* bb = reinterpret_cast<const float4*>(bias);
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b = bb[q];
-    o[2 * q] = relu_pack<FMT>(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y);
-    o[2 * q + 1] = relu_pack<FMT>(__uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w);
+    o[2 * q] = act_pack<ACT, FMT>(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y);
+    o[2 * q + 1] = act_pack<ACT, FMT>(__uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w);
   }
 }
 
 // 64 fp32 accumulator columns -> 32 packed 16-bit columns written over the start of the same region
-template <int FMT>
+template <int ACT, int FMT>
 __device__ __forceinline__ void epi_pack64(uint32_t t_src, uint32_t t_dst, const float* bias) {
   uint32_t v0[32], v1[32], o[32];
   ptx::tmem_ld32(t_src, v0);
   ptx::tmem_ld32(t_src + 32, v1);
   ptx::tc_wait_ld();
-  bias_relu_pack32<FMT>(v0, bias, o);
-  bias_relu_pack32<FMT>(v1, bias + 32, o + 16);
+  bias_act_pack32<ACT, FMT>(v0, bias, o);
+  bias_act_pack32<ACT, FMT>(v1, bias + 32, o + 16);
   ptx::tmem_st32(t_dst, o);
 }
 
-// concat layer 1 for one row and one 64-wide chunk: relu(Pu[user] + Pi[item]) -> 32 packed columns
-template <int FMT>
+// concat layer 1 for one row and one 64-wide chunk: act(Pu[user] + Pi[item]) -> 32 packed columns
+template <int ACT, int FMT>
 __device__ __forceinline__ void concat_h1_chunk(const uint8_t* pi_row, const uint8_t* pu_row, uint32_t t_dst) {
   uint32_t o[32];
 #pragma unroll
@@ -232,10 +256,10 @@ __device__ __forceinline__ void concat_h1_chunk(const uint8_t* pi_row, const uin
     const float4 a = *reinterpret_cast<const float4*>(pu_row + 32 * q);
     const float4 b = *reinterpret_cast<const float4*>(pu_row + 32 * q + 16);
     const float2 p0 = unpack2<FMT>(pv.x), p1 = unpack2<FMT>(pv.y), p2 = unpack2<FMT>(pv.z), p3 = unpack2<FMT>(pv.w);
-    o[4 * q + 0] = relu_pack<FMT>(a.x + p0.x, a.y + p0.y);
-    o[4 * q + 1] = relu_pack<FMT>(a.z + p1.x, a.w + p1.y);
-    o[4 * q + 2] = relu_pack<FMT>(b.x + p2.x, b.y + p2.y);
-    o[4 * q + 3] = relu_pack<FMT>(b.z + p3.x, b.w + p3.y);
+    o[4 * q + 0] = act_pack<ACT, FMT>(a.x + p0.x, a.y + p0.y);
+    o[4 * q + 1] = act_pack<ACT, FMT>(a.z + p1.x, a.w + p1.y);
+    o[4 * q + 2] = act_pack<ACT, FMT>(b.x + p2.x, b.y + p2.y);
+    o[4 * q + 3] = act_pack<ACT, FMT>(b.z + p3.x, b.w + p3.y);
   }
   ptx::tmem_st32(t_dst, o);
 }
@@ -556,7 +580,8 @@ __device__ __forceinline__ void attn_item_step(const AttnUserFrag& U, const uint
 // FUS selects the front end.  GATED below means "layer 1 runs on the tensor pipe from an A1 tile in shared memory"
 // (gated and attention fusion: the fused vector depends on the pair); concat feeds layer-1 partial sums instead.
 // TK2: two top-K warps (short units, where list updates are a visible share of the work) instead of one.
-template <int FUS, int FMT, bool TK2>
+// ACT: fusion_activation of the hidden layers (pxr_act; ReLU is the fast default, see act_pack).
+template <int FUS, int FMT, bool TK2, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads<FUS>(), 1)
 score_fused_kernel(const __grid_constant__ Params p) {
   constexpr int NT = n_threads<FUS>();
@@ -1024,8 +1049,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
       ptx::mbar_wait(BAR(BAR_D2_FULL), Tp & 1);
       ptx::tc_fence_after();
       const uint32_t c0 = MP::TM_D2 + grp * 128;
-      epi_pack64<FMT>(tl + c0, tl + c0, PXR_CB2 + grp * 128);
-      epi_pack64<FMT>(tl + c0 + 64, tl + c0 + 32, PXR_CB2 + grp * 128 + 64);
+      epi_pack64<ACT, FMT>(tl + c0, tl + c0, PXR_CB2 + grp * 128);
+      epi_pack64<ACT, FMT>(tl + c0 + 64, tl + c0 + 32, PXR_CB2 + grp * 128 + 64);
       ptx::tc_wait_st();
       ptx::tc_fence_before();
       __syncwarp();
@@ -1047,10 +1072,10 @@ score_fused_kernel(const __grid_constant__ Params p) {
         for (int i = 0; i < 16; ++i) {
           const float4 b = b3v[i], wv = w4v[i];
           const uint32_t* v = i < 8 ? v0 + 4 * i : v1 + 4 * (i - 8);
-          z = fmaf(fmaxf(__uint_as_float(v[0]) + b.x, 0.f), wv.x, z);
-          z = fmaf(fmaxf(__uint_as_float(v[1]) + b.y, 0.f), wv.y, z);
-          z = fmaf(fmaxf(__uint_as_float(v[2]) + b.z, 0.f), wv.z, z);
-          z = fmaf(fmaxf(__uint_as_float(v[3]) + b.w, 0.f), wv.w, z);
+          z = fmaf(act_fast<ACT>(__uint_as_float(v[0]) + b.x), wv.x, z);
+          z = fmaf(act_fast<ACT>(__uint_as_float(v[1]) + b.y), wv.y, z);
+          z = fmaf(act_fast<ACT>(__uint_as_float(v[2]) + b.z), wv.z, z);
+          z = fmaf(act_fast<ACT>(__uint_as_float(v[3]) + b.w), wv.w, z);
         }
       }
       ptx::tc_fence_before();
@@ -1094,13 +1119,13 @@ score_fused_kernel(const __grid_constant__ Params p) {
       if (GATED) {
         ptx::mbar_wait(BAR(BAR_D1_FULL0 + b), (d1ph >> (ci & 1)) & 1u); d1ph ^= 1u << (ci & 1);
         ptx::tc_fence_after();
-        epi_pack64<FMT>(tl + MP::h1buf(b), tl + MP::h1buf(b), PXR_CB1 + c * 64);
+        epi_pack64<ACT, FMT>(tl + MP::h1buf(b), tl + MP::h1buf(b), PXR_CB1 + c * 64);
       } else {
         const int buf = T & 1;
         if (ci == 0) ptx::mbar_wait(BAR(BAR_PI_FULL0 + buf), (T >> 1) & 1);          // this tile's item partials landed
         const uint32_t n = (ci & 1) ? h1use1++ : h1use0++;
         if (n > 0) { ptx::mbar_wait(BAR(BAR_H1_EMPTY0 + b), (n - 1) & 1); ptx::tc_fence_after(); }   // layer 2 consumed the buffer
-        concat_h1_chunk<FMT>(sm + MP::OFF_PI + buf * MP::PI_BUF + rj * MP::PI_STRIDE + c * 128,
+        concat_h1_chunk<ACT, FMT>(sm + MP::OFF_PI + buf * MP::PI_BUF + rj * MP::PI_STRIDE + c * 128,
                              sm + MP::OFF_PU + ru * MP::PU_STRIDE + c * 256, tl + MP::h1buf(b));
       }
       ptx::tc_wait_st();
@@ -1153,6 +1178,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
   if (warp == 4) ptx::tmem_dealloc_2cta(tmem, 512);
 }
 
+#if PXR_TC_TU == 0
 // ---------------------------------------------------------------------------------------------
 // one-off preparation kernels
 // ---------------------------------------------------------------------------------------------
@@ -1430,13 +1456,15 @@ struct FastWeights {       // lives in h->fast_w; attention: followed by one xc_
   uint4 wo_frag[4 * 4 * 32];   // attention: its 16-bit B fragments for the front end's register MMAs
 };
 
-template <int FUS, int FMT, bool TK2>
+#endif  // PXR_TC_TU == 0
+
+template <int FUS, int FMT, bool TK2, int ACT>
 static int launch_fused_tk(pxr_handle* h, const Params& p, int n_pairs, cudaStream_t st) {
-  auto kern = score_fused_kernel<FUS, FMT, TK2>;
-  const int slot = 2 * FUS + FMT + (TK2 ? 16 : 0);
-  if (!(h->tc_attr_set & (1u << slot))) {
+  auto kern = score_fused_kernel<FUS, FMT, TK2, ACT>;
+  const int slot = ((ACT * 3 + FUS) * 2 + FMT) * 2 + (TK2 ? 1 : 0);         // < 60; bit 63: item_pi_kernel
+  if (!(h->tc_attr_set & (1ull << slot))) {
     PXR_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Map<FUS>::SMEM));
-    h->tc_attr_set |= (1u << slot);
+    h->tc_attr_set |= (1ull << slot);
   }
   pxr_prof_begin(h, st);
   kern<<<2 * n_pairs, n_threads<FUS>(), Map<FUS>::SMEM, st>>>(p);
@@ -1449,14 +1477,39 @@ static int launch_fused_tk(pxr_handle* h, const Params& p, int n_pairs, cudaStre
 // The number of list updates per user grows like K (1 + ln(n / K)) with the n item rows of a unit, most of them at its
 // start: below ~8 K rows per unit one inserting warp is the bottleneck (measured: 10 K items x 1 024 users 5.1 -> 3.5 ms with
 // two); for long units the second warp only costs the front end issue slots (-2.8 % on the gated headline config).
-template <int FUS, int FMT>
+template <int FUS, int FMT, int ACT>
 static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_t st) {
   static int thr = -1;                    // PXR_TK2_ROWS: rows per unit below which the second top-K warp is used (experiments)
   if (thr < 0) { const char* e = getenv("PXR_TK2_ROWS"); thr = e ? atoi(e) : 8192; }
-  return p.rows_per_split < thr ? launch_fused_tk<FUS, FMT, true>(h, p, n_pairs, st) : launch_fused_tk<FUS, FMT, false>(h, p, n_pairs, st);
+  return p.rows_per_split < thr ? launch_fused_tk<FUS, FMT, true, ACT>(h, p, n_pairs, st)
+                                : launch_fused_tk<FUS, FMT, false, ACT>(h, p, n_pairs, st);
+}
+
+// every (front end, operand format) of one activation
+template <int ACT>
+static int launch_fused_act(pxr_handle* h, const Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st) {
+  if (fusion == PXR_FUSION_GATED)
+    return fmt == FMT_BF16 ? launch_fused<F_GATED, FMT_BF16, ACT>(h, p, n_pairs, st) : launch_fused<F_GATED, FMT_FP16, ACT>(h, p, n_pairs, st);
+  if (fusion == PXR_FUSION_ATTENTION)
+    return fmt == FMT_BF16 ? launch_fused<F_ATTN, FMT_BF16, ACT>(h, p, n_pairs, st) : launch_fused<F_ATTN, FMT_FP16, ACT>(h, p, n_pairs, st);
+  return fmt == FMT_BF16 ? launch_fused<F_CONCAT, FMT_BF16, ACT>(h, p, n_pairs, st) : launch_fused<F_CONCAT, FMT_FP16, ACT>(h, p, n_pairs, st);
 }
 
 }  // namespace tc
+
+// launchers of the other activations' objects (same signature in every TU)
+#define PXR_TC_CAT2(a, b) a##b
+#define PXR_TC_CAT(a, b) PXR_TC_CAT2(a, b)
+#if PXR_TC_TU != 0
+int PXR_TC_CAT(pxr_tc_launch_act, PXR_TC_TU)(pxr_handle* h, const tc::Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st) {
+  return tc::launch_fused_act<PXR_TC_TU>(h, p, fusion, fmt, n_pairs, st);
+}
+#else
+int pxr_tc_launch_act1(pxr_handle* h, const tc::Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st);   // gelu
+int pxr_tc_launch_act2(pxr_handle* h, const tc::Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st);   // tanh
+int pxr_tc_launch_act3(pxr_handle* h, const tc::Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st);   // leaky_relu
+int pxr_tc_launch_act4(pxr_handle* h, const tc::Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st);   // silu
+static_assert(PXR_ACT_GELU == 1 && PXR_ACT_TANH == 2 && PXR_ACT_LEAKY_RELU == 3 && PXR_ACT_SILU == 4, "object <-> activation mapping");
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -1470,7 +1523,6 @@ const char* pxr_tc_unsupported_reason(const pxr_handle* h) {
     return "fusion_hidden_dims exceeds [512, 256, 128] (the three weight matrices are resident in the CTA pair's shared memory)";
   // smaller hidden layers run zero-padded to [512, 256, 128]; concat feeds layer-1 partials of exactly 512 columns
   if (c.fusion == PXR_FUSION_CONCAT && c.hidden[0] != tc::H1) return "concat fusion with fusion_hidden_dims[0] != 512";
-  if (c.activation != PXR_ACT_RELU) return "fusion_activation is not relu (the in-place TMEM epilogues use cvt.relu)";
   if (h->M < 4 || h->M > 6) return "fewer than 4 modalities";
   if (c.fusion == PXR_FUSION_ATTENTION && c.num_heads != tc::NH) return "attention fusion with num_attention_heads != 4";
   if (c.fusion != PXR_FUSION_CONCAT && c.embedding_dim != tc::D) return "gated / attention fusion with embedding_dim != 64 (layer 1 is a K = 64 MMA)";
@@ -1551,9 +1603,9 @@ int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t s
     const int FD = (h->M - 1) * h->cfg.embedding_dim;
     const size_t smem = (size_t)32 * (FD + tc::H1) * sizeof(float);
     if (smem > (size_t)h->max_smem_optin) PXR_FAIL(h, PXR_ERR_INVALID, "concat item partial: embedding_dim %d needs the tensor-pipe item path", h->cfg.embedding_dim);
-    if (!(h->tc_attr_set & 256u)) {
+    if (!(h->tc_attr_set & (1ull << 63))) {
       PXR_CUDA(h, cudaFuncSetAttribute(tc::item_pi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      h->tc_attr_set |= 256u;
+      h->tc_attr_set |= (1ull << 63);
     }
     tc::item_pi_kernel<<<(unsigned)((n_rows + 31) / 32), PXR_SIMT_THREADS, smem, st>>>(h->item_feats, h->mlp[0].wt, h->mlp[0].b,
                                                                                        h->M, h->cfg.embedding_dim, n_rows, (uint16_t*)ws, tc_fmt(h));
@@ -1655,12 +1707,14 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
   p.out_scores = part_s; p.out_idx = part_i;
   int rc;
   const int fmt = tc_fmt(h);
-  if (gated) rc = fmt == tc::FMT_BF16 ? tc::launch_fused<tc::F_GATED, tc::FMT_BF16>(h, p, pl.n_pairs, st)
-                                      : tc::launch_fused<tc::F_GATED, tc::FMT_FP16>(h, p, pl.n_pairs, st);
-  else if (attn) rc = fmt == tc::FMT_BF16 ? tc::launch_fused<tc::F_ATTN, tc::FMT_BF16>(h, p, pl.n_pairs, st)
-                                          : tc::launch_fused<tc::F_ATTN, tc::FMT_FP16>(h, p, pl.n_pairs, st);
-  else rc = fmt == tc::FMT_BF16 ? tc::launch_fused<tc::F_CONCAT, tc::FMT_BF16>(h, p, pl.n_pairs, st)
-                                : tc::launch_fused<tc::F_CONCAT, tc::FMT_FP16>(h, p, pl.n_pairs, st);
+  switch (h->cfg.activation) {
+    case PXR_ACT_RELU: rc = tc::launch_fused_act<PXR_ACT_RELU>(h, p, h->cfg.fusion, fmt, pl.n_pairs, st); break;
+    case PXR_ACT_GELU: rc = pxr_tc_launch_act1(h, p, h->cfg.fusion, fmt, pl.n_pairs, st); break;
+    case PXR_ACT_TANH: rc = pxr_tc_launch_act2(h, p, h->cfg.fusion, fmt, pl.n_pairs, st); break;
+    case PXR_ACT_LEAKY_RELU: rc = pxr_tc_launch_act3(h, p, h->cfg.fusion, fmt, pl.n_pairs, st); break;
+    case PXR_ACT_SILU: rc = pxr_tc_launch_act4(h, p, h->cfg.fusion, fmt, pl.n_pairs, st); break;
+    default: PXR_FAIL(h, PXR_ERR_INVALID, "unknown fusion_activation %d", h->cfg.activation);
+  }
   if (rc) return rc;
   if (pl.S > 1) {
     rc = pxr_launch_merge(part_s, part_i, pl.S, n_users, kk, list_s, list_i, st);
@@ -1670,3 +1724,4 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
   if (exact) return pxr_launch_rescore(h, user_embedding, user_idx, n_users, list_i, k, out_scores, out_idx, wp, st);
   return PXR_OK;
 }
+#endif  // PXR_TC_TU == 0

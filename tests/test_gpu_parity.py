@@ -622,6 +622,36 @@ def test_tcgen05_smaller_mlp_zero_padded(fusion, hidden):
         _check_topk(xs[u].astype(np.float64), xi[u], ref[u], k, idx[indptr[u]:indptr[u + 1]], SIMT_TOL, 0.0)
 
 
+@pytest.mark.parametrize("fusion,act", [("gated", "gelu"), ("gated", "tanh"), ("gated", "leaky_relu"), ("gated", "silu"),
+                                        ("concatenate", "gelu"), ("concatenate", "silu"), ("concatenate", "leaky_relu"),
+                                        ("attention", "tanh"), ("attention", "silu")])
+def test_tcgen05_any_fusion_activation(fusion, act):
+    """Every `fusion_activation` of the reference (multimodal.py:150-167) runs on the fused path (the hidden-layer epilogues
+    are templated on it; round 1 / early round 2 sent everything but ReLU to the generic fp32 kernels): kernel == the
+    emulated oracle with that activation, exact mode == the fp32 oracle."""
+    n_users, n_items, k = 40, 900, 50
+    spec = syn.ModelSpec(n_users=n_users, n_items=n_items, fusion_type=fusion, fusion_activation=act)
+    sd = syn.make_state_dict(spec, seed=syn.SEED + 29)
+    feats = syn.make_item_features(spec, seed=syn.SEED + 29)
+    syn.condition_like_trained(sd, spec, feats)
+    indptr, idx, _ = syn.make_histories(n_users, n_items, seed=syn.SEED + 29, lo=3, hi=40)
+    model, eng = _engine_for(spec, sd, feats, "auto")
+    assert eng.active_path == "tcgen05", eng.path_reason
+    users = np.arange(n_users)
+    args = (model.user_embedding.weight.detach(), torch.from_numpy(users).cuda(), k, torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda())
+    s, i = _structural_checks(*eng.score_topk(*args), k, n_items, indptr, idx)
+    emu = _lowp_scores(sd, spec, feats, users)
+    errs = np.concatenate([np.abs(s[u].astype(np.float64) - emu[u][i[u]]) for u in users])
+    assert np.quantile(errs, 0.9) <= TC_EMU_TOL["bf16"] / 8, float(np.quantile(errs, 0.9))
+    same = sum(_check_topk(s[u].astype(np.float64), i[u], emu[u], k, idx[indptr[u]:indptr[u + 1]], _emu_tol(fusion, "bf16"), 0.0) for u in users)
+    assert same >= 0.9 * k * n_users      # the rest are swaps inside the flip band (checked position by position above)
+    eng.set_rescore(True)
+    xs, xi = _structural_checks(*eng.score_topk(*args), k, n_items, indptr, idx)
+    ref = orc.score_block(sd, cs.spec_cfg(spec), users, 0, n_items, feats)
+    for u in users:
+        _check_topk(xs[u].astype(np.float64), xi[u], ref[u], k, idx[indptr[u]:indptr[u + 1]], SIMT_TOL, 0.0)
+
+
 @pytest.mark.parametrize("D", [16, 128, 320, 512])
 def test_tcgen05_concat_any_embedding_dim(D):
     """concat fusion on the fused path for embedding dims other than 64 (BASELINE.json configs[4] sweeps 64-512):
