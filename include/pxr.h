@@ -163,7 +163,10 @@ int pxr_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* us
  * forward, src/models/multimodal.py:528-610 -- and ranked again with the reference's stable order
  * (src/inference/recommender.py:105-106, ties -> lower item index).  Returned scores then meet the fp32 tolerance
  * (1e-4) and the list equals the reference's whenever its top-K lies inside the 16-bit top-64.  The SIMT path is
- * always exact.  on = 0 returns the 16-bit scores and order as they are (K <= 64 either way). */
+ * always exact.  on = 0 returns the 16-bit scores and order as they are.
+ * top_k > 64 (up to 1 024): the kernel's per-user list has 64 slots, so the fused kernel runs once per 64-slot PAGE --
+ * page p admits only keys strictly below the user's last key of page p - 1 -- and the ceil(K / 64) * 64 candidates are
+ * re-scored / returned as above (cost: ceil(K / 64) passes; round 1 sent such calls to the generic fp32 kernels). */
 int pxr_set_rescore(pxr_handle* h, int on);
 int pxr_get_rescore(const pxr_handle* h);
 
@@ -178,6 +181,12 @@ size_t pxr_rescore_bytes(int64_t n_users);
 int pxr_rescore_topk(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
                      const int32_t* cand_idx, int32_t k, float* out_scores, int32_t* out_idx, void* workspace,
                      size_t workspace_bytes, pxr_stream stream);
+/* The same for candidate lists of list_len = 64 * pages slots (pages <= 16; what a top_k > 64 call keeps):
+ *   cand_idx : (n_users, list_len) ;  out_* : (n_users, K), K <= list_len ;  workspace : pxr_rescore_lists_bytes() bytes */
+size_t pxr_rescore_lists_bytes(int64_t n_users, int32_t list_len);
+int pxr_rescore_lists(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
+                      const int32_t* cand_idx, int32_t list_len, int32_t k, float* out_scores, int32_t* out_idx,
+                      void* workspace, size_t workspace_bytes, pxr_stream stream);
 
 /* on = 1: pxr_precompute_items of this handle keeps only the fp32 item records (1 280 B per item at D = 64) and skips the
  * fused kernel's per-item extras (up to 16.5 KB per item for attention): for a handle that only serves pxr_rescore_topk /
@@ -314,7 +323,7 @@ int64_t pxr_launch_count(const pxr_handle* h);       /* kernels launched through
 int pxr_active_path(const pxr_handle* h);            /* pxr_path pxr_score_topk will use      */
 /* why PXR_PATH_AUTO resolved to the generic fp32 SIMT kernels ("" when the fused tcgen05 kernel is active): the
  * generic path is ~100x slower, so the host logs this once per model (it is exact, and it too keeps the running
- * top-K on chip: no users x items score matrix in HBM).  A call with top_k > 64 on a tcgen05 handle also takes it. */
+ * top-K on chip: no users x items score matrix in HBM).  A call with top_k > 1 024 on a tcgen05 handle also takes it. */
 const char* pxr_path_reason(const pxr_handle* h);
 int pxr_set_path(pxr_handle* h, int path);           /* force SIMT / tcgen05 (tests)          */
 

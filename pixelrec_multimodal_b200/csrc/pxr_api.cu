@@ -307,18 +307,28 @@ extern "C" int pxr_score_pairs(pxr_handle* h, const float* user_embedding, const
   return pxr_launch_score_simt(h, user_embedding, user_idx, item_row, n, out, out_logit, (cudaStream_t)stream);
 }
 
-extern "C" size_t pxr_rescore_bytes(int64_t n_users) { return n_users > 0 ? pxr_rescore_list_bytes(n_users) + 256 : 256; }
+extern "C" size_t pxr_rescore_lists_bytes(int64_t n_users, int32_t list_len) {
+  return n_users > 0 && list_len > 0 ? pxr_rescore_list_bytes(n_users, list_len) + 256 : 256;
+}
+extern "C" size_t pxr_rescore_bytes(int64_t n_users) { return pxr_rescore_lists_bytes(n_users, 64); }
+
+extern "C" int pxr_rescore_lists(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
+                                 const int32_t* cand_idx, int32_t list_len, int32_t k, float* out_scores, int32_t* out_idx,
+                                 void* workspace, size_t workspace_bytes, pxr_stream stream) {
+  if (!h) return PXR_ERR_INVALID;
+  if (!h->weights_loaded || !h->items_ready || !h->item_feats) PXR_FAIL(h, PXR_ERR_STATE, "weights / items not loaded");
+  if (list_len < 64 || list_len > 1024 || list_len % 64) PXR_FAIL(h, PXR_ERR_INVALID, "pxr_rescore_lists: list_len must be a multiple of 64 up to 1024");
+  if (k <= 0 || k > list_len || n_users < 0 || (n_users && (!user_embedding || !user_idx || !cand_idx || !out_scores || !out_idx)))
+    PXR_FAIL(h, PXR_ERR_INVALID, "pxr_rescore_lists: bad arguments (1 <= k <= list_len)");
+  if (n_users == 0) return PXR_OK;
+  if (workspace_bytes < pxr_rescore_lists_bytes(n_users, list_len) || !workspace) PXR_FAIL(h, PXR_ERR_WORKSPACE, "re-score workspace too small");
+  return pxr_launch_rescore(h, user_embedding, user_idx, n_users, cand_idx, list_len, k, out_scores, out_idx, workspace, (cudaStream_t)stream);
+}
 
 extern "C" int pxr_rescore_topk(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
                                 const int32_t* cand_idx, int32_t k, float* out_scores, int32_t* out_idx, void* workspace,
                                 size_t workspace_bytes, pxr_stream stream) {
-  if (!h) return PXR_ERR_INVALID;
-  if (!h->weights_loaded || !h->items_ready || !h->item_feats) PXR_FAIL(h, PXR_ERR_STATE, "weights / items not loaded");
-  if (k <= 0 || k > 64 || n_users < 0 || (n_users && (!user_embedding || !user_idx || !cand_idx || !out_scores || !out_idx)))
-    PXR_FAIL(h, PXR_ERR_INVALID, "pxr_rescore_topk: bad arguments (1 <= k <= 64)");
-  if (n_users == 0) return PXR_OK;
-  if (workspace_bytes < pxr_rescore_bytes(n_users) || !workspace) PXR_FAIL(h, PXR_ERR_WORKSPACE, "re-score workspace too small");
-  return pxr_launch_rescore(h, user_embedding, user_idx, n_users, cand_idx, k, out_scores, out_idx, workspace, (cudaStream_t)stream);
+  return pxr_rescore_lists(h, user_embedding, user_idx, n_users, cand_idx, 64, k, out_scores, out_idx, workspace, workspace_bytes, stream);
 }
 
 extern "C" int pxr_merge_topk(const float* scores_in, const int32_t* idx_in, int32_t n_shards, int64_t n_users,

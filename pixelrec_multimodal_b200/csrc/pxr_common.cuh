@@ -229,10 +229,12 @@ int pxr_launch_topk_rows(pxr_handle* h, const float* scores, int64_t n_users, in
                          int32_t k, float* out_scores, int32_t* out_idx, cudaStream_t st);
 int pxr_launch_merge(const float* scores_in, const int32_t* idx_in, int32_t n_shards, int64_t n_users, int32_t k,
                      float* out_scores, int32_t* out_idx, cudaStream_t st);
-// exact mode: fp32 re-score + re-rank of (n_users, 64) candidate lists (global indices, -1 padded) -> (n_users, k)
-size_t pxr_rescore_list_bytes(int64_t n_users);
+// exact mode: fp32 re-score + re-rank of (n_users, list_len) candidate lists (global indices, -1 padded; list_len = 64 or a
+// multiple of 64 up to 1 024) -> (n_users, k)
+size_t pxr_rescore_list_bytes(int64_t n_users, int32_t list_len);
 int pxr_launch_rescore(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
-                       const int32_t* list_idx, int32_t k, float* out_scores, int32_t* out_idx, void* ws, cudaStream_t st);
+                       const int32_t* list_idx, int32_t list_len, int32_t k, float* out_scores, int32_t* out_idx, void* ws,
+                       cudaStream_t st);
 int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, const int64_t* gt_indptr,
                        const int32_t* gt_idx, const int32_t* recall_den, const int32_t* ks, int32_t n_ks, const double* discount,
                        const double* ideal, double* out_sums, void* ws, cudaStream_t st);
@@ -240,6 +242,7 @@ int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_user
 // tcgen05 path (score_tc.cu)
 bool pxr_tc_supported(const pxr_handle* h);
 const char* pxr_tc_unsupported_reason(const pxr_handle* h);   // NULL = supported
+#define PXR_TC_MAX_K 1024   // 16 pages of the fused kernel's 64-slot lists
 bool pxr_tc_can_run(const pxr_handle* h, int32_t k);   // this call (k, shard size) fits the kernel's limits
 size_t pxr_tc_weight_bytes(const pxr_handle* h);
 int pxr_tc_prepare_weights(pxr_handle* h, cudaStream_t st);

@@ -98,6 +98,7 @@ struct MiscT {
   float eu[ATT ? 1 : TU][D];
   float lu[ATT ? 1 : TU][8];
   unsigned long long list[TU][KCAP];
+  unsigned long long upper[TU];                      // per user slot: only keys strictly below it are admitted (pages of a top_k > 64 call)
   unsigned long long queue[QC];
   float thr[TU];
   uint32_t seen_mask[4][TU];
@@ -159,6 +160,8 @@ struct Params {
   const int64_t* seen_indptr;   // (n_users + 1,) or NULL
   const int32_t* seen_idx;      // global item indices, ascending per user
   const uint8_t* item_missing;  // per item row: 1 = features missing, the score is 0.0 (recommender.py:229-230); NULL = none
+  const unsigned long long* upper;   // [n_users] or NULL.  Page p > 0 of a top_k > 64 call: the key (ordered score << 32 | IDX_MASK - index)
+                                // of the user's last entry of page p - 1; only strictly smaller keys are admitted (0: nothing is left)
   float* out_scores;            // [S][n_users][K]
   int32_t* out_idx;
   int64_t n_users, n_rows, item_base;
@@ -633,7 +636,11 @@ score_fused_kernel(const __grid_constant__ Params p) {
   }
   for (int i = threadIdx.x; i < TU * KCAP; i += NT) (&ms.list[0][0])[i] = 0ull;
   for (int i = threadIdx.x; i < QC; i += NT) ms.queue[i] = 0ull;
-  if (threadIdx.x < TU) ms.thr[threadIdx.x] = -INFINITY;
+  if (threadIdx.x < TU) {
+    ms.thr[threadIdx.x] = -INFINITY;
+    const int64_t ord = ((int64_t)(pair / p.S) * 2 + rank) * TU + threadIdx.x;       // user slot of this CTA's first unit
+    ms.upper[threadIdx.x] = (p.upper && ord < p.n_users) ? p.upper[ord] : ~0ull;
+  }
   __syncthreads();
   if (warp == 4) {
     if (lane == 0) {   // this CTA's half of every weight matrix: 16 KB bulk copies through the TMA engine
@@ -1022,6 +1029,10 @@ score_fused_kernel(const __grid_constant__ Params p) {
         }
         if (lane == 0) ms.thr[u] = -INFINITY;
       }
+      if (p.upper && w + n_pairs < p.n_units && lane >= u_lo && lane < u_hi) {        // the next unit's page bounds
+        const int64_t ord = ((int64_t)((w + n_pairs) / p.S) * 2 + rank) * TU + lane;
+        ms.upper[lane] = ord < p.n_users ? p.upper[ord] : ~0ull;
+      }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_local(BAR(BAR_UNIT_RESET));
     }
@@ -1087,13 +1098,15 @@ score_fused_kernel(const __grid_constant__ Params p) {
       const bool ok = row >= 0 && !((ms.seen_mask[Tp & 3][ru] >> rj) & 1u);
       if (ok && y >= *reinterpret_cast<volatile float*>(&ms.thr[ru])) {
         const uint32_t gidx = (uint32_t)(p.item_base + row);
-        const unsigned long long e = ((unsigned long long)pxr_ord(y) << 32) | ((unsigned long long)ru << 28) |
-                                     (unsigned long long)(IDX_MASK - gidx);
-        const int qh = TK2 ? (ru >= TU / 2 ? 1 : 0) : 0;
-        constexpr uint32_t qcap = TK2 ? QC / 2 : QC;
-        const uint32_t slot = atomicAdd(&ms.q_tail[qh], 1u);
-        while (slot - *reinterpret_cast<volatile uint32_t*>(&ms.q_head[qh]) >= qcap) __nanosleep(64);
-        *reinterpret_cast<volatile unsigned long long*>(&ms.queue[qh * (QC / 2) + (slot & (qcap - 1))]) = e;
+        const unsigned long long key = ((unsigned long long)pxr_ord(y) << 32) | (unsigned long long)(IDX_MASK - gidx);
+        if (key < *reinterpret_cast<volatile unsigned long long*>(&ms.upper[ru])) {      // always true without page bounds (~0)
+          const unsigned long long e = key | ((unsigned long long)ru << 28);
+          const int qh = TK2 ? (ru >= TU / 2 ? 1 : 0) : 0;
+          constexpr uint32_t qcap = TK2 ? QC / 2 : QC;
+          const uint32_t slot = atomicAdd(&ms.q_tail[qh], 1u);
+          while (slot - *reinterpret_cast<volatile uint32_t*>(&ms.q_head[qh]) >= qcap) __nanosleep(64);
+          *reinterpret_cast<volatile unsigned long long*>(&ms.queue[qh * (QC / 2) + (slot & (qcap - 1))]) = e;
+        }
       }
       if (last_of_unit) {
         __syncwarp();
@@ -1448,6 +1461,20 @@ __global__ void attn_fold_ln_kernel(const float* __restrict__ w1, const float* _
   if (n < D) s1_out[n] = ln_w[n] / (float)M;
 }
 
+// top_k > 64: the merged 64-slot list of page `page` goes into the user's candidate row (64 * n_pages slots), and the key
+// of its last entry becomes the bound of the next page (0 = the list was not full: nothing is left for the next page)
+__global__ void page_commit_kernel(const float* __restrict__ page_s, const int32_t* __restrict__ page_i, int64_t n_users, int page,
+                                   int n_pages, float* __restrict__ cand_s, int32_t* __restrict__ cand_i,
+                                   unsigned long long* __restrict__ upper) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_users * KCAP) return;
+  const int64_t u = i / KCAP; const int j = (int)(i % KCAP);
+  const float sc = page_s[i]; const int32_t gi = page_i[i];
+  const int64_t o = (u * n_pages + page) * KCAP + j;
+  cand_s[o] = sc; cand_i[o] = gi;
+  if (j == KCAP - 1) upper[u] = gi >= 0 ? (((unsigned long long)pxr_ord(sc) << 32) | (unsigned long long)(IDX_MASK - (uint32_t)gi)) : 0ull;
+}
+
 struct FastWeights {       // lives in h->fast_w; attention: followed by one xc_0 scratch (ATT_XC0_U4 x 16 B) per SM
   uint8_t wimg[2 * Map<F_GATED>::WIMG];
   float bias[H1 + H2 + H3 + H3 + 4];
@@ -1538,7 +1565,7 @@ const char* pxr_tc_unsupported_reason(const pxr_handle* h) {
 bool pxr_tc_supported(const pxr_handle* h) { return pxr_tc_unsupported_reason(h) == nullptr; }
 
 bool pxr_tc_can_run(const pxr_handle* h, int32_t k) {
-  return h->fast_ok && k <= tc::KCAP && h->n_rows > 0 && h->item_base + h->n_rows < (int64_t)tc::IDX_MASK;
+  return h->fast_ok && k <= PXR_TC_MAX_K && h->n_rows > 0 && h->item_base + h->n_rows < (int64_t)tc::IDX_MASK;
 }
 
 size_t pxr_tc_weight_bytes(const pxr_handle* h) {
@@ -1645,21 +1672,44 @@ static TcPlan tc_plan(const pxr_handle* h, int64_t n_users) {
   return pl;
 }
 
+static int tc_pages(int32_t k) { return (k + tc::KCAP - 1) / tc::KCAP; }
+
 // workspace: [S > 1: per-split partial lists][exact mode: the merged 64-slot lists + the re-score pair arrays]
+// top_k > 64 (pages): [partial lists][one page list][candidate rows of 64 * pages slots][page bounds][re-score arrays]
 size_t pxr_tc_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k) {
   if (n_users <= 0 || h->n_rows <= 0) return 256;
   const TcPlan pl = tc_plan(h, n_users);
-  const int kk = h->rescore ? tc::KCAP : k;
+  const int P = tc_pages(k);
   size_t b = 256;
+  if (P > 1) {
+    const size_t page = (size_t)n_users * tc::KCAP * 8;
+    if (pl.S > 1) b += pxr_align_up((size_t)pl.S * page, 256);
+    b += pxr_align_up(page, 256) + pxr_align_up(page * P, 256) + pxr_align_up((size_t)n_users * 8, 256);
+    if (h->rescore) b += pxr_rescore_list_bytes(n_users, P * tc::KCAP);
+    return b;
+  }
+  const int kk = h->rescore ? tc::KCAP : k;
   if (pl.S > 1) b += pxr_align_up((size_t)pl.S * n_users * kk * 8, 256);
-  if (h->rescore) b += pxr_align_up((size_t)n_users * kk * 8, 256) + pxr_rescore_list_bytes(n_users);
+  if (h->rescore) b += pxr_align_up((size_t)n_users * kk * 8, 256) + pxr_rescore_list_bytes(n_users, tc::KCAP);
   return b;
+}
+
+static int tc_launch(pxr_handle* h, const tc::Params& p, int n_pairs, cudaStream_t st) {
+  const int fmt = tc_fmt(h);
+  switch (h->cfg.activation) {
+    case PXR_ACT_RELU: return tc::launch_fused_act<PXR_ACT_RELU>(h, p, h->cfg.fusion, fmt, n_pairs, st);
+    case PXR_ACT_GELU: return pxr_tc_launch_act1(h, p, h->cfg.fusion, fmt, n_pairs, st);
+    case PXR_ACT_TANH: return pxr_tc_launch_act2(h, p, h->cfg.fusion, fmt, n_pairs, st);
+    case PXR_ACT_LEAKY_RELU: return pxr_tc_launch_act3(h, p, h->cfg.fusion, fmt, n_pairs, st);
+    case PXR_ACT_SILU: return pxr_tc_launch_act4(h, p, h->cfg.fusion, fmt, n_pairs, st);
+    default: PXR_FAIL(h, PXR_ERR_INVALID, "unknown fusion_activation %d", h->cfg.activation);
+  }
 }
 
 int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
                       const int64_t* seen_indptr, const int32_t* seen_idx, int32_t k, float* out_scores, int32_t* out_idx,
                       void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (!pxr_tc_can_run(h, k)) PXR_FAIL(h, PXR_ERR_INVALID, "tcgen05 path cannot run this call (top_k <= %d, 28-bit item index)", tc::KCAP);
+  if (!pxr_tc_can_run(h, k)) PXR_FAIL(h, PXR_ERR_INVALID, "tcgen05 path cannot run this call (top_k <= %d, 28-bit item index)", PXR_TC_MAX_K);
   const TcPlan pl = tc_plan(h, n_users);
   tc::FastWeights* fw = reinterpret_cast<tc::FastWeights*>(h->fast_w);
   const bool gated = h->cfg.fusion == PXR_FUSION_GATED;
@@ -1686,11 +1736,44 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
   // exact mode: the kernel keeps its full 64-slot list per user (admission threshold = 64th best); the lists are
   // re-scored in fp32 and re-ranked afterwards (pxr_launch_rescore)
   const bool exact = h->rescore;
-  const int32_t kk = exact ? tc::KCAP : k;
+  const int P = tc_pages(k);
+  const int32_t kk = (exact || P > 1) ? tc::KCAP : k;
   p.M = h->M; p.K = kk; p.S = pl.S; p.rows_per_split = pl.rows_per_split; p.n_units = pl.n_units;
   p.final_act = h->cfg.final_activation;
   if (ws_bytes < pxr_tc_topk_bytes(h, n_users, k)) PXR_FAIL(h, PXR_ERR_WORKSPACE, "tcgen05 top-K workspace too small");
   char* wp = (char*)ws;
+  if (P > 1) {
+    // ---- top_k > 64: one pass of the fused kernel per 64-slot page, each bounded by the previous page's last key
+    const size_t page = (size_t)n_users * tc::KCAP;
+    float* part_s = nullptr; int32_t* part_i = nullptr;
+    if (pl.S > 1) { part_s = (float*)wp; part_i = (int32_t*)(wp + (size_t)pl.S * page * 4); wp += pxr_align_up((size_t)pl.S * page * 8, 256); }
+    float* page_s = (float*)wp; int32_t* page_i = (int32_t*)(wp + page * 4);
+    wp += pxr_align_up(page * 8, 256);
+    float* cand_s = (float*)wp; int32_t* cand_i = (int32_t*)(wp + page * P * 4);
+    wp += pxr_align_up(page * P * 8, 256);
+    unsigned long long* upper = (unsigned long long*)wp;
+    wp += pxr_align_up((size_t)n_users * 8, 256);
+    for (int pg = 0; pg < P; ++pg) {
+      p.upper = pg ? upper : nullptr;
+      p.out_scores = pl.S > 1 ? part_s : page_s; p.out_idx = pl.S > 1 ? part_i : page_i;
+      int rc = tc_launch(h, p, pl.n_pairs, st);
+      if (rc) return rc;
+      if (pl.S > 1) {
+        rc = pxr_launch_merge(part_s, part_i, pl.S, n_users, tc::KCAP, page_s, page_i, st);
+        h->launches++;
+        if (rc) PXR_FAIL(h, rc, "top-K merge of %d item splits failed", pl.S);
+      }
+      tc::page_commit_kernel<<<(unsigned)((page + 255) / 256), 256, 0, st>>>(page_s, page_i, n_users, pg, P, cand_s, cand_i, upper);
+      h->launches++;
+      PXR_CUDA(h, cudaGetLastError());
+    }
+    const int L = P * tc::KCAP;
+    if (exact) return pxr_launch_rescore(h, user_embedding, user_idx, n_users, cand_i, L, k, out_scores, out_idx, wp, st);
+    // raw mode: the pages are already in descending key order, the first k slots of a row are the list
+    PXR_CUDA(h, cudaMemcpy2DAsync(out_scores, (size_t)k * 4, cand_s, (size_t)L * 4, (size_t)k * 4, (size_t)n_users, cudaMemcpyDeviceToDevice, st));
+    PXR_CUDA(h, cudaMemcpy2DAsync(out_idx, (size_t)k * 4, cand_i, (size_t)L * 4, (size_t)k * 4, (size_t)n_users, cudaMemcpyDeviceToDevice, st));
+    return PXR_OK;
+  }
   float* part_s = out_scores; int32_t* part_i = out_idx;       // what the kernel writes
   float* list_s = out_scores; int32_t* list_i = out_idx;       // the merged lists
   if (pl.S > 1) {
@@ -1705,23 +1788,14 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
     if (pl.S == 1) { part_s = list_s; part_i = list_i; }
   }
   p.out_scores = part_s; p.out_idx = part_i;
-  int rc;
-  const int fmt = tc_fmt(h);
-  switch (h->cfg.activation) {
-    case PXR_ACT_RELU: rc = tc::launch_fused_act<PXR_ACT_RELU>(h, p, h->cfg.fusion, fmt, pl.n_pairs, st); break;
-    case PXR_ACT_GELU: rc = pxr_tc_launch_act1(h, p, h->cfg.fusion, fmt, pl.n_pairs, st); break;
-    case PXR_ACT_TANH: rc = pxr_tc_launch_act2(h, p, h->cfg.fusion, fmt, pl.n_pairs, st); break;
-    case PXR_ACT_LEAKY_RELU: rc = pxr_tc_launch_act3(h, p, h->cfg.fusion, fmt, pl.n_pairs, st); break;
-    case PXR_ACT_SILU: rc = pxr_tc_launch_act4(h, p, h->cfg.fusion, fmt, pl.n_pairs, st); break;
-    default: PXR_FAIL(h, PXR_ERR_INVALID, "unknown fusion_activation %d", h->cfg.activation);
-  }
+  int rc = tc_launch(h, p, pl.n_pairs, st);
   if (rc) return rc;
   if (pl.S > 1) {
     rc = pxr_launch_merge(part_s, part_i, pl.S, n_users, kk, list_s, list_i, st);
     h->launches++;
     if (rc) PXR_FAIL(h, rc, "top-K merge of %d item splits failed", pl.S);
   }
-  if (exact) return pxr_launch_rescore(h, user_embedding, user_idx, n_users, list_i, k, out_scores, out_idx, wp, st);
+  if (exact) return pxr_launch_rescore(h, user_embedding, user_idx, n_users, list_i, tc::KCAP, k, out_scores, out_idx, wp, st);
   return PXR_OK;
 }
 #endif  // PXR_TC_TU == 0

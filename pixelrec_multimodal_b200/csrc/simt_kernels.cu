@@ -838,21 +838,63 @@ __global__ void __launch_bounds__(256) rescore_sort_kernel(const float* __restri
   if (lane + 32 < k) { out_scores[u * k + lane + 32] = x1 ? pxr_key_score(x1) : -INFINITY; out_idx[u * k + lane + 32] = x1 ? (int32_t)pxr_key_idx(x1) : -1; }
 }
 
-size_t pxr_rescore_list_bytes(int64_t n_users) { return pxr_align_up((size_t)n_users * 64 * (8 + 8 + 4), 256); }
+// Lists longer than 64 (top_k > 64: the fused kernel is run once per 64-slot page, score_tc.cu): a block per user sorts the
+// L <= 1 024 keys (score, ~index) in shared memory with a bitonic network and writes the first k.
+__global__ void __launch_bounds__(256) rescore_sort_block_kernel(const float* __restrict__ rescored, const int32_t* __restrict__ list_idx,
+                                                                 int L, int NP2, int k, int64_t item_base, int64_t n_rows,
+                                                                 float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
+  __shared__ unsigned long long keys[1024];
+  const int64_t u = blockIdx.x;
+  for (int j = threadIdx.x; j < NP2; j += blockDim.x) {
+    unsigned long long x = 0ull;
+    if (j < L) {
+      const int32_t gi = list_idx[u * L + j];
+      if (gi >= 0 && gi >= item_base && gi < item_base + n_rows) x = pxr_key(rescored[u * L + j], (uint32_t)gi);
+    }
+    keys[j] = x;
+  }
+  __syncthreads();
+  for (int size = 2; size <= NP2; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < NP2 / 2; t += blockDim.x) {
+        const int i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1)), j = i | stride;      // i < j, the pair of this step
+        const bool desc = (i & size) == 0 || size == NP2;
+        const unsigned long long a = keys[i], b = keys[j];
+        if ((a < b) == desc) { keys[i] = b; keys[j] = a; }
+      }
+      __syncthreads();
+    }
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const unsigned long long x = j < NP2 ? keys[j] : 0ull;
+    out_scores[u * k + j] = x ? pxr_key_score(x) : -INFINITY;
+    out_idx[u * k + j] = x ? (int32_t)pxr_key_idx(x) : -1;
+  }
+}
 
+// scratch per candidate: pair user (8) + pair row (8) + re-scored value (4)
+size_t pxr_rescore_list_bytes(int64_t n_users, int32_t list_len) { return pxr_align_up((size_t)n_users * list_len * (8 + 8 + 4), 256); }
+
+// list_idx: (n_users, L) candidate item indices (global, -1 padded), L = 64 or a multiple of 64 up to 1 024; k <= L
 int pxr_launch_rescore(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
-                       const int32_t* list_idx, int32_t k, float* out_scores, int32_t* out_idx, void* ws, cudaStream_t st) {
+                       const int32_t* list_idx, int32_t L, int32_t k, float* out_scores, int32_t* out_idx, void* ws, cudaStream_t st) {
   if (n_users == 0) return PXR_OK;
-  const int64_t n_pairs = n_users * 64;
+  if (L < 64 || L > 1024 || L % 64 || k > L) PXR_FAIL(h, PXR_ERR_INVALID, "re-score: list length %d / k %d not supported", L, k);
+  const int64_t n_pairs = n_users * L;
   int64_t* pair_user = (int64_t*)ws;
   int64_t* pair_row = pair_user + n_pairs;
   float* resc = (float*)(pair_row + n_pairs);
-  rescore_prep_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(user_idx, list_idx, n_pairs, 64, h->item_base, h->n_rows, pair_user, pair_row);
+  rescore_prep_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, st>>>(user_idx, list_idx, n_pairs, L, h->item_base, h->n_rows, pair_user, pair_row);
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
   const int rc = pxr_launch_score_simt(h, user_embedding, pair_user, pair_row, n_pairs, resc, nullptr, st);
   if (rc) return rc;
-  rescore_sort_kernel<<<(unsigned)((n_users + 7) / 8), 256, 0, st>>>(resc, list_idx, n_users, k, h->item_base, h->n_rows, out_scores, out_idx);
+  if (L == 64) {
+    rescore_sort_kernel<<<(unsigned)((n_users + 7) / 8), 256, 0, st>>>(resc, list_idx, n_users, k, h->item_base, h->n_rows, out_scores, out_idx);
+  } else {
+    int np2 = 128;
+    while (np2 < L) np2 <<= 1;
+    rescore_sort_block_kernel<<<(unsigned)n_users, 256, 0, st>>>(resc, list_idx, L, np2, k, h->item_base, h->n_rows, out_scores, out_idx);
+  }
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
   return PXR_OK;

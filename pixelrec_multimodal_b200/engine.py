@@ -49,6 +49,8 @@ def check_index_range(idx, n: int, what: str):
 class PxrEngine:
     """One handle = one model configuration on one GPU (not thread-safe)."""
 
+    MAX_FUSED_K = 1024      # PXR_TC_MAX_K: top_k the fused path serves (64 list slots per pass, one pass per page of 64)
+
     def __init__(self, *, fusion_type: str, embedding_dim: int, vision_dim: int, language_dim: int,
                  num_numerical: int, hidden_dims: Sequence[int], n_tags: int, num_heads: int = 4,
                  activation: str = "relu", final_activation: str = "sigmoid", use_batch_norm: bool = True,
@@ -298,11 +300,11 @@ class PxrEngine:
             if seen_indptr.shape[0] != user_idx.shape[0] + 1:
                 raise ValueError("seen_indptr must have n_users + 1 entries")
         n = int(user_idx.shape[0])
-        if k > 64 and self.active_path == "tcgen05" and not self._warned_k:
+        if k > self.MAX_FUSED_K and self.active_path == "tcgen05" and not self._warned_k:
             self._warned_k = True
             logging.getLogger(__name__).warning(
-                "PxrEngine.score_topk: top_k=%d exceeds the 64 list slots of the fused tcgen05 kernel; this call runs on the "
-                "generic fp32 SIMT kernels (exact, ~100x slower)", k)
+                "PxrEngine.score_topk: top_k=%d exceeds the %d candidates (16 pages of 64 list slots) the fused tcgen05 kernel "
+                "keeps per user; this call runs on the generic fp32 SIMT kernels (exact, ~100x slower)", k, self.MAX_FUSED_K)
         out_s = torch.empty((n, k), dtype=torch.float32, device=dev)
         out_i = torch.empty((n, k), dtype=torch.int32, device=dev)
         nbytes = int(self.lib.pxr_score_topk_bytes(self._h, n, k))
@@ -319,23 +321,25 @@ class PxrEngine:
 
     def rescore_topk(self, user_embedding: torch.Tensor, user_idx: torch.Tensor, cand_idx: torch.Tensor, k: int
                      ) -> Tuple[torch.Tensor, torch.Tensor]:
-        """The re-score step of exact mode on its own (``pxr_rescore_topk``): (n, 64) candidate lists of GLOBAL item
-        indices (-1 padded) -> the K best by the fp32 arithmetic of ``score_pairs`` against this engine's records."""
+        """The re-score step of exact mode on its own (``pxr_rescore_lists``): (n, L) candidate lists of GLOBAL item
+        indices (-1 padded; L = 64 pages of the fused kernel's lists, a multiple of 64 up to 1 024) -> the K <= L best by the
+        fp32 arithmetic of ``score_pairs`` against this engine's records."""
         dev = self.device
         user_embedding, user_idx = self._user_args(user_embedding, user_idx)
         cand = _dev_idx(cand_idx, dev, torch.int32)
         n = int(user_idx.shape[0])
-        if cand.shape != (n, 64):
-            raise ValueError(f"cand_idx must be ({n}, 64), got {tuple(cand.shape)}")
+        L = int(cand.shape[1]) if cand.dim() == 2 else -1
+        if cand.dim() != 2 or cand.shape[0] != n or L < 64 or L % 64 or L > self.MAX_FUSED_K or k > L:
+            raise ValueError(f"cand_idx must be ({n}, L) with L a multiple of 64 up to {self.MAX_FUSED_K} and top_k <= L, got {tuple(cand.shape)}, top_k={k}")
         out_s = torch.empty((n, k), dtype=torch.float32, device=dev)
         out_i = torch.empty((n, k), dtype=torch.int32, device=dev)
-        nbytes = int(self.lib.pxr_rescore_bytes(n))
+        nbytes = int(self.lib.pxr_rescore_lists_bytes(n, L))
         ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
         off = (-ws.data_ptr()) % 256
         with torch.cuda.device(dev):
-            self._check(self.lib.pxr_rescore_topk(self._h, _ptr(user_embedding), _ptr(user_idx), n, _ptr(cand), int(k), _ptr(out_s),
-                                                  _ptr(out_i), C.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream()),
-                        "pxr_rescore_topk")
+            self._check(self.lib.pxr_rescore_lists(self._h, _ptr(user_embedding), _ptr(user_idx), n, _ptr(cand), L, int(k), _ptr(out_s),
+                                                   _ptr(out_i), C.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream()),
+                        "pxr_rescore_lists")
         return out_s, out_i
 
     def score_pairs(self, user_embedding: torch.Tensor, user_idx: torch.Tensor, item_row: torch.Tensor,

@@ -218,7 +218,7 @@ class FastRecommender:
 
     @torch.no_grad()
     def rescore(self, user_indices, cand_idx: torch.Tensor, top_k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(n, 64) candidate lists of global item indices (-1 padded) -> exact (fp32) top-K, ties -> lower index."""
+        """(n, 64 * pages) candidate lists of global item indices (-1 padded) -> exact (fp32) top-K, ties -> lower index."""
         users = torch.as_tensor(np.asarray(user_indices.cpu() if isinstance(user_indices, torch.Tensor) else user_indices, dtype=np.int64)).to(self.device)
         if users.numel() == 0:
             return (torch.empty((0, top_k), dtype=torch.float32, device=self.device),

@@ -123,7 +123,8 @@ class ShardedTopK:
     16-bit lists (``recommend_all(..., raw=True)``); the exchange carries their 64 slots, the rank that owns a user merges
     the shards' lists into the global 16-bit top-64 and re-scores THOSE in fp32 against whole-catalogue records --
     the same candidates, hence the same lists, as the unsharded exact mode, and 1 / world of the re-score work per rank
-    instead of every shard re-scoring every user."""
+    instead of every shard re-scoring every user.  ``top_k`` > 64: the raw lists have 64 * ceil(top_k / 64) slots (one
+    pass of the fused kernel per 64-slot page), exchanged, merged and re-scored the same way."""
 
     RAW_K = 64
 
@@ -139,7 +140,7 @@ class ShardedTopK:
         return dist.is_initialized() and dist.get_world_size(self.group) > 1
 
     def _k_exchange(self, top_k: int) -> int:
-        return self.RAW_K if self.rescore is not None else top_k
+        return self.RAW_K * ((top_k + self.RAW_K - 1) // self.RAW_K) if self.rescore is not None else top_k
 
     def _finish_owned(self, handle, blk, top_k: int):
         s, i = self.merge(*exchange_owned_finish(handle, self.group))

@@ -208,9 +208,9 @@ def test_topk_edge_cases():
 
 @pytest.mark.parametrize("fusion,n_users,n_items,k,path", [
     ("gated", 3, 900, 100, "simt"), ("concatenate", 70, 333, 200, "simt"), ("attention", 2, 40, 64, "simt"),
-    ("gated", 5, 700, 128, "auto"), ("gated", 400, 64, 10, "simt")])
+    ("gated", 5, 700, 128, "simt"), ("gated", 400, 64, 10, "simt")])
 def test_generic_path_keeps_topk_on_chip(fusion, n_users, n_items, k, path):
-    """The generic fp32 path (any K up to 1 024, any shape; what a tcgen05 handle uses for top_k > 64): per-user blocks
+    """The generic fp32 path (any K up to 1 024, any shape): per-user blocks
     sweep the catalogue and keep the running top-K in shared memory (score_topk_simt_kernel) -- no users x items score
     matrix in HBM; few users => the item range is split over several blocks and merged by K4.  == oracle, ties -> lower
     index, K larger than the catalogue -> padded tail."""
@@ -755,6 +755,83 @@ def test_tcgen05_full_size_properties(fusion):
         a = {int(x): float(y) for x, y in zip(i[u], s[u])}
         b = {int(x): float(y) for x, y in zip(i2[u], s2[u])}
         assert max(abs(a[c] - b[c]) for c in common.tolist()) <= TC_BF16_TOL
+
+
+# ======================================================================================
+# top_k > 64 on the fused path: the kernel's per-user list has 64 slots, so the kernel runs once per 64-slot page, page p
+# admitting only keys strictly below the user's last key of page p - 1 (pxr.h, pxr_set_rescore comment).  Round 1 / early
+# round 2 sent such calls to the generic fp32 kernels (~100x slower).
+# ======================================================================================
+@pytest.mark.parametrize("fusion,n_users,n_items,k,filt", [
+    ("gated", 48, 1500, 100, True), ("gated", 20, 100, 128, False), ("gated", 9, 150, 200, True),
+    ("concatenate", 40, 900, 100, True), ("attention", 40, 700, 130, True)])
+def test_tcgen05_topk_above_64_pages(fusion, n_users, n_items, k, filt):
+    spec, sd, feats, indptr, idx, _ = _tc_workload(n_users, n_items, syn.SEED + 33, fusion)
+    model, eng = _engine_for(spec, sd, feats, "tcgen05")
+    assert eng.active_path == "tcgen05"
+    users = np.arange(n_users)
+    d_users = torch.from_numpy(users).cuda()
+    args = (torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda()) if filt else ()
+    uemb = model.user_embedding.weight.detach()
+    n0 = eng.launch_count
+    s, i = eng.score_topk(uemb, d_users, k, *args)
+    assert eng.launch_count - n0 >= 2 * ((k + 63) // 64)                     # one fused pass + one commit per page, no generic kernel
+    s64, i64 = eng.score_topk(uemb, d_users, 64, *args)
+    assert torch.equal(i[:, :64], i64) and torch.equal(s[:, :64], s64)      # page 0 is the K = 64 call, bit for bit
+    s, i = _structural_checks(s, i, k, n_items, indptr if filt else None, idx)
+    emu = _lowp_scores(sd, spec, feats, users)
+    same = total = 0
+    for u in users:
+        seen = idx[indptr[u]:indptr[u + 1]] if filt else None
+        n_avail = n_items - (len(seen) if seen is not None else 0)
+        assert int((i[u] >= 0).sum()) == min(k, n_avail), (u, int((i[u] >= 0).sum()), n_avail)
+        same += _check_topk(s[u].astype(np.float64), i[u], emu[u], k, seen, _emu_tol(fusion, "bf16"), 0.0)
+        total += min(k, n_avail)
+    assert same >= 0.95 * total, (same, total)
+    # exact mode over the 64 * pages candidates == the fp32 oracle
+    eng.set_rescore(True)
+    xs, xi = _structural_checks(*eng.score_topk(uemb, d_users, k, *args), k, n_items, indptr if filt else None, idx)
+    ref = orc.score_block(sd, cs.spec_cfg(spec), users, 0, n_items, feats)
+    same_x = 0
+    for u in users:
+        seen = idx[indptr[u]:indptr[u + 1]] if filt else None
+        same_x += _check_topk(xs[u].astype(np.float64), xi[u], ref[u], k, seen, SIMT_TOL, 0.0)
+    assert same_x >= 0.97 * total, (same_x, total)
+    print(f"paged top-{k} {fusion}: {same}/{total} raw positions == emulated oracle, {same_x}/{total} exact-mode positions == fp32 oracle")
+
+
+def test_tcgen05_topk_above_64_many_units_and_shards():
+    """Paged top-100 with more user groups than CTA pairs and split item ranges (page bounds reloaded per unit), and across
+    item shards: per-shard raw lists of 128 slots merged (K4, k > 64) and re-scored once == the unsharded exact lists."""
+    from pixelrec_multimodal_b200.engine import merge_topk
+    from pixelrec_multimodal_b200.sharding import shard_range
+    n_users, n_items, k = 2500, 1203, 100
+    spec, sd, feats, indptr, idx, _ = _tc_workload(n_users, n_items, syn.SEED + 34, "gated")
+    model, eng = _engine_for(spec, sd, feats, "tcgen05")
+    users = torch.arange(n_users).cuda()
+    d_indptr, d_idx = torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda()
+    uemb = model.user_embedding.weight.detach()
+    fs, fi = eng.score_topk(uemb, users, 128, d_indptr, d_idx)
+    s64, i64 = eng.score_topk(uemb, users, 64, d_indptr, d_idx)
+    assert torch.equal(fi[:, :64], i64) and torch.equal(fs[:, :64], s64)
+    _structural_checks(fs, fi, 128, n_items, indptr, idx)
+    sample = np.arange(0, n_users, 97)
+    emu = _lowp_scores(sd, spec, feats, sample)
+    for r, u in enumerate(sample):
+        _check_topk(fs[u].cpu().numpy().astype(np.float64), fi[u].cpu().numpy(), emu[r], 128, idx[indptr[u]:indptr[u + 1]], _emu_tol("gated", "bf16"), 0.0)
+    parts_s, parts_i = [], []
+    for r in range(3):
+        lo, hi = shard_range(n_items, 3, r)
+        m, e = _engine_for(spec, sd, feats, "tcgen05", lo, hi)
+        s, i = e.score_topk(m.user_embedding.weight.detach(), users, 128, d_indptr, d_idx)
+        parts_s.append(s)
+        parts_i.append(i)
+    ms, mi = merge_topk(torch.stack(parts_s), torch.stack(parts_i))
+    assert torch.equal(mi, fi) and torch.equal(ms, fs)                      # sharded raw pages == unsharded raw pages
+    eng.set_rescore(True)
+    xs, xi = eng.score_topk(uemb, users, k, d_indptr, d_idx)
+    rs, ri = eng.rescore_topk(uemb, users, mi, k)                           # what the owning rank does with the merged lists
+    assert torch.equal(ri, xi) and torch.equal(rs, xs)
 
 
 # ======================================================================================
