@@ -51,6 +51,7 @@ struct pxr_handle {
   bool records_only = false;  // pxr_set_records_only: keep only the fp32 item records (a handle used for re-scoring / explicit pairs)
   bool rescore = true;        // exact mode of the fused path: fp32 re-score + re-rank of the 64-slot lists (pxr_set_rescore)
   uint64_t tc_attr_set = 0;   // bit per kernel whose max-dynamic-smem attribute has been set
+  uint64_t tc_attr_fused[2] = {0, 0};   // the same for the instantiations of the fused scoring kernel (score_tc.cu)
   void* fast_w = nullptr;     // bf16 swizzled operand images + fp32 vectors (see score_tc.cu)
   float tc_bias_host[1028];   // attention fast path: host copy of b1' b2 b3 w4 b4 (passed as kernel parameters)
   void* tc_items_w = nullptr;       // item precompute on the tensor pipe: hi / lo tf32 weight chunk images (items_tc.cu)

@@ -584,7 +584,9 @@ __device__ __forceinline__ void attn_item_step(const AttnUserFrag& U, const uint
 // (gated and attention fusion: the fused vector depends on the pair); concat feeds layer-1 partial sums instead.
 // TK2: two top-K warps (short units, where list updates are a visible share of the work) instead of one.
 // ACT: fusion_activation of the hidden layers (pxr_act; ReLU is the fast default, see act_pack).
-template <int FUS, int FMT, bool TK2, int ACT>
+// PAGED: pages p > 0 of a top_k > 64 call (Params::upper); a separate instantiation so that the page-bound code costs the
+// K <= 64 kernels nothing (their register allocation is tight: any extra live value shows up as spills in the epilogue).
+template <int FUS, int FMT, bool TK2, int ACT, bool PAGED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads<FUS>(), 1)
 score_fused_kernel(const __grid_constant__ Params p) {
   constexpr int NT = n_threads<FUS>();
@@ -638,8 +640,10 @@ score_fused_kernel(const __grid_constant__ Params p) {
   for (int i = threadIdx.x; i < QC; i += NT) ms.queue[i] = 0ull;
   if (threadIdx.x < TU) {
     ms.thr[threadIdx.x] = -INFINITY;
-    const int64_t ord = ((int64_t)(pair / p.S) * 2 + rank) * TU + threadIdx.x;       // user slot of this CTA's first unit
-    ms.upper[threadIdx.x] = (p.upper && ord < p.n_users) ? p.upper[ord] : ~0ull;
+    if (PAGED) {
+      const int64_t ord = ((int64_t)(pair / p.S) * 2 + rank) * TU + threadIdx.x;     // user slot of this CTA's first unit
+      ms.upper[threadIdx.x] = ord < p.n_users ? p.upper[ord] : ~0ull;
+    }
   }
   __syncthreads();
   if (warp == 4) {
@@ -988,7 +992,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
           const unsigned long long a = L[lane], b = L[lane + 32];
           const unsigned ba = __ballot_sync(0xffffffffu, key > a), bb = __ballot_sync(0xffffffffu, key > b);
           const int pos = ba ? 32 - __popc(ba) : 64 - __popc(bb);     // entries >= key come first
-          if (pos < p.K) {
+          // page bound (top_k > 64): entries of the previous pages pass the score threshold again and are dropped here
+          if (pos < p.K && (!PAGED || key < ms.upper[u])) {
             const unsigned long long a_up = __shfl_up_sync(0xffffffffu, a, 1), b_up = __shfl_up_sync(0xffffffffu, b, 1);
             const unsigned long long a31 = __shfl_sync(0xffffffffu, a, 31);
             const unsigned long long na = lane < pos ? a : (lane == pos ? key : a_up);
@@ -1029,7 +1034,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
         }
         if (lane == 0) ms.thr[u] = -INFINITY;
       }
-      if (p.upper && w + n_pairs < p.n_units && lane >= u_lo && lane < u_hi) {        // the next unit's page bounds
+      if (PAGED && w + n_pairs < p.n_units && lane >= u_lo && lane < u_hi) {          // the next unit's page bounds
         const int64_t ord = ((int64_t)((w + n_pairs) / p.S) * 2 + rank) * TU + lane;
         ms.upper[lane] = ord < p.n_users ? p.upper[ord] : ~0ull;
       }
@@ -1098,15 +1103,13 @@ score_fused_kernel(const __grid_constant__ Params p) {
       const bool ok = row >= 0 && !((ms.seen_mask[Tp & 3][ru] >> rj) & 1u);
       if (ok && y >= *reinterpret_cast<volatile float*>(&ms.thr[ru])) {
         const uint32_t gidx = (uint32_t)(p.item_base + row);
-        const unsigned long long key = ((unsigned long long)pxr_ord(y) << 32) | (unsigned long long)(IDX_MASK - gidx);
-        if (key < *reinterpret_cast<volatile unsigned long long*>(&ms.upper[ru])) {      // always true without page bounds (~0)
-          const unsigned long long e = key | ((unsigned long long)ru << 28);
-          const int qh = TK2 ? (ru >= TU / 2 ? 1 : 0) : 0;
-          constexpr uint32_t qcap = TK2 ? QC / 2 : QC;
-          const uint32_t slot = atomicAdd(&ms.q_tail[qh], 1u);
-          while (slot - *reinterpret_cast<volatile uint32_t*>(&ms.q_head[qh]) >= qcap) __nanosleep(64);
-          *reinterpret_cast<volatile unsigned long long*>(&ms.queue[qh * (QC / 2) + (slot & (qcap - 1))]) = e;
-        }
+        const unsigned long long e = ((unsigned long long)pxr_ord(y) << 32) | ((unsigned long long)ru << 28) |
+                                     (unsigned long long)(IDX_MASK - gidx);
+        const int qh = TK2 ? (ru >= TU / 2 ? 1 : 0) : 0;
+        constexpr uint32_t qcap = TK2 ? QC / 2 : QC;
+        const uint32_t slot = atomicAdd(&ms.q_tail[qh], 1u);
+        while (slot - *reinterpret_cast<volatile uint32_t*>(&ms.q_head[qh]) >= qcap) __nanosleep(64);
+        *reinterpret_cast<volatile unsigned long long*>(&ms.queue[qh * (QC / 2) + (slot & (qcap - 1))]) = e;
       }
       if (last_of_unit) {
         __syncwarp();
@@ -1485,13 +1488,14 @@ struct FastWeights {       // lives in h->fast_w; attention: followed by one xc_
 
 #endif  // PXR_TC_TU == 0
 
-template <int FUS, int FMT, bool TK2, int ACT>
+template <int FUS, int FMT, bool TK2, int ACT, bool PAGED>
 static int launch_fused_tk(pxr_handle* h, const Params& p, int n_pairs, cudaStream_t st) {
-  auto kern = score_fused_kernel<FUS, FMT, TK2, ACT>;
-  const int slot = ((ACT * 3 + FUS) * 2 + FMT) * 2 + (TK2 ? 1 : 0);         // < 60; bit 63: item_pi_kernel
-  if (!(h->tc_attr_set & (1ull << slot))) {
+  auto kern = score_fused_kernel<FUS, FMT, TK2, ACT, PAGED>;
+  static_assert(!(PAGED && TK2), "paged passes use one top-K warp");
+  const int slot = ((ACT * 3 + FUS) * 2 + FMT) * 3 + (PAGED ? 2 : (TK2 ? 1 : 0));   // < 90: two words; items_tc / item_pi use their own bits
+  if (!(h->tc_attr_fused[slot >> 6] & (1ull << (slot & 63)))) {
     PXR_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Map<FUS>::SMEM));
-    h->tc_attr_set |= (1ull << slot);
+    h->tc_attr_fused[slot >> 6] |= (1ull << (slot & 63));
   }
   pxr_prof_begin(h, st);
   kern<<<2 * n_pairs, n_threads<FUS>(), Map<FUS>::SMEM, st>>>(p);
@@ -1508,8 +1512,9 @@ template <int FUS, int FMT, int ACT>
 static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_t st) {
   static int thr = -1;                    // PXR_TK2_ROWS: rows per unit below which the second top-K warp is used (experiments)
   if (thr < 0) { const char* e = getenv("PXR_TK2_ROWS"); thr = e ? atoi(e) : 8192; }
-  return p.rows_per_split < thr ? launch_fused_tk<FUS, FMT, true, ACT>(h, p, n_pairs, st)
-                                : launch_fused_tk<FUS, FMT, false, ACT>(h, p, n_pairs, st);
+  if (p.upper) return launch_fused_tk<FUS, FMT, false, ACT, true>(h, p, n_pairs, st);
+  return p.rows_per_split < thr ? launch_fused_tk<FUS, FMT, true, ACT, false>(h, p, n_pairs, st)
+                                : launch_fused_tk<FUS, FMT, false, ACT, false>(h, p, n_pairs, st);
 }
 
 // every (front end, operand format) of one activation

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--items", nargs="+", type=int, default=[10_000, 100_000, 1_000_000])
     ap.add_argument("--batch", nargs="+", type=int, default=[1, 64, 1024, 8192])
     ap.add_argument("--dims", nargs="+", type=int, default=[64])
+    ap.add_argument("--activation", nargs="+", default=["relu"], help="fusion_activation of the model (one-GPU mode)")
+    ap.add_argument("--top-k", nargs="+", type=int, default=[50], help="list lengths; > 64 runs one fused pass per 64-slot page (one-GPU mode)")
     ap.add_argument("--min-ms", type=float, default=300.0, help="repeat launches until this much kernel time is accumulated")
     args = ap.parse_args()
     import os
@@ -35,15 +37,16 @@ def main():
     pk = bench.peaks()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     NU = max(args.batch)
-    for fusion, NI, Dm in [(f, n, d) for f in args.fusion for n in args.items for d in args.dims]:
+    for fusion, NI, Dm, act in [(f, n, d, a) for f in args.fusion for n in args.items for d in args.dims for a in args.activation]:
         if True:
             if fusion == "attention" and NI > 2_000_000:
                 continue                                   # 16.5 KB of MMA fragments per item
-            spec = syn.ModelSpec(n_users=NU, n_items=NI, fusion_type=fusion, embedding_dim=Dm)
+            spec = syn.ModelSpec(n_users=NU, n_items=NI, fusion_type=fusion, embedding_dim=Dm, fusion_activation=act)
             sd, feats, hist = syn.torch_workload(spec, dev, seed=11)
             syn.condition_like_trained(sd, spec, feats)
             m = FastMultimodalRecommender(n_users=NU, n_items=NI, n_tags=spec.n_tags, num_numerical_features=7, embedding_dim=Dm,
-                                          vision_model_name="cached512", language_model_name="cached384", fusion_type=fusion).to(dev)
+                                          vision_model_name="cached512", language_model_name="cached384", fusion_type=fusion,
+                                          fusion_activation=act).to(dev)
             m.load_state_dict(sd, strict=False)
             e = m.engine("catalogue")
             e.precompute_items(m.item_embedding.weight.detach(), feats["tag_idx"], feats["vis"], feats["txt"], feats["num"])
@@ -51,14 +54,14 @@ def main():
             uemb = m.user_embedding.weight.detach()
             wp = bench.w_pair(fusion, Dm, [512, 256, 128])
             slow = e.active_path != "tcgen05"
-            for B in args.batch:
+            for B, top_k in [(b, k) for b in args.batch for k in args.top_k]:
                 if slow and B * NI > 3e8:
                     continue                               # generic fp32 kernels: ~40 M pairs/s
                 users = torch.arange(B, device=dev)
                 ip, ix = hist["train_indptr"][:B + 1], hist["train_idx"]
                 huge = B * NI > 1.5e10                     # a 10 M-item catalogue x 8 192 users is ~30 s per call
                 for _ in range(1 if huge else 3):
-                    e.score_topk(uemb, users, 50, ip, ix)
+                    e.score_topk(uemb, users, top_k, ip, ix)
                 torch.cuda.synchronize()
                 flush.zero_()
                 e.profile(True)
@@ -66,7 +69,7 @@ def main():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 while reps < (1 if huge else 3) or (est < args.min_ms and reps < 200):
-                    e.score_topk(uemb, users, 50, ip, ix)
+                    e.score_topk(uemb, users, top_k, ip, ix)
                     reps += 1
                     if huge or reps % 3 == 0:
                         e1.record(); torch.cuda.synchronize(); est = e0.elapsed_time(e1)
@@ -76,7 +79,7 @@ def main():
                 ms = e0.elapsed_time(e1) / reps
                 pairs = B * NI
                 tf = pairs * wp / (k_ms / k_n * 1e-3) / 1e12
-                print(json.dumps({"fusion": fusion, "n_items": NI, "embedding_dim": Dm, "user_batch": B, "path": e.active_path, "exact_rescore": bool(e.rescore), "ms_per_call": ms,
+                print(json.dumps({"fusion": fusion, "n_items": NI, "embedding_dim": Dm, "user_batch": B, "activation": act, "top_k": top_k, "path": e.active_path, "exact_rescore": bool(e.rescore), "ms_per_call": ms,
                                   "kernel_ms": k_ms / k_n, "pairs_per_s": pairs / (ms * 1e-3), "users_per_s": B / (ms * 1e-3),
                                   "tflops": tf, "frac_of_bf16_peak": tf / pk["tf_sustained"], "reps": reps}), flush=True)
             del e, m, sd, hist
