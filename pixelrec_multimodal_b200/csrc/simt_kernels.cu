@@ -966,18 +966,23 @@ __global__ void __launch_bounds__(METRIC_THREADS) metrics_user_kernel(const int3
   }
 }
 
-// Fast variant for lists of at most 64 entries.  A warp owns a contiguous range of users and takes them 32 at a
-// time.  Their lists are one contiguous run of 32 k entries: the lanes stream it with coalesced loads
-// (METRIC_BATCH per lane in flight), each entry is compared with the positives of its user (held one user per
-// lane, fetched by a shuffle) and a match sets one bit of that user's 64-bit hit mask in shared memory.  Only users
-// with a hit have non-zero metrics: those lanes then do the float64 arithmetic (every cut-off is a popcount of the
-// hit mask; the discounted gain is summed left to right over the hit positions, the order of the reference loop,
-// tasks.py:733-747); everybody else adds exact zeros, i.e. nothing.  Lane partial sums are reduced in a fixed
-// order; blocks / warps own fixed user ranges => deterministic result.
+// Fast variant for lists of at most 64 entries.  A warp owns a contiguous range of users (a multiple of 32, so every
+// group of 32 lists starts 16-byte aligned) and takes them 32 at a time.  Their lists are one contiguous run of 32 k
+// entries: the lanes stream it with coalesced 16-byte loads, ALL of a group's loads in flight at once (VB = ceil(k / 4)
+// per lane: 6.4 KB per warp at k = 50) together with the first positive of each user and the next group's CSR offsets --
+// the stage is bound by the chain of memory latencies per group, not by instructions (~10 warp instructions per user)
+// nor by bytes in flight alone (ncu on the previous, batched version: 146 us for 223 MB with 1 - 2 KB in flight per warp and
+// three dependent round trips per group).  The run is parked in shared memory (conflict-free 16-byte stores) and read back
+// transposed: lane t scans the list of user ub + t against that user's positives (first one in a register) and builds the
+// user's 64-bit hit and valid masks in registers -- no shuffles, no atomics.  Only users with a hit have non-zero
+// metrics: those lanes then do the float64 arithmetic (every cut-off is a popcount of the hit mask; the discounted gain
+// is summed left to right over the hit positions, the order of the reference loop, tasks.py:733-747); everybody else adds
+// exact zeros, i.e. nothing.  Lane partial sums are reduced in a fixed order; blocks / warps own fixed user ranges =>
+// deterministic result.
 #define METRIC_WARPS 4
-#define METRIC_BATCH 8
-template <int NKS>     // cut-offs kept in registers (2 covers the usual @10 / @50; 8 = PXR_MAX_KS): occupancy
-__global__ void __launch_bounds__(32 * METRIC_WARPS, (NKS <= 2 ? 8 : 2)) metrics_warp_kernel(const int32_t* __restrict__ topk, int k_stride,
+// NKS: cut-offs (2 covers the usual @10 / @50; 8 = PXR_MAX_KS).  VEC: 16-byte loads (aligned lists), VB = loads per lane and batch
+template <int NKS, bool VEC, int VB>
+__global__ void __launch_bounds__(32 * METRIC_WARPS, (NKS <= 2 ? 4 : 2)) metrics_warp_kernel(const int32_t* __restrict__ topk, int k_stride,
                                                                          int64_t n_users, int64_t users_per_warp,
                                                                          const int64_t* __restrict__ gt_indptr,
                                                                          const int32_t* __restrict__ gt_idx,
@@ -986,7 +991,7 @@ __global__ void __launch_bounds__(32 * METRIC_WARPS, (NKS <= 2 ? 8 : 2)) metrics
                                                                          const double* __restrict__ ideal,
                                                                          double* __restrict__ block_sums) {
   __shared__ double acc[METRIC_WARPS][PXR_MAX_KS * METRIC_COLS];
-  __shared__ unsigned long long hitmask[METRIC_WARPS][32];
+  __shared__ __align__(16) int32_t runs[METRIC_WARPS][32 * 64];      // the 32 lists of the warp's current group
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double sums[NKS][METRIC_COLS];
 #pragma unroll
@@ -995,51 +1000,80 @@ __global__ void __launch_bounds__(32 * METRIC_WARPS, (NKS <= 2 ? 8 : 2)) metrics
     for (int c = 0; c < METRIC_COLS; ++c) sums[a][c] = 0.0;
   const int64_t w = (int64_t)blockIdx.x * METRIC_WARPS + warp;
   const int64_t u0 = w * users_per_warp, u1 = min(n_users, u0 + users_per_warp);
-  const int step_u = 32 / k_stride, step_p = 32 % k_stride;          // element i + 32 belongs to user + step_u (+1), position + step_p (- k)
-  unsigned long long* hm = hitmask[warp];
+  int32_t* run = runs[warp];
+  constexpr int EPL = VEC ? 4 : 1;                     // entries per load
+  int64_t g0n = 0; int nposn = 0;                      // lane t: CSR offsets of user ub + t, fetched one group ahead
+  if (u0 + lane < u1) { g0n = gt_indptr[u0 + lane]; nposn = (int)(gt_indptr[u0 + lane + 1] - g0n); }
   for (int64_t ub = u0; ub < u1; ub += 32) {
     const int nb = (int)min((int64_t)32, u1 - ub);
-    int64_t g0 = 0;                                    // lane t: positives of user ub + t
-    int npos = 0;
-    if (lane < nb) { g0 = gt_indptr[ub + lane]; npos = (int)(gt_indptr[ub + lane + 1] - g0); }
-    int max_pos = npos;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) max_pos = max(max_pos, __shfl_xor_sync(0xffffffffu, max_pos, o));
-    hm[lane] = 0ull;
-    __syncwarp();
-    // the nb lists are one contiguous run of nb * k_stride entries: lane l takes entries l, l + 32, ... (coalesced,
-    // METRIC_BATCH loads in flight), fetches the q-th positive of the entry's user from that user's lane and, on the
-    // rare match, sets bit `position` of the user's hit mask
     const int n_el = nb * k_stride;
     const int32_t* src = topk + ub * k_stride;
-    int eu = lane / k_stride, ep = lane - eu * k_stride;
-    for (int base = 0; base < n_el; base += 32 * METRIC_BATCH) {      // warp-uniform trip count (shuffles inside)
-      const int i0 = base + lane;
-      int32_t v[METRIC_BATCH];
+    // everything this group needs from memory is issued together: its list entries, the first positive of each user,
+    // and the CSR offsets of the next group
+    const int64_t g0 = g0n;                            // lane t: positives of user ub + t
+    const int npos = nposn;
+    int32_t pq0 = INT_MIN;                             // never equals a valid entry (>= 0)
+    for (int base = 0; base < n_el; base += 32 * VB * EPL) {
+      int32_t v[VB][EPL];
 #pragma unroll
-      for (int m = 0; m < METRIC_BATCH; ++m) v[m] = (i0 + 32 * m < n_el) ? __ldg(src + i0 + 32 * m) : -1;
-      for (int q = 0; q < max_pos; ++q) {
-        const int32_t pq = q < npos ? __ldg(gt_idx + g0 + q) : INT_MIN;       // never equals an entry (entries >= -1)
-        int u = eu, pp = ep;
+      for (int m = 0; m < VB; ++m) {
+        const int e = base + EPL * (lane + 32 * m);
+        if (VEC) {
+          if (e + 3 < n_el) {
+            const int4 q4 = __ldg(reinterpret_cast<const int4*>(src + e));
+            v[m][0] = q4.x; v[m][1 % EPL] = q4.y; v[m][2 % EPL] = q4.z; v[m][3 % EPL] = q4.w;
+          } else {
 #pragma unroll
-        for (int m = 0; m < METRIC_BATCH; ++m) {
-          const int32_t x = __shfl_sync(0xffffffffu, pq, u & 31);
-          if (v[m] == x && v[m] >= 0) atomicOr(&hm[u], 1ull << pp);
-          u += step_u; pp += step_p;
-          if (pp >= k_stride) { pp -= k_stride; ++u; }
+            for (int c = 0; c < EPL; ++c) v[m][c] = (e + c < n_el) ? __ldg(src + e + c) : -1;
+          }
+        } else {
+          v[m][0] = e < n_el ? __ldg(src + e) : -1;
         }
       }
+      if (base == 0) {
+        if (npos > 0) pq0 = __ldg(gt_idx + g0);
+        g0n = 0; nposn = 0;
+        if (ub + 32 + lane < u1) { g0n = gt_indptr[ub + 32 + lane]; nposn = (int)(gt_indptr[ub + 32 + lane + 1] - g0n); }
+      }
 #pragma unroll
-      for (int m = 0; m < METRIC_BATCH; ++m) { eu += step_u; ep += step_p; if (ep >= k_stride) { ep -= k_stride; ++eu; } }
+      for (int m = 0; m < VB; ++m) {
+        const int e = base + EPL * (lane + 32 * m);
+        if (VEC) { if (e < 32 * 64) *reinterpret_cast<int4*>(run + e) = make_int4(v[m][0], v[m][1 % EPL], v[m][2 % EPL], v[m][3 % EPL]); }
+        else if (e < 32 * 64) run[e] = v[m][0];
+      }
     }
     __syncwarp();
-    const unsigned long long hit = hm[lane];
-    __syncwarp();
+    unsigned long long hit = 0ull, valid = 0ull;
+    if (lane < nb) {
+      // eight entries at a time into 8-bit masks (constant shifts), then one 64-bit shift per chunk; the last chunk may
+      // run into the next user's entries (inside the 32 x 64 buffer for every k <= 64): masked off below
+      const int32_t* mine = run + lane * k_stride;
+      for (int j0 = 0; j0 < k_stride; j0 += 8) {
+        uint32_t h8 = 0u, v8 = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int32_t x = mine[j0 + i];
+          v8 |= (uint32_t)(x >= 0) << i;
+          h8 |= (uint32_t)(x == pq0) << i;                      // pq0 = INT_MIN without positives
+        }
+        valid |= (unsigned long long)v8 << j0;
+        hit |= (unsigned long long)h8 << j0;
+      }
+      for (int q = 1; q < npos; ++q) {                          // further positives of this user (leave-one-out: none)
+        const int32_t pq = __ldg(gt_idx + g0 + q);
+        for (int j0 = 0; j0 < k_stride; j0 += 8) {
+          uint32_t h8 = 0u;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h8 |= (uint32_t)(mine[j0 + i] == pq) << i;
+          hit |= (unsigned long long)h8 << j0;
+        }
+      }
+      valid &= k_stride >= 64 ? ~0ull : ((1ull << k_stride) - 1ull);
+      hit &= valid;
+    }
+    __syncwarp();                                     // the run may be overwritten by the next group's stores
     if (hit) {                                        // a user without hits (or without positives, tasks.py:589-591) adds exact zeros
       {
-        unsigned long long valid = 0ull;
-        const int32_t* rec = topk + (ub + lane) * k_stride;
-        for (int j = 0; j < k_stride; ++j) valid |= (unsigned long long)(__ldg(rec + j) >= 0) << j;
         const int first = hit ? __ffsll((long long)hit) : 0;
         double dcg = 0.0, apsum = 0.0;
         int nh = 0;
@@ -1072,13 +1106,14 @@ __global__ void __launch_bounds__(32 * METRIC_WARPS, (NKS <= 2 ? 8 : 2)) metrics
         }
       }
     }
-    __syncwarp();
   }
+  for (int i = lane; i < PXR_MAX_KS * METRIC_COLS; i += 32) acc[warp][i] = 0.0;      // cut-offs beyond NKS / ks.n
+  __syncwarp();
 #pragma unroll
-  for (int a = 0; a < PXR_MAX_KS; ++a)
+  for (int a = 0; a < NKS; ++a)
 #pragma unroll
     for (int c = 0; c < METRIC_COLS; ++c) {
-      double v = (a < NKS && a < ks.n) ? sums[a < NKS ? a : 0][c] : 0.0;
+      double v = a < ks.n ? sums[a][c] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0) acc[warp][a * METRIC_COLS + c] = v;
@@ -1091,15 +1126,22 @@ __global__ void __launch_bounds__(32 * METRIC_WARPS, (NKS <= 2 ? 8 : 2)) metrics
   }
 }
 
-__global__ void metrics_final_kernel(const double* __restrict__ block_sums, int64_t n_blocks, int n_ks, double* out) {
-  // one warp (block) per (k, column): lanes take blocks lane, lane + 32, ... then a fixed-order butterfly => deterministic
-  const int t = blockIdx.x, lane = threadIdx.x & 31;
+#define METRIC_FINAL_THREADS 256
+__global__ void __launch_bounds__(METRIC_FINAL_THREADS) metrics_final_kernel(const double* __restrict__ block_sums, int64_t n_blocks, int n_ks,
+                                                                            double* out) {
+  // one block per (k, column): thread i sums blocks i, i + 256, ... in order, then a fixed-shape tree => deterministic
+  __shared__ double part[METRIC_FINAL_THREADS];
+  const int t = blockIdx.x;
   if (t >= n_ks * METRIC_COLS) return;
   double s = 0.0;
-  for (int64_t b = lane; b < n_blocks; b += 32) s += block_sums[b * (PXR_MAX_KS * METRIC_COLS) + t];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) out[t] = s;
+  for (int64_t b = threadIdx.x; b < n_blocks; b += METRIC_FINAL_THREADS) s += block_sums[b * (PXR_MAX_KS * METRIC_COLS) + t];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = METRIC_FINAL_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[t] = part[0];
 }
 
 int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_users, const int64_t* gt_indptr,
@@ -1113,19 +1155,25 @@ int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_user
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    blocks = std::min<int64_t>(blocks, (int64_t)n_sm * 16);      // never more than the workspace holds (one row per 128 users)
+    // one wave of resident blocks (4 per SM for <= 2 cut-offs, 2 otherwise): a warp then walks many groups of 32 users and
+    // its fixed costs (the float64 reduction of its partial sums) are paid once; never more than the workspace holds
+    blocks = std::min<int64_t>(blocks, (int64_t)n_sm * (n_ks <= 2 ? 4 : 2));
     const int64_t warps = blocks * METRIC_WARPS;
-    const int64_t upw = (n_users + warps - 1) / warps;
-    if (n_ks <= 2)
-      metrics_warp_kernel<2><<<(unsigned)blocks, 32 * METRIC_WARPS, 0, st>>>(topk_idx, k_stride, n_users, upw, gt_indptr, gt_idx, recall_den, mk,
-                                                                            discount, ideal, (double*)ws);
-    else
-      metrics_warp_kernel<PXR_MAX_KS><<<(unsigned)blocks, 32 * METRIC_WARPS, 0, st>>>(topk_idx, k_stride, n_users, upw, gt_indptr, gt_idx,
-                                                                                     recall_den, mk, discount, ideal, (double*)ws);
+    const int64_t upw = ((n_users + warps - 1) / warps + 31) / 32 * 32;      // a multiple of 32: every group of lists starts 16-byte aligned
+    const bool vec = (reinterpret_cast<uintptr_t>(topk_idx) & 15) == 0;
+    // aligned lists: one batch of ceil(k / 4) 16-byte loads per lane covers a whole group of 32 lists; otherwise scalar loads, 8 per batch
+    // 35 KB of static shared memory per block: ask for the large carve-out, or the default split leaves one block per SM
+#define PXR_METRICS_LAUNCH(NK, V, VB) do { cudaFuncSetAttribute(metrics_warp_kernel<NK, V, VB>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared); \
+      metrics_warp_kernel<NK, V, VB><<<(unsigned)blocks, 32 * METRIC_WARPS, 0, st>>>(topk_idx, k_stride, n_users, upw, gt_indptr, gt_idx, recall_den, mk, discount, ideal, (double*)ws); } while (0)
+#define PXR_METRICS_VB(NK) do { if (!vec) PXR_METRICS_LAUNCH(NK, false, 8); else if (k_stride <= 16) PXR_METRICS_LAUNCH(NK, true, 4); \
+      else if (k_stride <= 32) PXR_METRICS_LAUNCH(NK, true, 8); else if (k_stride <= 52) PXR_METRICS_LAUNCH(NK, true, 13); else PXR_METRICS_LAUNCH(NK, true, 16); } while (0)
+    if (n_ks <= 2) PXR_METRICS_VB(2); else PXR_METRICS_VB(PXR_MAX_KS);
+#undef PXR_METRICS_VB
+#undef PXR_METRICS_LAUNCH
   } else {
     metrics_user_kernel<<<(unsigned)blocks, METRIC_THREADS, 0, st>>>(topk_idx, k_stride, n_users, gt_indptr, gt_idx, recall_den, mk,
                                                                      discount, ideal, (double*)ws);
   }
-  metrics_final_kernel<<<n_ks * METRIC_COLS, 32, 0, st>>>((const double*)ws, blocks, n_ks, out_sums);
+  metrics_final_kernel<<<n_ks * METRIC_COLS, METRIC_FINAL_THREADS, 0, st>>>((const double*)ws, blocks, n_ks, out_sums);
   return cudaGetLastError() == cudaSuccess ? PXR_OK : PXR_ERR_CUDA;
 }

@@ -225,9 +225,11 @@ class PxrEngine:
     def precompute_items(self, item_embedding: torch.Tensor, tag_idx: torch.Tensor,
                          vis: Optional[torch.Tensor], txt: Optional[torch.Tensor], num: Optional[torch.Tensor],
                          item_idx: Optional[torch.Tensor] = None, item_base: int = 0,
-                         n_rows: Optional[int] = None):
+                         n_rows: Optional[int] = None, validate: bool = True):
         """K1+K2 over ``n_rows`` item rows.  Row r describes global item
-        ``item_idx[r]`` (or ``item_base + r``); feature tensors are row-aligned."""
+        ``item_idx[r]`` (or ``item_base + r``); feature tensors are row-aligned.
+        ``validate=False`` skips the index range checks (two reductions and a device sync) for callers that vouch for
+        their indices -- e.g. to capture the call in a CUDA graph."""
         dev = self.device
         n = int(n_rows if n_rows is not None else tag_idx.shape[0])
         emb = _dev_f32(item_embedding, dev)
@@ -236,7 +238,8 @@ class PxrEngine:
         tag = _dev_idx(tag_idx, dev)
         if tag.shape[0] < n:
             raise ValueError(f"tag_idx has {tag.shape[0]} entries for {n} item rows")
-        check_index_range(tag[:n], int(self.cfg.n_tags), "tag_idx")
+        if validate:
+            check_index_range(tag[:n], int(self.cfg.n_tags), "tag_idx")
         v = _dev_f32(vis, dev) if vis is not None and self.cfg.vision_dim else None
         t = _dev_f32(txt, dev) if txt is not None and self.cfg.language_dim else None
         x = _dev_f32(num, dev) if num is not None and self.cfg.num_numerical else None
@@ -247,7 +250,8 @@ class PxrEngine:
                                  f"{None if ten is None else tuple(ten.shape)}")
         ii = _dev_idx(item_idx, dev) if item_idx is not None else None
         if ii is not None:
-            check_index_range(ii[:n], int(emb.shape[0]), "item_idx")
+            if validate:
+                check_index_range(ii[:n], int(emb.shape[0]), "item_idx")
         elif int(item_base) < 0 or int(item_base) + n > int(emb.shape[0]):
             raise IndexError(f"item rows [{item_base}, {int(item_base) + n}) not inside the item embedding table ({emb.shape[0]} rows)")
         nbytes = int(self.lib.pxr_items_bytes(self._h, n))

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Achieved HBM GB/s of the memory-bound stages next to the fused scoring kernel:
 K1+K2 item precompute, K4 S-way top-K merge, K5 ranking metrics.  Algorithmic bytes per unit are the
-§8(d) figures (stated in DESIGN.md §5); time = CUDA events around `reps` back-to-back launches after
-a warm-up, L2 flushed before each timed group.  One JSON line per stage.
+§8(d) figures (stated in DESIGN.md §5); time = CUDA events around `reps` replays of a CUDA graph of the stage's call
+(device time without host gaps: several of these stages are shorter than the Python cost of their call), after a
+warm-up, L2 flushed before the timed group; every stage's working set is larger than the L2.  One JSON line per stage.
 
   python scripts/bench_stages.py [--fusion gated] [--items 96282]
 """
@@ -18,17 +19,38 @@ from pixelrec_multimodal_b200 import FastMultimodalRecommender, synthetic as syn
 from pixelrec_multimodal_b200.engine import merge_topk, ranking_metric_sums, sample_candidates, weighted_candidates   # noqa: E402
 
 
+EAGER = False      # --eager: time the Python calls back to back instead of graph replays (includes host gaps)
+
+
 def timed(fn, reps, flush):
     # three untimed calls: the first two of a stage that allocates its workspace grow the caching allocator's pool
     # (cudaMalloc on the host path: 11 ms and 5 ms for the 222 MB concat workspace, profiles/r01_diag_precompute_concat.log)
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    run = fn
+    if not EAGER:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            run = g.replay
+            run(); torch.cuda.synchronize()
+        except Exception as ex:                                   # a stage that cannot be captured is timed eagerly
+            print(json.dumps({"note": f"graph capture failed, eager timing: {type(ex).__name__}: {str(ex)[:120]}"}), flush=True)
+            torch.cuda.synchronize()
+            run = fn
     flush.zero_(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        fn()
+        run()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
@@ -38,7 +60,10 @@ def main():
     ap.add_argument("--fusion", default="gated")
     ap.add_argument("--items", type=int, default=96282)
     ap.add_argument("--users", type=int, default=1 << 20)
+    ap.add_argument("--eager", action="store_true", help="time the Python calls (with their host gaps) instead of graph replays")
     args = ap.parse_args()
+    global EAGER
+    EAGER = args.eager
     peak = json.loads((REPO / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (REPO / "MEASURED_PEAKS.json").exists() else 6650.0
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -52,7 +77,8 @@ def main():
     D, Dv, Dl, F, M = 64, 512, 384, 7, 6
     out = []
     # ---- K1 + K2: gather + projections -> item records (the fast-path extras of the fusion type are part of the stage)
-    ms = timed(lambda: e.precompute_items(m.item_embedding.weight.detach(), feats["tag_idx"], feats["vis"], feats["txt"], feats["num"]), 3, flush)
+    ms = timed(lambda: e.precompute_items(m.item_embedding.weight.detach(), feats["tag_idx"], feats["vis"], feats["txt"], feats["num"],
+                                          validate=False), 3, flush)
     extra = {"gated": 8 * 4, "concatenate": 512 * 2, "attention": 1032 * 16}[args.fusion] if e.active_path == "tcgen05" else 0
     b_item = 4 * (2 * D + Dv + Dl + F) + 8 + 4 * (M - 1) * D + extra      # read features/embeddings/tag index + write record
     out.append(dict(stage="K1+K2 item precompute", fusion=args.fusion, units=args.items, unit="items", ms=ms,
@@ -73,7 +99,7 @@ def main():
     ms = timed(lambda: ranking_metric_sums(topk, gt_indptr, gt_idx, [10, 50], as_device=True), 5, flush)
     b = 4 * K + 8 + 4
     out.append(dict(stage="K5 metrics @10/@50", K=K, units=n, unit="users", ms=ms, bytes_per_unit=b,
-                    achieved_gbs=n * b / ms / 1e6, peak_gbs=peak, note="device time of pxr_metrics (two kernels), result left on the device"))
+                    achieved_gbs=n * b / ms / 1e6, peak_gbs=peak, note="pxr_metrics (two kernels), result left on the device"))
     # the same with a hit for every fifth user (a hit costs the float64 arithmetic; users without one add exact zeros)
     gt_hit = gt_idx.clone()
     sel = torch.arange(0, n, 5, device=dev)
