@@ -170,6 +170,13 @@ int pxr_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* us
 int pxr_set_rescore(pxr_handle* h, int on);
 int pxr_get_rescore(const pxr_handle* h);
 
+/* Small user batches on the fused path (gated fusion, <= 8 users, K <= 64): the unit's 16 user slots become (user, item
+ * sub-range) pairs, so that one Recommender.get_recommendations call (src/inference/recommender.py:52-110 scores ONE user
+ * per call) is not capped at 1/16 of the tile; the per-slot lists are merged by one or two pxr_merge_topk passes.  Same
+ * arithmetic per pair: the lists equal those of the plain tile shape bit for bit.
+ *   mode: -1 = when the built-in cost model expects a gain (default; ~ >= 30 K items per user), 0 = never, 1 = whenever possible */
+int pxr_set_small_batch(pxr_handle* h, int mode);
+
 /* The re-score step of exact mode on its own: candidate lists (for instance the merged 16-bit top-64 lists of several item
  * shards) are scored with the fp32 arithmetic of pxr_score_pairs against the records of THIS handle and ranked (ties ->
  * lower item index); the first K come back.  Under item-axis sharding the exchange carries the raw 64-slot lists and the

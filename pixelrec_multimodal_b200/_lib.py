@@ -61,6 +61,7 @@ _SIGNATURES = {
     "pxr_set_records_only": (C.c_int, [C.c_void_p, C.c_int]),
     "pxr_rescore_bytes": (C.c_size_t, [C.c_int64]),
     "pxr_rescore_topk": (C.c_int, [C.c_void_p, _F, _F, C.c_int64, _F, C.c_int32, _F, _F, _F, C.c_size_t, C.c_void_p]),
+    "pxr_set_small_batch": (C.c_int, [C.c_void_p, C.c_int]),
     "pxr_rescore_lists_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "pxr_rescore_lists": (C.c_int, [C.c_void_p, _F, _F, C.c_int64, _F, C.c_int32, C.c_int32, _F, _F, _F, C.c_size_t, C.c_void_p]),
     "pxr_score_pairs": (C.c_int, [C.c_void_p, _F, _F, _F, C.c_int64, _F, _F, C.c_void_p]),

@@ -307,6 +307,13 @@ extern "C" int pxr_score_pairs(pxr_handle* h, const float* user_embedding, const
   return pxr_launch_score_simt(h, user_embedding, user_idx, item_row, n, out, out_logit, (cudaStream_t)stream);
 }
 
+extern "C" int pxr_set_small_batch(pxr_handle* h, int mode) {
+  if (!h) return PXR_ERR_INVALID;
+  if (mode < -1 || mode > 1) PXR_FAIL(h, PXR_ERR_INVALID, "pxr_set_small_batch: mode must be -1 (auto), 0 (off) or 1 (whenever possible)");
+  h->small_batch = mode;
+  return PXR_OK;
+}
+
 extern "C" size_t pxr_rescore_lists_bytes(int64_t n_users, int32_t list_len) {
   return n_users > 0 && list_len > 0 ? pxr_rescore_list_bytes(n_users, list_len) + 256 : 256;
 }

@@ -49,6 +49,7 @@ struct pxr_handle {
   // fast (tcgen05) path images
   bool fast_ok = false;
   bool records_only = false;  // pxr_set_records_only: keep only the fp32 item records (a handle used for re-scoring / explicit pairs)
+  int small_batch = -1;       // small-batch tile shape of the fused gated kernel: -1 auto (cost model), 0 off, 1 whenever possible (pxr_set_small_batch)
   bool rescore = true;        // exact mode of the fused path: fp32 re-score + re-rank of the 64-slot lists (pxr_set_rescore)
   uint64_t tc_attr_set = 0;   // bit per kernel whose max-dynamic-smem attribute has been set
   uint64_t tc_attr_fused[2] = {0, 0};   // the same for the instantiations of the fused scoring kernel (score_tc.cu)

@@ -62,6 +62,7 @@ constexpr int THREADS = 512;                 // 16 warps
 constexpr uint32_t IDX_MASK = 0x0FFFFFFFu;   // 28-bit item index inside a queue / list key
 constexpr int FMT_BF16 = 0, FMT_FP16 = 1;
 constexpr int F_CONCAT = 0, F_GATED = 1, F_ATTN = 2;   // front ends of the kernel template
+constexpr int M_PLAIN = 0, M_PAGED = 1, M_SPREAD = 2;  // kernel modes (template parameter MODE)
 // users x items of one CTA tile (128 rows).  gated / concat: 8 x 16, row = user * 16 + item.  attention: 16 x 8,
 // row = item * 16 + user -- the 16 rows of an item are the M dimension of the front end's register MMAs
 template <int FUS> __host__ __device__ constexpr int tile_users() { return FUS == F_ATTN ? 16 : 8; }
@@ -99,6 +100,7 @@ struct MiscT {
   float lu[ATT ? 1 : TU][8];
   unsigned long long list[TU][KCAP];
   unsigned long long upper[TU];                      // per user slot: only keys strictly below it are admitted (pages of a top_k > 64 call)
+  int32_t slot_lo[TU], slot_hi[TU];                  // M_SPREAD: first row / end row of the slot's item sub-range (front end only)
   unsigned long long queue[QC];
   float thr[TU];
   uint32_t seen_mask[4][TU];
@@ -167,17 +169,21 @@ struct Params {
   int64_t n_users, n_rows, item_base;
   int M, K, S, rows_per_split, n_units, final_act;
   int Dm;                       // embedding dim of the model (concat: any multiple of 4 up to 512; gated / attention: 64)
+  // M_SPREAD (small batches): n_users above counts VIRTUAL users v = r * n_real + u: real user u on item sub-range
+  // r = rows [r * sub_rows, (r + 1) * sub_rows) of the shard; user_idx / seen_indptr are indexed by u = v % n_real
+  int64_t n_real;
+  int sub_rows;                 // multiple of the tile's item count
 };
 
 struct Unit { int g, s; int64_t row_lo, row_hi; int ntiles; };
 
-template <int TI>
+template <int TI, bool SPREAD = false>
 __device__ __forceinline__ Unit decode_unit(const Params& p, int w) {
   Unit u;
   u.g = w / p.S; u.s = w % p.S;
   u.row_lo = (int64_t)u.s * p.rows_per_split;
   u.row_hi = min(p.n_rows, u.row_lo + (int64_t)p.rows_per_split);
-  u.ntiles = (int)((u.row_hi - u.row_lo + TI - 1) / TI);
+  u.ntiles = SPREAD ? p.sub_rows / TI : (int)((u.row_hi - u.row_lo + TI - 1) / TI);      // SPREAD: every slot sweeps one sub-range
   return u;
 }
 
@@ -584,14 +590,18 @@ __device__ __forceinline__ void attn_item_step(const AttnUserFrag& U, const uint
 // (gated and attention fusion: the fused vector depends on the pair); concat feeds layer-1 partial sums instead.
 // TK2: two top-K warps (short units, where list updates are a visible share of the work) instead of one.
 // ACT: fusion_activation of the hidden layers (pxr_act; ReLU is the fast default, see act_pack).
-// PAGED: pages p > 0 of a top_k > 64 call (Params::upper); a separate instantiation so that the page-bound code costs the
-// K <= 64 kernels nothing (their register allocation is tight: any extra live value shows up as spills in the epilogue).
-template <int FUS, int FMT, bool TK2, int ACT, bool PAGED>
+// MODE: M_PAGED = pages p > 0 of a top_k > 64 call (Params::upper); M_SPREAD = small user batches (<= 8 users, gated front
+// end): the 16 user slots of a unit are (user, item sub-range) pairs, see "small batches" at the gated front end.  Separate
+// instantiations, so that this code costs the plain kernels nothing (their register allocation is tight: any extra live value
+// shows up as spills in the epilogue).
+template <int FUS, int FMT, bool TK2, int ACT, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads<FUS>(), 1)
 score_fused_kernel(const __grid_constant__ Params p) {
   constexpr int NT = n_threads<FUS>();
   constexpr bool GATED = (FUS != F_CONCAT);
   constexpr bool ATT = (FUS == F_ATTN);
+  constexpr bool PAGED = (MODE == M_PAGED), SPREAD = (MODE == M_SPREAD);
+  static_assert(!SPREAD || FUS == F_GATED, "small-batch mode exists for the gated front end");
   constexpr int TU = tile_users<FUS>(), TI = tile_items<FUS>();
   using MP = Map<FUS>;
   using MiscF = MiscT<FUS>;
@@ -683,7 +693,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
     AttnUserFrag UF;                        // attention: per-unit user operands of this thread (registers)
     uint4* const scr = ATT ? p.xc0_scratch + (size_t)blockIdx.x * ATT_XC0_U4 : nullptr;
     for (int w = pair; w < p.n_units; w += n_pairs) {
-      const Unit un = decode_unit<TI>(p, w);
+      const Unit un = decode_unit<TI, SPREAD>(p, w);
       const int64_t ubase = ((int64_t)un.g * 2 + rank) * TU;     // first user ordinal of this CTA's group
       if (!GATED && T > 0) {
         // Pu is read by the layer-1 producers of the previous unit's last tile: wait until they are done with it
@@ -699,8 +709,15 @@ score_fused_kernel(const __grid_constant__ Params p) {
       } else {
         const int u = tid >> 4, d4 = (tid & 15) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ubase + u < p.n_users && d4 < p.Dm) v = *reinterpret_cast<const float4*>(p.user_emb + p.user_idx[ubase + u] * p.Dm + d4);
+        const int64_t uo = SPREAD ? (ubase + u) % p.n_real : ubase + u;      // SPREAD: slot (ubase + u) = real user uo on sub-range (ubase + u) / n_real
+        if (ubase + u < p.n_users && d4 < p.Dm) v = *reinterpret_cast<const float4*>(p.user_emb + p.user_idx[uo] * p.Dm + d4);
         *reinterpret_cast<float4*>(&ms.eu[u][d4]) = v;
+        if (SPREAD && tid < TU) {            // the slot's item sub-range (rows of the shard)
+          const int64_t r = (ubase + tid) / p.n_real;
+          const int64_t lo = un.row_lo + r * p.sub_rows;
+          ms.slot_lo[tid] = (int32_t)min(lo, un.row_hi);
+          ms.slot_hi[tid] = (ubase + tid < p.n_users) ? (int32_t)min(lo + p.sub_rows, un.row_hi) : (int32_t)min(lo, un.row_hi);
+        }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (FUS == F_ATTN) {
@@ -766,8 +783,9 @@ score_fused_kernel(const __grid_constant__ Params p) {
       // seen-item cursors: lanes 0..TU-1 of warp 0 walk user u's ascending history with the item sweep
       int64_t cur = 0, cend = 0; int32_t nextv = 0x7fffffff;
       if (warp == 0 && lane < TU && p.seen_indptr && ubase + lane < p.n_users) {
-        cur = p.seen_indptr[ubase + lane]; cend = p.seen_indptr[ubase + lane + 1];
-        const int32_t first = (int32_t)(p.item_base + un.row_lo);
+        const int64_t uo = SPREAD ? (ubase + lane) % p.n_real : ubase + lane;
+        cur = p.seen_indptr[uo]; cend = p.seen_indptr[uo + 1];
+        const int32_t first = (int32_t)(p.item_base + (SPREAD ? (int64_t)ms.slot_lo[lane] : un.row_lo));
         int64_t lo = cur, hi = cend;
         while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (p.seen_idx[mid] < first) lo = mid + 1; else hi = mid; }
         cur = lo;
@@ -779,7 +797,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
         auto write_seen_mask = [&]() {         // lanes 0..TU-1 of warp 0: the TI-bit seen mask of this tile per user
           if (warp == 0 && lane < TU) {
             uint32_t mask = 0;
-            const int32_t i0 = (int32_t)(p.item_base + row0);
+            const int32_t i0 = (int32_t)(p.item_base + (SPREAD ? (int64_t)ms.slot_lo[lane] + (int64_t)t * TI : row0));
             while (nextv < i0 + TI) {
               if (nextv >= i0) mask |= 1u << (nextv - i0);
               ++cur;
@@ -807,6 +825,75 @@ score_fused_kernel(const __grid_constant__ Params p) {
               *reinterpret_cast<uint32_t*>(a1 + ((nn ^ g) << 4)) = pack2<FMT>(acc[nn][0], acc[nn][1]);
               *reinterpret_cast<uint32_t*>(a1 + 1024 + ((nn ^ g) << 4)) = pack2<FMT>(acc[nn][2], acc[nn][3]);
             }
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster_release(BAR(BAR_A_FULL), 0);
+        } else if (FUS == F_GATED && SPREAD) {
+          // ---- small batches: slot u of the CTA sweeps its own item sub-range, so the 16 items of a tile differ per slot:
+          // thread (j, s) computes the gate of pair (slot s, that slot's item j) and then, per slot u, fetches item j of
+          // slot u (software-pipelined one slot ahead: the records come from L2 / HBM once per pair here, not once per 8 pairs)
+          const int j = tid >> 3, s = tid & 7;
+          const int toff = t * TI + j;
+          auto load_item = [&](int u, float (&f)[5][8]) {
+            const int row = ms.slot_lo[u] + toff;
+            const bool valid = row < ms.slot_hi[u];
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+              if (m < Mm - 1 && valid) {
+                const float4* src = reinterpret_cast<const float4*>(p.item_feats + ((int64_t)row * (Mm - 1) + m) * D + 8 * s);
+                const float4 a = __ldg(src), b = __ldg(src + 1);
+                f[m][0] = a.x; f[m][1] = a.y; f[m][2] = a.z; f[m][3] = a.w; f[m][4] = b.x; f[m][5] = b.y; f[m][6] = b.z; f[m][7] = b.w;
+              } else {
+#pragma unroll
+                for (int d = 0; d < 8; ++d) f[m][d] = 0.f;
+              }
+            }
+          };
+          float fa[5][8], fb[5][8];
+          load_item(0, fa);
+          float g[6];
+          {
+            const int row = ms.slot_lo[s] + toff;
+            const int64_t rr = row < ms.slot_hi[s] ? row : un.row_lo;
+            const float4 l0 = __ldg(reinterpret_cast<const float4*>(p.item_logit + rr * 8));
+            const float4 l1 = __ldg(reinterpret_cast<const float4*>(p.item_logit + rr * 8 + 4));
+            const float li[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+            float mx = -INFINITY;
+#pragma unroll
+            for (int m = 0; m < 6; ++m) { g[m] = m < Mm ? li[m] + ms.lu[s][m] : -INFINITY; mx = fmaxf(mx, g[m]); }
+            float sum = 0.f;
+#pragma unroll
+            for (int m = 0; m < 6; ++m) { g[m] = m < Mm ? expf(g[m] - mx) : 0.f; sum += g[m]; }
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int m = 0; m < 6; ++m) g[m] *= inv;
+          }
+          write_seen_mask();
+          if (T > 0) ptx::mbar_wait(BAR(BAR_A_EMPTY), (T - 1) & 1);   // layer-1 MMAs of the previous tile have read A1
+          auto emit = [&](int u, const float (&f)[5][8]) {
+            float gm[6];
+#pragma unroll
+            for (int m = 0; m < 6; ++m) gm[m] = __shfl_sync(0xffffffffu, g[m], (lane & ~7) | u);
+            const float4 e0 = *reinterpret_cast<const float4*>(&ms.eu[u][8 * s]);
+            const float4 e1 = *reinterpret_cast<const float4*>(&ms.eu[u][8 * s + 4]);
+            float acc[8] = {gm[0] * e0.x, gm[0] * e0.y, gm[0] * e0.z, gm[0] * e0.w, gm[0] * e1.x, gm[0] * e1.y, gm[0] * e1.z, gm[0] * e1.w};
+#pragma unroll
+            for (int m = 0; m < 5; ++m)
+#pragma unroll
+              for (int d = 0; d < 8; ++d) acc[d] = fmaf(gm[m + 1], f[m][d], acc[d]);
+            uint4 pk;
+            pk.x = pack2<FMT>(acc[0], acc[1]); pk.y = pack2<FMT>(acc[2], acc[3]);
+            pk.z = pack2<FMT>(acc[4], acc[5]); pk.w = pack2<FMT>(acc[6], acc[7]);
+            const int r = u * TI + j;
+            *reinterpret_cast<uint4*>(sm + MP::OFF_A1 + (r >> 3) * 1024 + (r & 7) * 128 + ((s ^ (r & 7)) << 4)) = pk;
+          };
+#pragma unroll 1
+          for (int u = 0; u < TU; u += 2) {
+            load_item(u + 1, fb);
+            emit(u, fa);
+            if (u + 2 < TU) load_item(u + 2, fa);
+            emit(u + 1, fb);
           }
           ptx::fence_proxy_async();
           __syncwarp();
@@ -890,7 +977,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
     // =============================================================== MMA issuer (leader CTA, one thread)
     if (rank == 0 && lane == 0) {
       int NT = 0;
-      for (int w = pair; w < p.n_units; w += n_pairs) NT += decode_unit<TI>(p, w).ntiles;
+      for (int w = pair; w < p.n_units; w += n_pairs) NT += decode_unit<TI, SPREAD>(p, w).ntiles;
       const uint64_t dA1 = ptx::smem_desc_sw128(base + MP::OFF_A1);
       const uint64_t dW1 = ptx::smem_desc_sw128(base + MP::OFF_W1);
       const uint64_t dW2 = ptx::smem_desc_sw128(base + MP::OFF_W2);
@@ -970,7 +1057,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
     unsigned long long* const queue = ms.queue + qh * (QC / 2);
     uint32_t head = 0, done_ph = 0;
     for (int w = pair; w < p.n_units; w += n_pairs) {
-      const Unit un = decode_unit<TI>(p, w);
+      const Unit un = decode_unit<TI, SPREAD>(p, w);
       if (un.ntiles == 0) continue;
       const int64_t ubase = ((int64_t)un.g * 2 + rank) * TU;
       bool finished = false;
@@ -1154,7 +1241,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
     };
 
     for (int w = pair; w < p.n_units; w += n_pairs) {
-      const Unit un = decode_unit<TI>(p, w);
+      const Unit un = decode_unit<TI, SPREAD>(p, w);
       const int64_t ubase = ((int64_t)un.g * 2 + rank) * TU;
       for (int t = 0; t < un.ntiles; ++t, ++T) {
         // One rolled loop over this group's four layer-1 chunks (the body must stay resident in the instruction
@@ -1173,6 +1260,15 @@ score_fused_kernel(const __grid_constant__ Params p) {
         }
         if (ATT) {
           prev = un; prev_t = t; prev_ubase = ubase; have_prev = true;
+        } else if (SPREAD) {
+          // this thread's slot sweeps the sub-range (ubase + ru) / n_real of the shard (recomputed per tile: the division is
+          // off the critical path and the epilogue keeps no per-unit state for it)
+          const int64_t v = ubase + ru;
+          const int64_t lo = un.row_lo + (v / p.n_real) * p.sub_rows;
+          const int64_t row = lo + (int64_t)t * TI + rj;
+          prev_row = (row < min(lo + (int64_t)p.sub_rows, un.row_hi) && v < p.n_users) ? row : -1;
+          prev_flags = (t == 0 ? 1 : 0) | (t == un.ntiles - 1 ? 2 : 0);
+          have_prev = true;
         } else {
           const int64_t row = un.row_lo + (int64_t)t * TI + rj;
           prev_row = (row < un.row_hi && (ubase + ru) < p.n_users) ? row : -1;
@@ -1488,11 +1584,11 @@ struct FastWeights {       // lives in h->fast_w; attention: followed by one xc_
 
 #endif  // PXR_TC_TU == 0
 
-template <int FUS, int FMT, bool TK2, int ACT, bool PAGED>
+template <int FUS, int FMT, bool TK2, int ACT, int MODE>
 static int launch_fused_tk(pxr_handle* h, const Params& p, int n_pairs, cudaStream_t st) {
-  auto kern = score_fused_kernel<FUS, FMT, TK2, ACT, PAGED>;
-  static_assert(!(PAGED && TK2), "paged passes use one top-K warp");
-  const int slot = ((ACT * 3 + FUS) * 2 + FMT) * 3 + (PAGED ? 2 : (TK2 ? 1 : 0));   // < 90: two words; items_tc / item_pi use their own bits
+  auto kern = score_fused_kernel<FUS, FMT, TK2, ACT, MODE>;
+  static_assert(!(MODE == M_PAGED && TK2), "paged passes use one top-K warp");
+  const int slot = ((ACT * 3 + FUS) * 2 + FMT) * 4 + (MODE == M_PLAIN ? (TK2 ? 1 : 0) : 1 + MODE);   // < 120: two words
   if (!(h->tc_attr_fused[slot >> 6] & (1ull << (slot & 63)))) {
     PXR_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Map<FUS>::SMEM));
     h->tc_attr_fused[slot >> 6] |= (1ull << (slot & 63));
@@ -1512,9 +1608,13 @@ template <int FUS, int FMT, int ACT>
 static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_t st) {
   static int thr = -1;                    // PXR_TK2_ROWS: rows per unit below which the second top-K warp is used (experiments)
   if (thr < 0) { const char* e = getenv("PXR_TK2_ROWS"); thr = e ? atoi(e) : 8192; }
-  if (p.upper) return launch_fused_tk<FUS, FMT, false, ACT, true>(h, p, n_pairs, st);
-  return p.rows_per_split < thr ? launch_fused_tk<FUS, FMT, true, ACT, false>(h, p, n_pairs, st)
-                                : launch_fused_tk<FUS, FMT, false, ACT, false>(h, p, n_pairs, st);
+  if (p.upper) return launch_fused_tk<FUS, FMT, false, ACT, M_PAGED>(h, p, n_pairs, st);
+  if (p.sub_rows > 0) {                   // small batches: short sub-ranges per slot, two top-K warps
+    if constexpr (FUS == F_GATED) return launch_fused_tk<FUS, FMT, true, ACT, M_SPREAD>(h, p, n_pairs, st);
+    else PXR_FAIL(h, PXR_ERR_INVALID, "small-batch mode exists for gated fusion only");
+  }
+  return p.rows_per_split < thr ? launch_fused_tk<FUS, FMT, true, ACT, M_PLAIN>(h, p, n_pairs, st)
+                                : launch_fused_tk<FUS, FMT, false, ACT, M_PLAIN>(h, p, n_pairs, st);
 }
 
 // every (front end, operand format) of one activation
@@ -1679,6 +1779,38 @@ static TcPlan tc_plan(const pxr_handle* h, int64_t n_users) {
 
 static int tc_pages(int32_t k) { return (k + tc::KCAP - 1) / tc::KCAP; }
 
+// Small batches (<= 8 users, gated fusion, K <= 64): a unit's 16 user slots would be mostly empty, so each slot becomes a
+// (user, item sub-range) pair instead -- `lists` sub-ranges of `sub_rows` rows per user, sized so that the slots of all CTA
+// pairs are busy -- and the per-slot lists are merged afterwards in one or two K4 passes (G groups of J <= 64 lists).
+struct SpreadPlan { bool on; int sub_rows, lists, G, J; int64_t n_virtual; int n_groups, n_pairs; };
+
+static SpreadPlan tc_spread_plan(const pxr_handle* h, int64_t n_users, int32_t k) {
+  SpreadPlan sp;
+  memset(&sp, 0, sizeof(sp));
+  // h->small_batch (pxr_set_small_batch): 0 = never, 1 = whenever the shape allows it (tests), -1 = when the cost model below says so
+  if (h->small_batch == 0 || h->cfg.fusion != PXR_FUSION_GATED || n_users > 8 || n_users <= 0 || tc_pages(k) > 1 || h->n_rows < 512) return sp;
+  const int max_pairs = h->n_sm / 2;
+  const int64_t slots = (int64_t)max_pairs * 16;
+  int64_t sub = (h->n_rows * n_users + slots - 1) / slots;
+  sub = std::max<int64_t>(128, (sub + 15) / 16 * 16);                      // >= 8 tiles per slot: list warm-up and unit setup amortised
+  sub = std::min<int64_t>(sub, (h->n_rows + 15) / 16 * 16);
+  sp.sub_rows = (int)sub;
+  sp.lists = (int)((h->n_rows + sub - 1) / sub);
+  if (sp.lists < 2 || sp.lists > 4096) return sp;
+  sp.G = (sp.lists + 63) / 64;
+  sp.J = (sp.lists + sp.G - 1) / sp.G;
+  sp.n_virtual = n_users * sp.lists;
+  sp.n_groups = (int)((sp.n_virtual + 15) / 16);
+  sp.n_pairs = std::min(max_pairs, sp.n_groups);
+  // worth it?  Measured model (profiles/r02_sweep_small_batch.jsonl): a spread call costs ~110 us (every slot warms up its
+  // own list, 8x the record fetches per tile) + 7.4 us per tile of a slot; the plain shape ~20 us + 5.7 us per tile of a unit
+  const TcPlan pl = tc_plan(h, n_users);
+  const double t_plain = 20.0 + 5.7 * (double)((pl.rows_per_split + 15) / 16) * (double)((pl.n_units + max_pairs - 1) / max_pairs);
+  const double t_spread = 110.0 + 7.4 * (double)(sp.sub_rows / 16) * (double)((sp.n_groups + max_pairs - 1) / max_pairs);
+  sp.on = h->small_batch == 1 || t_spread < t_plain;
+  return sp;
+}
+
 // workspace: [S > 1: per-split partial lists][exact mode: the merged 64-slot lists + the re-score pair arrays]
 // top_k > 64 (pages): [partial lists][one page list][candidate rows of 64 * pages slots][page bounds][re-score arrays]
 size_t pxr_tc_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k) {
@@ -1694,7 +1826,9 @@ size_t pxr_tc_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k) {
     return b;
   }
   const int kk = h->rescore ? tc::KCAP : k;
-  if (pl.S > 1) b += pxr_align_up((size_t)pl.S * n_users * kk * 8, 256);
+  const SpreadPlan sp = tc_spread_plan(h, n_users, k);
+  if (sp.on) b += pxr_align_up((size_t)sp.J * sp.G * n_users * kk * 8, 256) + pxr_align_up((size_t)sp.G * n_users * kk * 8, 256);
+  else if (pl.S > 1) b += pxr_align_up((size_t)pl.S * n_users * kk * 8, 256);
   if (h->rescore) b += pxr_align_up((size_t)n_users * kk * 8, 256) + pxr_rescore_list_bytes(n_users, tc::KCAP);
   return b;
 }
@@ -1777,6 +1911,36 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
     // raw mode: the pages are already in descending key order, the first k slots of a row are the list
     PXR_CUDA(h, cudaMemcpy2DAsync(out_scores, (size_t)k * 4, cand_s, (size_t)L * 4, (size_t)k * 4, (size_t)n_users, cudaMemcpyDeviceToDevice, st));
     PXR_CUDA(h, cudaMemcpy2DAsync(out_idx, (size_t)k * 4, cand_i, (size_t)L * 4, (size_t)k * 4, (size_t)n_users, cudaMemcpyDeviceToDevice, st));
+    return PXR_OK;
+  }
+  const SpreadPlan sp = tc_spread_plan(h, n_users, k);
+  if (sp.on) {
+    // ---- small batches: (user, item sub-range) slots, then one or two merge passes over the per-slot lists
+    const size_t lst = (size_t)n_users * kk;                   // entries of one list set
+    const size_t n_all = (size_t)sp.J * sp.G * lst;
+    float* part_s = (float*)wp; int32_t* part_i = (int32_t*)(wp + n_all * 4);
+    wp += pxr_align_up(n_all * 8, 256);
+    float* tmp_s = (float*)wp; int32_t* tmp_i = (int32_t*)(wp + (size_t)sp.G * lst * 4);
+    wp += pxr_align_up((size_t)sp.G * lst * 8, 256);
+    float* list_s = out_scores; int32_t* list_i = out_idx;
+    if (exact) { list_s = (float*)wp; list_i = (int32_t*)(wp + lst * 4); wp += pxr_align_up(lst * 8, 256); }
+    if ((size_t)sp.J * sp.G > (size_t)sp.lists)                // lists that do not exist: empty (index -1)
+      PXR_CUDA(h, cudaMemsetAsync(part_i + (size_t)sp.lists * lst, 0xFF, ((size_t)sp.J * sp.G - sp.lists) * lst * 4, st));
+    p.n_real = n_users; p.n_users = sp.n_virtual; p.sub_rows = sp.sub_rows;
+    p.S = 1; p.rows_per_split = (int)((h->n_rows + 15) / 16 * 16); p.n_units = sp.n_groups;
+    p.out_scores = part_s; p.out_idx = part_i;
+    int rc = tc_launch(h, p, sp.n_pairs, st);
+    if (rc) return rc;
+    if (sp.G == 1) {
+      rc = pxr_launch_merge(part_s, part_i, sp.lists, n_users, kk, list_s, list_i, st);
+    } else {       // list l = j * G + g: one pass merges, for every (g, user), its J lists; the second pass the G results
+      rc = pxr_launch_merge(part_s, part_i, sp.J, (int64_t)sp.G * n_users, kk, tmp_s, tmp_i, st);
+      h->launches++;
+      if (!rc) rc = pxr_launch_merge(tmp_s, tmp_i, sp.G, n_users, kk, list_s, list_i, st);
+    }
+    h->launches++;
+    if (rc) PXR_FAIL(h, rc, "top-K merge of %d sub-range lists failed", sp.lists);
+    if (exact) return pxr_launch_rescore(h, user_embedding, user_idx, n_users, list_i, tc::KCAP, k, out_scores, out_idx, wp, st);
     return PXR_OK;
   }
   float* part_s = out_scores; int32_t* part_i = out_idx;       // what the kernel writes

@@ -156,6 +156,11 @@ class PxrEngine:
     def rescore(self) -> bool:
         return bool(self.lib.pxr_get_rescore(self._h))
 
+    def set_small_batch(self, mode: int):
+        """Small-batch tile shape of the fused gated kernel (include/pxr.h: pxr_set_small_batch): -1 = when the cost
+        model expects a gain (default), 0 = never, 1 = whenever the call allows it (<= 8 users, K <= 64)."""
+        self._check(self.lib.pxr_set_small_batch(self._h, int(mode)), "pxr_set_small_batch")
+
     def set_records_only(self, on: bool = True):
         """Keep only the fp32 item records at the next ``precompute_items`` (a handle that serves ``rescore_topk`` /
         ``score_pairs`` only, e.g. the whole-catalogue re-score records of an item-sharded rank)."""

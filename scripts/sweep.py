@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--dims", nargs="+", type=int, default=[64])
     ap.add_argument("--activation", nargs="+", default=["relu"], help="fusion_activation of the model (one-GPU mode)")
     ap.add_argument("--top-k", nargs="+", type=int, default=[50], help="list lengths; > 64 runs one fused pass per 64-slot page (one-GPU mode)")
+    ap.add_argument("--small-batch", type=int, default=-1, choices=[-1, 0, 1], help="pxr_set_small_batch mode (one-GPU mode): -1 auto, 0 plain tile shape, 1 forced")
     ap.add_argument("--min-ms", type=float, default=300.0, help="repeat launches until this much kernel time is accumulated")
     args = ap.parse_args()
     import os
@@ -49,6 +50,7 @@ def main():
                                           fusion_activation=act).to(dev)
             m.load_state_dict(sd, strict=False)
             e = m.engine("catalogue")
+            e.set_small_batch(args.small_batch)
             e.precompute_items(m.item_embedding.weight.detach(), feats["tag_idx"], feats["vis"], feats["txt"], feats["num"])
             del feats
             uemb = m.user_embedding.weight.detach()
@@ -79,7 +81,7 @@ def main():
                 ms = e0.elapsed_time(e1) / reps
                 pairs = B * NI
                 tf = pairs * wp / (k_ms / k_n * 1e-3) / 1e12
-                print(json.dumps({"fusion": fusion, "n_items": NI, "embedding_dim": Dm, "user_batch": B, "activation": act, "top_k": top_k, "path": e.active_path, "exact_rescore": bool(e.rescore), "ms_per_call": ms,
+                print(json.dumps({"fusion": fusion, "n_items": NI, "embedding_dim": Dm, "user_batch": B, "activation": act, "top_k": top_k, "small_batch_mode": args.small_batch, "path": e.active_path, "exact_rescore": bool(e.rescore), "ms_per_call": ms,
                                   "kernel_ms": k_ms / k_n, "pairs_per_s": pairs / (ms * 1e-3), "users_per_s": B / (ms * 1e-3),
                                   "tflops": tf, "frac_of_bf16_peak": tf / pk["tf_sustained"], "reps": reps}), flush=True)
             del e, m, sd, hist

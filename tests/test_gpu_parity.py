@@ -835,6 +835,47 @@ def test_tcgen05_topk_above_64_many_units_and_shards():
 
 
 # ======================================================================================
+# Small user batches (<= 8 users, gated fusion): the unit's 16 user slots become (user, item sub-range) pairs
+# (score_tc.cu, M_SPREAD) so that a single get_recommendations call is not capped at 1/16 of the tile; the per-slot lists
+# are merged in one or two K4 passes.  Same arithmetic per pair => the lists equal the first rows of a 16-user call bit for bit.
+# ======================================================================================
+@pytest.mark.parametrize("n_small,n_items,k,filt,mode", [(1, 5000, 50, True, 1), (1, 20011, 50, True, 1), (2, 5003, 10, True, 1), (3, 9000, 64, False, 1),
+                                                          (5, 20011, 50, True, 1), (8, 7001, 50, True, 1), (1, 600, 50, True, 1),
+                                                          (1, 60000, 50, True, -1), (6, 150001, 50, True, -1)])
+def test_tcgen05_small_batch_spread(n_small, n_items, k, filt, mode):
+    """mode 1: the small-batch shape forced on catalogues the CPU oracle scores quickly (incl. two merge passes at 20 011
+    items); mode -1: the cost model's own choice at sizes where it switches the shape on (equality with the plain shape only)."""
+    spec, sd, feats, indptr, idx, _ = _tc_workload(16, n_items, syn.SEED + 35, "gated")
+    model, eng = _engine_for(spec, sd, feats, "tcgen05")
+    eng.set_small_batch(mode)
+    missing = np.zeros(n_items, dtype=np.uint8)
+    missing[::37] = 1
+    eng.set_missing_items(torch.from_numpy(missing))
+    uemb = model.user_embedding.weight.detach()
+    users16 = torch.arange(16).cuda()
+    hist16 = (torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda()) if filt else ()
+    hist_s = (torch.from_numpy(indptr[:n_small + 1]).cuda(), torch.from_numpy(idx).cuda()) if filt else ()
+    for exact in (False, True):
+        eng.set_rescore(exact)
+        ws, wi = eng.score_topk(uemb, users16, k, *hist16)                 # plain tile shape (more than 8 users)
+        n0 = eng.launch_count
+        ss, si = eng.score_topk(uemb, users16[:n_small], k, *hist_s)      # small batch
+        assert torch.equal(si, wi[:n_small]) and torch.equal(ss, ws[:n_small]), (exact, n_small)
+        assert eng.launch_count - n0 >= 2                                    # fused kernel + merge of the sub-range lists
+    _structural_checks(ss, si, k, n_items, indptr[:n_small + 1] if filt else None, idx)
+    if mode == -1:
+        eng.set_small_batch(0)                                               # the plain shape for the same small batch, timed apart in the sweep
+        ps, pi = eng.score_topk(uemb, users16[:n_small], k, *hist_s)
+        assert torch.equal(pi, si) and torch.equal(ps, ss)
+        return
+    ref = orc.score_block(sd, cs.spec_cfg(spec), np.arange(n_small), 0, n_items, feats)
+    ref = np.where(missing.astype(bool)[None, :], 0.0, ref)               # items without features score exactly 0.0
+    for u in range(n_small if k <= 50 else 0):                            # (K = 64 leaves exact mode no spare candidates: DESIGN §6)
+        seen = idx[indptr[u]:indptr[u + 1]] if filt else None
+        _check_topk(ss[u].cpu().numpy().astype(np.float64), si[u].cpu().numpy(), ref[u], k, seen, SIMT_TOL, 0.0)
+
+
+# ======================================================================================
 # Exact mode (the product default): the fused kernel keeps its 64 best candidates per user in 16-bit arithmetic,
 # they are re-scored with the fp32 arithmetic of pxr_score_pairs and re-ranked (pxr_set_rescore, include/pxr.h).
 # Returned scores meet the fp32 tolerance; the list is the reference's whenever its top-K lies inside the 16-bit top-64.
