@@ -269,6 +269,8 @@ class _LazyIds:
         return self.n
 
     def __getitem__(self, i):
+        if not 0 <= int(i) < self.n:
+            raise IndexError(i)
         return f"{self.prefix}{int(i):08d}"
 
 
@@ -513,6 +515,21 @@ def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: i
         if args.literal_seconds > 0:
             lit = cpu_literal(cfg_name, args.literal_seconds, args.seed)
             line["cpu_baseline"].update(literal_value=lit["value"], literal_users_per_sec=lit["users_per_sec"], literal_sample=lit["sample"])
+    if with_cpu and rank == 0 and world == 1:
+        # the reference's own calling pattern on this arm: one get_recommendations(user_id: str) call per user
+        # (src/inference/recommender.py:52-110), host strings in, list of (item id, score) out
+        n_calls = 200
+        ids = [f"u{u:08d}" for u in range(n_calls)]
+        rec.get_recommendations(ids[0], top_k=TOP_K, filter_seen=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = 0
+        for uid in ids:
+            got += len(rec.get_recommendations(uid, top_k=TOP_K, filter_seen=True))
+        dt = time.perf_counter() - t0
+        line["literal_api"] = {"api": "FastRecommender.get_recommendations(user_id: str, top_k=50, filter_seen=True), one call per user",
+                               "calls": n_calls, "lists_returned": got // TOP_K, "ms_per_call": dt / n_calls * 1e3,
+                               "users_per_sec": n_calls / dt, "value": n_calls * NI / dt, "unit": UNIT}
     # free this configuration's device memory before the next one
     del rec, eng, rs_eng, model, store, feats, hist, sd, flush, uemb, d_indptr, d_idx, all_users
     torch.cuda.empty_cache()
