@@ -12,9 +12,10 @@ REPO = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libpxr.so"
 SOURCES = ["pxr_api.cu", "simt_kernels.cu", "score_tc.cu", "items_tc.cu", "sampling.cu", "novelty.cu", "diversity.cu"]
-# score_tc.cu is compiled once per fusion_activation (pxr_act value -> -DPXR_TC_TU): object 0 = ReLU kernels + host side,
-# objects 1-4 = the fused kernels of gelu / tanh / leaky_relu / silu.  (source, extra flags, object name)
-UNITS = [(s, [], s + ".o") for s in SOURCES] + [("score_tc.cu", [f"-DPXR_TC_TU={a}"], f"score_tc_act{a}.o") for a in (1, 2, 3, 4)]
+# score_tc.cu is compiled once per fusion_activation (pxr_act value -> -DPXR_TC_TU): object 0 = ReLU kernels (bf16 operands) +
+# host side, objects 1-4 = the fused kernels of gelu / tanh / leaky_relu / silu, object 5 = the ReLU kernels for fp16 operands.
+# (source, extra flags, object name); the longest units are started first
+UNITS = [("score_tc.cu", [f"-DPXR_TC_TU={a}"], f"score_tc_act{a}.o") for a in (5, 1, 2, 3, 4)] + [(s, [], s + ".o") for s in SOURCES]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math" if False else "-DPXR_PRECISE_MATH", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
               "-I", str(REPO / "include"), "-I", str(CSRC)]

@@ -46,9 +46,9 @@
 #include "pxr_common.cuh"
 #include "tc_ptx.cuh"
 
-// This source is compiled once per fusion_activation (build.py: -DPXR_TC_TU=<pxr_act>), one object each, so that the twelve
-// kernel instantiations of an activation build in parallel.  TU 0 (ReLU) also holds the one-off preparation kernels and the
-// host side; TU a > 0 only exports pxr_tc_launch_act<a>().
+// This source is compiled once per fusion_activation (build.py: -DPXR_TC_TU=<pxr_act>), one object each, so that the kernel
+// instantiations of the activations build in parallel.  TU 0 (ReLU, bf16 operands) also holds the one-off preparation kernels
+// and the host side; TU a = 1..4 only exports pxr_tc_launch_act<a>(); TU 5 holds the ReLU kernels for fp16 operands.
 #ifndef PXR_TC_TU
 #define PXR_TC_TU 0
 #endif
@@ -1617,14 +1617,21 @@ static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_
                                 : launch_fused_tk<FUS, FMT, false, ACT, M_PLAIN>(h, p, n_pairs, st);
 }
 
-// every (front end, operand format) of one activation
+// every (front end, operand format) of one activation; fp16 operands (an opt-in of the ReLU kernels) are not built for the
+// other activations (build time: 20 instantiations per activation object otherwise)
 template <int ACT>
 static int launch_fused_act(pxr_handle* h, const Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st) {
-  if (fusion == PXR_FUSION_GATED)
-    return fmt == FMT_BF16 ? launch_fused<F_GATED, FMT_BF16, ACT>(h, p, n_pairs, st) : launch_fused<F_GATED, FMT_FP16, ACT>(h, p, n_pairs, st);
-  if (fusion == PXR_FUSION_ATTENTION)
-    return fmt == FMT_BF16 ? launch_fused<F_ATTN, FMT_BF16, ACT>(h, p, n_pairs, st) : launch_fused<F_ATTN, FMT_FP16, ACT>(h, p, n_pairs, st);
-  return fmt == FMT_BF16 ? launch_fused<F_CONCAT, FMT_BF16, ACT>(h, p, n_pairs, st) : launch_fused<F_CONCAT, FMT_FP16, ACT>(h, p, n_pairs, st);
+  if constexpr (ACT != PXR_ACT_RELU || PXR_TC_TU == 0) {     // TU 0: the bf16 half of the ReLU kernels (fp16: TU 5)
+    if (fmt != FMT_BF16) PXR_FAIL(h, PXR_ERR_INVALID, "fp16 operands are built for relu models only");
+    if (fusion == PXR_FUSION_GATED) return launch_fused<F_GATED, FMT_BF16, ACT>(h, p, n_pairs, st);
+    if (fusion == PXR_FUSION_ATTENTION) return launch_fused<F_ATTN, FMT_BF16, ACT>(h, p, n_pairs, st);
+    return launch_fused<F_CONCAT, FMT_BF16, ACT>(h, p, n_pairs, st);
+  }
+  else {                                                      // TU 5: ReLU, fp16 operands
+    if (fusion == PXR_FUSION_GATED) return launch_fused<F_GATED, FMT_FP16, ACT>(h, p, n_pairs, st);
+    if (fusion == PXR_FUSION_ATTENTION) return launch_fused<F_ATTN, FMT_FP16, ACT>(h, p, n_pairs, st);
+    return launch_fused<F_CONCAT, FMT_FP16, ACT>(h, p, n_pairs, st);
+  }
 }
 
 }  // namespace tc
@@ -1632,11 +1639,16 @@ static int launch_fused_act(pxr_handle* h, const Params& p, int fusion, int fmt,
 // launchers of the other activations' objects (same signature in every TU)
 #define PXR_TC_CAT2(a, b) a##b
 #define PXR_TC_CAT(a, b) PXR_TC_CAT2(a, b)
-#if PXR_TC_TU != 0
+#if PXR_TC_TU == 5
+int pxr_tc_launch_relu_fp16(pxr_handle* h, const tc::Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st) {
+  return tc::launch_fused_act<PXR_ACT_RELU>(h, p, fusion, fmt, n_pairs, st);
+}
+#elif PXR_TC_TU != 0
 int PXR_TC_CAT(pxr_tc_launch_act, PXR_TC_TU)(pxr_handle* h, const tc::Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st) {
   return tc::launch_fused_act<PXR_TC_TU>(h, p, fusion, fmt, n_pairs, st);
 }
 #else
+int pxr_tc_launch_relu_fp16(pxr_handle* h, const tc::Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st);
 int pxr_tc_launch_act1(pxr_handle* h, const tc::Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st);   // gelu
 int pxr_tc_launch_act2(pxr_handle* h, const tc::Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st);   // tanh
 int pxr_tc_launch_act3(pxr_handle* h, const tc::Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st);   // leaky_relu
@@ -1655,6 +1667,7 @@ const char* pxr_tc_unsupported_reason(const pxr_handle* h) {
     return "fusion_hidden_dims exceeds [512, 256, 128] (the three weight matrices are resident in the CTA pair's shared memory)";
   // smaller hidden layers run zero-padded to [512, 256, 128]; concat feeds layer-1 partials of exactly 512 columns
   if (c.fusion == PXR_FUSION_CONCAT && c.hidden[0] != tc::H1) return "concat fusion with fusion_hidden_dims[0] != 512";
+  if (c.activation != PXR_ACT_RELU && c.precision == PXR_PRECISION_FP16) return "fp16 operands with a fusion_activation other than relu (only the relu kernels are built for fp16)";
   if (h->M < 4 || h->M > 6) return "fewer than 4 modalities";
   if (c.fusion == PXR_FUSION_ATTENTION && c.num_heads != tc::NH) return "attention fusion with num_attention_heads != 4";
   if (c.fusion != PXR_FUSION_CONCAT && c.embedding_dim != tc::D) return "gated / attention fusion with embedding_dim != 64 (layer 1 is a K = 64 MMA)";
@@ -1836,7 +1849,8 @@ size_t pxr_tc_topk_bytes(const pxr_handle* h, int64_t n_users, int32_t k) {
 static int tc_launch(pxr_handle* h, const tc::Params& p, int n_pairs, cudaStream_t st) {
   const int fmt = tc_fmt(h);
   switch (h->cfg.activation) {
-    case PXR_ACT_RELU: return tc::launch_fused_act<PXR_ACT_RELU>(h, p, h->cfg.fusion, fmt, n_pairs, st);
+    case PXR_ACT_RELU: return fmt == tc::FMT_BF16 ? tc::launch_fused_act<PXR_ACT_RELU>(h, p, h->cfg.fusion, fmt, n_pairs, st)
+                                                  : pxr_tc_launch_relu_fp16(h, p, h->cfg.fusion, fmt, n_pairs, st);
     case PXR_ACT_GELU: return pxr_tc_launch_act1(h, p, h->cfg.fusion, fmt, n_pairs, st);
     case PXR_ACT_TANH: return pxr_tc_launch_act2(h, p, h->cfg.fusion, fmt, n_pairs, st);
     case PXR_ACT_LEAKY_RELU: return pxr_tc_launch_act3(h, p, h->cfg.fusion, fmt, n_pairs, st);

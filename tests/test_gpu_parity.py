@@ -875,6 +875,25 @@ def test_tcgen05_small_batch_spread(n_small, n_items, k, filt, mode):
         _check_topk(ss[u].cpu().numpy().astype(np.float64), si[u].cpu().numpy(), ref[u], k, seen, SIMT_TOL, 0.0)
 
 
+def test_tcgen05_small_batch_spread_on_item_shard():
+    """The small-batch shape on an item shard (item_base != 0, history entries outside the shard): == the plain shape."""
+    n_items = 12000
+    spec, sd, feats, indptr, idx, _ = _tc_workload(16, n_items, syn.SEED + 36, "gated")
+    model, eng = _engine_for(spec, sd, feats, "tcgen05", 3001, 11500)
+    uemb = model.user_embedding.weight.detach()
+    for n_small in (1, 4, 7):
+        users = torch.arange(n_small).cuda()
+        hist = (torch.from_numpy(indptr[:n_small + 1]).cuda(), torch.from_numpy(idx).cuda())
+        for exact in (False, True):
+            eng.set_rescore(exact)
+            eng.set_small_batch(0)
+            ps, pi = eng.score_topk(uemb, users, 50, *hist)
+            eng.set_small_batch(1)
+            ss, si = eng.score_topk(uemb, users, 50, *hist)
+            assert torch.equal(pi, si) and torch.equal(ps, ss), (n_small, exact)
+        _structural_checks(ss, si, 50, 11500 - 3001, indptr[:n_small + 1], idx, item_lo=3001)
+
+
 # ======================================================================================
 # Exact mode (the product default): the fused kernel keeps its 64 best candidates per user in 16-bit arithmetic,
 # they are re-scored with the fp32 arithmetic of pxr_score_pairs and re-ranked (pxr_set_rescore, include/pxr.h).
