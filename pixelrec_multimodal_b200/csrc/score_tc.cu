@@ -601,7 +601,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
   constexpr bool GATED = (FUS != F_CONCAT);
   constexpr bool ATT = (FUS == F_ATTN);
   constexpr bool PAGED = (MODE == M_PAGED), SPREAD = (MODE == M_SPREAD);
-  static_assert(!SPREAD || FUS == F_GATED, "small-batch mode exists for the gated front end");
+  static_assert(!SPREAD || FUS != F_ATTN, "small-batch mode exists for the gated and concat front ends");
   constexpr int TU = tile_users<FUS>(), TI = tile_items<FUS>();
   using MP = Map<FUS>;
   using MiscF = MiscT<FUS>;
@@ -756,7 +756,8 @@ score_fused_kernel(const __grid_constant__ Params p) {
           {
             const int u = tid >> 4, d4 = k0 + D + (tid & 15) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ubase + u < p.n_users && d4 < p.Dm) v = *reinterpret_cast<const float4*>(p.user_emb + p.user_idx[ubase + u] * p.Dm + d4);
+            const int64_t uo2 = SPREAD ? (ubase + u) % p.n_real : ubase + u;
+            if (ubase + u < p.n_users && d4 < p.Dm) v = *reinterpret_cast<const float4*>(p.user_emb + p.user_idx[uo2] * p.Dm + d4);
             *reinterpret_cast<float4*>(&ms.eu[u][(tid & 15) * 4]) = v;
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -961,7 +962,11 @@ score_fused_kernel(const __grid_constant__ Params p) {
           const int buf = T & 1;
           if (T >= 2) ptx::mbar_wait(BAR(BAR_PI_EMPTY0 + buf), ((T >> 1) - 1) & 1);
           write_seen_mask();
-          if (tid == 0) {
+          if (SPREAD) {
+            // small batches: the 128 rows of a tile are 128 different items, more than the staging buffers hold; the
+            // layer-1 producers read each row's partial straight from L2 (prefetched a tile ahead), nothing to stage
+            if (tid == 0) ptx::mbar_arrive_local(BAR(BAR_PI_FULL0 + buf));
+          } else if (tid == 0) {
             const int nvalid = (int)min((int64_t)TI, un.row_hi - row0);
             ptx::mbar_expect_tx(BAR(BAR_PI_FULL0 + buf), (uint32_t)nvalid * 1024u);
             for (int jj = 0; jj < nvalid; ++jj)
@@ -1203,6 +1208,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
         if (lane == 0) ptx::mbar_arrive_local(BAR(BAR_UNIT_DONE));
       }
     };
+    const uint16_t* pi_g = nullptr;                  // concat, small batches: this row's item partial of the current tile (global)
     auto prev_e3 = [&]() {
       if (ATT) {
         if (prev_t == 0 && (T - 1) > 0) { ptx::mbar_wait(BAR(BAR_UNIT_RESET), reset_ph); reset_ph ^= 1; }
@@ -1228,8 +1234,9 @@ score_fused_kernel(const __grid_constant__ Params p) {
         if (ci == 0) ptx::mbar_wait(BAR(BAR_PI_FULL0 + buf), (T >> 1) & 1);          // this tile's item partials landed
         const uint32_t n = (ci & 1) ? h1use1++ : h1use0++;
         if (n > 0) { ptx::mbar_wait(BAR(BAR_H1_EMPTY0 + b), (n - 1) & 1); ptx::tc_fence_after(); }   // layer 2 consumed the buffer
-        concat_h1_chunk<ACT, FMT>(sm + MP::OFF_PI + buf * MP::PI_BUF + rj * MP::PI_STRIDE + c * 128,
-                             sm + MP::OFF_PU + ru * MP::PU_STRIDE + c * 256, tl + MP::h1buf(b));
+        concat_h1_chunk<ACT, FMT>(SPREAD ? reinterpret_cast<const uint8_t*>(pi_g) + c * 128
+                                         : sm + MP::OFF_PI + buf * MP::PI_BUF + rj * MP::PI_STRIDE + c * 128,
+                                  sm + MP::OFF_PU + ru * MP::PU_STRIDE + c * 256, tl + MP::h1buf(b));
       }
       ptx::tc_wait_st();
       ptx::tc_fence_before();
@@ -1249,6 +1256,16 @@ score_fused_kernel(const __grid_constant__ Params p) {
         // PREVIOUS tile are slotted in where their inputs become available:
         //   gated : E2(T-1), L1(0), E3(T-1), L1(1), L1(2), L1(3)
         //   concat: L1(0), E2(T-1), L1(1), E3(T-1), L1(2), L1(3)   (L1(0) refills a free buffer while layer 2 drains)
+        if (!GATED && SPREAD) {
+          const int64_t lo = un.row_lo + ((ubase + ru) / p.n_real) * p.sub_rows;
+          const int64_t row = lo + (int64_t)t * TI + rj;
+          const bool okr = row < min(lo + (int64_t)p.sub_rows, un.row_hi);
+          pi_g = p.item_pi + (okr ? row : un.row_lo) * H1;          // rows beyond the sub-range compute on a valid item and are dropped
+          if (t + 1 < un.ntiles && row + TI < un.row_hi) {
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) asm volatile("prefetch.global.L2 [%0];" ::"l"(pi_g + (size_t)TI * H1 + (2 * ci + grp) * 64));
+          }
+        }
         if (GATED && have_prev) do_e2(T - 1);
 #pragma unroll 1
         for (int ci = 0; ci < 4; ++ci) {
@@ -1610,8 +1627,8 @@ static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_
   if (thr < 0) { const char* e = getenv("PXR_TK2_ROWS"); thr = e ? atoi(e) : 8192; }
   if (p.upper) return launch_fused_tk<FUS, FMT, false, ACT, M_PAGED>(h, p, n_pairs, st);
   if (p.sub_rows > 0) {                   // small batches: short sub-ranges per slot, two top-K warps
-    if constexpr (FUS == F_GATED) return launch_fused_tk<FUS, FMT, true, ACT, M_SPREAD>(h, p, n_pairs, st);
-    else PXR_FAIL(h, PXR_ERR_INVALID, "small-batch mode exists for gated fusion only");
+    if constexpr (FUS != F_ATTN) return launch_fused_tk<FUS, FMT, true, ACT, M_SPREAD>(h, p, n_pairs, st);
+    else PXR_FAIL(h, PXR_ERR_INVALID, "small-batch mode exists for gated and concat fusion only");
   }
   return p.rows_per_split < thr ? launch_fused_tk<FUS, FMT, true, ACT, M_PLAIN>(h, p, n_pairs, st)
                                 : launch_fused_tk<FUS, FMT, false, ACT, M_PLAIN>(h, p, n_pairs, st);
@@ -1792,7 +1809,7 @@ static TcPlan tc_plan(const pxr_handle* h, int64_t n_users) {
 
 static int tc_pages(int32_t k) { return (k + tc::KCAP - 1) / tc::KCAP; }
 
-// Small batches (<= 8 users, gated fusion, K <= 64): a unit's 16 user slots would be mostly empty, so each slot becomes a
+// Small batches (<= 8 users, gated / concat fusion, K <= 64): a unit's 16 user slots would be mostly empty, so each slot becomes a
 // (user, item sub-range) pair instead -- `lists` sub-ranges of `sub_rows` rows per user, sized so that the slots of all CTA
 // pairs are busy -- and the per-slot lists are merged afterwards in one or two K4 passes (G groups of J <= 64 lists).
 struct SpreadPlan { bool on; int sub_rows, lists, G, J; int64_t n_virtual; int n_groups, n_pairs; };
@@ -1801,7 +1818,7 @@ static SpreadPlan tc_spread_plan(const pxr_handle* h, int64_t n_users, int32_t k
   SpreadPlan sp;
   memset(&sp, 0, sizeof(sp));
   // h->small_batch (pxr_set_small_batch): 0 = never, 1 = whenever the shape allows it (tests), -1 = when the cost model below says so
-  if (h->small_batch == 0 || h->cfg.fusion != PXR_FUSION_GATED || n_users > 8 || n_users <= 0 || tc_pages(k) > 1 || h->n_rows < 512) return sp;
+  if (h->small_batch == 0 || h->cfg.fusion == PXR_FUSION_ATTENTION || n_users > 8 || n_users <= 0 || tc_pages(k) > 1 || h->n_rows < 512) return sp;
   const int max_pairs = h->n_sm / 2;
   const int64_t slots = (int64_t)max_pairs * 16;
   int64_t sub = (h->n_rows * n_users + slots - 1) / slots;

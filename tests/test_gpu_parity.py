@@ -875,11 +875,18 @@ def test_tcgen05_small_batch_spread(n_small, n_items, k, filt, mode):
         _check_topk(ss[u].cpu().numpy().astype(np.float64), si[u].cpu().numpy(), ref[u], k, seen, SIMT_TOL, 0.0)
 
 
-def test_tcgen05_small_batch_spread_on_item_shard():
-    """The small-batch shape on an item shard (item_base != 0, history entries outside the shard): == the plain shape."""
+@pytest.mark.parametrize("fusion,D", [("gated", 64), ("concatenate", 64), ("concatenate", 128)])
+def test_tcgen05_small_batch_spread_on_item_shard(fusion, D):
+    """The small-batch shape on an item shard (item_base != 0, history entries outside the shard), gated and concat front
+    ends (concat: the layer-1 producers read the item partials from L2 instead of the staged tile): == the plain shape."""
     n_items = 12000
-    spec, sd, feats, indptr, idx, _ = _tc_workload(16, n_items, syn.SEED + 36, "gated")
+    spec = syn.ModelSpec(n_users=16, n_items=n_items, fusion_type=fusion, embedding_dim=D)
+    sd = syn.make_state_dict(spec, seed=syn.SEED + 36)
+    feats = syn.make_item_features(spec, seed=syn.SEED + 36)
+    syn.condition_like_trained(sd, spec, feats)
+    indptr, idx, _ = syn.make_histories(16, n_items, seed=syn.SEED + 36, lo=3, hi=60)
     model, eng = _engine_for(spec, sd, feats, "tcgen05", 3001, 11500)
+    assert eng.active_path == "tcgen05"
     uemb = model.user_embedding.weight.detach()
     for n_small in (1, 4, 7):
         users = torch.arange(n_small).cuda()
