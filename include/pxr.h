@@ -170,7 +170,7 @@ int pxr_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* us
 int pxr_set_rescore(pxr_handle* h, int on);
 int pxr_get_rescore(const pxr_handle* h);
 
-/* Small user batches on the fused path (gated fusion, <= 8 users, K <= 64): the unit's 16 user slots become (user, item
+/* Small user batches on the fused path (gated / concat fusion, <= 8 users, K <= 64): the unit's 16 user slots become (user, item
  * sub-range) pairs, so that one Recommender.get_recommendations call (src/inference/recommender.py:52-110 scores ONE user
  * per call) is not capped at 1/16 of the tile; the per-slot lists are merged by one or two pxr_merge_topk passes.  Same
  * arithmetic per pair: the lists equal those of the plain tile shape bit for bit.
