@@ -63,6 +63,14 @@ for fusion in ("gated", "attention", "concatenate"):
             full.engine().set_rescore(exact)
             fs, fi = full.recommend_all(users, top_k=50, filter_seen=True)
             assert torch.equal(fi, i) and torch.equal(fs, s), (fusion, exact, int((fi == i).all(dim=1).sum()))
+    # top_k > 64: the shards exchange their raw 128-slot lists (two pages of the fused kernel), merged by the k > 64 form
+    # of pxr_merge_topk and re-scored once by the owning rank == the single-GPU exact top-100
+    st = ShardedTopK(local_raw, rescore=rec.rescore)
+    s100, i100 = st.recommend_all(users, 100, True)
+    if rank == 0:
+        full.engine().set_rescore(True)
+        fs, fi = full.recommend_all(users, top_k=100, filter_seen=True)
+        assert torch.equal(fi, i100) and torch.equal(fs, s100), (fusion, "top-100", int((fi == i100).all(dim=1).sum()))
     # sharded evaluation (exact mode) == single-GPU evaluation
     st = ShardedTopK(local_raw, rescore=rec.rescore)
     test = pd.DataFrame({"user_id": [syn.user_ids(spec.n_users)[u] for u in range(spec.n_users) if test_item[u] >= 0],
