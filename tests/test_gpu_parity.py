@@ -267,6 +267,34 @@ def test_merge_topk_shapes(S, n, k):
         assert gi[u][:m].tolist() == ri.tolist() and np.all(gi[u][m:] == -1) and np.all(np.isneginf(gs[u][m:]))
         assert np.array_equal(gs[u][:m].astype(np.float64), rs)
 
+@pytest.mark.parametrize("S,n,k,skew", [(2, 257, 64, True), (4, 1000, 50, True), (5, 300, 7, False), (8, 999, 50, True), (16, 260, 64, True),
+                                         (3, 256, 1, False), (9, 513, 33, True)])
+def test_merge_topk_many_users_few_lists(S, n, k, skew):
+    """K4 for few lists and many users: skewed lists (one shard holds most of a user's winners), ties across shards,
+    ragged / empty lists, user counts that are not a multiple of the block == oracle merge.  (Written for the lane-per-user /
+    tournament kernels of profiles/r02_k4_lane_tournament_experiment.log; kept for the shipped kernel.)"""
+    from pixelrec_multimodal_b200.engine import merge_topk
+    rng = np.random.default_rng(7 * S + n + k)
+    sc = np.round(rng.standard_normal((S, n, k)), 1).astype(np.float32)          # one decimal: many ties across lists
+    if skew:
+        hot = rng.integers(0, S, n)
+        sc[hot, np.arange(n)] += 2.5                                             # user u's winners mostly come from list hot[u]
+    sc = -np.sort(-sc, axis=2)
+    ix = np.stack([np.stack([np.sort(rng.choice(5000, k, replace=False)) + 5000 * s for _ in range(n)]) for s in range(S)]).astype(np.int32)
+    for u in range(0, n, 3):                                                     # ragged tails and empty lists
+        s_ = int(rng.integers(0, S))
+        keep = int(rng.integers(0, k + 1))
+        sc[s_, u, keep:] = -np.inf; ix[s_, u, keep:] = -1
+    gs, gi = merge_topk(torch.from_numpy(sc).cuda(), torch.from_numpy(ix).cuda())
+    gs, gi = gs.cpu().numpy(), gi.cpu().numpy()
+    for u in range(n):
+        lists = [(ix[s, u][ix[s, u] >= 0].astype(np.int64), sc[s, u][ix[s, u] >= 0].astype(np.float64)) for s in range(S)]
+        ri, rs = orc.merge_topk(lists, k)
+        m = len(ri)
+        assert gi[u][:m].tolist() == ri.tolist() and np.all(gi[u][m:] == -1) and np.all(np.isneginf(gs[u][m:])), u
+        assert np.array_equal(gs[u][:m].astype(np.float64), rs)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("K,max_pos", [(50, 80), (64, 3), (100, 40), (7, 2)])
 def test_metrics_kernel_variants(K, max_pos):
