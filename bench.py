@@ -71,6 +71,10 @@ def w_pair(fusion: str, D: int, H):
     2*(sum H_{l-1} H_l + H_L), plus the per-pair first layer 2*D*H1 when the
     fused vector depends on the pair (gated / attention)."""
     tail = 2 * (sum(a * b for a, b in zip(H[:-1], H[1:])) + H[-1])
+    if fusion == "gated" and D != 64:
+        # F_GATEDW (csrc/score_tc.cu): layer 1 is a gate-weighted sum of per-user / per-item partials on CUDA cores,
+        # so only the tail runs on the tensor pipe -- count what the kernel executes, not SURVEY's 2*D*H1 estimate
+        return tail
     return tail + (0 if fusion == "concatenate" else 2 * D * H[0])
 
 

@@ -77,7 +77,7 @@ def modality_features(sd, act, user_idx, item_idx, tag_idx, vis=None, txt=None, 
     return feats
 
 
-def gated_fusion(sd, feats, dt):
+def gated_fusion(sd, feats, dt, return_gates=False):
     """src/models/layers.py:195-225."""
     cat = np.concatenate(feats, axis=1)
     logits = linear(cat, sd["fusion_layer.gating_network.0.weight"].astype(dt),
@@ -86,6 +86,8 @@ def gated_fusion(sd, feats, dt):
     g = np.exp(logits)
     g /= g.sum(axis=-1, keepdims=True)
     stack = np.stack(feats, axis=1)                    # (B, M, D)
+    if return_gates:
+        return g
     return (stack * g[:, :, None]).sum(axis=1)
 
 
@@ -477,7 +479,17 @@ def forward_pairs_lowp(sd, cfg, user_idx, item_idx, tag_idx, vis=None, txt=None,
     feats = modality_features(sd, act, np.asarray(user_idx), np.asarray(item_idx), np.asarray(tag_idx), vis, txt, num, dt)
     ft = cfg.get("fusion_type", "concatenate")
     ws, bs = fold_batchnorm(sd, bool(cfg.get("use_batch_norm", True)))
-    if ft == "gated":
+    if ft == "gated" and feats[0].shape[1] != 64:
+        # embedding_dim != 64 (F_GATEDW): layer 1 is linear in the fused vector and the gate weights sum to 1, so it is the
+        # gate-weighted sum of one per-user partial (fp32) and M - 1 per-item partials W1 f_m + b1 (stored in 16 bit);
+        # the sum goes through the activation and is rounded once as the layer-2 operand
+        g = gated_fusion(sd, feats, dt, return_gates=True)
+        z1 = g[:, :1] * (feats[0] @ ws[0].T + bs[0])
+        for m in range(1, len(feats)):
+            z1 = z1 + g[:, m:m + 1] * rnd(feats[m] @ ws[0].T + bs[0])
+        h = rnd(activation(z1, act))
+        start = 1
+    elif ft == "gated":
         x = rnd(gated_fusion(sd, feats, dt))
         h = x
         start = 0

@@ -45,6 +45,8 @@ struct GemmParams {
   const float* bias;                    // [N]
   int mode, act, fmt16;                 // OUT_F32_ACT: out_f[row * ldo + n] = act(acc + b) (act < 0: identity); OUT_16: 16-bit, no act
   int n_store;                          // columns of each N tile that are stored (0 = all): padded outputs
+  int qt_nm;                            // OUT_16, > 0: row = (item, modality m < qt_nm), stored chunk-major for the wide gated front end
+                                        // of score_tc.cu: [item / 16][column / 64][item % 16][qt_nm x 64 columns + 8 of padding]
   float* out_f; uint16_t* out_h; int64_t ldo;
   int n_stages;
 };
@@ -224,6 +226,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm3x_kernel(const __grid_constan
             }
           } else {
             uint16_t* o = p.out_h + row * p.ldo + nt * p.NT + n0;
+            if (p.qt_nm > 0) {
+              const int64_t item = row / p.qt_nm; const int m = (int)(row % p.qt_nm);
+              const int n = nt * p.NT + n0;                            // 32 columns inside one 64-column chunk
+              const size_t item_b = (size_t)p.qt_nm * 128 + 16, stage_b = 16 * item_b;
+              o = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(p.out_h) + ((size_t)(item >> 4) * 8 + (n >> 6)) * stage_b +
+                                              (size_t)(item & 15) * item_b + m * 128 + (n & 63) * 2);
+            }
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
               uint32_t pk[4];
@@ -377,7 +386,9 @@ int pxr_items_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
   const int FD = (h->M - 1) * D;
   if (concat) total += pxr_align_up(itc::img_bytes(c.hidden[0], FD), 1024);
   const bool gated = c.fusion == PXR_FUSION_GATED;
+  const bool wide = pxr_tc_gated_wide(h);     // gated at embedding_dim != 64: per-modality layer-1 partials, W1 (512 x D) as one image
   if (gated) total += pxr_align_up(itc::img_bytes(16, FD), 1024) + 1024;      // gate logits: 16 padded outputs + padded bias
+  if (wide) total += pxr_align_up(itc::img_bytes(c.hidden[0], D), 1024);
   if (h->tc_items_w) { cudaFree(h->tc_items_w); h->tc_items_w = nullptr; }
   PXR_CUDA(h, cudaMalloc(&h->tc_items_w, total + 1024));
   uint8_t* cur = reinterpret_cast<uint8_t*>(h->tc_items_w);
@@ -394,6 +405,12 @@ int pxr_items_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
     h->tc_items_img[2] = cur;
     itc::split_weights_kernel<<<512, 256, 0, st>>>(h->mlp[0].w, h->mlp[0].k, D, c.hidden[0], FD, 256, cur, c.hidden[0]);
     h->launches++;
+  }
+  if (wide) {
+    h->tc_items_img[2] = cur;
+    itc::split_weights_kernel<<<512, 256, 0, st>>>(h->mlp[0].w, h->mlp[0].k, 0, c.hidden[0], D, 256, cur, c.hidden[0]);
+    h->launches++;
+    cur += pxr_align_up(itc::img_bytes(c.hidden[0], D), 1024);
   }
   h->tc_items_img[3] = nullptr; h->tc_gate_bias = nullptr;
   if (gated) {
@@ -419,6 +436,19 @@ int pxr_launch_item_logit_tc(pxr_handle* h, int64_t n_rows, float* out, cudaStre
   gp.A = h->item_feats; gp.lda = FD; gp.M = n_rows; gp.K = FD; gp.N = 16; gp.NT = 16;
   gp.wimg = h->tc_items_img[3]; gp.bias = h->tc_gate_bias;
   gp.mode = itc::OUT_F32_ACT; gp.act = -1; gp.out_f = out; gp.ldo = 8; gp.n_store = 8;
+  return itc::launch_gemm(h, gp, st);
+}
+
+// wide gated: the M - 1 layer-1 partials of every item, Q[row][m] = W1 f_m + b1 -> 16 bit: the record viewed as
+// n_rows * (M - 1) vectors of embedding_dim (it is stored [rows][M-1][D]) times W1^T
+int pxr_launch_item_q_tc(pxr_handle* h, int64_t n_rows, uint16_t* out, int fmt16, cudaStream_t st) {
+  const pxr_config& c = h->cfg;
+  const int D = c.embedding_dim;
+  itc::GemmParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.A = h->item_feats; gp.lda = D; gp.M = n_rows * (h->M - 1); gp.K = D; gp.N = c.hidden[0]; gp.NT = 256;
+  gp.wimg = h->tc_items_img[2]; gp.bias = h->mlp[0].b;
+  gp.mode = itc::OUT_16; gp.fmt16 = fmt16; gp.out_h = out; gp.ldo = c.hidden[0]; gp.qt_nm = h->M - 1;
   return itc::launch_gemm(h, gp, st);
 }
 

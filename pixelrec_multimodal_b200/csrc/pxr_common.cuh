@@ -52,7 +52,7 @@ struct pxr_handle {
   int small_batch = -1;       // small-batch tile shape of the fused gated kernel: -1 auto (cost model), 0 off, 1 whenever possible (pxr_set_small_batch)
   bool rescore = true;        // exact mode of the fused path: fp32 re-score + re-rank of the 64-slot lists (pxr_set_rescore)
   uint64_t tc_attr_set = 0;   // bit per kernel whose max-dynamic-smem attribute has been set
-  uint64_t tc_attr_fused[2] = {0, 0};   // the same for the instantiations of the fused scoring kernel (score_tc.cu)
+  uint64_t tc_attr_fused[3] = {0, 0, 0};   // the same for the instantiations of the fused scoring kernel (score_tc.cu)
   void* fast_w = nullptr;     // bf16 swizzled operand images + fp32 vectors (see score_tc.cu)
   float tc_bias_host[1028];   // attention fast path: host copy of b1' b2 b3 w4 b4 (passed as kernel parameters)
   void* tc_items_w = nullptr;       // item precompute on the tensor pipe: hi / lo tf32 weight chunk images (items_tc.cu)
@@ -244,6 +244,7 @@ int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_user
 // tcgen05 path (score_tc.cu)
 bool pxr_tc_supported(const pxr_handle* h);
 const char* pxr_tc_unsupported_reason(const pxr_handle* h);   // NULL = supported
+bool pxr_tc_gated_wide(const pxr_handle* h);   // gated fusion at embedding_dim != 64: gate-weighted layer-1 partials (F_GATEDW)
 #define PXR_TC_MAX_K 1024   // 16 pages of the fused kernel's 64-slot lists
 bool pxr_tc_can_run(const pxr_handle* h, int32_t k);   // this call (k, shard size) fits the kernel's limits
 size_t pxr_tc_weight_bytes(const pxr_handle* h);
@@ -259,6 +260,7 @@ int pxr_launch_items_tc(pxr_handle* h, const float* item_embedding, const int64_
                         float* feats_out, cudaStream_t st);
 int pxr_launch_item_pi_tc(pxr_handle* h, int64_t n_rows, uint16_t* out, int fmt16, cudaStream_t st);
 int pxr_launch_item_logit_tc(pxr_handle* h, int64_t n_rows, float* out, cudaStream_t st);
+int pxr_launch_item_q_tc(pxr_handle* h, int64_t n_rows, uint16_t* out, int fmt16, cudaStream_t st);
 int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t* user_idx, int64_t n_users,
                       const int64_t* seen_indptr, const int32_t* seen_idx, int32_t k, float* out_scores,
                       int32_t* out_idx, void* ws, size_t ws_bytes, cudaStream_t st);

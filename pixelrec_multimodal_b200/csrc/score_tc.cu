@@ -61,7 +61,13 @@ constexpr int QCAP = 512;                 // candidate queue entries
 constexpr int THREADS = 512;                 // 16 warps
 constexpr uint32_t IDX_MASK = 0x0FFFFFFFu;   // 28-bit item index inside a queue / list key
 constexpr int FMT_BF16 = 0, FMT_FP16 = 1;
-constexpr int F_CONCAT = 0, F_GATED = 1, F_ATTN = 2;   // front ends of the kernel template
+constexpr int F_CONCAT = 0, F_GATED = 1, F_ATTN = 2, F_GATEDW = 3;   // front ends of the kernel template
+// F_GATEDW ("wide" gated fusion, any embedding_dim): layer 1 of a gated model is linear in the fused vector, so
+//   W1 (g_0 E_u + sum_m g_m f_m) + b1 = g_0 (W1 E_u + b1) + sum_m g_m (W1 f_m + b1)        (the gate weights sum to 1)
+// i.e. a gate-weighted sum of one per-user and M - 1 per-item PARTIALS of 512 columns, computed once per user / item
+// (SURVEY.md A3's split applied to A4).  The kernel is the concat pipeline (layer-1 producers on CUDA cores, layers 2 / 3 on
+// tcgen05) with the broadcast add replaced by that weighted sum; it does not depend on embedding_dim.
+template <int FUS> __host__ __device__ constexpr bool l1_on_tensor_pipe() { return FUS == F_GATED || FUS == F_ATTN; }
 constexpr int M_PLAIN = 0, M_PAGED = 1, M_SPREAD = 2;  // kernel modes (template parameter MODE)
 // users x items of one CTA tile (128 rows).  gated / concat: 8 x 16, row = user * 16 + item.  attention: 16 x 8,
 // row = item * 16 + user -- the 16 rows of an item are the M dimension of the front end's register MMAs
@@ -85,7 +91,7 @@ enum {
   BAR_W = 0, BAR_A_FULL, BAR_A_EMPTY, BAR_D1_FULL0, BAR_D1_FULL1, BAR_D1_FULL2, BAR_D1_FULL3, BAR_H1_FULL0, BAR_H1_FULL1,
   BAR_H1_FULL2, BAR_H1_FULL3, BAR_H1_EMPTY0, BAR_H1_EMPTY1, BAR_H1_EMPTY2, BAR_H1_EMPTY3, BAR_PI_FULL0, BAR_PI_FULL1,
   BAR_PI_EMPTY0, BAR_PI_EMPTY1, BAR_D2_FULL, BAR_H2_FULL0, BAR_H2_FULL1, BAR_D3_FULL, BAR_D3_EMPTY, BAR_UNIT_DONE,
-  BAR_UNIT_RESET, N_BARS
+  BAR_UNIT_RESET, BAR_Q_FULL0, BAR_Q_FULL1, BAR_Q_FULL2, BAR_Q_EMPTY0, BAR_Q_EMPTY1, BAR_Q_EMPTY2, N_BARS
 };
 
 // Per-CTA scratch in shared memory.  (The attention variant keeps the epilogue biases in the kernel-parameter constant
@@ -113,7 +119,7 @@ struct MiscT {
 // shared / tensor memory maps per front end
 template <int FUS>
 struct Map {
-  static constexpr bool GATED = (FUS != F_CONCAT);               // layer 1 on the tensor pipe from an A1 tile
+  static constexpr bool GATED = l1_on_tensor_pipe<FUS>();        // layer 1 on the tensor pipe from an A1 tile
   // shared memory (bytes from a 1024-aligned base); the weight image is the first WIMG bytes
   static constexpr uint32_t OFF_W1 = 0;                          // gated: 8 N-chunks x (32 rows x 128 B) = 32 KB
   static constexpr uint32_t OFF_W2 = GATED ? 32768u : 0u;        // 8 K-blocks x (128 rows x 128 B) = 128 KB
@@ -122,8 +128,12 @@ struct Map {
   static constexpr uint32_t OFF_A1 = WIMG;                       // gated: 128 rows x 128 B, SWIZZLE_128B
   static constexpr uint32_t PI_STRIDE = 1040, PI_BUF = tile_items<F_CONCAT>() * PI_STRIDE;   // concat: 16 item partials (512 x 16 bit)
   static constexpr uint32_t OFF_PI = WIMG;                       // padded by 16 B per row: conflict-free reads
+  // wide gated: the item partials of a tile are staged one 64-column chunk at a time: per item M - 1 rows of 128 B + 16 B of
+  // padding (conflict-free 16-byte reads), 16 items per stage, a ring of three stages in the Pi area
+  static constexpr uint32_t Q_STAGES = 3, Q_STAGE_MAX = 16u * (5u * 128u + 16u);
   static constexpr uint32_t PU_STRIDE = 2064;                    // concat: 8 user partials (512 fp32), padded
   static constexpr uint32_t OFF_PU = OFF_PI + 2 * PI_BUF;
+  static_assert(Q_STAGES * Q_STAGE_MAX <= 2 * PI_BUF, "the chunk ring of the wide gated front end lives in the Pi area");
   static constexpr uint32_t OFF_MISC = GATED ? OFF_A1 + 16384u : OFF_PU + tile_users<F_CONCAT>() * PU_STRIDE;
   static constexpr uint32_t SMEM = OFF_MISC + (uint32_t)sizeof(MiscT<FUS>) + 1024u;   // + alignment slack
   // tensor memory (columns)
@@ -134,8 +144,8 @@ struct Map {
     return GATED ? (b < 2 ? 64u * b : TM_D3 + 64u * (b - 2)) : 32u * b;
   }
 };
-static_assert(Map<F_GATED>::SMEM <= 232448 && Map<F_CONCAT>::SMEM <= 232448 && Map<F_ATTN>::SMEM <= 232448, "shared memory budget");
-static_assert(Map<F_CONCAT>::OFF_MISC % 16 == 0 && Map<F_GATED>::OFF_MISC % 16 == 0, "alignment");
+static_assert(Map<F_GATED>::SMEM <= 232448 && Map<F_CONCAT>::SMEM <= 232448 && Map<F_ATTN>::SMEM <= 232448 && Map<F_GATEDW>::SMEM <= 232448, "shared memory budget");
+static_assert(Map<F_CONCAT>::OFF_MISC % 16 == 0 && Map<F_GATED>::OFF_MISC % 16 == 0 && Map<F_GATEDW>::OFF_MISC % 16 == 0, "alignment");
 static_assert(offsetof(MiscT<F_ATTN>, list) % 8 == 0, "alignment");
 static_assert(offsetof(MiscT<F_GATED>, list) % 8 == 0 && offsetof(MiscT<F_GATED>, bars) % 8 == 0 && offsetof(MiscT<F_ATTN>, bars) % 8 == 0, "alignment");
 
@@ -145,6 +155,8 @@ struct Params {
   const float* gate_w;          // gated: (M, M*D) fp32 row-major; the user part is the first D of each row
   const float* item_feats;      // gated: [rows][M-1][D] fp32 projected item-side modality vectors
   const float* item_logit;      // gated: [rows][8] fp32 item part of the gate logits (+ gate bias)
+  const uint16_t* item_q;       // wide gated: 16-bit per-modality item partials of layer 1, Q_m = W1 f_m + b1, chunk-major:
+                                // [tile of 16 rows][8 chunks][16 items][(M-1) x 64 columns + 8 of padding]  (q_stage_bytes per chunk)
   const uint16_t* item_pi;      // concat: [rows][512] 16-bit item partial of layer 1 (+ b1)
   const float* w1u_t;           // concat: [64][512] fp32, user columns of W1 transposed
   const uint4* attn_rec;        // attention: [rows][ATT_REC_U4] per-item records (16-bit MMA B fragments in lane order)
@@ -168,7 +180,7 @@ struct Params {
   int32_t* out_idx;
   int64_t n_users, n_rows, item_base;
   int M, K, S, rows_per_split, n_units, final_act;
-  int Dm;                       // embedding dim of the model (concat: any multiple of 4 up to 512; gated / attention: 64)
+  int Dm;                       // embedding dim of the model (concat / wide gated: any multiple of 4 up to 512; gated / attention: 64)
   // M_SPREAD (small batches): n_users above counts VIRTUAL users v = r * n_real + u: real user u on item sub-range
   // r = rows [r * sub_rows, (r + 1) * sub_rows) of the shard; user_idx / seen_indptr are indexed by u = v % n_real
   int64_t n_real;
@@ -269,6 +281,49 @@ __device__ __forceinline__ void concat_h1_chunk(const uint8_t* pi_row, const uin
     o[4 * q + 1] = act_pack<ACT, FMT>(a.z + p1.x, a.w + p1.y);
     o[4 * q + 2] = act_pack<ACT, FMT>(b.x + p2.x, b.y + p2.y);
     o[4 * q + 3] = act_pack<ACT, FMT>(b.z + p3.x, b.w + p3.y);
+  }
+  ptx::tmem_st32(t_dst, o);
+}
+
+// wide gated layer 1 for one row and one 64-wide chunk: act(g_0 Pu[user] + sum_m g_{m+1} Q_m[item]) -> 32 packed columns.
+// `qi` = this row's item block of the staged chunk in shared memory ([M-1] rows of 64 columns, 16 bit; blocks are 16 B
+// apart modulo 128, so the 16-byte reads of a quarter warp hit distinct banks; the two user rows of a warp share every read).
+__host__ __device__ constexpr uint32_t q_item_bytes(int nm) { return (uint32_t)nm * 128u + 16u; }
+__host__ __device__ constexpr uint32_t q_stage_bytes(int nm) { return 16u * q_item_bytes(nm); }       // one chunk of one 16-item tile
+template <int ACT, int FMT>
+__device__ __forceinline__ void gatedw_h1_chunk(const uint8_t* qi, int nm, const float (&g)[6], const uint8_t* pu_row, uint32_t t_dst) {
+  uint32_t o[32];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {                      // 16 columns per step
+    uint4 pv[5][2];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      if (m < nm) {
+        const uint4* src = reinterpret_cast<const uint4*>(qi + m * 128 + 32 * s);
+        pv[m][0] = src[0]; pv[m][1] = src[1];
+      } else {
+        pv[m][0] = pv[m][1] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = *reinterpret_cast<const float4*>(pu_row + 64 * s + 16 * q);
+      acc[4 * q + 0] = g[0] * a.x; acc[4 * q + 1] = g[0] * a.y; acc[4 * q + 2] = g[0] * a.z; acc[4 * q + 3] = g[0] * a.w;
+    }
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      const float gm = g[m + 1];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const float2 p0 = unpack2<FMT>(pv[m][hh].x), p1 = unpack2<FMT>(pv[m][hh].y), p2 = unpack2<FMT>(pv[m][hh].z), p3 = unpack2<FMT>(pv[m][hh].w);
+        float* ac = acc + 8 * hh;
+        ac[0] = fmaf(gm, p0.x, ac[0]); ac[1] = fmaf(gm, p0.y, ac[1]); ac[2] = fmaf(gm, p1.x, ac[2]); ac[3] = fmaf(gm, p1.y, ac[3]);
+        ac[4] = fmaf(gm, p2.x, ac[4]); ac[5] = fmaf(gm, p2.y, ac[5]); ac[6] = fmaf(gm, p3.x, ac[6]); ac[7] = fmaf(gm, p3.y, ac[7]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[8 * s + i] = act_pack<ACT, FMT>(acc[2 * i], acc[2 * i + 1]);
   }
   ptx::tmem_st32(t_dst, o);
 }
@@ -598,10 +653,11 @@ template <int FUS, int FMT, bool TK2, int ACT, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(n_threads<FUS>(), 1)
 score_fused_kernel(const __grid_constant__ Params p) {
   constexpr int NT = n_threads<FUS>();
-  constexpr bool GATED = (FUS != F_CONCAT);
+  constexpr bool GATED = l1_on_tensor_pipe<FUS>();
   constexpr bool ATT = (FUS == F_ATTN);
+  constexpr bool WIDE = (FUS == F_GATEDW);       // gated fusion on the concat pipeline: gate-weighted layer-1 partials
   constexpr bool PAGED = (MODE == M_PAGED), SPREAD = (MODE == M_SPREAD);
-  static_assert(!SPREAD || FUS != F_ATTN, "small-batch mode exists for the gated and concat front ends");
+  static_assert(!SPREAD || FUS == F_GATED || FUS == F_CONCAT, "small-batch mode exists for the gated and concat front ends");
   constexpr int TU = tile_users<FUS>(), TI = tile_items<FUS>();
   using MP = Map<FUS>;
   using MiscF = MiscT<FUS>;
@@ -638,6 +694,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
       ptx::mbar_init(BAR(BAR_H1_EMPTY0 + b), 1);
     }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(BAR(BAR_PI_FULL0 + b), 1); ptx::mbar_init(BAR(BAR_PI_EMPTY0 + b), 8); }
+    for (int b = 0; b < 3; ++b) { ptx::mbar_init(BAR(BAR_Q_FULL0 + b), 1); ptx::mbar_init(BAR(BAR_Q_EMPTY0 + b), 4); }   // wide gated: 4 warps read a chunk
     ptx::mbar_init(BAR(BAR_D2_FULL), 1);
     ptx::mbar_init(BAR(BAR_H2_FULL0), 8); ptx::mbar_init(BAR(BAR_H2_FULL1), 8);
     ptx::mbar_init(BAR(BAR_D3_FULL), 1);
@@ -739,8 +796,13 @@ score_fused_kernel(const __grid_constant__ Params p) {
 #pragma unroll
         for (int u = 0; u < TU; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f; }
         const float* wcol = p.w1u_t + 4 * tid;
+        float lacc = 0.f;                    // wide gated: user part of gate logit m of user u (layers.py:207 split), tid = 8 u + m
         for (int k0 = 0;; k0 += D) {
           const int kn = min(D, p.Dm - k0);
+          if (WIDE && tid < 64 && (tid & 7) < Mm) {
+            const float* wr = p.gate_w + (size_t)(tid & 7) * Mm * p.Dm + k0;
+            for (int k = 0; k < kn; ++k) lacc = fmaf(wr[k], ms.eu[tid >> 3][k], lacc);
+          }
 #pragma unroll 4
           for (int k = 0; k < kn; ++k) {
             const float4 wv = *reinterpret_cast<const float4*>(wcol + (size_t)(k0 + k) * H1);
@@ -761,6 +823,12 @@ score_fused_kernel(const __grid_constant__ Params p) {
             *reinterpret_cast<float4*>(&ms.eu[u][(tid & 15) * 4]) = v;
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (WIDE) {                          // the per-user partial carries b1 (every partial does: the gate weights sum to 1)
+          const float4 bb = *reinterpret_cast<const float4*>(&ms.b1[4 * tid]);
+#pragma unroll
+          for (int u = 0; u < TU; ++u) { acc[u][0] += bb.x; acc[u][1] += bb.y; acc[u][2] += bb.z; acc[u][3] += bb.w; }
+          if (tid < 64) ms.lu[tid >> 3][tid & 7] = lacc;
         }
 #pragma unroll
         for (int u = 0; u < TU; ++u)
@@ -962,7 +1030,24 @@ score_fused_kernel(const __grid_constant__ Params p) {
           const int buf = T & 1;
           if (T >= 2) ptx::mbar_wait(BAR(BAR_PI_EMPTY0 + buf), ((T >> 1) - 1) & 1);
           write_seen_mask();
-          if (SPREAD) {
+          if (WIDE) {
+            // M - 1 partials per item = 80 KB per tile: staged one 64-column chunk (10 KB, contiguous in the chunk-major
+            // layout) at a time through a ring of three buffers, one TMA bulk copy each; the tile itself (seen masks, the
+            // unit's user constants) is announced first
+            if (tid == 0) {
+              ptx::mbar_arrive_local(BAR(BAR_PI_FULL0 + buf));
+              const uint32_t stage = q_stage_bytes(Mm - 1);
+              const uint8_t* src = reinterpret_cast<const uint8_t*>(p.item_q) + (size_t)(row0 >> 4) * 8 * stage;
+#pragma unroll 1
+              for (int c = 0; c < 8; ++c) {
+                const uint32_t G = (uint32_t)T * 8u + c, slot = G % MP::Q_STAGES, n = G / MP::Q_STAGES;
+                if (n > 0) ptx::mbar_wait(BAR(BAR_Q_EMPTY0 + slot), (n - 1) & 1);      // its four readers are done with the slot
+                ptx::mbar_expect_tx(BAR(BAR_Q_FULL0 + slot), stage);
+                ptx::bulk_g2s(base + MP::OFF_PI + slot * MP::Q_STAGE_MAX, src + (size_t)c * stage, stage, BAR(BAR_Q_FULL0 + slot));
+              }
+            }
+            __syncwarp();
+          } else if (SPREAD) {
             // small batches: the 128 rows of a tile are 128 different items, more than the staging buffers hold; the
             // layer-1 producers read each row's partial straight from L2 (prefetched a tile ahead), nothing to stage
             if (tid == 0) ptx::mbar_arrive_local(BAR(BAR_PI_FULL0 + buf));
@@ -1209,6 +1294,10 @@ score_fused_kernel(const __grid_constant__ Params p) {
       }
     };
     const uint16_t* pi_g = nullptr;                  // concat, small batches: this row's item partial of the current tile (global)
+    // wide gated: the item part of this row's gate logits (loaded at the top of the tile, used once the tile's user
+    // constants are known to be in place), its gate weights
+    float4 wl0 = make_float4(0.f, 0.f, 0.f, 0.f), wl1 = wl0;
+    float wg[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     auto prev_e3 = [&]() {
       if (ATT) {
         if (prev_t == 0 && (T - 1) > 0) { ptx::mbar_wait(BAR(BAR_UNIT_RESET), reset_ph); reset_ph ^= 1; }
@@ -1232,8 +1321,28 @@ score_fused_kernel(const __grid_constant__ Params p) {
       } else {
         const int buf = T & 1;
         if (ci == 0) ptx::mbar_wait(BAR(BAR_PI_FULL0 + buf), (T >> 1) & 1);          // this tile's item partials landed
+        if (WIDE && ci == 0) {
+          // gate of this row's pair: softmax over the M modality logits (layers.py:207-211); the unit's user parts
+          // (ms.lu, Pu) are in place once the tile has been announced
+          const float li[8] = {wl0.x, wl0.y, wl0.z, wl0.w, wl1.x, wl1.y, wl1.z, wl1.w};
+          float mx = -INFINITY;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) { wg[m] = m < p.M ? li[m] + ms.lu[ru][m] : -INFINITY; mx = fmaxf(mx, wg[m]); }
+          float sum = 0.f;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) { wg[m] = m < p.M ? expf(wg[m] - mx) : 0.f; sum += wg[m]; }
+          const float inv = 1.f / sum;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) wg[m] *= inv;
+        }
         const uint32_t n = (ci & 1) ? h1use1++ : h1use0++;
         if (n > 0) { ptx::mbar_wait(BAR(BAR_H1_EMPTY0 + b), (n - 1) & 1); ptx::tc_fence_after(); }   // layer 2 consumed the buffer
+        if (WIDE) {
+          const uint32_t G = (uint32_t)T * 8u + c, slot = G % MP::Q_STAGES;
+          ptx::mbar_wait(BAR(BAR_Q_FULL0 + slot), (G / MP::Q_STAGES) & 1);        // this chunk of the tile's item partials landed
+          gatedw_h1_chunk<ACT, FMT>(sm + MP::OFF_PI + slot * MP::Q_STAGE_MAX + rj * q_item_bytes(p.M - 1), p.M - 1, wg,
+                                    sm + MP::OFF_PU + ru * MP::PU_STRIDE + c * 256, tl + MP::h1buf(b));
+        } else
         concat_h1_chunk<ACT, FMT>(SPREAD ? reinterpret_cast<const uint8_t*>(pi_g) + c * 128
                                          : sm + MP::OFF_PI + buf * MP::PI_BUF + rj * MP::PI_STRIDE + c * 128,
                                   sm + MP::OFF_PU + ru * MP::PU_STRIDE + c * 256, tl + MP::h1buf(b));
@@ -1243,6 +1352,7 @@ score_fused_kernel(const __grid_constant__ Params p) {
       __syncwarp();
       if (lane == 0) {
         ptx::mbar_arrive_cluster(BAR(BAR_H1_FULL0 + b), 0);
+        if (WIDE) ptx::mbar_arrive_local(BAR(BAR_Q_EMPTY0 + ((uint32_t)T * 8u + c) % MP::Q_STAGES));   // this warp is done with the staged chunk
         if (!GATED && ci == 3) ptx::mbar_arrive_local(BAR(BAR_PI_EMPTY0 + (T & 1)));   // done with this tile's Pi (and Pu)
       }
     };
@@ -1265,6 +1375,12 @@ score_fused_kernel(const __grid_constant__ Params p) {
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) asm volatile("prefetch.global.L2 [%0];" ::"l"(pi_g + (size_t)TI * H1 + (2 * ci + grp) * 64));
           }
+        }
+        if (WIDE) {
+          const int64_t row = un.row_lo + (int64_t)t * TI + rj;
+          const int64_t rr = row < un.row_hi ? row : un.row_lo;        // padding rows compute on a valid item's logits and are dropped
+          wl0 = __ldg(reinterpret_cast<const float4*>(p.item_logit + rr * 8));
+          wl1 = __ldg(reinterpret_cast<const float4*>(p.item_logit + rr * 8 + 4));
         }
         if (GATED && have_prev) do_e2(T - 1);
 #pragma unroll 1
@@ -1356,16 +1472,16 @@ __global__ void build_wimg_kernel(const float* __restrict__ w1, int k1, const fl
 
 // gated: item part of the gate logits: Wg[:, D:] . concat(item-side vectors) + bg   (layers.py:207 split)
 __global__ void item_logit_kernel(const float* __restrict__ feats, const float* __restrict__ gate_w,
-                                  const float* __restrict__ gate_b, int M, int64_t n_rows, float* __restrict__ out) {
+                                  const float* __restrict__ gate_b, int M, int Dm, int64_t n_rows, float* __restrict__ out) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
-  const int FD = (M - 1) * D;
+  const int FD = (M - 1) * Dm;
   const float* x = feats + row * FD;
   for (int m = 0; m < 8; ++m) {
     float acc = 0.f;
     if (m < M) {
-      const float* wr = gate_w + (size_t)m * M * D + D;
+      const float* wr = gate_w + (size_t)m * M * Dm + Dm;
       for (int k = lane; k < FD; k += 32) acc += wr[k] * x[k];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -1377,11 +1493,11 @@ __global__ void item_logit_kernel(const float* __restrict__ feats, const float* 
 
 // concat: item partial of layer 1, Pi[row] = W1[:, D:] . concat(item-side vectors) + b1   -> 16 bit.
 // 32 rows per block; W1^T (k-major, [M*D][512]) rows D.. are the item part.
+// (wide gated: the same kernel with FD = D over the n_rows * (M - 1) modality vectors and all of W1^T: Q_m = W1 f_m + b1)
 __global__ void __launch_bounds__(PXR_SIMT_THREADS) item_pi_kernel(const float* __restrict__ feats, const float* __restrict__ w1t,
-                                                                    const float* __restrict__ b1, int M, int Dm, int64_t n_rows,
-                                                                    uint16_t* __restrict__ out, int fmt) {
+                                                                    const float* __restrict__ b1, int FD, int64_t n_rows,
+                                                                    uint16_t* __restrict__ out, int fmt, int qt_nm) {
   extern __shared__ __align__(16) float smem_pi[];
-  const int FD = (M - 1) * Dm;
   float* in = smem_pi;                       // [32][FD]
   float* res = smem_pi + 32 * FD;            // [32][512]
   const int64_t row0 = (int64_t)blockIdx.x * 32;
@@ -1390,11 +1506,19 @@ __global__ void __launch_bounds__(PXR_SIMT_THREADS) item_pi_kernel(const float* 
     in[i] = row < n_rows ? feats[row * FD + i % FD] : 0.f;
   }
   __syncthreads();
-  linear_rows<32>(in, FD, FD, w1t + (size_t)Dm * H1, b1, H1, res, H1, -1);
+  linear_rows<32>(in, FD, FD, w1t, b1, H1, res, H1, -1);
   __syncthreads();
   for (int i = threadIdx.x; i < 32 * H1; i += PXR_SIMT_THREADS) {
     const int64_t row = row0 + i / H1;
-    if (row < n_rows) out[row * H1 + i % H1] = to16(res[i], fmt);
+    if (row >= n_rows) continue;
+    const int n = i % H1;
+    if (qt_nm > 0) {            // wide gated: vector `row` = (item, modality), stored chunk-major (Params::item_q)
+      const int64_t item = row / qt_nm; const int m = (int)(row % qt_nm);
+      const size_t off = ((size_t)(item >> 4) * 8 + (n >> 6)) * q_stage_bytes(qt_nm) + (size_t)(item & 15) * q_item_bytes(qt_nm) + m * 128 + (n & 63) * 2;
+      *reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(out) + off) = to16(res[i], fmt);
+    } else {
+      out[row * H1 + n] = to16(res[i], fmt);
+    }
   }
 }
 
@@ -1605,7 +1729,8 @@ template <int FUS, int FMT, bool TK2, int ACT, int MODE>
 static int launch_fused_tk(pxr_handle* h, const Params& p, int n_pairs, cudaStream_t st) {
   auto kern = score_fused_kernel<FUS, FMT, TK2, ACT, MODE>;
   static_assert(!(MODE == M_PAGED && TK2), "paged passes use one top-K warp");
-  const int slot = ((ACT * 3 + FUS) * 2 + FMT) * 4 + (MODE == M_PLAIN ? (TK2 ? 1 : 0) : 1 + MODE);   // < 120: two words
+  const int slot = ((ACT * 4 + FUS) * 2 + FMT) * 4 + (MODE == M_PLAIN ? (TK2 ? 1 : 0) : 1 + MODE);   // < 160: three words
+  static_assert(sizeof(h->tc_attr_fused) >= 3 * sizeof(uint64_t), "one bit per instantiation");
   if (!(h->tc_attr_fused[slot >> 6] & (1ull << (slot & 63)))) {
     PXR_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Map<FUS>::SMEM));
     h->tc_attr_fused[slot >> 6] |= (1ull << (slot & 63));
@@ -1627,8 +1752,8 @@ static int launch_fused(pxr_handle* h, const Params& p, int n_pairs, cudaStream_
   if (thr < 0) { const char* e = getenv("PXR_TK2_ROWS"); thr = e ? atoi(e) : 8192; }
   if (p.upper) return launch_fused_tk<FUS, FMT, false, ACT, M_PAGED>(h, p, n_pairs, st);
   if (p.sub_rows > 0) {                   // small batches: short sub-ranges per slot, two top-K warps
-    if constexpr (FUS != F_ATTN) return launch_fused_tk<FUS, FMT, true, ACT, M_SPREAD>(h, p, n_pairs, st);
-    else PXR_FAIL(h, PXR_ERR_INVALID, "small-batch mode exists for gated and concat fusion only");
+    if constexpr (FUS == F_GATED || FUS == F_CONCAT) return launch_fused_tk<FUS, FMT, true, ACT, M_SPREAD>(h, p, n_pairs, st);
+    else PXR_FAIL(h, PXR_ERR_INVALID, "small-batch mode exists for gated (embedding_dim 64) and concat fusion only");
   }
   return p.rows_per_split < thr ? launch_fused_tk<FUS, FMT, true, ACT, M_PLAIN>(h, p, n_pairs, st)
                                 : launch_fused_tk<FUS, FMT, false, ACT, M_PLAIN>(h, p, n_pairs, st);
@@ -1640,11 +1765,13 @@ template <int ACT>
 static int launch_fused_act(pxr_handle* h, const Params& p, int fusion, int fmt, int n_pairs, cudaStream_t st) {
   if constexpr (ACT != PXR_ACT_RELU || PXR_TC_TU == 0) {     // TU 0: the bf16 half of the ReLU kernels (fp16: TU 5)
     if (fmt != FMT_BF16) PXR_FAIL(h, PXR_ERR_INVALID, "fp16 operands are built for relu models only");
+    if (fusion == PXR_FUSION_GATED && p.item_q) return launch_fused<F_GATEDW, FMT_BF16, ACT>(h, p, n_pairs, st);   // embedding_dim != 64
     if (fusion == PXR_FUSION_GATED) return launch_fused<F_GATED, FMT_BF16, ACT>(h, p, n_pairs, st);
     if (fusion == PXR_FUSION_ATTENTION) return launch_fused<F_ATTN, FMT_BF16, ACT>(h, p, n_pairs, st);
     return launch_fused<F_CONCAT, FMT_BF16, ACT>(h, p, n_pairs, st);
   }
   else {                                                      // TU 5: ReLU, fp16 operands
+    if (fusion == PXR_FUSION_GATED && p.item_q) return launch_fused<F_GATEDW, FMT_FP16, ACT>(h, p, n_pairs, st);
     if (fusion == PXR_FUSION_GATED) return launch_fused<F_GATED, FMT_FP16, ACT>(h, p, n_pairs, st);
     if (fusion == PXR_FUSION_ATTENTION) return launch_fused<F_ATTN, FMT_FP16, ACT>(h, p, n_pairs, st);
     return launch_fused<F_CONCAT, FMT_FP16, ACT>(h, p, n_pairs, st);
@@ -1687,15 +1814,21 @@ const char* pxr_tc_unsupported_reason(const pxr_handle* h) {
   if (c.activation != PXR_ACT_RELU && c.precision == PXR_PRECISION_FP16) return "fp16 operands with a fusion_activation other than relu (only the relu kernels are built for fp16)";
   if (h->M < 4 || h->M > 6) return "fewer than 4 modalities";
   if (c.fusion == PXR_FUSION_ATTENTION && c.num_heads != tc::NH) return "attention fusion with num_attention_heads != 4";
-  if (c.fusion != PXR_FUSION_CONCAT && c.embedding_dim != tc::D) return "gated / attention fusion with embedding_dim != 64 (layer 1 is a K = 64 MMA)";
-  // concat: layer 1 is applied as per-user / per-item partials, so the fused kernel does not depend on embedding_dim
-  // (item side: 3xTF32 GEMMs of items_tc.cu, which need single-layer projections and 16-byte aligned rows)
-  if (c.fusion == PXR_FUSION_CONCAT && c.embedding_dim != tc::D &&
+  if (c.fusion == PXR_FUSION_ATTENTION && c.embedding_dim != tc::D) return "attention fusion with embedding_dim != 64 (its front end is built for 4 heads of 16)";
+  // concat, and gated at embedding_dim != 64 (F_GATEDW): layer 1 is applied as per-user / per-item partials, so the fused
+  // kernel does not depend on embedding_dim (item side: 3xTF32 GEMMs of items_tc.cu, which need single-layer projections
+  // and 16-byte aligned rows)
+  if (c.fusion == PXR_FUSION_GATED && c.embedding_dim != tc::D && c.hidden[0] != tc::H1)
+    return "gated fusion with embedding_dim != 64 and fusion_hidden_dims[0] != 512 (layer 1 runs as 512-column partials)";
+  if (c.fusion != PXR_FUSION_ATTENTION && c.embedding_dim != tc::D &&
       !(c.embedding_dim % 16 == 0 && c.embedding_dim <= 512 && c.projection_hidden == 0 && c.vision_dim % 4 == 0 &&
         c.language_dim % 4 == 0 && c.num_numerical <= 32))
-    return "concat fusion with embedding_dim != 64 needs embedding_dim % 16 == 0, single-layer projections and feature dims % 4 == 0";
+    return "concat / gated fusion with embedding_dim != 64 needs embedding_dim % 16 == 0, single-layer projections and feature dims % 4 == 0";
   return nullptr;
 }
+
+// gated fusion at embedding_dim != 64: the F_GATEDW front end (gate-weighted layer-1 partials on the concat pipeline)
+bool pxr_tc_gated_wide(const pxr_handle* h) { return h->cfg.fusion == PXR_FUSION_GATED && h->cfg.embedding_dim != tc::D; }
 
 bool pxr_tc_supported(const pxr_handle* h) { return pxr_tc_unsupported_reason(h) == nullptr; }
 
@@ -1713,7 +1846,7 @@ static int tc_fmt(const pxr_handle* h) { return h->cfg.precision == PXR_PRECISIO
 int pxr_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
   if (!h->fast_w) PXR_CUDA(h, cudaMalloc(&h->fast_w, pxr_tc_weight_bytes(h)));
   tc::FastWeights* fw = reinterpret_cast<tc::FastWeights*>(h->fast_w);
-  const bool gated = h->cfg.fusion != PXR_FUSION_CONCAT;    // layer 1 on the tensor pipe
+  const bool gated = h->cfg.fusion != PXR_FUSION_CONCAT && !pxr_tc_gated_wide(h);    // layer 1 on the tensor pipe
   const bool attn = h->cfg.fusion == PXR_FUSION_ATTENTION;
   float* b = fw->bias;
   const int n1 = h->cfg.hidden[0], n2 = h->cfg.hidden[1], n3 = h->cfg.hidden[2];     // <= 512 / 256 / 128: zero-padded to the kernel's shape
@@ -1742,6 +1875,8 @@ int pxr_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
 
 size_t pxr_tc_item_bytes(const pxr_handle* h, int64_t n_rows) {
   const size_t rows = (size_t)((n_rows + 31) / 32 * 32);
+  if (pxr_tc_gated_wide(h))      // gate logits + the M - 1 layer-1 partials per item (16 bit, 512 columns each, chunk-major with padding)
+    return pxr_align_up(rows * 8 * sizeof(float), 256) + pxr_align_up(rows / 16 * 8 * (size_t)tc::q_stage_bytes(h->M - 1), 256);
   if (h->cfg.fusion == PXR_FUSION_GATED) return pxr_align_up(rows * 8 * sizeof(float), 256);
   if (h->cfg.fusion == PXR_FUSION_ATTENTION) return pxr_align_up(rows * tc::ATT_REC_U4 * sizeof(uint4), 256);
   return pxr_align_up(rows * tc::H1 * sizeof(uint16_t), 256);
@@ -1749,12 +1884,37 @@ size_t pxr_tc_item_bytes(const pxr_handle* h, int64_t n_rows) {
 
 int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t st) {
   if (n_rows == 0) return PXR_OK;
-  if (h->cfg.fusion == PXR_FUSION_GATED && h->tc_items_img[3] && h->path == PXR_PATH_TCGEN05) {
+  if (pxr_tc_gated_wide(h)) {
+    // gate logits (as for embedding_dim 64), then the M - 1 layer-1 partials per item: one GEMM over the record viewed as
+    // n_rows * (M - 1) modality vectors of embedding_dim, [.. x D] . W1^T + b1 -> 16 bit
+    const int Dm = h->cfg.embedding_dim;
+    const int64_t rows = (n_rows + 31) / 32 * 32;
+    uint16_t* q = (uint16_t*)((char*)ws + pxr_align_up((size_t)rows * 8 * sizeof(float), 256));
+    const bool on_tc = h->path == PXR_PATH_TCGEN05 && h->tc_items_img[3] && h->tc_items_img[2];
+    // rows of the last tile that do not exist are staged like the others (their scores are dropped): keep them finite
+    PXR_CUDA(h, cudaMemsetAsync(q, 0, (size_t)rows / 16 * 8 * tc::q_stage_bytes(h->M - 1), st));
+    if (on_tc) {
+      int rc = pxr_launch_item_logit_tc(h, n_rows, (float*)ws, st);
+      if (rc) return rc;
+      return pxr_launch_item_q_tc(h, n_rows, q, tc_fmt(h), st);
+    }
+    const int wpb = 8;
+    tc::item_logit_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(h->item_feats, h->gate.w, h->gate.b, h->M, Dm,
+                                                                                     n_rows, (float*)ws);
+    h->launches++;
+    const size_t smem = (size_t)32 * (Dm + tc::H1) * sizeof(float);
+    if (!(h->tc_attr_set & (1ull << 63))) {
+      PXR_CUDA(h, cudaFuncSetAttribute(tc::item_pi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      h->tc_attr_set |= (1ull << 63);
+    }
+    const int64_t nv = n_rows * (h->M - 1);
+    tc::item_pi_kernel<<<(unsigned)((nv + 31) / 32), PXR_SIMT_THREADS, smem, st>>>(h->item_feats, h->mlp[0].wt, h->mlp[0].b, Dm, nv, q, tc_fmt(h), h->M - 1);
+  } else if (h->cfg.fusion == PXR_FUSION_GATED && h->tc_items_img[3] && h->path == PXR_PATH_TCGEN05) {
     return pxr_launch_item_logit_tc(h, n_rows, (float*)ws, st);                  // 3xTF32 GEMM on the tensor pipe (N = 6 padded to 16)
   } else if (h->cfg.fusion == PXR_FUSION_GATED) {
     const int wpb = 8;
     tc::item_logit_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(h->item_feats, h->gate.w, h->gate.b, h->M,
-                                                                                     n_rows, (float*)ws);
+                                                                                     h->cfg.embedding_dim, n_rows, (float*)ws);
   } else if (h->cfg.fusion == PXR_FUSION_ATTENTION) {
     tc::item_attn_kernel<<<(unsigned)n_rows, 64, 0, st>>>(h->item_feats, h->attn_in.wt, h->attn_in.b,
                                                           reinterpret_cast<tc::FastWeights*>(h->fast_w)->wc, h->attn_out.b, h->M,
@@ -1769,8 +1929,8 @@ int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t s
       PXR_CUDA(h, cudaFuncSetAttribute(tc::item_pi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       h->tc_attr_set |= (1ull << 63);
     }
-    tc::item_pi_kernel<<<(unsigned)((n_rows + 31) / 32), PXR_SIMT_THREADS, smem, st>>>(h->item_feats, h->mlp[0].wt, h->mlp[0].b,
-                                                                                       h->M, h->cfg.embedding_dim, n_rows, (uint16_t*)ws, tc_fmt(h));
+    tc::item_pi_kernel<<<(unsigned)((n_rows + 31) / 32), PXR_SIMT_THREADS, smem, st>>>(h->item_feats, h->mlp[0].wt + (size_t)h->cfg.embedding_dim * tc::H1,
+                                                                                       h->mlp[0].b, FD, n_rows, (uint16_t*)ws, tc_fmt(h), 0);
   }
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
@@ -1818,7 +1978,7 @@ static SpreadPlan tc_spread_plan(const pxr_handle* h, int64_t n_users, int32_t k
   SpreadPlan sp;
   memset(&sp, 0, sizeof(sp));
   // h->small_batch (pxr_set_small_batch): 0 = never, 1 = whenever the shape allows it (tests), -1 = when the cost model below says so
-  if (h->small_batch == 0 || h->cfg.fusion == PXR_FUSION_ATTENTION || n_users > 8 || n_users <= 0 || tc_pages(k) > 1 || h->n_rows < 512) return sp;
+  if (h->small_batch == 0 || h->cfg.fusion == PXR_FUSION_ATTENTION || pxr_tc_gated_wide(h) || n_users > 8 || n_users <= 0 || tc_pages(k) > 1 || h->n_rows < 512) return sp;
   const int max_pairs = h->n_sm / 2;
   const int64_t slots = (int64_t)max_pairs * 16;
   int64_t sub = (h->n_rows * n_users + slots - 1) / slots;
@@ -1890,6 +2050,8 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
   p.item_feats = h->item_feats;
   p.item_logit = gated ? (const float*)h->item_fast : nullptr;
   p.item_pi = (gated || attn) ? nullptr : (const uint16_t*)h->item_fast;
+  if (pxr_tc_gated_wide(h))      // [gate logits][item partials], see pxr_tc_item_bytes
+    p.item_q = (const uint16_t*)((const char*)h->item_fast + pxr_align_up((size_t)((h->n_rows + 31) / 32 * 32) * 8 * sizeof(float), 256));
   if (attn) {
     p.attn_rec = (const uint4*)h->item_fast;
     p.wo_frag = fw->wo_frag;

@@ -565,8 +565,8 @@ def _lowp_scores(sd, spec, feats, users, rnd=None):
     out = np.empty((len(users), NI))
     for r, u in enumerate(users):
         ii = np.arange(NI)
-        out[r] = orc.forward_pairs_lowp(sd, cs.spec_cfg(spec), np.full(NI, u), ii, feats["tag_idx"], feats["vis"],
-                                        feats["txt"], feats["num"], rnd=rnd)
+        out[r] = orc.forward_pairs_lowp(sd, cs.spec_cfg(spec), np.full(NI, u), ii, feats["tag_idx"], feats.get("vis"),
+                                        feats.get("txt"), feats.get("num"), rnd=rnd)
     return out
 
 
@@ -709,6 +709,72 @@ def test_tcgen05_concat_any_embedding_dim(D):
     z = eng.score_pairs(model.user_embedding.weight.detach(), torch.from_numpy(uu).cuda(), torch.from_numpy(ii).cuda(), want_logit=True)[1]
     zr = orc.forward_pairs(sd, cs.spec_cfg(spec), uu, ii, feats["tag_idx"][ii], feats["vis"][ii], feats["txt"][ii], feats["num"][ii], return_logit=True)
     assert np.max(np.abs(z.cpu().numpy() - zr)) <= 5e-4 * max(1.0, D / 128), float(np.max(np.abs(z.cpu().numpy() - zr)))   # fp32 sums over 6 D inputs
+
+
+@pytest.mark.parametrize("D,n_users,n_items,k,kw", [
+    (128, 40, 700, 50, {}), (16, 40, 700, 50, {}), (256, 40, 700, 50, {}), (512, 24, 500, 50, {}),
+    (128, 700, 2600, 50, {}),                                      # several units per CTA pair, item splits merged by K4
+    (128, 40, 900, 100, {}),                                       # top_k > 64: pages
+    (128, 40, 700, 50, dict(fusion_activation="silu")),
+    (192, 40, 700, 50, dict(num_numerical_features=0)),            # five modalities
+    (128, 40, 700, 50, dict(vision_dim=0))])                       # no vision modality
+def test_tcgen05_gated_any_embedding_dim(D, n_users, n_items, k, kw):
+    """Gated fusion on the fused path at embedding dims other than 64 (BASELINE.json configs[4] sweeps 64-512; the
+    reference recommends 64 / 128 / 256, configs/simple_config_example.yaml:6).  Layer 1 is linear in the fused vector
+    and the gate weights sum to 1 (layers.py:207-223), so it is the gate-weighted sum of one per-user and M - 1 per-item
+    partials of 512 columns (F_GATEDW): kernel == the emulated oracle with those roundings, exact mode == the fp32
+    oracle, fp32 records stay fp32-accurate."""
+    spec = syn.ModelSpec(n_users=n_users, n_items=n_items, fusion_type="gated", embedding_dim=D, **kw)
+    sd = syn.make_state_dict(spec, seed=syn.SEED + 31)
+    feats = syn.make_item_features(spec, seed=syn.SEED + 31)
+    syn.condition_like_trained(sd, spec, feats)
+    indptr, idx, _ = syn.make_histories(n_users, n_items, seed=syn.SEED + 31, lo=3, hi=40)
+    model, eng = _engine_for(spec, sd, feats, "auto")
+    assert eng.active_path == "tcgen05", eng.path_reason
+    users = np.arange(n_users)
+    args = (model.user_embedding.weight.detach(), torch.from_numpy(users).cuda(), k, torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda())
+    s, i = _structural_checks(*eng.score_topk(*args), k, n_items, indptr, idx)
+    sample = users if n_users <= 64 else np.array([0, 1, 7, 8, 15, 16, 17, 333, 334, 591, 592, 687, 688, 699])
+    emu = _lowp_scores(sd, spec, feats, sample)
+    errs = np.concatenate([np.abs(s[u].astype(np.float64) - emu[r][i[u]]) for r, u in enumerate(sample)])
+    assert np.quantile(errs, 0.9) <= TC_EMU_TOL["bf16"] / 8, float(np.quantile(errs, 0.9))
+    same = sum(_check_topk(s[u].astype(np.float64), i[u], emu[r], k, idx[indptr[u]:indptr[u + 1]], _emu_tol("gated", "bf16"), 0.0)
+               for r, u in enumerate(sample))
+    assert same >= 0.9 * k * len(sample)      # the rest are swaps inside the flip band (checked position by position above)
+    eng.set_rescore(True)
+    xs, xi = _structural_checks(*eng.score_topk(*args), k, n_items, indptr, idx)
+    ref = orc.score_block(sd, cs.spec_cfg(spec), sample, 0, n_items, feats)
+    for r, u in enumerate(sample):
+        _check_topk(xs[u].astype(np.float64), xi[u], ref[r], k, idx[indptr[u]:indptr[u + 1]], SIMT_TOL, 0.0)
+    rng = np.random.default_rng(D)
+    uu, ii = rng.integers(0, n_users, 500), rng.integers(0, n_items, 500)
+    z = eng.score_pairs(model.user_embedding.weight.detach(), torch.from_numpy(uu).cuda(), torch.from_numpy(ii).cuda(), want_logit=True)[1]
+    g = lambda name: None if feats.get(name) is None else feats[name][ii]
+    zr = orc.forward_pairs(sd, cs.spec_cfg(spec), uu, ii, feats["tag_idx"][ii], g("vis"), g("txt"), g("num"), return_logit=True)
+    assert np.max(np.abs(z.cpu().numpy() - zr)) <= 5e-4 * max(1.0, D / 128), float(np.max(np.abs(z.cpu().numpy() - zr)))
+
+
+def test_tcgen05_gated_wide_item_shards():
+    """F_GATEDW (gated fusion, embedding_dim 128) on three item shards + K4 merge == the unsharded lists bit for bit."""
+    from pixelrec_multimodal_b200.engine import merge_topk
+    from pixelrec_multimodal_b200.sharding import shard_range
+    n_users, n_items, k, D = 100, 1203, 50, 128
+    spec = syn.ModelSpec(n_users=n_users, n_items=n_items, fusion_type="gated", embedding_dim=D)
+    sd = syn.make_state_dict(spec, seed=syn.SEED + 33)
+    feats = syn.make_item_features(spec, seed=syn.SEED + 33)
+    syn.condition_like_trained(sd, spec, feats)
+    indptr, idx, _ = syn.make_histories(n_users, n_items, seed=syn.SEED + 33, lo=3, hi=40)
+    model, eng = _engine_for(spec, sd, feats, "tcgen05")
+    users = torch.arange(n_users).cuda()
+    d_indptr, d_idx = torch.from_numpy(indptr).cuda(), torch.from_numpy(idx).cuda()
+    fs, fi = eng.score_topk(model.user_embedding.weight.detach(), users, k, d_indptr, d_idx)
+    parts = []
+    for r in range(3):
+        lo, hi = shard_range(n_items, 3, r)
+        m2, e2 = _engine_for(spec, sd, feats, "tcgen05", item_lo=lo, item_hi=hi)
+        parts.append(e2.score_topk(m2.user_embedding.weight.detach(), users, k, d_indptr, d_idx))
+    ms, mi = merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    assert torch.equal(mi, fi) and torch.equal(ms, fs)
 
 
 @pytest.mark.parametrize("fusion", ["gated", "concatenate", "attention"])
