@@ -483,10 +483,15 @@ def forward_pairs_lowp(sd, cfg, user_idx, item_idx, tag_idx, vis=None, txt=None,
         # embedding_dim != 64 (F_GATEDW): layer 1 is linear in the fused vector and the gate weights sum to 1, so it is the
         # gate-weighted sum of one per-user partial (fp32) and M - 1 per-item partials W1 f_m + b1 (stored in 16 bit);
         # the sum goes through the activation and is rounded once as the layer-2 operand
+        # The item partials are stored in fp16 whatever the operand format, and their gate-weighted sum runs on packed
+        # fp16 FMAs (one rounding per multiply / fused multiply-add, modality order); the user term stays fp32.
         g = gated_fusion(sd, feats, dt, return_gates=True)
-        z1 = g[:, :1] * (feats[0] @ ws[0].T + bs[0])
+        acc = None
         for m in range(1, len(feats)):
-            z1 = z1 + g[:, m:m + 1] * rnd(feats[m] @ ws[0].T + bs[0])
+            gm = round_fp16(g[:, m:m + 1])
+            qm = round_fp16(np.clip(feats[m] @ ws[0].T + bs[0], -65504.0, 65504.0))
+            acc = round_fp16(gm * qm) if acc is None else round_fp16(gm * qm + acc)
+        z1 = g[:, :1] * (feats[0] @ ws[0].T + bs[0]) + acc
         h = rnd(activation(z1, act))
         start = 1
     elif ft == "gated":

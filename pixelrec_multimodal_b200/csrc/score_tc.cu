@@ -290,6 +290,49 @@ __device__ __forceinline__ void concat_h1_chunk(const uint8_t* pi_row, const uin
 // apart modulo 128, so the 16-byte reads of a quarter warp hit distinct banks; the two user rows of a warp share every read).
 __host__ __device__ constexpr uint32_t q_item_bytes(int nm) { return (uint32_t)nm * 128u + 16u; }
 __host__ __device__ constexpr uint32_t q_stage_bytes(int nm) { return 16u * q_item_bytes(nm); }       // one chunk of one 16-item tile
+// PXR_GW_HALF2 (default): the item partials are stored in fp16 (11-bit significand, saturating convert) whatever the MMA
+// operand format, and their gate-weighted sum runs on packed fp16 FMAs -- 5 HFMA2 per two columns instead of 10 unpack + 10
+// FFMA: the producers are issue-bound (1.90 -> see DESIGN K3w).  The fp16 sum carries <= 5 roundings of 2^-11 relative, a
+// fifth of the 16-bit rounding of the activation that follows; the user term g_0 Pu stays fp32.
+#ifndef PXR_GW_HALF2
+#define PXR_GW_HALF2 1
+#endif
+constexpr bool GW_HALF2 = PXR_GW_HALF2 != 0;
+template <int ACT, int FMT>
+__device__ __forceinline__ void gatedw_h1_chunk_h2(const uint8_t* qi, int nm, float g0, const __half2 (&gh)[5], const uint8_t* pu_row, uint32_t t_dst) {
+  uint32_t o[32];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {                      // 16 columns per step
+    uint4 pv[5][2];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      if (m < nm) {
+        const uint4* src = reinterpret_cast<const uint4*>(qi + m * 128 + 32 * s);
+        pv[m][0] = src[0]; pv[m][1] = src[1];
+      } else {
+        pv[m][0] = pv[m][1] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const float4 pa = *reinterpret_cast<const float4*>(pu_row + 64 * s + 32 * hh);
+      const float4 pb = *reinterpret_cast<const float4*>(pu_row + 64 * s + 32 * hh + 16);
+      const float pu[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+      uint32_t w[5][4];
+#pragma unroll
+      for (int m = 0; m < 5; ++m) { w[m][0] = pv[m][hh].x; w[m][1] = pv[m][hh].y; w[m][2] = pv[m][hh].z; w[m][3] = pv[m][hh].w; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __half2 a = __hmul2(gh[0], *reinterpret_cast<const __half2*>(&w[0][j]));
+#pragma unroll
+        for (int m = 1; m < 5; ++m) a = __hfma2(gh[m], *reinterpret_cast<const __half2*>(&w[m][j]), a);
+        const float2 f = __half22float2(a);
+        o[8 * s + 4 * hh + j] = act_pack<ACT, FMT>(fmaf(g0, pu[2 * j], f.x), fmaf(g0, pu[2 * j + 1], f.y));
+      }
+    }
+  }
+  ptx::tmem_st32(t_dst, o);
+}
 template <int ACT, int FMT>
 __device__ __forceinline__ void gatedw_h1_chunk(const uint8_t* qi, int nm, const float (&g)[6], const uint8_t* pu_row, uint32_t t_dst) {
   uint32_t o[32];
@@ -1298,6 +1341,9 @@ score_fused_kernel(const __grid_constant__ Params p) {
     // constants are known to be in place), its gate weights
     float4 wl0 = make_float4(0.f, 0.f, 0.f, 0.f), wl1 = wl0;
     float wg[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    __half2 wgh[5];                                  // PXR_GW_HALF2: the item-side gate weights as packed fp16 pairs
+#pragma unroll
+    for (int m = 0; m < 5; ++m) wgh[m] = __float2half2_rn(0.f);
     auto prev_e3 = [&]() {
       if (ATT) {
         if (prev_t == 0 && (T - 1) > 0) { ptx::mbar_wait(BAR(BAR_UNIT_RESET), reset_ph); reset_ph ^= 1; }
@@ -1334,12 +1380,20 @@ score_fused_kernel(const __grid_constant__ Params p) {
           const float inv = 1.f / sum;
 #pragma unroll
           for (int m = 0; m < 6; ++m) wg[m] *= inv;
+          if (GW_HALF2) {
+#pragma unroll
+            for (int m = 0; m < 5; ++m) wgh[m] = __float2half2_rn(wg[m + 1]);
+          }
         }
         const uint32_t n = (ci & 1) ? h1use1++ : h1use0++;
         if (n > 0) { ptx::mbar_wait(BAR(BAR_H1_EMPTY0 + b), (n - 1) & 1); ptx::tc_fence_after(); }   // layer 2 consumed the buffer
         if (WIDE) {
           const uint32_t G = (uint32_t)T * 8u + c, slot = G % MP::Q_STAGES;
           ptx::mbar_wait(BAR(BAR_Q_FULL0 + slot), (G / MP::Q_STAGES) & 1);        // this chunk of the tile's item partials landed
+          if (GW_HALF2)
+            gatedw_h1_chunk_h2<ACT, FMT>(sm + MP::OFF_PI + slot * MP::Q_STAGE_MAX + rj * q_item_bytes(p.M - 1), p.M - 1, wg[0], wgh,
+                                         sm + MP::OFF_PU + ru * MP::PU_STRIDE + c * 256, tl + MP::h1buf(b));
+          else
           gatedw_h1_chunk<ACT, FMT>(sm + MP::OFF_PI + slot * MP::Q_STAGE_MAX + rj * q_item_bytes(p.M - 1), p.M - 1, wg,
                                     sm + MP::OFF_PU + ru * MP::PU_STRIDE + c * 256, tl + MP::h1buf(b));
         } else
@@ -1896,7 +1950,7 @@ int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t s
     if (on_tc) {
       int rc = pxr_launch_item_logit_tc(h, n_rows, (float*)ws, st);
       if (rc) return rc;
-      return pxr_launch_item_q_tc(h, n_rows, q, tc_fmt(h), st);
+      return pxr_launch_item_q_tc(h, n_rows, q, tc::GW_HALF2 ? tc::FMT_FP16 : tc_fmt(h), st);
     }
     const int wpb = 8;
     tc::item_logit_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(h->item_feats, h->gate.w, h->gate.b, h->M, Dm,
@@ -1908,7 +1962,7 @@ int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t s
       h->tc_attr_set |= (1ull << 63);
     }
     const int64_t nv = n_rows * (h->M - 1);
-    tc::item_pi_kernel<<<(unsigned)((nv + 31) / 32), PXR_SIMT_THREADS, smem, st>>>(h->item_feats, h->mlp[0].wt, h->mlp[0].b, Dm, nv, q, tc_fmt(h), h->M - 1);
+    tc::item_pi_kernel<<<(unsigned)((nv + 31) / 32), PXR_SIMT_THREADS, smem, st>>>(h->item_feats, h->mlp[0].wt, h->mlp[0].b, Dm, nv, q, tc::GW_HALF2 ? tc::FMT_FP16 : tc_fmt(h), h->M - 1);
   } else if (h->cfg.fusion == PXR_FUSION_GATED && h->tc_items_img[3] && h->path == PXR_PATH_TCGEN05) {
     return pxr_launch_item_logit_tc(h, n_rows, (float*)ws, st);                  // 3xTF32 GEMM on the tensor pipe (N = 6 padded to 16)
   } else if (h->cfg.fusion == PXR_FUSION_GATED) {
