@@ -13,7 +13,7 @@ cached features, Pixel200K-shaped synthetic (200 000 users x 96 282 items), top-
 Per-GPU work is fixed as N grows (users per step = user_block * N, items per
 rank = NI / N): "scaling": "weak".  The same JSON object carries an `also` array
 with short runs of the other BASELINE configs (configs[2] attention at every N,
-the concat shape at N=1, configs[3] Pixel8M-shaped at N=8, and at N>1 the
+the concat shape and gated fusion at embedding_dim 128 at N=1, configs[3] Pixel8M-shaped at N=8, and at N>1 the
 user-axis-sharded variant of the headline for comparison), each with its own
 roofline and clocks.
 
@@ -44,10 +44,11 @@ CONFIGS = {
     "A": (1_000, 2_000, "concatenate", "configs[0] simple_config_example concat 1K x 2K"),
     "B": (200_000, 96_282, "gated", "configs[1] gated, CLIP-512 + SBERT-384, Pixel200K-shaped 200K x 96K, top-50"),
     "Bc": (200_000, 96_282, "concatenate", "concat fusion at the configs[1] shape (200K x 96K), top-50 (not a BASELINE config: kernel comparison)"),
+    "B128": (200_000, 96_282, "gated", "gated fusion at embedding_dim 128 at the configs[1] shape (200K x 96K), top-50 (a configs[4] sweep point: the wide gated front end)"),
     "C": (1_001_822, 100_541, "attention", "configs[2] attention + numerical, Pixel1M-shaped 1M x 100K"),
     "D": (8_886_078, 407_082, "gated", "configs[3] Pixel8M-shaped 8.9M x 407K item-sharded"),
 }
-CONFIG_DIMS = {}          # config name -> embedding_dim when it is not 64 (scripts/sweep.py registers its sweep points here)
+CONFIG_DIMS = {"B128": 128}   # config name -> embedding_dim when it is not 64 (scripts/sweep.py registers its sweep points here)
 TOP_K = 50
 METRIC = "scored user-item pairs/sec (full catalogue, top-50 per user)"
 UNIT = "pairs/s"
@@ -498,7 +499,8 @@ def run_config(args, cfg_name: str, steps: int, warmup: int, world: int, rank: i
     peak_tf = pk["tf_sustained"]
     roofline = {"bound": "tensor", "kernel": f"pair-scoring ({eng.active_path})", "achieved": achieved_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if achieved_tf else None,
-                "traffic": ncu_traffic(fusion, int(rank_users / max(1, steps)), hi - lo),
+                "traffic": ncu_traffic(fusion if (spec.embedding_dim == 64 or fusion == "concatenate") else f"{fusion}_d{spec.embedding_dim}",
+                                       int(rank_users / max(1, steps)), hi - lo),    # captures are per kernel: gated at D != 64 is another front end
                 "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside a long step); burst {pk['tf_burst']}",
                 "flop_per_pair": wp, "pairs_per_launch": pairs_per_launch, "kernel_ms_avg": k_avg_ms, "kernel_launches": k_n,
                 "kernel_share_of_step": (k_ms / ms) if ms else None}
@@ -556,7 +558,7 @@ def b200_arm(args):
                       with_cpu=(world == 1 and args.cpu_seconds > 0))
     also = []
     if args.also and args.config == "B":
-        extra = [("C", "items")] + ([("Bc", "items")] if world == 1 else [("B", "users")]) + ([("D", "items")] if world == 8 else [])
+        extra = [("C", "items")] + ([("Bc", "items"), ("B128", "items")] if world == 1 else [("B", "users")]) + ([("D", "items")] if world == 8 else [])
         for cfg_name, shard in extra:
             try:
                 r = run_config(args, cfg_name, args.also_steps, 3, world, rank, dev, shard=shard, with_e2e=False, with_checks=(shard == "items"))
