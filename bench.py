@@ -19,10 +19,13 @@ roofline and clocks.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-`--impl reference` times the reference's CPU path (the PyTorch-eager oracle port:
-the reference is pure Python/PyTorch and cannot travel to the GPU box) on the
-host cores for the same metric and config.  The oracle is only ever the CPU
-arm here; the product path never touches it.
+`--impl reference` times the reference's CPU path on the host cores for the same
+metric and config: the UNMODIFIED reference module, pip-installed from
+/root/reference into baseline/_ref by `__graft_entry__.build()` (git-ignored, travels
+to the GPU box; oracle/reference_arm.py) -- `kind: "reference"`; only when that
+install is absent does it fall back to the PyTorch-eager oracle port (`kind: "port"`).
+The oracle / reference are only ever the CPU arm here; the product path never
+touches them.
 """
 from __future__ import annotations
 
@@ -161,29 +164,44 @@ def cpu_workload(cfg_name: str, seed: int):
     return _CPU_WL[(cfg_name, seed)]
 
 
+def reference_model(wl):
+    """The UNMODIFIED reference module (oracle/reference_arm.py: the pip install under baseline/_ref) with this workload's
+    weights, or None when the install is absent (then the oracle port is timed and `kind` says "port")."""
+    if "ref_model" not in wl:
+        from oracle import reference_arm as ra
+        wl["ref_model"] = ra.build_model(wl["spec"], wl["sd"]) if ra.available() else None
+    return wl["ref_model"]
+
+
 def cpu_arm(cfg_name: str, seconds: float, seed: int, first_user: int = 0):
-    """Times the reference's CPU path (oracle/pxr_oracle_torch.py: the reference
-    forward restated op-for-op in PyTorch eager fp32, pinned to the reference's
-    outputs in tests/) on a bounded sample of the SAME workload: `n` users x the
-    full catalogue as flattened pairs (multimodal.py:528-610), seen items
-    dropped, stable top-50 (recommender.py:88-106).  Returns pairs/s."""
+    """Times the reference's CPU path on a bounded sample of the SAME workload: `n` users x the full catalogue as
+    flattened pairs through `MultimodalRecommender.forward` (multimodal.py:528-610), seen items dropped, stable top-50
+    (recommender.py:88-106).  kind "reference": the unmodified reference module installed under baseline/_ref
+    (oracle/reference_arm.py); kind "port" (only when that install is absent): oracle/pxr_oracle_torch.py, the same forward
+    restated op for op in PyTorch eager fp32 and pinned to the reference's outputs in tests/.  Returns pairs/s."""
     import torch
     from oracle import pxr_oracle_torch as ot
+    from oracle import reference_arm as ra
     wl = cpu_workload(cfg_name, seed)
     NU, NI, fusion = wl["NU"], wl["NI"], wl["fusion"]
     threads = torch.get_num_threads()
+    ref = reference_model(wl)
 
     def run(users):
-        ot.recommend_block(wl["sd"], wl["cfg"], torch.as_tensor(users), wl["feats"], TOP_K, wl["indptr"], wl["idx"])
+        if ref is not None:
+            ra.recommend_block(ref, torch.as_tensor(users), wl["feats"], TOP_K, wl["indptr"], wl["idx"])
+        else:
+            ot.recommend_block(wl["sd"], wl["cfg"], torch.as_tensor(users), wl["feats"], TOP_K, wl["indptr"], wl["idx"])
 
     t0 = time.perf_counter(); run(np.arange(first_user, first_user + 2) % NU); t1 = (time.perf_counter() - t0) / 2
     n = int(max(2, min(NU, seconds / max(t1, 1e-3))))
     users = np.arange(first_user + 2, first_user + 2 + n) % NU
     t0 = time.perf_counter(); run(users); dt = time.perf_counter() - t0
-    return dict(value=n * NI / dt, unit=UNIT, cores=threads, kind="port", seconds=dt, users=n,
-                sample=f"{n} users x {NI} items of config {cfg_name} ({fusion}): PyTorch-eager fp32 restatement of the "
-                       f"reference forward on flattened pairs ({threads} intra-op threads of {os.cpu_count()} cores) "
-                       f"+ seen filter + stable top-{TOP_K}")
+    what = ("the unmodified reference MultimodalRecommender.forward (pip-installed under baseline/_ref, cached features through "
+            "identity backbones)" if ref is not None else "PyTorch-eager fp32 restatement of the reference forward")
+    return dict(value=n * NI / dt, unit=UNIT, cores=threads, kind="reference" if ref is not None else "port", seconds=dt, users=n,
+                sample=f"{n} users x {NI} items of config {cfg_name} ({fusion}): {what} on flattened pairs "
+                       f"({threads} intra-op threads of {os.cpu_count()} cores) + seen filter + stable top-{TOP_K}")
 
 
 def cpu_literal(cfg_name: str, seconds: float, seed: int, max_items: int = 20_000):
@@ -208,19 +226,28 @@ def cpu_literal(cfg_name: str, seconds: float, seed: int, max_items: int = 20_00
     ds = _DS()
     ds.user_encoder, ds.item_encoder = LabelEncoder().fit(uids), LabelEncoder().fit(iids)
     ds.feature_cache = {}
+    ones = torch.ones(1, dtype=torch.long)
     for i, iid in enumerate(iids):
         d = {"tag_idx": feats["tag_idx"][i]}
         if "vis" in feats:
             d["image"] = feats["vis"][i]
         if "txt" in feats:
             d["text_input_ids"] = feats["txt"][i]
+            d["text_attention_mask"] = ones
         if "num" in feats:
             d["numerical_features"] = feats["num"][i]
         ds.feature_cache[iid] = d
     ds.get_user_history = lambda uid: {iids[int(j)] for j in idx[indptr[int(uid[1:])]:indptr[int(uid[1:]) + 1]] if j < NI}
     sd = dict(wl["sd"])
     sd["item_embedding.weight"] = sd["item_embedding.weight"][:NI]
-    lit = ot.LiteralRecommender(sd, wl["cfg"], ds)
+    ref = reference_model(wl)
+    if ref is not None:          # the installed reference Recommender on the reference model cut to the same catalogue
+        from oracle import reference_arm as ra
+        import dataclasses
+        sub = ra.build_model(dataclasses.replace(wl["spec"], n_items=NI), sd)
+        lit = ra.literal_recommender(sub, ds)
+    else:
+        lit = ot.LiteralRecommender(sd, wl["cfg"], ds)
     t0 = time.perf_counter(); lit.get_recommendations(uids[0], top_k=TOP_K, filter_seen=True); t1 = time.perf_counter() - t0
     n = int(max(1, min(64, seconds / max(t1, 1e-3))))
     t0 = time.perf_counter()
@@ -228,9 +255,9 @@ def cpu_literal(cfg_name: str, seconds: float, seed: int, max_items: int = 20_00
         r = lit.get_recommendations(uids[u], top_k=TOP_K, filter_seen=True)
         assert len(r) == TOP_K
     dt = time.perf_counter() - t0
-    return dict(value=n * NI / dt, users_per_sec=n / dt, users=n, items=NI, seconds=dt,
-                sample=f"{n} get_recommendations calls (top-{TOP_K}, filter_seen) over the first {NI} items of config {cfg_name}, "
-                       f"{n_enc_users} users in the encoder")
+    return dict(value=n * NI / dt, users_per_sec=n / dt, users=n, items=NI, seconds=dt, kind="reference" if ref is not None else "port",
+                sample=f"{n} {'reference Recommender' if ref is not None else 'LiteralRecommender (port)'}.get_recommendations calls "
+                       f"(top-{TOP_K}, filter_seen) over the first {NI} items of config {cfg_name}, {n_enc_users} users in the encoder")
 
 
 def reference_arm(args):
@@ -247,7 +274,7 @@ def reference_arm(args):
     tot_s = sum(r["seconds"] for r in vals)
     v = tot_pairs / tot_s
     NI = CONFIGS[args.config][1]
-    base = {"value": v, "unit": UNIT, "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"]}
+    base = {"value": v, "unit": UNIT, "cores": vals[-1]["cores"], "kind": vals[-1]["kind"], "sample": vals[-1]["sample"]}
     if args.literal_seconds > 0:
         lit = cpu_literal(args.config, args.literal_seconds, args.seed)
         base.update(literal_value=lit["value"], literal_users_per_sec=lit["users_per_sec"], literal_sample=lit["sample"])
