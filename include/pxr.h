@@ -213,7 +213,10 @@ int pxr_score_pairs(pxr_handle* h, const float* user_embedding, const int64_t* u
 
 /* K4.  Merge S per-shard top-K lists per user (the step after the NCCL
  * all-gather of SURVEY.md §8(e)); ties -> lower global item index.
- *   scores_in / idx_in : (S, n_users, K) ;  out_* : (n_users, K) */
+ *   scores_in / idx_in : (S, n_users, K) ;  out_* : (n_users, K)
+ * Each input list must be sorted the way the scoring entry points write it: score descending, ties by ascending index, -1 /
+ * -inf padding at the tail.  Scores are ordered by their IEEE bit pattern, so -0.0 sorts below +0.0 (Python's float compare
+ * calls them equal); the library's own kernels emit +0.0 for missing-feature items and NaN, so this only matters for caller-made lists. */
 int pxr_merge_topk(const float* scores_in, const int32_t* idx_in, int32_t n_shards, int64_t n_users,
                    int32_t k, float* out_scores, int32_t* out_idx, pxr_stream stream);
 

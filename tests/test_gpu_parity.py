@@ -279,7 +279,8 @@ def test_merge_topk_many_users_few_lists(S, n, k, skew):
     if skew:
         hot = rng.integers(0, S, n)
         sc[hot, np.arange(n)] += 2.5                                             # user u's winners mostly come from list hot[u]
-    sc = -np.sort(-sc, axis=2)
+    sc = -np.sort(-sc, axis=2) + np.float32(0.0)      # + 0.0: no negative zeros (the negation makes them; the kernels order scores by
+    #                                                   their IEEE bit pattern, -0.0 < +0.0, and never emit -0.0 themselves: include/pxr.h)
     ix = np.stack([np.stack([np.sort(rng.choice(5000, k, replace=False)) + 5000 * s for _ in range(n)]) for s in range(S)]).astype(np.int32)
     for u in range(0, n, 3):                                                     # ragged tails and empty lists
         s_ = int(rng.integers(0, S))
