@@ -384,11 +384,11 @@ int pxr_items_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
   for (int m = 0; m < 2; ++m) if (h->has_mod[m]) total += pxr_align_up(itc::img_bytes(D, kdim[m]), 1024);
   const bool concat = c.fusion == PXR_FUSION_CONCAT;
   const int FD = (h->M - 1) * D;
-  if (concat) total += pxr_align_up(itc::img_bytes(c.hidden[0], FD), 1024);
+  if (concat) total += pxr_align_up(itc::img_bytes(PXR_TC_H1, FD), 1024);          // layer-1 partials: 512 columns, rows past hidden[0] zero
   const bool gated = c.fusion == PXR_FUSION_GATED;
   const bool wide = pxr_tc_gated_wide(h);     // gated at embedding_dim != 64: per-modality layer-1 partials, W1 (512 x D) as one image
   if (gated) total += pxr_align_up(itc::img_bytes(16, FD), 1024) + 1024;      // gate logits: 16 padded outputs + padded bias
-  if (wide) total += pxr_align_up(itc::img_bytes(c.hidden[0], D), 1024);
+  if (wide) total += pxr_align_up(itc::img_bytes(PXR_TC_H1, D), 1024);
   if (h->tc_items_w) { cudaFree(h->tc_items_w); h->tc_items_w = nullptr; }
   PXR_CUDA(h, cudaMalloc(&h->tc_items_w, total + 1024));
   uint8_t* cur = reinterpret_cast<uint8_t*>(h->tc_items_w);
@@ -403,18 +403,18 @@ int pxr_items_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
   h->tc_items_img[2] = nullptr;
   if (concat) {
     h->tc_items_img[2] = cur;
-    itc::split_weights_kernel<<<512, 256, 0, st>>>(h->mlp[0].w, h->mlp[0].k, D, c.hidden[0], FD, 256, cur, c.hidden[0]);
+    itc::split_weights_kernel<<<512, 256, 0, st>>>(h->mlp[0].w, h->mlp[0].k, D, PXR_TC_H1, FD, 256, cur, c.hidden[0]);
     h->launches++;
   }
   if (wide) {
     h->tc_items_img[2] = cur;
-    itc::split_weights_kernel<<<512, 256, 0, st>>>(h->mlp[0].w, h->mlp[0].k, 0, c.hidden[0], D, 256, cur, c.hidden[0]);
+    itc::split_weights_kernel<<<512, 256, 0, st>>>(h->mlp[0].w, h->mlp[0].k, 0, PXR_TC_H1, D, 256, cur, c.hidden[0]);
     h->launches++;
-    cur += pxr_align_up(itc::img_bytes(c.hidden[0], D), 1024);
+    cur += pxr_align_up(itc::img_bytes(PXR_TC_H1, D), 1024);
   }
   h->tc_items_img[3] = nullptr; h->tc_gate_bias = nullptr;
   if (gated) {
-    if (concat) cur += pxr_align_up(itc::img_bytes(c.hidden[0], FD), 1024);
+    if (concat) cur += pxr_align_up(itc::img_bytes(PXR_TC_H1, FD), 1024);
     h->tc_items_img[3] = cur;
     itc::split_weights_kernel<<<64, 256, 0, st>>>(h->gate.w, (int64_t)h->M * D, D, 16, FD, 16, cur, h->M);
     h->launches++;
@@ -446,9 +446,9 @@ int pxr_launch_item_q_tc(pxr_handle* h, int64_t n_rows, uint16_t* out, int fmt16
   const int D = c.embedding_dim;
   itc::GemmParams gp;
   memset(&gp, 0, sizeof(gp));
-  gp.A = h->item_feats; gp.lda = D; gp.M = n_rows * (h->M - 1); gp.K = D; gp.N = c.hidden[0]; gp.NT = 256;
-  gp.wimg = h->tc_items_img[2]; gp.bias = h->mlp[0].b;
-  gp.mode = itc::OUT_16; gp.fmt16 = fmt16; gp.out_h = out; gp.ldo = c.hidden[0]; gp.qt_nm = h->M - 1;
+  gp.A = h->item_feats; gp.lda = D; gp.M = n_rows * (h->M - 1); gp.K = D; gp.N = PXR_TC_H1; gp.NT = 256;
+  gp.wimg = h->tc_items_img[2]; gp.bias = pxr_tc_b1_padded(h);
+  gp.mode = itc::OUT_16; gp.fmt16 = fmt16; gp.out_h = out; gp.ldo = PXR_TC_H1; gp.qt_nm = h->M - 1;
   return itc::launch_gemm(h, gp, st);
 }
 
@@ -497,8 +497,8 @@ int pxr_launch_item_pi_tc(pxr_handle* h, int64_t n_rows, uint16_t* out, int fmt1
   const int D = c.embedding_dim, FD = (h->M - 1) * D;
   itc::GemmParams gp;
   memset(&gp, 0, sizeof(gp));
-  gp.A = h->item_feats; gp.lda = FD; gp.M = n_rows; gp.K = FD; gp.N = c.hidden[0]; gp.NT = 256;
-  gp.wimg = h->tc_items_img[2]; gp.bias = h->mlp[0].b;
-  gp.mode = itc::OUT_16; gp.fmt16 = fmt16; gp.out_h = out; gp.ldo = c.hidden[0];
+  gp.A = h->item_feats; gp.lda = FD; gp.M = n_rows; gp.K = FD; gp.N = PXR_TC_H1; gp.NT = 256;
+  gp.wimg = h->tc_items_img[2]; gp.bias = pxr_tc_b1_padded(h);
+  gp.mode = itc::OUT_16; gp.fmt16 = fmt16; gp.out_h = out; gp.ldo = PXR_TC_H1;
   return itc::launch_gemm(h, gp, st);
 }

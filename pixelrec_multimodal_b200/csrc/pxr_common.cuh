@@ -244,6 +244,9 @@ int pxr_launch_metrics(const int32_t* topk_idx, int32_t k_stride, int64_t n_user
 // tcgen05 path (score_tc.cu)
 bool pxr_tc_supported(const pxr_handle* h);
 const char* pxr_tc_unsupported_reason(const pxr_handle* h);   // NULL = supported
+#define PXR_TC_H1 512      // columns of the fused kernel's first hidden layer (layer-1 partials are padded to it)
+const float* pxr_tc_w1t_padded(const pxr_handle* h);   // concat / wide gated: W1^T as [k][512], zero-padded columns
+const float* pxr_tc_b1_padded(const pxr_handle* h);    // b1 zero-padded to 512
 bool pxr_tc_gated_wide(const pxr_handle* h);   // gated fusion at embedding_dim != 64: gate-weighted layer-1 partials (F_GATEDW)
 #define PXR_TC_MAX_K 1024   // 16 pages of the fused kernel's 64-slot lists
 bool pxr_tc_can_run(const pxr_handle* h, int32_t k);   // this call (k, shard size) fits the kernel's limits

@@ -1524,6 +1524,14 @@ __global__ void build_wimg_kernel(const float* __restrict__ w1, int k1, const fl
   }
 }
 
+// concat / wide gated: W1^T [k][n1] -> [k][512], columns past n1 zero
+__global__ void pad_w1t_kernel(const float* __restrict__ wt, int k1, int n1, float* __restrict__ out) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)k1 * H1) return;
+  const int n = (int)(e % H1); const size_t k = e / H1;
+  out[e] = n < n1 ? wt[k * n1 + n] : 0.f;
+}
+
 // gated: item part of the gate logits: Wg[:, D:] . concat(item-side vectors) + bg   (layers.py:207 split)
 __global__ void item_logit_kernel(const float* __restrict__ feats, const float* __restrict__ gate_w,
                                   const float* __restrict__ gate_b, int M, int Dm, int64_t n_rows, float* __restrict__ out) {
@@ -1863,8 +1871,7 @@ const char* pxr_tc_unsupported_reason(const pxr_handle* h) {
   if (c.n_hidden != 3) return "the prediction MLP does not have three hidden layers";
   if (c.hidden[0] > tc::H1 || c.hidden[1] > tc::H2 || c.hidden[2] > tc::H3)
     return "fusion_hidden_dims exceeds [512, 256, 128] (the three weight matrices are resident in the CTA pair's shared memory)";
-  // smaller hidden layers run zero-padded to [512, 256, 128]; concat feeds layer-1 partials of exactly 512 columns
-  if (c.fusion == PXR_FUSION_CONCAT && c.hidden[0] != tc::H1) return "concat fusion with fusion_hidden_dims[0] != 512";
+  // smaller hidden layers run zero-padded to [512, 256, 128] (concat / wide gated: the layer-1 partials are padded to 512 columns)
   if (c.activation != PXR_ACT_RELU && c.precision == PXR_PRECISION_FP16) return "fp16 operands with a fusion_activation other than relu (only the relu kernels are built for fp16)";
   if (h->M < 4 || h->M > 6) return "fewer than 4 modalities";
   if (c.fusion == PXR_FUSION_ATTENTION && c.num_heads != tc::NH) return "attention fusion with num_attention_heads != 4";
@@ -1872,8 +1879,6 @@ const char* pxr_tc_unsupported_reason(const pxr_handle* h) {
   // concat, and gated at embedding_dim != 64 (F_GATEDW): layer 1 is applied as per-user / per-item partials, so the fused
   // kernel does not depend on embedding_dim (item side: 3xTF32 GEMMs of items_tc.cu, which need single-layer projections
   // and 16-byte aligned rows)
-  if (c.fusion == PXR_FUSION_GATED && c.embedding_dim != tc::D && c.hidden[0] != tc::H1)
-    return "gated fusion with embedding_dim != 64 and fusion_hidden_dims[0] != 512 (layer 1 runs as 512-column partials)";
   if (c.fusion != PXR_FUSION_ATTENTION && c.embedding_dim != tc::D &&
       !(c.embedding_dim % 16 == 0 && c.embedding_dim <= 512 && c.projection_hidden == 0 && c.vision_dim % 4 == 0 &&
         c.language_dim % 4 == 0 && c.num_numerical <= 32))
@@ -1884,6 +1889,15 @@ const char* pxr_tc_unsupported_reason(const pxr_handle* h) {
 // gated fusion at embedding_dim != 64: the F_GATEDW front end (gate-weighted layer-1 partials on the concat pipeline)
 bool pxr_tc_gated_wide(const pxr_handle* h) { return h->cfg.fusion == PXR_FUSION_GATED && h->cfg.embedding_dim != tc::D; }
 
+// concat / wide gated: layer 1 is applied as partials of exactly 512 columns, so a smaller first hidden layer runs on a
+// zero-padded copy of W1^T ([k][512], the rows of h->mlp[0].wt padded with zeros) and the zero-padded b1 of the bias block
+static bool tc_l1_partials(const pxr_handle* h) { return h->cfg.fusion == PXR_FUSION_CONCAT || pxr_tc_gated_wide(h); }
+static size_t tc_w1t_pad_bytes(const pxr_handle* h) {
+  if (!tc_l1_partials(h)) return 0;
+  const int k1 = (h->cfg.fusion == PXR_FUSION_CONCAT ? h->M : 1) * h->cfg.embedding_dim;
+  return pxr_align_up((size_t)k1 * tc::H1 * sizeof(float), 256);
+}
+
 bool pxr_tc_supported(const pxr_handle* h) { return pxr_tc_unsupported_reason(h) == nullptr; }
 
 bool pxr_tc_can_run(const pxr_handle* h, int32_t k) {
@@ -1891,9 +1905,15 @@ bool pxr_tc_can_run(const pxr_handle* h, int32_t k) {
 }
 
 size_t pxr_tc_weight_bytes(const pxr_handle* h) {
-  return pxr_align_up(sizeof(tc::FastWeights), 256) +
+  return pxr_align_up(sizeof(tc::FastWeights), 256) + tc_w1t_pad_bytes(h) +
          (h->cfg.fusion == PXR_FUSION_ATTENTION ? (size_t)h->n_sm * tc::ATT_XC0_U4 * sizeof(uint4) : 0);
 }
+
+// [k][512] zero-padded W1^T (concat / wide gated; lives behind FastWeights in h->fast_w) and the zero-padded b1
+const float* pxr_tc_w1t_padded(const pxr_handle* h) {
+  return reinterpret_cast<const float*>((const char*)h->fast_w + pxr_align_up(sizeof(tc::FastWeights), 256));
+}
+const float* pxr_tc_b1_padded(const pxr_handle* h) { return reinterpret_cast<const tc::FastWeights*>(h->fast_w)->bias; }
 
 static int tc_fmt(const pxr_handle* h) { return h->cfg.precision == PXR_PRECISION_FP16 ? tc::FMT_FP16 : tc::FMT_BF16; }
 
@@ -1911,6 +1931,12 @@ int pxr_tc_prepare_weights(pxr_handle* h, cudaStream_t st) {
     h->launches += 2;
   } else {
     PXR_CUDA(h, cudaMemcpyAsync(b, h->mlp[0].b, sizeof(float) * n1, cudaMemcpyDeviceToDevice, st));
+  }
+  if (tc_l1_partials(h)) {
+    const int k1 = h->mlp[0].k;
+    float* wp = const_cast<float*>(pxr_tc_w1t_padded(h));
+    tc::pad_w1t_kernel<<<(unsigned)(((size_t)k1 * tc::H1 + 255) / 256), 256, 0, st>>>(h->mlp[0].wt, k1, n1, wp);
+    h->launches++;
   }
   tc::build_wimg_kernel<<<296, 256, 0, st>>>(gated ? h->mlp[0].w : nullptr, h->mlp[0].k, attn ? fw->s1 : nullptr, h->mlp[1].w,
                                              h->mlp[2].w, fw->wimg, gated ? 1 : 0, tc_fmt(h), n1, n2, n3);
@@ -1962,7 +1988,7 @@ int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t s
       h->tc_attr_set |= (1ull << 63);
     }
     const int64_t nv = n_rows * (h->M - 1);
-    tc::item_pi_kernel<<<(unsigned)((nv + 31) / 32), PXR_SIMT_THREADS, smem, st>>>(h->item_feats, h->mlp[0].wt, h->mlp[0].b, Dm, nv, q, tc::GW_HALF2 ? tc::FMT_FP16 : tc_fmt(h), h->M - 1);
+    tc::item_pi_kernel<<<(unsigned)((nv + 31) / 32), PXR_SIMT_THREADS, smem, st>>>(h->item_feats, pxr_tc_w1t_padded(h), pxr_tc_b1_padded(h), Dm, nv, q, tc::GW_HALF2 ? tc::FMT_FP16 : tc_fmt(h), h->M - 1);
   } else if (h->cfg.fusion == PXR_FUSION_GATED && h->tc_items_img[3] && h->path == PXR_PATH_TCGEN05) {
     return pxr_launch_item_logit_tc(h, n_rows, (float*)ws, st);                  // 3xTF32 GEMM on the tensor pipe (N = 6 padded to 16)
   } else if (h->cfg.fusion == PXR_FUSION_GATED) {
@@ -1983,8 +2009,8 @@ int pxr_tc_prepare_items(pxr_handle* h, int64_t n_rows, void* ws, cudaStream_t s
       PXR_CUDA(h, cudaFuncSetAttribute(tc::item_pi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       h->tc_attr_set |= (1ull << 63);
     }
-    tc::item_pi_kernel<<<(unsigned)((n_rows + 31) / 32), PXR_SIMT_THREADS, smem, st>>>(h->item_feats, h->mlp[0].wt + (size_t)h->cfg.embedding_dim * tc::H1,
-                                                                                       h->mlp[0].b, FD, n_rows, (uint16_t*)ws, tc_fmt(h), 0);
+    tc::item_pi_kernel<<<(unsigned)((n_rows + 31) / 32), PXR_SIMT_THREADS, smem, st>>>(h->item_feats, pxr_tc_w1t_padded(h) + (size_t)h->cfg.embedding_dim * tc::H1,
+                                                                                       pxr_tc_b1_padded(h), FD, n_rows, (uint16_t*)ws, tc_fmt(h), 0);
   }
   h->launches++;
   PXR_CUDA(h, cudaGetLastError());
@@ -2114,7 +2140,7 @@ int pxr_tc_score_topk(pxr_handle* h, const float* user_embedding, const int64_t*
     p.ln_w = h->ln_w; p.ln_b = h->ln_b;
     memcpy(p.bias_c, h->tc_bias_host, sizeof(float) * (tc::H1 + tc::H2 + 2 * tc::H3 + 1));
   }
-  p.w1u_t = h->mlp[0].wt;                   // [k][512]: rows 0..63 are the user columns of W1
+  p.w1u_t = tc_l1_partials(h) ? pxr_tc_w1t_padded(h) : h->mlp[0].wt;     // [k][512] (zero-padded columns): rows 0..D-1 are the user columns of W1
   p.user_emb = user_embedding; p.user_idx = user_idx; p.seen_indptr = seen_indptr; p.seen_idx = seen_idx;
   p.item_missing = h->item_missing;
   p.n_users = n_users; p.n_rows = h->n_rows; p.item_base = h->item_base;

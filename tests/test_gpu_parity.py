@@ -624,14 +624,15 @@ def test_tcgen05_matches_emulated_and_exact_oracle(fusion, dtype, n_users, n_ite
           f"{same_ref}/{total} to the exact oracle; max|emu-exact| = {np.max(np.abs(emu - ref)):.2e}")
 
 
-@pytest.mark.parametrize("fusion,hidden", [("gated", [256, 128, 64]), ("attention", [384, 200, 100]), ("gated", [512, 256, 32]),
-                                           ("concatenate", [512, 128, 64])])
-def test_tcgen05_smaller_mlp_zero_padded(fusion, hidden):
+@pytest.mark.parametrize("fusion,hidden,D", [("gated", [256, 128, 64], 64), ("attention", [384, 200, 100], 64), ("gated", [512, 256, 32], 64),
+                                             ("concatenate", [512, 128, 64], 64), ("concatenate", [256, 128, 64], 64),
+                                             ("concatenate", [320, 200, 100], 128), ("gated", [256, 128, 64], 128)])
+def test_tcgen05_smaller_mlp_zero_padded(fusion, hidden, D):
     """Prediction MLPs smaller than the kernel's resident [512, 256, 128] run on the fused path zero-padded (a padded unit
     has weight 0 and bias 0, relu(0) = 0: exact): kernel == the emulated oracle of the UNPADDED model, exact mode == the
     fp32 oracle."""
     n_users, n_items, k = 40, 900, 50
-    spec = syn.ModelSpec(n_users=n_users, n_items=n_items, fusion_type=fusion, fusion_hidden_dims=hidden)
+    spec = syn.ModelSpec(n_users=n_users, n_items=n_items, fusion_type=fusion, fusion_hidden_dims=hidden, embedding_dim=D)
     sd = syn.make_state_dict(spec, seed=syn.SEED + 27)
     feats = syn.make_item_features(spec, seed=syn.SEED + 27)
     syn.condition_like_trained(sd, spec, feats)
