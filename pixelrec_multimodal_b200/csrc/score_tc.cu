@@ -292,7 +292,7 @@ __host__ __device__ constexpr uint32_t q_item_bytes(int nm) { return (uint32_t)n
 __host__ __device__ constexpr uint32_t q_stage_bytes(int nm) { return 16u * q_item_bytes(nm); }       // one chunk of one 16-item tile
 // PXR_GW_HALF2 (default): the item partials are stored in fp16 (11-bit significand, saturating convert) whatever the MMA
 // operand format, and their gate-weighted sum runs on packed fp16 FMAs -- 5 HFMA2 per two columns instead of 10 unpack + 10
-// FFMA: the producers are issue-bound (1.90 -> see DESIGN K3w).  The fp16 sum carries <= 5 roundings of 2^-11 relative, a
+// FFMA: the producers are issue-bound (1.90 -> 2.51 G pairs/s, DESIGN K3w).  The fp16 sum carries <= 5 roundings of 2^-11 relative, a
 // fifth of the 16-bit rounding of the activation that follows; the user term g_0 Pu stays fp32.
 #ifndef PXR_GW_HALF2
 #define PXR_GW_HALF2 1
