@@ -276,9 +276,13 @@ def make_parser() -> argparse.ArgumentParser:
 
     def common(p):
         p.add_argument("--config", type=str, default=None, help="reference-style YAML (model / recommendation sections)")
-        p.add_argument("--checkpoint", type=str, default=None, help="reference checkpoint (.pth with model_state_dict)")
+        p.add_argument("--checkpoint", type=str, default=None,
+                       help="reference checkpoint (.pth with model_state_dict), or the directory holding it (then --checkpoint_name, "
+                            "falling back to final_model.pth / last_model.pth like scripts/evaluate.py:76-90)")
+        p.add_argument("--checkpoint_name", type=str, default="best_model.pth", help="scripts/evaluate.py:250")
         p.add_argument("--cache", type=str, required=True, help="packed feature cache directory (packed_cache.py)")
-        p.add_argument("--interactions", type=str, required=True, help="train interactions CSV (user_id, item_id): histories / encoders")
+        p.add_argument("--interactions", "--train_data", dest="interactions", type=str, required=True,
+                       help="train interactions CSV (user_id, item_id): histories / encoders (--train_data: the name scripts/evaluate.py uses)")
         p.add_argument("--encoders", type=str, default=None,
                        help="directory with the training-time user_encoder.pkl / item_encoder.pkl (default: searched next to the "
                             "checkpoint like scripts/evaluate.py; rebuilt from the tables only when none exist)")
@@ -292,6 +296,9 @@ def make_parser() -> argparse.ArgumentParser:
     g.add_argument("--sample_users", type=int)
     g.add_argument("--all_users", action="store_true", help="every user of the interaction table (batched API)")
     g.add_argument("--no_filter_seen", action="store_true")
+    g.add_argument("--use_diversity", action="store_true",
+                   help="accepted like scripts/generate_recommendations.py:252; the reference Recommender has no diversity-aware method, "
+                        "so (as there, :206-212) a warning is printed and the standard lists are produced")
     g.add_argument("--output", type=str, default="recommendations.json")
     g.set_defaults(fn=cmd_generate)
 
@@ -300,8 +307,17 @@ def make_parser() -> argparse.ArgumentParser:
     e.add_argument("--test_data", type=str, required=True)
     e.add_argument("--eval_task", type=str, default="retrieval", choices=["retrieval", "ranking"],
                    help="retrieval: top-K lists against the test positives; ranking: order of each user's own test items (tasks.py:776-901)")
-    e.add_argument("--use_sampling", action="store_true", help="positives + sampled negatives (the reference default protocol)")
-    e.add_argument("--num_negatives", type=int, default=100)
+    e.add_argument("--use_sampling", action="store_true", help="positives + sampled negatives (the reference script's default protocol; "
+                                                               "here the full catalogue is the default -- it is what this path is for)")
+    e.add_argument("--no_sampling", dest="use_sampling", action="store_false", help="scripts/evaluate.py:247 (the default here)")
+    e.add_argument("--num_negatives", type=int, default=100, help="negatives per user (scripts/evaluate.py:248 defaults to 20)")
+    e.add_argument("--recommender_type", type=str, default="multimodal",
+                   help="scripts/evaluate.py:239-241; only the multimodal recommender lives on this path (the baselines stay in the reference)")
+    e.add_argument("--num_workers", type=int, default=1,
+                   help="accepted for compatibility (scripts/evaluate.py:245); the evaluation is one batched GPU pass, forked workers "
+                        "cannot share a CUDA context: values > 1 are ignored with a warning")
+    e.add_argument("--warmup_recommender_cache", action="store_true",
+                   help="accepted for compatibility (scripts/evaluate.py:244); the item records are resident after the one precompute")
     e.add_argument("--sampling_strategy", type=str, default="random", choices=["random", "popularity", "popularity_inverse"],
                    help="how the negatives are drawn (evaluate.py / tasks.py:221-308)")
     e.add_argument("--seed", type=int, default=20261018)
@@ -313,8 +329,30 @@ def make_parser() -> argparse.ArgumentParser:
     return ap
 
 
+def resolve_compat(args):
+    """The reference scripts' flags that have no work to do on this path, and the checkpoint-directory form."""
+    import logging
+    if getattr(args, "recommender_type", "multimodal") not in ("multimodal", "fast_multimodal"):
+        raise SystemExit(f"--recommender_type {args.recommender_type}: only the multimodal recommender runs on the GPU path "
+                         "(random / popularity / item_knn / user_knn baselines: use the reference's scripts/evaluate.py)")
+    if getattr(args, "num_workers", 1) > 1:
+        logging.warning("--num_workers %d ignored: the evaluation is one batched pass on the GPU (no forked workers)", args.num_workers)
+        args.num_workers = 1
+    if getattr(args, "use_diversity", False):
+        print("Warning: Diversity method not implemented. Falling back to standard recommendations.")
+    if args.checkpoint and Path(args.checkpoint).is_dir():
+        d = Path(args.checkpoint)
+        for name in [args.checkpoint_name, "best_model.pth", "final_model.pth", "last_model.pth"]:
+            if (d / name).is_file():
+                args.checkpoint = str(d / name)
+                break
+        else:
+            raise SystemExit(f"no checkpoint ({args.checkpoint_name}, best_model.pth, final_model.pth, last_model.pth) in {d}")
+    return args
+
+
 def main(argv: Optional[Sequence[str]] = None):
-    args = make_parser().parse_args(argv)
+    args = resolve_compat(make_parser().parse_args(argv))
     return args.fn(args)
 
 

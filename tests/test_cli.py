@@ -25,6 +25,35 @@ def test_parser_mirrors_reference_flags():
         p.parse_args(["evaluate", "--cache", "c", "--interactions", "i.csv", "--test_data", "t.csv", "--eval_task", "other"])
 
 
+def test_parser_accepts_the_reference_scripts_command_lines(tmp_path, capsys):
+    """Every flag of scripts/evaluate.py:236-250 and scripts/generate_recommendations.py:248-254 parses; the ones without
+    work on this path are accepted and say so; a checkpoint directory resolves like find_model_checkpoint (evaluate.py:54-110)."""
+    p = cli.make_parser()
+    a = cli.resolve_compat(p.parse_args(["evaluate", "--cache", "c", "--train_data", "train.csv", "--test_data", "t.csv", "--no_sampling",
+                                         "--num_negatives", "20", "--sampling_strategy", "popularity", "--recommender_type", "multimodal",
+                                         "--num_workers", "4", "--warmup_recommender_cache", "--save_predictions", "p.json",
+                                         "--checkpoint_name", "final_model.pth", "--device", "cuda:0"]))
+    assert a.interactions == "train.csv" and a.use_sampling is False and a.num_negatives == 20 and a.num_workers == 1
+    assert a.sampling_strategy == "popularity" and a.warmup_recommender_cache and a.checkpoint is None
+    with pytest.raises(SystemExit):
+        cli.resolve_compat(p.parse_args(["evaluate", "--cache", "c", "--interactions", "i.csv", "--test_data", "t.csv",
+                                         "--recommender_type", "item_knn"]))
+    g = cli.resolve_compat(p.parse_args(["generate", "--cache", "c", "--interactions", "i.csv", "--sample_users", "3", "--use_diversity"]))
+    assert g.use_diversity and "Diversity method not implemented" in capsys.readouterr().out     # generate_recommendations.py:206-208
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    (d / "last_model.pth").write_bytes(b"x")
+    a = cli.resolve_compat(p.parse_args(["evaluate", "--cache", "c", "--interactions", "i.csv", "--test_data", "t.csv", "--checkpoint", str(d)]))
+    assert a.checkpoint == str(d / "last_model.pth")
+    (d / "final_model.pth").write_bytes(b"x")
+    a = cli.resolve_compat(p.parse_args(["evaluate", "--cache", "c", "--interactions", "i.csv", "--test_data", "t.csv", "--checkpoint", str(d),
+                                         "--checkpoint_name", "final_model.pth"]))
+    assert a.checkpoint == str(d / "final_model.pth")
+    with pytest.raises(SystemExit):
+        cli.resolve_compat(p.parse_args(["evaluate", "--cache", "c", "--interactions", "i.csv", "--test_data", "t.csv",
+                                         "--checkpoint", str(tmp_path)]))
+
+
 def test_config_defaults_and_yaml(tmp_path):
     c = cli.load_config(None)
     assert c["model"]["fusion_hidden_dims"] == [512, 256, 128] and c["recommendation"]["top_k"] == 50 and c["results_dir"] == "results"
